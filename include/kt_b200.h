@@ -1,0 +1,250 @@
+/*
+ * kt_b200.h -- C ABI of the B200-native throttle-admission engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of everpeace/kube-throttler:
+ * the per-pod PreFilter/Reserve check (pkg/scheduler_plugin/plugin.go:148-238) plus
+ * the controllers' used-resource reconcile (pkg/controllers/throttle_controller.go:84-269,
+ * 349-397; clusterthrottle_controller.go:87-298, 378-425) recast as one batched pass.
+ *
+ * The reference has NO FFI (Makefile:3 sets CGO_ENABLED=0), so every entry point below
+ * is new; each one names the reference Go code it replaces.  The Go plugin would bind
+ * these through cgo (see INTEGRATION.md for the stub).  Plain pointers and sizes only;
+ * no C++/torch types.  All functions return KT_OK (0) or a negative kt_status; the
+ * message is available from kt_last_error().  The caller owns every host buffer; the
+ * library owns all device memory.  Re-entrant from arbitrary OS threads (cgo calls hop
+ * threads): every call takes the context mutex and does cudaSetDevice itself.
+ *
+ * There is deliberately NO CPU fallback: on a machine without a usable sm_100 GPU
+ * kt_create() fails with KT_ERR_CUDA.
+ *
+ * Data model (all integers; exact decimal arithmetic is the packer's job, see
+ * include/kt_host.h and DESIGN.md "Quantity columns"):
+ *   - label keys / values are dictionary ids chosen by the packer (uint32 each);
+ *     a label slot is int64  (keyId << 32) | valId ;  KT_LABEL_EMPTY marks an unused slot.
+ *   - resource.Quantity values are int64 at a per-resource-column scale chosen by the
+ *     packer (default 10^-3); presence (Go map "has key") is a bitmask per row.
+ *   - matrices are column-major by attribute ("SoA"): labels[L][n], req[R][n], thr[R][m].
+ */
+#ifndef KT_B200_H_
+#define KT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KT_ABI_VERSION 1
+#define KT_MAX_RESOURCES 31      /* bit 31 of every resource mask is the pod-count bit */
+#define KT_COUNT_BIT 0x80000000u
+#define KT_MAX_LABEL_SLOTS 32
+#define KT_LABEL_EMPTY ((int64_t)-1)
+#define KT_TIME_OPEN_BEGIN INT64_MIN /* override.begin == ""  (temporary_threshold_override.go:33-44) */
+#define KT_TIME_OPEN_END INT64_MAX   /* override.end == "" or zero time (:64-69) */
+
+typedef enum kt_status {
+  KT_OK = 0,
+  KT_ERR_INVALID = -1, /* bad argument / inconsistent columns */
+  KT_ERR_CUDA = -2,    /* CUDA runtime error (no device, launch failure, ...) */
+  KT_ERR_STATE = -3,   /* call order: e.g. evaluate before upload */
+  KT_ERR_LIMIT = -4,   /* exceeds kt_limits */
+  KT_ERR_NCCL = -5
+} kt_status;
+
+typedef enum kt_pod_kind {
+  KT_PODS_RUNNING = 0, /* rows the reconcile sums over (podInformer cache) */
+  KT_PODS_PENDING = 1  /* rows PreFilter is asked about (scheduling queue) */
+} kt_pod_kind;
+
+/* pod row flags -- pkg/controllers/throttle_controller.go:217-219, pod_util.go:22-28 */
+#define KT_POD_SCHEDULER_MATCH 1u /* spec.schedulerName == targetSchedulerName */
+#define KT_POD_SCHEDULED 2u       /* spec.nodeName != ""            (isScheduled) */
+#define KT_POD_NOT_FINISHED 4u    /* phase not in {Succeeded,Failed} (isNotFinished) */
+
+/* throttle flags */
+#define KT_THR_RESPONSIBLE 1u    /* spec.throttlerName == ours (throttle_controller.go:213-215) */
+#define KT_THR_SELECTOR_ERROR 2u /* pod selector failed metav1.LabelSelectorAsSelector; never matches
+                                    on device, the host turns it into framework.Error (plugin.go:154) */
+#define KT_KIND_THROTTLE 0
+#define KT_KIND_CLUSTERTHROTTLE 1
+
+/* selector requirement operators (metav1.LabelSelectorRequirement; matchLabels k=v is IN{v}) */
+#define KT_OP_IN 0
+#define KT_OP_NOTIN 1
+#define KT_OP_EXISTS 2
+#define KT_OP_DOESNOTEXIST 3
+
+/* term flags */
+#define KT_TERM_NS_INVALID 1u /* namespaceSelector conversion error => term is false (Q9,
+                                 clusterthrottle_selector.go:63-77) */
+
+/* override flags */
+#define KT_OVR_PARSE_ERROR 1u /* begin/end failed time.Parse: entry skipped (throttle_types.go:80-84) */
+
+/* CheckThrottleStatus codes, 2 bits each (throttle_types.go:121-126) */
+#define KT_CHECK_NOT_THROTTLED 0u /* also "throttle does not affect this pod" (see match bitmap) */
+#define KT_CHECK_ACTIVE 1u
+#define KT_CHECK_INSUFFICIENT 2u
+#define KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD 3u
+
+/* kt_evaluate flags */
+#define KT_EVAL_FRESH_STATUS 0u  /* status.{used,throttled,calculatedThreshold} come from this pass's
+                                    reconcile (every throttle reconciled at `now`) */
+#define KT_EVAL_GIVEN_STATUS 1u  /* PreFilter sees the informer copy of status uploaded with
+                                    kt_upload_status (throttle_types.go:128-132) */
+#define KT_EVAL_ON_EQUAL 2u      /* isThrottledOnEqual argument of CheckThrottled (PreFilter passes false) */
+#define KT_EVAL_SKIP_RECONCILE 4u /* only the pending check (needs GIVEN_STATUS) */
+#define KT_EVAL_SKIP_CHECK 8u    /* only the reconcile */
+
+typedef struct kt_ctx kt_ctx;
+
+typedef struct kt_limits {
+  int32_t abi_version;     /* KT_ABI_VERSION */
+  int32_t n_resources;     /* R: resource columns, 1..KT_MAX_RESOURCES */
+  int32_t label_slots;     /* L: label slots per pod row, 1..KT_MAX_LABEL_SLOTS */
+  int32_t ns_label_slots;  /* label slots per namespace row */
+} kt_limits;
+
+/* Selector table: CSR over throttles -> terms -> requirements -> values.
+ * Replaces metav1.LabelSelectorAsSelector + labels.Selector.Matches as called from
+ * v1alpha1/throttle_selector.go:30-54 and clusterthrottle_selector.go:30-87. */
+typedef struct kt_selector_table {
+  int32_t n_terms;
+  int32_t n_reqs;
+  int32_t n_vals;
+  const int32_t* term_off;    /* [m+1]      throttle -> terms (0 terms => matches nothing) */
+  const uint8_t* term_flags;  /* [n_terms]  KT_TERM_* */
+  const int32_t* pod_req_off; /* [n_terms+1] term -> podSelector requirements (none => Everything) */
+  const int32_t* ns_req_off;  /* [n_terms+1] term -> namespaceSelector requirements (ClusterThrottle) */
+  const uint32_t* req_key;    /* [n_reqs] keyId */
+  const uint8_t* req_op;      /* [n_reqs] KT_OP_* */
+  const int32_t* req_val_off; /* [n_reqs+1] */
+  const uint32_t* req_vals;   /* [n_vals] valIds */
+} kt_selector_table;
+
+/* Throttle / ClusterThrottle spec columns (v1alpha1/throttle_types.go:29-36,
+ * temporary_threshold_override.go:25-31). */
+typedef struct kt_throttle_cols {
+  const uint8_t* kind;            /* [m] KT_KIND_* */
+  const int32_t* ns_id;           /* [m] namespace id (Throttle); ignored for ClusterThrottle */
+  const uint8_t* flags;           /* [m] KT_THR_* */
+  const int64_t* thr;             /* [R][m] spec.threshold.resourceRequests */
+  const uint32_t* thr_present;    /* [m]    bit r: threshold has resource r; KT_COUNT_BIT: resourceCounts != nil */
+  const int64_t* thr_cnt;         /* [m]    spec.threshold.resourceCounts.pod */
+  const int32_t* ovr_off;         /* [m+1]  CSR into temporaryThresholdOverrides (in spec order) */
+  int32_t n_ovr;
+  const int64_t* ovr_begin;       /* [n_ovr] unix ns, KT_TIME_OPEN_BEGIN if empty */
+  const int64_t* ovr_end;         /* [n_ovr] unix ns, KT_TIME_OPEN_END if empty */
+  const uint8_t* ovr_flags;       /* [n_ovr] KT_OVR_* */
+  const int64_t* ovr_thr;         /* [R][n_ovr] */
+  const uint32_t* ovr_present;    /* [n_ovr] as thr_present */
+  const int64_t* ovr_cnt;         /* [n_ovr] */
+} kt_throttle_cols;
+
+/* Observed status columns for KT_EVAL_GIVEN_STATUS (v1alpha1/throttle_types.go:113-117). */
+typedef struct kt_status_cols {
+  const uint8_t* calculated;       /* [m] status.calculatedThreshold.calculatedAt != zero time */
+  const int64_t* calc_thr;         /* [R][m] status.calculatedThreshold.threshold */
+  const uint32_t* calc_present;    /* [m] */
+  const int64_t* calc_cnt;         /* [m] */
+  const int64_t* used;             /* [R][m] status.used.resourceRequests */
+  const uint32_t* used_present;    /* [m] bit r; KT_COUNT_BIT: status.used.resourceCounts != nil */
+  const int64_t* used_cnt;         /* [m] */
+  const uint32_t* throttled;       /* [m] bit r: status.throttled.resourceRequests[r]==true; KT_COUNT_BIT: .resourceCounts.pod */
+} kt_status_cols;
+
+/* Per-throttle results of the reconcile half (what UpdateStatus would write,
+ * throttle_controller.go:116-133).  Any pointer may be NULL to skip that column. */
+typedef struct kt_reconcile_out {
+  int64_t* used;            /* [R][m] */
+  uint32_t* used_present;   /* [m] bit r: some counted pod has the key; KT_COUNT_BIT: >=1 pod counted */
+  int64_t* used_cnt;        /* [m] */
+  uint32_t* throttled;      /* [m] threshold.IsThrottled(used, true): bit r / KT_COUNT_BIT */
+  int64_t* calc_thr;        /* [R][m] CalculateThreshold(now).threshold */
+  uint32_t* calc_present;   /* [m] */
+  int64_t* calc_cnt;        /* [m] */
+  uint8_t* override_active; /* [m] 1 if >=1 override active at `now` */
+} kt_reconcile_out;
+
+typedef struct kt_timing {
+  float reconcile_ms;   /* match-running + segmented sums */
+  float allreduce_ms;   /* NCCL all-reduce of the partials (0 when single GPU) */
+  float finalize_ms;    /* threshold/override/compare per throttle */
+  float check_ms;       /* match-pending + 4-step check */
+  float total_ms;       /* first launch -> last kernel end (device clock) */
+  int32_t launches;     /* kernels of this library launched by the last kt_evaluate */
+} kt_timing;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+/* Replaces the controller construction in NewPlugin (plugin.go:100-113). */
+int kt_create(kt_ctx** out, int device, const kt_limits* limits);
+void kt_destroy(kt_ctx* ctx);
+const char* kt_last_error(const kt_ctx* ctx); /* valid until the next call on ctx */
+const char* kt_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the private stream. */
+int kt_set_stream(kt_ctx* ctx, void* cuda_stream);
+int kt_sync(kt_ctx* ctx);
+/* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost). */
+void* kt_host_alloc(size_t bytes);
+void kt_host_free(void* p);
+
+/* ---- snapshot upload (host -> HBM) --------------------------------------------- */
+/* Pod rows: replaces podInformer.Lister().Pods(ns).List() + ResourceAmountOfPod per pod
+ * (throttle_controller.go:221-246, resource_amount.go:71-76). Replaces the whole kind. */
+int kt_upload_pods(kt_ctx* ctx, int kind, int64_t n,
+                   const int64_t* labels /*[L][n]*/, const int64_t* req /*[R][n]*/,
+                   const uint32_t* present /*[n]*/, const uint32_t* flags /*[n]*/,
+                   const int32_t* ns_id /*[n]*/);
+/* Row-level delta (pod informer Add/Update/Delete, throttle_controller.go:431-532):
+ * columns are compact [L][k] / [R][k] / [k]; rows[i] < current n.  A deleted pod is a row
+ * with flags == 0 (never counted) and all label slots empty. */
+int kt_update_pod_rows(kt_ctx* ctx, int kind, int64_t k, const int64_t* rows,
+                       const int64_t* labels, const int64_t* req, const uint32_t* present,
+                       const uint32_t* flags, const int32_t* ns_id);
+/* Namespace rows (namespaceInformer, clusterthrottle_controller.go:224-247). */
+int kt_upload_namespaces(kt_ctx* ctx, int32_t n_ns, const int64_t* labels /*[LN][n_ns]*/);
+/* Throttle + ClusterThrottle specs; compiles the selectors into the bit-sliced match tables. */
+int kt_upload_throttles(kt_ctx* ctx, int32_t m, const kt_throttle_cols* cols,
+                        const kt_selector_table* sel);
+/* Informer copy of .status for KT_EVAL_GIVEN_STATUS. */
+int kt_upload_status(kt_ctx* ctx, const kt_status_cols* st);
+/* reservedResourceAmounts.reservedResourceAmount(nn) for every throttle
+ * (reserved_resource_amounts.go:113-126): sums, presence, pod count (KT_COUNT_BIT set
+ * in present[t] iff >=1 pod is reserved on t).  NULL pointers mean "nothing reserved". */
+int kt_set_reserved(kt_ctx* ctx, const int64_t* reserved /*[R][m]*/,
+                    const uint32_t* present /*[m]*/, const int64_t* cnt /*[m]*/);
+
+/* ---- the pass ------------------------------------------------------------------- */
+/* One batched pass: reconcile every throttle (throttle_controller.go:84-133) and check
+ * every pending pod against every throttle (CheckThrottled, :349-397).  Asynchronous on
+ * the context stream unless a getter is called; kt_sync() waits. */
+int kt_evaluate(kt_ctx* ctx, int64_t now_unix_ns, uint32_t flags);
+
+/* ---- results (HBM -> host) ------------------------------------------------------ */
+int kt_get_reconcile(kt_ctx* ctx, const kt_reconcile_out* out);
+/* words_per_row = kt_match_words(ctx); bitmap rows are pod-major: bit (t&31) of
+ * words[p*words_per_row + (t>>5)] == throttle t affects pod p.
+ * RUNNING: affectedPods relation (shouldCountIn && selector match, finished pods included);
+ * PENDING: affectedThrottles relation (responsible && namespace && selector match). */
+int32_t kt_match_words(const kt_ctx* ctx);
+int kt_get_match_bitmap(kt_ctx* ctx, int kind, uint32_t* words /*[n][words_per_row]*/);
+/* codes: 2 bits per (pending pod, throttle), pod-major, 16 codes per uint32:
+ *   code(p,t) = (codes[p*2*words_per_row + (t>>4)] >> (2*(t&15))) & 3
+ * admit[p] = 1 iff every affected throttle is KT_CHECK_NOT_THROTTLED (plugin.go:177-180).
+ * Either pointer may be NULL. */
+int kt_get_check(kt_ctx* ctx, uint32_t* codes /*[p][2*words_per_row]*/, uint8_t* admit /*[p]*/);
+int kt_get_timing(kt_ctx* ctx, kt_timing* out);
+
+/* ---- multi-GPU (row-sharded snapshot, one context per GPU) --------------------- */
+/* Each context holds a row shard of both pod kinds and a replica of the throttles; the
+ * only exchange is one int64 sum all-reduce of the per-throttle partials between the
+ * reconcile and finalize kernels.  uid is an ncclUniqueId (128 bytes) created on rank 0. */
+int kt_comm_unique_id(uint8_t uid[128]);
+int kt_comm_init(kt_ctx* ctx, const uint8_t uid[128], int nranks, int rank);
+int kt_comm_destroy(kt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KT_B200_H_ */

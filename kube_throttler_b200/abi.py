@@ -1,0 +1,288 @@
+"""ctypes mirror of include/kt_b200.h (the C ABI of the engine) plus the columnar Snapshot
+container that both the engine wrapper and the test-side oracle wrapper consume.
+
+Nothing here computes anything: it only describes memory.  Field order and types must match
+include/kt_b200.h exactly (tests/test_abi.py checks sizes against the compiled library).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+ABI_VERSION = 1
+MAX_RESOURCES = 31
+COUNT_BIT = 0x80000000
+MAX_LABEL_SLOTS = 32
+LABEL_EMPTY = -1
+TIME_OPEN_BEGIN = -(2**63)
+TIME_OPEN_END = 2**63 - 1
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_LIMIT, ERR_NCCL = 0, -1, -2, -3, -4, -5
+PODS_RUNNING, PODS_PENDING = 0, 1
+POD_SCHEDULER_MATCH, POD_SCHEDULED, POD_NOT_FINISHED = 1, 2, 4
+THR_RESPONSIBLE, THR_SELECTOR_ERROR = 1, 2
+KIND_THROTTLE, KIND_CLUSTERTHROTTLE = 0, 1
+OP_IN, OP_NOTIN, OP_EXISTS, OP_DOESNOTEXIST = 0, 1, 2, 3
+TERM_NS_INVALID = 1
+OVR_PARSE_ERROR = 1
+CHECK_NOT_THROTTLED, CHECK_ACTIVE, CHECK_INSUFFICIENT, CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD = 0, 1, 2, 3
+CHECK_NAMES = ("not-throttled", "active", "insufficient", "pod-requests-exceeds-threshold")
+EVAL_FRESH_STATUS, EVAL_GIVEN_STATUS, EVAL_ON_EQUAL, EVAL_SKIP_RECONCILE, EVAL_SKIP_CHECK = 0, 1, 2, 4, 8
+
+_p = C.POINTER
+
+
+class Limits(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_resources", C.c_int32), ("label_slots", C.c_int32),
+                ("ns_label_slots", C.c_int32)]
+
+
+class SelectorTable(C.Structure):
+    _fields_ = [("n_terms", C.c_int32), ("n_reqs", C.c_int32), ("n_vals", C.c_int32),
+                ("term_off", C.c_void_p), ("term_flags", C.c_void_p), ("pod_req_off", C.c_void_p),
+                ("ns_req_off", C.c_void_p), ("req_key", C.c_void_p), ("req_op", C.c_void_p),
+                ("req_val_off", C.c_void_p), ("req_vals", C.c_void_p)]
+
+
+class ThrottleCols(C.Structure):
+    _fields_ = [("kind", C.c_void_p), ("ns_id", C.c_void_p), ("flags", C.c_void_p), ("thr", C.c_void_p),
+                ("thr_present", C.c_void_p), ("thr_cnt", C.c_void_p), ("ovr_off", C.c_void_p),
+                ("n_ovr", C.c_int32), ("ovr_begin", C.c_void_p), ("ovr_end", C.c_void_p),
+                ("ovr_flags", C.c_void_p), ("ovr_thr", C.c_void_p), ("ovr_present", C.c_void_p),
+                ("ovr_cnt", C.c_void_p)]
+
+
+class StatusCols(C.Structure):
+    _fields_ = [("calculated", C.c_void_p), ("calc_thr", C.c_void_p), ("calc_present", C.c_void_p),
+                ("calc_cnt", C.c_void_p), ("used", C.c_void_p), ("used_present", C.c_void_p),
+                ("used_cnt", C.c_void_p), ("throttled", C.c_void_p)]
+
+
+class ReconcileOut(C.Structure):
+    _fields_ = [("used", C.c_void_p), ("used_present", C.c_void_p), ("used_cnt", C.c_void_p),
+                ("throttled", C.c_void_p), ("calc_thr", C.c_void_p), ("calc_present", C.c_void_p),
+                ("calc_cnt", C.c_void_p), ("override_active", C.c_void_p)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("reconcile_ms", C.c_float), ("allreduce_ms", C.c_float), ("finalize_ms", C.c_float),
+                ("check_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32)]
+
+
+def ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    """Raw address of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "columns must be C-contiguous"
+    return a.ctypes.data
+
+
+def _arr(x, dtype, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+@dataclass
+class PodCols:
+    """One pod kind: labels[L][n] int64, req[R][n] int64, present[n] u32, flags[n] u32, ns_id[n] i32."""
+    labels: np.ndarray
+    req: np.ndarray
+    present: np.ndarray
+    flags: np.ndarray
+    ns_id: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.present.shape[0])
+
+    def normalized(self, L: int, R: int) -> "PodCols":
+        n = self.n
+        return PodCols(_arr(self.labels, np.int64, (L, n)), _arr(self.req, np.int64, (R, n)),
+                       _arr(self.present, np.uint32, (n,)), _arr(self.flags, np.uint32, (n,)),
+                       _arr(self.ns_id, np.int32, (n,)))
+
+    def rows(self, sl) -> "PodCols":
+        return PodCols(np.ascontiguousarray(self.labels[:, sl]), np.ascontiguousarray(self.req[:, sl]),
+                       np.ascontiguousarray(self.present[sl]), np.ascontiguousarray(self.flags[sl]),
+                       np.ascontiguousarray(self.ns_id[sl]))
+
+
+@dataclass
+class Snapshot:
+    """Everything one pass consumes, as the int64/u32 columns of include/kt_b200.h."""
+    R: int
+    L: int
+    LN: int
+    running: PodCols
+    pending: PodCols
+    ns_labels: np.ndarray  # [LN][n_ns] int64
+    # throttles
+    kind: np.ndarray       # [m] u8
+    thr_ns: np.ndarray     # [m] i32
+    thr_flags: np.ndarray  # [m] u8
+    thr: np.ndarray        # [R][m] i64
+    thr_present: np.ndarray  # [m] u32
+    thr_cnt: np.ndarray    # [m] i64
+    ovr_off: np.ndarray    # [m+1] i32
+    ovr_begin: np.ndarray
+    ovr_end: np.ndarray
+    ovr_flags: np.ndarray
+    ovr_thr: np.ndarray    # [R][n_ovr]
+    ovr_present: np.ndarray
+    ovr_cnt: np.ndarray
+    # selector CSR
+    term_off: np.ndarray
+    term_flags: np.ndarray
+    pod_req_off: np.ndarray
+    ns_req_off: np.ndarray
+    req_key: np.ndarray
+    req_op: np.ndarray
+    req_val_off: np.ndarray
+    req_vals: np.ndarray
+    # reservation cache totals (optional)
+    reserved: Optional[np.ndarray] = None
+    reserved_present: Optional[np.ndarray] = None
+    reserved_cnt: Optional[np.ndarray] = None
+    # observed status for GIVEN_STATUS (optional dict of arrays named like kt_status_cols)
+    status: Optional[dict] = None
+    now: int = 0
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def m(self) -> int:
+        return int(self.kind.shape[0])
+
+    @property
+    def n_ns(self) -> int:
+        return int(self.ns_labels.shape[1])
+
+    def normalize(self) -> "Snapshot":
+        m, R = self.m, self.R
+        self.running = self.running.normalized(self.L, R)
+        self.pending = self.pending.normalized(self.L, R)
+        self.ns_labels = _arr(self.ns_labels, np.int64, (self.LN, -1))
+        self.kind = _arr(self.kind, np.uint8)
+        self.thr_ns = _arr(self.thr_ns, np.int32)
+        self.thr_flags = _arr(self.thr_flags, np.uint8)
+        self.thr = _arr(self.thr, np.int64, (R, m))
+        self.thr_present = _arr(self.thr_present, np.uint32)
+        self.thr_cnt = _arr(self.thr_cnt, np.int64)
+        self.ovr_off = _arr(self.ovr_off, np.int32)
+        n_ovr = int(self.ovr_off[-1])
+        self.ovr_begin = _arr(self.ovr_begin, np.int64)
+        self.ovr_end = _arr(self.ovr_end, np.int64)
+        self.ovr_flags = _arr(self.ovr_flags, np.uint8)
+        self.ovr_thr = _arr(self.ovr_thr, np.int64, (R, n_ovr))
+        self.ovr_present = _arr(self.ovr_present, np.uint32)
+        self.ovr_cnt = _arr(self.ovr_cnt, np.int64)
+        self.term_off = _arr(self.term_off, np.int32)
+        self.term_flags = _arr(self.term_flags, np.uint8)
+        self.pod_req_off = _arr(self.pod_req_off, np.int32)
+        self.ns_req_off = _arr(self.ns_req_off, np.int32)
+        self.req_key = _arr(self.req_key, np.uint32)
+        self.req_op = _arr(self.req_op, np.uint8)
+        self.req_val_off = _arr(self.req_val_off, np.int32)
+        self.req_vals = _arr(self.req_vals, np.uint32)
+        if self.reserved is not None:
+            self.reserved = _arr(self.reserved, np.int64, (R, m))
+            self.reserved_present = _arr(self.reserved_present, np.uint32)
+            self.reserved_cnt = _arr(self.reserved_cnt, np.int64)
+        if self.status is not None:
+            s = self.status
+            self.status = dict(
+                calculated=_arr(s["calculated"], np.uint8), calc_thr=_arr(s["calc_thr"], np.int64, (R, m)),
+                calc_present=_arr(s["calc_present"], np.uint32), calc_cnt=_arr(s["calc_cnt"], np.int64),
+                used=_arr(s["used"], np.int64, (R, m)), used_present=_arr(s["used_present"], np.uint32),
+                used_cnt=_arr(s["used_cnt"], np.int64), throttled=_arr(s["throttled"], np.uint32))
+        return self
+
+    # ---- ctypes views (the returned structs borrow the numpy memory: keep `self` alive) ----
+    def limits(self) -> Limits:
+        return Limits(ABI_VERSION, self.R, self.L, self.LN)
+
+    def selector_table(self) -> SelectorTable:
+        return SelectorTable(int(self.term_off[-1]), int(self.req_key.shape[0]), int(self.req_vals.shape[0]),
+                             ptr(self.term_off), ptr(self.term_flags), ptr(self.pod_req_off), ptr(self.ns_req_off),
+                             ptr(self.req_key), ptr(self.req_op), ptr(self.req_val_off), ptr(self.req_vals))
+
+    def throttle_cols(self) -> ThrottleCols:
+        return ThrottleCols(ptr(self.kind), ptr(self.thr_ns), ptr(self.thr_flags), ptr(self.thr), ptr(self.thr_present),
+                            ptr(self.thr_cnt), ptr(self.ovr_off), int(self.ovr_off[-1]), ptr(self.ovr_begin),
+                            ptr(self.ovr_end), ptr(self.ovr_flags), ptr(self.ovr_thr), ptr(self.ovr_present),
+                            ptr(self.ovr_cnt))
+
+    def status_cols(self) -> Optional[StatusCols]:
+        if self.status is None:
+            return None
+        s = self.status
+        return StatusCols(ptr(s["calculated"]), ptr(s["calc_thr"]), ptr(s["calc_present"]), ptr(s["calc_cnt"]),
+                          ptr(s["used"]), ptr(s["used_present"]), ptr(s["used_cnt"]), ptr(s["throttled"]))
+
+    def shard(self, rank: int, world: int) -> "Snapshot":
+        """Row shard for rank `rank` of `world`: contiguous row ranges of both pod kinds, throttles replicated
+        (SURVEY section 8e)."""
+        import copy
+
+        def cut(n):
+            lo = (n * rank) // world
+            hi = (n * (rank + 1)) // world
+            return slice(lo, hi)
+
+        s = copy.copy(self)
+        s.running = self.running.rows(cut(self.running.n))
+        s.pending = self.pending.rows(cut(self.pending.n))
+        s.meta = dict(self.meta, rank=rank, world=world)
+        return s
+
+
+@dataclass
+class PassResult:
+    """Host copies of every output of one pass (same layout for engine and oracle)."""
+    words_per_row: int
+    used: np.ndarray          # [R][m] i64
+    used_present: np.ndarray  # [m] u32
+    used_cnt: np.ndarray      # [m] i64
+    throttled: np.ndarray     # [m] u32
+    calc_thr: np.ndarray      # [R][m]
+    calc_present: np.ndarray
+    calc_cnt: np.ndarray
+    override_active: np.ndarray
+    run_bitmap: np.ndarray    # [N][W] u32
+    pend_bitmap: np.ndarray   # [P][W] u32
+    codes: np.ndarray         # [P][2W] u32
+    admit: np.ndarray         # [P] u8
+
+    @staticmethod
+    def alloc(snap: Snapshot, words_per_row: int) -> "PassResult":
+        m, R, W = snap.m, snap.R, words_per_row
+        N, P = snap.running.n, snap.pending.n
+        z = np.zeros
+        return PassResult(W, z((R, m), np.int64), z(m, np.uint32), z(m, np.int64), z(m, np.uint32), z((R, m), np.int64),
+                          z(m, np.uint32), z(m, np.int64), z(m, np.uint8), z((N, W), np.uint32), z((P, W), np.uint32),
+                          z((P, 2 * W), np.uint32), z(P, np.uint8))
+
+    def reconcile_out(self) -> ReconcileOut:
+        return ReconcileOut(ptr(self.used), ptr(self.used_present), ptr(self.used_cnt), ptr(self.throttled),
+                            ptr(self.calc_thr), ptr(self.calc_present), ptr(self.calc_cnt), ptr(self.override_active))
+
+    def code_matrix(self, m: int) -> np.ndarray:
+        """[P][m] uint8 of 2-bit check codes."""
+        P = self.codes.shape[0]
+        t = np.arange(m)
+        return ((self.codes[:, t >> 4] >> (2 * (t & 15)).astype(np.uint32)) & 3).astype(np.uint8).reshape(P, m)
+
+    def match_matrix(self, which: str, m: int) -> np.ndarray:
+        bm = self.run_bitmap if which == "running" else self.pend_bitmap
+        t = np.arange(m)
+        return ((bm[:, t >> 5] >> (t & 31).astype(np.uint32)) & 1).astype(np.uint8)
+
+
+def default_words_per_row(m: int) -> int:
+    """ceil(m/32) rounded up to a multiple of 4 words (16-byte rows) -- must equal kt_match_words()."""
+    w = (m + 31) // 32
+    return max(4, (w + 3) // 4 * 4)

@@ -1,0 +1,961 @@
+// ko_model.h -- ORACLE (test infrastructure only; the product never includes or links this).
+//
+// Object-level CPU restatement of the kube-throttler throttle-admission path.  Every function
+// names the reference code (relative to /root/reference) it follows.  The data structures are
+// deliberately the same shape as the Go ones (string-keyed maps, per-call selector construction,
+// ResourceAmountOfPod recomputed at every use) so that this doubles as the "reference-shaped"
+// CPU baseline of BASELINE.md section 3.
+//
+// Pinned against the reference's own tests (transcribed in tests/test_oracle_kat.py):
+//   resource_amount_test.go, throttle_types_test.go, temporary_threshold_override_test.go,
+//   throttle_selector_test.go, clusterthrottle_selector_test.go, resourcelist_test.go,
+//   test/integration/{throttle,clusterthrottle,clusterthrottle_stress}_test.go scenarios.
+// PARITY UNPINNED: matchExpressions operators and selector validation errors (the reference
+// tests only use matchLabels / empty selectors) -- these follow apimachinery v0.26.4's published
+// semantics (pkg/apis/meta/v1/helpers.go LabelSelectorAsSelector, pkg/labels/selector.go).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ko_json.h"
+#include "ko_quantity.h"
+
+namespace ko {
+
+// ------------------------------------------------------------------------------------------
+// pkg/resourcelist/resourcelist.go
+// ------------------------------------------------------------------------------------------
+using ResourceList = std::map<std::string, Quantity>;  // corev1.ResourceList (Go map; order-free)
+
+// resourcelist.go:48-54
+inline void RL_Add(ResourceList& lhs, const ResourceList& rhs) {
+  for (auto& kv : rhs) {
+    Quantity q = lhs.count(kv.first) ? lhs[kv.first] : Quantity{};
+    q.Add(kv.second);
+    lhs[kv.first] = q;
+  }
+}
+// resourcelist.go:56-62
+inline void RL_Sub(ResourceList& lhs, const ResourceList& rhs) {
+  for (auto& kv : rhs) {
+    Quantity q = lhs.count(kv.first) ? lhs[kv.first] : Quantity{};
+    q.Sub(kv.second);
+    lhs[kv.first] = q;
+  }
+}
+// resourcelist.go:64-74
+inline bool RL_GreaterOrEqual(const ResourceList& lhs, const ResourceList& rhs) {
+  for (auto& kv : rhs) {
+    auto it = lhs.find(kv.first);
+    if (it == lhs.end()) return false;
+    if (it->second.Cmp(kv.second) < 0) return false;
+  }
+  return true;
+}
+// resourcelist.go:76-84 (+ quantityMax :113-123): rhs-only names are inserted even when zero
+inline void RL_SetMax(ResourceList& lhs, const ResourceList& rhs) {
+  for (auto& kv : rhs) {
+    auto it = lhs.find(kv.first);
+    if (it != lhs.end()) {
+      if (it->second.Cmp(kv.second) < 0) it->second = kv.second;
+      continue;
+    }
+    lhs[kv.first] = kv.second;
+  }
+}
+// resourcelist.go:86-98
+inline void RL_SetMin(ResourceList& lhs, const ResourceList& rhs) {
+  for (auto& kv : rhs) {
+    auto it = lhs.find(kv.first);
+    if (it != lhs.end() && it->second.Cmp(kv.second) > 0) it->second = kv.second;
+  }
+  for (auto it = lhs.begin(); it != lhs.end();) {
+    if (!rhs.count(it->first)) it = lhs.erase(it);
+    else ++it;
+  }
+}
+// resourcelist.go:100-111: a missing name compares as the zero Quantity
+inline bool RL_EqualTo(const ResourceList& lhs, const ResourceList& rhs) {
+  auto half = [](const ResourceList& r1, const ResourceList& r2) {
+    for (auto& kv : r1) {
+      auto it = r2.find(kv.first);
+      Quantity other = it == r2.end() ? Quantity{} : it->second;
+      if (kv.second.Cmp(other) != 0) return false;
+    }
+    return true;
+  };
+  return half(lhs, rhs) && half(rhs, lhs);
+}
+
+// ------------------------------------------------------------------------------------------
+// Objects (only the fields the path reads)
+// ------------------------------------------------------------------------------------------
+using LabelMap = std::map<std::string, std::string>;
+
+struct Container {
+  ResourceList requests;
+};
+
+struct Pod {
+  std::string ns, name;
+  LabelMap labels;
+  std::string schedulerName, nodeName, phase;
+  std::vector<Container> initContainers, containers;
+  bool hasOverhead = false;
+  ResourceList overhead;
+  std::string NN() const { return ns + "/" + name; }
+};
+
+struct Namespace {
+  std::string name;
+  LabelMap labels;
+};
+
+// resourcelist.go:27-46
+inline ResourceList PodRequestResourceList(const Pod& pod) {
+  ResourceList icRes;
+  for (auto& c : pod.initContainers) RL_SetMax(icRes, c.requests);
+  ResourceList cRes;
+  for (auto& c : pod.containers) RL_Add(cRes, c.requests);
+  RL_SetMax(cRes, icRes);
+  if (pod.hasOverhead) RL_Add(cRes, pod.overhead);
+  return cRes;
+}
+
+// ------------------------------------------------------------------------------------------
+// pkg/apis/schedule/v1alpha1/resource_amount.go
+// ------------------------------------------------------------------------------------------
+struct ResourceAmount {
+  bool hasCounts = false;  // ResourceCounts != nil
+  long long pod = 0;
+  bool requestsNil = true;  // ResourceRequests == nil (only matters for DeepEqual-free printing)
+  ResourceList requests;
+};
+
+struct IsResourceAmountThrottled {
+  bool pod = false;                      // ResourceCounts.Pod
+  bool requestsNil = true;
+  std::map<std::string, bool> requests;  // ResourceRequests
+};
+
+// resource_amount.go:71-76
+inline ResourceAmount ResourceAmountOfPod(const Pod& pod) {
+  ResourceAmount a;
+  a.hasCounts = true;
+  a.pod = 1;
+  a.requestsNil = false;
+  a.requests = PodRequestResourceList(pod);
+  return a;
+}
+
+// resource_amount.go:91-110
+inline ResourceAmount RA_Add(ResourceAmount a, const ResourceAmount& b) {
+  a.requestsNil = false;
+  if (!a.hasCounts) {
+    if (b.hasCounts) { a.hasCounts = true; a.pod = b.pod; }
+  } else if (b.hasCounts) {
+    a.pod += b.pod;
+  }
+  RL_Add(a.requests, b.requests);
+  return a;
+}
+// resource_amount.go:112-125 (+ ResourceCounts.Sub :82-89 clamps at 0)
+inline ResourceAmount RA_Sub(ResourceAmount a, const ResourceAmount& b) {
+  a.requestsNil = false;
+  if (a.hasCounts && b.hasCounts) {
+    a.pod -= b.pod;
+    if (a.pod < 0) a.pod = 0;
+  }
+  RL_Sub(a.requests, b.requests);
+  return a;
+}
+
+// resource_amount.go:127-159
+inline IsResourceAmountThrottled RA_IsThrottled(const ResourceAmount& threshold, const ResourceAmount& used,
+                                                bool isThrottledOnEqual) {
+  IsResourceAmountThrottled t;
+  if (threshold.hasCounts && used.hasCounts)
+    t.pod = isThrottledOnEqual ? used.pod >= threshold.pod : used.pod > threshold.pod;
+  for (auto& kv : threshold.requests) {
+    t.requestsNil = false;
+    auto it = used.requests.find(kv.first);
+    if (it != used.requests.end()) {
+      int c = it->second.Cmp(kv.second);
+      t.requests[kv.first] = isThrottledOnEqual ? c >= 0 : c > 0;
+    } else {
+      t.requests[kv.first] = false;
+    }
+  }
+  return t;
+}
+
+// resource_amount.go:46-65
+inline bool IsThrottledFor(const IsResourceAmountThrottled& t, const Pod& pod) {
+  if (t.pod) return true;
+  ResourceAmount podAmount = ResourceAmountOfPod(pod);
+  for (auto& kv : podAmount.requests) {
+    if (kv.second.IsZero()) continue;
+    auto it = t.requests.find(kv.first);
+    if (it == t.requests.end()) continue;
+    if (it->second) return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// Label selectors: apimachinery v0.26.4 metav1.LabelSelectorAsSelector + labels.Selector.Matches
+// (not under /root/reference; call sites v1alpha1/throttle_selector.go:49-53,
+// clusterthrottle_selector.go:64-68)
+// ------------------------------------------------------------------------------------------
+struct LabelSelectorRequirement {
+  std::string key, op;  // op: In | NotIn | Exists | DoesNotExist (anything else is an error)
+  std::vector<std::string> values;
+};
+struct LabelSelector {
+  LabelMap matchLabels;
+  std::vector<LabelSelectorRequirement> matchExpressions;
+};
+
+struct SelectorError {
+  bool failed = false;
+  std::string msg;
+};
+
+namespace detail {
+inline bool is_alnum(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9'); }
+// validation.IsQualifiedName name part / IsValidLabelValue body: ([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]
+inline bool name_part_ok(const std::string& s) {
+  if (s.empty() || s.size() > 63) return false;
+  if (!is_alnum(s.front()) || !is_alnum(s.back())) return false;
+  for (char c : s)
+    if (!(is_alnum(c) || c == '-' || c == '_' || c == '.')) return false;
+  return true;
+}
+// validation.IsDNS1123Subdomain
+inline bool dns1123_subdomain_ok(const std::string& s) {
+  if (s.empty() || s.size() > 253) return false;
+  size_t start = 0;
+  while (true) {
+    size_t dot = s.find('.', start);
+    std::string lab = s.substr(start, dot == std::string::npos ? std::string::npos : dot - start);
+    if (lab.empty()) return false;
+    auto lower_alnum = [](char c) { return (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9'); };
+    if (!lower_alnum(lab.front()) || !lower_alnum(lab.back())) return false;
+    for (char c : lab)
+      if (!(lower_alnum(c) || c == '-')) return false;
+    if (dot == std::string::npos) break;
+    start = dot + 1;
+  }
+  return true;
+}
+inline bool label_key_ok(const std::string& k) {
+  size_t slash = k.find('/');
+  if (slash == std::string::npos) return name_part_ok(k);
+  if (k.find('/', slash + 1) != std::string::npos) return false;
+  std::string prefix = k.substr(0, slash), name = k.substr(slash + 1);
+  return dns1123_subdomain_ok(prefix) && name_part_ok(name);
+}
+inline bool label_value_ok(const std::string& v) { return v.empty() || name_part_ok(v); }
+}  // namespace detail
+
+// A compiled requirement (labels.Requirement).  "=" from matchLabels is selection.Equals, same
+// Matches() branch as In.
+struct Requirement {
+  std::string key;
+  enum Op { In, NotIn, Exists, DoesNotExist } op;
+  std::set<std::string> values;
+  // labels.Requirement.Matches (pkg/labels/selector.go)
+  bool Matches(const LabelMap& ls) const {
+    auto it = ls.find(key);
+    switch (op) {
+      case In: return it != ls.end() && values.count(it->second) > 0;
+      case NotIn: return it == ls.end() || values.count(it->second) == 0;
+      case Exists: return it != ls.end();
+      case DoesNotExist: return it == ls.end();
+    }
+    return false;
+  }
+};
+
+// metav1.LabelSelectorAsSelector: empty selector => labels.Everything() (zero requirements);
+// rebuilt (validated + sorted by key) on every call, like the reference does.
+inline std::vector<Requirement> LabelSelectorAsSelector(const LabelSelector& ps, SelectorError* err) {
+  std::vector<Requirement> reqs;
+  auto add = [&](const std::string& key, Requirement::Op op, const std::vector<std::string>& vals, bool equals) {
+    if (!detail::label_key_ok(key)) { err->failed = true; err->msg = "key: Invalid value: \"" + key + "\""; return; }
+    if ((op == Requirement::In || op == Requirement::NotIn) && !equals && vals.empty()) {
+      err->failed = true; err->msg = "values: Invalid value: []string(nil): for 'in', 'notin' operators, values set can't be empty"; return;
+    }
+    if ((op == Requirement::Exists || op == Requirement::DoesNotExist) && !vals.empty()) {
+      err->failed = true; err->msg = "values: Invalid value: values set must be empty for exists and does not exist"; return;
+    }
+    for (auto& v : vals)
+      if (!detail::label_value_ok(v)) { err->failed = true; err->msg = "values[0][" + key + "]: Invalid value: \"" + v + "\""; return; }
+    Requirement r;
+    r.key = key;
+    r.op = op;
+    r.values.insert(vals.begin(), vals.end());
+    reqs.push_back(std::move(r));
+  };
+  for (auto& kv : ps.matchLabels) {
+    add(kv.first, Requirement::In, {kv.second}, true);
+    if (err->failed) return {};
+  }
+  for (auto& e : ps.matchExpressions) {
+    Requirement::Op op;
+    if (e.op == "In") op = Requirement::In;
+    else if (e.op == "NotIn") op = Requirement::NotIn;
+    else if (e.op == "Exists") op = Requirement::Exists;
+    else if (e.op == "DoesNotExist") op = Requirement::DoesNotExist;
+    else { err->failed = true; err->msg = "\"" + e.op + "\" is not a valid label selector operator"; return {}; }
+    add(e.key, op, e.values, false);
+    if (err->failed) return {};
+  }
+  // labels.NewSelector().Add(...) sorts requirements ByKey
+  std::stable_sort(reqs.begin(), reqs.end(), [](const Requirement& a, const Requirement& b) { return a.key < b.key; });
+  return reqs;
+}
+inline bool SelectorMatches(const std::vector<Requirement>& reqs, const LabelMap& ls) {
+  for (auto& r : reqs)
+    if (!r.Matches(ls)) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// v1alpha1/throttle_selector.go, clusterthrottle_selector.go
+// ------------------------------------------------------------------------------------------
+struct SelectorTerm {
+  LabelSelector podSelector;
+  LabelSelector namespaceSelector;  // ClusterThrottle only
+};
+
+// throttle_selector.go:48-54
+inline bool Term_MatchesToPod(const SelectorTerm& t, const Pod& pod, SelectorError* err) {
+  auto sel = LabelSelectorAsSelector(t.podSelector, err);
+  if (err->failed) return false;
+  return SelectorMatches(sel, pod.labels);
+}
+// throttle_selector.go:30-42
+inline bool ThrottleSelector_MatchesToPod(const std::vector<SelectorTerm>& terms, const Pod& pod, SelectorError* err) {
+  for (auto& t : terms) {
+    bool m = Term_MatchesToPod(t, pod, err);
+    if (err->failed) return false;
+    if (m) return true;
+  }
+  return false;
+}
+// clusterthrottle_selector.go:63-69 -- the conversion error is swallowed (Q9)
+inline bool ClusterTerm_MatchesToNamespace(const SelectorTerm& t, const Namespace& ns) {
+  SelectorError e;
+  auto sel = LabelSelectorAsSelector(t.namespaceSelector, &e);
+  if (e.failed) return false;
+  return SelectorMatches(sel, ns.labels);
+}
+// clusterthrottle_selector.go:71-87
+inline bool ClusterTerm_MatchesToPod(const SelectorTerm& t, const Pod& pod, const Namespace& ns, SelectorError* err) {
+  if (!ClusterTerm_MatchesToNamespace(t, ns)) return false;
+  return Term_MatchesToPod(t, pod, err);
+}
+// clusterthrottle_selector.go:30-42
+inline bool ClusterSelector_MatchesToNamespace(const std::vector<SelectorTerm>& terms, const Namespace& ns) {
+  for (auto& t : terms)
+    if (ClusterTerm_MatchesToNamespace(t, ns)) return true;
+  return false;
+}
+// clusterthrottle_selector.go:44-56
+inline bool ClusterSelector_MatchesToPod(const std::vector<SelectorTerm>& terms, const Pod& pod, const Namespace& ns,
+                                         SelectorError* err) {
+  for (auto& t : terms) {
+    bool m = ClusterTerm_MatchesToPod(t, pod, ns, err);
+    if (err->failed) return false;
+    if (m) return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// time.Parse(time.RFC3339, s) (Go stdlib) as used by temporary_threshold_override.go:33-57
+// ------------------------------------------------------------------------------------------
+struct Time {
+  long long sec = kZeroSec;  // unix seconds; the Go zero Time is 0001-01-01T00:00:00Z
+  int nsec = 0;
+  static constexpr long long kZeroSec = -62135596800LL;
+  bool IsZero() const { return sec == kZeroSec && nsec == 0; }
+  bool Before(const Time& o) const { return sec < o.sec || (sec == o.sec && nsec < o.nsec); }
+  bool Equal(const Time& o) const { return sec == o.sec && nsec == o.nsec; }
+  bool After(const Time& o) const { return o.Before(*this); }
+};
+
+namespace detail {
+inline long long days_from_civil(long long y, unsigned m, unsigned d) {
+  y -= m <= 2;
+  const long long era = (y >= 0 ? y : y - 399) / 400;
+  const unsigned yoe = (unsigned)(y - era * 400);
+  const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + (long long)doe - 719468;
+}
+}  // namespace detail
+
+// Returns "" on success, otherwise Go's *time.ParseError text.
+inline std::string ParseRFC3339(const std::string& value, Time* out) {
+  static const std::string layout = "2006-01-02T15:04:05Z07:00";
+  auto perr = [&](size_t pos, const char* elem) {
+    return "parsing time \"" + value + "\" as \"" + layout + "\": cannot parse \"" + value.substr(std::min(pos, value.size())) +
+           "\" as \"" + elem + "\"";
+  };
+  auto range_err = [&](const char* what) { return "parsing time \"" + value + "\": " + what + " out of range"; };
+  size_t p = 0;
+  auto num = [&](int width, int* v) -> bool {
+    if (p + width > value.size()) return false;
+    int x = 0;
+    for (int i = 0; i < width; ++i) {
+      char c = value[p + i];
+      if (c < '0' || c > '9') return false;
+      x = x * 10 + (c - '0');
+    }
+    *v = x;
+    p += width;
+    return true;
+  };
+  auto lit = [&](char c) -> bool {
+    if (p < value.size() && value[p] == c) { ++p; return true; }
+    return false;
+  };
+  int Y, M, D, h, mi, s;
+  size_t at = p;
+  if (!num(4, &Y)) return perr(at, "2006");
+  at = p; if (!lit('-')) return perr(at, "-");
+  at = p; if (!num(2, &M)) return perr(at, "01");
+  if (M < 1 || M > 12) return range_err("month");
+  at = p; if (!lit('-')) return perr(at, "-");
+  at = p; if (!num(2, &D)) return perr(at, "02");
+  at = p; if (!lit('T')) return perr(at, "T");
+  at = p; if (!num(2, &h)) return perr(at, "15");
+  if (h < 0 || h >= 24) return range_err("hour");
+  at = p; if (!lit(':')) return perr(at, ":");
+  at = p; if (!num(2, &mi)) return perr(at, "04");
+  if (mi >= 60) return range_err("minute");
+  at = p; if (!lit(':')) return perr(at, ":");
+  at = p; if (!num(2, &s)) return perr(at, "05");
+  if (s >= 60) return range_err("second");
+  int nsec = 0;
+  if (p < value.size() && (value[p] == '.' || value[p] == ',') && p + 1 < value.size() && value[p + 1] >= '0' && value[p + 1] <= '9') {
+    ++p;
+    int digits = 0;
+    long long frac = 0;
+    while (p < value.size() && value[p] >= '0' && value[p] <= '9') {
+      if (digits < 9) { frac = frac * 10 + (value[p] - '0'); ++digits; }
+      ++p;
+    }
+    while (digits < 9) { frac *= 10; ++digits; }
+    nsec = (int)frac;
+  }
+  long long offset = 0;
+  at = p;
+  if (lit('Z')) {
+  } else if (p < value.size() && (value[p] == '+' || value[p] == '-')) {
+    int sign = value[p] == '-' ? -1 : 1;
+    ++p;
+    int oh, om;
+    if (!num(2, &oh)) return perr(at, "Z07:00");
+    if (!lit(':')) return perr(at, "Z07:00");
+    if (!num(2, &om)) return perr(at, "Z07:00");
+    if (oh > 24) return range_err("time zone offset hour");
+    if (om > 60) return range_err("time zone offset minute");
+    offset = sign * (oh * 3600LL + om * 60LL);
+  } else {
+    return perr(at, "Z07:00");
+  }
+  if (p != value.size()) return "parsing time \"" + value + "\": extra text: \"" + value.substr(p) + "\"";
+  static const int mdays[] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  bool leap = (Y % 4 == 0 && Y % 100 != 0) || Y % 400 == 0;
+  int dim = mdays[M - 1] + ((M == 2 && leap) ? 1 : 0);
+  if (D < 1 || D > dim) return range_err("day");
+  long long days = detail::days_from_civil(Y, (unsigned)M, (unsigned)D);
+  out->sec = days * 86400LL + h * 3600LL + mi * 60LL + s - offset;
+  out->nsec = nsec;
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------
+// v1alpha1/temporary_threshold_override.go, throttle_types.go
+// ------------------------------------------------------------------------------------------
+struct TemporaryThresholdOverride {
+  std::string begin, end;
+  ResourceAmount threshold;
+};
+
+// temporary_threshold_override.go:33-57 ("Failed to parse Begin/End" via errors.Wrap)
+inline std::string Override_BeginTime(const TemporaryThresholdOverride& o, Time* t) {
+  *t = Time{};
+  if (!o.begin.empty()) {
+    std::string e = ParseRFC3339(o.begin, t);
+    if (!e.empty()) return "Failed to parse Begin: " + e;
+  }
+  return "";
+}
+inline std::string Override_EndTime(const TemporaryThresholdOverride& o, Time* t) {
+  *t = Time{};
+  if (!o.end.empty()) {
+    std::string e = ParseRFC3339(o.end, t);
+    if (!e.empty()) return "Failed to parse End: " + e;
+  }
+  return "";
+}
+// temporary_threshold_override.go:59-72
+inline std::string Override_IsActive(const TemporaryThresholdOverride& o, const Time& now, bool* active) {
+  Time b, e;
+  *active = false;
+  std::string err = Override_BeginTime(o, &b);
+  if (!err.empty()) return err;
+  err = Override_EndTime(o, &e);
+  if (!err.empty()) return err;
+  bool begin = b.Before(now) || b.Equal(now);
+  bool end = e.IsZero() || now.Before(e) || now.Equal(e);
+  *active = begin && end;
+  return "";
+}
+
+struct CalculatedThreshold {
+  ResourceAmount threshold;
+  bool calculatedAtSet = false;  // !CalculatedAt.Time.IsZero()
+  Time calculatedAt;
+  std::vector<std::string> messages;
+};
+
+struct ThrottleStatus {
+  CalculatedThreshold calculatedThreshold;
+  IsResourceAmountThrottled throttled;
+  ResourceAmount used;
+};
+
+enum Kind { KindThrottle = 0, KindClusterThrottle = 1 };
+
+struct Throttle {  // Throttle and ClusterThrottle share everything but the selector evaluation
+  Kind kind = KindThrottle;
+  std::string ns, name;  // ClusterThrottle: ns == ""
+  std::string throttlerName;
+  ResourceAmount threshold;
+  std::vector<TemporaryThresholdOverride> overrides;
+  std::vector<SelectorTerm> terms;
+  ThrottleStatus status;
+  std::string NN() const { return ns + "/" + name; }  // types.NamespacedName.String(): "/name" for ClusterThrottle (plugin.go:289-294)
+};
+
+// throttle_types.go:65-106
+inline CalculatedThreshold CalculateThreshold(const Throttle& thr, const Time& now) {
+  CalculatedThreshold calculated;
+  calculated.calculatedAt = now;
+  calculated.calculatedAtSet = !now.IsZero();
+  calculated.threshold = thr.threshold;
+  bool activeFound = false;
+  ResourceAmount overrideResult;
+  overrideResult.requestsNil = false;
+  std::vector<std::string> errMessages;
+  for (size_t i = 0; i < thr.overrides.size(); ++i) {
+    const auto& o = thr.overrides[i];
+    bool isActive = false;
+    std::string err = Override_IsActive(o, now, &isActive);
+    if (!err.empty()) {
+      errMessages.push_back("index " + std::to_string(i) + ": " + err);
+      continue;
+    }
+    if (isActive) {
+      activeFound = true;
+      if (!overrideResult.hasCounts && o.threshold.hasCounts) {
+        overrideResult.hasCounts = true;
+        overrideResult.pod = o.threshold.pod;
+      }
+      for (auto& kv : o.threshold.requests)
+        if (!overrideResult.requests.count(kv.first)) overrideResult.requests[kv.first] = kv.second;
+    }
+  }
+  if (activeFound) calculated.threshold = overrideResult;
+  if (!errMessages.empty()) calculated.messages = errMessages;
+  return calculated;
+}
+
+// throttle_types.go:37-63 -- returns false if there is no next event; *out = nanoseconds
+inline bool NextOverrideHappensIn(const Throttle& thr, const Time& now, __int128* out) {
+  bool have = false;
+  __int128 best = 0;
+  auto upd = [&](const Time& t) {
+    __int128 d = ((__int128)t.sec - now.sec) * 1000000000 + (t.nsec - now.nsec);
+    if (!have || best > d) { have = true; best = d; }
+  };
+  for (auto& o : thr.overrides) {
+    Time b, e;
+    if (!Override_BeginTime(o, &b).empty()) continue;
+    if (b.After(now)) upd(b);
+    if (!Override_EndTime(o, &e).empty()) continue;
+    if (e.After(now)) upd(e);
+  }
+  if (have) *out = best;
+  return have;
+}
+
+enum CheckThrottleStatus { NotThrottled = 0, Active = 1, Insufficient = 2, PodRequestsExceedsThreshold = 3 };
+inline const char* CheckStatusName(CheckThrottleStatus s) {
+  switch (s) {
+    case NotThrottled: return "not-throttled";
+    case Active: return "active";
+    case Insufficient: return "insufficient";
+    case PodRequestsExceedsThreshold: return "pod-requests-exceeds-threshold";
+  }
+  return "?";
+}
+
+// throttle_types.go:128-153 (Throttle) and clusterthrottle_types.go:30-55 (ClusterThrottle).
+// The only difference is step 3's onEqual argument: hard-coded true for Throttle (:143),
+// isThrottledOnEqual for ClusterThrottle (:45).
+inline CheckThrottleStatus CheckThrottledFor(const Throttle& thr, const Pod& pod, const ResourceAmount& reserved,
+                                             bool isThrottledOnEqual) {
+  const ResourceAmount* threshold = &thr.threshold;
+  if (thr.status.calculatedThreshold.calculatedAtSet) threshold = &thr.status.calculatedThreshold.threshold;
+
+  if (IsThrottledFor(RA_IsThrottled(*threshold, ResourceAmountOfPod(pod), false), pod)) return PodRequestsExceedsThreshold;
+  if (IsThrottledFor(thr.status.throttled, pod)) return Active;
+
+  ResourceAmount alreadyUsed = RA_Add(RA_Add(ResourceAmount{}, thr.status.used), reserved);
+  bool step3OnEqual = thr.kind == KindThrottle ? true : isThrottledOnEqual;
+  if (IsThrottledFor(RA_IsThrottled(*threshold, alreadyUsed, step3OnEqual), pod)) return Active;
+
+  ResourceAmount used = RA_Add(RA_Add(RA_Add(ResourceAmount{}, thr.status.used), ResourceAmountOfPod(pod)), reserved);
+  if (IsThrottledFor(RA_IsThrottled(*threshold, used, isThrottledOnEqual), pod)) return Insufficient;
+  return NotThrottled;
+}
+
+// ------------------------------------------------------------------------------------------
+// pkg/controllers/reserved_resource_amounts.go
+// ------------------------------------------------------------------------------------------
+struct ReservedResourceAmounts {
+  // throttle NN -> (pod NN -> amount); std::map keeps iteration deterministic
+  std::map<std::string, std::map<std::string, ResourceAmount>> cache;
+  // :66-77 / :129-136 -- overwrites, returns !existed
+  bool addPod(const std::string& thrNN, const Pod& pod) {
+    auto& m = cache[thrNN];
+    bool existed = m.count(pod.NN()) > 0;
+    m[pod.NN()] = ResourceAmountOfPod(pod);
+    return !existed;
+  }
+  // :79-90 / :138-146
+  bool removePod(const std::string& thrNN, const Pod& pod) {
+    auto& m = cache[thrNN];
+    return m.erase(pod.NN()) > 0;
+  }
+  // :113-126 / :148-156
+  ResourceAmount reservedResourceAmount(const std::string& thrNN, std::vector<std::string>* podNNs = nullptr) const {
+    ResourceAmount result;
+    auto it = cache.find(thrNN);
+    if (it == cache.end()) return result;
+    for (auto& kv : it->second) {
+      if (podNNs) podNNs->push_back(kv.first);
+      result = RA_Add(result, kv.second);
+    }
+    return result;
+  }
+  // :92-111
+  void moveThrottleAssignmentForPods(const Pod& pod, const std::set<std::string>& from, const std::set<std::string>& to) {
+    for (auto& nn : from) removePod(nn, pod);
+    for (auto& nn : to) addPod(nn, pod);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// DeepEqual helpers (apiequality.Semantic.DeepEqual as used at throttle_controller.go:123-124,157):
+// nil and empty maps/slices are equal, Quantities compare by Cmp, pointers by pointee (nil != non-nil).
+// ------------------------------------------------------------------------------------------
+inline bool RL_SemanticEqual(const ResourceList& a, const ResourceList& b) {
+  if (a.size() != b.size()) return false;
+  for (auto& kv : a) {
+    auto it = b.find(kv.first);
+    if (it == b.end() || it->second.Cmp(kv.second) != 0) return false;
+  }
+  return true;
+}
+inline bool RA_SemanticEqual(const ResourceAmount& a, const ResourceAmount& b) {
+  if (a.hasCounts != b.hasCounts) return false;
+  if (a.hasCounts && a.pod != b.pod) return false;
+  return RL_SemanticEqual(a.requests, b.requests);
+}
+inline bool Throttled_SemanticEqual(const IsResourceAmountThrottled& a, const IsResourceAmountThrottled& b) {
+  return a.pod == b.pod && a.requests == b.requests;
+}
+
+// ------------------------------------------------------------------------------------------
+// Controllers + plugin: pkg/controllers/{throttle,clusterthrottle}_controller.go, pod_util.go,
+// pkg/scheduler_plugin/plugin.go
+// ------------------------------------------------------------------------------------------
+struct CheckResult {  // CheckThrottled's four lists (throttle_controller.go:349-397)
+  std::vector<const Throttle*> active, insufficient, exceeds, affected;
+  std::string error;  // non-empty => (nil,nil,nil,nil,err)
+};
+
+struct PreFilterResult {
+  std::string code;  // "Success" | "UnschedulableAndUnresolvable" | "Error"
+  std::vector<std::string> reasons;
+  bool hasEvent = false;
+  std::string eventMessage;
+  CheckResult thr, clthr;
+};
+
+struct World {
+  std::string throttlerName, targetSchedulerName;
+  // insertion-ordered stores (Go lister order is unspecified; tests that depend on order sort)
+  std::vector<std::unique_ptr<Pod>> pods;
+  std::unordered_map<std::string, size_t> podIndex;                       // ns/name -> pods[]
+  std::unordered_map<std::string, std::vector<size_t>> podsByNs;          // the namespace index (plugin.go:81-84)
+  std::vector<std::unique_ptr<Namespace>> namespaces;
+  std::unordered_map<std::string, size_t> nsIndex;
+  std::vector<std::unique_ptr<Throttle>> throttles;                       // kind==KindThrottle
+  std::unordered_map<std::string, size_t> thrIndex;
+  std::unordered_map<std::string, std::vector<size_t>> thrByNs;
+  std::vector<std::unique_ptr<Throttle>> clusterThrottles;
+  std::unordered_map<std::string, size_t> clthrIndex;
+  ReservedResourceAmounts thrCache, clthrCache;                           // one cache per controller (controller.go:34-50)
+
+  // pod_util.go:22-28
+  static bool isScheduled(const Pod& p) { return !p.nodeName.empty(); }
+  static bool isNotFinished(const Pod& p) { return p.phase != "Succeeded" && p.phase != "Failed"; }
+  // throttle_controller.go:213-219
+  bool isResponsibleFor(const Throttle& t) const { return throttlerName == t.throttlerName; }
+  bool shouldCountIn(const Pod& p) const { return p.schedulerName == targetSchedulerName && isScheduled(p); }
+
+  const Namespace* getNamespace(const std::string& name) const {
+    auto it = nsIndex.find(name);
+    return it == nsIndex.end() ? nullptr : namespaces[it->second].get();
+  }
+
+  // ---- store maintenance (informer cache stand-in) ----
+  void upsertPod(Pod p) {
+    std::string nn = p.NN();
+    auto it = podIndex.find(nn);
+    if (it != podIndex.end()) { *pods[it->second] = std::move(p); return; }
+    podIndex[nn] = pods.size();
+    podsByNs[p.ns].push_back(pods.size());
+    pods.push_back(std::make_unique<Pod>(std::move(p)));
+  }
+  void upsertNamespace(Namespace n) {
+    auto it = nsIndex.find(n.name);
+    if (it != nsIndex.end()) { *namespaces[it->second] = std::move(n); return; }
+    nsIndex[n.name] = namespaces.size();
+    namespaces.push_back(std::make_unique<Namespace>(std::move(n)));
+  }
+  void upsertThrottle(Throttle t) {
+    if (t.kind == KindThrottle) {
+      std::string nn = t.NN();
+      auto it = thrIndex.find(nn);
+      if (it != thrIndex.end()) { *throttles[it->second] = std::move(t); return; }
+      thrIndex[nn] = throttles.size();
+      thrByNs[t.ns].push_back(throttles.size());
+      throttles.push_back(std::make_unique<Throttle>(std::move(t)));
+    } else {
+      auto it = clthrIndex.find(t.name);
+      if (it != clthrIndex.end()) { *clusterThrottles[it->second] = std::move(t); return; }
+      clthrIndex[t.name] = clusterThrottles.size();
+      clusterThrottles.push_back(std::make_unique<Throttle>(std::move(t)));
+    }
+  }
+
+  // ---- affectedPods: throttle_controller.go:221-246 / clusterthrottle_controller.go:224-270 ----
+  // Q8: the Throttle version has `terminatedPods = append(nonterminatedPods, pod)` (:241); reproduced.
+  std::string affectedPods(const Throttle& thr, std::vector<const Pod*>* nonterminated, std::vector<const Pod*>* terminated) const {
+    nonterminated->clear();
+    terminated->clear();
+    if (thr.kind == KindThrottle) {
+      auto it = podsByNs.find(thr.ns);
+      if (it == podsByNs.end()) return "";
+      for (size_t pi : it->second) {
+        const Pod& pod = *pods[pi];
+        if (!shouldCountIn(pod)) continue;
+        SelectorError err;
+        bool match = ThrottleSelector_MatchesToPod(thr.terms, pod, &err);
+        if (err.failed) return err.msg;
+        if (match) {
+          if (isNotFinished(pod)) nonterminated->push_back(&pod);
+          else { *terminated = *nonterminated; terminated->push_back(&pod); }
+        }
+      }
+      return "";
+    }
+    std::vector<const Pod*> cand;
+    std::unordered_map<std::string, const Namespace*> nsMap;
+    for (auto& ns : namespaces) {
+      if (!ClusterSelector_MatchesToNamespace(thr.terms, *ns)) continue;
+      nsMap[ns->name] = ns.get();
+      auto it = podsByNs.find(ns->name);
+      if (it == podsByNs.end()) continue;
+      for (size_t pi : it->second) cand.push_back(pods[pi].get());
+    }
+    for (const Pod* pod : cand) {
+      if (!shouldCountIn(*pod)) continue;
+      SelectorError err;
+      bool match = ClusterSelector_MatchesToPod(thr.terms, *pod, *nsMap[pod->ns], &err);
+      if (err.failed) return err.msg;
+      if (!match) continue;
+      if (isNotFinished(*pod)) nonterminated->push_back(pod);
+      else terminated->push_back(pod);
+    }
+    return "";
+  }
+
+  // ---- reconcile: throttle_controller.go:84-211 / clusterthrottle_controller.go:87-214 ----
+  // UpdateStatus is applied in place (quiescent snapshot).  Returns error text or "".
+  std::string reconcile(Throttle& thr, const Time& now, bool* statusChanged = nullptr) {
+    std::vector<const Pod*> nonterm, term;
+    std::string err = affectedPods(thr, &nonterm, &term);
+    if (!err.empty()) return err;
+    ResourceAmount used;
+    for (const Pod* p : nonterm) used = RA_Add(used, ResourceAmountOfPod(*p));
+    ThrottleStatus newStatus = thr.status;
+    newStatus.used = used;
+    CalculatedThreshold calculated = CalculateThreshold(thr, now);
+    if (!RA_SemanticEqual(thr.status.calculatedThreshold.threshold, calculated.threshold) ||
+        thr.status.calculatedThreshold.messages != calculated.messages)
+      newStatus.calculatedThreshold = calculated;
+    newStatus.throttled = RA_IsThrottled(newStatus.calculatedThreshold.threshold, newStatus.used, true);
+
+    bool changed = !(RA_SemanticEqual(thr.status.used, newStatus.used) &&
+                     Throttled_SemanticEqual(thr.status.throttled, newStatus.throttled) &&
+                     RA_SemanticEqual(thr.status.calculatedThreshold.threshold, newStatus.calculatedThreshold.threshold) &&
+                     thr.status.calculatedThreshold.messages == newStatus.calculatedThreshold.messages &&
+                     thr.status.calculatedThreshold.calculatedAtSet == newStatus.calculatedThreshold.calculatedAtSet &&
+                     thr.status.calculatedThreshold.calculatedAt.Equal(newStatus.calculatedThreshold.calculatedAt));
+    if (changed) thr.status = newStatus;
+    if (statusChanged) *statusChanged = changed;
+    // unreserveAffectedPods (:135-155): both branches
+    ReservedResourceAmounts& cache = thr.kind == KindThrottle ? thrCache : clthrCache;
+    std::vector<const Pod*> all = nonterm;
+    all.insert(all.end(), term.begin(), term.end());
+    for (const Pod* p : all) cache.removePod(thr.NN(), *p);
+    return "";
+  }
+
+  std::string reconcileAll(const Time& now) {
+    for (auto& t : throttles)
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
+    for (auto& t : clusterThrottles)
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
+    return "";
+  }
+
+  // ---- affectedThrottles: throttle_controller.go:248-269 ----
+  std::string affectedThrottles(const Pod& pod, std::vector<Throttle*>* out) const {
+    out->clear();
+    auto it = thrByNs.find(pod.ns);
+    if (it == thrByNs.end()) return "";
+    for (size_t ti : it->second) {
+      Throttle* thr = throttles[ti].get();
+      if (!isResponsibleFor(*thr)) continue;
+      SelectorError err;
+      bool match = ThrottleSelector_MatchesToPod(thr->terms, pod, &err);
+      if (err.failed) return err.msg;
+      if (match) out->push_back(thr);
+    }
+    return "";
+  }
+  // ---- affectedClusterThrottles: clusterthrottle_controller.go:272-298 ----
+  std::string affectedClusterThrottles(const Pod& pod, std::vector<Throttle*>* out) const {
+    out->clear();
+    const Namespace* ns = getNamespace(pod.ns);
+    if (!ns) return "namespace \"" + pod.ns + "\" not found";
+    for (auto& t : clusterThrottles) {
+      if (!isResponsibleFor(*t)) continue;
+      SelectorError err;
+      bool match = ClusterSelector_MatchesToPod(t->terms, pod, *ns, &err);
+      if (err.failed) return err.msg;
+      if (match) out->push_back(t.get());
+    }
+    return "";
+  }
+
+  // ---- CheckThrottled: throttle_controller.go:349-397 / clusterthrottle_controller.go:378-425 ----
+  CheckResult CheckThrottled(Kind kind, const Pod& pod, bool isThrottledOnEqual) const {
+    CheckResult r;
+    std::vector<Throttle*> thrs;
+    r.error = kind == KindThrottle ? affectedThrottles(pod, &thrs) : affectedClusterThrottles(pod, &thrs);
+    if (!r.error.empty()) return r;
+    const ReservedResourceAmounts& cache = kind == KindThrottle ? thrCache : clthrCache;
+    for (Throttle* thr : thrs) {
+      r.affected.push_back(thr);
+      ResourceAmount reservedAmt = cache.reservedResourceAmount(thr->NN());
+      CheckThrottleStatus st = CheckThrottledFor(*thr, pod, reservedAmt, isThrottledOnEqual);
+      // the eagerly evaluated klog arguments of :376-386 (part of the reference's per-check cost)
+      ResourceAmount logRequested = ResourceAmountOfPod(pod);
+      ResourceAmount logAmountForCheck = RA_Add(RA_Add(RA_Add(ResourceAmount{}, thr->status.used), ResourceAmountOfPod(pod)), reservedAmt);
+      (void)logRequested; (void)logAmountForCheck;
+      switch (st) {
+        case Active: r.active.push_back(thr); break;
+        case Insufficient: r.insufficient.push_back(thr); break;
+        case PodRequestsExceedsThreshold: r.exceeds.push_back(thr); break;
+        default: break;
+      }
+    }
+    return r;
+  }
+
+  // ---- PreFilter: plugin.go:148-215 ----
+  PreFilterResult PreFilter(const Pod& pod) const {
+    PreFilterResult out;
+    out.thr = CheckThrottled(KindThrottle, pod, false);
+    if (!out.thr.error.empty()) { out.code = "Error"; out.reasons = {out.thr.error}; return out; }
+    out.clthr = CheckThrottled(KindClusterThrottle, pod, false);
+    if (!out.clthr.error.empty()) { out.code = "Error"; out.reasons = {out.clthr.error}; return out; }
+    auto& t = out.thr; auto& c = out.clthr;
+    if (t.active.size() + t.insufficient.size() + t.exceeds.size() + c.active.size() + c.insufficient.size() + c.exceeds.size() == 0) {
+      out.code = "Success";
+      return out;
+    }
+    auto names = [](const std::vector<const Throttle*>& v) {
+      std::string s;
+      for (size_t i = 0; i < v.size(); ++i) { if (i) s += ","; s += v[i]->NN(); }
+      return s;
+    };
+    if (!c.exceeds.empty()) out.reasons.push_back(std::string("clusterthrottle[") + CheckStatusName(PodRequestsExceedsThreshold) + "]=" + names(c.exceeds));
+    if (!t.exceeds.empty()) out.reasons.push_back(std::string("throttle[") + CheckStatusName(PodRequestsExceedsThreshold) + "]=" + names(t.exceeds));
+    if (c.exceeds.size() + t.exceeds.size() > 0) {
+      out.hasEvent = true;
+      std::vector<const Throttle*> both = c.exceeds;
+      both.insert(both.end(), t.exceeds.begin(), t.exceeds.end());
+      out.eventMessage =
+          "It won't be scheduled unless decreasing resource requests or increasing ClusterThrottle/Throttle threshold because its "
+          "resource requests exceeds their thresholds: " + names(both);
+    }
+    if (!c.active.empty()) out.reasons.push_back(std::string("clusterthrottle[") + CheckStatusName(Active) + "]=" + names(c.active));
+    if (!t.active.empty()) out.reasons.push_back(std::string("throttle[") + CheckStatusName(Active) + "]=" + names(t.active));
+    if (!c.insufficient.empty()) out.reasons.push_back(std::string("clusterthrottle[") + CheckStatusName(Insufficient) + "]=" + names(c.insufficient));
+    if (!t.insufficient.empty()) out.reasons.push_back(std::string("throttle[") + CheckStatusName(Insufficient) + "]=" + names(t.insufficient));
+    out.code = "UnschedulableAndUnresolvable";
+    return out;
+  }
+
+  // ---- Reserve / Unreserve: plugin.go:217-257, throttle_controller.go:271-331 ----
+  std::string Reserve(const Pod& pod) {
+    std::vector<std::string> errs;
+    std::vector<Throttle*> thrs;
+    std::string e = affectedThrottles(pod, &thrs);
+    if (!e.empty()) errs.push_back("Failed to reserve pod=" + pod.NN() + " in ThrottleController: " + e);
+    else for (Throttle* t : thrs) thrCache.addPod(t->NN(), pod);
+    e = affectedClusterThrottles(pod, &thrs);
+    if (!e.empty()) errs.push_back("Failed to reserve pod=" + pod.NN() + " in ClusterThrottleController: " + e);
+    else for (Throttle* t : thrs) clthrCache.addPod(t->NN(), pod);
+    std::string joined;
+    for (size_t i = 0; i < errs.size(); ++i) { if (i) joined += ", "; joined += errs[i]; }
+    return joined;
+  }
+  void Unreserve(const Pod& pod) {
+    std::vector<Throttle*> thrs;
+    if (affectedThrottles(pod, &thrs).empty()) for (Throttle* t : thrs) thrCache.removePod(t->NN(), pod);
+    if (affectedClusterThrottles(pod, &thrs).empty()) for (Throttle* t : thrs) clthrCache.removePod(t->NN(), pod);
+  }
+};
+
+}  // namespace ko

@@ -185,6 +185,8 @@ const char* kt_version(void);
 /* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the private stream. */
 int kt_set_stream(kt_ctx* ctx, void* cuda_stream);
 int kt_sync(kt_ctx* ctx);
+/* Record CUDA events around each kernel of kt_evaluate so kt_get_timing reports device times. */
+int kt_enable_timing(kt_ctx* ctx, int on);
 /* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost). */
 void* kt_host_alloc(size_t bytes);
 void kt_host_free(void* p);

@@ -1,0 +1,625 @@
+// kt_engine.cu -- implementation of the C ABI in include/kt_b200.h: context, HBM-resident snapshot,
+// kernel launches, result download, multi-GPU all-reduce.  There is NO CPU evaluation path in this
+// library: without a CUDA device every entry point that needs one fails with KT_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kt_b200.h"
+#include "kt_kernels.cuh"
+#include "kt_tables.h"
+
+namespace {
+
+using namespace kt;
+
+// ---- grow-only device buffer ---------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;  // slack so row appends do not reallocate every time
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PodStore {
+  int64_t n = 0;
+  DevBuf labels, req, present, flags, ns;
+  DevBuf bitmap;  // [n][Wp]
+  void release() { labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); }
+};
+
+// ---- NCCL through dlopen: the library loads without NCCL; only kt_comm_* needs it ------------------
+struct Uid128 { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Uid128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+const char* load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) return nullptr;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return "libnccl.so.2 not found";
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Uid128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) return "NCCL symbols missing";
+  g_nccl.handle = h;
+  return nullptr;
+}
+constexpr int kNcclInt64 = 4;  // ncclInt64
+constexpr int kNcclSum = 0;    // ncclSum
+
+}  // namespace
+
+struct kt_ctx {
+  std::mutex mu;
+  int device = 0;
+  kt_limits lim{};
+  std::string err;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool timing = false;
+  kt_timing last{};
+
+  PodStore pods[2];
+  // namespaces (host copy: table compilation needs them again when throttles change)
+  int32_t n_ns = 0;
+  std::vector<int64_t> ns_labels;
+  // throttles
+  bool have_throttles = false;
+  int32_t M = 0;
+  int32_t n_ovr = 0;
+  SelectorSpec spec;
+  HostTables ht;
+  DevBuf d_hash, d_table, d_need, d_nsmask, d_nsw_off, d_nsw_idx;
+  DevBuf d_kind, d_tflags, d_thr, d_thr_present, d_thr_cnt, d_ovr_off, d_ovr_begin, d_ovr_end, d_ovr_flags, d_ovr_thr,
+      d_ovr_present, d_ovr_cnt;
+  bool have_status = false;
+  DevBuf d_st_calculated, d_st_calc_thr, d_st_calc_present, d_st_calc_cnt, d_st_used, d_st_used_present, d_st_used_cnt,
+      d_st_throttled;
+  bool have_reserved = false;
+  DevBuf d_reserved, d_reserved_present, d_reserved_cnt;
+  // pass state / outputs
+  DevBuf d_part;   // [2R+1][M] u64, zero outside of kt_evaluate
+  DevBuf d_check;  // [M][16+16R]
+  DevBuf d_o_used, d_o_used_present, d_o_used_cnt, d_o_throttled, d_o_calc_thr, d_o_calc_present, d_o_calc_cnt, d_o_ovr_active;
+  DevBuf d_codes, d_admit;
+  bool evaluated = false;
+  // multi-GPU
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(kt_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define KT_CUDA(c, expr)                                                                                     \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) return fail((c), KT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));    \
+  } while (0)
+
+template <class T>
+int upload(kt_ctx* c, DevBuf& b, const T* src, size_t count) {
+  KT_CUDA(c, b.reserve(count * sizeof(T) + 16));
+  if (count) KT_CUDA(c, cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return KT_OK;
+}
+template <class T>
+int upload_vec(kt_ctx* c, DevBuf& b, const std::vector<T>& v) { return upload(c, b, v.data(), v.size()); }
+
+int set_device(kt_ctx* c) {
+  KT_CUDA(c, cudaSetDevice(c->device));
+  return KT_OK;
+}
+
+int recompile_tables(kt_ctx* c) {
+  std::string e = compile_tables(c->lim, c->spec, c->n_ns, c->ns_labels.empty() ? nullptr : c->ns_labels.data(), &c->ht);
+  if (!e.empty()) return fail(c, KT_ERR_INVALID, "compile_tables: %s", e.c_str());
+  int rc;
+  if ((rc = upload_vec(c, c->d_hash, c->ht.hash))) return rc;
+  if ((rc = upload_vec(c, c->d_table, c->ht.table))) return rc;
+  if ((rc = upload_vec(c, c->d_need, c->ht.need))) return rc;
+  if ((rc = upload_vec(c, c->d_nsmask, c->ht.nsmask))) return rc;
+  if ((rc = upload_vec(c, c->d_nsw_off, c->ht.nsw_off))) return rc;
+  if ((rc = upload_vec(c, c->d_nsw_idx, c->ht.nsw_idx))) return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors may be rebuilt right after
+  return KT_OK;
+}
+
+TableView table_view(const kt_ctx* c) {
+  TableView tb;
+  tb.hash = c->d_hash.as<ulonglong2>();
+  tb.hash_mask = c->ht.hash_mask;
+  tb.table = c->d_table.as<uint32_t>();
+  tb.need = c->d_need.as<uint32_t>();
+  tb.nsmask = c->d_nsmask.as<uint32_t>();
+  tb.nsw_off = c->d_nsw_off.as<int32_t>();
+  tb.nsw_idx = c->d_nsw_idx.as<int32_t>();
+  tb.M = c->ht.M; tb.W = c->ht.W; tb.Wp = c->ht.Wp; tb.TPpad = c->ht.TPpad; tb.B = c->ht.B; tb.rows = c->ht.rows; tb.NS = c->ht.NS;
+  return tb;
+}
+
+PodView pod_view(const PodStore& s) {
+  PodView v;
+  v.labels = s.labels.as<int64_t>();
+  v.req = s.req.as<int64_t>();
+  v.present = s.present.as<uint32_t>();
+  v.flags = s.flags.as<uint32_t>();
+  v.ns = s.ns.as<int32_t>();
+  v.n = s.n;
+  return v;
+}
+
+// Kernel variant dispatch: LMAX in {8,32}, planes per chunk in {1,2}, counter bits in {2,6}.
+template <int LMAX, int TPC, int B>
+void launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+  k_reconcile<LMAX, TPC, B><<<blocks, kTile, 0, c->stream>>>(pv, tb, c->lim.label_slots, c->lim.n_resources,
+                                                              c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(),
+                                                              c->d_part.as<unsigned long long>());
+}
+template <int LMAX, int TPC, int B>
+void launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+  k_check<LMAX, TPC, B><<<blocks, kTile, 0, c->stream>>>(pv, tb, c->lim.label_slots, c->lim.n_resources, c->d_check.as<unsigned char>(),
+                                                          c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(), c->d_codes.as<uint32_t>(),
+                                                          c->d_admit.as<unsigned char>());
+}
+#define KT_DISPATCH(fn, ...)                                                   \
+  do {                                                                         \
+    const bool l8 = c->lim.label_slots <= 8, t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2; \
+    if (l8 && t1 && b2) fn<8, 1, 2>(__VA_ARGS__);                              \
+    else if (l8 && t1) fn<8, 1, 6>(__VA_ARGS__);                               \
+    else if (l8 && b2) fn<8, 2, 2>(__VA_ARGS__);                               \
+    else if (l8) fn<8, 2, 6>(__VA_ARGS__);                                     \
+    else if (t1 && b2) fn<32, 1, 2>(__VA_ARGS__);                              \
+    else if (t1) fn<32, 1, 6>(__VA_ARGS__);                                    \
+    else if (b2) fn<32, 2, 2>(__VA_ARGS__);                                    \
+    else fn<32, 2, 6>(__VA_ARGS__);                                            \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* kt_version(void) { return "kt_b200 0.1 (sm_100a, abi 1)"; }
+
+const char* kt_last_error(const kt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int kt_create(kt_ctx** out, int device, const kt_limits* lim) {
+  if (!out || !lim) return KT_ERR_INVALID;
+  *out = nullptr;
+  if (lim->abi_version != KT_ABI_VERSION) return KT_ERR_INVALID;
+  if (lim->n_resources < 1 || lim->n_resources > KT_MAX_RESOURCES) return KT_ERR_LIMIT;
+  if (lim->label_slots < 1 || lim->label_slots > KT_MAX_LABEL_SLOTS) return KT_ERR_LIMIT;
+  if (lim->ns_label_slots < 0 || lim->ns_label_slots > KT_MAX_LABEL_SLOTS) return KT_ERR_LIMIT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KT_ERR_CUDA;  // no GPU: no fallback, by design
+  if (device < 0 || device >= ndev) return KT_ERR_INVALID;
+  kt_ctx* c = new kt_ctx();
+  c->device = device;
+  c->lim = *lim;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return KT_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  for (auto& e : c->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { delete c; return KT_ERR_CUDA; }
+  *out = c;
+  return KT_OK;
+}
+
+void kt_destroy(kt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->pods) s.release();
+  DevBuf* all[] = {&c->d_hash, &c->d_table, &c->d_need, &c->d_nsmask, &c->d_nsw_off, &c->d_nsw_idx, &c->d_kind, &c->d_tflags, &c->d_thr,
+                   &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
+                   &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
+                   &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
+                   &c->d_reserved_cnt, &c->d_part, &c->d_check, &c->d_o_used, &c->d_o_used_present, &c->d_o_used_cnt, &c->d_o_throttled,
+                   &c->d_o_calc_thr, &c->d_o_calc_present, &c->d_o_calc_cnt, &c->d_o_ovr_active, &c->d_codes, &c->d_admit};
+  for (DevBuf* b : all) b->release();
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int kt_set_stream(kt_ctx* c, void* cuda_stream) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return KT_OK;
+}
+
+int kt_enable_timing(kt_ctx* c, int on) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->timing = on != 0;
+  return KT_OK;
+}
+
+int kt_sync(kt_ctx* c) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = set_device(c);
+  if (rc) return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+void* kt_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void kt_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const int64_t* req, const uint32_t* present,
+                   const uint32_t* flags, const int32_t* ns_id) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (n < 0 || (n > 0 && (!labels || !req || !present || !flags || !ns_id))) return fail(c, KT_ERR_INVALID, "null pod columns");
+  int rc = set_device(c);
+  if (rc) return rc;
+  PodStore& s = c->pods[kind];
+  const int L = c->lim.label_slots, R = c->lim.n_resources;
+  if ((rc = upload(c, s.labels, labels, (size_t)L * n))) return rc;
+  if ((rc = upload(c, s.req, req, (size_t)R * n))) return rc;
+  if ((rc = upload(c, s.present, present, (size_t)n))) return rc;
+  if ((rc = upload(c, s.flags, flags, (size_t)n))) return rc;
+  if ((rc = upload(c, s.ns, ns_id, (size_t)n))) return rc;
+  s.n = n;
+  c->evaluated = false;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
+  return KT_OK;
+}
+
+int kt_update_pod_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, const int64_t* labels, const int64_t* req,
+                       const uint32_t* present, const uint32_t* flags, const int32_t* ns_id) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (k < 0 || (k > 0 && (!rows || !labels || !req || !present || !flags || !ns_id))) return fail(c, KT_ERR_INVALID, "null delta columns");
+  if (k == 0) return KT_OK;
+  PodStore& s = c->pods[kind];
+  for (int64_t i = 0; i < k; ++i)
+    if (rows[i] < 0 || rows[i] >= s.n) return fail(c, KT_ERR_INVALID, "delta row %lld out of range [0,%lld)", (long long)rows[i], (long long)s.n);
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int L = c->lim.label_slots, R = c->lim.n_resources;
+  DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns;
+  auto cleanup = [&]() { t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); };
+  if ((rc = upload(c, t_rows, rows, (size_t)k)) || (rc = upload(c, t_labels, labels, (size_t)L * k)) || (rc = upload(c, t_req, req, (size_t)R * k)) ||
+      (rc = upload(c, t_present, present, (size_t)k)) || (rc = upload(c, t_flags, flags, (size_t)k)) || (rc = upload(c, t_ns, ns_id, (size_t)k))) {
+    cleanup();
+    return rc;
+  }
+  k_scatter_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, t_rows.as<int64_t>(), L, R, s.n, t_labels.as<int64_t>(), t_req.as<int64_t>(),
+                                                                     t_present.as<uint32_t>(), t_flags.as<uint32_t>(), t_ns.as<int32_t>(),
+                                                                     s.labels.as<int64_t>(), s.req.as<int64_t>(), s.present.as<uint32_t>(),
+                                                                     s.flags.as<uint32_t>(), s.ns.as<int32_t>());
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(c, KT_ERR_CUDA, "k_scatter_rows: %s", cudaGetErrorString(e));
+  c->evaluated = false;
+  return KT_OK;
+}
+
+int kt_upload_namespaces(kt_ctx* c, int32_t n_ns, const int64_t* labels) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (n_ns < 0 || (n_ns > 0 && c->lim.ns_label_slots > 0 && !labels)) return fail(c, KT_ERR_INVALID, "null namespace labels");
+  int rc = set_device(c);
+  if (rc) return rc;
+  c->n_ns = n_ns;
+  c->ns_labels.assign(labels, labels + (size_t)c->lim.ns_label_slots * n_ns);
+  c->evaluated = false;
+  if (c->have_throttles) return recompile_tables(c);
+  return KT_OK;
+}
+
+int kt_upload_throttles(kt_ctx* c, int32_t m, const kt_throttle_cols* cols, const kt_selector_table* sel) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::string e = copy_selector_spec(m, cols, sel, &c->spec);
+  if (!e.empty()) return fail(c, KT_ERR_INVALID, "selector table: %s", e.c_str());
+  if (m > 0 && (!cols->thr || !cols->thr_present || !cols->thr_cnt || !cols->ovr_off)) return fail(c, KT_ERR_INVALID, "null threshold columns");
+  const int32_t n_ovr = m > 0 ? cols->ovr_off[m] : 0;
+  if (m > 0 && (cols->ovr_off[0] != 0 || n_ovr != cols->n_ovr)) return fail(c, KT_ERR_INVALID, "ovr_off must span [0, n_ovr]");
+  for (int32_t t = 0; t < m; ++t)
+    if (cols->ovr_off[t] > cols->ovr_off[t + 1]) return fail(c, KT_ERR_INVALID, "ovr_off not monotone");
+  if (n_ovr > 0 && (!cols->ovr_begin || !cols->ovr_end || !cols->ovr_flags || !cols->ovr_thr || !cols->ovr_present || !cols->ovr_cnt))
+    return fail(c, KT_ERR_INVALID, "null override columns");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int R = c->lim.n_resources;
+  c->M = m;
+  c->n_ovr = n_ovr;
+  if ((rc = upload(c, c->d_kind, cols->kind, (size_t)m)) || (rc = upload(c, c->d_tflags, cols->flags, (size_t)m)) ||
+      (rc = upload(c, c->d_thr, cols->thr, (size_t)R * m)) || (rc = upload(c, c->d_thr_present, cols->thr_present, (size_t)m)) ||
+      (rc = upload(c, c->d_thr_cnt, cols->thr_cnt, (size_t)m)) || (rc = upload(c, c->d_ovr_off, cols->ovr_off, (size_t)m + 1)) ||
+      (rc = upload(c, c->d_ovr_begin, cols->ovr_begin, (size_t)n_ovr)) || (rc = upload(c, c->d_ovr_end, cols->ovr_end, (size_t)n_ovr)) ||
+      (rc = upload(c, c->d_ovr_flags, cols->ovr_flags, (size_t)n_ovr)) || (rc = upload(c, c->d_ovr_thr, cols->ovr_thr, (size_t)R * n_ovr)) ||
+      (rc = upload(c, c->d_ovr_present, cols->ovr_present, (size_t)n_ovr)) || (rc = upload(c, c->d_ovr_cnt, cols->ovr_cnt, (size_t)n_ovr)))
+    return rc;
+  // per-throttle pass state
+  const size_t part_bytes = (size_t)(2 * R + 1) * m * sizeof(unsigned long long);
+  KT_CUDA(c, c->d_part.reserve(part_bytes + 16));
+  KT_CUDA(c, cudaMemsetAsync(c->d_part.p, 0, c->d_part.cap, c->stream));
+  KT_CUDA(c, c->d_check.reserve((size_t)m * (16 + 16 * R) + 16));
+  KT_CUDA(c, c->d_o_used.reserve((size_t)R * m * 8 + 16));
+  KT_CUDA(c, c->d_o_used_present.reserve((size_t)m * 4 + 16));
+  KT_CUDA(c, c->d_o_used_cnt.reserve((size_t)m * 8 + 16));
+  KT_CUDA(c, c->d_o_throttled.reserve((size_t)m * 4 + 16));
+  KT_CUDA(c, c->d_o_calc_thr.reserve((size_t)R * m * 8 + 16));
+  KT_CUDA(c, c->d_o_calc_present.reserve((size_t)m * 4 + 16));
+  KT_CUDA(c, c->d_o_calc_cnt.reserve((size_t)m * 8 + 16));
+  KT_CUDA(c, c->d_o_ovr_active.reserve((size_t)m + 16));
+  c->have_throttles = true;
+  c->have_status = false;
+  c->have_reserved = false;
+  c->evaluated = false;
+  return recompile_tables(c);
+}
+
+int kt_upload_status(kt_ctx* c, const kt_status_cols* st) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->have_throttles) return fail(c, KT_ERR_STATE, "kt_upload_status before kt_upload_throttles");
+  if (!st || !st->calculated || !st->calc_thr || !st->calc_present || !st->calc_cnt || !st->used || !st->used_present || !st->used_cnt ||
+      !st->throttled)
+    return fail(c, KT_ERR_INVALID, "null status columns");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const size_t m = (size_t)c->M, R = (size_t)c->lim.n_resources;
+  if ((rc = upload(c, c->d_st_calculated, st->calculated, m)) || (rc = upload(c, c->d_st_calc_thr, st->calc_thr, R * m)) ||
+      (rc = upload(c, c->d_st_calc_present, st->calc_present, m)) || (rc = upload(c, c->d_st_calc_cnt, st->calc_cnt, m)) ||
+      (rc = upload(c, c->d_st_used, st->used, R * m)) || (rc = upload(c, c->d_st_used_present, st->used_present, m)) ||
+      (rc = upload(c, c->d_st_used_cnt, st->used_cnt, m)) || (rc = upload(c, c->d_st_throttled, st->throttled, m)))
+    return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_status = true;
+  c->evaluated = false;
+  return KT_OK;
+}
+
+int kt_set_reserved(kt_ctx* c, const int64_t* reserved, const uint32_t* present, const int64_t* cnt) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->have_throttles) return fail(c, KT_ERR_STATE, "kt_set_reserved before kt_upload_throttles");
+  if (!reserved && !present && !cnt) { c->have_reserved = false; c->evaluated = false; return KT_OK; }
+  if (!reserved || !present || !cnt) return fail(c, KT_ERR_INVALID, "reserved columns must be all set or all null");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const size_t m = (size_t)c->M, R = (size_t)c->lim.n_resources;
+  if ((rc = upload(c, c->d_reserved, reserved, R * m)) || (rc = upload(c, c->d_reserved_present, present, m)) ||
+      (rc = upload(c, c->d_reserved_cnt, cnt, m)))
+    return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_reserved = true;
+  c->evaluated = false;
+  return KT_OK;
+}
+
+int32_t kt_match_words(const kt_ctx* c) { return c && c->have_throttles ? c->ht.Wp : 0; }
+
+int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->have_throttles) return fail(c, KT_ERR_STATE, "kt_evaluate before kt_upload_throttles");
+  const bool given = flags & KT_EVAL_GIVEN_STATUS;
+  const bool do_rec = !(flags & KT_EVAL_SKIP_RECONCILE), do_chk = !(flags & KT_EVAL_SKIP_CHECK);
+  if (given && !c->have_status) return fail(c, KT_ERR_STATE, "KT_EVAL_GIVEN_STATUS without kt_upload_status");
+  if (!do_rec && !given && do_chk) return fail(c, KT_ERR_INVALID, "KT_EVAL_SKIP_RECONCILE needs KT_EVAL_GIVEN_STATUS");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int R = c->lim.n_resources, M = c->M, Wp = c->ht.Wp;
+  PodStore& run = c->pods[KT_PODS_RUNNING];
+  PodStore& pend = c->pods[KT_PODS_PENDING];
+  KT_CUDA(c, run.bitmap.reserve((size_t)run.n * Wp * 4 + 16));
+  KT_CUDA(c, pend.bitmap.reserve((size_t)pend.n * Wp * 4 + 16));
+  KT_CUDA(c, c->d_codes.reserve((size_t)pend.n * 2 * Wp * 4 + 16));
+  KT_CUDA(c, c->d_admit.reserve((size_t)pend.n + 16));
+  const TableView tb = table_view(c);
+  int launches = 0;
+  const bool tm = c->timing;
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+
+  if (do_rec && run.n > 0 && M > 0) {
+    const PodView pv = pod_view(run);
+    const unsigned blocks = (unsigned)((run.n + kTile - 1) / kTile);
+    KT_DISPATCH(launch_reconcile, c, pv, tb, blocks);
+    ++launches;
+    KT_CUDA(c, cudaGetLastError());
+  }
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (do_rec && c->comm && c->nranks > 1 && M > 0) {
+    // the single exchange of the pass: int64 sum of the per-throttle partials over NVLink
+    int e = g_nccl.AllReduce(c->d_part.p, c->d_part.p, (size_t)(2 * R + 1) * M, kNcclInt64, kNcclSum, c->comm, c->stream);
+    if (e != 0) return fail(c, KT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  }
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (M > 0) {
+    ThrottleView tv{};
+    tv.kind = c->d_kind.as<uint8_t>(); tv.flags = c->d_tflags.as<uint8_t>();
+    tv.thr = c->d_thr.as<int64_t>(); tv.thr_present = c->d_thr_present.as<uint32_t>(); tv.thr_cnt = c->d_thr_cnt.as<int64_t>();
+    tv.ovr_off = c->d_ovr_off.as<int32_t>(); tv.ovr_begin = c->d_ovr_begin.as<int64_t>(); tv.ovr_end = c->d_ovr_end.as<int64_t>();
+    tv.ovr_flags = c->d_ovr_flags.as<uint8_t>(); tv.ovr_thr = c->d_ovr_thr.as<int64_t>(); tv.ovr_present = c->d_ovr_present.as<uint32_t>();
+    tv.ovr_cnt = c->d_ovr_cnt.as<int64_t>(); tv.n_ovr = c->n_ovr;
+    if (given) {
+      tv.st_calculated = c->d_st_calculated.as<uint8_t>(); tv.st_calc_thr = c->d_st_calc_thr.as<int64_t>();
+      tv.st_calc_present = c->d_st_calc_present.as<uint32_t>(); tv.st_calc_cnt = c->d_st_calc_cnt.as<int64_t>();
+      tv.st_used = c->d_st_used.as<int64_t>(); tv.st_used_present = c->d_st_used_present.as<uint32_t>();
+      tv.st_used_cnt = c->d_st_used_cnt.as<int64_t>(); tv.st_throttled = c->d_st_throttled.as<uint32_t>();
+    }
+    if (c->have_reserved) {
+      tv.reserved = c->d_reserved.as<int64_t>(); tv.reserved_present = c->d_reserved_present.as<uint32_t>();
+      tv.reserved_cnt = c->d_reserved_cnt.as<int64_t>();
+    }
+    ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
+                     c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
+    k_finalize<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(tv, M, R, (long long)now, flags, c->d_part.as<unsigned long long>(), ov,
+                                                                   c->d_check.as<unsigned char>());
+    ++launches;
+    KT_CUDA(c, cudaGetLastError());
+  }
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  if (do_chk && pend.n > 0) {
+    const PodView pv = pod_view(pend);
+    const unsigned blocks = (unsigned)((pend.n + kTile - 1) / kTile);
+    KT_DISPATCH(launch_check, c, pv, tb, blocks);
+    ++launches;
+    KT_CUDA(c, cudaGetLastError());
+  }
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+  c->last = kt_timing{};
+  c->last.launches = launches;
+  c->evaluated = true;
+  return KT_OK;
+}
+
+int kt_get_timing(kt_ctx* c, kt_timing* out) {
+  if (!c || !out) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = set_device(c);
+  if (rc) return rc;
+  if (c->timing && c->evaluated) {
+    KT_CUDA(c, cudaEventSynchronize(c->ev[4]));
+    cudaEventElapsedTime(&c->last.reconcile_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->last.allreduce_ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->last.finalize_ms, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->last.check_ms, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&c->last.total_ms, c->ev[0], c->ev[4]);
+  }
+  *out = c->last;
+  return KT_OK;
+}
+
+int kt_get_reconcile(kt_ctx* c, const kt_reconcile_out* o) {
+  if (!c || !o) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_reconcile before kt_evaluate");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const size_t m = (size_t)c->M, R = (size_t)c->lim.n_resources;
+  auto dl = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
+    if (!dst || !bytes) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream);
+  };
+  KT_CUDA(c, dl(o->used, c->d_o_used, R * m * 8));
+  KT_CUDA(c, dl(o->used_present, c->d_o_used_present, m * 4));
+  KT_CUDA(c, dl(o->used_cnt, c->d_o_used_cnt, m * 8));
+  KT_CUDA(c, dl(o->throttled, c->d_o_throttled, m * 4));
+  KT_CUDA(c, dl(o->calc_thr, c->d_o_calc_thr, R * m * 8));
+  KT_CUDA(c, dl(o->calc_present, c->d_o_calc_present, m * 4));
+  KT_CUDA(c, dl(o->calc_cnt, c->d_o_calc_cnt, m * 8));
+  KT_CUDA(c, dl(o->override_active, c->d_o_ovr_active, m));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_get_match_bitmap(kt_ctx* c, int kind, uint32_t* words) {
+  if (!c || !words) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_match_bitmap before kt_evaluate");
+  int rc = set_device(c);
+  if (rc) return rc;
+  PodStore& s = c->pods[kind];
+  if (s.n > 0) KT_CUDA(c, cudaMemcpyAsync(words, s.bitmap.p, (size_t)s.n * c->ht.Wp * 4, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check before kt_evaluate");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int64_t P = c->pods[KT_PODS_PENDING].n;
+  if (codes && P > 0) KT_CUDA(c, cudaMemcpyAsync(codes, c->d_codes.p, (size_t)P * 2 * c->ht.Wp * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_comm_unique_id(uint8_t uid[128]) {
+  if (!uid) return KT_ERR_INVALID;
+  if (load_nccl()) return KT_ERR_NCCL;
+  return g_nccl.GetUniqueId(uid) == 0 ? KT_OK : KT_ERR_NCCL;
+}
+
+int kt_comm_init(kt_ctx* c, const uint8_t uid[128], int nranks, int rank) {
+  if (!c || !uid || nranks < 1 || rank < 0 || rank >= nranks) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (const char* e = load_nccl()) return fail(c, KT_ERR_NCCL, "%s", e);
+  int rc = set_device(c);
+  if (rc) return rc;
+  Uid128 id;
+  std::memcpy(id.internal, uid, 128);
+  int e = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (e != 0) return fail(c, KT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  c->nranks = nranks;
+  c->rank = rank;
+  return KT_OK;
+}
+
+int kt_comm_destroy(kt_ctx* c) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
+  c->nranks = 1;
+  c->rank = 0;
+  return KT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// kt_tables.h -- selector compiler: turns the CSR selector table of include/kt_b200.h into the
+// bit-sliced match tables the sm_100a kernels scan (DESIGN.md "Bit-sliced selector match").
+//
+// This is packer-side work that runs when Throttles/ClusterThrottles/Namespaces change, not per pass.
+// It replaces what the reference redoes on EVERY MatchesToPod call:
+//   metav1.LabelSelectorAsSelector(&t.PodSelector)      (v1alpha1/throttle_selector.go:49)
+//   metav1.LabelSelectorAsSelector(&t.NamespaceSelector) (v1alpha1/clusterthrottle_selector.go:64)
+// It contains no pod-evaluation code: matching pods happens only on the GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/kt_b200.h"
+
+namespace kt {
+
+// Host copy of everything table compilation depends on (the caller's pointers are not retained).
+struct SelectorSpec {
+  int32_t m = 0;
+  std::vector<uint8_t> kind, flags;
+  std::vector<int32_t> ns_id;
+  std::vector<int32_t> term_off, pod_req_off, ns_req_off, req_val_off;
+  std::vector<uint8_t> term_flags, req_op;
+  std::vector<uint32_t> req_key, req_vals;
+};
+
+struct HostTables {
+  int32_t M = 0;
+  int32_t W = 0;       // ceil(M/32)
+  int32_t Wp = 0;      // words per bitmap row (multiple of 4)
+  int32_t TP = 1;      // max terms per throttle
+  int32_t TPpad = 1;   // planes stored per entry (1, or TP rounded up to even)
+  int32_t B = 1;       // counter bit-planes: bit_width(max #positive keys of a term)
+  int32_t rows = 1;    // table rows incl. the neutral row (index rows-1)
+  int32_t NS = 0;      // namespaces covered by nsmask
+  uint32_t hash_mask = 0;
+  std::vector<uint64_t> hash;    // [hash_mask+1][2]: {label key (pair or key|0xffffffff), row}
+  std::vector<uint32_t> table;   // [W][rows][TPpad][2]: {sat, pos}
+  std::vector<uint32_t> need;    // [W][TPpad][B]
+  std::vector<uint32_t> nsmask;  // [NS][W][TPpad]
+  std::vector<int32_t> nsw_off;  // [NS+1]
+  std::vector<int32_t> nsw_idx;  // non-zero words per namespace
+};
+
+// Validates the CSR arrays and copies them.  Returns "" or an error description.
+std::string copy_selector_spec(int32_t m, const kt_throttle_cols* cols, const kt_selector_table* sel, SelectorSpec* out);
+
+// Builds the tables.  ns_labels: [LN][n_ns] (may be null when n_ns == 0).
+std::string compile_tables(const kt_limits& lim, const SelectorSpec& spec, int32_t n_ns, const int64_t* ns_labels,
+                           HostTables* out);
+
+inline int32_t words_per_row(int32_t m) {
+  int32_t w = (m + 31) / 32;
+  w = (w + 3) / 4 * 4;
+  return w < 4 ? 4 : w;
+}
+
+inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; the device uses the same function
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+}  // namespace kt

@@ -1,0 +1,149 @@
+"""GPU parity: the CUDA path (through the C ABI) against the columnar oracle, bit-exact.
+
+Every output is compared: both match bitmaps, the 2-bit check codes, admit bits, used sums / presence /
+counts, throttled masks, calculated thresholds.  Sizes are chosen so the oracle finishes in seconds.
+"""
+import numpy as np
+import pytest
+
+from kube_throttler_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _live(snap):
+    return ((snap.thr_flags & abi.THR_RESPONSIBLE) != 0) & ((snap.thr_flags & abi.THR_SELECTOR_ERROR) == 0)
+
+
+def assert_same(snap, got, want, check_reconcile=True):
+    m = snap.m
+    assert got.words_per_row == want.words_per_row
+    np.testing.assert_array_equal(got.pend_bitmap, want.pend_bitmap, err_msg="pending match bitmap")
+    np.testing.assert_array_equal(got.codes, want.codes, err_msg="check codes")
+    np.testing.assert_array_equal(got.admit, want.admit, err_msg="admit")
+    np.testing.assert_array_equal(got.calc_thr, want.calc_thr, err_msg="calculated threshold")
+    np.testing.assert_array_equal(got.calc_present, want.calc_present)
+    np.testing.assert_array_equal(got.calc_cnt, want.calc_cnt)
+    np.testing.assert_array_equal(got.override_active, want.override_active)
+    if check_reconcile:
+        live = _live(snap)
+        np.testing.assert_array_equal(got.run_bitmap, want.run_bitmap, err_msg="running match bitmap")
+        np.testing.assert_array_equal(got.used[:, live], want.used[:, live], err_msg="used")
+        np.testing.assert_array_equal(got.used_present[live], want.used_present[live], err_msg="used_present")
+        np.testing.assert_array_equal(got.used_cnt[live], want.used_cnt[live], err_msg="used_cnt")
+        np.testing.assert_array_equal(got.throttled[live], want.throttled[live], err_msg="throttled")
+
+
+def run_both(kt, oracle, snap, flags=abi.EVAL_FRESH_STATUS):
+    got = kt.evaluate_snapshot(snap, flags)
+    want = oracle.columnar_evaluate(snap, flags, words_per_row=got.words_per_row)
+    return got, want
+
+
+def test_c1_example(kt, oracle):
+    snap = synth.generate("C1")
+    got, want = run_both(kt, oracle, snap)
+    assert_same(snap, got, want)
+    assert list(got.code_matrix(1)[:, 0]) == [0, 2, 3]  # 100m admit, 101m insufficient, 300m exceeds
+    assert list(got.admit) == [1, 0, 0]
+    assert got.used[0, 0] == 100 and got.used_cnt[0] == 10
+
+
+@pytest.mark.parametrize("kw", [
+    dict(config="C2", m=64, n=3000, p=400),
+    dict(config="C2", m=200, n=5000, p=500),
+    dict(config="C2", m=1000, n=20000, p=2000),
+    dict(config="C2", m=333, n=7777, p=1111, sort_by_namespace=False),
+    dict(config="C3", m=300, n=6000, p=800),
+    dict(config="C3", m=1000, n=20000, p=2000),
+    dict(config="C4", m=500, n=8000, p=1000),
+])
+def test_scaled_configs(kt, oracle, kw):
+    kw = dict(kw)
+    snap = synth.generate(kw.pop("config"), **kw)
+    got, want = run_both(kt, oracle, snap)
+    assert_same(snap, got, want)
+    assert got.match_matrix("pending", snap.m).sum() > 0
+
+
+def test_on_equal_flag(kt, oracle):
+    snap = synth.generate("C3", m=300, n=6000, p=800)
+    got, want = run_both(kt, oracle, snap, abi.EVAL_ON_EQUAL)
+    assert_same(snap, got, want)
+
+
+def test_given_status(kt, oracle):
+    """PreFilter between reconciles: the check uses an uploaded (stale) status, not this pass's."""
+    snap = synth.generate("C4", m=400, n=6000, p=900)
+    fresh = oracle.columnar_evaluate(snap)
+    rng = np.random.default_rng(7)
+    m, R = snap.m, snap.R
+    st = dict(calculated=(rng.random(m) < 0.8).astype(np.uint8), calc_thr=fresh.calc_thr.copy(), calc_present=fresh.calc_present.copy(),
+              calc_cnt=fresh.calc_cnt.copy(), used=fresh.used.copy(), used_present=fresh.used_present.copy(),
+              used_cnt=fresh.used_cnt.copy(), throttled=fresh.throttled.copy())
+    # make it stale: perturb used on a third of the throttles, drop throttled bits on some
+    stale = rng.random(m) < 0.33
+    st["used"][:, stale] = (st["used"][:, stale] * 0.5).astype(np.int64)
+    st["throttled"][rng.random(m) < 0.2] = 0
+    snap.status = st
+    snap.normalize()
+    for flags in (abi.EVAL_GIVEN_STATUS, abi.EVAL_GIVEN_STATUS | abi.EVAL_ON_EQUAL, abi.EVAL_GIVEN_STATUS | abi.EVAL_SKIP_RECONCILE):
+        got, want = run_both(kt, oracle, snap, flags)
+        assert_same(snap, got, want, check_reconcile=not (flags & abi.EVAL_SKIP_RECONCILE))
+
+
+def test_c2_full_size(kt, oracle):
+    """BASELINE config 2 at full size (1k x 100k x 10k): the oracle needs ~1 s for it."""
+    snap = synth.generate("C2")
+    got, want = run_both(kt, oracle, snap)
+    assert_same(snap, got, want)
+    used, present, cnt = snap.meta["true_used"]  # third implementation (numpy)
+    live = _live(snap)
+    np.testing.assert_array_equal(got.used[:, live], used[:, live])
+    np.testing.assert_array_equal(got.used_cnt[live], cnt[live])
+
+
+def test_repeat_pass_is_idempotent(kt):
+    """The partial-sum buffer is consumed and re-zeroed by every pass: two passes give identical results."""
+    snap = synth.generate("C2", m=200, n=5000, p=500)
+    eng = kt.Engine(snap.R, snap.L, snap.LN)
+    eng.upload_snapshot(snap)
+    eng.evaluate(snap.now)
+    a = eng.download()
+    eng.evaluate(snap.now)
+    b = eng.download()
+    for f in ("used", "used_cnt", "used_present", "throttled", "codes", "admit", "run_bitmap", "pend_bitmap"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+    eng.close()
+
+
+def test_pod_row_delta(kt, oracle):
+    """kt_update_pod_rows == re-uploading the modified columns (informer Add/Update/Delete as row scatters)."""
+    snap = synth.generate("C2", m=200, n=5000, p=500)
+    other = synth.generate("C2", m=200, n=5000, p=500, seed=99)
+    eng = kt.Engine(snap.R, snap.L, snap.LN)
+    eng.upload_snapshot(snap)
+    rng = np.random.default_rng(3)
+    rows = np.sort(rng.choice(snap.running.n, size=600, replace=False)).astype(np.int64)
+    delta = other.running.rows(rows)
+    delta.flags[:50] = 0  # deleted pods: never counted
+    delta.labels[:, :50] = abi.LABEL_EMPTY
+    eng.update_pod_rows(abi.PODS_RUNNING, rows, delta)
+    eng.evaluate(snap.now)
+    got = eng.download()
+    eng.close()
+    for name in ("labels", "req"):
+        getattr(snap.running, name)[:, rows] = getattr(delta, name)
+    for name in ("present", "flags", "ns_id"):
+        getattr(snap.running, name)[rows] = getattr(delta, name)
+    want = oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
+    assert_same(snap, got, want)
+
+
+def test_no_gpu_error_contract(kt):
+    """Calls out of order fail with KT_ERR_STATE, never with a silent default."""
+    eng = kt.Engine(4, 8, 4)
+    with pytest.raises(kt.KtError) as e:
+        eng.evaluate(0)
+    assert e.value.code == abi.ERR_STATE
+    eng.close()

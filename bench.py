@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- pod x throttle admission checks/sec of the batched throttle-admission pass.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+  (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is ONE pass of the hot path over one synthetic snapshot: reconcile every throttle against the
+running pods, (all-reduce the per-throttle partials when N>1), finalize, check every pending pod against
+every throttle.  Workload at N=1 = BASELINE.json configs[1] (C2: 1k Throttles x 100k running x 10k
+pending, R=4).  N>1 is WEAK scaling: every rank holds a C2-sized row shard (its own 100k running + 10k
+pending rows) and a replica of the same 1k throttles (thresholds scaled by N), i.e. one N-times-larger
+snapshot row-sharded across the GPUs; `value` counts the checks of all ranks.
+
+One JSON line on rank 0 (keys per the driver contract + roofline + cpu_baseline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pod_x_throttle_admission_checks_per_sec"
+UNIT = "checks/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    """HBM copy bandwidth measured on this pool's B200s by the driver; fallback per B200_PROFILING.md."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_snapshot(config: str, rank: int, world: int):
+    from kube_throttler_b200 import synth
+
+    snap = synth.generate(config)
+    if world > 1:
+        # weak scaling: same throttles on every rank, rank-specific pod rows, thresholds scaled with the snapshot
+        own = synth.generate(config, seed=synth.CONFIGS[config]["seed"] + 1000 * (rank + 1), calibrate=False)
+        snap.running, snap.pending = own.running, own.pending
+        snap.thr = snap.thr * world
+        snap.thr_cnt = snap.thr_cnt * world
+        snap.normalize()
+    return snap
+
+
+def algorithmic_bytes(snap, Wp):
+    """bytes one pass must move, per kernel."""
+    L, R, M = snap.L, snap.R, snap.m
+    n, p = snap.running.n, snap.pending.n
+    pod_row = 8 * L + 8 * R + 12
+    s_thr = 16 * 2 + 8 * (2 * R + 2) + 16
+    rec = n * pod_row + n * M / 8 + M * (2 * R + 1) * 8
+    chk = p * pod_row + p * M / 8 + p * M / 4 + p + M * (16 + 16 * R)
+    fin = M * s_thr + 2 * M * (2 * R + 2) * 8
+    return dict(reconcile=rec, check=chk, finalize=fin, total=rec + chk + fin)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm for this path.  The reference is pure Go and no Go
+    toolchain exists in this image, so this times the ORACLE's reference-shaped port
+    (oracle/ko_model.h: string maps, per-call selector construction, ResourceAmountOfPod recomputed per use)
+    with every host thread, on the same config.  Each step = one full pass over the snapshot."""
+    if rank != 0:
+        return
+    from oracle import ko
+
+    snap = make_snapshot(args.config, 0, 1)
+    threads = ko.hardware_threads()
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    times = []
+    for i in range(warm + steps):
+        _, tm = ko.object_evaluate(snap, threads=threads)
+        if i >= warm:
+            times.append(tm["total_s"])
+    T = sum(times)
+    checks = snap.pending.n * snap.m
+    value = checks * steps / T
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * T / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{args.config}: {snap.m} throttles x {snap.running.n} running x {snap.pending.n} pending, R={snap.R}, L={snap.L}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "full snapshot per step (reconcile of every throttle + PreFilter of every pending pod)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C++ restatement of the reference algorithm (not Go): no Go toolchain in this image",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    import torch
+    import torch.distributed as dist
+
+    import kube_throttler_b200 as kt
+    from kube_throttler_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    snap = make_snapshot(args.config, rank, world)
+    eng = kt.Engine(snap.R, snap.L, snap.LN, device=local_rank)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [kt.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], world, rank)
+    eng.upload_snapshot(snap)
+    Wp = eng.words_per_row
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def one_pass(timed):
+        with torch.cuda.stream(stream):
+            flush.zero_()  # evict the snapshot from L2 so every pass reads its inputs from HBM
+            if timed is not None:
+                timed[0].record(stream)
+            eng.evaluate(snap.now)
+            if timed is not None:
+                timed[1].record(stream)
+
+    # ---- device-resident timing: W warm-up, then exactly K timed steps ------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_pass(None)
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for e in evs:
+        one_pass(e)
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    T_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(T_ms, op=dist.ReduceOp.MAX)
+    T_ms = float(T_ms.item())
+    launches_per_step = eng.timing().launches
+    checks_per_step = snap.pending.n * snap.m * world
+
+    # ---- per-kernel device times (library events), same flush discipline ----------------------------
+    eng.enable_timing(True)
+    per = {"reconcile": [], "allreduce": [], "finalize": [], "check": []}
+    for _ in range(min(args.steps, 20)):
+        one_pass(None)
+        torch.cuda.synchronize()
+        t = eng.timing()
+        per["reconcile"].append(t.reconcile_ms); per["allreduce"].append(t.allreduce_ms)
+        per["finalize"].append(t.finalize_ms); per["check"].append(t.check_ms)
+    eng.enable_timing(False)
+    kernel_ms = {k: float(np.mean(v)) for k, v in per.items()}
+    ab = algorithmic_bytes(snap, Wp)
+    dom = "reconcile" if kernel_ms["reconcile"] >= kernel_ms["check"] else "check"
+    peak, peak_src = measured_peaks()
+    achieved = ab[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": ab[dom], "kernel_ms": kernel_ms,
+                "whole_pass_frac": ab["total"] / (T_ms / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D pods, pass, D2H results ---------
+    r, p = snap.running, snap.pending
+    pinned = []
+
+    def pin(a):
+        b = kt.Pinned(a.shape, a.dtype)
+        b.array[...] = a
+        pinned.append(b)
+        return b.array
+
+    hr = abi.PodCols(pin(r.labels), pin(r.req), pin(r.present), pin(r.flags), pin(r.ns_id))
+    hp = abi.PodCols(pin(p.labels), pin(p.req), pin(p.present), pin(p.flags), pin(p.ns_id))
+    out = abi.PassResult.alloc(snap, Wp)
+    codes_b, admit_b = kt.Pinned(out.codes.shape, np.uint32), kt.Pinned(out.admit.shape, np.uint8)
+    h2d = sum(a.nbytes for c in (hr, hp) for a in (c.labels, c.req, c.present, c.flags, c.ns_id))
+    d2h = codes_b.array.nbytes + admit_b.array.nbytes + sum(getattr(out, f).nbytes for f in
+                                                            ("used", "used_present", "used_cnt", "throttled", "calc_thr", "calc_present", "calc_cnt", "override_active"))
+
+    def e2e_step():
+        eng.upload_pods(abi.PODS_RUNNING, hr)
+        eng.upload_pods(abi.PODS_PENDING, hp)
+        eng.evaluate(snap.now)
+        eng.get_check(codes_b.array, admit_b.array)
+        eng.get_reconcile(out)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = checks_per_step * args.e2e_steps / float(e2e_s.item())
+    admit_frac = float(admit_b.array.mean())
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded, ~seconds ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ko  # checker / baseline only -- never on the measured GPU path
+
+        threads = ko.hardware_threads()
+        _, tm = ko.object_evaluate(snap, threads=threads)
+        cpu = {"value": snap.pending.n * snap.m / tm["total_s"], "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"one full {args.config} pass (reconcile {tm['reconcile_s']:.2f}s + check {tm['check_s']:.2f}s), "
+                         "C++ restatement of the reference algorithm (not Go)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": checks_per_step * args.steps / (T_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": T_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {snap.m} throttles x {snap.running.n} running x {snap.pending.n} pending per GPU, "
+                                   f"R={snap.R}, L={snap.L}", "per_gpu_rows": [snap.running.n, snap.pending.n], "throttles": snap.m,
+                       "l2": "flushed between steps (512 MiB memset, outside the timed events)", "parallelism": f"row-shard x{world}",
+                       "admit_fraction": admit_frac},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps, "path": "kt_upload_pods x2 + kt_evaluate + kt_get_check + kt_get_reconcile (pinned host buffers)"},
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -666,7 +666,7 @@ double ko_world_run_columns(void* h, const ko_columnar_args* a, int threads, int
       while (true) {
         int64_t p = next.fetch_add(1);
         if (p >= P) break;
-        PreFilterResult r = k->w.PreFilter(k->colPending[p]);
+        PreFilterResult r = k->w.PreFilter(k->colPending[p], (in.flags & KT_EVAL_ON_EQUAL) != 0);
         if (r.code == "Error") {
           // engine convention: a throttle with a selector error never matches; redo the two halves tolerantly
           if (a->admit) a->admit[p] = 1;

@@ -903,11 +903,13 @@ struct World {
   }
 
   // ---- PreFilter: plugin.go:148-215 ----
-  PreFilterResult PreFilter(const Pod& pod) const {
+  // isThrottledOnEqual is hard-coded false in the reference (plugin.go:153,165); the parameter exists only so
+  // the tests can drive CheckThrottled's other branch through the same composition code.
+  PreFilterResult PreFilter(const Pod& pod, bool isThrottledOnEqual = false) const {
     PreFilterResult out;
-    out.thr = CheckThrottled(KindThrottle, pod, false);
+    out.thr = CheckThrottled(KindThrottle, pod, isThrottledOnEqual);
     if (!out.thr.error.empty()) { out.code = "Error"; out.reasons = {out.thr.error}; return out; }
-    out.clthr = CheckThrottled(KindClusterThrottle, pod, false);
+    out.clthr = CheckThrottled(KindClusterThrottle, pod, isThrottledOnEqual);
     if (!out.clthr.error.empty()) { out.code = "Error"; out.reasons = {out.clthr.error}; return out; }
     auto& t = out.thr; auto& c = out.clthr;
     if (t.active.size() + t.insufficient.size() + t.exceeds.size() + c.active.size() + c.insufficient.size() + c.exceeds.size() == 0) {

@@ -168,7 +168,7 @@ int recompile_tables(kt_ctx* c) {
 
 TableView table_view(const kt_ctx* c) {
   TableView tb;
-  tb.hash = c->d_hash.as<ulonglong2>();
+  tb.hash = c->d_hash.as<uint4>();
   tb.hash_mask = c->ht.hash_mask;
   tb.table = c->d_table.as<uint32_t>();
   tb.need = c->d_need.as<uint32_t>();
@@ -190,31 +190,61 @@ PodView pod_view(const PodStore& s) {
   return v;
 }
 
-// Kernel variant dispatch: LMAX in {8,32}, planes per chunk in {1,2}, counter bits in {2,6}.
-template <int LMAX, int TPC, int B>
-void launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
-  k_reconcile<LMAX, TPC, B><<<blocks, kTile, 0, c->stream>>>(pv, tb, c->lim.label_slots, c->lim.n_resources,
-                                                              c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(),
-                                                              c->d_part.as<unsigned long long>());
+// ---- launches ------------------------------------------------------------------------------------
+// Every kernel goes through cudaLaunchKernelEx so that the dependent ones can carry the programmatic
+// stream serialization attribute (PDL): the secondary grid may start while the primary still runs and
+// synchronises on it with griddepcontrol.wait where it first needs the primary's results.
+template <class... KArgs, class... Args>
+cudaError_t launch(kt_ctx* c, void (*kern)(KArgs...), unsigned blocks, unsigned threads, size_t smem, bool pdl, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
-template <int LMAX, int TPC, int B>
-void launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
-  k_check<LMAX, TPC, B><<<blocks, kTile, 0, c->stream>>>(pv, tb, c->lim.label_slots, c->lim.n_resources, c->d_check.as<unsigned char>(),
-                                                          c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(), c->d_codes.as<uint32_t>(),
-                                                          c->d_admit.as<unsigned char>());
+
+// Kernel variant dispatch: planes per chunk in {1,2}, counter bits in {2,6}; k_reconcile additionally on
+// the register-accumulator bound RT in {4, 8, 0 (= any R, shared-memory accumulation)}.
+template <int TPC, int B, int RT>
+cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+  const int L = c->lim.label_slots, R = c->lim.n_resources;
+  return launch(c, k_reconcile<TPC, B, RT>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, kTileReconcile), false, pv, tb, L, R,
+                c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), c->d_part.as<unsigned long long>());
 }
-#define KT_DISPATCH(fn, ...)                                                   \
-  do {                                                                         \
-    const bool l8 = c->lim.label_slots <= 8, t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2; \
-    if (l8 && t1 && b2) fn<8, 1, 2>(__VA_ARGS__);                              \
-    else if (l8 && t1) fn<8, 1, 6>(__VA_ARGS__);                               \
-    else if (l8 && b2) fn<8, 2, 2>(__VA_ARGS__);                               \
-    else if (l8) fn<8, 2, 6>(__VA_ARGS__);                                     \
-    else if (t1 && b2) fn<32, 1, 2>(__VA_ARGS__);                              \
-    else if (t1) fn<32, 1, 6>(__VA_ARGS__);                                    \
-    else if (b2) fn<32, 2, 2>(__VA_ARGS__);                                    \
-    else fn<32, 2, 6>(__VA_ARGS__);                                            \
-  } while (0)
+template <int TPC, int B>
+cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
+  const int L = c->lim.label_slots, R = c->lim.n_resources;
+  return launch(c, k_check<TPC, B>, blocks, kTileCheck, check_smem_bytes(L, R, kTileCheck), pdl, pv, tb, L, R,
+                (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
+                c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>());
+}
+cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+  const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
+  const int R = c->lim.n_resources;
+#define KT_RT(TPC, B)                                                        \
+  (R <= 4 ? launch_reconcile<TPC, B, 4>(c, pv, tb, blocks)                   \
+          : R <= 8 ? launch_reconcile<TPC, B, 8>(c, pv, tb, blocks) : launch_reconcile<TPC, B, 0>(c, pv, tb, blocks))
+  if (t1 && b2) return KT_RT(1, 2);
+  if (t1) return KT_RT(1, 6);
+  if (b2) return KT_RT(2, 2);
+  return KT_RT(2, 6);
+#undef KT_RT
+}
+cudaError_t dispatch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
+  const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
+  if (t1 && b2) return launch_check<1, 2>(c, pv, tb, blocks, pdl);
+  if (t1) return launch_check<1, 6>(c, pv, tb, blocks, pdl);
+  if (b2) return launch_check<2, 2>(c, pv, tb, blocks, pdl);
+  return launch_check<2, 6>(c, pv, tb, blocks, pdl);
+}
 
 }  // namespace
 
@@ -474,10 +504,9 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
 
   if (do_rec && run.n > 0 && M > 0) {
     const PodView pv = pod_view(run);
-    const unsigned blocks = (unsigned)((run.n + kTile - 1) / kTile);
-    KT_DISPATCH(launch_reconcile, c, pv, tb, blocks);
+    const unsigned blocks = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
+    KT_CUDA(c, dispatch_reconcile(c, pv, tb, blocks));
     ++launches;
-    KT_CUDA(c, cudaGetLastError());
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   if (do_rec && c->comm && c->nranks > 1 && M > 0) {
@@ -505,18 +534,17 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     }
     ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
                      c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
-    k_finalize<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(tv, M, R, (long long)now, flags, c->d_part.as<unsigned long long>(), ov,
-                                                                   c->d_check.as<unsigned char>());
+    // PDL: overlaps its launch + override merge with the tail of k_reconcile (or of the all-reduce kernel)
+    KT_CUDA(c, launch(c, k_finalize, (unsigned)((M + 63) / 64), 64, 0, /*pdl=*/!tm, tv, M, R, (long long)now, flags,
+                      c->d_part.as<unsigned long long>(), ov, c->d_check.as<unsigned char>()));
     ++launches;
-    KT_CUDA(c, cudaGetLastError());
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   if (do_chk && pend.n > 0) {
     const PodView pv = pod_view(pend);
-    const unsigned blocks = (unsigned)((pend.n + kTile - 1) / kTile);
-    KT_DISPATCH(launch_check, c, pv, tb, blocks);
+    const unsigned blocks = (unsigned)((pend.n + kTileCheck - 1) / kTileCheck);
+    KT_CUDA(c, dispatch_check(c, pv, tb, blocks, /*pdl=*/!tm && M > 0));
     ++launches;
-    KT_CUDA(c, cudaGetLastError());
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
   c->last = kt_timing{};

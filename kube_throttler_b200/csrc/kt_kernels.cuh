@@ -9,18 +9,28 @@
 //                 (throttle_controller.go:248-269,349-397; throttle_types.go:128-153;
 //                  clusterthrottle_types.go:30-55; plugin.go:177-180)
 //
-// HBM-bound integer work: no tensor cores.  One lane = one pod row; the selector match is word-parallel
-// (32 throttles per LOP3) over the bit-sliced tables built by kt_tables.cc, so a pod costs
+// HBM-bound integer work: no tensor cores.  One lane = one pod row for the selector match, which is
+// word-parallel (32 throttles per LOP3) over the bit-sliced tables built by kt_tables.cc, so a pod costs
 // O(label slots x non-zero namespace words) instead of O(throttles x terms x requirements).
+// The segmented sum then flips the roles inside the warp: the 32x32 match bits are transposed with five
+// shuffles so that one lane = one THROTTLE, which adds up its pods' requests from shared memory without
+// any atomics; warps meet in per-CTA shared-memory accumulators and only those reach HBM (RED.ADD.64).
+//
+// The three kernels are chained with programmatic dependent launch (griddepcontrol): k_check matches the
+// pending pods while k_reconcile is still summing, and only its 4-step compare waits for k_finalize.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/kt_b200.h"
+#include "kt_tables.h"
 
 namespace kt {
 
-constexpr int kTile = 256;  // pods per CTA (one lane per pod)
+constexpr int kTileReconcile = 128;  // running pods per CTA (one lane per pod)
+constexpr int kTileCheck = 64;       // pending pods per CTA
+constexpr int kSlots = 16;           // per-CTA accumulator slots (one per distinct 32-throttle word)
+constexpr uint32_t kFull = 0xffffffffu;
 
 struct PodView {
   const int64_t* labels;    // [L][n]
@@ -32,7 +42,7 @@ struct PodView {
 };
 
 struct TableView {
-  const ulonglong2* hash;   // {label, row}
+  const uint4* hash;        // {keyId, valId, row, 0}; empty = {~0,~0,..}
   uint32_t hash_mask;
   const uint32_t* table;    // [W][rows][TPpad][2]
   const uint32_t* need;     // [W][TPpad][B]
@@ -91,38 +101,77 @@ struct ReconcileView {  // device-resident kt_reconcile_out
   uint8_t* override_active;
 };
 
-__device__ __forceinline__ uint64_t d_mix64(uint64_t x) {
-  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
-  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
-  x ^= x >> 31;
-  return x;
+// ---- programmatic dependent launch (PTX griddepcontrol; both are no-ops in a plain launch) -------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- label -> table row ---------------------------------------------------------------------------
+// label_hash(): 32-bit mixer shared with kt_tables.cc (kt_tables.h).
+
+// Continue a linear probe that did not resolve on its first slot.  Returns the row or -1.
+__device__ __noinline__ int32_t probe_slow(const TableView& tb, uint32_t key, uint32_t val, uint32_t slot) {
+#pragma unroll 1
+  while (true) {
+    slot = (slot + 1) & tb.hash_mask;
+    const uint4 e = __ldg(&tb.hash[slot]);
+    if (e.x == key && e.y == val) return (int32_t)e.z;
+    if ((e.x & e.y) == 0xffffffffu) return -1;
+  }
 }
 
-// label -> table row: exact (key,value) row, else the key's "other value" row, else the neutral row.
-__device__ __forceinline__ int32_t lookup_row(const TableView& tb, int64_t label) {
+// Translate the label slots of one pod (lane) into table rows and park them in shared memory:
+// exact (key,value) row, else the key's "other value" row, else the neutral row.  Both first probes of
+// all eight labels of a chunk are in flight together; only collisions take the serial path.
+__device__ __forceinline__ void stage_rowids(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, bool active,
+                                             int L, int32_t* s_rowid, int stride) {
   const int32_t neutral = tb.rows - 1;
-  if (label == KT_LABEL_EMPTY) return neutral;
-  uint64_t key = (uint64_t)label;
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    uint32_t slot = (uint32_t)d_mix64(key) & tb.hash_mask;
-#pragma unroll 1
-    while (true) {
-      ulonglong2 e = __ldg(&tb.hash[slot]);
-      if (e.x == key) return (int32_t)e.y;
-      if (e.x == ~0ull) break;
-      slot = (slot + 1) & tb.hash_mask;
+  for (int i0 = 0; i0 < L; i0 += 8) {
+    int64_t lab[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lab[k] = (active && i0 + k < L) ? __ldg(&labels[(int64_t)(i0 + k) * n + p]) : KT_LABEL_EMPTY;
+    uint4 ea[8], eb[8];
+    uint32_t sa[8], sb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
+      sa[k] = label_hash(key, val) & tb.hash_mask;
+      sb[k] = label_hash(key, 0xffffffffu) & tb.hash_mask;
+      if (lab[k] != KT_LABEL_EMPTY) {
+        ea[k] = __ldg(&tb.hash[sa[k]]);
+        eb[k] = __ldg(&tb.hash[sb[k]]);
+      } else {
+        ea[k] = eb[k] = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
+      }
     }
-    key |= 0xffffffffull;  // second pass: the key's "other value" row
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (i0 + k < L) {
+        const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
+        int32_t row = neutral;
+        if (lab[k] != KT_LABEL_EMPTY) {
+          int32_t r = -1;
+          if (ea[k].x == key && ea[k].y == val) r = (int32_t)ea[k].z;
+          else if ((ea[k].x & ea[k].y) != 0xffffffffu) r = probe_slow(tb, key, val, sa[k]);
+          if (r < 0) {
+            if (eb[k].x == key && eb[k].y == 0xffffffffu) r = (int32_t)eb[k].z;
+            else if ((eb[k].x & eb[k].y) != 0xffffffffu) r = probe_slow(tb, key, 0xffffffffu, sb[k]);
+          }
+          if (r >= 0) row = r;
+        }
+        s_rowid[(i0 + k) * stride] = row;
+      }
+    }
   }
-  return neutral;
 }
 
 // Match word w (32 throttles) of one pod: OR over term planes of
 //   AND_labels sat  &  (count of positive keys present == need)  &  namespace mask.
-template <int LMAX, int TPC, int B>
-__device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t (&rowid)[LMAX], int L, int ns, int w) {
+// s_rowid points at this lane's column of the staged rows (stride = pods per CTA).
+template <int TPC, int B>
+__device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t* s_rowid, int stride, int L, int ns, int w) {
   uint32_t result = 0;
+  const int32_t neutral = tb.rows - 1;
   const size_t row_stride = (size_t)tb.TPpad * 2;
   const uint32_t* wbase = tb.table + (size_t)w * tb.rows * row_stride;
   const uint32_t* nsm = tb.nsmask + ((size_t)ns * tb.W + w) * tb.TPpad;
@@ -132,14 +181,15 @@ __device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t
     uint32_t sat[TPC], cnt[TPC][B];
 #pragma unroll
     for (int s = 0; s < TPC; ++s) {
-      sat[s] = 0xffffffffu;
+      sat[s] = __ldg(&nsm[s0 + s]);
 #pragma unroll
       for (int b = 0; b < B; ++b) cnt[s][b] = 0;
     }
-#pragma unroll
-    for (int i = 0; i < LMAX; ++i) {
-      if (i < L) {
-        const uint32_t* e = wbase + (size_t)rowid[i] * row_stride + s0 * 2;
+#pragma unroll 8
+    for (int i = 0; i < L; ++i) {
+      const int32_t rid = s_rowid[i * stride];
+      if (rid != neutral) {  // the neutral row is sat=~0, pos=0: nothing to fold in
+        const uint32_t* e = wbase + (size_t)rid * row_stride + s0 * 2;
         uint32_t v[TPC * 2];
         if constexpr (TPC == 2) {
           uint4 q = __ldg(reinterpret_cast<const uint4*>(e));
@@ -163,7 +213,7 @@ __device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t
     }
 #pragma unroll
     for (int s = 0; s < TPC; ++s) {
-      uint32_t m = sat[s] & __ldg(&nsm[s0 + s]);
+      uint32_t m = sat[s];
 #pragma unroll
       for (int b = 0; b < B; ++b) m &= ~(cnt[s][b] ^ __ldg(&need[(s0 + s) * B + b]));
       result |= m;
@@ -172,63 +222,179 @@ __device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t
   return result;
 }
 
+// 32x32 bit-matrix transpose across the warp: in = lane l holds row l; out = lane b holds column b.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+  uint32_t m = 0x0000ffffu;
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t o = __shfl_xor_sync(kFull, x, j);
+    x = (lane & j) ? ((x & ~m) | ((o >> j) & m)) : ((x & m) | ((o & m) << j));
+    m ^= m << (j >> 1);
+  }
+  return x;
+}
+
+// Shared-memory carve-up of k_reconcile (host and device must agree).
+__host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int tile) {
+  return (size_t)R * tile * 8 + (size_t)kSlots * R * 32 * 8 + (size_t)L * tile * 4 + (size_t)tile * 4 + (size_t)kSlots * 32 * 4 * 2 +
+         (size_t)kSlots * 4;
+}
+__host__ __device__ inline size_t check_smem_bytes(int L, int R, int tile) { return (size_t)R * tile * 8 + (size_t)L * tile * 4; }
+
 // ------------------------------------------------------------------------------------------------
-// k_reconcile: one lane per RUNNING pod.
+// k_reconcile: one lane per RUNNING pod.   RT = compile-time bound on R for the register accumulators
+// (RT == 0: any R, accumulate straight into shared memory).
 // ------------------------------------------------------------------------------------------------
-template <int LMAX, int TPC, int B>
-__global__ void __launch_bounds__(kTile) k_reconcile(PodView pods, TableView tb, int L, int R, uint32_t* __restrict__ bitmap,
-                                                     unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
-  const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+template <int TPC, int B, int RT>
+__global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, TableView tb, int L, int R, uint32_t* __restrict__ bitmap,
+                                                              unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
+  constexpr int TILE = kTileReconcile;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                                  // [R][TILE], 0 where absent
+  unsigned long long* s_used = reinterpret_cast<unsigned long long*>(s_req + (size_t)R * TILE);  // [kSlots][R][32]
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_used + (size_t)kSlots * R * 32);            // [L][TILE]
+  uint32_t* s_present = reinterpret_cast<uint32_t*>(s_rowid + (size_t)L * TILE);              // [TILE]
+  uint32_t* s_cnt = s_present + TILE;                                                          // [kSlots][32]
+  uint32_t* s_pres = s_cnt + kSlots * 32;                                                      // [kSlots][32]
+  int* s_key = reinterpret_cast<int*>(s_pres + kSlots * 32);                                  // [kSlots] word index or -1
+
+  pdl_launch_dependents();  // k_finalize / k_check may be scheduled; they wait for our completion where they need it
+
+  const int tid = threadIdx.x, lane = tid & 31, wbase_pod = tid & ~31;
+  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
   const int Wp = tb.Wp;
-  {  // zero the tile's bitmap rows (contiguous: pod-major)
-    int64_t rows_here = pods.n - tile0 < kTile ? pods.n - tile0 : kTile;
+  {  // zero the tile's bitmap rows (contiguous: pod-major) and the CTA accumulators
+    const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* dst = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
-    int64_t nvec = rows_here * (Wp / 4);
-    for (int64_t i = threadIdx.x; i < nvec; i += kTile) dst[i] = make_uint4(0, 0, 0, 0);
+    const int64_t nvec = rows_here * (Wp / 4);
+    for (int64_t i = tid; i < nvec; i += TILE) dst[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kSlots * R * 32; i += TILE) s_used[i] = 0ull;
+    for (int i = tid; i < kSlots * 32; i += TILE) { s_cnt[i] = 0u; s_pres[i] = 0u; }
+    if (tid < kSlots) s_key[tid] = -1;
+  }
+  const int64_t p = tile0 + tid;
+  const bool valid = p < pods.n;
+  const uint32_t flags = valid ? __ldg(&pods.flags[p]) : 0u;
+  int ns = valid ? __ldg(&pods.ns[p]) : -1;
+  const uint32_t present = valid ? __ldg(&pods.present[p]) : 0u;
+  // shouldCountIn (throttle_controller.go:217-219): schedulerName == target && nodeName != ""
+  const bool counted = (flags & (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) == (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED) &&
+                       (unsigned)ns < (unsigned)tb.NS;
+  const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
+  int j = 0, hi = 0;
+  if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+  const bool active = j < hi;
+  // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
+  for (int r = 0; r < R; ++r) {
+    long long v = 0;
+    if (alive && active && ((present >> r) & 1)) v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
+    s_req[r * TILE + tid] = v;
+  }
+  s_present[tid] = present & ~KT_COUNT_BIT;
+  stage_rowids(tb, pods.labels, pods.n, p, active, L, s_rowid + tid, TILE);
+  int cur = active ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
+
+  unsigned long long* part_used = part;
+  unsigned long long* part_pres = part + (size_t)R * tb.M;
+  unsigned long long* part_cnt = part + (size_t)2 * R * tb.M;
+
+  // Words in ascending order, warp-uniform: lanes whose namespace has word w evaluate it, the others idle.
+  // Namespace-clustered rows (the reference's pod informer is namespace-indexed) make this 1-3 rounds.
+#pragma unroll 1
+  while (true) {
+    const int w = __reduce_min_sync(kFull, cur);
+    if (w == 0x7fffffff) break;
+    uint32_t word = 0;
+    if (cur == w) {
+      word = eval_word<TPC, B>(tb, s_rowid + tid, TILE, L, ns, w);
+      if (word) bitmap[p * Wp + w] = word;
+      ++j;
+      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+    }
+    const uint32_t aword = alive ? word : 0u;
+    if (!__any_sync(kFull, aword != 0u)) continue;
+    // used = used.Add(ResourceAmountOfPod(p)) for every matched throttle (throttle_controller.go:116-119):
+    // lane b now owns throttle w*32+b and the set of this warp's pods that matched it.
+    uint32_t T = warp_transpose32(aword, lane);
+    int slot = -1;
+    if (lane == 0) {
+#pragma unroll 1
+      for (int s = 0; s < kSlots; ++s) {
+        int k = *reinterpret_cast<volatile int*>(&s_key[s]);
+        if (k == -1) k = atomicCAS(&s_key[s], -1, w);
+        if (k == -1 || k == w) { slot = s; break; }
+      }
+    }
+    slot = __shfl_sync(kFull, slot, 0);
+    if (!T) continue;
+    const int t = w * 32 + lane;
+    if constexpr (RT > 0) {
+      unsigned long long acc[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r] = 0ull;
+      uint32_t cnt = 0, pres = 0;
+      while (T) {
+        const int i = wbase_pod + __ffs(T) - 1;
+        T &= T - 1;
+        ++cnt;
+        pres |= s_present[i];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R) acc[r] += (unsigned long long)s_req[r * TILE + i];
+      }
+      if (slot >= 0) {
+        atomicAdd(&s_cnt[slot * 32 + lane], cnt);
+        atomicOr(&s_pres[slot * 32 + lane], pres);
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R && acc[r]) atomicAdd(&s_used[(slot * R + r) * 32 + lane], acc[r]);
+      } else {  // more distinct words in this CTA than slots: straight to HBM
+        atomicAdd(&part_cnt[t], (unsigned long long)cnt);
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R) {
+            if (acc[r]) atomicAdd(&part_used[(size_t)r * tb.M + t], acc[r]);
+            if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;
+          }
+      }
+    } else {
+      while (T) {
+        const int i = wbase_pod + __ffs(T) - 1;
+        T &= T - 1;
+        const uint32_t pres = s_present[i];
+        if (slot >= 0) {
+          atomicAdd(&s_cnt[slot * 32 + lane], 1u);
+          atomicOr(&s_pres[slot * 32 + lane], pres);
+        } else {
+          atomicAdd(&part_cnt[t], 1ull);
+        }
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long v = (unsigned long long)s_req[r * TILE + i];
+          if (slot >= 0) {
+            if (v) atomicAdd(&s_used[(slot * R + r) * 32 + lane], v);
+          } else {
+            if (v) atomicAdd(&part_used[(size_t)r * tb.M + t], v);
+            if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;
+          }
+        }
+      }
+    }
   }
   __syncthreads();
-  const int64_t p = tile0 + threadIdx.x;
-  if (p >= pods.n) return;
-  const uint32_t flags = __ldg(&pods.flags[p]);
-  // shouldCountIn (throttle_controller.go:217-219): schedulerName == target && nodeName != ""
-  if ((flags & (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) != (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) return;
-  const int ns = __ldg(&pods.ns[p]);
-  if ((unsigned)ns >= (unsigned)tb.NS) return;
-  const int lo = __ldg(&tb.nsw_off[ns]), hi = __ldg(&tb.nsw_off[ns + 1]);
-  if (lo == hi) return;
-
-  int32_t rowid[LMAX];
-#pragma unroll
-  for (int i = 0; i < LMAX; ++i) rowid[i] = (i < L) ? lookup_row(tb, __ldg(&pods.labels[(int64_t)i * pods.n + p])) : 0;
-
-  const bool alive = flags & KT_POD_NOT_FINISHED;  // isNotFinished (pod_util.go:26-28)
-  const uint32_t present = __ldg(&pods.present[p]);
-  const int M = tb.M;
-  unsigned long long* part_used = part;
-  unsigned long long* part_pres = part + (size_t)R * M;
-  unsigned long long* part_cnt = part + (size_t)2 * R * M;
-
-#pragma unroll 1
-  for (int j = lo; j < hi; ++j) {
-    const int w = __ldg(&tb.nsw_idx[j]);
-    uint32_t word = eval_word<LMAX, TPC, B>(tb, rowid, L, ns, w);
-    if (!word) continue;
-    bitmap[p * Wp + w] = word;
-    if (!alive) continue;
-    // used = used.Add(ResourceAmountOfPod(p)) for every matched throttle (throttle_controller.go:116-119)
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      const int t = w * 32 + b;
-      atomicAdd(&part_cnt[t], 1ull);
-      uint32_t pr = present;
-      while (pr) {
-        const int r = __ffs(pr) - 1;
-        pr &= pr - 1;
-        const long long v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
-        if (v != 0) atomicAdd(&part_used[(size_t)r * M + t], (unsigned long long)v);
-        if (__ldcg(&part_pres[(size_t)r * M + t]) == 0ull) part_pres[(size_t)r * M + t] = 1ull;  // idempotent flag
-      }
+  // CTA accumulators -> HBM partials: one RED per (throttle, resource) the tile touched.
+  for (int idx = tid; idx < kSlots * 32; idx += TILE) {
+    const int slot = idx >> 5, b = idx & 31;
+    const int w = s_key[slot];
+    const uint32_t cnt = s_cnt[idx];
+    if (w < 0 || cnt == 0) continue;
+    const int t = w * 32 + b;
+    atomicAdd(&part_cnt[t], (unsigned long long)cnt);
+    const uint32_t pres = s_pres[idx];
+    for (int r = 0; r < R; ++r) {
+      const unsigned long long u = s_used[(slot * R + r) * 32 + b];
+      if (u) atomicAdd(&part_used[(size_t)r * tb.M + t], u);
+      if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;  // idempotent flag
     }
   }
 }
@@ -236,36 +402,25 @@ __global__ void __launch_bounds__(kTile) k_reconcile(PodView pods, TableView tb,
 // ------------------------------------------------------------------------------------------------
 // k_finalize: one lane per throttle.  Consumes (and re-zeroes) the partial sums.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, long long now, uint32_t eval_flags,
-                                                  unsigned long long* __restrict__ part, ReconcileView out,
-                                                  unsigned char* __restrict__ check /* [M][16 + 16R] */) {
+__global__ void __launch_bounds__(64) k_finalize(ThrottleView tv, int M, int R, long long now, uint32_t eval_flags,
+                                                 unsigned long long* __restrict__ part, ReconcileView out,
+                                                 unsigned char* __restrict__ check /* [M][16 + 16R] */) {
+  pdl_launch_dependents();  // k_check can start matching the pending pods right away
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M) return;
   const bool given = eval_flags & KT_EVAL_GIVEN_STATUS;
   const bool on_equal = eval_flags & KT_EVAL_ON_EQUAL;
-  const uint32_t tflags = tv.flags[t];
-  const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
 
-  // ---- used (this pass) ----
-  long long used[KT_MAX_RESOURCES];
-  uint32_t used_present = 0;
-  long long used_cnt = (long long)part[(size_t)2 * R * M + t];
-  part[(size_t)2 * R * M + t] = 0ull;
-  if (used_cnt > 0) used_present |= KT_COUNT_BIT;  // Counts stays nil with zero counted pods (Q3)
-  for (int r = 0; r < R; ++r) {
-    used[r] = (long long)part[(size_t)r * M + t];
-    if (part[(size_t)(R + r) * M + t] != 0ull) used_present |= 1u << r;
-    part[(size_t)r * M + t] = 0ull;
-    part[(size_t)(R + r) * M + t] = 0ull;
-  }
-
-  // ---- CalculateThreshold(now): merged active overrides REPLACE spec.threshold (throttle_types.go:65-106) ----
+  // ---- everything that does not depend on the running pods: CalculateThreshold(now) ----
+  // merged active overrides REPLACE spec.threshold (throttle_types.go:65-106)
   long long calc[KT_MAX_RESOURCES];
-  uint32_t calc_present = tv.thr_present[t];
-  long long calc_cnt = tv.thr_cnt[t];
-  for (int r = 0; r < R; ++r) calc[r] = tv.thr[(size_t)r * M + t];
-  {
-    bool active_found = false;
+  uint32_t calc_present = 0, tflags = 0;
+  long long calc_cnt = 0;
+  bool active_found = false;
+  if (t < M) {
+    tflags = tv.flags[t];
+    calc_present = tv.thr_present[t];
+    calc_cnt = tv.thr_cnt[t];
+    for (int r = 0; r < R; ++r) calc[r] = tv.thr[(size_t)r * M + t];
     long long ov[KT_MAX_RESOURCES];
     uint32_t ov_present = 0;
     long long ov_cnt = 0;
@@ -284,8 +439,26 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
       calc_cnt = ov_cnt;
       for (int r = 0; r < R; ++r) calc[r] = ov[r];
     }
-    if (out.override_active) out.override_active[t] = active_found;
   }
+  pdl_wait_primary();  // the partial sums of k_reconcile (or the all-reduce) are complete and visible
+  if (t >= M) return;
+  const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
+
+  // ---- used (this pass) ----
+  long long used[KT_MAX_RESOURCES];
+  uint32_t used_present = 0;
+  long long used_cnt = (long long)__ldcg(&part[(size_t)2 * R * M + t]);
+  if (used_cnt > 0) used_present |= KT_COUNT_BIT;  // Counts stays nil with zero counted pods (Q3)
+  for (int r = 0; r < R; ++r) {
+    used[r] = (long long)__ldcg(&part[(size_t)r * M + t]);
+    if (__ldcg(&part[(size_t)(R + r) * M + t]) != 0ull) used_present |= 1u << r;
+  }
+  part[(size_t)2 * R * M + t] = 0ull;
+  for (int r = 0; r < R; ++r) {
+    part[(size_t)r * M + t] = 0ull;
+    part[(size_t)(R + r) * M + t] = 0ull;
+  }
+  if (out.override_active) out.override_active[t] = active_found;
 
   // ---- status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133) ----
   uint32_t throttled = 0;
@@ -360,51 +533,65 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_check: one lane per PENDING pod.
+// k_check: one lane per PENDING pod.  Phase 1 (no dependency on the running pods): selector match ->
+// affectedThrottles bitmap.  Phase 2 (after k_finalize): 4-step CheckThrottledFor per matched pair.
 // ------------------------------------------------------------------------------------------------
-template <int LMAX, int TPC, int B>
-__global__ void __launch_bounds__(kTile) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
-                                                 uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                 unsigned char* __restrict__ admit) {
-  const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+template <int TPC, int B>
+__global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
+                                                      uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
+                                                      unsigned char* __restrict__ admit) {
+  constexpr int TILE = kTileCheck;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                     // [R][TILE]
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_req + (size_t)R * TILE);       // [L][TILE]
+  const int tid = threadIdx.x;
+  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
   const int Wp = tb.Wp;
   {
-    int64_t rows_here = pods.n - tile0 < kTile ? pods.n - tile0 : kTile;
+    const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
     uint4* d1 = reinterpret_cast<uint4*>(codes + tile0 * 2 * Wp);
-    int64_t nvec = rows_here * (Wp / 4);
-    for (int64_t i = threadIdx.x; i < nvec; i += kTile) d0[i] = make_uint4(0, 0, 0, 0);
-    for (int64_t i = threadIdx.x; i < 2 * nvec; i += kTile) d1[i] = make_uint4(0, 0, 0, 0);
+    const int64_t nvec = rows_here * (Wp / 4);
+    for (int64_t i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
+    for (int64_t i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
-  __syncthreads();
-  const int64_t p = tile0 + threadIdx.x;
-  if (p >= pods.n) return;
-  unsigned char ok = 1;
-  const int ns = __ldg(&pods.ns[p]);
+  const int64_t p = tile0 + tid;
+  const bool valid = p < pods.n;
+  const int ns = valid ? __ldg(&pods.ns[p]) : -1;
+  const uint32_t present = valid ? __ldg(&pods.present[p]) : 0u;
   int lo = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  if (lo != hi) {
-    int32_t rowid[LMAX];
-#pragma unroll
-    for (int i = 0; i < LMAX; ++i) rowid[i] = (i < L) ? lookup_row(tb, __ldg(&pods.labels[(int64_t)i * pods.n + p])) : 0;
-    const uint32_t present = __ldg(&pods.present[p]);
-    // ResourceAmountOfPod(pod): the non-zero requests are the only ones IsThrottledFor looks at (Q5)
-    uint32_t nz = 0;
-    {
-      uint32_t pr = present;
-      while (pr) {
-        const int r = __ffs(pr) - 1;
-        pr &= pr - 1;
-        if (__ldg(&pods.req[(int64_t)r * pods.n + p]) != 0) nz |= 1u << r;
-      }
-    }
+  const bool active = lo < hi;
+  // ResourceAmountOfPod(pod): the non-zero requests are the only ones IsThrottledFor looks at (Q5)
+  uint32_t nz = 0;
+  for (int r = 0; r < R; ++r) {
+    long long v = 0;
+    if (active && ((present >> r) & 1)) v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
+    s_req[r * TILE + tid] = v;
+    if (v != 0) nz |= 1u << r;
+  }
+  stage_rowids(tb, pods.labels, pods.n, p, active, L, s_rowid + tid, TILE);
+  __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
+
+  // ---- phase 1: affectedThrottles (throttle_controller.go:248-269) ----
+  uint32_t nzw = 0;  // does any word match at all?
+#pragma unroll 1
+  for (int j = lo; j < hi; ++j) {
+    const int w = __ldg(&tb.nsw_idx[j]);
+    const uint32_t word = eval_word<TPC, B>(tb, s_rowid + tid, TILE, L, ns, w);
+    if (word) { bitmap[p * Wp + w] = word; nzw = 1; }
+  }
+  pdl_wait_primary();  // k_finalize has written the check constants
+
+  // ---- phase 2: CheckThrottledFor per affected throttle ----
+  unsigned char ok = 1;
+  if (nzw) {
     const size_t stride = 16 + 16 * (size_t)R;
 #pragma unroll 1
     for (int j = lo; j < hi; ++j) {
       const int w = __ldg(&tb.nsw_idx[j]);
-      uint32_t word = eval_word<LMAX, TPC, B>(tb, rowid, L, ns, w);
+      uint32_t word = bitmap[p * Wp + w];  // this lane's own store (or the zero fill, ordered by the barrier)
       if (!word) continue;
-      bitmap[p * Wp + w] = word;
       uint32_t c0 = 0, c1 = 0;
       while (word) {
         const int b = __ffs(word) - 1;
@@ -421,7 +608,7 @@ __global__ void __launch_bounds__(kTile) k_check(PodView pods, TableView tb, int
         for (uint32_t c = cand; c && !s1;) {
           const int r = __ffs(c) - 1;
           c &= c - 1;
-          s1 = __ldg(&pods.req[(int64_t)r * pods.n + p]) > __ldg(&thrv[r]);
+          s1 = s_req[r * TILE + tid] > __ldg(&thrv[r]);
         }
         if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
         else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
@@ -432,7 +619,7 @@ __global__ void __launch_bounds__(kTile) k_check(PodView pods, TableView tb, int
           for (uint32_t c = cand; c && !s4;) {
             const int r = __ffs(c) - 1;
             c &= c - 1;
-            const long long v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
+            const long long v = s_req[r * TILE + tid];
             const long long hd = __ldg(&head[r]);
             s4 = ge ? v >= hd : v > hd;
           }
@@ -446,7 +633,7 @@ __global__ void __launch_bounds__(kTile) k_check(PodView pods, TableView tb, int
       if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
     }
   }
-  admit[p] = ok;
+  if (valid) admit[p] = ok;
 }
 
 // Row-level delta: scatter k packed rows into the resident columns (pod informer Add/Update/Delete).

@@ -226,21 +226,22 @@ std::string compile_tables(const kt_limits& lim, const SelectorSpec& s, int32_t 
     h.nsw_off[ns + 1] = (int32_t)h.nsw_idx.size();
   }
 
-  // ---- label -> row hash (open addressing, <= 50% load) ---------------------------------------
+  // ---- label -> row hash (open addressing, linear probing, <= 50% load) --------------------------
   size_t entries = key_row.size() + pair_row.size();
   size_t cap = 16;
   while (cap < entries * 2 + 2) cap <<= 1;
   h.hash_mask = (uint32_t)(cap - 1);
-  h.hash.assign(cap * 2, 0);
-  for (size_t i = 0; i < cap; ++i) h.hash[2 * i] = ~0ull;
-  auto insert = [&](uint64_t key, int32_t row) {
-    size_t slot = mix64(key) & h.hash_mask;
-    while (h.hash[2 * slot] != ~0ull) slot = (slot + 1) & h.hash_mask;
-    h.hash[2 * slot] = key;
-    h.hash[2 * slot + 1] = (uint64_t)row;
+  h.hash.assign(cap * 4, 0);
+  for (size_t i = 0; i < cap; ++i) h.hash[4 * i] = h.hash[4 * i + 1] = 0xffffffffu;
+  auto insert = [&](uint32_t key, uint32_t val, int32_t row) {
+    size_t slot = label_hash(key, val) & h.hash_mask;
+    while ((h.hash[4 * slot] & h.hash[4 * slot + 1]) != 0xffffffffu) slot = (slot + 1) & h.hash_mask;
+    h.hash[4 * slot] = key;
+    h.hash[4 * slot + 1] = val;
+    h.hash[4 * slot + 2] = (uint32_t)row;
   };
-  for (auto& kv : key_row) insert(((uint64_t)kv.first << 32) | 0xffffffffu, kv.second);
-  for (auto& kv : pair_row) insert(kv.first, kv.second);
+  for (auto& kv : key_row) insert(kv.first, 0xffffffffu, kv.second);
+  for (auto& kv : pair_row) insert((uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second);
 
   *out = std::move(h);
   return "";

@@ -35,7 +35,7 @@ struct HostTables {
   int32_t rows = 1;    // table rows incl. the neutral row (index rows-1)
   int32_t NS = 0;      // namespaces covered by nsmask
   uint32_t hash_mask = 0;
-  std::vector<uint64_t> hash;    // [hash_mask+1][2]: {label key (pair or key|0xffffffff), row}
+  std::vector<uint32_t> hash;    // [hash_mask+1][4]: {keyId, valId (0xffffffff = the key's "other value" row), row, 0}; empty = {~0,~0,0,0}
   std::vector<uint32_t> table;   // [W][rows][TPpad][2]: {sat, pos}
   std::vector<uint32_t> need;    // [W][TPpad][B]
   std::vector<uint32_t> nsmask;  // [NS][W][TPpad]
@@ -56,11 +56,18 @@ inline int32_t words_per_row(int32_t m) {
   return w < 4 ? 4 : w;
 }
 
-inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; the device uses the same function
-  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
-  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
-  x ^= x >> 31;
-  return x;
+#ifdef __CUDACC__
+#define KT_HOST_DEVICE __host__ __device__ __forceinline__
+#else
+#define KT_HOST_DEVICE inline
+#endif
+// 32-bit mixer of a (keyId, valId) label; the kernels and the table compiler must agree on it.
+KT_HOST_DEVICE uint32_t label_hash(uint32_t key, uint32_t val) {
+  uint32_t h = key * 0x9E3779B1u + val * 0x85EBCA77u;
+  h ^= h >> 16;
+  h *= 0x7feb352du;
+  h ^= h >> 15;
+  return h;
 }
 
 }  // namespace kt

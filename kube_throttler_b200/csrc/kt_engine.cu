@@ -101,7 +101,7 @@ struct kt_ctx {
   int32_t n_ovr = 0;
   SelectorSpec spec;
   HostTables ht;
-  DevBuf d_hash, d_table, d_need, d_nsmask, d_nsw_off, d_nsw_idx;
+  DevBuf d_hash, d_keydir, d_valrow, d_table, d_need, d_nsmask, d_nsw_off, d_nsw_idx;
   DevBuf d_kind, d_tflags, d_thr, d_thr_present, d_thr_cnt, d_ovr_off, d_ovr_begin, d_ovr_end, d_ovr_flags, d_ovr_thr,
       d_ovr_present, d_ovr_cnt;
   bool have_status = false;
@@ -157,6 +157,8 @@ int recompile_tables(kt_ctx* c) {
   if (!e.empty()) return fail(c, KT_ERR_INVALID, "compile_tables: %s", e.c_str());
   int rc;
   if ((rc = upload_vec(c, c->d_hash, c->ht.hash))) return rc;
+  if ((rc = upload_vec(c, c->d_keydir, c->ht.keydir))) return rc;
+  if ((rc = upload_vec(c, c->d_valrow, c->ht.valrow))) return rc;
   if ((rc = upload_vec(c, c->d_table, c->ht.table))) return rc;
   if ((rc = upload_vec(c, c->d_need, c->ht.need))) return rc;
   if ((rc = upload_vec(c, c->d_nsmask, c->ht.nsmask))) return rc;
@@ -170,6 +172,9 @@ TableView table_view(const kt_ctx* c) {
   TableView tb;
   tb.hash = c->d_hash.as<uint4>();
   tb.hash_mask = c->ht.hash_mask;
+  tb.keydir = c->d_keydir.as<uint4>();
+  tb.valrow = c->d_valrow.as<int32_t>();
+  tb.n_keydir = (uint32_t)c->ht.n_keydir;
   tb.table = c->d_table.as<uint32_t>();
   tb.need = c->d_need.as<uint32_t>();
   tb.nsmask = c->d_nsmask.as<uint32_t>();
@@ -284,7 +289,7 @@ void kt_destroy(kt_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->pods) s.release();
-  DevBuf* all[] = {&c->d_hash, &c->d_table, &c->d_need, &c->d_nsmask, &c->d_nsw_off, &c->d_nsw_idx, &c->d_kind, &c->d_tflags, &c->d_thr,
+  DevBuf* all[] = {&c->d_hash, &c->d_keydir, &c->d_valrow, &c->d_table, &c->d_need, &c->d_nsmask, &c->d_nsw_off, &c->d_nsw_idx, &c->d_kind, &c->d_tflags, &c->d_thr,
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
@@ -535,7 +540,10 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
                      c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
     // PDL: overlaps its launch + override merge with the tail of k_reconcile (or of the all-reduce kernel)
-    KT_CUDA(c, launch(c, k_finalize, (unsigned)((M + 63) / 64), 64, 0, /*pdl=*/!tm, tv, M, R, (long long)now, flags,
+    int G = 1;
+    while (G < R + 1) G <<= 1;  // lanes per throttle: resources + the pod count, padded to a power of two
+    const long long lanes = (long long)M * G;
+    KT_CUDA(c, launch(c, k_finalize, (unsigned)((lanes + 127) / 128), 128, 0, /*pdl=*/!tm, tv, M, R, G, (long long)now, flags,
                       c->d_part.as<unsigned long long>(), ov, c->d_check.as<unsigned char>()));
     ++launches;
   }

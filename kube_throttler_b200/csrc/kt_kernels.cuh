@@ -31,6 +31,8 @@ constexpr int kTileReconcile = 128;  // running pods per CTA (one lane per pod)
 constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kSlots = 16;           // per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kCheckStash = 4;       // match words per pending pod kept in shared memory between the two phases
+constexpr int kHeavyPods = 6;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
   const int64_t* labels;    // [L][n]
@@ -42,8 +44,11 @@ struct PodView {
 };
 
 struct TableView {
-  const uint4* hash;        // {keyId, valId, row, 0}; empty = {~0,~0,..}
+  const uint4* hash;        // {keyId, valId, row, 0}; empty = {~0,~0,..}   (fallback for sparse ids)
   uint32_t hash_mask;
+  const uint4* keydir;      // [n_keydir] {other_row, vmin, vcnt (~0: hashed values), off}
+  const int32_t* valrow;    // row or -1
+  uint32_t n_keydir;        // 0: no direct table, every label is hashed
   const uint32_t* table;    // [W][rows][TPpad][2]
   const uint32_t* need;     // [W][TPpad][B]
   const uint32_t* nsmask;   // [NS][W][TPpad]
@@ -106,22 +111,28 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- label -> table row ---------------------------------------------------------------------------
-// label_hash(): 32-bit mixer shared with kt_tables.cc (kt_tables.h).
-
-// Continue a linear probe that did not resolve on its first slot.  Returns the row or -1.
-__device__ __noinline__ int32_t probe_slow(const TableView& tb, uint32_t key, uint32_t val, uint32_t slot) {
+// Exact (key,value) row, else the key's "other value" row, else the neutral row.
+// Fast path: two-level direct dictionary (keydir -> valrow), two dependent loads and no probing.
+// Fallback for sparse ids: open-addressing hash (label_hash() shared with kt_tables.cc), probed serially.
+__device__ __noinline__ int32_t hash_lookup(const TableView& tb, uint32_t key, uint32_t val) {
+  const int32_t neutral = tb.rows - 1;
 #pragma unroll 1
-  while (true) {
-    slot = (slot + 1) & tb.hash_mask;
-    const uint4 e = __ldg(&tb.hash[slot]);
-    if (e.x == key && e.y == val) return (int32_t)e.z;
-    if ((e.x & e.y) == 0xffffffffu) return -1;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t slot = label_hash(key, val) & tb.hash_mask;
+#pragma unroll 1
+    while (true) {
+      const uint4 e = __ldg(&tb.hash[slot]);
+      if (e.x == key && e.y == val) return (int32_t)e.z;
+      if ((e.x & e.y) == 0xffffffffu) break;
+      slot = (slot + 1) & tb.hash_mask;
+    }
+    val = 0xffffffffu;  // second pass: the key's "other value" row
   }
+  return neutral;
 }
 
-// Translate the label slots of one pod (lane) into table rows and park them in shared memory:
-// exact (key,value) row, else the key's "other value" row, else the neutral row.  Both first probes of
-// all eight labels of a chunk are in flight together; only collisions take the serial path.
+// Translate the label slots of one pod (lane) into table rows and park them in shared memory.
+// All slots of a chunk of eight are in flight together (two dependent L1/L2 hits each).
 __device__ __forceinline__ void stage_rowids(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, bool active,
                                              int L, int32_t* s_rowid, int stride) {
   const int32_t neutral = tb.rows - 1;
@@ -130,35 +141,27 @@ __device__ __forceinline__ void stage_rowids(const TableView& tb, const int64_t*
     int64_t lab[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) lab[k] = (active && i0 + k < L) ? __ldg(&labels[(int64_t)(i0 + k) * n + p]) : KT_LABEL_EMPTY;
-    uint4 ea[8], eb[8];
-    uint32_t sa[8], sb[8];
+    uint4 ke[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
-      sa[k] = label_hash(key, val) & tb.hash_mask;
-      sb[k] = label_hash(key, 0xffffffffu) & tb.hash_mask;
-      if (lab[k] != KT_LABEL_EMPTY) {
-        ea[k] = __ldg(&tb.hash[sa[k]]);
-        eb[k] = __ldg(&tb.hash[sb[k]]);
-      } else {
-        ea[k] = eb[k] = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
-      }
+      const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32);
+      ke[k] = make_uint4((uint32_t)neutral, 0u, 0u, 0u);
+      if (key < tb.n_keydir) ke[k] = __ldg(&tb.keydir[key]);
+    }
+    int32_t vr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t d = (uint32_t)lab[k] - ke[k].y;
+      vr[k] = -1;
+      if (d < ke[k].z && ke[k].z != 0xffffffffu) vr[k] = __ldg(&tb.valrow[ke[k].w + d]);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (i0 + k < L) {
         const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
-        int32_t row = neutral;
-        if (lab[k] != KT_LABEL_EMPTY) {
-          int32_t r = -1;
-          if (ea[k].x == key && ea[k].y == val) r = (int32_t)ea[k].z;
-          else if ((ea[k].x & ea[k].y) != 0xffffffffu) r = probe_slow(tb, key, val, sa[k]);
-          if (r < 0) {
-            if (eb[k].x == key && eb[k].y == 0xffffffffu) r = (int32_t)eb[k].z;
-            else if ((eb[k].x & eb[k].y) != 0xffffffffu) r = probe_slow(tb, key, 0xffffffffu, sb[k]);
-          }
-          if (r >= 0) row = r;
-        }
+        int32_t row = vr[k] >= 0 ? vr[k] : (int32_t)ke[k].x;
+        if (lab[k] != KT_LABEL_EMPTY && (tb.n_keydir == 0 || (key < tb.n_keydir && ke[k].z == 0xffffffffu)))
+          row = hash_lookup(tb, key, val);  // sparse ids: rare, serial
         s_rowid[(i0 + k) * stride] = row;
       }
     }
@@ -234,12 +237,20 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
+// Sum of one 64-bit value per lane (mod 2^64) with three 32-bit REDUX: 22+22+20-bit limbs cannot overflow
+// when 32 lanes are added.
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+  const uint32_t lo = __reduce_add_sync(kFull, (uint32_t)v & 0x3fffffu);
+  const uint32_t mi = __reduce_add_sync(kFull, (uint32_t)(v >> 22) & 0x3fffffu);
+  const uint32_t hi = __reduce_add_sync(kFull, (uint32_t)(v >> 44));
+  return (unsigned long long)lo + ((unsigned long long)mi << 22) + ((unsigned long long)hi << 44);
+}
+
 // Shared-memory carve-up of k_reconcile (host and device must agree).
 __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int tile) {
   return (size_t)R * tile * 8 + (size_t)kSlots * R * 32 * 8 + (size_t)L * tile * 4 + (size_t)tile * 4 + (size_t)kSlots * 32 * 4 * 2 +
          (size_t)kSlots * 4;
 }
-__host__ __device__ inline size_t check_smem_bytes(int L, int R, int tile) { return (size_t)R * tile * 8 + (size_t)L * tile * 4; }
 
 // ------------------------------------------------------------------------------------------------
 // k_reconcile: one lane per RUNNING pod.   RT = compile-time bound on R for the register accumulators
@@ -327,22 +338,50 @@ __global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, T
       }
     }
     slot = __shfl_sync(kFull, slot, 0);
-    if (!T) continue;
     const int t = w * 32 + lane;
     if constexpr (RT > 0) {
       unsigned long long acc[RT];
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r] = 0ull;
       uint32_t cnt = 0, pres = 0;
-      while (T) {
-        const int i = wbase_pod + __ffs(T) - 1;
-        T &= T - 1;
-        ++cnt;
-        pres |= s_present[i];
+      // Throttles that matched many of the warp's pods ("everything in the namespace", NotIn, DoesNotExist)
+      // would make one lane walk up to 32 pods while the others idle: those are summed by the whole warp
+      // (lane = pod again, REDUX tree), the sparse rest by their owning lane.
+      const bool is_heavy = __popc(T) > kHeavyPods;
+      uint32_t heavy = __ballot_sync(kFull, is_heavy);
+      if (heavy) {
+        unsigned long long mine[RT];
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
-          if (r < R) acc[r] += (unsigned long long)s_req[r * TILE + i];
+        for (int r = 0; r < RT; ++r) mine[r] = r < R ? (unsigned long long)s_req[r * TILE + tid] : 0ull;
+        const uint32_t mypres = s_present[tid];
+        while (heavy) {
+          const int b = __ffs(heavy) - 1;
+          heavy &= heavy - 1;
+          const uint32_t mask = __shfl_sync(kFull, T, b);  // the pods (lanes) matched by throttle w*32+b
+          const bool in = (mask >> lane) & 1;
+          const uint32_t pr = __reduce_or_sync(kFull, in ? mypres : 0u);
+          if (lane == b) { cnt = __popc(mask); pres = pr; }
+#pragma unroll
+          for (int r = 0; r < RT; ++r)
+            if (r < R) {
+              const unsigned long long v = in ? mine[r] : 0ull;
+              const unsigned long long sum = warp_sum_u64(v);
+              if (lane == b) acc[r] = sum;
+            }
+        }
       }
+      if (!is_heavy) {
+        while (T) {
+          const int i = wbase_pod + __ffs(T) - 1;
+          T &= T - 1;
+          ++cnt;
+          pres |= s_present[i];
+#pragma unroll
+          for (int r = 0; r < RT; ++r)
+            if (r < R) acc[r] += (unsigned long long)s_req[r * TILE + i];
+        }
+      }
+      if (cnt == 0) continue;
       if (slot >= 0) {
         atomicAdd(&s_cnt[slot * 32 + lane], cnt);
         atomicOr(&s_pres[slot * 32 + lane], pres);
@@ -400,151 +439,170 @@ __global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, T
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finalize: one lane per throttle.  Consumes (and re-zeroes) the partial sums.
+// k_finalize: a group of G = 2^g >= R+1 lanes per throttle; lane r < R owns resource r, lane R owns the
+// pod count.  Every Quantity compare of the reconcile tail and of CheckThrottledFor's constants is one
+// lane's scalar work, the per-throttle bitmasks are assembled with a ballot.  Consumes (and re-zeroes)
+// the partial sums.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_finalize(ThrottleView tv, int M, int R, long long now, uint32_t eval_flags,
-                                                 unsigned long long* __restrict__ part, ReconcileView out,
-                                                 unsigned char* __restrict__ check /* [M][16 + 16R] */) {
+__global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, int G, long long now, uint32_t eval_flags,
+                                                  unsigned long long* __restrict__ part, ReconcileView out,
+                                                  unsigned char* __restrict__ check /* [M][16 + 16R] */) {
   pdl_launch_dependents();  // k_check can start matching the pending pods right away
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int t = gid / G, r = gid % G;  // G divides 32: a group never straddles a warp
+  const int gbase = lane - r;          // first lane of this group inside the warp
   const bool given = eval_flags & KT_EVAL_GIVEN_STATUS;
   const bool on_equal = eval_flags & KT_EVAL_ON_EQUAL;
+  const bool in_range = t < M;
+  const bool is_res = in_range && r < R, is_cnt = in_range && r == R;
+  const uint32_t mybit = r < R ? (1u << r) : KT_COUNT_BIT;
+  const size_t col = (size_t)r * M + t;  // resource lanes: index into [R][M] columns
 
-  // ---- everything that does not depend on the running pods: CalculateThreshold(now) ----
-  // merged active overrides REPLACE spec.threshold (throttle_types.go:65-106)
-  long long calc[KT_MAX_RESOURCES];
-  uint32_t calc_present = 0, tflags = 0;
-  long long calc_cnt = 0;
-  bool active_found = false;
-  if (t < M) {
+  // ---- independent of the running pods: CalculateThreshold(now) ----
+  // merged active overrides REPLACE spec.threshold; per resource name the first active override wins
+  // (throttle_types.go:65-106)
+  uint32_t tflags = 0;
+  bool spec_has = false, calc_has = false, active_found = false;
+  long long spec_val = 0, calc_val = 0;
+  if (is_res || is_cnt) {
     tflags = tv.flags[t];
-    calc_present = tv.thr_present[t];
-    calc_cnt = tv.thr_cnt[t];
-    for (int r = 0; r < R; ++r) calc[r] = tv.thr[(size_t)r * M + t];
-    long long ov[KT_MAX_RESOURCES];
-    uint32_t ov_present = 0;
-    long long ov_cnt = 0;
-    for (int r = 0; r < R; ++r) ov[r] = 0;
-    for (int i = tv.ovr_off[t]; i < tv.ovr_off[t + 1]; ++i) {
-      if (tv.ovr_flags[i] & KT_OVR_PARSE_ERROR) continue;          // skipped, reported in Messages by the host
+    spec_has = tv.thr_present[t] & mybit;
+    spec_val = is_res ? tv.thr[col] : tv.thr_cnt[t];
+    bool ov_has = false;
+    long long ov_val = 0;
+    const int o_lo = tv.ovr_off[t], o_hi = tv.ovr_off[t + 1];
+    for (int i = o_lo; i < o_hi; ++i) {
+      if (tv.ovr_flags[i] & KT_OVR_PARSE_ERROR) continue;               // skipped, reported in Messages by the host
       if (!(tv.ovr_begin[i] <= now && now <= tv.ovr_end[i])) continue;  // IsActive: inclusive both ends
       active_found = true;
-      const uint32_t op = tv.ovr_present[i];
-      if (!(ov_present & KT_COUNT_BIT) && (op & KT_COUNT_BIT)) { ov_present |= KT_COUNT_BIT; ov_cnt = tv.ovr_cnt[i]; }
-      for (int r = 0; r < R; ++r)
-        if (((op >> r) & 1) && !((ov_present >> r) & 1)) { ov_present |= 1u << r; ov[r] = tv.ovr_thr[(size_t)r * tv.n_ovr + i]; }
+      if (!ov_has && (tv.ovr_present[i] & mybit)) {
+        ov_has = true;
+        ov_val = is_res ? tv.ovr_thr[(size_t)r * tv.n_ovr + i] : tv.ovr_cnt[i];
+      }
     }
-    if (active_found) {
-      calc_present = ov_present;
-      calc_cnt = ov_cnt;
-      for (int r = 0; r < R; ++r) calc[r] = ov[r];
-    }
+    calc_has = active_found ? ov_has : spec_has;
+    calc_val = active_found ? ov_val : spec_val;
   }
+  // GIVEN_STATUS: what PreFilter sees is the informer copy of .status (throttle_types.go:128-132)
+  bool g_thr_has = false, g_su_has = false, g_st_thr = false;
+  long long g_thr = 0, g_su = 0;
+  if (given && (is_res || is_cnt)) {
+    if (tv.st_calculated[t]) {  // calculatedAt != zero => status.calculatedThreshold.threshold
+      g_thr_has = tv.st_calc_present[t] & mybit;
+      g_thr = is_res ? tv.st_calc_thr[col] : tv.st_calc_cnt[t];
+    } else {
+      g_thr_has = spec_has;
+      g_thr = spec_val;
+    }
+    g_su_has = tv.st_used_present[t] & mybit;
+    g_su = is_res ? tv.st_used[col] : tv.st_used_cnt[t];
+    g_st_thr = tv.st_throttled[t] & mybit;
+  }
+  bool res_has = false;
+  long long res_val = 0;
+  if ((is_res || is_cnt) && tv.reserved_present) {
+    res_has = tv.reserved_present[t] & mybit;
+    if (res_has) res_val = is_res ? (tv.reserved ? tv.reserved[col] : 0) : (tv.reserved_cnt ? tv.reserved_cnt[t] : 0);
+  }
+  const bool is_throttle_kind = in_range ? tv.kind[t] == KT_KIND_THROTTLE : true;
+
   pdl_wait_primary();  // the partial sums of k_reconcile (or the all-reduce) are complete and visible
-  if (t >= M) return;
-  const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
 
-  // ---- used (this pass) ----
-  long long used[KT_MAX_RESOURCES];
-  uint32_t used_present = 0;
-  long long used_cnt = (long long)__ldcg(&part[(size_t)2 * R * M + t]);
-  if (used_cnt > 0) used_present |= KT_COUNT_BIT;  // Counts stays nil with zero counted pods (Q3)
-  for (int r = 0; r < R; ++r) {
-    used[r] = (long long)__ldcg(&part[(size_t)r * M + t]);
-    if (__ldcg(&part[(size_t)(R + r) * M + t]) != 0ull) used_present |= 1u << r;
-  }
-  part[(size_t)2 * R * M + t] = 0ull;
-  for (int r = 0; r < R; ++r) {
-    part[(size_t)r * M + t] = 0ull;
+  // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count ----
+  long long used_val = 0;
+  bool used_has = false;
+  if (is_res) {
+    used_val = (long long)__ldcg(&part[col]);
+    used_has = __ldcg(&part[(size_t)(R + r) * M + t]) != 0ull;
+    part[col] = 0ull;
     part[(size_t)(R + r) * M + t] = 0ull;
+  } else if (is_cnt) {
+    used_val = (long long)__ldcg(&part[(size_t)2 * R * M + t]);
+    used_has = used_val > 0;  // Counts stays nil with zero counted pods (Q3)
+    part[(size_t)2 * R * M + t] = 0ull;
   }
-  if (out.override_active) out.override_active[t] = active_found;
-
-  // ---- status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133) ----
-  uint32_t throttled = 0;
-  if (live) {
-    if ((calc_present & KT_COUNT_BIT) && (used_present & KT_COUNT_BIT) && used_cnt >= calc_cnt) throttled |= KT_COUNT_BIT;
-    for (int r = 0; r < R; ++r)
-      if (((calc_present >> r) & 1) && ((used_present >> r) & 1) && used[r] >= calc[r]) throttled |= 1u << r;
-  }
-  if (out.used) for (int r = 0; r < R; ++r) out.used[(size_t)r * M + t] = used[r];
-  if (out.used_present) out.used_present[t] = used_present;
-  if (out.used_cnt) out.used_cnt[t] = used_cnt;
-  if (out.throttled) out.throttled[t] = throttled;
-  if (out.calc_thr) for (int r = 0; r < R; ++r) out.calc_thr[(size_t)r * M + t] = calc[r];
-  if (out.calc_present) out.calc_present[t] = calc_present;
-  if (out.calc_cnt) out.calc_cnt[t] = calc_cnt;
+  const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
+  // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
+  const bool throttled = live && calc_has && used_has && used_val >= calc_val;
 
   // ---- constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55) ----
-  // Which status does PreFilter see: this pass's (FRESH) or the informer copy (GIVEN)?
-  long long thr[KT_MAX_RESOURCES], su[KT_MAX_RESOURCES];
-  uint32_t thr_present, su_present, st_throttled;
-  long long thr_cnt, su_cnt;
-  if (given) {
-    if (tv.st_calculated[t]) {  // calculatedAt != zero => status.calculatedThreshold.threshold
-      thr_present = tv.st_calc_present[t];
-      thr_cnt = tv.st_calc_cnt[t];
-      for (int r = 0; r < R; ++r) thr[r] = tv.st_calc_thr[(size_t)r * M + t];
-    } else {
-      thr_present = tv.thr_present[t];
-      thr_cnt = tv.thr_cnt[t];
-      for (int r = 0; r < R; ++r) thr[r] = tv.thr[(size_t)r * M + t];
-    }
-    su_present = tv.st_used_present[t];
-    su_cnt = tv.st_used_cnt[t];
-    for (int r = 0; r < R; ++r) su[r] = tv.st_used[(size_t)r * M + t];
-    st_throttled = tv.st_throttled[t];
-  } else {
-    thr_present = calc_present;
-    thr_cnt = calc_cnt;
-    su_present = used_present;
-    su_cnt = used_cnt;
-    for (int r = 0; r < R; ++r) { thr[r] = calc[r]; su[r] = used[r]; }
-    st_throttled = throttled;
-  }
-  const uint32_t res_present = tv.reserved_present ? tv.reserved_present[t] : 0u;
-  const long long res_cnt = (tv.reserved_cnt && (res_present & KT_COUNT_BIT)) ? tv.reserved_cnt[t] : 0;
-  // alreadyUsed = {} + status.used + reserved : nil counts are 0, presence is the union
-  const uint32_t au_present = su_present | res_present;
-  const long long au_cnt = ((su_present & KT_COUNT_BIT) ? su_cnt : 0) + res_cnt;
-  const bool e3 = tv.kind[t] == KT_KIND_THROTTLE ? true : on_equal;  // Q1: Throttle hard-codes true (:143)
+  const bool thr_has = given ? g_thr_has : calc_has;
+  const long long thr = given ? g_thr : calc_val;
+  const bool su_has = given ? g_su_has : used_has;
+  const long long su = given ? g_su : used_val;
+  const bool st_thr = given ? g_st_thr : throttled;
+  // alreadyUsed = {} + status.used + reserved : absent values are 0, presence is the union
+  const bool au_has = su_has || res_has;
+  const long long au = (su_has ? su : 0) + res_val;
+  const bool e3 = is_throttle_kind ? true : on_equal;  // Q1: Throttle hard-codes true (:143)
+  const bool s3 = thr_has && au_has && (e3 ? au >= thr : au > thr);
 
-  CheckHdr h;
-  h.thr_has = thr_present & ~KT_COUNT_BIT;
-  h.m2 = st_throttled & ~KT_COUNT_BIT;
-  h.m3 = 0;
-  h.cntbits = on_equal ? 16u : 0u;
-  long long* thrv = reinterpret_cast<long long*>(check + (size_t)t * (16 + 16 * R) + 16);
-  long long* head = thrv + R;
-  for (int r = 0; r < R; ++r) {
-    const long long au = (((su_present >> r) & 1) ? su[r] : 0) + ((tv.reserved && ((res_present >> r) & 1)) ? tv.reserved[(size_t)r * M + t] : 0);
-    if (((thr_present >> r) & 1) && ((au_present >> r) & 1) && (e3 ? au >= thr[r] : au > thr[r])) h.m3 |= 1u << r;
-    thrv[r] = thr[r];
-    head[r] = thr[r] - au;  // S4: used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+  // ---- per-throttle masks: one ballot each, bit (lane - gbase) = resource r, bit R = count ----
+  const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+  const uint32_t rmask = (R == 32 ? 0xffffffffu : ((1u << R) - 1u));
+  auto group_mask = [&](bool pred) -> uint32_t {
+    const uint32_t g = (__ballot_sync(kFull, pred) >> gbase) & gmask;
+    return (g & rmask) | (((g >> R) & 1u) ? KT_COUNT_BIT : 0u);
+  };
+  const uint32_t m_used = group_mask(used_has);
+  const uint32_t m_throttled = group_mask(throttled);
+  const uint32_t m_calc = group_mask(calc_has);
+  const uint32_t m_thr = group_mask(thr_has);
+  const uint32_t m_st = group_mask(st_thr);
+  const uint32_t m_s3 = group_mask(s3);
+  // count-lane specials of the 4-step check
+  const bool s1c = is_cnt && thr_has && 1 > thr;                                           // S1: pod count 1 > threshold (Q4)
+  const bool s4c = is_cnt && thr_has && (on_equal ? au + 1 >= thr : au + 1 > thr);        // S4 (counts always present: the pod)
+  const uint32_t m_s1c = group_mask(s1c), m_s4c = group_mask(s4c);
+
+  if (is_res) {
+    if (out.used) out.used[col] = used_val;
+    if (out.calc_thr) out.calc_thr[col] = calc_val;
+    long long* thrv = reinterpret_cast<long long*>(check + (size_t)t * (16 + 16 * R) + 16);
+    thrv[r] = thr;
+    thrv[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+  } else if (is_cnt) {
+    if (out.used_cnt) out.used_cnt[t] = used_val;
+    if (out.calc_cnt) out.calc_cnt[t] = calc_val;
+    if (out.used_present) out.used_present[t] = m_used;
+    if (out.throttled) out.throttled[t] = m_throttled;
+    if (out.calc_present) out.calc_present[t] = m_calc;
+    if (out.override_active) out.override_active[t] = active_found;
+    CheckHdr h;
+    h.thr_has = m_thr & ~KT_COUNT_BIT;
+    h.m2 = m_st & ~KT_COUNT_BIT;
+    h.m3 = m_s3 & ~KT_COUNT_BIT;
+    h.cntbits = (on_equal ? 16u : 0u) | ((m_s1c & KT_COUNT_BIT) ? 1u : 0u) | ((m_st & KT_COUNT_BIT) ? 2u : 0u) |
+                ((m_s3 & KT_COUNT_BIT) ? 4u : 0u) | ((m_s4c & KT_COUNT_BIT) ? 8u : 0u);
+    if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
+    *reinterpret_cast<CheckHdr*>(check + (size_t)t * (16 + 16 * R)) = h;
   }
-  if (thr_present & KT_COUNT_BIT) {
-    if (1 > thr_cnt) h.cntbits |= 1u;                                              // S1: pod count 1 > threshold (Q4)
-    if ((au_present & KT_COUNT_BIT) && (e3 ? au_cnt >= thr_cnt : au_cnt > thr_cnt)) h.cntbits |= 4u;  // S3
-    if (on_equal ? au_cnt + 1 >= thr_cnt : au_cnt + 1 > thr_cnt) h.cntbits |= 8u;  // S4 (counts always present: the pod)
-  }
-  if (st_throttled & KT_COUNT_BIT) h.cntbits |= 2u;                                // S2
-  if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
-  *reinterpret_cast<CheckHdr*>(check + (size_t)t * (16 + 16 * R)) = h;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_check: one lane per PENDING pod.  Phase 1 (no dependency on the running pods): selector match ->
-// affectedThrottles bitmap.  Phase 2 (after k_finalize): 4-step CheckThrottledFor per matched pair.
+// affectedThrottles bitmap.  Phase 2 (after k_finalize): 4-step CheckThrottledFor per matched pair; the
+// constants of a word's 32 throttles are staged in shared memory by the warp (lane = throttle) so the
+// per-pair work is shared-memory compares instead of dependent global gathers.
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t check_smem_bytes(int L, int R, int tile) {
+  return (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R) + (size_t)L * tile * 4 + (size_t)kCheckStash * tile * 4;
+}
+
 template <int TPC, int B>
 __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
                                                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                       unsigned char* __restrict__ admit) {
   constexpr int TILE = kTileCheck;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* s_req = reinterpret_cast<long long*>(smem_raw);                     // [R][TILE]
-  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_req + (size_t)R * TILE);       // [L][TILE]
-  const int tid = threadIdx.x;
+  const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                                   // [R][TILE]
+  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);           // [warps][32][rec]
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_chk + (size_t)(TILE / 32) * 32 * rec);      // [L][TILE]
+  uint32_t* s_words = reinterpret_cast<uint32_t*>(s_rowid + (size_t)L * TILE);                // [kCheckStash][TILE]
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * 32 * rec;
   const int64_t tile0 = (int64_t)blockIdx.x * TILE;
   const int Wp = tb.Wp;
   {
@@ -574,64 +632,81 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 
   // ---- phase 1: affectedThrottles (throttle_controller.go:248-269) ----
-  uint32_t nzw = 0;  // does any word match at all?
+  int first = 0x7fffffff;  // first word with a match
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
     const int w = __ldg(&tb.nsw_idx[j]);
     const uint32_t word = eval_word<TPC, B>(tb, s_rowid + tid, TILE, L, ns, w);
-    if (word) { bitmap[p * Wp + w] = word; nzw = 1; }
+    if (j - lo < kCheckStash) s_words[(j - lo) * TILE + tid] = word;
+    if (word) {
+      bitmap[p * Wp + w] = word;
+      if (first == 0x7fffffff) first = j;
+    }
   }
   pdl_wait_primary();  // k_finalize has written the check constants
 
-  // ---- phase 2: CheckThrottledFor per affected throttle ----
+  // ---- phase 2: CheckThrottledFor per affected throttle; words in ascending order, warp-uniform ----
   unsigned char ok = 1;
-  if (nzw) {
-    const size_t stride = 16 + 16 * (size_t)R;
+  int j = first == 0x7fffffff ? hi : first;
+  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
 #pragma unroll 1
-    for (int j = lo; j < hi; ++j) {
-      const int w = __ldg(&tb.nsw_idx[j]);
-      uint32_t word = bitmap[p * Wp + w];  // this lane's own store (or the zero fill, ordered by the barrier)
-      if (!word) continue;
-      uint32_t c0 = 0, c1 = 0;
-      while (word) {
-        const int b = __ffs(word) - 1;
-        word &= word - 1;
-        const int t = w * 32 + b;
-        const unsigned char* cb = check + (size_t)t * stride;
-        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(cb));
-        const long long* thrv = reinterpret_cast<const long long*>(cb + 16);
-        const long long* head = thrv + R;
-        const uint32_t cand = nz & hq.x;
-        uint32_t code;
-        // S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod)
-        bool s1 = hq.w & 1u;
-        for (uint32_t c = cand; c && !s1;) {
+  while (true) {
+    const int w = __reduce_min_sync(kFull, cur);
+    if (w == 0x7fffffff) break;
+    uint32_t word = 0;
+    if (cur == w) {
+      word = (j - lo < kCheckStash) ? s_words[(j - lo) * TILE + tid] : bitmap[p * Wp + w];  // own store, ordered by the barrier
+      ++j;
+      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+    }
+    const uint32_t any = __reduce_or_sync(kFull, word);
+    if (!any) continue;
+    __syncwarp();
+    if ((any >> lane) & 1) {  // lane = throttle: stage its record
+      const uint4* src = reinterpret_cast<const uint4*>(check + (size_t)(w * 32 + lane) * rec);
+      uint4* dst = reinterpret_cast<uint4*>(my_chk + (size_t)lane * rec);
+      for (int q = 0; q <= R; ++q) dst[q] = __ldcg(&src[q]);
+    }
+    __syncwarp();
+    if (!word) continue;
+    uint32_t c0 = 0, c1 = 0;
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      const unsigned char* cb = my_chk + (size_t)b * rec;
+      const uint4 hq = *reinterpret_cast<const uint4*>(cb);
+      const long long* thrv = reinterpret_cast<const long long*>(cb + 16);
+      const long long* head = thrv + R;
+      const uint32_t cand = nz & hq.x;
+      uint32_t code;
+      // S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod)
+      bool s1 = hq.w & 1u;
+      for (uint32_t c = cand; c && !s1;) {
+        const int r = __ffs(c) - 1;
+        c &= c - 1;
+        s1 = s_req[r * TILE + tid] > thrv[r];
+      }
+      if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
+      else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
+      else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
+      else {
+        bool s4 = hq.w & 8u;                                         // S4 used+pod+reserved
+        const bool ge = hq.w & 16u;
+        for (uint32_t c = cand; c && !s4;) {
           const int r = __ffs(c) - 1;
           c &= c - 1;
-          s1 = s_req[r * TILE + tid] > __ldg(&thrv[r]);
+          const long long v = s_req[r * TILE + tid];
+          const long long hd = head[r];
+          s4 = ge ? v >= hd : v > hd;
         }
-        if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
-        else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
-        else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
-        else {
-          bool s4 = hq.w & 8u;                                         // S4 used+pod+reserved
-          const bool ge = hq.w & 16u;
-          for (uint32_t c = cand; c && !s4;) {
-            const int r = __ffs(c) - 1;
-            c &= c - 1;
-            const long long v = s_req[r * TILE + tid];
-            const long long hd = __ldg(&head[r]);
-            s4 = ge ? v >= hd : v > hd;
-          }
-          code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
-        }
-        if (code) ok = 0;
-        if (b < 16) c0 |= code << (2 * b);
-        else c1 |= code << (2 * (b - 16));
+        code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
       }
-      if (c0) codes[p * 2 * Wp + 2 * w] = c0;
-      if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+      if (code) ok = 0;
+      if (b < 16) c0 |= code << (2 * b);
+      else c1 |= code << (2 * (b - 16));
     }
+    if (c0) codes[p * 2 * Wp + 2 * w] = c0;
+    if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
   }
   if (valid) admit[p] = ok;
 }

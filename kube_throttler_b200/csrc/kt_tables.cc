@@ -243,6 +243,37 @@ std::string compile_tables(const kt_limits& lim, const SelectorSpec& s, int32_t 
   for (auto& kv : key_row) insert(kv.first, 0xffffffffu, kv.second);
   for (auto& kv : pair_row) insert((uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second);
 
+  // ---- two-level direct dictionary ---------------------------------------------------------------
+  // key ids small enough -> one keydir entry per id up to the largest mentioned one; per key the mentioned
+  // value ids either form a compact range (direct valrow slice) or stay in the hash (vcnt = ~0).
+  h.n_keydir = 0;
+  h.keydir.clear();
+  h.valrow.clear();
+  if (!key_row.empty() && key_row.rbegin()->first < kKeyDirMax) {
+    const uint32_t nk = key_row.rbegin()->first + 1;
+    h.n_keydir = (int32_t)nk;
+    h.keydir.assign((size_t)nk * 4, 0);
+    for (uint32_t k = 0; k < nk; ++k) h.keydir[4 * (size_t)k] = (uint32_t)(rows - 1);  // unmentioned key: neutral row, no values
+    for (auto& kv : key_row) {
+      const uint32_t k = kv.first;
+      uint32_t vmin = 0xffffffffu, vmax = 0, cnt = 0;
+      for (const RowRef& rr : rows_of_key[k])
+        if (!rr.other) { vmin = std::min(vmin, rr.val); vmax = std::max(vmax, rr.val); ++cnt; }
+      uint32_t* e = &h.keydir[4 * (size_t)k];
+      e[0] = (uint32_t)kv.second;
+      if (cnt == 0) continue;  // only Exists / DoesNotExist on this key
+      const uint64_t span = (uint64_t)vmax - vmin + 1;
+      if (span > (uint64_t)cnt * 4 + 64) { e[2] = 0xffffffffu; continue; }  // sparse value ids: hashed
+      e[1] = vmin;
+      e[2] = (uint32_t)span;
+      e[3] = (uint32_t)h.valrow.size();
+      h.valrow.resize(h.valrow.size() + span, -1);
+      for (const RowRef& rr : rows_of_key[k])
+        if (!rr.other) h.valrow[e[3] + (rr.val - vmin)] = rr.row;
+    }
+  }
+  if (h.valrow.empty()) h.valrow.push_back(-1);
+
   *out = std::move(h);
   return "";
 }

@@ -36,6 +36,13 @@ struct HostTables {
   int32_t NS = 0;      // namespaces covered by nsmask
   uint32_t hash_mask = 0;
   std::vector<uint32_t> hash;    // [hash_mask+1][4]: {keyId, valId (0xffffffff = the key's "other value" row), row, 0}; empty = {~0,~0,0,0}
+  // Two-level direct dictionary (the fast path; dictionary ids handed out by a packer are small and dense):
+  //   keydir[keyId] = {other_row, vmin, vcnt, off}; vcnt == 0xffffffff: this key's values are looked up in `hash`
+  //   valrow[off + (valId - vmin)] = row, or -1 for "a value no requirement mentions" (=> other_row)
+  // n_keydir == 0 (some mentioned keyId >= kKeyDirMax): every label goes through `hash`.
+  int32_t n_keydir = 0;
+  std::vector<uint32_t> keydir;  // [n_keydir][4]
+  std::vector<int32_t> valrow;
   std::vector<uint32_t> table;   // [W][rows][TPpad][2]: {sat, pos}
   std::vector<uint32_t> need;    // [W][TPpad][B]
   std::vector<uint32_t> nsmask;  // [NS][W][TPpad]
@@ -49,6 +56,8 @@ std::string copy_selector_spec(int32_t m, const kt_throttle_cols* cols, const kt
 // Builds the tables.  ns_labels: [LN][n_ns] (may be null when n_ns == 0).
 std::string compile_tables(const kt_limits& lim, const SelectorSpec& spec, int32_t n_ns, const int64_t* ns_labels,
                            HostTables* out);
+
+constexpr uint32_t kKeyDirMax = 1u << 16;  // direct key table only for key ids below this
 
 inline int32_t words_per_row(int32_t m) {
   int32_t w = (m + 31) / 32;

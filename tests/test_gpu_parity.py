@@ -57,6 +57,9 @@ def test_c1_example(kt, oracle):
     dict(config="C3", m=300, n=6000, p=800),
     dict(config="C3", m=1000, n=20000, p=2000),
     dict(config="C4", m=500, n=8000, p=1000),
+    dict(config="C3", m=1000, n=20000, p=2000, sort_by_namespace=False),  # > kSlots distinct words per CTA: direct REDs
+    dict(config="C2", m=150, n=4000, p=600, R=12),                        # R > 8: shared-memory accumulation variant
+    dict(config="C2", m=40, n=70, p=33, R=1),                             # ragged: partial tiles, partial last word
 ])
 def test_scaled_configs(kt, oracle, kw):
     kw = dict(kw)
@@ -64,6 +67,35 @@ def test_scaled_configs(kt, oracle, kw):
     got, want = run_both(kt, oracle, snap)
     assert_same(snap, got, want)
     assert got.match_matrix("pending", snap.m).sum() > 0
+
+
+def _remap_label_ids(snap, kf, vf):
+    """Re-number label key / value dictionary ids everywhere they occur (pods, namespaces, selectors)."""
+    def remap(lab):
+        key, val = lab >> 32, lab & 0xFFFFFFFF
+        return np.where(lab == abi.LABEL_EMPTY, abi.LABEL_EMPTY, (kf(key) << 32) | vf(val)).astype(np.int64)
+    for pods in (snap.running, snap.pending):
+        pods.labels = np.ascontiguousarray(remap(pods.labels))
+    snap.ns_labels = np.ascontiguousarray(remap(snap.ns_labels))
+    snap.req_key = kf(snap.req_key.astype(np.int64)).astype(np.uint32)
+    snap.req_vals = vf(snap.req_vals.astype(np.int64)).astype(np.uint32)
+    return snap.normalize()
+
+
+@pytest.mark.parametrize("mode", ["sparse_keys", "sparse_values"])
+def test_sparse_dictionary_ids(kt, oracle, mode):
+    """Label ids are opaque: ids too sparse for the direct key/value tables take the hashed lookup."""
+    snap = synth.generate("C3", m=300, n=6000, p=800)
+    base = kt.evaluate_snapshot(snap)
+    if mode == "sparse_keys":  # key ids beyond the direct key table: every label is hashed
+        snap = _remap_label_ids(snap, lambda k: k * 7919 + 70000, lambda v: v * 1009 + 5)
+    else:                      # small key ids, value ids spread out: per-key hashed values
+        snap = _remap_label_ids(snap, lambda k: k, lambda v: v * 1000003 % (1 << 31))
+    got, want = run_both(kt, oracle, snap)
+    assert_same(snap, got, want)
+    # a pure renaming of ids must not change any decision
+    np.testing.assert_array_equal(got.codes, base.codes)
+    np.testing.assert_array_equal(got.used, base.used)
 
 
 def test_on_equal_flag(kt, oracle):

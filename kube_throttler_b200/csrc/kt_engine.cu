@@ -173,7 +173,7 @@ TableView table_view(const kt_ctx* c) {
   tb.hash = c->d_hash.as<uint4>();
   tb.hash_mask = c->ht.hash_mask;
   tb.keydir = c->d_keydir.as<uint4>();
-  tb.valrow = c->d_valrow.as<int32_t>();
+  tb.valrow = c->d_valrow.as<uint32_t>();
   tb.n_keydir = (uint32_t)c->ht.n_keydir;
   tb.table = c->d_table.as<uint32_t>();
   tb.need = c->d_need.as<uint32_t>();
@@ -216,39 +216,48 @@ cudaError_t launch(kt_ctx* c, void (*kern)(KArgs...), unsigned blocks, unsigned 
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-// Kernel variant dispatch: planes per chunk in {1,2}, counter bits in {2,6}; k_reconcile additionally on
-// the register-accumulator bound RT in {4, 8, 0 (= any R, shared-memory accumulation)}.
-template <int TPC, int B, int RT>
+// Kernel variant dispatch.  Fast family (label rows in registers): L <= 8 and counter bits B = 2, with the
+// register accumulators sized for R <= 4 / R <= 8.  General family (rows in shared memory, shared-memory
+// accumulation): any L <= 32, R <= 31, B in {2, 6}.  Both come for 1 or 2 term planes per table entry.
+int reconcile_slots(const kt_ctx* c) {
+  int s = c->ht.max_ns_words + 2;  // a tile usually spans one or two namespaces
+  if (s < 4) s = 4;
+  if (s > kMaxSlots) s = kMaxSlots;
+  return s;
+}
+template <int TPC, int B, int RT, bool REG>
 cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
-  const int L = c->lim.label_slots, R = c->lim.n_resources;
-  return launch(c, k_reconcile<TPC, B, RT>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, kTileReconcile), false, pv, tb, L, R,
+  const int L = c->lim.label_slots, R = c->lim.n_resources, S = reconcile_slots(c);
+  return launch(c, k_reconcile<TPC, B, RT, REG>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, S, REG, kTileReconcile), false, pv, tb, L, R, S,
                 c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), c->d_part.as<unsigned long long>());
 }
-template <int TPC, int B>
+template <int TPC, int B, bool REG>
 cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
-  return launch(c, k_check<TPC, B>, blocks, kTileCheck, check_smem_bytes(L, R, kTileCheck), pdl, pv, tb, L, R,
+  return launch(c, k_check<TPC, B, REG>, blocks, kTileCheck, check_smem_bytes(L, R, REG, kTileCheck), pdl, pv, tb, L, R,
                 (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
                 c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>());
 }
 cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
   const int R = c->lim.n_resources;
-#define KT_RT(TPC, B)                                                        \
-  (R <= 4 ? launch_reconcile<TPC, B, 4>(c, pv, tb, blocks)                   \
-          : R <= 8 ? launch_reconcile<TPC, B, 8>(c, pv, tb, blocks) : launch_reconcile<TPC, B, 0>(c, pv, tb, blocks))
-  if (t1 && b2) return KT_RT(1, 2);
-  if (t1) return KT_RT(1, 6);
-  if (b2) return KT_RT(2, 2);
-  return KT_RT(2, 6);
-#undef KT_RT
+  const bool fast = c->lim.label_slots <= 8 && b2 && R <= 8;
+  if (fast) {
+    if (t1) return R <= 4 ? launch_reconcile<1, 2, 4, true>(c, pv, tb, blocks) : launch_reconcile<1, 2, 8, true>(c, pv, tb, blocks);
+    return R <= 4 ? launch_reconcile<2, 2, 4, true>(c, pv, tb, blocks) : launch_reconcile<2, 2, 8, true>(c, pv, tb, blocks);
+  }
+  if (t1 && b2) return launch_reconcile<1, 2, 0, false>(c, pv, tb, blocks);
+  if (t1) return launch_reconcile<1, 6, 0, false>(c, pv, tb, blocks);
+  if (b2) return launch_reconcile<2, 2, 0, false>(c, pv, tb, blocks);
+  return launch_reconcile<2, 6, 0, false>(c, pv, tb, blocks);
 }
 cudaError_t dispatch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
-  if (t1 && b2) return launch_check<1, 2>(c, pv, tb, blocks, pdl);
-  if (t1) return launch_check<1, 6>(c, pv, tb, blocks, pdl);
-  if (b2) return launch_check<2, 2>(c, pv, tb, blocks, pdl);
-  return launch_check<2, 6>(c, pv, tb, blocks, pdl);
+  if (c->lim.label_slots <= 8 && b2) return t1 ? launch_check<1, 2, true>(c, pv, tb, blocks, pdl) : launch_check<2, 2, true>(c, pv, tb, blocks, pdl);
+  if (t1 && b2) return launch_check<1, 2, false>(c, pv, tb, blocks, pdl);
+  if (t1) return launch_check<1, 6, false>(c, pv, tb, blocks, pdl);
+  if (b2) return launch_check<2, 2, false>(c, pv, tb, blocks, pdl);
+  return launch_check<2, 6, false>(c, pv, tb, blocks, pdl);
 }
 
 }  // namespace
@@ -344,7 +353,14 @@ int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const 
   if (rc) return rc;
   PodStore& s = c->pods[kind];
   const int L = c->lim.label_slots, R = c->lim.n_resources;
-  if ((rc = upload(c, s.labels, labels, (size_t)L * n))) return rc;
+  // label columns are padded to a multiple of eight slots with KT_LABEL_EMPTY (all bytes 0xFF): the kernels
+  // translate labels in unpredicated chunks of eight
+  const int Lpad = (L + 7) & ~7;
+  KT_CUDA(c, s.labels.reserve((size_t)Lpad * n * 8 + 16));
+  if (n) {
+    KT_CUDA(c, cudaMemcpyAsync(s.labels.p, labels, (size_t)L * n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (Lpad > L) KT_CUDA(c, cudaMemsetAsync(s.labels.as<int64_t>() + (size_t)L * n, 0xFF, (size_t)(Lpad - L) * n * 8, c->stream));
+  }
   if ((rc = upload(c, s.req, req, (size_t)R * n))) return rc;
   if ((rc = upload(c, s.present, present, (size_t)n))) return rc;
   if ((rc = upload(c, s.flags, flags, (size_t)n))) return rc;

@@ -29,7 +29,7 @@ namespace kt {
 
 constexpr int kTileReconcile = 128;  // running pods per CTA (one lane per pod)
 constexpr int kTileCheck = 64;       // pending pods per CTA
-constexpr int kSlots = 16;           // per-CTA accumulator slots (one per distinct 32-throttle word)
+constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kCheckStash = 4;       // match words per pending pod kept in shared memory between the two phases
 constexpr int kHeavyPods = 6;        // a throttle matching more pods of a warp than this is summed by the whole warp
@@ -46,8 +46,8 @@ struct PodView {
 struct TableView {
   const uint4* hash;        // {keyId, valId, row, 0}; empty = {~0,~0,..}   (fallback for sparse ids)
   uint32_t hash_mask;
-  const uint4* keydir;      // [n_keydir] {other_row, vmin, vcnt (~0: hashed values), off}
-  const int32_t* valrow;    // row or -1
+  const uint4* keydir;      // [n_keydir + 1] {other roff, vmin, vcnt, off (~0: hashed values)}; [n_keydir] = unmentioned key
+  const uint32_t* valrow;   // roff or kOtherRoff; [0] = kOtherRoff
   uint32_t n_keydir;        // 0: no direct table, every label is hashed
   const uint32_t* table;    // [W][rows][TPpad][2]
   const uint32_t* need;     // [W][TPpad][B]
@@ -114,69 +114,105 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 // Exact (key,value) row, else the key's "other value" row, else the neutral row.
 // Fast path: two-level direct dictionary (keydir -> valrow), two dependent loads and no probing.
 // Fallback for sparse ids: open-addressing hash (label_hash() shared with kt_tables.cc), probed serially.
-__device__ __noinline__ int32_t hash_lookup(const TableView& tb, uint32_t key, uint32_t val) {
-  const int32_t neutral = tb.rows - 1;
+__device__ __noinline__ int32_t hash_lookup(const uint4* __restrict__ hash, uint32_t hash_mask, int32_t neutral, uint32_t key, uint32_t val) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-    uint32_t slot = label_hash(key, val) & tb.hash_mask;
+    uint32_t slot = label_hash(key, val) & hash_mask;
 #pragma unroll 1
     while (true) {
-      const uint4 e = __ldg(&tb.hash[slot]);
+      const uint4 e = __ldg(&hash[slot]);
       if (e.x == key && e.y == val) return (int32_t)e.z;
       if ((e.x & e.y) == 0xffffffffu) break;
-      slot = (slot + 1) & tb.hash_mask;
+      slot = (slot + 1) & hash_mask;
     }
     val = 0xffffffffu;  // second pass: the key's "other value" row
   }
   return neutral;
 }
 
-// Translate the label slots of one pod (lane) into table rows and park them in shared memory.
-// All slots of a chunk of eight are in flight together (two dependent L1/L2 hits each).
-__device__ __forceinline__ void stage_rowids(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, bool active,
-                                             int L, int32_t* s_rowid, int stride) {
-  const int32_t neutral = tb.rows - 1;
+// Table rows travel as BYTE offsets inside one 32-throttle word slice of the match table ("roff").
+// keydir / valrow hold roffs too; kOtherRoff in valrow means "a value no requirement mentions".
+constexpr uint32_t kOtherRoff = 0xfffffffeu;
+
+// Where a lane keeps the roffs of its pod's labels: registers when L <= 8 (the common shape), else a
+// shared-memory column.
+template <bool REG>
+struct PodRows;
+template <>
+struct PodRows<true> {
+  uint32_t off[8];
+  __device__ __forceinline__ void init(int32_t*, int, int) {}
+};
+template <>
+struct PodRows<false> {
+  uint32_t* col;  // this lane's column: col[i * stride]
+  int stride;
+  __device__ __forceinline__ void init(int32_t* base, int tid, int tile) { col = reinterpret_cast<uint32_t*>(base) + tid; stride = tile; }
+};
+
+// Translate eight label slots (one chunk) of a pod row.  No predicates: the device label columns are
+// padded to a multiple of eight slots with KT_LABEL_EMPTY, keydir has a sentinel entry at [n_keydir]
+// and valrow a sentinel at [0], so every load is unconditional and the addresses are one IMAD.WIDE each.
+__device__ __forceinline__ void translate8(const TableView& tb, const int64_t* __restrict__ lp, int64_t n, uint32_t (&out)[8]) {
+  int64_t lab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    lab[k] = __ldg(lp);
+    lp += n;
+  }
+  uint4 ke[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32);
+    ke[k] = __ldg(&tb.keydir[min(key, tb.n_keydir)]);  // {other roff | hashed flag in w, vmin, vcnt, off}
+  }
+  uint32_t vr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t d = (uint32_t)lab[k] - ke[k].y;
+    vr[k] = __ldg(&tb.valrow[d < ke[k].z ? ke[k].w + d : 0u]);  // valrow[0] == kOtherRoff
+  }
+  uint32_t hashed = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    out[k] = vr[k] != kOtherRoff ? vr[k] : ke[k].x;
+    hashed |= ke[k].w;
+  }
+  if (tb.n_keydir == 0 || (hashed >> 31)) {  // offsets never reach 2^31; the hashed flag is w = ~0  // sparse dictionary ids: rare, serial
+    const uint32_t row_bytes = (uint32_t)tb.TPpad * 8u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
+      if (lab[k] != KT_LABEL_EMPTY && (tb.n_keydir == 0 || ke[k].w == 0xffffffffu))
+        out[k] = (uint32_t)hash_lookup(tb.hash, tb.hash_mask, tb.rows - 1, key, val) * row_bytes;
+    }
+  }
+}
+
+// labels: device columns [Lpad][n] with Lpad = L rounded up to 8.
+template <bool REG>
+__device__ __forceinline__ void stage_rows(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, int L, PodRows<REG>& rows) {
+  if constexpr (REG) {
+    translate8(tb, labels + p, n, rows.off);
+  } else {
 #pragma unroll 1
-  for (int i0 = 0; i0 < L; i0 += 8) {
-    int64_t lab[8];
+    for (int i0 = 0; i0 < L; i0 += 8) {
+      uint32_t o[8];
+      translate8(tb, labels + (int64_t)i0 * n + p, n, o);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) lab[k] = (active && i0 + k < L) ? __ldg(&labels[(int64_t)(i0 + k) * n + p]) : KT_LABEL_EMPTY;
-    uint4 ke[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32);
-      ke[k] = make_uint4((uint32_t)neutral, 0u, 0u, 0u);
-      if (key < tb.n_keydir) ke[k] = __ldg(&tb.keydir[key]);
-    }
-    int32_t vr[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t d = (uint32_t)lab[k] - ke[k].y;
-      vr[k] = -1;
-      if (d < ke[k].z && ke[k].z != 0xffffffffu) vr[k] = __ldg(&tb.valrow[ke[k].w + d]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (i0 + k < L) {
-        const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32), val = (uint32_t)lab[k];
-        int32_t row = vr[k] >= 0 ? vr[k] : (int32_t)ke[k].x;
-        if (lab[k] != KT_LABEL_EMPTY && (tb.n_keydir == 0 || (key < tb.n_keydir && ke[k].z == 0xffffffffu)))
-          row = hash_lookup(tb, key, val);  // sparse ids: rare, serial
-        s_rowid[(i0 + k) * stride] = row;
-      }
+      for (int k = 0; k < 8; ++k) rows.col[(i0 + k) * rows.stride] = o[k];  // the column has Lpad entries
     }
   }
 }
 
 // Match word w (32 throttles) of one pod: OR over term planes of
 //   AND_labels sat  &  (count of positive keys present == need)  &  namespace mask.
-// s_rowid points at this lane's column of the staged rows (stride = pods per CTA).
-template <int TPC, int B>
-__device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t* s_rowid, int stride, int L, int ns, int w) {
+// Unmentioned / empty labels point at the neutral row (sat = ~0, pos = 0): no branches.
+template <int TPC, int B, bool REG>
+__device__ __forceinline__ uint32_t eval_word(const TableView& tb, const PodRows<REG>& rows, int Lpad, int ns, int w) {
   uint32_t result = 0;
-  const int32_t neutral = tb.rows - 1;
-  const size_t row_stride = (size_t)tb.TPpad * 2;
-  const uint32_t* wbase = tb.table + (size_t)w * tb.rows * row_stride;
+  const uint32_t row_bytes = (uint32_t)tb.TPpad * 8u;
+  const unsigned char* wbase = reinterpret_cast<const unsigned char*>(tb.table) + (size_t)w * tb.rows * row_bytes;
   const uint32_t* nsm = tb.nsmask + ((size_t)ns * tb.W + w) * tb.TPpad;
   const uint32_t* need = tb.need + (size_t)w * tb.TPpad * B;
 #pragma unroll 1
@@ -188,31 +224,34 @@ __device__ __forceinline__ uint32_t eval_word(const TableView& tb, const int32_t
 #pragma unroll
       for (int b = 0; b < B; ++b) cnt[s][b] = 0;
     }
-#pragma unroll 8
-    for (int i = 0; i < L; ++i) {
-      const int32_t rid = s_rowid[i * stride];
-      if (rid != neutral) {  // the neutral row is sat=~0, pos=0: nothing to fold in
-        const uint32_t* e = wbase + (size_t)rid * row_stride + s0 * 2;
-        uint32_t v[TPC * 2];
-        if constexpr (TPC == 2) {
-          uint4 q = __ldg(reinterpret_cast<const uint4*>(e));
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
-          uint2 q = __ldg(reinterpret_cast<const uint2*>(e));
-          v[0] = q.x; v[1] = q.y;
-        }
+    auto fold = [&](uint32_t off) {
+      const unsigned char* e = wbase + off + s0 * 8;
+      uint32_t v[TPC * 2];
+      if constexpr (TPC == 2) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(e));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(e));
+        v[0] = q.x; v[1] = q.y;
+      }
 #pragma unroll
-        for (int s = 0; s < TPC; ++s) {
-          sat[s] &= v[2 * s];
-          uint32_t carry = v[2 * s + 1];  // ripple-add one bit into the bit-sliced counter
+      for (int s = 0; s < TPC; ++s) {
+        sat[s] &= v[2 * s];
+        uint32_t carry = v[2 * s + 1];  // ripple-add one bit into the bit-sliced counter
 #pragma unroll
-          for (int b = 0; b < B; ++b) {
-            uint32_t t = cnt[s][b] & carry;
-            cnt[s][b] ^= carry;
-            carry = t;
-          }
+        for (int b = 0; b < B; ++b) {
+          const uint32_t t = cnt[s][b] & carry;
+          cnt[s][b] ^= carry;
+          carry = t;
         }
       }
+    };
+    if constexpr (REG) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) fold(rows.off[i]);
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < Lpad; ++i) fold(rows.col[i * rows.stride]);
     }
 #pragma unroll
     for (int s = 0; s < TPC; ++s) {
@@ -246,64 +285,73 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return (unsigned long long)lo + ((unsigned long long)mi << 22) + ((unsigned long long)hi << 44);
 }
 
-// Shared-memory carve-up of k_reconcile (host and device must agree).
-__host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int tile) {
-  return (size_t)R * tile * 8 + (size_t)kSlots * R * 32 * 8 + (size_t)L * tile * 4 + (size_t)tile * 4 + (size_t)kSlots * 32 * 4 * 2 +
-         (size_t)kSlots * 4;
+// Shared-memory carve-up of k_reconcile (host and device must agree).  S = accumulator slots.
+__host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool reg_rows, int tile) {
+  return (size_t)R * tile * 8 + (size_t)S * R * 32 * 8 + (reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4) + (size_t)tile * 4 + (size_t)S * 32 * 4 * 2 +
+         (size_t)S * 4;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_reconcile: one lane per RUNNING pod.   RT = compile-time bound on R for the register accumulators
-// (RT == 0: any R, accumulate straight into shared memory).
+// k_reconcile: one lane per RUNNING pod.
+//   RT  compile-time bound on R for the register accumulators (0: any R, accumulate in shared memory)
+//   REG label rows in registers (L <= 8) or in a shared-memory column (any L)
+//   S   per-CTA accumulator slots, one per distinct 32-throttle word the tile touches (host: from the
+//       largest per-namespace word list); words beyond S go straight to HBM
 // ------------------------------------------------------------------------------------------------
-template <int TPC, int B, int RT>
-__global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, TableView tb, int L, int R, uint32_t* __restrict__ bitmap,
-                                                              unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
+template <int TPC, int B, int RT, bool REG>
+__global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, TableView tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
+                                                                 unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
   constexpr int TILE = kTileReconcile;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* s_req = reinterpret_cast<long long*>(smem_raw);                                  // [R][TILE], 0 where absent
-  unsigned long long* s_used = reinterpret_cast<unsigned long long*>(s_req + (size_t)R * TILE);  // [kSlots][R][32]
-  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_used + (size_t)kSlots * R * 32);            // [L][TILE]
-  uint32_t* s_present = reinterpret_cast<uint32_t*>(s_rowid + (size_t)L * TILE);              // [TILE]
-  uint32_t* s_cnt = s_present + TILE;                                                          // [kSlots][32]
-  uint32_t* s_pres = s_cnt + kSlots * 32;                                                      // [kSlots][32]
-  int* s_key = reinterpret_cast<int*>(s_pres + kSlots * 32);                                  // [kSlots] word index or -1
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                                     // [R][TILE], 0 where absent
+  unsigned long long* s_used = reinterpret_cast<unsigned long long*>(s_req + (size_t)R * TILE);  // [S][R][32]
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_used + (size_t)S * R * 32);                    // [L][TILE] (!REG)
+  uint32_t* s_present = reinterpret_cast<uint32_t*>(s_rowid + (REG ? 0 : (size_t)((L + 7) & ~7) * TILE));     // [TILE]
+  uint32_t* s_cnt = s_present + TILE;                                                            // [S][32]
+  uint32_t* s_pres = s_cnt + S * 32;                                                             // [S][32]
+  int* s_key = reinterpret_cast<int*>(s_pres + S * 32);                                          // [S] word index or -1
 
   pdl_launch_dependents();  // k_finalize / k_check may be scheduled; they wait for our completion where they need it
 
   const int tid = threadIdx.x, lane = tid & 31, wbase_pod = tid & ~31;
   const int64_t tile0 = (int64_t)blockIdx.x * TILE;
   const int Wp = tb.Wp;
+  const int Lpad = (L + 7) & ~7;
+  const int64_t p = tile0 + tid;
+  const bool valid = p < pods.n;
+  const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
+  // ---- all of the pod row's loads are issued before anything waits on them ----
+  const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
+  const int ns = __ldg(&pods.ns[pc]);
+  const uint32_t present = __ldg(&pods.present[pc]);
+  PodRows<REG> rows;
+  rows.init(s_rowid, tid, TILE);
+  {  // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
+    const int64_t* rp = pods.req + pc;
+    for (int r = 0; r < R; ++r) {
+      const long long v = __ldg(rp);
+      rp += pods.n;
+      s_req[r * TILE + tid] = ((present >> r) & 1) ? v : 0;
+    }
+    s_present[tid] = present & ~KT_COUNT_BIT;
+  }
+  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
   {  // zero the tile's bitmap rows (contiguous: pod-major) and the CTA accumulators
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* dst = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
-    const int64_t nvec = rows_here * (Wp / 4);
-    for (int64_t i = tid; i < nvec; i += TILE) dst[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kSlots * R * 32; i += TILE) s_used[i] = 0ull;
-    for (int i = tid; i < kSlots * 32; i += TILE) { s_cnt[i] = 0u; s_pres[i] = 0u; }
-    if (tid < kSlots) s_key[tid] = -1;
+    const int nvec = (int)rows_here * (Wp / 4);
+    for (int i = tid; i < nvec; i += TILE) dst[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < S * R * 32; i += TILE) s_used[i] = 0ull;
+    for (int i = tid; i < S * 32; i += TILE) { s_cnt[i] = 0u; s_pres[i] = 0u; }
+    if (tid < S) s_key[tid] = -1;
   }
-  const int64_t p = tile0 + tid;
-  const bool valid = p < pods.n;
-  const uint32_t flags = valid ? __ldg(&pods.flags[p]) : 0u;
-  int ns = valid ? __ldg(&pods.ns[p]) : -1;
-  const uint32_t present = valid ? __ldg(&pods.present[p]) : 0u;
   // shouldCountIn (throttle_controller.go:217-219): schedulerName == target && nodeName != ""
   const bool counted = (flags & (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) == (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED) &&
                        (unsigned)ns < (unsigned)tb.NS;
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
   int j = 0, hi = 0;
   if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  const bool active = j < hi;
-  // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
-  for (int r = 0; r < R; ++r) {
-    long long v = 0;
-    if (alive && active && ((present >> r) & 1)) v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
-    s_req[r * TILE + tid] = v;
-  }
-  s_present[tid] = present & ~KT_COUNT_BIT;
-  stage_rowids(tb, pods.labels, pods.n, p, active, L, s_rowid + tid, TILE);
-  int cur = active ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
   __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
 
   unsigned long long* part_used = part;
@@ -318,7 +366,7 @@ __global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, T
     if (w == 0x7fffffff) break;
     uint32_t word = 0;
     if (cur == w) {
-      word = eval_word<TPC, B>(tb, s_rowid + tid, TILE, L, ns, w);
+      word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
       if (word) bitmap[p * Wp + w] = word;
       ++j;
       cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
@@ -331,7 +379,7 @@ __global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, T
     int slot = -1;
     if (lane == 0) {
 #pragma unroll 1
-      for (int s = 0; s < kSlots; ++s) {
+      for (int s = 0; s < S; ++s) {
         int k = *reinterpret_cast<volatile int*>(&s_key[s]);
         if (k == -1) k = atomicCAS(&s_key[s], -1, w);
         if (k == -1 || k == w) { slot = s; break; }
@@ -422,7 +470,7 @@ __global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, T
   }
   __syncthreads();
   // CTA accumulators -> HBM partials: one RED per (throttle, resource) the tile touched.
-  for (int idx = tid; idx < kSlots * 32; idx += TILE) {
+  for (int idx = tid; idx < S * 32; idx += TILE) {
     const int slot = idx >> 5, b = idx & 31;
     const int w = s_key[slot];
     const uint32_t cnt = s_cnt[idx];
@@ -586,11 +634,12 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 // constants of a word's 32 throttles are staged in shared memory by the warp (lane = throttle) so the
 // per-pair work is shared-memory compares instead of dependent global gathers.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t check_smem_bytes(int L, int R, int tile) {
-  return (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R) + (size_t)L * tile * 4 + (size_t)kCheckStash * tile * 4;
+__host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
+  return (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R) + (reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4) +
+         (size_t)kCheckStash * tile * 4;
 }
 
-template <int TPC, int B>
+template <int TPC, int B, bool REG>
 __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
                                                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                       unsigned char* __restrict__ admit) {
@@ -599,8 +648,8 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                                   // [R][TILE]
   unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);           // [warps][32][rec]
-  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_chk + (size_t)(TILE / 32) * 32 * rec);      // [L][TILE]
-  uint32_t* s_words = reinterpret_cast<uint32_t*>(s_rowid + (size_t)L * TILE);                // [kCheckStash][TILE]
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_chk + (size_t)(TILE / 32) * 32 * rec);      // [L][TILE] (!REG)
+  uint32_t* s_words = reinterpret_cast<uint32_t*>(s_rowid + (REG ? 0 : (size_t)((L + 7) & ~7) * TILE));    // [kCheckStash][TILE]
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * 32 * rec;
   const int64_t tile0 = (int64_t)blockIdx.x * TILE;
@@ -613,22 +662,29 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
     for (int64_t i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
     for (int64_t i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
+  const int Lpad = (L + 7) & ~7;
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
-  const int ns = valid ? __ldg(&pods.ns[p]) : -1;
-  const uint32_t present = valid ? __ldg(&pods.present[p]) : 0u;
-  int lo = 0, hi = 0;
-  if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  const bool active = lo < hi;
+  const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes never store
+  const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
+  const uint32_t present = __ldg(&pods.present[pc]);
+  PodRows<REG> rows;
+  rows.init(s_rowid, tid, TILE);
   // ResourceAmountOfPod(pod): the non-zero requests are the only ones IsThrottledFor looks at (Q5)
   uint32_t nz = 0;
-  for (int r = 0; r < R; ++r) {
-    long long v = 0;
-    if (active && ((present >> r) & 1)) v = __ldg(&pods.req[(int64_t)r * pods.n + p]);
-    s_req[r * TILE + tid] = v;
-    if (v != 0) nz |= 1u << r;
+  {
+    const int64_t* rp = pods.req + pc;
+    for (int r = 0; r < R; ++r) {
+      long long v = __ldg(rp);
+      rp += pods.n;
+      if (!((present >> r) & 1)) v = 0;
+      s_req[r * TILE + tid] = v;
+      if (v != 0) nz |= 1u << r;
+    }
   }
-  stage_rowids(tb, pods.labels, pods.n, p, active, L, s_rowid + tid, TILE);
+  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+  int lo = 0, hi = 0;
+  if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 
   // ---- phase 1: affectedThrottles (throttle_controller.go:248-269) ----
@@ -636,7 +692,7 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
     const int w = __ldg(&tb.nsw_idx[j]);
-    const uint32_t word = eval_word<TPC, B>(tb, s_rowid + tid, TILE, L, ns, w);
+    const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
     if (j - lo < kCheckStash) s_words[(j - lo) * TILE + tid] = word;
     if (word) {
       bitmap[p * Wp + w] = word;

@@ -224,6 +224,7 @@ std::string compile_tables(const kt_limits& lim, const SelectorSpec& s, int32_t 
       if (any) h.nsw_idx.push_back(w);
     }
     h.nsw_off[ns + 1] = (int32_t)h.nsw_idx.size();
+    h.max_ns_words = std::max(h.max_ns_words, h.nsw_off[ns + 1] - h.nsw_off[ns]);
   }
 
   // ---- label -> row hash (open addressing, linear probing, <= 50% load) --------------------------
@@ -245,34 +246,34 @@ std::string compile_tables(const kt_limits& lim, const SelectorSpec& s, int32_t 
 
   // ---- two-level direct dictionary ---------------------------------------------------------------
   // key ids small enough -> one keydir entry per id up to the largest mentioned one; per key the mentioned
-  // value ids either form a compact range (direct valrow slice) or stay in the hash (vcnt = ~0).
+  // value ids either form a compact range (direct valrow slice) or stay in the hash (off = ~0).
+  const uint32_t row_bytes = (uint32_t)TPp * 8u, kOther = 0xfffffffeu;
+  const uint32_t neutral_roff = (uint32_t)(rows - 1) * row_bytes;
   h.n_keydir = 0;
-  h.keydir.clear();
-  h.valrow.clear();
-  if (!key_row.empty() && key_row.rbegin()->first < kKeyDirMax) {
-    const uint32_t nk = key_row.rbegin()->first + 1;
-    h.n_keydir = (int32_t)nk;
-    h.keydir.assign((size_t)nk * 4, 0);
-    for (uint32_t k = 0; k < nk; ++k) h.keydir[4 * (size_t)k] = (uint32_t)(rows - 1);  // unmentioned key: neutral row, no values
+  h.valrow.assign(1, kOther);  // [0]: sentinel
+  if (!key_row.empty() && key_row.rbegin()->first < kKeyDirMax) h.n_keydir = (int32_t)key_row.rbegin()->first + 1;
+  const uint32_t nk = (uint32_t)h.n_keydir;
+  h.keydir.assign(((size_t)nk + 1) * 4, 0);
+  for (uint32_t k = 0; k <= nk; ++k) h.keydir[4 * (size_t)k] = neutral_roff;  // unmentioned key / sentinel: neutral row, no values
+  if (nk > 0) {
     for (auto& kv : key_row) {
       const uint32_t k = kv.first;
       uint32_t vmin = 0xffffffffu, vmax = 0, cnt = 0;
       for (const RowRef& rr : rows_of_key[k])
         if (!rr.other) { vmin = std::min(vmin, rr.val); vmax = std::max(vmax, rr.val); ++cnt; }
       uint32_t* e = &h.keydir[4 * (size_t)k];
-      e[0] = (uint32_t)kv.second;
+      e[0] = (uint32_t)kv.second * row_bytes;
       if (cnt == 0) continue;  // only Exists / DoesNotExist on this key
       const uint64_t span = (uint64_t)vmax - vmin + 1;
-      if (span > (uint64_t)cnt * 4 + 64) { e[2] = 0xffffffffu; continue; }  // sparse value ids: hashed
+      if (span > (uint64_t)cnt * 4 + 64 || h.valrow.size() + span >= (1ull << 31)) { e[3] = 0xffffffffu; continue; }  // sparse value ids: hashed
       e[1] = vmin;
       e[2] = (uint32_t)span;
       e[3] = (uint32_t)h.valrow.size();
-      h.valrow.resize(h.valrow.size() + span, -1);
+      h.valrow.resize(h.valrow.size() + span, kOther);
       for (const RowRef& rr : rows_of_key[k])
-        if (!rr.other) h.valrow[e[3] + (rr.val - vmin)] = rr.row;
+        if (!rr.other) h.valrow[e[3] + (rr.val - vmin)] = (uint32_t)rr.row * row_bytes;
     }
   }
-  if (h.valrow.empty()) h.valrow.push_back(-1);
 
   *out = std::move(h);
   return "";

@@ -36,18 +36,22 @@ struct HostTables {
   int32_t NS = 0;      // namespaces covered by nsmask
   uint32_t hash_mask = 0;
   std::vector<uint32_t> hash;    // [hash_mask+1][4]: {keyId, valId (0xffffffff = the key's "other value" row), row, 0}; empty = {~0,~0,0,0}
-  // Two-level direct dictionary (the fast path; dictionary ids handed out by a packer are small and dense):
-  //   keydir[keyId] = {other_row, vmin, vcnt, off}; vcnt == 0xffffffff: this key's values are looked up in `hash`
-  //   valrow[off + (valId - vmin)] = row, or -1 for "a value no requirement mentions" (=> other_row)
+  // Two-level direct dictionary (the fast path; dictionary ids handed out by a packer are small and dense).
+  // Rows are stored as "roff" = row * TPpad * 8, the byte offset of the row inside a word slice of `table`.
+  //   keydir[keyId] = {other roff, vmin, vcnt, off}; off == 0xffffffff (vcnt = 0): the key's values live in `hash`
+  //   keydir[n_keydir] = {neutral roff, 0, 0, 0}: sentinel for every key id >= n_keydir (unmentioned key)
+  //   valrow[off + (valId - vmin)] = roff, or kOtherRoff (0xfffffffe) for "a value no requirement mentions";
+  //   valrow[0] = kOtherRoff is the sentinel out-of-range values read.
   // n_keydir == 0 (some mentioned keyId >= kKeyDirMax): every label goes through `hash`.
   int32_t n_keydir = 0;
-  std::vector<uint32_t> keydir;  // [n_keydir][4]
-  std::vector<int32_t> valrow;
+  std::vector<uint32_t> keydir;  // [n_keydir + 1][4]
+  std::vector<uint32_t> valrow;
   std::vector<uint32_t> table;   // [W][rows][TPpad][2]: {sat, pos}
   std::vector<uint32_t> need;    // [W][TPpad][B]
   std::vector<uint32_t> nsmask;  // [NS][W][TPpad]
   std::vector<int32_t> nsw_off;  // [NS+1]
   std::vector<int32_t> nsw_idx;  // non-zero words per namespace
+  int32_t max_ns_words = 0;      // longest per-namespace word list
 };
 
 // Validates the CSR arrays and copies them.  Returns "" or an error description.

@@ -90,7 +90,7 @@ def _gen_pods(rng, n: int, n_ns: int, R: int, L: int, running: bool, sort_by_nam
     return abi.PodCols(labels, req, present.astype(np.uint32), flags.astype(np.uint32), ns)
 
 
-def _gen_selectors(rng, m: int, kind: np.ndarray):
+def _gen_selectors(rng, m: int, kind: np.ndarray, q_max: int = 0):
     """CSR selector table: T in {1,2} (80/20), Q in {1,2,3} (60/30/10); 85% equality, 5% each
     In(2-3 values) / NotIn / Exists / DoesNotExist.  ClusterThrottle terms get 0-2 namespace requirements.
     Requirement pool layout: all podSelector requirements (term order), then all namespaceSelector ones."""
@@ -100,7 +100,7 @@ def _gen_selectors(rng, m: int, kind: np.ndarray):
     for t in range(m):
         T = 1 if rng.random() < 0.8 else 2
         for _ in range(T):
-            Q = int(rng.choice([1, 2, 3], p=[0.6, 0.3, 0.1]))
+            Q = int(rng.integers(1, q_max + 1)) if q_max else int(rng.choice([1, 2, 3], p=[0.6, 0.3, 0.1]))
             keys = rng.choice(K_POD_KEYS, size=Q, replace=False)
             pr = []
             for k in keys:
@@ -245,7 +245,7 @@ def true_used_numpy(snap: abi.Snapshot):
 
 def generate(config: str = "C2", *, seed=None, m=None, n=None, p=None, R=None, n_ns=None, cluster_frac=None,
              override_frac=None, L: int = 8, sort_by_namespace: bool = True, now: int = NOW_2026,
-             calibrate: bool = True) -> abi.Snapshot:
+             calibrate: bool = True, q_max: int = 0) -> abi.Snapshot:
     """Build the snapshot of a BASELINE config (or a scaled variant via keyword overrides)."""
     base = dict(CONFIGS[config])
     for k, v in dict(seed=seed, m=m, n=n, p=p, R=R, n_ns=n_ns, cluster_frac=cluster_frac, override_frac=override_frac).items():
@@ -277,7 +277,7 @@ def generate(config: str = "C2", *, seed=None, m=None, n=None, p=None, R=None, n
     thr_flags = np.full(m, abi.THR_RESPONSIBLE, np.uint8)
     thr_flags[rng.random(m) < 0.01] = 0  # 1% belong to another throttler instance
 
-    sel = _gen_selectors(rng, m, kind)
+    sel = _gen_selectors(rng, m, kind, q_max)  # q_max > 3: terms needing > 3 keys present (6-bit counters)
 
     snap = abi.Snapshot(
         R=R, L=L, LN=LN, running=running, pending=pending, ns_labels=ns_labels, kind=kind, thr_ns=thr_ns,

@@ -18,7 +18,7 @@ from . import abi
 from .abi import PassResult, PodCols, Snapshot  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkt_b200.so")
+LIB_PATH = os.environ.get("KT_B200_LIB") or os.path.join(_HERE, "libkt_b200.so")  # override: kernel-variant experiments only
 _lib = None
 
 

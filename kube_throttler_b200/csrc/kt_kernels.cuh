@@ -27,12 +27,18 @@
 
 namespace kt {
 
-constexpr int kTileReconcile = 128;  // running pods per CTA (one lane per pod)
+#ifndef KT_TILE_RECONCILE
+#define KT_TILE_RECONCILE 128
+#endif
+#ifndef KT_HEAVY_PODS
+#define KT_HEAVY_PODS 6
+#endif
+constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one lane per pod)
 constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kCheckStash = 4;       // match words per pending pod kept in shared memory between the two phases
-constexpr int kHeavyPods = 6;        // a throttle matching more pods of a warp than this is summed by the whole warp
+constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
   const int64_t* labels;    // [L][n]
@@ -299,7 +305,7 @@ __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool
 //       largest per-namespace word list); words beyond S go straight to HBM
 // ------------------------------------------------------------------------------------------------
 template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, 6) k_reconcile(PodView pods, TableView tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
+__global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconcile(PodView pods, TableView tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
                                                                  unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
   constexpr int TILE = kTileReconcile;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -231,6 +231,10 @@ int kt_get_reconcile(kt_ctx* ctx, const kt_reconcile_out* out);
  * PENDING: affectedThrottles relation (responsible && namespace && selector match). */
 int32_t kt_match_words(const kt_ctx* ctx);
 int kt_get_match_bitmap(kt_ctx* ctx, int kind, uint32_t* words /*[n][words_per_row]*/);
+/* The same for k selected rows only (gathered on the device): words[i] = bitmap row rows[i].  This is how the
+ * host finds which reserved pods a reconcile has observed (unreserveAffectedPods, throttle_controller.go:135-155)
+ * without downloading the whole relation. */
+int kt_get_match_rows(kt_ctx* ctx, int kind, int64_t k, const int64_t* rows, uint32_t* words /*[k][words_per_row]*/);
 /* codes: 2 bits per (pending pod, throttle), pod-major, 16 codes per uint32:
  *   code(p,t) = (codes[p*2*words_per_row + (t>>4)] >> (2*(t&15))) & 3
  * admit[p] = 1 iff every affected throttle is KT_CHECK_NOT_THROTTLED (plugin.go:177-180).

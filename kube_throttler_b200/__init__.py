@@ -30,8 +30,9 @@ class KtError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kt_engine.cu", "kt_tables.cc", "kt_kernels.cuh", "kt_tables.h")]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kt_engine.cu", "kt_tables.cc", "kt_host.cc", "kt_kernels.cuh", "kt_tables.h", "kt_json.h", "kt_quantity.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "kt_b200.h"))
+    srcs.append(os.path.join(_HERE, "..", "include", "kt_host.h"))
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-B", "NVCCFLAGS_EXTRA="], check=True,
@@ -43,7 +44,7 @@ EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
     "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy",
 ]
 

@@ -630,6 +630,34 @@ int kt_get_match_bitmap(kt_ctx* c, int kind, uint32_t* words) {
   return KT_OK;
 }
 
+int kt_get_match_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, uint32_t* words) {
+  if (!c || k < 0 || (k > 0 && (!rows || !words))) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_match_rows before kt_evaluate");
+  if (k == 0) return KT_OK;
+  PodStore& s = c->pods[kind];
+  for (int64_t i = 0; i < k; ++i)
+    if (rows[i] < 0 || rows[i] >= s.n) return fail(c, KT_ERR_INVALID, "row %lld out of range [0,%lld)", (long long)rows[i], (long long)s.n);
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int Wp = c->ht.Wp;
+  DevBuf t_rows, t_out;
+  cudaError_t e = t_rows.reserve((size_t)k * 8);
+  if (e == cudaSuccess) e = t_out.reserve((size_t)k * Wp * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t_rows.p, rows, (size_t)k * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_gather_rows<<<(unsigned)((k + 7) / 8), 256, 0, c->stream>>>(k, t_rows.as<int64_t>(), Wp, s.bitmap.as<uint32_t>(), t_out.as<uint32_t>());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(words, t_out.p, (size_t)k * Wp * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  t_rows.release();
+  t_out.release();
+  if (e != cudaSuccess) return fail(c, KT_ERR_CUDA, "kt_get_match_rows: %s", cudaGetErrorString(e));
+  return KT_OK;
+}
+
 int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   if (!c) return KT_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);

@@ -1,0 +1,1389 @@
+// kt_host.cc -- the plugin surface (NewPlugin / PreFilter / Reserve / Unreserve) and both controllers'
+// bookkeeping of everpeace/kube-throttler restated above the device engine (include/kt_host.h).
+//
+// Shape: the informer caches are kept COLUMN-first.  A pod is parsed once per event into its packed row
+// (dictionary-encoded labels, ResourceAmountOfPod as exact quantities); rows live in a slotted table that
+// mirrors the device columns one to one, so an informer event is a row scatter (kt_update_pod_rows) and a
+// pass never rebuilds anything.  Throttles / namespaces are small and re-uploaded whole when they change.
+// Nothing in this file decides whether a pod matches a selector or compares a quantity with a threshold:
+// that is the device's job (kt_evaluate); this file packs, calls, and spells the results.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kt_b200.h"
+#include "../../include/kt_host.h"
+#include "kt_json.h"
+#include "kt_quantity.h"
+
+namespace {
+
+using ktjson::Node;
+using ktjson::Writer;
+using kt::Quantity;
+
+// ---- dictionaries --------------------------------------------------------------------------------
+struct Dict {
+  std::unordered_map<std::string, uint32_t> ids;
+  std::vector<std::string> names;
+  uint32_t id(const std::string& s) {
+    auto it = ids.find(s);
+    if (it != ids.end()) return it->second;
+    const uint32_t v = (uint32_t)names.size();
+    ids.emplace(s, v);
+    names.push_back(s);
+    return v;
+  }
+  int find(const std::string& s) const {
+    auto it = ids.find(s);
+    return it == ids.end() ? -1 : (int)it->second;
+  }
+  size_t size() const { return names.size(); }
+};
+
+// label keys share one id space (pod and namespace labels, selector keys); values are numbered per key, so
+// the ids are dense in both dimensions and the device takes its direct key/value tables (kt_tables.cc)
+struct LabelDict {
+  Dict keys;
+  std::vector<Dict> vals;
+  int64_t encode(const std::string& k, const std::string& v) {
+    const uint32_t kid = keys.id(k);
+    if (vals.size() <= kid) vals.resize(kid + 1);
+    return (int64_t)(((uint64_t)kid << 32) | vals[kid].id(v));
+  }
+};
+
+// ---- time: time.Parse(time.RFC3339, s) with Go's error texts ---------------------------------------
+struct GoTime {
+  long long sec = 0;  // unix seconds
+  int nsec = 0;
+  bool zero = true;   // time.Time{} (year 1): "not set"
+  __int128 ns() const { return (__int128)sec * 1000000000 + nsec; }
+};
+long long days_from_civil(long long y, unsigned m, unsigned d) {
+  y -= m <= 2;
+  const long long era = (y >= 0 ? y : y - 399) / 400;
+  const unsigned yoe = (unsigned)(y - era * 400);
+  const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + (long long)doe - 719468;
+}
+// Layout-driven: the RFC3339 layout "2006-01-02T15:04:05Z07:00" is a list of chunks; the first chunk that
+// fails to parse produces `cannot parse "<rest>" as "<chunk>"` exactly as time.Parse reports it.
+std::string parse_rfc3339(const std::string& value, GoTime* out) {
+  static const char* kLayout = "2006-01-02T15:04:05Z07:00";
+  struct Chunk { const char* text; int digits; };  // digits > 0: fixed-width number; 0: literal
+  static const Chunk chunks[] = {{"2006", 4}, {"-", 0}, {"01", 2}, {"-", 0}, {"02", 2}, {"T", 0}, {"15", 2}, {":", 0}, {"04", 2}, {":", 0}, {"05", 2}};
+  int field[6] = {0, 0, 0, 0, 0, 0};
+  int nf = 0;
+  size_t p = 0;
+  auto bad = [&](size_t at, const char* elem) {
+    return "parsing time \"" + value + "\" as \"" + kLayout + "\": cannot parse \"" + value.substr(std::min(at, value.size())) + "\" as \"" + elem + "\"";
+  };
+  auto out_of_range = [&](const char* what) { return "parsing time \"" + value + "\": " + what + " out of range"; };
+  for (const Chunk& c : chunks) {
+    if (c.digits == 0) {
+      if (p >= value.size() || value[p] != c.text[0]) return bad(p, c.text);
+      ++p;
+      continue;
+    }
+    if (p + c.digits > value.size()) return bad(p, c.text);
+    int v = 0;
+    for (int i = 0; i < c.digits; ++i) {
+      const char ch = value[p + i];
+      if (ch < '0' || ch > '9') return bad(p, c.text);
+      v = v * 10 + (ch - '0');
+    }
+    p += c.digits;
+    field[nf++] = v;
+    if (nf == 2 && (v < 1 || v > 12)) return out_of_range("month");
+    if (nf == 4 && v >= 24) return out_of_range("hour");
+    if (nf == 5 && v >= 60) return out_of_range("minute");
+    if (nf == 6 && v >= 60) return out_of_range("second");
+  }
+  int nsec = 0;
+  if (p + 1 < value.size() && (value[p] == '.' || value[p] == ',') && value[p + 1] >= '0' && value[p + 1] <= '9') {
+    ++p;
+    int nd = 0;
+    long long frac = 0;
+    while (p < value.size() && value[p] >= '0' && value[p] <= '9') {
+      if (nd < 9) { frac = frac * 10 + (value[p] - '0'); ++nd; }
+      ++p;
+    }
+    for (; nd < 9; ++nd) frac *= 10;
+    nsec = (int)frac;
+  }
+  long long offset = 0;
+  const size_t zone_at = p;
+  if (p < value.size() && value[p] == 'Z') {
+    ++p;
+  } else if (p < value.size() && (value[p] == '+' || value[p] == '-')) {
+    const int sign = value[p] == '-' ? -1 : 1;
+    auto two = [&](size_t at, int* v) {
+      if (at + 2 > value.size() || value[at] < '0' || value[at] > '9' || value[at + 1] < '0' || value[at + 1] > '9') return false;
+      *v = (value[at] - '0') * 10 + (value[at + 1] - '0');
+      return true;
+    };
+    int oh = 0, om = 0;
+    if (!two(p + 1, &oh) || p + 3 >= value.size() || value[p + 3] != ':' || !two(p + 4, &om)) return bad(zone_at, "Z07:00");
+    p += 6;
+    if (oh > 24) return out_of_range("time zone offset hour");
+    if (om > 60) return out_of_range("time zone offset minute");
+    offset = sign * (oh * 3600LL + om * 60LL);
+  } else {
+    return bad(zone_at, "Z07:00");
+  }
+  if (p != value.size()) return "parsing time \"" + value + "\": extra text: \"" + value.substr(p) + "\"";
+  const int Y = field[0], M = field[1], D = field[2];
+  static const int mdays[] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  const bool leap = (Y % 4 == 0 && Y % 100 != 0) || Y % 400 == 0;
+  if (D < 1 || D > mdays[M - 1] + (M == 2 && leap ? 1 : 0)) return out_of_range("day");
+  out->sec = days_from_civil(Y, (unsigned)M, (unsigned)D) * 86400LL + field[3] * 3600LL + field[4] * 60LL + field[5] - offset;
+  out->nsec = nsec;
+  out->zero = false;
+  return "";
+}
+int64_t clamp_ns(__int128 v) {
+  const __int128 lo = (__int128)INT64_MIN + 1, hi = (__int128)INT64_MAX - 1;
+  return (int64_t)(v < lo ? lo : (v > hi ? hi : v));
+}
+
+// ---- label selector validation (metav1.LabelSelectorAsSelector -> labels.NewRequirement) -----------
+bool is_alnum(char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+bool valid_name_part(const std::string& s) {  // [A-Za-z0-9]([-A-Za-z0-9_.]*[A-Za-z0-9])?, at most 63 chars
+  if (s.empty() || s.size() > 63 || !is_alnum(s.front()) || !is_alnum(s.back())) return false;
+  for (char c : s)
+    if (!is_alnum(c) && c != '-' && c != '_' && c != '.') return false;
+  return true;
+}
+bool valid_dns_subdomain(const std::string& s) {
+  if (s.empty() || s.size() > 253) return false;
+  size_t b = 0;
+  while (true) {
+    size_t e = s.find('.', b);
+    const std::string lab = s.substr(b, e == std::string::npos ? std::string::npos : e - b);
+    if (lab.empty()) return false;
+    auto low = [](char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z'); };
+    if (!low(lab.front()) || !low(lab.back())) return false;
+    for (char c : lab)
+      if (!low(c) && c != '-') return false;
+    if (e == std::string::npos) return true;
+    b = e + 1;
+  }
+}
+std::string validate_label_key(const std::string& k) {
+  const size_t slash = k.find('/');
+  std::string name = k, prefix;
+  if (slash != std::string::npos) {
+    if (k.find('/', slash + 1) != std::string::npos) return "a qualified name must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character with an optional DNS subdomain prefix and '/'";
+    prefix = k.substr(0, slash);
+    name = k.substr(slash + 1);
+    if (prefix.empty()) return "prefix part must be non-empty";
+    if (!valid_dns_subdomain(prefix)) return "prefix part a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with an alphanumeric character";
+  }
+  if (name.empty()) return "name part must be non-empty";
+  if (name.size() > 63) return "name part must be no more than 63 characters";
+  if (!valid_name_part(name)) return "name part must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
+  return "";
+}
+std::string validate_label_value(const std::string& v) {
+  if (v.empty()) return "";
+  if (v.size() > 63) return "must be no more than 63 characters";
+  if (!valid_name_part(v)) return "a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
+  return "";
+}
+
+struct Requirement {
+  std::string key;
+  uint8_t op = KT_OP_IN;
+  std::vector<std::string> values;
+};
+struct CompiledSelector {
+  std::vector<Requirement> reqs;  // empty => Everything
+  std::string error;              // non-empty => LabelSelectorAsSelector failed
+};
+CompiledSelector compile_selector(const Node& sel) {
+  CompiledSelector out;
+  if (!sel.is(Node::Obj)) return out;
+  auto add = [&](const std::string& key, const std::string& opname, std::vector<std::string> values) {
+    if (!out.error.empty()) return;
+    Requirement r;
+    r.key = key;
+    if (opname == "In") r.op = KT_OP_IN;
+    else if (opname == "NotIn") r.op = KT_OP_NOTIN;
+    else if (opname == "Exists") r.op = KT_OP_EXISTS;
+    else if (opname == "DoesNotExist") r.op = KT_OP_DOESNOTEXIST;
+    else { out.error = "\"" + opname + "\" is not a valid label selector operator"; return; }
+    if ((r.op == KT_OP_IN || r.op == KT_OP_NOTIN) && values.empty()) { out.error = "values: Invalid value: []string(nil): for 'in', 'notin' operators, values set can't be empty"; return; }
+    if ((r.op == KT_OP_EXISTS || r.op == KT_OP_DOESNOTEXIST) && !values.empty()) { out.error = "values: Invalid value: []string{...}: values set must be empty for exists and does not exist"; return; }
+    std::string e = validate_label_key(key);
+    if (!e.empty()) { out.error = "key: Invalid value: \"" + key + "\": " + e; return; }
+    for (auto& v : values) {
+      e = validate_label_value(v);
+      if (!e.empty()) { out.error = "values[0][" + key + "]: Invalid value: \"" + v + "\": " + e; return; }
+    }
+    r.values = std::move(values);
+    out.reqs.push_back(std::move(r));
+  };
+  // matchLabels first, keys sorted (LabelSelectorAsSelector iterates a sorted key list), then matchExpressions in order
+  std::map<std::string, std::string> ml;
+  for (auto& kv : sel["matchLabels"].obj) ml[kv.first] = kv.second->str();
+  for (auto& kv : ml) add(kv.first, "In", {kv.second});
+  for (auto& e : sel["matchExpressions"].arr) {
+    std::vector<std::string> vals;
+    for (auto& v : (*e)["values"].arr) vals.push_back(v->str());
+    add((*e)["key"].str(), (*e)["operator"].str(), std::move(vals));
+  }
+  if (!out.error.empty()) out.reqs.clear();
+  return out;
+}
+
+// ---- objects ----------------------------------------------------------------------------------------
+struct ResAmount {  // ResourceAmount with exact quantities, keyed by resource column id
+  bool has_counts = false;
+  long long pod = 0;
+  std::map<int, Quantity> requests;  // key present <=> Go map has the key
+  bool requests_nil = true;
+};
+
+struct PodObj {
+  std::string ns, name;
+  std::vector<std::pair<std::string, std::string>> labels;
+  std::string scheduler_name, node_name, phase;
+  std::map<int, Quantity> request;  // PodRequestResourceList (resource id -> quantity); ResourceAmountOfPod adds Counts{1}
+  int64_t row = -1;                 // slot in the running-pod table
+  bool live = false;
+  std::string nn() const { return ns + "/" + name; }
+};
+
+struct Override {
+  std::string begin, end;
+  ResAmount threshold;
+};
+struct Term {
+  CompiledSelector pod_sel, ns_sel;
+};
+struct ThrottleObj {
+  int kind = KT_KIND_THROTTLE;
+  std::string ns, name, throttler_name;
+  ResAmount threshold;
+  std::vector<Override> overrides;
+  std::vector<Term> terms;
+  // status (the informer copy; reconcile writes it back)
+  ResAmount st_calc;
+  bool st_calc_at_set = false;
+  long long st_calc_at = 0;
+  std::vector<std::string> st_messages;
+  bool st_thr_pod = false;
+  std::map<int, bool> st_thr_req;
+  bool st_thr_req_nil = true;
+  ResAmount st_used;
+  bool live = false;
+  std::string nn() const { return ns + "/" + name; }
+  std::string selector_error() const {  // the first podSelector that LabelSelectorAsSelector rejects
+    for (auto& t : terms)
+      if (!t.pod_sel.error.empty()) return t.pod_sel.error;
+    return "";
+  }
+};
+
+struct NamespaceObj {
+  std::string name;
+  std::vector<std::pair<std::string, std::string>> labels;
+  bool exists = false;  // a Namespace object was applied (pods may reference namespaces the informer has not seen)
+};
+
+// reservedResourceAmounts (reserved_resource_amounts.go): throttle -> pod -> ResourceAmountOfPod
+struct ReservationCache {
+  std::map<std::string, std::map<std::string, std::map<int, Quantity>>> by_thr;  // thrNN -> podNN -> request list
+  bool add(const std::string& thr, const PodObj& pod) {
+    auto& m = by_thr[thr];
+    const bool existed = m.count(pod.nn()) != 0;
+    m[pod.nn()] = pod.request;  // overwrites (podResourceAmountMap.add, :131-136)
+    return !existed;
+  }
+  bool remove(const std::string& thr, const std::string& pod_nn) {
+    auto it = by_thr.find(thr);
+    if (it == by_thr.end()) return false;
+    return it->second.erase(pod_nn) != 0;
+  }
+};
+
+struct ResourceColumn {
+  std::string name;
+  int scale_exp = 0;  // device value = quantity / 10^scale_exp
+  Quantity::Format format = Quantity::DecimalSI;
+};
+
+[[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
+
+thread_local std::string g_ret;
+const char* ret(std::string s) {
+  g_ret = std::move(s);
+  return g_ret.c_str();
+}
+std::string err_json(const std::string& m) {
+  Writer w;
+  w.begin_obj().key("error").str(m).end_obj();
+  return w.out;
+}
+std::string g_new_plugin_error;
+
+}  // namespace
+
+struct kth_plugin {
+  std::mutex mu;
+  std::string name, target_scheduler;
+  int device = 0;
+  kt_ctx* ctx = nullptr;
+  kt_limits lim{};  // limits the current engine was created with
+
+  LabelDict labels;
+  Dict ns_dict;
+  std::vector<NamespaceObj> namespaces;  // by ns id
+  std::vector<ResourceColumn> cols;      // resource column table
+  Dict col_dict;
+
+  std::vector<PodObj> pods;  // slot == device row of the running-pod table
+  std::unordered_map<std::string, int64_t> pod_index;
+  std::vector<int64_t> free_rows;
+  std::set<int64_t> dirty_rows;
+  int64_t row_capacity = 0;  // rows the device table currently holds
+  bool pods_full_upload = true;
+
+  std::vector<ThrottleObj> throttles;  // column order == device order (both kinds interleaved, insertion order)
+  std::unordered_map<std::string, int> thr_index;  // "T:ns/name" | "C:/name"
+  bool throttles_dirty = true, namespaces_dirty = true, status_dirty = true, reserved_dirty = true;
+
+  ReservationCache cache[2];  // one per controller (controller.go:34-50)
+  int max_labels = 0, max_ns_labels = 0;
+
+  // ---- resource columns / scales ----------------------------------------------------------------
+  int column(const std::string& rname) {
+    int c = col_dict.find(rname);
+    if (c >= 0) return c;
+    c = (int)col_dict.id(rname);
+    ResourceColumn rc;
+    rc.name = rname;
+    rc.scale_exp = rname == "cpu" ? -3 : 0;  // milli-cpu, whole units / bytes elsewhere; refined on demand
+    cols.push_back(rc);
+    if ((int)cols.size() > KT_MAX_RESOURCES) fail("more than 31 distinct resource names");
+    if (ctx && (int)cols.size() > lim.n_resources) drop_engine();
+    return c;
+  }
+  void note_quantity(int c, const Quantity& q) {
+    const int need = kt::quantity_min_exp(q);
+    if (need < cols[c].scale_exp) {  // a finer value than the column holds: every row of the column is re-packed
+      cols[c].scale_exp = need;
+      pods_full_upload = throttles_dirty = status_dirty = reserved_dirty = true;
+    }
+    if (q.format == Quantity::BinarySI) cols[c].format = Quantity::BinarySI;
+  }
+  int64_t at_scale(int c, const Quantity& q) const {
+    bool ok;
+    const int64_t v = kt::quantity_at_scale(q, cols[c].scale_exp, &ok);
+    if (!ok) fail("resource '" + cols[c].name + "': value " + kt::decimal_string(q) + " does not fit the int64 column at scale 1e" + std::to_string(cols[c].scale_exp));
+    return v;
+  }
+  std::map<int, Quantity> resource_list(const Node& n) {  // corev1.ResourceList
+    std::map<int, Quantity> out;
+    for (auto& kv : n.obj) {
+      const int c = column(kv.first);
+      const Quantity q = kt::parse_quantity(kv.second->scalar());
+      note_quantity(c, q);
+      out[c] = q;
+    }
+    return out;
+  }
+  ResAmount res_amount(const Node& n) {
+    ResAmount a;
+    if (!n.is(Node::Obj)) return a;
+    const Node& rc = n["resourceCounts"];
+    if (rc.is(Node::Obj)) { a.has_counts = true; a.pod = rc["pod"].integer(0); }
+    const Node& rr = n["resourceRequests"];
+    if (rr.is(Node::Obj)) { a.requests_nil = false; a.requests = resource_list(rr); }
+    return a;
+  }
+
+  // ---- PodRequestResourceList (pkg/resourcelist/resourcelist.go:27-46) ------------------------------
+  std::map<int, Quantity> pod_request_resource_list(const Node& spec) {
+    std::map<int, Quantity> ic, c;
+    for (auto& ctr : spec["initContainers"].arr)  // icRes.SetMax(requests): rhs-only names are inserted as they are
+      for (auto& kv : resource_list((*ctr)["resources"]["requests"])) {
+        auto it = ic.find(kv.first);
+        if (it == ic.end()) ic[kv.first] = kv.second;
+        else if (kt::quantity_cmp(kv.second, it->second) > 0) it->second = kv.second;
+      }
+    for (auto& ctr : spec["containers"].arr)  // cRes.Add(requests)
+      for (auto& kv : resource_list((*ctr)["resources"]["requests"])) {
+        auto it = c.find(kv.first);
+        if (it == c.end()) c[kv.first] = kv.second;
+        else it->second = kt::quantity_add(it->second, kv.second);
+      }
+    for (auto& kv : ic) {  // cRes.SetMax(icRes)
+      auto it = c.find(kv.first);
+      if (it == c.end()) c[kv.first] = kv.second;
+      else if (kt::quantity_cmp(kv.second, it->second) > 0) it->second = kv.second;
+    }
+    if (spec["overhead"].is(Node::Obj))  // pod.Spec.Overhead != nil
+      for (auto& kv : resource_list(spec["overhead"])) {
+        auto it = c.find(kv.first);
+        if (it == c.end()) c[kv.first] = kv.second;
+        else it->second = kt::quantity_add(it->second, kv.second);
+      }
+    for (auto& kv : c) note_quantity(kv.first, kv.second);
+    return c;
+  }
+  PodObj pod_from(const Node& v) {
+    PodObj p;
+    const Node& md = v["metadata"];
+    p.ns = md["namespace"].str();
+    p.name = md["name"].str();
+    for (auto& kv : md["labels"].obj) p.labels.emplace_back(kv.first, kv.second->str());
+    const Node& spec = v["spec"];
+    p.scheduler_name = spec["schedulerName"].str();
+    p.node_name = spec["nodeName"].str();
+    p.phase = v["status"]["phase"].str();
+    p.request = pod_request_resource_list(spec);
+    p.live = true;
+    if ((int)p.labels.size() > max_labels) {
+      max_labels = (int)p.labels.size();
+      if (max_labels > KT_MAX_LABEL_SLOTS) fail("pod " + p.nn() + " has more than 32 labels");
+      if (ctx && max_labels > lim.label_slots) drop_engine();
+    }
+    return p;
+  }
+  uint32_t pod_flags(const PodObj& p) const {
+    uint32_t f = 0;
+    if (p.scheduler_name == target_scheduler) f |= KT_POD_SCHEDULER_MATCH;       // shouldCountIn, throttle_controller.go:217-219
+    if (!p.node_name.empty()) f |= KT_POD_SCHEDULED;                            // isScheduled, pod_util.go:22-24
+    if (p.phase != "Succeeded" && p.phase != "Failed") f |= KT_POD_NOT_FINISHED;  // isNotFinished, pod_util.go:26-28
+    return f;
+  }
+  bool should_count_in(const PodObj& p) const { return p.scheduler_name == target_scheduler && !p.node_name.empty(); }
+
+  int32_t ns_id(const std::string& name) {
+    const uint32_t id = ns_dict.id(name);
+    if (namespaces.size() <= id) {
+      namespaces.resize(id + 1);
+      namespaces[id].name = name;
+      namespaces_dirty = throttles_dirty = true;  // Throttle namespace equality is part of the compiled tables
+    }
+    return (int32_t)id;
+  }
+
+  // ---- engine --------------------------------------------------------------------------------------
+  void drop_engine() {
+    if (ctx) kt_destroy(ctx);
+    ctx = nullptr;
+    pods_full_upload = throttles_dirty = namespaces_dirty = status_dirty = reserved_dirty = true;
+  }
+  void check(int rc, const char* what) {
+    if (rc != KT_OK) fail(std::string(what) + ": " + (ctx ? kt_last_error(ctx) : "no engine") + " (" + std::to_string(rc) + ")");
+  }
+  static int round_up(int v, std::initializer_list<int> steps) {
+    for (int s : steps)
+      if (v <= s) return s;
+    return *(steps.end() - 1);
+  }
+  void ensure_engine() {
+    if (ctx) return;
+    lim.abi_version = KT_ABI_VERSION;
+    lim.n_resources = round_up(std::max<int>(1, (int)cols.size()), {4, 8, 16, 31});
+    lim.label_slots = round_up(std::max(1, max_labels), {8, 16, 32});
+    lim.ns_label_slots = round_up(std::max(1, max_ns_labels), {4, 8, 16, 32});
+    const int rc = kt_create(&ctx, device, &lim);
+    if (rc != KT_OK) { ctx = nullptr; fail("kt_create failed (" + std::to_string(rc) + "): no usable CUDA device -- there is no CPU path"); }
+  }
+
+  // pack one pod into compact single-row columns appended to the given vectors
+  void pack_pod(const PodObj& p, std::vector<int64_t>& lab, std::vector<int64_t>& req, std::vector<uint32_t>& present, std::vector<uint32_t>& flags,
+                std::vector<int32_t>& nsid, size_t k, size_t i) {
+    const int L = lim.label_slots, R = lim.n_resources;
+    for (int s = 0; s < L; ++s) lab[(size_t)s * k + i] = KT_LABEL_EMPTY;
+    for (int r = 0; r < R; ++r) req[(size_t)r * k + i] = 0;
+    present[i] = 0;
+    flags[i] = 0;
+    nsid[i] = 0;
+    if (!p.live) return;  // tombstone: never counted, matches nothing
+    int s = 0;
+    for (auto& kv : p.labels) lab[(size_t)(s++) * k + i] = labels.encode(kv.first, kv.second);
+    for (auto& kv : p.request) {
+      req[(size_t)kv.first * k + i] = at_scale(kv.first, kv.second);
+      present[i] |= 1u << kv.first;
+    }
+    flags[i] = pod_flags(p);
+    nsid[i] = ns_id(p.ns);
+  }
+
+  void sync_pods() {
+    ensure_engine();
+    const int L = lim.label_slots, R = lim.n_resources;
+    if ((int64_t)pods.size() > row_capacity) pods_full_upload = true;
+    if (pods_full_upload) {
+      int64_t cap = std::max<int64_t>(64, row_capacity);
+      while (cap < (int64_t)pods.size()) cap *= 2;
+      const size_t k = (size_t)cap;
+      std::vector<int64_t> lab((size_t)L * k), req((size_t)R * k);
+      std::vector<uint32_t> present(k), flags(k);
+      std::vector<int32_t> nsid(k);
+      PodObj tomb;
+      for (size_t i = 0; i < k; ++i) pack_pod(i < pods.size() ? pods[i] : tomb, lab, req, present, flags, nsid, k, i);
+      overflow_check();
+      check(kt_upload_pods(ctx, KT_PODS_RUNNING, cap, lab.data(), req.data(), present.data(), flags.data(), nsid.data()), "kt_upload_pods");
+      row_capacity = cap;
+      pods_full_upload = false;
+      dirty_rows.clear();
+    } else if (!dirty_rows.empty()) {
+      const size_t k = dirty_rows.size();
+      std::vector<int64_t> rows(dirty_rows.begin(), dirty_rows.end());
+      std::vector<int64_t> lab((size_t)L * k), req((size_t)R * k);
+      std::vector<uint32_t> present(k), flags(k);
+      std::vector<int32_t> nsid(k);
+      for (size_t i = 0; i < k; ++i) pack_pod(pods[(size_t)rows[i]], lab, req, present, flags, nsid, k, i);
+      overflow_check();
+      check(kt_update_pod_rows(ctx, KT_PODS_RUNNING, (int64_t)k, rows.data(), lab.data(), req.data(), present.data(), flags.data(), nsid.data()),
+            "kt_update_pod_rows");
+      dirty_rows.clear();
+    }
+  }
+  // int64 adds (and the NCCL sum) wrap silently: prove per column that they cannot (DESIGN.md "Quantity columns")
+  void overflow_check() {
+    std::vector<__int128> total(cols.size(), 0);
+    for (auto& p : pods)
+      if (p.live)
+        for (auto& kv : p.request) {
+          const int64_t v = at_scale(kv.first, kv.second);
+          total[kv.first] += v < 0 ? -(__int128)v : v;
+        }
+    for (size_t c = 0; c < cols.size(); ++c)
+      if (total[c] >= ((__int128)1 << 62)) fail("resource '" + cols[c].name + "': the column sum can overflow int64 at scale 1e" + std::to_string(cols[c].scale_exp));
+  }
+
+  void sync_namespaces() {
+    ensure_engine();
+    if (!namespaces_dirty) return;
+    const int LN = lim.ns_label_slots;
+    const size_t n = namespaces.size();
+    std::vector<int64_t> lab((size_t)LN * std::max<size_t>(n, 1), KT_LABEL_EMPTY);
+    for (size_t i = 0; i < n; ++i) {
+      int s = 0;
+      for (auto& kv : namespaces[i].labels) lab[(size_t)(s++) * n + i] = labels.encode(kv.first, kv.second);
+    }
+    check(kt_upload_namespaces(ctx, (int32_t)n, lab.data()), "kt_upload_namespaces");
+    namespaces_dirty = false;
+  }
+
+  // Throttle specs -> kt_throttle_cols + kt_selector_table.  Terms after the first invalid podSelector are
+  // unreachable in the reference (MatchesToPod returns the error first), so they are not compiled.
+  void sync_throttles() {
+    ensure_engine();
+    if (!throttles_dirty) return;
+    const int R = lim.n_resources;
+    const size_t m = throttles.size();
+    std::vector<uint8_t> kind(m), flags(m);
+    std::vector<int32_t> nsid(m), ovr_off(m + 1, 0);
+    std::vector<int64_t> thr((size_t)R * std::max<size_t>(m, 1), 0), thr_cnt(m, 0);
+    std::vector<uint32_t> thr_present(m, 0);
+    std::vector<int64_t> ovr_begin, ovr_end, ovr_cnt;
+    std::vector<uint8_t> ovr_flags;
+    std::vector<uint32_t> ovr_present;
+    std::vector<std::vector<int64_t>> ovr_vals;  // per override: R values
+    std::vector<int32_t> term_off(m + 1, 0), pod_req_off{0}, ns_req_off, req_val_off{0};
+    std::vector<uint8_t> term_flags, req_op;
+    std::vector<uint32_t> req_key, req_vals;
+    std::vector<std::vector<Requirement>> ns_reqs_of_term;
+    auto push_reqs = [&](const std::vector<Requirement>& reqs) {
+      for (auto& r : reqs) {
+        const uint32_t kid = labels.keys.id(r.key);
+        if (labels.vals.size() <= kid) labels.vals.resize(kid + 1);
+        req_key.push_back(kid);
+        req_op.push_back(r.op);
+        for (auto& v : r.values) req_vals.push_back(labels.vals[kid].id(v));
+        req_val_off.push_back((int32_t)req_vals.size());
+      }
+    };
+    auto amount_cols = [&](const ResAmount& a, int64_t* vals, size_t stride, uint32_t* present, int64_t* cnt) {
+      *present = 0;
+      *cnt = 0;
+      if (a.has_counts) { *present |= KT_COUNT_BIT; *cnt = a.pod; }
+      for (auto& kv : a.requests) {
+        vals[(size_t)kv.first * stride] = at_scale(kv.first, kv.second);
+        *present |= 1u << kv.first;
+      }
+    };
+    for (size_t t = 0; t < m; ++t) {
+      const ThrottleObj& o = throttles[t];
+      kind[t] = (uint8_t)o.kind;
+      nsid[t] = o.kind == KT_KIND_THROTTLE ? ns_id(o.ns) : -1;
+      flags[t] = 0;
+      if (o.live && o.throttler_name == name) flags[t] |= KT_THR_RESPONSIBLE;  // isResponsibleFor, throttle_controller.go:213-215
+      amount_cols(o.threshold, &thr[t], m, &thr_present[t], &thr_cnt[t]);
+      for (size_t i = 0; i < o.overrides.size(); ++i) {
+        const Override& ov = o.overrides[i];
+        GoTime b, e;
+        uint8_t f = 0;
+        if (!ov.begin.empty() && !parse_rfc3339(ov.begin, &b).empty()) f = KT_OVR_PARSE_ERROR;
+        if (!ov.end.empty() && !parse_rfc3339(ov.end, &e).empty()) f = KT_OVR_PARSE_ERROR;
+        ovr_begin.push_back(b.zero ? KT_TIME_OPEN_BEGIN : clamp_ns(b.ns()));
+        ovr_end.push_back(e.zero ? KT_TIME_OPEN_END : clamp_ns(e.ns()));
+        ovr_flags.push_back(f);
+        std::vector<int64_t> vals((size_t)R, 0);
+        uint32_t pr;
+        int64_t cnt;
+        amount_cols(ov.threshold, vals.data(), 1, &pr, &cnt);
+        ovr_vals.push_back(std::move(vals));
+        ovr_present.push_back(pr);
+        ovr_cnt.push_back(cnt);
+      }
+      ovr_off[t + 1] = (int32_t)ovr_begin.size();
+      for (auto& term : o.terms) {
+        if (!term.pod_sel.error.empty()) break;  // the reference returns this error before looking at later terms
+        term_flags.push_back(term.ns_sel.error.empty() ? 0 : KT_TERM_NS_INVALID);  // Q9: swallowed, the term is false
+        push_reqs(term.pod_sel.reqs);
+        pod_req_off.push_back((int32_t)req_key.size());
+        ns_reqs_of_term.push_back(o.kind == KT_KIND_CLUSTERTHROTTLE && term.ns_sel.error.empty() ? term.ns_sel.reqs : std::vector<Requirement>{});
+      }
+      term_off[t + 1] = (int32_t)term_flags.size();
+    }
+    // requirement pool layout: all podSelector requirements (term order), then all namespaceSelector ones
+    ns_req_off.push_back((int32_t)req_key.size());
+    for (auto& reqs : ns_reqs_of_term) {
+      push_reqs(reqs);
+      ns_req_off.push_back((int32_t)req_key.size());
+    }
+    const size_t n_ovr = ovr_begin.size();
+    std::vector<int64_t> ovr_thr((size_t)R * std::max<size_t>(n_ovr, 1), 0);
+    for (size_t i = 0; i < n_ovr; ++i)
+      for (int r = 0; r < R; ++r) ovr_thr[(size_t)r * n_ovr + i] = ovr_vals[i][(size_t)r];
+    kt_throttle_cols tc{};
+    tc.kind = kind.data(); tc.ns_id = nsid.data(); tc.flags = flags.data(); tc.thr = thr.data(); tc.thr_present = thr_present.data();
+    tc.thr_cnt = thr_cnt.data(); tc.ovr_off = ovr_off.data(); tc.n_ovr = (int32_t)n_ovr; tc.ovr_begin = ovr_begin.data(); tc.ovr_end = ovr_end.data();
+    tc.ovr_flags = ovr_flags.data(); tc.ovr_thr = ovr_thr.data(); tc.ovr_present = ovr_present.data(); tc.ovr_cnt = ovr_cnt.data();
+    kt_selector_table st{};
+    st.n_terms = (int32_t)term_flags.size(); st.n_reqs = (int32_t)req_key.size(); st.n_vals = (int32_t)req_vals.size();
+    st.term_off = term_off.data(); st.term_flags = term_flags.data(); st.pod_req_off = pod_req_off.data(); st.ns_req_off = ns_req_off.data();
+    st.req_key = req_key.data(); st.req_op = req_op.data(); st.req_val_off = req_val_off.data(); st.req_vals = req_vals.data();
+    sync_namespaces();  // Throttle rows may have introduced namespace ids
+    check(kt_upload_throttles(ctx, (int32_t)m, &tc, &st), "kt_upload_throttles");
+    throttles_dirty = false;
+    status_dirty = reserved_dirty = true;  // kt_upload_throttles forgets both
+  }
+
+  void sync_status() {
+    if (!status_dirty) return;
+    const int R = lim.n_resources;
+    const size_t m = throttles.size();
+    if (m == 0) { status_dirty = false; return; }
+    std::vector<uint8_t> calculated(m, 0);
+    std::vector<int64_t> calc_thr((size_t)R * m, 0), calc_cnt(m, 0), used((size_t)R * m, 0), used_cnt(m, 0);
+    std::vector<uint32_t> calc_present(m, 0), used_present(m, 0), throttled(m, 0);
+    for (size_t t = 0; t < m; ++t) {
+      const ThrottleObj& o = throttles[t];
+      calculated[t] = o.st_calc_at_set;  // !CalculatedAt.Time.IsZero() (throttle_types.go:129-132)
+      if (o.st_calc.has_counts) { calc_present[t] |= KT_COUNT_BIT; calc_cnt[t] = o.st_calc.pod; }
+      for (auto& kv : o.st_calc.requests) { calc_thr[(size_t)kv.first * m + t] = at_scale(kv.first, kv.second); calc_present[t] |= 1u << kv.first; }
+      if (o.st_used.has_counts) { used_present[t] |= KT_COUNT_BIT; used_cnt[t] = o.st_used.pod; }
+      for (auto& kv : o.st_used.requests) { used[(size_t)kv.first * m + t] = at_scale(kv.first, kv.second); used_present[t] |= 1u << kv.first; }
+      if (o.st_thr_pod) throttled[t] |= KT_COUNT_BIT;
+      for (auto& kv : o.st_thr_req)
+        if (kv.second) throttled[t] |= 1u << kv.first;
+    }
+    kt_status_cols sc{calculated.data(), calc_thr.data(), calc_present.data(), calc_cnt.data(), used.data(), used_present.data(), used_cnt.data(), throttled.data()};
+    check(kt_upload_status(ctx, &sc), "kt_upload_status");
+    status_dirty = false;
+  }
+
+  void sync_reserved() {
+    if (!reserved_dirty) return;
+    const int R = lim.n_resources;
+    const size_t m = throttles.size();
+    if (m == 0) { reserved_dirty = false; return; }
+    std::vector<int64_t> reserved((size_t)R * m, 0), cnt(m, 0);
+    std::vector<uint32_t> present(m, 0);
+    bool any = false;
+    for (size_t t = 0; t < m; ++t) {
+      const ThrottleObj& o = throttles[t];
+      auto it = cache[o.kind].by_thr.find(o.nn());
+      if (it == cache[o.kind].by_thr.end() || it->second.empty()) continue;
+      any = true;
+      present[t] |= KT_COUNT_BIT;  // every reserved ResourceAmountOfPod carries Counts{Pod: 1}
+      cnt[t] = (int64_t)it->second.size();
+      for (auto& pod : it->second)
+        for (auto& kv : pod.second) {
+          reserved[(size_t)kv.first * m + t] += at_scale(kv.first, kv.second);
+          present[t] |= 1u << kv.first;
+        }
+    }
+    if (any) check(kt_set_reserved(ctx, reserved.data(), present.data(), cnt.data()), "kt_set_reserved");
+    else check(kt_set_reserved(ctx, nullptr, nullptr, nullptr), "kt_set_reserved");
+    reserved_dirty = false;
+  }
+  void sync_all() {
+    sync_pods();
+    sync_namespaces();
+    sync_throttles();
+  }
+
+  // ---- results -> objects ------------------------------------------------------------------------------
+  Quantity from_scale(int c, int64_t v) const {
+    Quantity q;
+    q.mant = v;
+    q.exp = cols[c].scale_exp;
+    q.format = cols[c].format;
+    q.canon();
+    return q;
+  }
+  void amount_json(Writer& w, const ResAmount& a) const {
+    w.begin_obj();
+    if (a.has_counts) { w.key("resourceCounts").begin_obj().key("pod").num(a.pod).end_obj(); }
+    if (!a.requests_nil) {
+      w.key("resourceRequests").begin_obj();
+      for (auto& kv : a.requests) w.key(cols[kv.first].name).str(kt::decimal_string(kv.second));
+      w.end_obj();
+    }
+    w.end_obj();
+  }
+  static bool amount_equal(const ResAmount& a, const ResAmount& b) {  // apiequality.Semantic.DeepEqual on ResourceAmount
+    if (a.has_counts != b.has_counts || (a.has_counts && a.pod != b.pod)) return false;
+    if (a.requests.size() != b.requests.size()) return false;  // nil and empty maps are equal
+    for (auto& kv : a.requests) {
+      auto it = b.requests.find(kv.first);
+      if (it == b.requests.end() || kt::quantity_cmp(kv.second, it->second) != 0) return false;
+    }
+    return true;
+  }
+
+  // CalculateThreshold's Messages (throttle_types.go:78-84): "index %d: Failed to parse Begin|End: <time.Parse error>"
+  static std::vector<std::string> override_messages(const ThrottleObj& o) {
+    std::vector<std::string> msgs;
+    for (size_t i = 0; i < o.overrides.size(); ++i) {
+      GoTime t;
+      std::string e;
+      if (!o.overrides[i].begin.empty() && !(e = parse_rfc3339(o.overrides[i].begin, &t)).empty()) {
+        msgs.push_back("index " + std::to_string(i) + ": Failed to parse Begin: " + e);
+        continue;
+      }
+      if (!o.overrides[i].end.empty() && !(e = parse_rfc3339(o.overrides[i].end, &t)).empty())
+        msgs.push_back("index " + std::to_string(i) + ": Failed to parse End: " + e);
+    }
+    return msgs;
+  }
+
+  // ---- reconcile: every throttle in one device pass ------------------------------------------------
+  std::string reconcile_all(const std::string& now_s) {
+    GoTime now;
+    std::string e = parse_rfc3339(now_s, &now);
+    if (!e.empty()) fail(e);
+    sync_all();
+    const size_t m = throttles.size();
+    Writer w;
+    w.begin_obj();
+    if (m == 0) { w.key("reconciled").num(0).key("changed").begin_arr().end_arr().end_obj(); return w.out; }
+    check(kt_evaluate(ctx, clamp_ns(now.ns()), KT_EVAL_FRESH_STATUS | KT_EVAL_SKIP_CHECK), "kt_evaluate");
+    const int R = lim.n_resources;
+    std::vector<int64_t> used((size_t)R * m), used_cnt(m), calc_thr((size_t)R * m), calc_cnt(m);
+    std::vector<uint32_t> used_present(m), throttled(m), calc_present(m);
+    std::vector<uint8_t> ovr_active(m);
+    kt_reconcile_out ro{used.data(), used_present.data(), used_cnt.data(), throttled.data(), calc_thr.data(), calc_present.data(), calc_cnt.data(), ovr_active.data()};
+    check(kt_get_reconcile(ctx, &ro), "kt_get_reconcile");
+    // pods that are reserved somewhere: their match rows decide what reconcile un-reserves (:135-155)
+    std::vector<int64_t> rows;
+    std::vector<std::string> row_pod;
+    for (int k = 0; k < 2; ++k)
+      for (auto& thr : cache[k].by_thr)
+        for (auto& pod : thr.second) {
+          auto it = pod_index.find(pod.first);
+          if (it != pod_index.end() && std::find(row_pod.begin(), row_pod.end(), pod.first) == row_pod.end()) { rows.push_back(it->second); row_pod.push_back(pod.first); }
+        }
+    const int Wp = kt_match_words(ctx);
+    std::vector<uint32_t> words(rows.size() * (size_t)Wp);
+    if (!rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)rows.size(), rows.data(), words.data()), "kt_get_match_rows");
+
+    int reconciled = 0;
+    std::vector<std::string> changed;
+    for (size_t t = 0; t < m; ++t) {
+      ThrottleObj& o = throttles[t];
+      if (!o.live || o.throttler_name != name) continue;   // only responsible throttles are ever enqueued (:403-425)
+      if (!o.selector_error().empty()) continue;            // affectedPods fails -> reconcile returns the error, status untouched
+      ++reconciled;
+      ResAmount nu;  // used := ResourceAmount{}; used = used.Add(ResourceAmountOfPod(p)) ...
+      if (used_present[t] & KT_COUNT_BIT) {
+        nu.has_counts = true;
+        nu.pod = used_cnt[t];
+        nu.requests_nil = false;
+        for (int r = 0; r < (int)cols.size(); ++r)
+          if ((used_present[t] >> r) & 1) nu.requests[r] = from_scale(r, used[(size_t)r * m + t]);
+      }
+      ResAmount nc;  // CalculateThreshold(now).Threshold
+      nc.has_counts = calc_present[t] & KT_COUNT_BIT;
+      nc.pod = nc.has_counts ? calc_cnt[t] : 0;
+      nc.requests_nil = false;
+      for (int r = 0; r < (int)cols.size(); ++r)
+        if ((calc_present[t] >> r) & 1) nc.requests[r] = from_scale(r, calc_thr[(size_t)r * m + t]);
+      if (!ovr_active[t]) nc = o.threshold;  // no active override: spec.threshold itself (keeps nil-ness and spelling)
+      const std::vector<std::string> msgs = override_messages(o);
+      bool status_changed = false;
+      if (!amount_equal(o.st_calc, nc) || o.st_messages != msgs) {  // Q6: otherwise the old calculatedAt is kept
+        o.st_calc = nc;
+        o.st_calc_at_set = true;
+        o.st_calc_at = now.sec;
+        o.st_messages = msgs;
+        status_changed = true;
+      }
+      // newStatus.Throttled = CalculatedThreshold.Threshold.IsThrottled(Used, true): one entry per threshold resource
+      const bool thr_pod = throttled[t] & KT_COUNT_BIT;
+      std::map<int, bool> thr_req;
+      for (auto& kv : o.st_calc.requests) thr_req[kv.first] = (throttled[t] >> kv.first) & 1;
+      const bool thr_nil = o.st_calc.requests.empty();
+      if (thr_pod != o.st_thr_pod || thr_req != o.st_thr_req) status_changed = true;
+      o.st_thr_pod = thr_pod;
+      o.st_thr_req = thr_req;
+      o.st_thr_req_nil = thr_nil;
+      if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
+      o.st_used = nu;
+      if (status_changed) changed.push_back(o.nn());
+      // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache
+      auto it = cache[o.kind].by_thr.find(o.nn());
+      if (it != cache[o.kind].by_thr.end())
+        for (size_t i = 0; i < rows.size(); ++i)
+          if ((words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)
+            if (it->second.erase(row_pod[i])) reserved_dirty = true;
+    }
+    status_dirty = true;
+    w.key("reconciled").num(reconciled).key("changed").begin_arr();
+    for (auto& c : changed) w.str(c);
+    w.end_arr().end_obj();
+    return w.out;
+  }
+
+  // ---- pending pods: one device pass for a batch ----------------------------------------------------------
+  struct PendingResult {
+    std::vector<uint32_t> bitmap, codes;
+    std::vector<uint8_t> admit;
+    int Wp = 0;
+  };
+  PendingResult check_pending(const std::vector<PodObj>& batch, uint32_t extra_flags) {
+    sync_all();
+    sync_status();
+    sync_reserved();
+    const int L = lim.label_slots, R = lim.n_resources;
+    const size_t k = batch.size();
+    std::vector<int64_t> lab((size_t)L * k), req((size_t)R * k);
+    std::vector<uint32_t> present(k), flags(k);
+    std::vector<int32_t> nsid(k);
+    for (size_t i = 0; i < k; ++i) pack_pod(batch[i], lab, req, present, flags, nsid, k, i);
+    if (namespaces_dirty || throttles_dirty) { sync_all(); sync_status(); sync_reserved(); }  // packing introduced new namespace ids
+    check(kt_upload_pods(ctx, KT_PODS_PENDING, (int64_t)k, lab.data(), req.data(), present.data(), flags.data(), nsid.data()), "kt_upload_pods(pending)");
+    PendingResult out;
+    out.Wp = kt_match_words(ctx);
+    out.bitmap.assign(k * (size_t)out.Wp, 0);
+    out.codes.assign(k * 2 * (size_t)out.Wp, 0);
+    out.admit.assign(k, 1);
+    if (throttles.empty() || k == 0) return out;
+    // PreFilter reads the informer copy of .status; reconcile is a separate event (KT_EVAL_GIVEN_STATUS)
+    check(kt_evaluate(ctx, 0, KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE | extra_flags), "kt_evaluate");
+    check(kt_get_check(ctx, out.codes.data(), out.admit.data()), "kt_get_check");
+    check(kt_get_match_bitmap(ctx, KT_PODS_PENDING, out.bitmap.data()), "kt_get_match_bitmap");
+    return out;
+  }
+  std::vector<int> affected(const PendingResult& r, size_t i, int kind) const {
+    std::vector<int> out;
+    for (size_t t = 0; t < throttles.size(); ++t)
+      if (throttles[t].kind == kind && ((r.bitmap[i * (size_t)r.Wp + (t >> 5)] >> (t & 31)) & 1)) out.push_back((int)t);
+    return out;
+  }
+  // affectedThrottles / affectedClusterThrottles error paths that never reach the device:
+  // an invalid podSelector (MatchesToPod returns the error) and a namespace the informer does not know.
+  std::string controller_error(const PodObj& pod, const PendingResult& r, size_t i, int kind) {
+    if (kind == KT_KIND_CLUSTERTHROTTLE) {
+      const int id = ns_dict.find(pod.ns);
+      if (id < 0 || !namespaces[(size_t)id].exists) return "namespace \"" + pod.ns + "\" not found";  // namespaceInformer.Lister().Get (clusterthrottle_controller.go:273-276)
+    }
+    for (size_t t = 0; t < throttles.size(); ++t) {
+      const ThrottleObj& o = throttles[t];
+      if (!o.live || o.kind != kind || o.throttler_name != name) continue;
+      const std::string e = o.selector_error();
+      if (e.empty()) continue;
+      if (kind == KT_KIND_THROTTLE && o.ns != pod.ns) continue;
+      if ((r.bitmap[i * (size_t)r.Wp + (t >> 5)] >> (t & 31)) & 1) continue;  // an earlier, valid term already matched
+      return e;
+    }
+    return "";
+  }
+
+  void names_json(Writer& w, const char* key, const std::vector<int>& idx) const {
+    w.key(key).begin_arr();
+    for (int t : idx) w.str(throttles[(size_t)t].nn());
+    w.end_arr();
+  }
+  std::string join_names(const std::vector<int>& idx) const {
+    std::string s;
+    for (size_t i = 0; i < idx.size(); ++i) s += (i ? "," : "") + throttles[(size_t)idx[i]].nn();
+    return s;
+  }
+  // plugin.go:148-215
+  void prefilter_json(Writer& w, const PodObj& pod, const PendingResult& r, size_t i) {
+    std::vector<int> bucket[2][4], aff[2];
+    std::string err;
+    for (int kind = 0; kind < 2 && err.empty(); ++kind) {  // throttleCtr first, then clusterThrottleCtr (plugin.go:153,165)
+      err = controller_error(pod, r, i, kind);
+      if (!err.empty()) break;
+      aff[kind] = affected(r, i, kind);
+      for (int t : aff[kind]) {
+        const uint32_t code = (r.codes[i * 2 * (size_t)r.Wp + ((size_t)t >> 4)] >> (2 * (t & 15))) & 3u;
+        bucket[kind][code].push_back(t);
+      }
+    }
+    w.begin_obj();
+    if (!err.empty()) {
+      w.key("code").str("Error").key("reasons").begin_arr().str(err).end_arr().end_obj();
+      return;
+    }
+    const int T = KT_KIND_THROTTLE, C = KT_KIND_CLUSTERTHROTTLE;
+    const auto& ex_c = bucket[C][KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD];
+    const auto& ex_t = bucket[T][KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD];
+    size_t total = 0;
+    for (int kind = 0; kind < 2; ++kind)
+      for (int c = 1; c < 4; ++c) total += bucket[kind][c].size();
+    std::vector<std::string> reasons;
+    auto reason = [&](const char* what, const char* status, const std::vector<int>& v) {
+      if (!v.empty()) reasons.push_back(std::string(what) + "[" + status + "]=" + join_names(v));
+    };
+    if (total) {  // fixed order (Q10)
+      reason("clusterthrottle", "pod-requests-exceeds-threshold", ex_c);
+      reason("throttle", "pod-requests-exceeds-threshold", ex_t);
+      reason("clusterthrottle", "active", bucket[C][KT_CHECK_ACTIVE]);
+      reason("throttle", "active", bucket[T][KT_CHECK_ACTIVE]);
+      reason("clusterthrottle", "insufficient", bucket[C][KT_CHECK_INSUFFICIENT]);
+      reason("throttle", "insufficient", bucket[T][KT_CHECK_INSUFFICIENT]);
+    }
+    w.key("code").str(total ? "UnschedulableAndUnresolvable" : "Success");
+    w.key("reasons").begin_arr();
+    for (auto& s : reasons) w.str(s);
+    w.end_arr();
+    if (!ex_c.empty() || !ex_t.empty()) {
+      std::vector<int> both = ex_c;
+      both.insert(both.end(), ex_t.begin(), ex_t.end());
+      w.key("event").begin_obj().key("type").str("Warning").key("reason").str("ResourceRequestsExceedsThrottleThreshold");
+      w.key("message").str("It won't be scheduled unless decreasing resource requests or increasing ClusterThrottle/Throttle threshold because its resource "
+                           "requests exceeds their thresholds: " + join_names(both));
+      w.end_obj();
+    }
+    const char* ctl[2] = {"throttle", "clusterthrottle"};
+    for (int kind = 0; kind < 2; ++kind) {
+      w.key(ctl[kind]).begin_obj();
+      names_json(w, "active", bucket[kind][KT_CHECK_ACTIVE]);
+      names_json(w, "insufficient", bucket[kind][KT_CHECK_INSUFFICIENT]);
+      names_json(w, "podRequestsExceedsThreshold", bucket[kind][KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD]);
+      names_json(w, "affected", aff[kind]);
+      w.end_obj();
+    }
+    w.end_obj();
+  }
+
+  // Reserve / UnReserve (throttle_controller.go:271-331): the pod's affected throttles come from the device
+  std::string reserve_json(const Node& pod_node, bool reserve) {
+    PodObj pod = pod_from(pod_node);
+    PendingResult r = check_pending({pod}, 0);
+    std::vector<std::string> errs;
+    const char* ctl[2] = {"ThrottleController", "ClusterThrottleController"};
+    for (int kind = 0; kind < 2; ++kind) {
+      const std::string e = controller_error(pod, r, 0, kind);
+      if (!e.empty()) {
+        errs.push_back(std::string(reserve ? "Failed to reserve pod=" : "Failed to unreserve pod ") + pod.nn() + " in " + ctl[kind] + ": " + e);
+        continue;
+      }
+      for (int t : affected(r, 0, kind)) {
+        if (reserve) cache[kind].add(throttles[(size_t)t].nn(), pod);
+        else cache[kind].remove(throttles[(size_t)t].nn(), pod.nn());
+        reserved_dirty = true;
+      }
+    }
+    Writer w;
+    w.begin_obj();
+    if (reserve && !errs.empty()) {  // Reserve aggregates into one Error status; Unreserve only logs (plugin.go:223-235,246-254)
+      w.key("code").str("Error").key("reasons").begin_arr();
+      for (auto& e : errs) w.str(e);
+      w.end_arr();
+    } else {
+      w.key("code").str("Success");
+    }
+    w.end_obj();
+    return w.out;
+  }
+
+  // ---- informer events --------------------------------------------------------------------------------
+  void apply_pod(const Node& v) {
+    PodObj p = pod_from(v);
+    auto it = pod_index.find(p.nn());
+    if (it == pod_index.end()) {
+      int64_t row;
+      if (!free_rows.empty()) { row = free_rows.back(); free_rows.pop_back(); }
+      else { row = (int64_t)pods.size(); pods.emplace_back(); }
+      p.row = row;
+      pod_index[p.nn()] = row;
+      pods[(size_t)row] = std::move(p);
+      dirty_rows.insert(row);
+      return;
+    }
+    PodObj& old = pods[(size_t)it->second];
+    p.row = old.row;
+    // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
+    // then the pod's reservation moves from (old \ new) to (new \ old) throttles
+    const bool relevant = should_count_in(old) || should_count_in(p);
+    if (relevant && !throttles.empty() && old.labels != p.labels) {
+      PendingResult r = check_pending({old, p}, 0);
+      for (int kind = 0; kind < 2; ++kind) {
+        if (!controller_error(old, r, 0, kind).empty() || !controller_error(p, r, 1, kind).empty()) continue;  // HandleError + return
+        const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
+        for (int t : a)
+          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), p.nn()); reserved_dirty = true; }
+        for (int t : b)
+          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), p); reserved_dirty = true; }
+      }
+    }
+    const int64_t row = old.row;
+    pods[(size_t)row] = std::move(p);
+    dirty_rows.insert(row);
+  }
+  void delete_pod(const std::string& ns, const std::string& pname) {
+    auto it = pod_index.find(ns + "/" + pname);
+    if (it == pod_index.end()) return;
+    const int64_t row = it->second;
+    PodObj old = pods[(size_t)row];
+    // DeleteFunc (:509-515): a scheduled pod that disappears is un-reserved from its affected throttles
+    if (should_count_in(old) && !old.node_name.empty() && !throttles.empty()) {
+      PendingResult r = check_pending({old}, 0);
+      for (int kind = 0; kind < 2; ++kind) {
+        if (!controller_error(old, r, 0, kind).empty()) continue;
+        for (int t : affected(r, 0, kind))
+          if (cache[kind].remove(throttles[(size_t)t].nn(), old.nn())) reserved_dirty = true;
+      }
+    }
+    pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
+    pods[(size_t)row].row = row;
+    pod_index.erase(it);
+    free_rows.push_back(row);
+    dirty_rows.insert(row);
+  }
+  void apply_namespace(const Node& v) {
+    const std::string nm = v["metadata"]["name"].str();
+    const int32_t id = ns_id(nm);
+    NamespaceObj& n = namespaces[(size_t)id];
+    n.exists = true;
+    n.labels.clear();
+    for (auto& kv : v["metadata"]["labels"].obj) n.labels.emplace_back(kv.first, kv.second->str());
+    if ((int)n.labels.size() > max_ns_labels) {
+      max_ns_labels = (int)n.labels.size();
+      if (max_ns_labels > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than 32 labels");
+      if (ctx && max_ns_labels > lim.ns_label_slots) drop_engine();
+    }
+    namespaces_dirty = true;
+  }
+  void apply_throttle(const Node& v, int kind) {
+    ThrottleObj o;
+    o.kind = kind;
+    const Node& md = v["metadata"];
+    o.ns = kind == KT_KIND_THROTTLE ? md["namespace"].str() : "";
+    o.name = md["name"].str();
+    const Node& spec = v["spec"];
+    o.throttler_name = spec["throttlerName"].str();
+    o.threshold = res_amount(spec["threshold"]);
+    for (auto& ov : spec["temporaryThresholdOverrides"].arr) {
+      Override x;
+      x.begin = (*ov)["begin"].str();
+      x.end = (*ov)["end"].str();
+      x.threshold = res_amount((*ov)["threshold"]);
+      o.overrides.push_back(std::move(x));
+    }
+    // the reference's JSON tag is "selectorTerms" (throttle_selector.go:26)
+    for (auto& t : spec["selector"]["selectorTerms"].arr) {
+      Term term;
+      term.pod_sel = compile_selector((*t)["podSelector"]);
+      if (kind == KT_KIND_CLUSTERTHROTTLE) term.ns_sel = compile_selector((*t)["namespaceSelector"]);
+      o.terms.push_back(std::move(term));
+    }
+    o.live = true;
+    const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
+    auto it = thr_index.find(key);
+    const Node& st = v["status"];
+    if (it == thr_index.end()) {
+      thr_index[key] = (int)throttles.size();
+      throttles.push_back(std::move(o));
+      it = thr_index.find(key);
+    } else {  // spec update: the status subresource is kept unless the manifest carries one
+      ThrottleObj& old = throttles[(size_t)it->second];
+      o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
+      o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
+      old = std::move(o);
+    }
+    if (st.is(Node::Obj)) {
+      ThrottleObj& x = throttles[(size_t)it->second];
+      const Node& ct = st["calculatedThreshold"];
+      x.st_calc = res_amount(ct["threshold"]);
+      x.st_calc_at_set = false;
+      x.st_calc_at = 0;
+      if (ct["calculatedAt"].is(Node::Str) && !ct["calculatedAt"].text.empty()) {
+        GoTime at;
+        const std::string e = parse_rfc3339(ct["calculatedAt"].text, &at);
+        if (!e.empty()) fail(e);
+        x.st_calc_at_set = !at.zero;
+        x.st_calc_at = at.sec;
+      }
+      x.st_messages.clear();
+      for (auto& mnode : ct["messages"].arr) x.st_messages.push_back(mnode->str());
+      x.st_thr_pod = st["throttled"]["resourceCounts"]["pod"].boolean(false);
+      x.st_thr_req.clear();
+      x.st_thr_req_nil = !st["throttled"]["resourceRequests"].is(Node::Obj);
+      for (auto& kv : st["throttled"]["resourceRequests"].obj) x.st_thr_req[column(kv.first)] = kv.second->boolean(false);
+      x.st_used = res_amount(st["used"]);
+    }
+    throttles_dirty = status_dirty = reserved_dirty = true;
+  }
+  void delete_throttle(int kind, const std::string& ns, const std::string& tname) {
+    const std::string nn = (kind == KT_KIND_THROTTLE ? ns : std::string()) + "/" + tname;
+    auto it = thr_index.find(std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + nn);
+    if (it == thr_index.end()) return;
+    // the column is kept (device order is insertion order) but can never match or be reconciled again
+    ThrottleObj& o = throttles[(size_t)it->second];
+    o.live = false;
+    o.terms.clear();
+    cache[kind].by_thr.erase(nn);
+    thr_index.erase(it);
+    throttles_dirty = status_dirty = reserved_dirty = true;
+  }
+
+  std::string status_json(const std::string& ns, const std::string& tname) {
+    auto it = thr_index.find(ns.empty() ? "C:/" + tname : "T:" + ns + "/" + tname);
+    if (it == thr_index.end()) fail("throttle " + ns + "/" + tname + " not found");
+    const ThrottleObj& o = throttles[(size_t)it->second];
+    Writer w;
+    w.begin_obj().key("calculatedThreshold").begin_obj().key("threshold");
+    amount_json(w, o.st_calc);
+    w.key("calculatedAtSet").boolean(o.st_calc_at_set).key("calculatedAtUnix").num(o.st_calc_at);
+    if (!o.st_messages.empty()) {
+      w.key("messages").begin_arr();
+      for (auto& s : o.st_messages) w.str(s);
+      w.end_arr();
+    }
+    w.end_obj();
+    w.key("throttled").begin_obj().key("resourceCounts").begin_obj().key("pod").boolean(o.st_thr_pod).end_obj();
+    if (!o.st_thr_req_nil) {
+      w.key("resourceRequests").begin_obj();
+      for (auto& kv : o.st_thr_req) w.key(cols[(size_t)kv.first].name).boolean(kv.second);
+      w.end_obj();
+    }
+    w.end_obj();
+    w.key("used");
+    amount_json(w, o.st_used);
+    w.end_obj();
+    return w.out;
+  }
+  std::string reserved_json(int kind, const std::string& nn) {
+    Writer w;
+    ResAmount total;
+    std::vector<std::string> names;
+    auto it = cache[kind ? 1 : 0].by_thr.find(nn);
+    if (it != cache[kind ? 1 : 0].by_thr.end())
+      for (auto& pod : it->second) {  // totalResoruceAmount (:148-156): result = result.Add(ResourceAmountOfPod)
+        names.push_back(pod.first);
+        total.has_counts = true;
+        total.pod += 1;
+        total.requests_nil = false;
+        for (auto& kv : pod.second) {
+          auto f = total.requests.find(kv.first);
+          if (f == total.requests.end()) total.requests[kv.first] = kv.second;
+          else f->second = kt::quantity_add(f->second, kv.second);
+        }
+      }
+    w.begin_obj().key("amount");
+    amount_json(w, total);
+    w.key("pods").begin_arr();
+    for (auto& n : names) w.str(n);
+    w.end_arr().end_obj();
+    return w.out;
+  }
+};
+
+namespace {
+
+template <class F>
+const char* guarded(kth_plugin* p, F&& f) {
+  if (!p) return ret(err_json("null plugin handle"));
+  std::lock_guard<std::mutex> lk(p->mu);
+  try {
+    return ret(f());
+  } catch (const std::exception& e) {
+    return ret(err_json(e.what()));
+  }
+}
+
+// kth_eval: host-only pieces, no device (a scratch plugin supplies the dictionaries)
+std::string eval_request(const Node& req) {
+  const std::string fn = req["fn"].str();
+  kth_plugin scratch;
+  Writer w;
+  if (fn == "ParseQuantity" || fn == "CanonicalQuantity") {
+    const Quantity q = kt::parse_quantity(req["value"].scalar());
+    w.begin_obj().key("decimal").str(kt::decimal_string(q)).key("format").num((int)q.format);
+    w.key("canonical").str(kt::canonical_string(q.mant, q.exp, q.format)).end_obj();
+    return w.out;
+  }
+  if (fn == "PodRequestResourceList" || fn == "ResourceAmountOfPod") {
+    const PodObj p = scratch.pod_from(req["pod"]);
+    ResAmount a;
+    a.requests_nil = false;
+    a.requests = p.request;
+    if (fn == "ResourceAmountOfPod") { a.has_counts = true; a.pod = 1; }
+    if (fn == "PodRequestResourceList") {
+      w.begin_obj();
+      for (auto& kv : a.requests) w.key(scratch.cols[(size_t)kv.first].name).str(kt::decimal_string(kv.second));
+      w.end_obj();
+    } else {
+      scratch.amount_json(w, a);
+    }
+    return w.out;
+  }
+  if (fn == "ParseRFC3339") {
+    GoTime t;
+    const std::string e = parse_rfc3339(req["value"].str(), &t);
+    w.begin_obj();
+    if (!e.empty()) w.key("error").str(e);
+    w.key("unix").num(t.sec).key("nsec").num(t.nsec).end_obj();
+    return w.out;
+  }
+  if (fn == "OverrideMessages") {
+    scratch.apply_throttle(req["throttle"], req["throttle"]["kind"].str("Throttle") == "ClusterThrottle" ? KT_KIND_CLUSTERTHROTTLE : KT_KIND_THROTTLE);
+    w.begin_arr();
+    for (auto& s : kth_plugin::override_messages(scratch.throttles[0])) w.str(s);
+    w.end_arr();
+    return w.out;
+  }
+  if (fn == "ValidateSelector") {
+    const CompiledSelector c = compile_selector(req["selector"]);
+    w.begin_obj().key("valid").boolean(c.error.empty());
+    if (!c.error.empty()) w.key("error").str(c.error);
+    w.key("requirements").num((long long)c.reqs.size()).end_obj();
+    return w.out;
+  }
+  fail("unknown fn: " + fn);
+}
+
+}  // namespace
+
+extern "C" {
+
+int kth_new_plugin(kth_plugin** out, const char* args_json, int device) {
+  if (!out) return KT_ERR_INVALID;
+  *out = nullptr;
+  try {
+    ktjson::NodePtr args = ktjson::parse(args_json ? args_json : "{}");
+    // DecodePluginArgs (plugin_args.go:42-60): name and targetSchedulerName are required
+    const std::string nm = (*args)["name"].str(), target = (*args)["targetSchedulerName"].str();
+    if (nm.empty()) { g_new_plugin_error = "Name must not be empty"; return KT_ERR_INVALID; }
+    if (target.empty()) { g_new_plugin_error = "TargetSchedulerName must not be empty"; return KT_ERR_INVALID; }
+    kth_plugin* p = new kth_plugin();
+    p->name = nm;
+    p->target_scheduler = target;
+    p->device = device;
+    try {
+      p->ensure_engine();  // fail at construction, like NewPlugin does when its controllers cannot start
+    } catch (const std::exception& e) {
+      g_new_plugin_error = e.what();
+      delete p;
+      return KT_ERR_CUDA;
+    }
+    p->drop_engine();  // created again with the right limits once objects arrive
+    *out = p;
+    return KT_OK;
+  } catch (const std::exception& e) {
+    g_new_plugin_error = e.what();
+    return KT_ERR_INVALID;
+  }
+}
+const char* kth_new_plugin_error(void) { return g_new_plugin_error.c_str(); }
+void kth_free(kth_plugin* p) {
+  if (!p) return;
+  if (p->ctx) kt_destroy(p->ctx);
+  delete p;
+}
+
+const char* kth_apply(kth_plugin* p, const char* manifest_json) {
+  return guarded(p, [&]() -> std::string {
+    ktjson::NodePtr v = ktjson::parse(manifest_json);
+    const std::string kind = (*v)["kind"].str();
+    if (kind == "Pod") p->apply_pod(*v);
+    else if (kind == "Namespace") p->apply_namespace(*v);
+    else if (kind == "Throttle") p->apply_throttle(*v, KT_KIND_THROTTLE);
+    else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
+    else fail("unsupported kind: " + kind);
+    return "{\"ok\":true}";
+  });
+}
+const char* kth_delete(kth_plugin* p, const char* kind, const char* ns, const char* name) {
+  return guarded(p, [&]() -> std::string {
+    const std::string k = kind ? kind : "", n = ns ? ns : "", nm = name ? name : "";
+    if (k == "Pod") p->delete_pod(n, nm);
+    else if (k == "Throttle") p->delete_throttle(KT_KIND_THROTTLE, n, nm);
+    else if (k == "ClusterThrottle") p->delete_throttle(KT_KIND_CLUSTERTHROTTLE, "", nm);
+    else if (k == "Namespace") {
+      const int id = p->ns_dict.find(nm);
+      if (id >= 0) { p->namespaces[(size_t)id].exists = false; p->namespaces[(size_t)id].labels.clear(); p->namespaces_dirty = true; }
+    } else fail("unsupported kind: " + k);
+    return "{\"ok\":true}";
+  });
+}
+const char* kth_reconcile_all(kth_plugin* p, const char* now_rfc3339) {
+  return guarded(p, [&]() { return p->reconcile_all(now_rfc3339 ? now_rfc3339 : ""); });
+}
+const char* kth_get_status(kth_plugin* p, const char* ns, const char* name) {
+  return guarded(p, [&]() { return p->status_json(ns ? ns : "", name ? name : ""); });
+}
+const char* kth_pre_filter(kth_plugin* p, const char* pod_json) {
+  return guarded(p, [&]() {
+    ktjson::NodePtr v = ktjson::parse(pod_json);
+    std::vector<PodObj> batch{p->pod_from(*v)};
+    kth_plugin::PendingResult r = p->check_pending(batch, 0);  // PreFilter passes isThrottledOnEqual = false
+    Writer w;
+    p->prefilter_json(w, batch[0], r, 0);
+    return w.out;
+  });
+}
+const char* kth_pre_filter_batch(kth_plugin* p, const char* pods_json) {
+  return guarded(p, [&]() {
+    ktjson::NodePtr v = ktjson::parse(pods_json);
+    if (!v->is(Node::Arr)) fail("expected a JSON array of pods");
+    std::vector<PodObj> batch;
+    for (auto& e : v->arr) batch.push_back(p->pod_from(*e));
+    kth_plugin::PendingResult r = p->check_pending(batch, 0);
+    Writer w;
+    w.begin_arr();
+    for (size_t i = 0; i < batch.size(); ++i) p->prefilter_json(w, batch[i], r, i);
+    w.end_arr();
+    return w.out;
+  });
+}
+const char* kth_reserve(kth_plugin* p, const char* pod_json) {
+  return guarded(p, [&]() { return p->reserve_json(*ktjson::parse(pod_json), true); });
+}
+const char* kth_unreserve(kth_plugin* p, const char* pod_json) {
+  return guarded(p, [&]() { return p->reserve_json(*ktjson::parse(pod_json), false); });
+}
+const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn) {
+  return guarded(p, [&]() { return p->reserved_json(kind, throttle_nn ? throttle_nn : ""); });
+}
+const char* kth_eval(const char* request_json) {
+  try {
+    return ret(eval_request(*ktjson::parse(request_json)));
+  } catch (const std::exception& e) {
+    return ret(err_json(e.what()));
+  }
+}
+
+}  // extern "C"

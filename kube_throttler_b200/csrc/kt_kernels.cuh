@@ -790,4 +790,13 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* 
   d_ns[row] = ns[i];
 }
 
+// Gather k bitmap rows (one warp-wide strided copy per row).
+__global__ void __launch_bounds__(256) k_gather_rows(int64_t k, const int64_t* __restrict__ rows, int Wp, const uint32_t* __restrict__ bitmap,
+                                                     uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (i >= k) return;
+  const int64_t row = rows[i];
+  for (int w = threadIdx.x & 31; w < Wp; w += 32) out[i * Wp + w] = bitmap[row * Wp + w];
+}
+
 }  // namespace kt

@@ -1,0 +1,104 @@
+"""ctypes binding of include/kt_host.h: the kube-scheduler plugin surface above the device engine.
+
+`Plugin` reads like the reference's plugin: `Plugin(name, target_scheduler_name)` is NewPlugin
+(plugin.go:63), `pre_filter` / `reserve` / `unreserve` are PreFilter / Reserve / Unreserve (plugin.go:148-257),
+`apply` / `delete` are the informer events and `reconcile_all` runs every throttle's reconcile(key)
+(throttle_controller.go:84) as one device pass.  Manifests are plain dicts (Kubernetes JSON).
+Nothing is computed here; every call crosses the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+from . import KtError, abi, lib
+
+
+def _bind():
+    L = lib()
+    if getattr(L, "_kth_bound", False):
+        return L
+    vp, cp = C.c_void_p, C.c_char_p
+    L.kth_new_plugin.argtypes = [C.POINTER(vp), cp, C.c_int]
+    L.kth_new_plugin_error.restype = cp
+    L.kth_free.argtypes = [vp]
+    L.kth_free.restype = None
+    for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_reconcile_all", [vp, cp]),
+                       ("kth_get_status", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
+                       ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_eval", [cp])):
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = cp
+    L._kth_bound = True
+    return L
+
+
+HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status",
+                "kth_pre_filter", "kth_pre_filter_batch", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_eval"]
+
+
+def _result(raw):
+    out = json.loads(raw.decode())
+    if isinstance(out, dict) and set(out.keys()) == {"error"}:
+        raise RuntimeError(out["error"])
+    return out
+
+
+def eval_host(fn: str, **kw):
+    """Host-only packer helpers (kth_eval): no device involved."""
+    return _result(_bind().kth_eval(json.dumps(dict(kw, fn=fn)).encode()))
+
+
+class Plugin:
+    """kubethrottler.NewPlugin(configuration, handle) -- fails without a GPU (there is no CPU path)."""
+
+    def __init__(self, name="kube-throttler", target_scheduler_name="my-scheduler", device=0, **extra_args):
+        self._L = _bind()
+        self._h = C.c_void_p()
+        args = dict(extra_args, name=name, targetSchedulerName=target_scheduler_name)
+        rc = self._L.kth_new_plugin(C.byref(self._h), json.dumps(args).encode(), device)
+        if rc != abi.OK:
+            self._h = None
+            raise KtError(rc, self._L.kth_new_plugin_error().decode())
+
+    def close(self):
+        if self._h:
+            self._L.kth_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # informer events
+    def apply(self, *manifests):
+        for m in manifests:
+            _result(self._L.kth_apply(self._h, json.dumps(m).encode()))
+
+    def delete(self, kind, name, namespace=""):
+        _result(self._L.kth_delete(self._h, kind.encode(), namespace.encode(), name.encode()))
+
+    # controllers
+    def reconcile_all(self, now="2026-01-01T00:00:00Z"):
+        return _result(self._L.kth_reconcile_all(self._h, now.encode()))
+
+    def status(self, name, namespace=""):
+        return _result(self._L.kth_get_status(self._h, namespace.encode(), name.encode()))
+
+    # plugin
+    def prefilter(self, pod):
+        return _result(self._L.kth_pre_filter(self._h, json.dumps(pod).encode()))
+
+    def prefilter_batch(self, pods):
+        return _result(self._L.kth_pre_filter_batch(self._h, json.dumps(list(pods)).encode()))
+
+    def reserve(self, pod):
+        return _result(self._L.kth_reserve(self._h, json.dumps(pod).encode()))
+
+    def unreserve(self, pod):
+        return _result(self._L.kth_unreserve(self._h, json.dumps(pod).encode()))
+
+    def reserved(self, kind: str, thr_nn: str):
+        return _result(self._L.kth_reserved(self._h, 0 if kind == "Throttle" else 1, thr_nn.encode()))

@@ -9,10 +9,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    text = open(os.path.join(ROOT, "include", "kt_b200.h")).read()
+def header_functions(header="kt_b200.h", prefix="kt_"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(kt_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", text)))
 
 
 def test_header_exports_match_library(kt):
@@ -22,6 +22,18 @@ def test_header_exports_match_library(kt):
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/kt_b200.h but not exported by libkt_b200.so"
     assert sorted(kt.EXPORTS) == names, "python binding and header disagree"
+
+
+def test_host_header_exports_match_library(kt):
+    """include/kt_host.h (the plugin surface: NewPlugin / PreFilter / Reserve / Unreserve) is exported too."""
+    from kube_throttler_b200 import host
+
+    L = kt.lib()
+    names = header_functions("kt_host.h", "kth_")
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/kt_host.h but not exported by libkt_b200.so"
+    assert sorted(host.HOST_EXPORTS) == names, "python binding and kt_host.h disagree"
 
 
 def test_struct_layouts(kt):

@@ -1,0 +1,117 @@
+"""Host-side packer of the PRODUCT (kube_throttler_b200/csrc/kt_host.cc via kth_eval), CPU only.
+
+The same vectors that pin the oracle (reference unit tests) are run against the product's own
+Quantity parser, PodRequestResourceList, RFC3339/override messages and selector validation, and the two
+independent implementations (product host layer vs oracle) are compared on a wider input set.
+No device is touched: kth_eval is host-only by construction.
+"""
+from fractions import Fraction
+
+import pytest
+
+from test_oracle_kat import rl_values
+
+
+@pytest.fixture(scope="module")
+def host(kt):
+    from kube_throttler_b200 import host as h
+
+    return h
+
+
+QUANTITIES = [
+    ("0", 0), ("1", 1), ("-2", -2), ("+3", 3), ("500m", Fraction(1, 2)), ("1.1", Fraction(11, 10)), ("0.200", Fraction(1, 5)),
+    ("512Mi", 536870912), ("1Gi", 2**30), ("1Ki", 1024), ("1.5Gi", 3 * 2**29), ("100n", Fraction(1, 10**7)), ("5u", Fraction(5, 10**6)),
+    ("3k", 3000), ("2M", 2 * 10**6), ("1G", 10**9), ("1T", 10**12), ("1P", 10**15), ("1E", 10**18), ("1e3", 1000), ("1E-3", Fraction(1, 1000)),
+    ("12e6", 12 * 10**6), (".5", Fraction(1, 2)), ("5.", 5), ("0.0000000001", Fraction(1, 10**9)), ("1.0000000001", Fraction(10**9 + 1, 10**9)),
+    ("-0.0000000001", Fraction(-1, 10**9)), ("16Ei", 2**63 - 1), ("0.1Ki", Fraction(1024, 10)), ("50m", Fraction(1, 20)), ("1000m", 1),
+]
+
+
+@pytest.mark.parametrize("s,want", QUANTITIES)
+def test_parse_quantity_values(host, oracle, s, want):
+    got = host.eval_host("ParseQuantity", value=s)
+    assert Fraction(got["decimal"]) == want
+    ref = oracle.call("ParseQuantity", value=s)  # two independent parsers agree, value and format class
+    assert Fraction(ref["decimal"]) == want and ref["format"] == got["format"]
+
+
+@pytest.mark.parametrize("s", ["", "abc", "1x", "1Kii", "--1", "1e", "1e1.5", "1 ", " 1", "1.1.M", "0.1mi", "1i"])
+def test_parse_quantity_errors(host, s):
+    with pytest.raises(RuntimeError):
+        host.eval_host("ParseQuantity", value=s)
+
+
+@pytest.mark.parametrize("s,canon", [("500m", "500m"), ("0.5", "500m"), ("1", "1"), ("1000m", "1"), ("900m", "900m"), ("1.1", "1100m"),
+                                     ("512Mi", "512Mi"), ("1536Mi", "1536Mi"), ("1Gi", "1Gi"), ("2000", "2k"), ("100n", "100n"), ("0", "0")])
+def test_canonical_quantity_strings(host, s, canon):
+    """resource.Quantity.String spellings the integration suite asserts on status fields
+    (util_throttle_test.go:169-177: "500m", "200m", "900m", "1"; README.md:287-309: 512Mi)."""
+    assert host.eval_host("CanonicalQuantity", value=s)["canonical"] == canon
+
+
+def test_pod_request_resource_list(host, oracle):
+    """resourcelist_test.go:47-117"""
+    pod = {"kind": "Pod", "metadata": {"name": "p"}, "spec": {"containers": [
+        {"resources": {"requests": {"n1": "1"}}}, {"resources": {"requests": {"n1": "1"}}}]}}
+    assert rl_values(host.eval_host("PodRequestResourceList", pod=pod)) == {"n1": 2}
+    pod["spec"]["initContainers"] = [{"resources": {"requests": {"n1": "1"}}}, {"resources": {"requests": {"n2": "2"}}}]
+    assert rl_values(host.eval_host("PodRequestResourceList", pod=pod)) == {"n1": 2, "n2": 2}
+    pod["spec"]["overhead"] = {"n1": "500m", "n3": "1"}
+    assert rl_values(host.eval_host("PodRequestResourceList", pod=pod)) == {"n1": Fraction(5, 2), "n2": 2, "n3": 1}
+    # init container larger than the container sum wins; zero-valued init-only names are still inserted (SetMax, :76-84)
+    pod = {"spec": {"initContainers": [{"resources": {"requests": {"cpu": "3", "x": "0"}}}],
+                    "containers": [{"resources": {"requests": {"cpu": "1"}}}, {"resources": {"requests": {"cpu": "500m", "memory": "1Gi"}}}]}}
+    want = {"cpu": 3, "x": 0, "memory": 2**30}
+    assert rl_values(host.eval_host("PodRequestResourceList", pod=pod)) == want
+    assert rl_values(oracle.call("PodRequestResourceList", pod=pod)) == want
+    amt = host.eval_host("ResourceAmountOfPod", pod=pod)  # resource_amount.go:71-76
+    assert amt["resourceCounts"] == {"pod": 1} and rl_values(amt["resourceRequests"]) == want
+
+
+@pytest.mark.parametrize("s", ["2026-01-01T00:00:00Z", "2019-02-01T00:00:00+09:00", "2021-08-04T10:00:00.5Z", "error", "2021-13-04T10:00:00Z",
+                               "2021-02-30T10:00:00Z", "2021-02-03", "2021-02-03T10:00:00", "2021-02-03T10:00:00Zjunk", "2021-02-03T25:00:00Z",
+                               "2021-02-03T10:00:00+0900", "", "20210203T100000Z"])
+def test_rfc3339_matches_oracle(host, oracle, s):
+    """time.Parse(time.RFC3339, s): value and Go's exact error text (throttle_types_test.go:147 pins one of them)."""
+    got, want = host.eval_host("ParseRFC3339", value=s), oracle.call("ParseRFC3339", value=s)
+    assert got.get("error") == want.get("error")
+    if "error" not in want:
+        assert (got["unix"], got["nsec"]) == (want["unix"], want["nsec"])
+
+
+def test_override_messages(host):
+    """throttle_types_test.go:110-152: unparsable overrides are skipped and reported by index"""
+    thr = {"kind": "Throttle", "metadata": {"name": "t", "namespace": "default"},
+           "spec": {"throttlerName": "dummy", "threshold": {"resourceRequests": {"cpu": "1"}}, "temporaryThresholdOverrides": [
+               {"begin": "2006-01-02T15:03:05Z", "end": "2006-01-02T15:05:05Z", "threshold": {"resourceRequests": {"cpu": "2"}}},
+               {"begin": "error", "end": "error"}, {"begin": "", "end": "nope"}]}}
+    assert host.eval_host("OverrideMessages", throttle=thr) == [
+        'index 1: Failed to parse Begin: parsing time "error" as "2006-01-02T15:04:05Z07:00": cannot parse "error" as "2006"',
+        'index 2: Failed to parse End: parsing time "nope" as "2006-01-02T15:04:05Z07:00": cannot parse "nope" as "2006"']
+
+
+@pytest.mark.parametrize("sel,valid", [
+    ({}, True), ({"matchLabels": {"a": "b"}}, True), ({"matchExpressions": [{"key": "a", "operator": "In", "values": ["x"]}]}, True),
+    ({"matchExpressions": [{"key": "a", "operator": "Exists"}]}, True), ({"matchExpressions": [{"key": "a", "operator": "In", "values": []}]}, False),
+    ({"matchExpressions": [{"key": "a", "operator": "Exists", "values": ["x"]}]}, False), ({"matchExpressions": [{"key": "a", "operator": "Bogus"}]}, False),
+    ({"matchLabels": {"bad key!": "b"}}, False), ({"matchLabels": {"a": "bad value!"}}, False), ({"matchLabels": {"example.com/role": "db"}}, True),
+    ({"matchLabels": {"a": "x" * 64}}, False), ({"matchLabels": {"/name": "x"}}, False),
+])
+def test_selector_validation(host, sel, valid):
+    """metav1.LabelSelectorAsSelector / labels.NewRequirement validation (PARITY UNPINNED by reference tests; apimachinery v0.26.4 rules)"""
+    assert host.eval_host("ValidateSelector", selector=sel)["valid"] is valid
+
+
+def test_new_plugin_needs_a_gpu_or_fails(host, kt):
+    """NewPlugin without a device is an error, never a CPU fallback; bad args are rejected like DecodePluginArgs."""
+    import ctypes as C
+    L = host._bind()
+    h = C.c_void_p()
+    assert L.kth_new_plugin(C.byref(h), b'{"targetSchedulerName":"s"}', 0) == kt.abi.ERR_INVALID and not h
+    assert L.kth_new_plugin(C.byref(h), b'{"name":"n"}', 0) == kt.abi.ERR_INVALID and not h
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(kt.KtError) as e:
+            host.Plugin()
+        assert e.value.code == kt.abi.ERR_CUDA

@@ -1,5 +1,8 @@
 """End-to-end decision vectors of the reference's integration suite and README walk-through, replayed on
-the object-level ORACLE (plugin PreFilter/Reserve + both controllers).  CPU only.
+BOTH implementations of the plugin surface through the same test bodies:
+  [oracle]  the object-level ORACLE (plugin PreFilter/Reserve + both controllers), CPU only;
+  [b200]    the PRODUCT: include/kt_host.h above the CUDA engine (marked gpu: every match, sum and compare
+            of these scenarios runs in the sm_100a kernels, the host only packs and spells).
 
 The integration suite needs Go + kind + a real kube-scheduler, none of which exist here; its scenarios
 are deterministic decision sequences, so they are transcribed as golden vectors:
@@ -61,12 +64,22 @@ def namespace(name, labels=None):
     return {"kind": "Namespace", "metadata": {"name": name, "labels": l}}
 
 
+@pytest.fixture(params=["oracle", pytest.param("b200", marks=pytest.mark.gpu)])
+def new_world(request, oracle):
+    """Constructor of a plugin world: NewPlugin(name, targetSchedulerName) on either implementation."""
+    if request.param == "oracle":
+        return oracle.World
+    from kube_throttler_b200 import host  # the product path: fails loudly without the CUDA library / a GPU
+
+    return host.Plugin
+
+
 class Cluster:
     """A miniature scheduler loop: PreFilter -> (Success) Reserve -> bind (nodeName set, pod informer
     sees it) -> reconcile.  Mirrors what the integration suite observes through the API server."""
 
-    def __init__(self, oracle):
-        self.w = oracle.World(THROTTLER, SCHED)
+    def __init__(self, new_world):
+        self.w = new_world(THROTTLER, SCHED)
         self.w.apply(namespace("default"))
 
     def try_schedule(self, p):
@@ -93,8 +106,8 @@ LBL = {"throttle": "test-throttle"}
 
 
 @pytest.fixture
-def cluster(oracle):
-    return Cluster(oracle)
+def cluster(new_world):
+    return Cluster(new_world)
 
 
 # ---- throttle_test.go:41-65 --------------------------------------------------------------------
@@ -218,8 +231,8 @@ def test_q1_step3_asymmetry(cluster):
 
 
 # ---- clusterthrottle_stress_test.go:33-86 --------------------------------------------------------
-def test_clusterthrottle_stress(oracle):
-    w = oracle.World(THROTTLER, SCHED)
+def test_clusterthrottle_stress(new_world):
+    w = new_world(THROTTLER, SCHED)
     n_clthr, n_ns, n_pods = 50, 10, 10
     for i in range(n_clthr):
         w.apply(clthrottle(f"clthr-{i}", {"targetns": "true"}, {"clthr-target": "true"}, pod_cnt=n_ns * n_pods, cpu=f"{n_ns * n_pods}m"))
@@ -327,8 +340,8 @@ def test_override_replaces_threshold_in_check(cluster):
     assert s["throttled"] == {"resourceCounts": {"pod": False}, "resourceRequests": {"cpu": False}}
 
 
-def test_missing_namespace_is_an_error(oracle):
-    w = oracle.World(THROTTLER, SCHED)
+def test_missing_namespace_is_an_error(new_world):
+    w = new_world(THROTTLER, SCHED)
     w.apply(clthrottle("c", {}, LBL, cpu="1"))
     r = w.prefilter(pod("ghost", "p", "1m", LBL))
     assert r["code"] == "Error" and "not found" in r["reasons"][0]

@@ -332,9 +332,9 @@ const char* ko_world_apply(void* h, const char* json) {
     KoWorld* k = (KoWorld*)h;
     Value v = kojson::parse(json);
     std::string kind = v.get("kind").str_or("");
-    if (kind == "Pod") k->w.upsertPod(pod_from(v));
+    if (kind == "Pod") k->w.applyPod(pod_from(v));
     else if (kind == "Namespace") k->w.upsertNamespace(ns_from(v));
-    else if (kind == "Throttle" || kind == "ClusterThrottle") k->w.upsertThrottle(throttle_from(v));
+    else if (kind == "Throttle" || kind == "ClusterThrottle") k->w.upsertThrottle(throttle_from(v), !v.get("status").is_obj());
     else return ret(err_obj("unknown kind: " + kind));
     return ret(Value::object());
   } catch (const std::exception& e) {

@@ -749,17 +749,18 @@ struct World {
     nsIndex[n.name] = namespaces.size();
     namespaces.push_back(std::make_unique<Namespace>(std::move(n)));
   }
-  void upsertThrottle(Throttle t) {
+  // keepStatus: a manifest without .status is a spec edit -- the status subresource survives it (CRD status subresource)
+  void upsertThrottle(Throttle t, bool keepStatus = false) {
     if (t.kind == KindThrottle) {
       std::string nn = t.NN();
       auto it = thrIndex.find(nn);
-      if (it != thrIndex.end()) { *throttles[it->second] = std::move(t); return; }
+      if (it != thrIndex.end()) { if (keepStatus) t.status = throttles[it->second]->status; *throttles[it->second] = std::move(t); return; }
       thrIndex[nn] = throttles.size();
       thrByNs[t.ns].push_back(throttles.size());
       throttles.push_back(std::make_unique<Throttle>(std::move(t)));
     } else {
       auto it = clthrIndex.find(t.name);
-      if (it != clthrIndex.end()) { *clusterThrottles[it->second] = std::move(t); return; }
+      if (it != clthrIndex.end()) { if (keepStatus) t.status = clusterThrottles[it->second]->status; *clusterThrottles[it->second] = std::move(t); return; }
       clthrIndex[t.name] = clusterThrottles.size();
       clusterThrottles.push_back(std::make_unique<Throttle>(std::move(t)));
     }
@@ -957,6 +958,32 @@ struct World {
     std::vector<Throttle*> thrs;
     if (affectedThrottles(pod, &thrs).empty()) for (Throttle* t : thrs) thrCache.removePod(t->NN(), pod);
     if (affectedClusterThrottles(pod, &thrs).empty()) for (Throttle* t : thrs) clthrCache.removePod(t->NN(), pod);
+  }
+
+  // ---- pod informer Add / Update event (throttle_controller.go:431-507, clusterthrottle_controller.go:459-535) ----
+  // Add only enqueues reconciles (nothing to model here).  Update: when the set of affected throttles changed,
+  // the pod's reservation moves from (old \ new) to (new \ old) -- addPod on the new ones is unconditional (:92-111).
+  void applyPod(Pod p) {
+    auto it = podIndex.find(p.NN());
+    if (it != podIndex.end()) {
+      const Pod old = *pods[it->second];
+      if (shouldCountIn(old) || shouldCountIn(p)) {
+        for (int kind = 0; kind < 2; ++kind) {
+          std::vector<Throttle*> forOld, forNew;
+          const std::string e1 = kind == 0 ? affectedThrottles(old, &forOld) : affectedClusterThrottles(old, &forOld);
+          if (!e1.empty()) continue;  // utilruntime.HandleError + return
+          const std::string e2 = kind == 0 ? affectedThrottles(p, &forNew) : affectedClusterThrottles(p, &forNew);
+          if (!e2.empty()) continue;
+          std::set<std::string> o, n, from, to;
+          for (Throttle* t : forOld) o.insert(t->NN());
+          for (Throttle* t : forNew) n.insert(t->NN());
+          for (auto& nn : o) if (!n.count(nn)) from.insert(nn);
+          for (auto& nn : n) if (!o.count(nn)) to.insert(nn);
+          if (!from.empty() || !to.empty()) (kind == 0 ? thrCache : clthrCache).moveThrottleAssignmentForPods(p, from, to);
+        }
+      }
+    }
+    upsertPod(std::move(p));
   }
 };
 

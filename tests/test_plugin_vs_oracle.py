@@ -1,0 +1,217 @@
+"""Randomised object-level parity: the PRODUCT plugin (kt_host.h above the CUDA engine) against the object-level
+ORACLE on the same Kubernetes manifests -- quantities as strings (m, Mi, Gi, decimals), matchLabels and
+matchExpressions, both throttle kinds, namespace selectors, overrides, reservations, pod updates.
+
+Every status field and every PreFilter result must be identical (quantities compared by value)."""
+import random
+from fractions import Fraction
+
+import pytest
+
+from test_oracle_kat import q
+from test_scenarios import NOW, SCHED, THROTTLER, namespace
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["app", "tier", "team", "env", "zone"]
+VALS = ["a", "b", "c", "d"]
+CPUS = ["50m", "100m", "250m", "0.5", "1", "1500m", "2", "0"]
+MEMS = ["64Mi", "128Mi", "512Mi", "1Gi", "1.5Gi", "1000000", "0"]
+
+
+def rand_labels(rng, lo=0, hi=4):
+    return {k: rng.choice(VALS) for k in rng.sample(KEYS, rng.randint(lo, hi))}
+
+
+def rand_selector(rng):
+    sel = {}
+    if rng.random() < 0.85:
+        sel["matchLabels"] = rand_labels(rng, 0 if rng.random() < 0.1 else 1, 3)
+    exprs = []
+    for _ in range(rng.choice([0, 0, 1, 2])):
+        op = rng.choice(["In", "NotIn", "Exists", "DoesNotExist"])
+        e = {"key": rng.choice(KEYS), "operator": op}
+        if op in ("In", "NotIn"):
+            e["values"] = rng.sample(VALS, rng.randint(1, 3))
+        exprs.append(e)
+    if exprs:
+        sel["matchExpressions"] = exprs
+    return sel
+
+
+def rand_amount(rng, scale=1):
+    a = {}
+    if rng.random() < 0.5:
+        a["resourceCounts"] = {"pod": (0 if rng.random() < 0.05 else rng.choice([3, 20, 60, 200])) * scale}
+    rr = {}
+    if rng.random() < 0.8:
+        rr["cpu"] = rng.choice(["200m", "2500m", "10", "30.5", "80", "400"] if rng.random() < 0.8 else ["0", "1n"])
+    if rng.random() < 0.5:
+        rr["memory"] = rng.choice(["256Mi", "4Gi", "30000000000", "64Gi", "1Ti"])
+    if rng.random() < 0.2:
+        rr["nvidia.com/gpu"] = str(rng.choice([0, 4, 40]))
+    if rr or rng.random() < 0.5:
+        a["resourceRequests"] = rr
+    return a
+
+
+def rand_pod(rng, ns, name, running):
+    reqs = {}
+    if rng.random() < 0.9:
+        reqs["cpu"] = rng.choice(CPUS)
+    if rng.random() < 0.6:
+        reqs["memory"] = rng.choice(MEMS)
+    if rng.random() < 0.15:
+        reqs["nvidia.com/gpu"] = str(rng.randint(0, 2))
+    spec = {"schedulerName": SCHED if rng.random() < 0.92 else "other", "nodeName": "", "containers": [{"name": "c", "resources": {"requests": reqs}}]}
+    if rng.random() < 0.2:
+        spec["containers"].append({"name": "c2", "resources": {"requests": {"cpu": rng.choice(CPUS)}}})
+    if rng.random() < 0.15:
+        spec["initContainers"] = [{"name": "i", "resources": {"requests": {"cpu": rng.choice(CPUS), "memory": rng.choice(MEMS)}}}]
+    if rng.random() < 0.1:
+        spec["overhead"] = {"cpu": "10m"}
+    phase = "Pending"
+    if running:
+        spec["nodeName"] = "node-1" if rng.random() < 0.95 else ""
+        phase = rng.choice(["Running", "Running", "Running", "Succeeded", "Failed", "Pending"])
+    return {"kind": "Pod", "metadata": {"namespace": ns, "name": name, "labels": rand_labels(rng)}, "spec": spec, "status": {"phase": phase}}
+
+
+def rand_throttle(rng, i, nss):
+    kind = "ClusterThrottle" if rng.random() < 0.4 else "Throttle"
+    terms = []
+    for _ in range(rng.choice([0, 1, 1, 1, 2])):
+        t = {"podSelector": rand_selector(rng)}
+        if kind == "ClusterThrottle":
+            t["namespaceSelector"] = rng.choice([{}, {"matchLabels": {"team": rng.choice(VALS)}}, {"matchExpressions": [{"key": "env", "operator": "NotIn", "values": ["a"]}]}])
+        terms.append(t)
+    spec = {"throttlerName": THROTTLER if rng.random() < 0.93 else "foreign", "threshold": rand_amount(rng), "selector": {"selectorTerms": terms}}
+    if rng.random() < 0.3:
+        spec["temporaryThresholdOverrides"] = [
+            {"begin": rng.choice(["", "2025-12-01T00:00:00Z", "2026-06-01T00:00:00Z", "garbage"]),
+             "end": rng.choice(["", "2026-02-01T00:00:00+09:00", "2025-12-15T00:00:00Z"]), "threshold": rand_amount(rng, 2)}
+            for _ in range(rng.randint(1, 3))]
+    md = {"name": f"t{i}"}
+    if kind == "Throttle":
+        md["namespace"] = rng.choice(nss)
+    return {"kind": kind, "metadata": md, "spec": spec}
+
+
+def norm_amount(a):
+    return (a.get("resourceCounts"), {k: q(v) for k, v in a.get("resourceRequests", {}).items()} if "resourceRequests" in a else None)
+
+
+def norm_status(s):
+    ct = s["calculatedThreshold"]
+    return dict(thr=norm_amount(ct["threshold"]), at=(ct["calculatedAtSet"], ct["calculatedAtUnix"] if ct["calculatedAtSet"] else None), msgs=ct.get("messages"),
+                throttled=s["throttled"], used=norm_amount(s["used"]))
+
+
+def norm_prefilter(r):
+    return {k: r.get(k) for k in ("code", "reasons", "event", "throttle", "clusterthrottle")}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_world(oracle, seed):
+    from kube_throttler_b200 import host
+
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i}" for i in range(5)]
+    for n in nss:
+        both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+    throttles = [rand_throttle(rng, i, nss) for i in range(40)]
+    both(*throttles)
+    pods = [rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(300)]
+    both(*pods)
+
+    def compare_status():
+        for t in throttles:
+            ns = t["metadata"].get("namespace", "")
+            a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+            assert norm_status(a) == norm_status(b), (t, a, b)
+
+    def compare_prefilter(pending):
+        want = [norm_prefilter(ref.prefilter(p)) for p in pending]
+        got = [norm_prefilter(r) for r in dut.prefilter_batch(pending)]  # the whole queue in ONE device pass
+        assert got == want
+        assert norm_prefilter(dut.prefilter(pending[0])) == want[0]    # and the per-pod entry point agrees
+        return want
+
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    compare_status()
+    pending = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(120)]
+    res = compare_prefilter(pending)
+    assert len({x.split("=")[0] for r in res for x in r["reasons"]} | {r["code"] for r in res}) >= 3  # the scenario is not degenerate
+
+    # admit a few: Reserve on both, bind half of them, leave the rest reserved-only; then update labels of some running pods
+    admitted = [p for p, r in zip(pending, res) if r["code"] == "Success"][:20]
+    for i, p in enumerate(admitted):
+        assert ref.reserve(p)["code"] == dut.reserve(p)["code"] == "Success"
+        if i % 2 == 0:
+            both(dict(p, spec=dict(p["spec"], nodeName="node-2"), status={"phase": "Running"}))
+    for p in rng.sample(pods, 25):
+        p["metadata"]["labels"] = rand_labels(rng)
+        both(p)
+    compare_prefilter(pending[20:80])  # stale status + reservations in play
+    for t in throttles:
+        k, nn = t["kind"], t["metadata"].get("namespace", "") + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (nn, a, b)
+    later = "2026-03-01T12:00:00Z"  # the override windows have moved on
+    ref.reconcile_all(later), dut.reconcile_all(later)
+    compare_status()
+    compare_prefilter(pending[60:])
+    # a threshold edit is invisible to PreFilter until the next reconcile (Q6)
+    throttles[0]["spec"]["threshold"] = {"resourceCounts": {"pod": 0}}
+    both(throttles[0])
+    compare_prefilter(pending[:40])
+    ref.reconcile_all(later), dut.reconcile_all(later)
+    compare_status()
+    compare_prefilter(pending[:40])
+    dut.close()
+
+
+def test_delete_events(oracle):
+    """Pod and throttle deletes (informer DeleteFunc): the row becomes a tombstone and is reused; used sums follow."""
+    from kube_throttler_b200 import host
+    from test_scenarios import pod, throttle
+
+    w = host.Plugin(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    for i in range(5):
+        w.apply(pod("default", f"p{i}", "100m", {"a": "1"}, node="n", phase="Running"))
+    w.reconcile_all(NOW)
+    assert q(w.status("t", "default")["used"]["resourceRequests"]["cpu"]) == Fraction(1, 2)
+    w.delete("Pod", "p1", "default")
+    w.delete("Pod", "p3", "default")
+    w.reconcile_all(NOW)
+    s = w.status("t", "default")
+    assert s["used"]["resourceCounts"]["pod"] == 3 and q(s["used"]["resourceRequests"]["cpu"]) == Fraction(3, 10)
+    w.apply(pod("default", "p9", "700m", {"a": "1"}, node="n", phase="Running"))  # reuses a tombstone row
+    w.reconcile_all(NOW)
+    s = w.status("t", "default")
+    assert s["used"]["resourceCounts"]["pod"] == 4 and q(s["used"]["resourceRequests"]["cpu"]) == 1 and s["throttled"]["resourceRequests"]["cpu"] is True
+    w.delete("Throttle", "t", "default")
+    assert w.prefilter(pod("default", "x", "1", {"a": "1"}))["code"] == "Success"
+    w.close()
+
+
+def test_column_scale_refinement():
+    """A quantity finer than the column's scale (cpu below 1m) re-packs the column at a finer power of ten; sums stay exact."""
+    from kube_throttler_b200 import host
+    from test_scenarios import pod, throttle
+
+    w = host.Plugin(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running"))
+    w.reconcile_all(NOW)
+    w.apply(pod("default", "p1", "100u", {"a": "1"}, node="n", phase="Running"), pod("default", "p2", "1n", {"a": "1"}, node="n", phase="Running"))
+    w.reconcile_all(NOW)
+    assert q(w.status("t", "default")["used"]["resourceRequests"]["cpu"]) == Fraction(1, 10) + Fraction(1, 10**4) + Fraction(1, 10**9)
+    r = w.prefilter(pod("default", "x", "899899999n", {"a": "1"}))  # 0.1 + 0.0001 + 1n + 0.899899999 == 1 exactly: not > threshold
+    assert r["code"] == "Success"
+    r = w.prefilter(pod("default", "y", "899900000n", {"a": "1"}))
+    assert r["reasons"] == ["throttle[insufficient]=default/t"]
+    w.close()

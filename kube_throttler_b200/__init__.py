@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
 
 EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
-    "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_update_pod_rows", "kt_upload_namespaces",
+    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
     "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy",
@@ -66,6 +66,9 @@ def lib():
         L.kt_set_stream.argtypes = [vp, vp]
         L.kt_sync.argtypes = [vp]
         L.kt_enable_timing.argtypes = [vp, C.c_int]
+        L.kt_enable_trace.argtypes = [vp, C.c_int]
+        L.kt_get_trace.argtypes = [vp, vp, C.c_int64, vp]
+        L.kt_get_trace.restype = C.c_int64
         L.kt_host_alloc.argtypes = [C.c_size_t]
         L.kt_host_alloc.restype = vp
         L.kt_host_free.argtypes = [vp]
@@ -150,6 +153,19 @@ class Engine:
 
     def enable_timing(self, on: bool = True):
         self._ck(self._L.kt_enable_timing(self._h, int(on)))
+
+    def enable_trace(self, on: bool = True):
+        self._ck(self._L.kt_enable_trace(self._h, int(on)))
+
+    def trace(self):
+        """(rows[n][4] = ticket, sm, start_ns, end_ns ; roles[4] = tiles per role) of the last fused pass."""
+        roles = np.zeros(4, np.uint32)
+        n = self._L.kt_get_trace(self._h, None, 0, roles.ctypes.data)
+        rows = np.zeros((int(roles.sum()), 4), np.uint64)
+        n = self._L.kt_get_trace(self._h, rows.ctypes.data, rows.shape[0], roles.ctypes.data)
+        if n < 0:
+            self._ck(int(n))
+        return rows[: int(n)], roles
 
     def sync(self):
         self._ck(self._L.kt_sync(self._h))

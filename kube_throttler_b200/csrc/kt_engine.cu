@@ -111,6 +111,11 @@ struct kt_ctx {
   DevBuf d_reserved, d_reserved_present, d_reserved_cnt;
   // pass state / outputs
   DevBuf d_part;   // [2R+1][M] u64, zero outside of kt_evaluate
+  DevBuf d_sync;   // PassSync counters of the fused pass (zero between launches)
+  DevBuf d_trace;  // optional per-CTA trace rows of the fused pass
+  bool trace = false;
+  uint32_t trace_roles[4] = {0, 0, 0, 0};
+  bool fused = true;  // one-launch pass (k_pass) when the whole pass is asked for; three PDL-chained kernels otherwise
   DevBuf d_check;  // [M][16+16R]
   DevBuf d_o_used, d_o_used_present, d_o_used_cnt, d_o_throttled, d_o_calc_thr, d_o_calc_present, d_o_calc_cnt, d_o_ovr_active;
   DevBuf d_codes, d_admit;
@@ -238,6 +243,27 @@ cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsi
                 (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
                 c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>());
 }
+template <int TPC, int B, int RT, bool REG>
+cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
+  const int L = c->lim.label_slots, R = c->lim.n_resources;
+  size_t smem = reconcile_smem_bytes(L, R, a.S, REG, kTileReconcile);
+  const size_t smem_chk = check_smem_bytes(L, R, REG, kTileReconcile);
+  if (smem_chk > smem) smem = smem_chk;
+  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin, kTileReconcile, smem, false, a);
+}
+cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
+  const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
+  const int R = c->lim.n_resources;
+  const bool fast = c->lim.label_slots <= 8 && b2 && R <= 8;
+  if (fast) {
+    if (t1) return R <= 4 ? launch_pass<1, 2, 4, true>(c, a) : launch_pass<1, 2, 8, true>(c, a);
+    return R <= 4 ? launch_pass<2, 2, 4, true>(c, a) : launch_pass<2, 2, 8, true>(c, a);
+  }
+  if (t1 && b2) return launch_pass<1, 2, 0, false>(c, a);
+  if (t1) return launch_pass<1, 6, 0, false>(c, a);
+  if (b2) return launch_pass<2, 2, 0, false>(c, a);
+  return launch_pass<2, 6, 0, false>(c, a);
+}
 cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
   const int R = c->lim.n_resources;
@@ -288,6 +314,7 @@ int kt_create(kt_ctx** out, int device, const kt_limits* lim) {
   c->stream = c->own_stream;
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { delete c; return KT_ERR_CUDA; }
+  if (c->d_sync.reserve(sizeof(PassSync)) != cudaSuccess || cudaMemset(c->d_sync.p, 0, sizeof(PassSync)) != cudaSuccess) { kt_destroy(c); return KT_ERR_CUDA; }
   *out = c;
   return KT_OK;
 }
@@ -302,7 +329,7 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
-                   &c->d_reserved_cnt, &c->d_part, &c->d_check, &c->d_o_used, &c->d_o_used_present, &c->d_o_used_cnt, &c->d_o_throttled,
+                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_o_used, &c->d_o_used_present, &c->d_o_used_cnt, &c->d_o_throttled,
                    &c->d_o_calc_thr, &c->d_o_calc_present, &c->d_o_calc_cnt, &c->d_o_ovr_active, &c->d_codes, &c->d_admit};
   for (DevBuf* b : all) b->release();
   for (auto& e : c->ev)
@@ -323,6 +350,27 @@ int kt_enable_timing(kt_ctx* c, int on) {
   std::lock_guard<std::mutex> lk(c->mu);
   c->timing = on != 0;
   return KT_OK;
+}
+
+int kt_enable_trace(kt_ctx* c, int on) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->trace = on != 0;
+  return KT_OK;
+}
+
+int64_t kt_get_trace(kt_ctx* c, uint64_t* rows, int64_t cap, uint32_t roles[4]) {
+  if (!c || cap < 0 || (cap > 0 && !rows)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int64_t total = (int64_t)c->trace_roles[0] + c->trace_roles[1] + c->trace_roles[2] + c->trace_roles[3];
+  if (roles) std::memcpy(roles, c->trace_roles, sizeof c->trace_roles);
+  if (!c->trace || !c->d_trace.p || total == 0) return 0;
+  const int64_t n = total < cap ? total : cap;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 int kt_sync(kt_ctx* c) {
@@ -521,8 +569,57 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   const TableView tb = table_view(c);
   int launches = 0;
   const bool tm = c->timing;
-  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
 
+  ThrottleView tv{};
+  tv.kind = c->d_kind.as<uint8_t>(); tv.flags = c->d_tflags.as<uint8_t>();
+  tv.thr = c->d_thr.as<int64_t>(); tv.thr_present = c->d_thr_present.as<uint32_t>(); tv.thr_cnt = c->d_thr_cnt.as<int64_t>();
+  tv.ovr_off = c->d_ovr_off.as<int32_t>(); tv.ovr_begin = c->d_ovr_begin.as<int64_t>(); tv.ovr_end = c->d_ovr_end.as<int64_t>();
+  tv.ovr_flags = c->d_ovr_flags.as<uint8_t>(); tv.ovr_thr = c->d_ovr_thr.as<int64_t>(); tv.ovr_present = c->d_ovr_present.as<uint32_t>();
+  tv.ovr_cnt = c->d_ovr_cnt.as<int64_t>(); tv.n_ovr = c->n_ovr;
+  if (given) {
+    tv.st_calculated = c->d_st_calculated.as<uint8_t>(); tv.st_calc_thr = c->d_st_calc_thr.as<int64_t>();
+    tv.st_calc_present = c->d_st_calc_present.as<uint32_t>(); tv.st_calc_cnt = c->d_st_calc_cnt.as<int64_t>();
+    tv.st_used = c->d_st_used.as<int64_t>(); tv.st_used_present = c->d_st_used_present.as<uint32_t>();
+    tv.st_used_cnt = c->d_st_used_cnt.as<int64_t>(); tv.st_throttled = c->d_st_throttled.as<uint32_t>();
+  }
+  if (c->have_reserved) {
+    tv.reserved = c->d_reserved.as<int64_t>(); tv.reserved_present = c->d_reserved_present.as<uint32_t>();
+    tv.reserved_cnt = c->d_reserved_cnt.as<int64_t>();
+  }
+  const ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
+                         c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
+  int G = 1;
+  while (G < R + 1) G <<= 1;  // finalize lanes per throttle: resources + the pod count, padded to a power of two
+  PartExchange px{};
+  px.mine = px.zero = c->d_part.as<unsigned long long>();
+  px.sync = c->d_sync.as<PassSync>();
+
+  // ---- the whole pass in one launch (k_pass): single GPU, both halves asked for ----
+  const bool multi = c->comm && c->nranks > 1;
+  if (c->fused && !tm && !multi && do_rec && do_chk && M > 0 && run.n > 0 && pend.n > 0) {
+    PassArgs a{};
+    a.run = pod_view(run); a.pend = pod_view(pend); a.tb = tb; a.tv = tv; a.out = ov; a.px = px;
+    a.run_bitmap = run.bitmap.as<uint32_t>(); a.pend_bitmap = pend.bitmap.as<uint32_t>(); a.codes = c->d_codes.as<uint32_t>();
+    a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = c->d_sync.as<PassSync>();
+    a.now = (long long)now; a.eval_flags = flags; a.L = c->lim.label_slots; a.R = R; a.S = reconcile_slots(c); a.G = G;
+    a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
+    a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
+    a.n_chk = (unsigned)((pend.n + kTileReconcile - 1) / kTileReconcile);
+    if (c->trace) {
+      const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;
+      KT_CUDA(c, c->d_trace.reserve(rows * 32));
+      a.trace = c->d_trace.as<unsigned long long>();
+      c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
+    }
+    KT_CUDA(c, dispatch_pass(c, a));
+    c->last = kt_timing{};
+    c->last.launches = 1;
+    c->evaluated = true;
+    return KT_OK;
+  }
+
+  // ---- separate kernels, PDL-chained: partial passes (SKIP_*), per-kernel timing, NCCL all-reduce in between ----
+  if (tm) KT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   if (do_rec && run.n > 0 && M > 0) {
     const PodView pv = pod_view(run);
     const unsigned blocks = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
@@ -530,37 +627,17 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  if (do_rec && c->comm && c->nranks > 1 && M > 0) {
+  if (do_rec && multi && M > 0) {
     // the single exchange of the pass: int64 sum of the per-throttle partials over NVLink
     int e = g_nccl.AllReduce(c->d_part.p, c->d_part.p, (size_t)(2 * R + 1) * M, kNcclInt64, kNcclSum, c->comm, c->stream);
     if (e != 0) return fail(c, KT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   if (M > 0) {
-    ThrottleView tv{};
-    tv.kind = c->d_kind.as<uint8_t>(); tv.flags = c->d_tflags.as<uint8_t>();
-    tv.thr = c->d_thr.as<int64_t>(); tv.thr_present = c->d_thr_present.as<uint32_t>(); tv.thr_cnt = c->d_thr_cnt.as<int64_t>();
-    tv.ovr_off = c->d_ovr_off.as<int32_t>(); tv.ovr_begin = c->d_ovr_begin.as<int64_t>(); tv.ovr_end = c->d_ovr_end.as<int64_t>();
-    tv.ovr_flags = c->d_ovr_flags.as<uint8_t>(); tv.ovr_thr = c->d_ovr_thr.as<int64_t>(); tv.ovr_present = c->d_ovr_present.as<uint32_t>();
-    tv.ovr_cnt = c->d_ovr_cnt.as<int64_t>(); tv.n_ovr = c->n_ovr;
-    if (given) {
-      tv.st_calculated = c->d_st_calculated.as<uint8_t>(); tv.st_calc_thr = c->d_st_calc_thr.as<int64_t>();
-      tv.st_calc_present = c->d_st_calc_present.as<uint32_t>(); tv.st_calc_cnt = c->d_st_calc_cnt.as<int64_t>();
-      tv.st_used = c->d_st_used.as<int64_t>(); tv.st_used_present = c->d_st_used_present.as<uint32_t>();
-      tv.st_used_cnt = c->d_st_used_cnt.as<int64_t>(); tv.st_throttled = c->d_st_throttled.as<uint32_t>();
-    }
-    if (c->have_reserved) {
-      tv.reserved = c->d_reserved.as<int64_t>(); tv.reserved_present = c->d_reserved_present.as<uint32_t>();
-      tv.reserved_cnt = c->d_reserved_cnt.as<int64_t>();
-    }
-    ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
-                     c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
     // PDL: overlaps its launch + override merge with the tail of k_reconcile (or of the all-reduce kernel)
-    int G = 1;
-    while (G < R + 1) G <<= 1;  // lanes per throttle: resources + the pod count, padded to a power of two
     const long long lanes = (long long)M * G;
-    KT_CUDA(c, launch(c, k_finalize, (unsigned)((lanes + 127) / 128), 128, 0, /*pdl=*/!tm, tv, M, R, G, (long long)now, flags,
-                      c->d_part.as<unsigned long long>(), ov, c->d_check.as<unsigned char>()));
+    KT_CUDA(c, launch(c, k_finalize, (unsigned)((lanes + 127) / 128), 128, 0, /*pdl=*/!tm, tv, M, R, G, (long long)now, flags, px, ov,
+                      c->d_check.as<unsigned char>()));
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));

@@ -37,7 +37,6 @@ constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one 
 constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kCheckStash = 4;       // match words per pending pod kept in shared memory between the two phases
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
@@ -115,6 +114,82 @@ struct ReconcileView {  // device-resident kt_reconcile_out
 // ---- programmatic dependent launch (PTX griddepcontrol; both are no-ops in a plain launch) -------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- in-kernel hand-off between the roles of the fused pass (k_pass) ----------------------------------
+// Tiles are handed out by a ticket counter, reconcile tiles first, then finalize, then check tiles: a CTA that
+// waits on a counter can only be waiting for tiles with SMALLER tickets, which are already running on some SM,
+// so the waits cannot deadlock whatever the residency.  Signals are fence + relaxed add (release pattern) by
+// thread 0 after a CTA barrier; waits are acquire loads by thread 0 followed by a CTA barrier.
+struct PassSync {
+  unsigned ticket;    // next tile
+  unsigned rec_done;  // reconcile tiles finished (their REDs are performed at L2)
+  unsigned fin_done;  // finalize tiles finished (check constants written)
+  unsigned exited;    // CTAs that are done with everything; the last one re-arms the counters
+  unsigned epoch;     // multi-GPU: last pass whose partial sums this rank has published (peers poll it over NVLink)
+  unsigned pad[3];
+};
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cta_signal(unsigned* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+  }
+}
+__device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target) {
+  if (threadIdx.x == 0)
+    while (ld_acquire_gpu(counter) < target) __nanosleep(40);
+  __syncthreads();
+}
+
+// Where the per-throttle partial sums of this pass live.  Single GPU / NCCL path: mine == zero, no peers
+// (the all-reduce already happened in place).  Peer path: every rank pulls the other ranks' buffers over
+// NVLink inside its finalize tiles; buffers alternate by pass parity so that a rank can re-zero the buffer
+// of the NEXT pass while slower peers may still be reading the current one.
+struct PartExchange {
+  unsigned long long* mine;   // this pass's partial sums of this rank
+  unsigned long long* zero;   // buffer to leave zeroed for a later pass
+  const unsigned long long* peer[7];
+  const PassSync* peer_sync[7];
+  PassSync* sync;             // this rank's counters (epoch is what the peers poll)
+  int npeers;
+  unsigned epoch;             // this pass
+};
+
+// How a dependent role waits for its producer: programmatic dependent launch between separate kernels ...
+struct PdlSync {
+  __device__ __forceinline__ void wait_reconciled(const PartExchange&) const { pdl_wait_primary(); }
+  __device__ __forceinline__ void wait_finalized() const { pdl_wait_primary(); }
+};
+// ... or counters inside the one fused kernel (plus the peers' epochs when the sums are exchanged over NVLink)
+struct FlagSync {
+  PassSync* s;
+  unsigned n_rec, n_fin;
+  __device__ __forceinline__ void wait_reconciled(const PartExchange& px) const {
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu(&s->rec_done) < n_rec) __nanosleep(40);
+      if (px.npeers > 0) {
+        // publish: this rank's partial sums of pass `epoch` are complete (all its REDs are performed) ...
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;  // every finalize tile stores the same value
+        // ... and wait until every peer has published the same pass
+        for (int i = 0; i < px.npeers; ++i)
+          while ((int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) < 0) __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin); }
+};
 
 // ---- label -> table row ---------------------------------------------------------------------------
 // Exact (key,value) row, else the key's "other value" row, else the neutral row.
@@ -305,10 +380,10 @@ __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool
 //       largest per-namespace word list); words beyond S go straight to HBM
 // ------------------------------------------------------------------------------------------------
 template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconcile(PodView pods, TableView tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
-                                                                 unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */) {
+__device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableView& tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
+                                               unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */,
+                                               unsigned char* smem_raw, int64_t tile_index) {
   constexpr int TILE = kTileReconcile;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                                     // [R][TILE], 0 where absent
   unsigned long long* s_used = reinterpret_cast<unsigned long long*>(s_req + (size_t)R * TILE);  // [S][R][32]
   int32_t* s_rowid = reinterpret_cast<int32_t*>(s_used + (size_t)S * R * 32);                    // [L][TILE] (!REG)
@@ -317,10 +392,8 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconc
   uint32_t* s_pres = s_cnt + S * 32;                                                             // [S][32]
   int* s_key = reinterpret_cast<int*>(s_pres + S * 32);                                          // [S] word index or -1
 
-  pdl_launch_dependents();  // k_finalize / k_check may be scheduled; they wait for our completion where they need it
-
   const int tid = threadIdx.x, lane = tid & 31, wbase_pod = tid & ~31;
-  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+  const int64_t tile0 = tile_index * TILE;
   const int Wp = tb.Wp;
   const int Lpad = (L + 7) & ~7;
   const int64_t p = tile0 + tid;
@@ -492,17 +565,25 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconc
   }
 }
 
+template <int TPC, int B, int RT, bool REG>
+__global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconcile(PodView pods, TableView tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
+                                                                                    unsigned long long* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();  // k_finalize / k_check may be scheduled; they wait for our completion where they need it
+  reconcile_tile<TPC, B, RT, REG>(pods, tb, L, R, S, bitmap, part, smem_raw, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_finalize: a group of G = 2^g >= R+1 lanes per throttle; lane r < R owns resource r, lane R owns the
 // pod count.  Every Quantity compare of the reconcile tail and of CheckThrottledFor's constants is one
 // lane's scalar work, the per-throttle bitmasks are assembled with a ballot.  Consumes (and re-zeroes)
 // the partial sums.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, int G, long long now, uint32_t eval_flags,
-                                                  unsigned long long* __restrict__ part, ReconcileView out,
-                                                  unsigned char* __restrict__ check /* [M][16 + 16R] */) {
-  pdl_launch_dependents();  // k_check can start matching the pending pods right away
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+template <class Sync>
+__device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int R, int G, long long now, uint32_t eval_flags, const PartExchange& px,
+                                              const ReconcileView& out, unsigned char* __restrict__ check /* [M][16 + 16R] */, int tile_index,
+                                              const Sync& sync) {
+  const int gid = tile_index * (int)blockDim.x + (int)threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int t = gid / G, r = gid % G;  // G divides 32: a group never straddles a warp
   const int gbase = lane - r;          // first lane of this group inside the warp
@@ -561,20 +642,25 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
   }
   const bool is_throttle_kind = in_range ? tv.kind[t] == KT_KIND_THROTTLE : true;
 
-  pdl_wait_primary();  // the partial sums of k_reconcile (or the all-reduce) are complete and visible
+  sync.wait_reconciled(px);  // the partial sums (of every rank) are complete and visible
 
-  // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count ----
+  // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count; with peers the
+  // all-reduce happens right here: every rank adds up the same buffers over NVLink (uncached loads) ----
   long long used_val = 0;
   bool used_has = false;
-  if (is_res) {
-    used_val = (long long)__ldcg(&part[col]);
-    used_has = __ldcg(&part[(size_t)(R + r) * M + t]) != 0ull;
-    part[col] = 0ull;
-    part[(size_t)(R + r) * M + t] = 0ull;
-  } else if (is_cnt) {
-    used_val = (long long)__ldcg(&part[(size_t)2 * R * M + t]);
-    used_has = used_val > 0;  // Counts stays nil with zero counted pods (Q3)
-    part[(size_t)2 * R * M + t] = 0ull;
+  if (is_res || is_cnt) {
+    const size_t i_val = is_res ? col : (size_t)2 * R * M + t;
+    const size_t i_has = (size_t)(R + r) * M + t;  // resource lanes only
+    unsigned long long v = __ldcg(&px.mine[i_val]);
+    unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
+    for (int i = 0; i < px.npeers; ++i) {
+      v += __ldcv(&px.peer[i][i_val]);
+      if (is_res) h += __ldcv(&px.peer[i][i_has]);
+    }
+    used_val = (long long)v;
+    used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
+    px.zero[i_val] = 0ull;
+    if (is_res) px.zero[i_has] = 0ull;
   }
   const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
   // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
@@ -634,6 +720,12 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
   }
 }
 
+__global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, int G, long long now, uint32_t eval_flags, PartExchange px,
+                                                  ReconcileView out, unsigned char* __restrict__ check) {
+  pdl_launch_dependents();  // k_check can start matching the pending pods right away
+  finalize_tile(tv, M, R, G, now, eval_flags, px, out, check, blockIdx.x, PdlSync{});
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_check: one lane per PENDING pod.  Phase 1 (no dependency on the running pods): selector match ->
 // affectedThrottles bitmap.  Phase 2 (after k_finalize): 4-step CheckThrottledFor per matched pair; the
@@ -641,41 +733,66 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 // per-pair work is shared-memory compares instead of dependent global gathers.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
-  return (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R) + (reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4) +
-         (size_t)kCheckStash * tile * 4;
+  const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                              // check_match_tile
+  const size_t decide = (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);    // check_decide_tile
+  return match > decide ? match : decide;
 }
 
-template <int TPC, int B, bool REG>
-__global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
-                                                      uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                      unsigned char* __restrict__ admit) {
-  constexpr int TILE = kTileCheck;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
-  long long* s_req = reinterpret_cast<long long*>(smem_raw);                                   // [R][TILE]
-  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);           // [warps][32][rec]
-  int32_t* s_rowid = reinterpret_cast<int32_t*>(s_chk + (size_t)(TILE / 32) * 32 * rec);      // [L][TILE] (!REG)
-  uint32_t* s_words = reinterpret_cast<uint32_t*>(s_rowid + (REG ? 0 : (size_t)((L + 7) & ~7) * TILE));    // [kCheckStash][TILE]
-  const int tid = threadIdx.x, lane = tid & 31;
-  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * 32 * rec;
-  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+// Phase 1 of the pending check, no dependency on the running pods: selector match of TILE pending pods ->
+// affectedThrottles bitmap rows (throttle_controller.go:248-269); also clears the tile's code rows.
+template <int TPC, int B, bool REG, int TILE>
+__device__ __forceinline__ void check_match_tile(const PodView& pods, const TableView& tb, int L, uint32_t* __restrict__ bitmap,
+                                                 uint32_t* __restrict__ codes, unsigned char* smem_raw, int64_t tile_index) {
+  int32_t* s_rowid = reinterpret_cast<int32_t*>(smem_raw);  // [Lpad][TILE] (!REG)
+  const int tid = threadIdx.x;
+  const int64_t tile0 = tile_index * TILE;
   const int Wp = tb.Wp;
-  {
-    const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
-    uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
-    uint4* d1 = reinterpret_cast<uint4*>(codes + tile0 * 2 * Wp);
-    const int64_t nvec = rows_here * (Wp / 4);
-    for (int64_t i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
-    for (int64_t i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
-  }
   const int Lpad = (L + 7) & ~7;
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes never store
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
-  const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
+  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+  {
+    const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
+    uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
+    uint4* d1 = reinterpret_cast<uint4*>(codes + tile0 * 2 * Wp);
+    const int nvec = (int)rows_here * (Wp / 4);
+    for (int i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
+  }
+  int lo = 0, hi = 0;
+  if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+  __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
+#pragma unroll 1
+  for (int j = lo; j < hi; ++j) {
+    const int w = __ldg(&tb.nsw_idx[j]);
+    const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
+    if (word) bitmap[p * Wp + w] = word;
+  }
+}
+
+// Phase 2, after finalize: the 4-step CheckThrottledFor per (pending pod, affected throttle), 2-bit codes and the admit
+// bit.  Everything that does not depend on the reconcile is loaded before the wait.  The constants of a word's 32
+// throttles are staged in shared memory by the warp (lane = throttle), so the per-pair work is shared-memory compares
+// instead of dependent global gathers.
+template <int TILE, class Sync>
+__device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, const unsigned char* __restrict__ check,
+                                                  const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
+                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync) {
+  const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
+  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][32][rec]
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * 32 * rec;
+  const int Wp = tb.Wp;
+  const int64_t p = tile_index * TILE + tid;
+  const bool valid = p < pods.n;
+  const int64_t pc = valid ? p : pods.n - 1;
+  const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
+  const uint32_t present = __ldg(&pods.present[pc]);
   // ResourceAmountOfPod(pod): the non-zero requests are the only ones IsThrottledFor looks at (Q5)
   uint32_t nz = 0;
   {
@@ -688,36 +805,20 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
       if (v != 0) nz |= 1u << r;
     }
   }
-  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
-  int lo = 0, hi = 0;
-  if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
-
-  // ---- phase 1: affectedThrottles (throttle_controller.go:248-269) ----
-  int first = 0x7fffffff;  // first word with a match
-#pragma unroll 1
-  for (int j = lo; j < hi; ++j) {
-    const int w = __ldg(&tb.nsw_idx[j]);
-    const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
-    if (j - lo < kCheckStash) s_words[(j - lo) * TILE + tid] = word;
-    if (word) {
-      bitmap[p * Wp + w] = word;
-      if (first == 0x7fffffff) first = j;
-    }
-  }
-  pdl_wait_primary();  // k_finalize has written the check constants
-
-  // ---- phase 2: CheckThrottledFor per affected throttle; words in ascending order, warp-uniform ----
-  unsigned char ok = 1;
-  int j = first == 0x7fffffff ? hi : first;
+  int j = 0, hi = 0;
+  if ((unsigned)ns < (unsigned)tb.NS) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+
+  sync.wait_finalized();  // the match rows of this tile and the check constants are written
+
+  unsigned char ok = 1;
 #pragma unroll 1
-  while (true) {
+  while (true) {  // words in ascending order, warp-uniform
     const int w = __reduce_min_sync(kFull, cur);
     if (w == 0x7fffffff) break;
     uint32_t word = 0;
     if (cur == w) {
-      word = (j - lo < kCheckStash) ? s_words[(j - lo) * TILE + tid] : bitmap[p * Wp + w];  // own store, ordered by the barrier
+      word = __ldcg(&bitmap[p * Wp + w]);
       ++j;
       cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
     }
@@ -771,6 +872,92 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
     if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
   }
   if (valid) admit[p] = ok;
+}
+
+// k_check: both phases of one tile in one CTA (the PDL-chained path: phase 1 overlaps k_reconcile / k_finalize).
+template <int TPC, int B, bool REG>
+__global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
+                                                      uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
+                                                      unsigned char* __restrict__ admit) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
+  __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
+  check_decide_tile<kTileCheck>(pods, tb, R, check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{});
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pass: the whole pass in ONE launch.  Every CTA draws a ticket and becomes a reconcile tile, a finalize
+// tile or a check tile (in that ticket order).  Check tiles match their pending pods while the reconcile
+// tiles are still summing; finalize tiles load thresholds / overrides meanwhile and, with peers, perform the
+// all-reduce themselves by pulling the other ranks' partial sums over NVLink.  One cold start instead of
+// three, and the hand-offs cost a poll of an L2 counter instead of a kernel boundary.
+// ------------------------------------------------------------------------------------------------
+struct PassArgs {
+  PodView run, pend;
+  TableView tb;
+  ThrottleView tv;
+  ReconcileView out;
+  PartExchange px;
+  uint32_t* run_bitmap;
+  uint32_t* pend_bitmap;
+  uint32_t* codes;
+  unsigned char* admit;
+  unsigned char* check;
+  PassSync* sync;
+  long long now;
+  uint32_t eval_flags;
+  int L, R, S, G;
+  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]
+  unsigned long long* trace;     // optional (kt_enable_trace): per CTA {ticket, sm, t_start, t_end} in globaltimer ns
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int TPC, int B, int RT, bool REG>
+__global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned s_ticket;
+  unsigned long long t_start = 0;
+  if (threadIdx.x == 0) {
+    s_ticket = atomicAdd(&a.sync->ticket, 1u);
+    if (a.trace) t_start = globaltimer_ns();
+  }
+  __syncthreads();
+  unsigned tile = s_ticket;
+  // fin_done counts the pending-match tiles as well: a decide tile needs both its match rows and the constants
+  const FlagSync sync{a.sync, a.n_rec, a.n_fin + a.n_chk};
+  if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+    check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
+    cta_signal(&a.sync->fin_done);
+  } else if ((tile -= a.n_chk) < a.n_rec) {
+    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile);
+    cta_signal(&a.sync->rec_done);
+  } else if ((tile -= a.n_rec) < a.n_fin) {
+    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync);
+    cta_signal(&a.sync->fin_done);
+  } else {
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
+  }
+  // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (a.trace) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* row = a.trace + (size_t)s_ticket * 4;
+      row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
+    }
+    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
+    if (atomicAdd(&a.sync->exited, 1u) == total - 1) {
+      a.sync->ticket = 0;
+      a.sync->rec_done = 0;
+      a.sync->fin_done = 0;
+      a.sync->exited = 0;
+    }
+  }
 }
 
 // Row-level delta: scatter k packed rows into the resident columns (pod informer Add/Update/Delete).

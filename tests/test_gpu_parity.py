@@ -152,6 +152,27 @@ def test_repeat_pass_is_idempotent(kt):
     eng.close()
 
 
+def test_fused_and_chained_paths_agree(kt, oracle):
+    """kt_evaluate runs the whole pass as ONE launch (k_pass: ticketed reconcile / finalize / check tiles with in-kernel
+    hand-offs); with per-kernel timing enabled it runs the three PDL-chained kernels instead.  Same bits either way,
+    pass after pass (the ticket / done counters re-arm themselves)."""
+    for kw in (dict(config="C3", m=300, n=6000, p=800), dict(config="C2", m=1000, n=30000, p=3000), dict(config="C2", m=40, n=70, p=33, R=1)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        outs = []
+        for timing in (False, False, True, False):
+            eng.enable_timing(timing)
+            eng.evaluate(snap.now)
+            outs.append(eng.download())
+            assert eng.timing().launches == (3 if timing else 1)
+        eng.close()
+        want = oracle.columnar_evaluate(snap, words_per_row=outs[0].words_per_row)
+        for got in outs:
+            assert_same(snap, got, want)
+
+
 def test_pod_row_delta(kt, oracle):
     """kt_update_pod_rows == re-uploading the modified columns (informer Add/Update/Delete as row scatters)."""
     snap = synth.generate("C2", m=200, n=5000, p=500)

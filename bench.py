@@ -190,6 +190,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -208,6 +210,7 @@ def main():
     Wp = eng.words_per_row
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     drain = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    align_t = torch.zeros(1, device="cuda")
 
     def one_pass(timed):
         with torch.cuda.stream(stream):
@@ -217,6 +220,11 @@ def main():
                 # line the pass allocates first writes back 128 B of the flush's own dirty data (24 MB of foreign DRAM
                 # writes inside the timed region of a 28 MB pass)
                 drain.sum()
+            if world > 1:
+                # line the ranks up AFTER the flush and OUTSIDE the timed events: the flush kernels of different GPUs
+                # finish several microseconds apart, and a rank that enters the pass early would otherwise spend that
+                # skew waiting inside the pass's own exchange and book it as pass time
+                dist.all_reduce(align_t)
             if timed is not None:
                 timed[0].record(stream)
             eng.evaluate(snap.now)
@@ -293,6 +301,18 @@ def main():
         eng.get_check(codes_b.array, admit_b.array)
         eng.get_reconcile(out)
 
+    # what the host link of this box can do at all (pinned, one 64 MiB copy each way): the floor of any e2e number
+    probe_h, probe_d = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    link = {}
+    for name, (dst, src) in (("h2d", (probe_d, probe_h)), ("d2h", (probe_h, probe_d))):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        link[name + "_gbs"] = 4 * (64 << 20) / (time.perf_counter() - t0) / 1e9
+    del probe_h, probe_d
+
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize()
@@ -330,7 +350,8 @@ def main():
                               (" then 512 MiB read (L2 holds clean foreign lines; inputs still come from HBM)" if args.flush == "write+read" else "")), "parallelism": f"row-shard x{world}",
                        "admit_fraction": admit_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "path": "kt_upload_pods x2 + kt_evaluate + kt_get_check + kt_get_reconcile (pinned host buffers)"},
+                    "steps": args.e2e_steps, "path": "kt_upload_pods x2 + kt_evaluate + kt_get_check + kt_get_reconcile (pinned host buffers)",
+                    "host_link_gbs": link, "link_floor_value": checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world},
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }

@@ -3,6 +3,7 @@
 // library: without a CUDA device every entry point that needs one fails with KT_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -56,6 +57,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Uid128, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -70,6 +72,7 @@ const char* load_nccl() {
   g_nccl.CommInitRank = (int (*)(void**, int, Uid128, int))dlsym(h, "ncclCommInitRank");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) return "NCCL symbols missing";
   g_nccl.handle = h;
@@ -77,6 +80,16 @@ const char* load_nccl() {
 }
 constexpr int kNcclInt64 = 4;  // ncclInt64
 constexpr int kNcclSum = 0;    // ncclSum
+constexpr int kNcclChar = 0;   // ncclInt8 / ncclChar
+
+// What the ranks tell each other about their exchange window (one ncclAllGather when the window is (re)allocated).
+struct PeerInfo {
+  cudaIpcMemHandle_t handle;  // 64 bytes
+  unsigned long long ptr;     // the raw device pointer: used instead of the handle when the peer lives in this process
+  long long pid;
+  int device;
+  int ok;                     // the rank could allocate / export its window
+};
 
 }  // namespace
 
@@ -123,6 +136,14 @@ struct kt_ctx {
   // multi-GPU
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer exchange window: [PassSync | partial sums, even passes | partial sums, odd passes], mapped by every rank.
+  // The fused pass does the all-reduce itself: finalize tiles pull the peers' partial sums over NVLink.
+  void* win = nullptr;
+  size_t win_part_bytes = 0;  // bytes of ONE partial-sum buffer in the current window
+  void* peer_win[8] = {};     // peer_win[r] for r != rank (IPC-opened or raw)
+  bool peer_ipc[8] = {};
+  bool p2p_failed = false;    // no peer access between the GPUs: stay on the NCCL path
+  unsigned epoch = 0;         // passes exchanged through the window so far
 };
 
 namespace {
@@ -198,6 +219,92 @@ PodView pod_view(const PodStore& s) {
   v.ns = s.ns.as<int32_t>();
   v.n = s.n;
   return v;
+}
+
+// ---- peer exchange window ------------------------------------------------------------------------------
+constexpr size_t kWinHeader = 256;  // PassSync lives at offset 0, the partial-sum buffers follow
+void release_window(kt_ctx* c) {
+  for (int r = 0; r < 8; ++r) {
+    if (c->peer_win[r] && c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
+    c->peer_win[r] = nullptr;
+    c->peer_ipc[r] = false;
+  }
+  if (c->win) cudaFree(c->win);
+  c->win = nullptr;
+  c->win_part_bytes = 0;
+}
+// Collective over the communicator (every rank reaches it in the same kt_evaluate because M and R are replicated):
+// (re)allocate this rank's window, exchange the IPC handles with one ncclAllGather, map the peers' windows.
+// Returns KT_OK with c->p2p_failed set when the GPUs cannot reach each other (the caller then uses NCCL).
+int ensure_window(kt_ctx* c, size_t part_bytes) {
+  if (c->p2p_failed || (c->win && c->win_part_bytes >= part_bytes)) return KT_OK;
+  if (!g_nccl.AllGather || c->nranks > 8) { c->p2p_failed = true; return KT_OK; }
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  release_window(c);
+  const size_t want = part_bytes + part_bytes / 4 + 4096;
+  PeerInfo mine{};
+  mine.pid = (long long)getpid();
+  mine.device = c->device;
+  void* w = nullptr;
+  if (cudaMalloc(&w, kWinHeader + 2 * want) == cudaSuccess && cudaMemset(w, 0, kWinHeader + 2 * want) == cudaSuccess &&
+      cudaIpcGetMemHandle(&mine.handle, w) == cudaSuccess) {
+    mine.ok = 1;
+    mine.ptr = (unsigned long long)w;
+  } else {
+    cudaGetLastError();
+  }
+  DevBuf d_in, d_out;
+  KT_CUDA(c, d_in.reserve(sizeof(PeerInfo)));
+  KT_CUDA(c, d_out.reserve(sizeof(PeerInfo) * c->nranks));
+  KT_CUDA(c, cudaMemcpyAsync(d_in.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  int e = g_nccl.AllGather(d_in.p, d_out.p, sizeof(PeerInfo), kNcclChar, c->comm, c->stream);
+  if (e != 0) return fail(c, KT_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  std::vector<PeerInfo> all((size_t)c->nranks);
+  KT_CUDA(c, cudaMemcpyAsync(all.data(), d_out.p, sizeof(PeerInfo) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  d_in.release();
+  d_out.release();
+  bool ok = true;
+  for (auto& pi : all) ok = ok && pi.ok;
+  for (int r = 0; ok && r < c->nranks; ++r) {
+    if (r == c->rank) continue;
+    if (all[r].pid == mine.pid) {  // another context of this process (one Go process driving several GPUs)
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[r].device) != cudaSuccess || !can) { ok = false; break; }
+      cudaError_t pe = cudaDeviceEnablePeerAccess(all[r].device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+      cudaGetLastError();
+      c->peer_win[r] = (void*)all[r].ptr;
+    } else {
+      void* pw = nullptr;
+      if (cudaIpcOpenMemHandle(&pw, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      c->peer_win[r] = pw;
+      c->peer_ipc[r] = true;
+    }
+  }
+  // every rank must reach the same verdict: a second tiny all-gather of the local one
+  int verdict = ok ? 1 : 0;
+  DevBuf d_v, d_vs;
+  KT_CUDA(c, d_v.reserve(4));
+  KT_CUDA(c, d_vs.reserve(4 * (size_t)c->nranks));
+  KT_CUDA(c, cudaMemcpyAsync(d_v.p, &verdict, 4, cudaMemcpyHostToDevice, c->stream));
+  e = g_nccl.AllGather(d_v.p, d_vs.p, 4, kNcclChar, c->comm, c->stream);
+  if (e != 0) return fail(c, KT_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  std::vector<int> verdicts((size_t)c->nranks);
+  KT_CUDA(c, cudaMemcpyAsync(verdicts.data(), d_vs.p, 4 * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  d_v.release();
+  d_vs.release();
+  for (int v : verdicts) ok = ok && v;
+  c->win = w;
+  if (!ok) {
+    release_window(c);
+    c->p2p_failed = true;
+    return KT_OK;
+  }
+  c->win_part_bytes = want;
+  c->epoch = 0;  // fresh windows everywhere: all epochs restart together
+  return KT_OK;
 }
 
 // ---- launches ------------------------------------------------------------------------------------
@@ -322,8 +429,9 @@ int kt_create(kt_ctx** out, int device, const kt_limits* lim) {
 void kt_destroy(kt_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaStreamSynchronize(c->stream);
+  release_window(c);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& s : c->pods) s.release();
   DevBuf* all[] = {&c->d_hash, &c->d_keydir, &c->d_valrow, &c->d_table, &c->d_need, &c->d_nsmask, &c->d_nsw_off, &c->d_nsw_idx, &c->d_kind, &c->d_tflags, &c->d_thr,
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
@@ -369,7 +477,7 @@ int64_t kt_get_trace(kt_ctx* c, uint64_t* rows, int64_t cap, uint32_t roles[4]) 
   if (!c->trace || !c->d_trace.p || total == 0) return 0;
   const int64_t n = total < cap ? total : cap;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
   return n;
 }
 
@@ -594,20 +702,42 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   px.mine = px.zero = c->d_part.as<unsigned long long>();
   px.sync = c->d_sync.as<PassSync>();
 
-  // ---- the whole pass in one launch (k_pass): single GPU, both halves asked for ----
+  // ---- the whole pass in one launch (k_pass), both halves asked for.  With several ranks the all-reduce happens
+  // inside it: finalize tiles pull the peers' partial sums over NVLink from the exchange windows. ----
   const bool multi = c->comm && c->nranks > 1;
-  if (c->fused && !tm && !multi && do_rec && do_chk && M > 0 && run.n > 0 && pend.n > 0) {
+  const bool whole = c->fused && !tm && do_rec && do_chk && M > 0 && run.n > 0 && pend.n > 0;
+  if (whole && multi) {
+    if ((rc = ensure_window(c, (size_t)(2 * R + 1) * M * 8))) return rc;
+    if (!c->p2p_failed) {
+      unsigned char* base = reinterpret_cast<unsigned char*>(c->win);
+      const unsigned epoch = ++c->epoch;
+      px.sync = reinterpret_cast<PassSync*>(base);
+      px.mine = reinterpret_cast<unsigned long long*>(base + kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes);
+      px.zero = reinterpret_cast<unsigned long long*>(base + kWinHeader + (size_t)((epoch + 1) & 1) * c->win_part_bytes);
+      px.epoch = epoch;
+      px.npeers = 0;
+      for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) continue;
+        const unsigned char* pb = reinterpret_cast<const unsigned char*>(c->peer_win[r]);
+        px.peer[px.npeers] = reinterpret_cast<const unsigned long long*>(pb + kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes);
+        px.peer_sync[px.npeers] = reinterpret_cast<const PassSync*>(pb);
+        ++px.npeers;
+      }
+    }
+  }
+  if (whole && (!multi || !c->p2p_failed)) {
     PassArgs a{};
     a.run = pod_view(run); a.pend = pod_view(pend); a.tb = tb; a.tv = tv; a.out = ov; a.px = px;
     a.run_bitmap = run.bitmap.as<uint32_t>(); a.pend_bitmap = pend.bitmap.as<uint32_t>(); a.codes = c->d_codes.as<uint32_t>();
-    a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = c->d_sync.as<PassSync>();
+    a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = px.sync;
     a.now = (long long)now; a.eval_flags = flags; a.L = c->lim.label_slots; a.R = R; a.S = reconcile_slots(c); a.G = G;
     a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
     a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
     a.n_chk = (unsigned)((pend.n + kTileReconcile - 1) / kTileReconcile);
     if (c->trace) {
       const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;
-      KT_CUDA(c, c->d_trace.reserve(rows * 32));
+      KT_CUDA(c, c->d_trace.reserve(rows * 64));
+      KT_CUDA(c, cudaMemsetAsync(c->d_trace.p, 0, rows * 64, c->stream));
       a.trace = c->d_trace.as<unsigned long long>();
       c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
     }
@@ -619,6 +749,9 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   }
 
   // ---- separate kernels, PDL-chained: partial passes (SKIP_*), per-kernel timing, NCCL all-reduce in between ----
+  px = PartExchange{};
+  px.mine = px.zero = c->d_part.as<unsigned long long>();
+  px.sync = c->d_sync.as<PassSync>();
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   if (do_rec && run.n > 0 && M > 0) {
     const PodView pv = pod_view(run);
@@ -772,10 +905,15 @@ int kt_comm_init(kt_ctx* c, const uint8_t uid[128], int nranks, int rank) {
 int kt_comm_destroy(kt_ctx* c) {
   if (!c) return KT_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
+  if (set_device(c) == KT_OK) {
+    cudaStreamSynchronize(c->stream);
+    release_window(c);
+  }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   c->nranks = 1;
   c->rank = 0;
+  c->p2p_failed = false;
   return KT_OK;
 }
 

@@ -37,6 +37,7 @@ constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one 
 constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kDecidePrefetch = 3;   // match words per warp whose check constants the decide tile stages in one go
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
@@ -124,9 +125,10 @@ struct PassSync {
   unsigned ticket;    // next tile
   unsigned rec_done;  // reconcile tiles finished (their REDs are performed at L2)
   unsigned fin_done;  // finalize tiles finished (check constants written)
+  unsigned match_done;  // pending-match tiles finished (affectedThrottles rows written)
   unsigned exited;    // CTAs that are done with everything; the last one re-arms the counters
   unsigned epoch;     // multi-GPU: last pass whose partial sums this rank has published (peers poll it over NVLink)
-  unsigned pad[3];
+  unsigned pad[2];
 };
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -168,12 +170,13 @@ struct PartExchange {
 // How a dependent role waits for its producer: programmatic dependent launch between separate kernels ...
 struct PdlSync {
   __device__ __forceinline__ void wait_reconciled(const PartExchange&) const { pdl_wait_primary(); }
+  __device__ __forceinline__ void wait_matched() const {}  // same CTA: a barrier already ordered the rows
   __device__ __forceinline__ void wait_finalized() const { pdl_wait_primary(); }
 };
 // ... or counters inside the one fused kernel (plus the peers' epochs when the sums are exchanged over NVLink)
 struct FlagSync {
   PassSync* s;
-  unsigned n_rec, n_fin;
+  unsigned n_rec, n_fin, n_match;
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px) const {
     if (threadIdx.x == 0) {
       while (ld_acquire_gpu(&s->rec_done) < n_rec) __nanosleep(40);
@@ -188,6 +191,7 @@ struct FlagSync {
     }
     __syncthreads();
   }
+  __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match); }
   __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin); }
 };
 
@@ -230,6 +234,12 @@ struct PodRows<false> {
   int stride;
   __device__ __forceinline__ void init(int32_t* base, int tid, int tile) { col = reinterpret_cast<uint32_t*>(base) + tid; stride = tile; }
 };
+
+template <bool REG>
+__device__ __forceinline__ uint32_t rows_touch(const PodRows<REG>& r) {
+  if constexpr (REG) return r.off[0] ^ r.off[7];
+  else return r.col[0];
+}
 
 // Translate eight label slots (one chunk) of a pod row.  No predicates: the device label columns are
 // padded to a multiple of eight slots with KT_LABEL_EMPTY, keydir has a sentinel entry at [n_keydir]
@@ -382,8 +392,16 @@ __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool
 template <int TPC, int B, int RT, bool REG>
 __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableView& tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
                                                unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */,
-                                               unsigned char* smem_raw, int64_t tile_index) {
+                                               unsigned char* smem_raw, int64_t tile_index, unsigned long long* trace_row = nullptr) {
   constexpr int TILE = kTileReconcile;
+  // optional stage stamps of warp 0 (kt_enable_trace): [4] rows loaded+translated, [5] barrier passed, [6] words done, [7] sweep done
+  auto stamp = [&](int k) {
+    if (trace_row && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace_row[k] = t;
+    }
+  };
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                                     // [R][TILE], 0 where absent
   unsigned long long* s_used = reinterpret_cast<unsigned long long*>(s_req + (size_t)R * TILE);  // [S][R][32]
   int32_t* s_rowid = reinterpret_cast<int32_t*>(s_used + (size_t)S * R * 32);                    // [L][TILE] (!REG)
@@ -431,7 +449,10 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   int j = 0, hi = 0;
   if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  if (trace_row && threadIdx.x == 0 && (rows_touch(rows) | (uint32_t)cur) == 0x12345u) trace_row[4] = 1;  // forces the loads to have landed
+  stamp(4);
   __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
+  stamp(5);
 
   unsigned long long* part_used = part;
   unsigned long long* part_pres = part + (size_t)R * tb.M;
@@ -547,6 +568,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       }
     }
   }
+  stamp(6);
   __syncthreads();
   // CTA accumulators -> HBM partials: one RED per (throttle, resource) the tile touched.
   for (int idx = tid; idx < S * 32; idx += TILE) {
@@ -563,6 +585,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;  // idempotent flag
     }
   }
+  stamp(7);
 }
 
 template <int TPC, int B, int RT, bool REG>
@@ -732,9 +755,15 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 // constants of a word's 32 throttles are staged in shared memory by the warp (lane = throttle) so the
 // per-pair work is shared-memory compares instead of dependent global gathers.
 // ------------------------------------------------------------------------------------------------
+// KS = match words per warp whose constants are staged together (1..kDecidePrefetch, bounded by shared memory)
+__host__ __device__ inline int decide_stage_words(int R, int tile) {
+  const size_t per_word = (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);
+  int ks = (int)((40u << 10) / per_word);
+  return ks < 1 ? 1 : (ks > 3 ? 3 : ks);
+}
 __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
-  const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                              // check_match_tile
-  const size_t decide = (size_t)R * tile * 8 + (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);    // check_decide_tile
+  const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                                                        // check_match_tile
+  const size_t decide = (size_t)R * tile * 8 + (size_t)decide_stage_words(R, tile) * (tile / 32) * 32 * (16 + 16 * (size_t)R);  // check_decide_tile
   return match > decide ? match : decide;
 }
 
@@ -779,14 +808,14 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 // throttles are staged in shared memory by the warp (lane = throttle), so the per-pair work is shared-memory compares
 // instead of dependent global gathers.
 template <int TILE, class Sync>
-__device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, const unsigned char* __restrict__ check,
+__device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ check,
                                                   const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                   unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync) {
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
-  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][32][rec]
+  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][KS][32][rec]
   const int tid = threadIdx.x, lane = tid & 31;
-  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * 32 * rec;
+  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * KS * 32 * rec;
   const int Wp = tb.Wp;
   const int64_t p = tile_index * TILE + tid;
   const bool valid = p < pods.n;
@@ -807,36 +836,42 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
   }
   int j = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+  // Everything that can be known before finalize is done is worked out now: the pod's match words, and the warp's
+  // first KS words in the warp-uniform order with the set of throttles any lane needs of each.  After the wait only the
+  // constants are missing, and the records of all KS words are staged with ONE round trip to L2.
+  sync.wait_matched();
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  int pw[kDecidePrefetch];         // warp-uniform word index
+  uint32_t pany[kDecidePrefetch];  // throttles of that word some lane matched
+  uint32_t pword[kDecidePrefetch]; // this lane's match word
+#pragma unroll
+  for (int k = 0; k < kDecidePrefetch; ++k) {
+    pw[k] = 0x7fffffff;
+    pany[k] = 0;
+    pword[k] = 0;
+    if (k < KS) {
+      pw[k] = __reduce_min_sync(kFull, cur);
+      if (pw[k] != 0x7fffffff) {
+        if (cur == pw[k]) {
+          pword[k] = __ldcg(&bitmap[p * Wp + pw[k]]);
+          ++j;
+          cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+        }
+        pany[k] = __reduce_or_sync(kFull, pword[k]);
+      }
+    }
+  }
 
-  sync.wait_finalized();  // the match rows of this tile and the check constants are written
+  sync.wait_finalized();  // the check constants are written
 
   unsigned char ok = 1;
-#pragma unroll 1
-  while (true) {  // words in ascending order, warp-uniform
-    const int w = __reduce_min_sync(kFull, cur);
-    if (w == 0x7fffffff) break;
-    uint32_t word = 0;
-    if (cur == w) {
-      word = __ldcg(&bitmap[p * Wp + w]);
-      ++j;
-      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
-    }
-    const uint32_t any = __reduce_or_sync(kFull, word);
-    if (!any) continue;
-    __syncwarp();
-    if ((any >> lane) & 1) {  // lane = throttle: stage its record
-      const uint4* src = reinterpret_cast<const uint4*>(check + (size_t)(w * 32 + lane) * rec);
-      uint4* dst = reinterpret_cast<uint4*>(my_chk + (size_t)lane * rec);
-      for (int q = 0; q <= R; ++q) dst[q] = __ldcg(&src[q]);
-    }
-    __syncwarp();
-    if (!word) continue;
+  // one lane's verdicts on the throttles of one word, from the staged records
+  auto decide_word = [&](uint32_t word, int w, const unsigned char* recs) {
     uint32_t c0 = 0, c1 = 0;
     while (word) {
       const int b = __ffs(word) - 1;
       word &= word - 1;
-      const unsigned char* cb = my_chk + (size_t)b * rec;
+      const unsigned char* cb = recs + (size_t)b * rec;
       const uint4 hq = *reinterpret_cast<const uint4*>(cb);
       const long long* thrv = reinterpret_cast<const long long*>(cb + 16);
       const long long* head = thrv + R;
@@ -870,6 +905,38 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     }
     if (c0) codes[p * 2 * Wp + 2 * w] = c0;
     if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+  };
+  auto stage = [&](uint32_t any, int w, unsigned char* recs) {  // lane = throttle
+    if ((any >> lane) & 1) {
+      const uint4* src = reinterpret_cast<const uint4*>(check + (size_t)(w * 32 + lane) * rec);
+      uint4* dst = reinterpret_cast<uint4*>(recs + (size_t)lane * rec);
+      for (int q = 0; q <= R; ++q) dst[q] = __ldcg(&src[q]);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kDecidePrefetch; ++k)
+    if (k < KS && pany[k]) stage(pany[k], pw[k], my_chk + (size_t)k * 32 * rec);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < kDecidePrefetch; ++k)
+    if (k < KS && pword[k]) decide_word(pword[k], pw[k], my_chk + (size_t)k * 32 * rec);
+  // pods with more words than were prefetched (ClusterThrottle-heavy namespaces): one word at a time
+#pragma unroll 1
+  while (true) {
+    const int w = __reduce_min_sync(kFull, cur);
+    if (w == 0x7fffffff) break;
+    uint32_t word = 0;
+    if (cur == w) {
+      word = __ldcg(&bitmap[p * Wp + w]);
+      ++j;
+      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+    }
+    const uint32_t any = __reduce_or_sync(kFull, word);
+    if (!any) continue;
+    __syncwarp();
+    stage(any, w, my_chk);
+    __syncwarp();
+    if (word) decide_word(word, w, my_chk);
   }
   if (valid) admit[p] = ok;
 }
@@ -882,7 +949,7 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
   extern __shared__ __align__(16) unsigned char smem_raw[];
   check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
   __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
-  check_decide_tile<kTileCheck>(pods, tb, R, check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{});
+  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -908,7 +975,7 @@ struct PassArgs {
   uint32_t eval_flags;
   int L, R, S, G;
   unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]
-  unsigned long long* trace;     // optional (kt_enable_trace): per CTA {ticket, sm, t_start, t_end} in globaltimer ns
+  unsigned long long* trace;     // optional (kt_enable_trace): per CTA 8 x u64 {ticket, sm, t_start, t_end, 4 stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -927,19 +994,19 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(c
   }
   __syncthreads();
   unsigned tile = s_ticket;
-  // fin_done counts the pending-match tiles as well: a decide tile needs both its match rows and the constants
-  const FlagSync sync{a.sync, a.n_rec, a.n_fin + a.n_chk};
+  const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
   if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
-    cta_signal(&a.sync->fin_done);
+    cta_signal(&a.sync->match_done);
   } else if ((tile -= a.n_chk) < a.n_rec) {
-    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile);
+    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile,
+                                    a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
     finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync);
     cta_signal(&a.sync->fin_done);
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -947,7 +1014,7 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(c
     if (a.trace) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* row = a.trace + (size_t)s_ticket * 4;
+      unsigned long long* row = a.trace + (size_t)s_ticket * 8;
       row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
     }
     const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
@@ -955,6 +1022,7 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(c
       a.sync->ticket = 0;
       a.sync->rec_done = 0;
       a.sync->fin_done = 0;
+      a.sync->match_done = 0;
       a.sync->exited = 0;
     }
   }

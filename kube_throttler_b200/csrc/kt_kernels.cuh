@@ -128,7 +128,8 @@ struct PassSync {
   unsigned match_done;  // pending-match tiles finished (affectedThrottles rows written)
   unsigned exited;    // CTAs that are done with everything; the last one re-arms the counters
   unsigned epoch;     // multi-GPU: last pass whose partial sums this rank has published (peers poll it over NVLink)
-  unsigned pad[2];
+  unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
+  unsigned pad;
 };
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -169,7 +170,7 @@ struct PartExchange {
 
 // How a dependent role waits for its producer: programmatic dependent launch between separate kernels ...
 struct PdlSync {
-  __device__ __forceinline__ void wait_reconciled(const PartExchange&) const { pdl_wait_primary(); }
+  __device__ __forceinline__ void wait_reconciled(const PartExchange&, bool = true) const { pdl_wait_primary(); }
   __device__ __forceinline__ void wait_matched() const {}  // same CTA: a barrier already ordered the rows
   __device__ __forceinline__ void wait_finalized() const { pdl_wait_primary(); }
 };
@@ -177,16 +178,25 @@ struct PdlSync {
 struct FlagSync {
   PassSync* s;
   unsigned n_rec, n_fin, n_match;
-  __device__ __forceinline__ void wait_reconciled(const PartExchange& px) const {
+  // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
+  __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
       while (ld_acquire_gpu(&s->rec_done) < n_rec) __nanosleep(40);
       if (px.npeers > 0) {
-        // publish: this rank's partial sums of pass `epoch` are complete (all its REDs are performed) ...
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;  // every finalize tile stores the same value
-        // ... and wait until every peer has published the same pass
-        for (int i = 0; i < px.npeers; ++i)
-          while ((int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) < 0) __nanosleep(100);
+        if (first_tile) {
+          // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
+          // which is where the peers read them) ...
+          __threadfence_system();
+          *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
+          // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
+          for (int i = 0; i < px.npeers; ++i)
+            while ((int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) < 0) __nanosleep(20);
+          // ... and tell the other finalize tiles of this rank
+          __threadfence();
+          *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
+        } else {
+          while ((int)(ld_acquire_gpu(&px.sync->peers_epoch) - px.epoch) < 0) __nanosleep(40);
+        }
       }
     }
     __syncthreads();
@@ -605,7 +615,16 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconc
 template <class Sync>
 __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int R, int G, long long now, uint32_t eval_flags, const PartExchange& px,
                                               const ReconcileView& out, unsigned char* __restrict__ check /* [M][16 + 16R] */, int tile_index,
-                                              const Sync& sync) {
+                                              const Sync& sync, unsigned long long* trace_row = nullptr) {
+  // optional stage stamps (kt_enable_trace): [4] thresholds loaded, waiting; [5] partial sums of every rank complete;
+  // [6] sums read (peers over NVLink); [7] constants written
+  auto stamp = [&](int k) {
+    if (trace_row && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace_row[k] = t;
+    }
+  };
   const int gid = tile_index * (int)blockDim.x + (int)threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int t = gid / G, r = gid % G;  // G divides 32: a group never straddles a warp
@@ -665,7 +684,9 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   }
   const bool is_throttle_kind = in_range ? tv.kind[t] == KT_KIND_THROTTLE : true;
 
-  sync.wait_reconciled(px);  // the partial sums (of every rank) are complete and visible
+  stamp(4);
+  sync.wait_reconciled(px, tile_index == 0);  // the partial sums (of every rank) are complete and visible
+  stamp(5);
 
   // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count; with peers the
   // all-reduce happens right here: every rank adds up the same buffers over NVLink (uncached loads) ----
@@ -676,15 +697,26 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     const size_t i_has = (size_t)(R + r) * M + t;  // resource lanes only
     unsigned long long v = __ldcg(&px.mine[i_val]);
     unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
-    for (int i = 0; i < px.npeers; ++i) {
-      v += __ldcv(&px.peer[i][i_val]);
-      if (is_res) h += __ldcv(&px.peer[i][i_has]);
+    // peer windows are not cached in this GPU's L2; ld.cg keeps them out of L1 as well and, unlike volatile loads, lets
+    // all of a lane's peer loads be in flight together (one NVLink round trip instead of 2 x npeers)
+    unsigned long long pv[7], ph[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      pv[i] = ph[i] = 0ull;
+      if (i < px.npeers) {
+        pv[i] = __ldcg(&px.peer[i][i_val]);
+        if (is_res) ph[i] = __ldcg(&px.peer[i][i_has]);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { v += pv[i]; h += ph[i]; }
     used_val = (long long)v;
     used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
     px.zero[i_val] = 0ull;
     if (is_res) px.zero[i_has] = 0ull;
   }
+  if (trace_row && threadIdx.x == 0 && used_val == 0x7fffffffffffffffll) trace_row[6] = 1;  // the loads have landed
+  stamp(6);
   const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
   // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
   const bool throttled = live && calc_has && used_has && used_val >= calc_val;
@@ -741,6 +773,7 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
     *reinterpret_cast<CheckHdr*>(check + (size_t)t * (16 + 16 * R)) = h;
   }
+  stamp(7);
 }
 
 __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, int G, long long now, uint32_t eval_flags, PartExchange px,
@@ -1003,7 +1036,7 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(c
                                     a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
-    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync);
+    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
     cta_signal(&a.sync->fin_done);
   } else {
     check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);

@@ -196,10 +196,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    # NCCL prints its version banner on stdout at communicator creation; stdout belongs to the ONE JSON line of rank 0,
+    # so file descriptor 1 points at stderr until the communicators exist
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -214,6 +218,12 @@ def main():
         uid = [kt.Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], world, rank)
+        dist.barrier()  # first collective on torch's communicator: creates it now, while stdout is still parked
+        torch.cuda.synchronize()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     eng.upload_snapshot(snap)
     Wp = eng.words_per_row
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2

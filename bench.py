@@ -228,6 +228,7 @@ def main():
     Wp = eng.words_per_row
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     drain = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    drain_i64 = drain.view(torch.int64)  # summed in place: a plain 512 MiB read, no dtype-promotion copy
     align_t = torch.zeros(1, device="cuda")
 
     def one_pass(timed):
@@ -237,7 +238,7 @@ def main():
                 # ... then READ another one, so that what sits in L2 when the timed region starts is clean: otherwise every
                 # line the pass allocates first writes back 128 B of the flush's own dirty data (24 MB of foreign DRAM
                 # writes inside the timed region of a 28 MB pass)
-                drain.sum()
+                drain_i64.sum()
             if world > 1:
                 # line the ranks up AFTER the flush and OUTSIDE the timed events: the flush kernels of different GPUs
                 # finish several microseconds apart, and a rank that enters the pass early would otherwise spend that

@@ -205,6 +205,23 @@ int kt_upload_pods(kt_ctx* ctx, int kind, int64_t n,
                    const int64_t* labels /*[L][n]*/, const int64_t* req /*[R][n]*/,
                    const uint32_t* present /*[n]*/, const uint32_t* flags /*[n]*/,
                    const int32_t* ns_id /*[n]*/);
+/* The same rows in a COMPACT transfer format: the host link, not the device, bounds an end-to-end pass (11.9 MB of int64
+ * columns per C2 snapshot), so a packer that knows its dictionaries are small can send 56 instead of 108 bytes per row;
+ * a device kernel expands them into the very int64 columns above (the HBM layout and every result are unchanged).
+ *   labels32[L][n]  (keyId << val_bits) | valId, 0xFFFFFFFF = empty slot; needs keyId < 2^(32-val_bits), valId < 2^val_bits
+ *                   and (keyId, valId) != (all ones)
+ *   req32[R][n]     value >> req_shift[r], as int32: exact only if the low req_shift[r] bits of every value are zero and the
+ *                   quotient fits (the packer checks; e.g. shift 20 for byte quantities that are multiples of 1Mi)
+ *   present[n]      as above
+ *   meta[n]         ns_id | flags << 29   (ns_id < 2^29)
+ * Returns KT_ERR_INVALID for val_bits outside 1..31 or a shift outside 0..32. */
+int kt_upload_pods_compact(kt_ctx* ctx, int kind, int64_t n, int32_t val_bits, const uint32_t* labels32 /*[L][n]*/,
+                           const int32_t* req32 /*[R][n]*/, const int32_t* req_shift /*[R]*/,
+                           const uint32_t* present /*[n]*/, const uint32_t* meta /*[n]*/);
+/* With async uploads on, kt_upload_pods / kt_upload_pods_compact return as soon as the copies are QUEUED: the caller must
+ * keep the host buffers alive and unchanged until kt_sync or any kt_get_* has returned.  Saves one stream
+ * synchronisation per upload on the latency-sensitive end-to-end path.  Off by default. */
+int kt_set_async_uploads(kt_ctx* ctx, int on);
 /* Row-level delta (pod informer Add/Update/Delete, throttle_controller.go:431-532):
  * columns are compact [L][k] / [R][k] / [k]; rows[i] < current n.  A deleted pod is a row
  * with flags == 0 (never counted) and all label slots empty. */

@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
 
 EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
-    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_update_pod_rows", "kt_upload_namespaces",
+    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
     "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy",
@@ -74,6 +74,8 @@ def lib():
         L.kt_host_free.argtypes = [vp]
         L.kt_host_free.restype = None
         L.kt_upload_pods.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
+        L.kt_set_async_uploads.argtypes = [vp, C.c_int]
+        L.kt_upload_pods_compact.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
         L.kt_update_pod_rows.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.kt_upload_namespaces.argtypes = [vp, C.c_int32, vp]
         L.kt_upload_throttles.argtypes = [vp, C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable)]
@@ -175,6 +177,16 @@ class Engine:
         self._ck(self._L.kt_upload_pods(self._h, kind, pods.n, abi.ptr(pods.labels), abi.ptr(pods.req), abi.ptr(pods.present),
                                         abi.ptr(pods.flags), abi.ptr(pods.ns_id)))
         self.n[kind] = pods.n
+
+    def set_async_uploads(self, on: bool = True):
+        """Uploads return once queued; the host buffers must stay untouched until sync() / a getter returns."""
+        self._ck(self._L.kt_set_async_uploads(self._h, int(on)))
+
+    def upload_pods_compact(self, kind: int, cp: "abi.CompactPodCols"):
+        """kt_upload_pods_compact: 56 instead of 108 bytes per row over the host link; expanded to the same int64 columns on the device."""
+        self._ck(self._L.kt_upload_pods_compact(self._h, kind, cp.n, cp.val_bits, abi.ptr(cp.labels32), abi.ptr(cp.req32), abi.ptr(cp.req_shift),
+                                                abi.ptr(cp.present), abi.ptr(cp.meta)))
+        self.n[kind] = cp.n
 
     def update_pod_rows(self, kind: int, rows: np.ndarray, pods: PodCols):
         rows = np.ascontiguousarray(rows, np.int64)

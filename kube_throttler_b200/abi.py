@@ -113,6 +113,58 @@ class PodCols:
 
 
 @dataclass
+class CompactPodCols:
+    """The compact transfer format of kt_upload_pods_compact (include/kt_b200.h).  Built by a packer that knows its
+    dictionaries; `compact_pods` below derives it from wide columns and REFUSES anything that would not expand exactly."""
+    val_bits: int
+    labels32: np.ndarray   # [L][n] u32
+    req32: np.ndarray      # [R][n] i32
+    req_shift: np.ndarray  # [R] i32
+    present: np.ndarray    # [n] u32
+    meta: np.ndarray       # [n] u32 = ns_id | flags << 29
+
+    @property
+    def n(self) -> int:
+        return int(self.present.shape[0])
+
+    @property
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.labels32, self.req32, self.req_shift, self.present, self.meta))
+
+
+def compact_pods(pods: PodCols, val_bits: int = 20) -> CompactPodCols:
+    """Wide int64 pod columns -> compact transfer columns, exactly (raises ValueError when a value does not fit:
+    key/value ids beyond the bit split, requests that are not multiples of a power of two small enough for int32,
+    namespace ids >= 2^29).  Pure repacking; nothing is evaluated."""
+    lab = pods.labels
+    empty = lab == LABEL_EMPTY
+    key, val = (lab >> 32) & 0xFFFFFFFF, lab & 0xFFFFFFFF
+    if ((~empty) & ((key >> (32 - val_bits) != 0) | (val >> val_bits != 0))).any():
+        raise ValueError(f"label ids do not fit a {32 - val_bits}+{val_bits} bit split")
+    lab32 = np.where(empty, 0xFFFFFFFF, (key << val_bits) | val).astype(np.uint32)
+    if ((~empty) & (lab32 == 0xFFFFFFFF)).any():
+        raise ValueError("a label collides with the empty-slot code")
+    R = pods.req.shape[0]
+    shift = np.zeros(R, np.int32)
+    req32 = np.zeros(pods.req.shape, np.int32)
+    for r in range(R):
+        col = pods.req[r]
+        nz = col[col != 0]
+        sh = 0
+        if nz.size:
+            low = int(np.bitwise_or.reduce(nz))           # common trailing zero bits of the column
+            sh = min((low & -low).bit_length() - 1, 32)
+            if np.abs(nz >> sh).max() >= 2**31:
+                raise ValueError(f"resource column {r} does not fit int32 even after dropping {sh} common zero bits")
+        shift[r] = sh
+        req32[r] = (col >> sh).astype(np.int32)
+    if pods.n and (int(pods.ns_id.max()) >= 1 << 29 or int(pods.ns_id.min()) < 0 or int(pods.flags.max()) > 7):
+        raise ValueError("namespace id / flags do not fit the packed meta word")
+    meta = (pods.ns_id.astype(np.uint32) | (pods.flags.astype(np.uint32) << np.uint32(29))).astype(np.uint32)
+    return CompactPodCols(val_bits, np.ascontiguousarray(lab32), np.ascontiguousarray(req32), shift, np.ascontiguousarray(pods.present, np.uint32), meta)
+
+
+@dataclass
 class Snapshot:
     """Everything one pass consumes, as the int64/u32 columns of include/kt_b200.h."""
     R: int

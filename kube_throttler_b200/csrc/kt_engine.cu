@@ -45,8 +45,12 @@ struct DevBuf {
 struct PodStore {
   int64_t n = 0;
   DevBuf labels, req, present, flags, ns;
+  DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
   DevBuf bitmap;  // [n][Wp]
-  void release() { labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); }
+  void release() {
+    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release();
+    c_labels.release(); c_req.release(); c_meta.release();
+  }
 };
 
 // ---- NCCL through dlopen: the library loads without NCCL; only kt_comm_* needs it ------------------
@@ -130,7 +134,14 @@ struct kt_ctx {
   uint32_t trace_roles[4] = {0, 0, 0, 0};
   bool fused = true;  // one-launch pass (k_pass) when the whole pass is asked for; three PDL-chained kernels otherwise
   DevBuf d_check;  // [M][16+16R]
-  DevBuf d_o_used, d_o_used_present, d_o_used_cnt, d_o_throttled, d_o_calc_thr, d_o_calc_present, d_o_calc_cnt, d_o_ovr_active;
+  // per-throttle outputs of the reconcile half: ONE device block (and one pinned host mirror) so that kt_get_reconcile
+  // is a single D2H copy; o_off[i] = byte offset of {used, used_cnt, calc_thr, calc_cnt, used_present, throttled,
+  // calc_present, override_active}
+  DevBuf d_out;
+  void* h_out = nullptr;
+  size_t h_out_cap = 0, out_bytes = 0;
+  size_t o_off[8] = {};
+  bool async_uploads = false;  // kt_set_async_uploads
   DevBuf d_codes, d_admit;
   bool evaluated = false;
   // multi-GPU
@@ -437,8 +448,8 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
-                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_o_used, &c->d_o_used_present, &c->d_o_used_cnt, &c->d_o_throttled,
-                   &c->d_o_calc_thr, &c->d_o_calc_present, &c->d_o_calc_cnt, &c->d_o_ovr_active, &c->d_codes, &c->d_admit};
+                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_out, &c->d_codes, &c->d_admit};
+  if (c->h_out) cudaFreeHost(c->h_out);
   for (DevBuf* b : all) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -479,6 +490,13 @@ int64_t kt_get_trace(kt_ctx* c, uint64_t* rows, int64_t cap, uint32_t roles[4]) 
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
   if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
   return n;
+}
+
+int kt_set_async_uploads(kt_ctx* c, int on) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->async_uploads = on != 0;
+  return KT_OK;
 }
 
 int kt_sync(kt_ctx* c) {
@@ -523,7 +541,41 @@ int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const 
   if ((rc = upload(c, s.ns, ns_id, (size_t)n))) return rc;
   s.n = n;
   c->evaluated = false;
-  KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
+  if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
+  return KT_OK;
+}
+
+int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, const uint32_t* labels32, const int32_t* req32, const int32_t* req_shift,
+                           const uint32_t* present, const uint32_t* meta) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (n < 0 || !req_shift || (n > 0 && (!labels32 || !req32 || !present || !meta))) return fail(c, KT_ERR_INVALID, "null compact pod columns");
+  if (val_bits < 1 || val_bits > 31) return fail(c, KT_ERR_INVALID, "val_bits %d outside 1..31", val_bits);
+  const int L = c->lim.label_slots, R = c->lim.n_resources, Lpad = (L + 7) & ~7;
+  for (int r = 0; r < R; ++r)
+    if (req_shift[r] < 0 || req_shift[r] > 32) return fail(c, KT_ERR_INVALID, "req_shift[%d] = %d outside 0..32", r, req_shift[r]);
+  int rc = set_device(c);
+  if (rc) return rc;
+  PodStore& s = c->pods[kind];
+  KT_CUDA(c, s.labels.reserve((size_t)Lpad * n * 8 + 16));
+  KT_CUDA(c, s.req.reserve((size_t)R * n * 8 + 16));
+  KT_CUDA(c, s.flags.reserve((size_t)n * 4 + 16));
+  KT_CUDA(c, s.ns.reserve((size_t)n * 4 + 16));
+  if ((rc = upload(c, s.c_labels, labels32, (size_t)L * n)) || (rc = upload(c, s.c_req, req32, (size_t)R * n)) ||
+      (rc = upload(c, s.c_meta, meta, (size_t)n)) || (rc = upload(c, s.present, present, (size_t)n)))
+    return rc;
+  if (n > 0) {
+    ReqShifts sh{};
+    for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)req_shift[r];
+    k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, val_bits, s.c_labels.as<uint32_t>(), s.c_req.as<int32_t>(), sh,
+                                                                      s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(), s.req.as<int64_t>(),
+                                                                      s.flags.as<uint32_t>(), s.ns.as<int32_t>());
+    KT_CUDA(c, cudaGetLastError());
+  }
+  s.n = n;
+  c->evaluated = false;
+  if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
 }
 
@@ -601,14 +653,20 @@ int kt_upload_throttles(kt_ctx* c, int32_t m, const kt_throttle_cols* cols, cons
   KT_CUDA(c, c->d_part.reserve(part_bytes + 16));
   KT_CUDA(c, cudaMemsetAsync(c->d_part.p, 0, c->d_part.cap, c->stream));
   KT_CUDA(c, c->d_check.reserve((size_t)m * (16 + 16 * R) + 16));
-  KT_CUDA(c, c->d_o_used.reserve((size_t)R * m * 8 + 16));
-  KT_CUDA(c, c->d_o_used_present.reserve((size_t)m * 4 + 16));
-  KT_CUDA(c, c->d_o_used_cnt.reserve((size_t)m * 8 + 16));
-  KT_CUDA(c, c->d_o_throttled.reserve((size_t)m * 4 + 16));
-  KT_CUDA(c, c->d_o_calc_thr.reserve((size_t)R * m * 8 + 16));
-  KT_CUDA(c, c->d_o_calc_present.reserve((size_t)m * 4 + 16));
-  KT_CUDA(c, c->d_o_calc_cnt.reserve((size_t)m * 8 + 16));
-  KT_CUDA(c, c->d_o_ovr_active.reserve((size_t)m + 16));
+  {
+    const size_t sizes[8] = {(size_t)R * m * 8, (size_t)m * 8, (size_t)R * m * 8, (size_t)m * 8, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m};
+    size_t at = 0;
+    for (int i = 0; i < 8; ++i) { c->o_off[i] = at; at += (sizes[i] + 15) & ~(size_t)15; }
+    c->out_bytes = at;
+    KT_CUDA(c, c->d_out.reserve(at + 16));
+    if (c->h_out_cap < at) {
+      if (c->h_out) cudaFreeHost(c->h_out);
+      c->h_out = nullptr;
+      c->h_out_cap = 0;
+      KT_CUDA(c, cudaHostAlloc(&c->h_out, at + 16, cudaHostAllocDefault));
+      c->h_out_cap = at;
+    }
+  }
   c->have_throttles = true;
   c->have_status = false;
   c->have_reserved = false;
@@ -694,8 +752,10 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     tv.reserved = c->d_reserved.as<int64_t>(); tv.reserved_present = c->d_reserved_present.as<uint32_t>();
     tv.reserved_cnt = c->d_reserved_cnt.as<int64_t>();
   }
-  const ReconcileView ov{c->d_o_used.as<int64_t>(), c->d_o_used_present.as<uint32_t>(), c->d_o_used_cnt.as<int64_t>(), c->d_o_throttled.as<uint32_t>(),
-                         c->d_o_calc_thr.as<int64_t>(), c->d_o_calc_present.as<uint32_t>(), c->d_o_calc_cnt.as<int64_t>(), c->d_o_ovr_active.as<uint8_t>()};
+  unsigned char* ob = c->d_out.as<unsigned char>();
+  const ReconcileView ov{reinterpret_cast<int64_t*>(ob + c->o_off[0]), reinterpret_cast<uint32_t*>(ob + c->o_off[4]), reinterpret_cast<int64_t*>(ob + c->o_off[1]),
+                         reinterpret_cast<uint32_t*>(ob + c->o_off[5]), reinterpret_cast<int64_t*>(ob + c->o_off[2]), reinterpret_cast<uint32_t*>(ob + c->o_off[6]),
+                         reinterpret_cast<int64_t*>(ob + c->o_off[3]), reinterpret_cast<uint8_t*>(ob + c->o_off[7])};
   int G = 1;
   while (G < R + 1) G <<= 1;  // finalize lanes per throttle: resources + the pod count, padded to a power of two
   PartExchange px{};
@@ -811,19 +871,21 @@ int kt_get_reconcile(kt_ctx* c, const kt_reconcile_out* o) {
   int rc = set_device(c);
   if (rc) return rc;
   const size_t m = (size_t)c->M, R = (size_t)c->lim.n_resources;
-  auto dl = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
-    if (!dst || !bytes) return cudaSuccess;
-    return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream);
-  };
-  KT_CUDA(c, dl(o->used, c->d_o_used, R * m * 8));
-  KT_CUDA(c, dl(o->used_present, c->d_o_used_present, m * 4));
-  KT_CUDA(c, dl(o->used_cnt, c->d_o_used_cnt, m * 8));
-  KT_CUDA(c, dl(o->throttled, c->d_o_throttled, m * 4));
-  KT_CUDA(c, dl(o->calc_thr, c->d_o_calc_thr, R * m * 8));
-  KT_CUDA(c, dl(o->calc_present, c->d_o_calc_present, m * 4));
-  KT_CUDA(c, dl(o->calc_cnt, c->d_o_calc_cnt, m * 8));
-  KT_CUDA(c, dl(o->override_active, c->d_o_ovr_active, m));
+  // one copy of the whole block into the pinned mirror, then plain host copies into the caller's columns
+  if (c->out_bytes) KT_CUDA(c, cudaMemcpyAsync(c->h_out, c->d_out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const unsigned char* hb = reinterpret_cast<const unsigned char*>(c->h_out);
+  auto put = [&](void* dst, int i, size_t bytes) {
+    if (dst && bytes) std::memcpy(dst, hb + c->o_off[i], bytes);
+  };
+  put(o->used, 0, R * m * 8);
+  put(o->used_cnt, 1, m * 8);
+  put(o->calc_thr, 2, R * m * 8);
+  put(o->calc_cnt, 3, m * 8);
+  put(o->used_present, 4, m * 4);
+  put(o->throttled, 5, m * 4);
+  put(o->calc_present, 6, m * 4);
+  put(o->override_active, 7, m);
   return KT_OK;
 }
 

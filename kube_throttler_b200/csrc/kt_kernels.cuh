@@ -1078,6 +1078,30 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* 
   d_ns[row] = ns[i];
 }
 
+// Compact transfer rows -> the int64 HBM columns (kt_upload_pods_compact).  One lane per pod row; every column access is
+// coalesced.  Lpad - L padding label rows are filled with KT_LABEL_EMPTY here as well.
+struct ReqShifts { unsigned char s[32]; };
+__global__ void __launch_bounds__(256) k_unpack_rows(int64_t n, int L, int Lpad, int R, int val_bits, const uint32_t* __restrict__ labels32,
+                                                     const int32_t* __restrict__ req32, const ReqShifts req_shift,
+                                                     const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
+                                                     uint32_t* __restrict__ flags, int32_t* __restrict__ ns) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t vmask = (1u << val_bits) - 1u;
+  for (int s = 0; s < Lpad; ++s) {
+    int64_t lab = KT_LABEL_EMPTY;
+    if (s < L) {
+      const uint32_t c = __ldg(&labels32[(int64_t)s * n + p]);
+      if (c != 0xffffffffu) lab = (int64_t)(((uint64_t)(c >> val_bits) << 32) | (uint64_t)(c & vmask));
+    }
+    labels[(int64_t)s * n + p] = lab;
+  }
+  for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
+  const uint32_t m = __ldg(&meta[p]);
+  ns[p] = (int32_t)(m & 0x1fffffffu);
+  flags[p] = m >> 29;
+}
+
 // Gather k bitmap rows (one warp-wide strided copy per row).
 __global__ void __launch_bounds__(256) k_gather_rows(int64_t k, const int64_t* __restrict__ rows, int Wp, const uint32_t* __restrict__ bitmap,
                                                      uint32_t* __restrict__ out) {

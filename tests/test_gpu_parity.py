@@ -173,6 +173,32 @@ def test_fused_and_chained_paths_agree(kt, oracle):
             assert_same(snap, got, want)
 
 
+def test_compact_upload_equals_wide_upload(kt, oracle):
+    """kt_upload_pods_compact expands to exactly the int64 columns kt_upload_pods would have copied: same bits out."""
+    for kw in (dict(config="C3", m=300, n=6000, p=800), dict(config="C2", m=200, n=5000, p=700, L=12), dict(config="C2", m=40, n=70, p=33, R=1, L=3)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        for kind, pods in ((abi.PODS_RUNNING, snap.running), (abi.PODS_PENDING, snap.pending)):
+            cp = abi.compact_pods(pods)
+            assert cp.nbytes < 0.6 * sum(a.nbytes for a in (pods.labels, pods.req, pods.present, pods.flags, pods.ns_id))
+            eng.upload_pods_compact(kind, cp)
+        eng.evaluate(snap.now)
+        got = eng.download()
+        eng.close()
+        want = oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
+        assert_same(snap, got, want)
+    bad = synth.generate("C2", m=40, n=70, p=33).running
+    bad.req[0, 3] = (1 << 40) + 1  # odd and huge: no power-of-two unit makes the column fit int32
+    with pytest.raises(ValueError):
+        abi.compact_pods(bad)
+    bad = synth.generate("C2", m=40, n=70, p=33).running
+    bad.labels[0, 0] = (5 << 32) | (1 << 25)  # value id beyond the 20-bit split
+    with pytest.raises(ValueError):
+        abi.compact_pods(bad)
+
+
 def test_pod_row_delta(kt, oracle):
     """kt_update_pod_rows == re-uploading the modified columns (informer Add/Update/Delete as row scatters)."""
     snap = synth.generate("C2", m=200, n=5000, p=500)

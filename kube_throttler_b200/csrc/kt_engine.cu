@@ -46,10 +46,12 @@ struct PodStore {
   int64_t n = 0;
   DevBuf labels, req, present, flags, ns;
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
+  DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
     labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release();
     c_labels.release(); c_req.release(); c_meta.release();
+    t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
   }
 };
 
@@ -592,21 +594,16 @@ int kt_update_pod_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, cons
   int rc = set_device(c);
   if (rc) return rc;
   const int L = c->lim.label_slots, R = c->lim.n_resources;
-  DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns;
-  auto cleanup = [&]() { t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); };
-  if ((rc = upload(c, t_rows, rows, (size_t)k)) || (rc = upload(c, t_labels, labels, (size_t)L * k)) || (rc = upload(c, t_req, req, (size_t)R * k)) ||
-      (rc = upload(c, t_present, present, (size_t)k)) || (rc = upload(c, t_flags, flags, (size_t)k)) || (rc = upload(c, t_ns, ns_id, (size_t)k))) {
-    cleanup();
+  // grow-only staging buffers: an informer event must not cost a cudaMalloc/cudaFree pair
+  if ((rc = upload(c, s.t_rows, rows, (size_t)k)) || (rc = upload(c, s.t_labels, labels, (size_t)L * k)) || (rc = upload(c, s.t_req, req, (size_t)R * k)) ||
+      (rc = upload(c, s.t_present, present, (size_t)k)) || (rc = upload(c, s.t_flags, flags, (size_t)k)) || (rc = upload(c, s.t_ns, ns_id, (size_t)k)))
     return rc;
-  }
-  k_scatter_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, t_rows.as<int64_t>(), L, R, s.n, t_labels.as<int64_t>(), t_req.as<int64_t>(),
-                                                                     t_present.as<uint32_t>(), t_flags.as<uint32_t>(), t_ns.as<int32_t>(),
+  k_scatter_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, s.t_rows.as<int64_t>(), L, R, s.n, s.t_labels.as<int64_t>(), s.t_req.as<int64_t>(),
+                                                                     s.t_present.as<uint32_t>(), s.t_flags.as<uint32_t>(), s.t_ns.as<int32_t>(),
                                                                      s.labels.as<int64_t>(), s.req.as<int64_t>(), s.present.as<uint32_t>(),
                                                                      s.flags.as<uint32_t>(), s.ns.as<int32_t>());
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cleanup();
-  if (e != cudaSuccess) return fail(c, KT_ERR_CUDA, "k_scatter_rows: %s", cudaGetErrorString(e));
+  KT_CUDA(c, cudaGetLastError());
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   c->evaluated = false;
   return KT_OK;
 }
@@ -914,19 +911,13 @@ int kt_get_match_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, uint3
   int rc = set_device(c);
   if (rc) return rc;
   const int Wp = c->ht.Wp;
-  DevBuf t_rows, t_out;
-  cudaError_t e = t_rows.reserve((size_t)k * 8);
-  if (e == cudaSuccess) e = t_out.reserve((size_t)k * Wp * 4);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(t_rows.p, rows, (size_t)k * 8, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) {
-    k_gather_rows<<<(unsigned)((k + 7) / 8), 256, 0, c->stream>>>(k, t_rows.as<int64_t>(), Wp, s.bitmap.as<uint32_t>(), t_out.as<uint32_t>());
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(words, t_out.p, (size_t)k * Wp * 4, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  t_rows.release();
-  t_out.release();
-  if (e != cudaSuccess) return fail(c, KT_ERR_CUDA, "kt_get_match_rows: %s", cudaGetErrorString(e));
+  KT_CUDA(c, s.t_rows.reserve((size_t)k * 8));
+  KT_CUDA(c, s.t_words.reserve((size_t)k * Wp * 4));
+  KT_CUDA(c, cudaMemcpyAsync(s.t_rows.p, rows, (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+  k_gather_rows<<<(unsigned)((k + 7) / 8), 256, 0, c->stream>>>(k, s.t_rows.as<int64_t>(), Wp, s.bitmap.as<uint32_t>(), s.t_words.as<uint32_t>());
+  KT_CUDA(c, cudaGetLastError());
+  KT_CUDA(c, cudaMemcpyAsync(words, s.t_words.p, (size_t)k * Wp * 4, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
   return KT_OK;
 }
 

@@ -332,7 +332,7 @@ std::string err_json(const std::string& m) {
   w.begin_obj().key("error").str(m).end_obj();
   return w.out;
 }
-std::string g_new_plugin_error;
+thread_local std::string g_new_plugin_error;  // read back by kth_new_plugin_error() on the calling thread
 
 }  // namespace
 
@@ -795,12 +795,15 @@ struct kth_plugin {
     // pods that are reserved somewhere: their match rows decide what reconcile un-reserves (:135-155)
     std::vector<int64_t> rows;
     std::vector<std::string> row_pod;
-    for (int k = 0; k < 2; ++k)
-      for (auto& thr : cache[k].by_thr)
-        for (auto& pod : thr.second) {
-          auto it = pod_index.find(pod.first);
-          if (it != pod_index.end() && std::find(row_pod.begin(), row_pod.end(), pod.first) == row_pod.end()) { rows.push_back(it->second); row_pod.push_back(pod.first); }
-        }
+    {
+      std::set<std::string> seen;
+      for (int k = 0; k < 2; ++k)
+        for (auto& thr : cache[k].by_thr)
+          for (auto& pod : thr.second) {
+            auto it = pod_index.find(pod.first);
+            if (it != pod_index.end() && seen.insert(pod.first).second) { rows.push_back(it->second); row_pod.push_back(pod.first); }
+          }
+    }
     const int Wp = kt_match_words(ctx);
     std::vector<uint32_t> words(rows.size() * (size_t)Wp);
     if (!rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)rows.size(), rows.data(), words.data()), "kt_get_match_rows");

@@ -56,7 +56,9 @@ const char* kth_delete(kth_plugin* p, const char* kind, const char* ns, const ch
  * (throttle_controller.go:84-211, clusterthrottle_controller.go:87-214): status.used,
  * status.calculatedThreshold (replaced only when threshold or messages changed, Q6), status.throttled
  * (onEqual = true), observed pods un-reserved.  now_rfc3339 is the controller clock.
- * Returns {"reconciled":N,"changed":[...names of throttles whose status changed...]}. */
+ * Returns {"reconciled":N,"changed":[...names of throttles whose status changed...],
+ *          "requeueAfterNanos":{name: ns until the next temporaryThresholdOverride boundary}} -- the latter is
+ * NextOverrideHappensIn (throttle_types.go:37-63), what the reference passes to enqueueAfter (:201-208). */
 const char* kth_reconcile_all(kth_plugin* p, const char* now_rfc3339);
 
 /* status of one Throttle (ns != "") or ClusterThrottle (ns == ""):
@@ -84,7 +86,7 @@ const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn);
 /* Host-only helpers of the packer, exposed so that they can be pinned against the reference's unit
  * tests without a GPU: {"fn":"ParseQuantity","value":..} | {"fn":"PodRequestResourceList","pod":{..}} |
  * {"fn":"ResourceAmountOfPod","pod":{..}} | {"fn":"ParseRFC3339","value":..} |
- * {"fn":"OverrideMessages","throttle":{..}} | {"fn":"ValidateSelector","selector":{..}} |
+ * {"fn":"OverrideMessages","throttle":{..}} | {"fn":"NextOverrideHappensIn","throttle":{..},"now":..} | {"fn":"ValidateSelector","selector":{..}} |
  * {"fn":"CanonicalQuantity","value":..}.  Never touches a device. */
 const char* kth_eval(const char* request_json);
 

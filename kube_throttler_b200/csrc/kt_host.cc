@@ -775,6 +775,26 @@ struct kth_plugin {
     return msgs;
   }
 
+  // NextOverrideHappensIn (throttle_types.go:37-63): the nearest override boundary after `now`, i.e. when the throttle
+  // must be reconciled again although no object changed (the reference enqueues it with enqueueAfter, :201-208).
+  // An override whose Begin does not parse is skipped entirely; one whose End does not parse still contributes its Begin.
+  static bool next_override_happens_in(const ThrottleObj& o, const GoTime& now, __int128* nanos) {
+    bool have = false;
+    auto consider = [&](const GoTime& t) {
+      if (t.zero) return;  // time.Time{} is never After(now)
+      const __int128 d = t.ns() - now.ns();
+      if (d > 0 && (!have || d < *nanos)) { *nanos = d; have = true; }
+    };
+    for (auto& ov : o.overrides) {
+      GoTime b, e;
+      if (!ov.begin.empty() && !parse_rfc3339(ov.begin, &b).empty()) continue;
+      consider(b);
+      if (!ov.end.empty() && !parse_rfc3339(ov.end, &e).empty()) continue;
+      consider(e);
+    }
+    return have;
+  }
+
   // ---- reconcile: every throttle in one device pass ------------------------------------------------
   std::string reconcile_all(const std::string& now_s) {
     GoTime now;
@@ -784,7 +804,7 @@ struct kth_plugin {
     const size_t m = throttles.size();
     Writer w;
     w.begin_obj();
-    if (m == 0) { w.key("reconciled").num(0).key("changed").begin_arr().end_arr().end_obj(); return w.out; }
+    if (m == 0) { w.key("reconciled").num(0).key("changed").begin_arr().end_arr().key("requeueAfterNanos").begin_obj().end_obj().end_obj(); return w.out; }
     check(kt_evaluate(ctx, clamp_ns(now.ns()), KT_EVAL_FRESH_STATUS | KT_EVAL_SKIP_CHECK), "kt_evaluate");
     const int R = lim.n_resources;
     std::vector<int64_t> used((size_t)R * m), used_cnt(m), calc_thr((size_t)R * m), calc_cnt(m);
@@ -810,6 +830,7 @@ struct kth_plugin {
 
     int reconciled = 0;
     std::vector<std::string> changed;
+    std::vector<std::pair<std::string, long long>> requeue;
     for (size_t t = 0; t < m; ++t) {
       ThrottleObj& o = throttles[t];
       if (!o.live || o.throttler_name != name) continue;   // only responsible throttles are ever enqueued (:403-425)
@@ -851,6 +872,8 @@ struct kth_plugin {
       if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
       o.st_used = nu;
       if (status_changed) changed.push_back(o.nn());
+      __int128 after = 0;
+      if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
       // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache
       auto it = cache[o.kind].by_thr.find(o.nn());
       if (it != cache[o.kind].by_thr.end())
@@ -861,7 +884,10 @@ struct kth_plugin {
     status_dirty = true;
     w.key("reconciled").num(reconciled).key("changed").begin_arr();
     for (auto& c : changed) w.str(c);
-    w.end_arr().end_obj();
+    w.end_arr();
+    w.key("requeueAfterNanos").begin_obj();  // enqueueAfter(thr, *nextOverrideHappensIn)
+    for (auto& r : requeue) w.key(r.first).num(r.second);
+    w.end_obj().end_obj();
     return w.out;
   }
 
@@ -1266,6 +1292,16 @@ std::string eval_request(const Node& req) {
     w.begin_arr();
     for (auto& s : kth_plugin::override_messages(scratch.throttles[0])) w.str(s);
     w.end_arr();
+    return w.out;
+  }
+  if (fn == "NextOverrideHappensIn") {
+    scratch.apply_throttle(req["throttle"], req["throttle"]["kind"].str("Throttle") == "ClusterThrottle" ? KT_KIND_CLUSTERTHROTTLE : KT_KIND_THROTTLE);
+    GoTime now;
+    const std::string e = parse_rfc3339(req["now"].str(), &now);
+    if (!e.empty()) fail(e);
+    __int128 d = 0;
+    const bool have = kth_plugin::next_override_happens_in(scratch.throttles[0], now, &d);
+    w.begin_obj().key("have").boolean(have).key("nanos").num((long long)d).end_obj();
     return w.out;
   }
   if (fn == "ValidateSelector") {

@@ -91,6 +91,17 @@ def test_override_messages(host):
         'index 2: Failed to parse End: parsing time "nope" as "2006-01-02T15:04:05Z07:00": cannot parse "nope" as "2006"']
 
 
+@pytest.mark.parametrize("now", ["2021-08-04T09:00:00Z", "2021-08-04T10:00:00Z", "2021-08-04T12:00:00+09:00", "2021-08-05T10:00:00Z", "2021-08-06T00:00:00Z"])
+def test_next_override_happens_in(host, oracle, now):
+    """throttle_types.go:37-63: nearest begin/end after now; entries whose Begin does not parse are skipped whole."""
+    thr = {"kind": "Throttle", "metadata": {"name": "t", "namespace": "default"},
+           "spec": {"throttlerName": "x", "threshold": {}, "temporaryThresholdOverrides": [
+               {"begin": "2021-08-04T10:00:00Z", "end": "2021-08-05T10:00:00Z"}, {"begin": "garbage", "end": "2021-08-04T09:30:00Z"},
+               {"begin": "", "end": "2021-08-05T12:00:00Z"}, {"begin": "2021-08-04T11:00:00Z", "end": "nonsense"}]}}
+    got, want = host.eval_host("NextOverrideHappensIn", throttle=thr, now=now), oracle.call("NextOverrideHappensIn", throttle=thr, now=now)
+    assert got["have"] == want["have"] and (not want["have"] or got["nanos"] == want["nanos"])
+
+
 @pytest.mark.parametrize("sel,valid", [
     ({}, True), ({"matchLabels": {"a": "b"}}, True), ({"matchExpressions": [{"key": "a", "operator": "In", "values": ["x"]}]}, True),
     ({"matchExpressions": [{"key": "a", "operator": "Exists"}]}, True), ({"matchExpressions": [{"key": "a", "operator": "In", "values": []}]}, False),

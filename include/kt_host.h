@@ -76,6 +76,14 @@ const char* kth_pre_filter(kth_plugin* p, const char* pod_json);
  * result a JSON array of PreFilter results (each pod checked against the same snapshot, independently). */
 const char* kth_pre_filter_batch(kth_plugin* p, const char* pods_json);
 
+/* Queue-ordered admission: PreFilter and, on Success, Reserve for every pod of a SORTED scheduling queue, with exactly
+ * the results the scheduler gets admitting them one per cycle (each admitted pod raises the reservations the next one is
+ * checked against, plugin.go:148-238) -- but in as few device passes as the conflicts between the pods allow: a pass
+ * decides every undecided pod none of whose affected throttles was reserved on earlier in the same pass.
+ * {"rounds":k,"admitted":n,"results":[{"pod":"ns/name","round":i,"preFilter":{...as kth_pre_filter...}}...]} in queue order;
+ * the admitted pods stay reserved (kth_unreserve / a reconcile that observes them bound releases them). */
+const char* kth_admit_queue(kth_plugin* p, const char* pods_json);
+
 /* Reserve / Unreserve -- plugin.go:217-257: {"code":"Success"} or {"code":"Error","reasons":[...]}. */
 const char* kth_reserve(kth_plugin* p, const char* pod_json);
 const char* kth_unreserve(kth_plugin* p, const char* pod_json);

@@ -1047,6 +1047,69 @@ struct kth_plugin {
     return w.out;
   }
 
+  // ---- queue-ordered admission ----------------------------------------------------------------------------
+  // The scheduler admits one pod per cycle: PreFilter, and on Success Reserve, so every admitted pod raises the reserved
+  // amounts the NEXT pod is checked against (plugin.go:148-238).  For a sorted queue that sequence is reproduced exactly
+  // with far fewer device passes than pods: one pass checks every undecided pod against the current reservations; going
+  // through them in queue order, a pod's verdict is FINAL unless one of its affected throttles was reserved on by an
+  // earlier pod of this very pass or is shared with an earlier pod that is itself still undecided -- those pods wait
+  // for the next pass.  The first undecided pod is always final, so the loop terminates; pods that touch disjoint sets of
+  // throttles are decided together.
+  std::string admit_queue(const Node& arr) {
+    if (!arr.is(Node::Arr)) fail("expected a JSON array of pods");
+    std::vector<PodObj> queue;
+    for (auto& e : arr.arr) queue.push_back(pod_from(*e));
+    const size_t n = queue.size();
+    std::vector<std::string> results(n);
+    std::vector<int> round_of(n, 0);
+    std::vector<size_t> undecided(n);
+    for (size_t i = 0; i < n; ++i) undecided[i] = i;
+    int rounds = 0, admitted = 0;
+    while (!undecided.empty()) {
+      ++rounds;
+      std::vector<PodObj> batch;
+      for (size_t i : undecided) batch.push_back(queue[i]);
+      const PendingResult r = check_pending(batch, 0);
+      const size_t W = (size_t)r.Wp;
+      std::vector<uint32_t> dirty(W, 0);  // throttles whose reservation changed in this pass, or that an undecided earlier pod may still change
+      std::vector<size_t> next;
+      for (size_t k = 0; k < batch.size(); ++k) {
+        const size_t i = undecided[k];
+        const uint32_t* row = &r.bitmap[k * W];
+        bool clean = true;
+        for (size_t w = 0; w < W && clean; ++w) clean = (row[w] & dirty[w]) == 0;
+        if (!clean) {  // depends on something not settled yet: decide it in a later pass, and shield what it may change
+          for (size_t w = 0; w < W; ++w) dirty[w] |= row[w];
+          next.push_back(i);
+          continue;
+        }
+        Writer w;
+        prefilter_json(w, batch[k], r, k);
+        results[i] = w.out;
+        round_of[i] = rounds;
+        bool success = w.out.compare(0, 17, "{\"code\":\"Success\"") == 0;
+        if (!success) continue;
+        // Reserve (throttle_controller.go:271-292): ResourceAmountOfPod joins the reservation of every affected throttle
+        bool reserve_error = false;
+        for (int kind = 0; kind < 2; ++kind) reserve_error = reserve_error || !controller_error(batch[k], r, k, kind).empty();
+        if (reserve_error) continue;
+        ++admitted;
+        for (int kind = 0; kind < 2; ++kind)
+          for (int t : affected(r, k, kind)) cache[kind].add(throttles[(size_t)t].nn(), batch[k]);
+        reserved_dirty = true;
+        for (size_t w2 = 0; w2 < W; ++w2) dirty[w2] |= row[w2];
+      }
+      undecided.swap(next);
+    }
+    Writer out;
+    out.begin_obj().key("rounds").num(rounds).key("admitted").num(admitted).key("results").begin_arr();
+    for (size_t i = 0; i < n; ++i) {
+      out.begin_obj().key("pod").str(queue[i].nn()).key("round").num(round_of[i]).key("preFilter").raw(results[i]).end_obj();
+    }
+    out.end_arr().end_obj();
+    return out.out;
+  }
+
   // ---- informer events --------------------------------------------------------------------------------
   void apply_pod(const Node& v) {
     PodObj p = pod_from(v);
@@ -1407,6 +1470,9 @@ const char* kth_pre_filter_batch(kth_plugin* p, const char* pods_json) {
     w.end_arr();
     return w.out;
   });
+}
+const char* kth_admit_queue(kth_plugin* p, const char* pods_json) {
+  return guarded(p, [&]() { return p->admit_queue(*ktjson::parse(pods_json)); });
 }
 const char* kth_reserve(kth_plugin* p, const char* pod_json) {
   return guarded(p, [&]() { return p->reserve_json(*ktjson::parse(pod_json), true); });

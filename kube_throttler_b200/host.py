@@ -25,7 +25,7 @@ def _bind():
     L.kth_free.restype = None
     for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_reconcile_all", [vp, cp]),
                        ("kth_get_status", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
-                       ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_eval", [cp])):
+                       ("kth_admit_queue", [vp, cp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_eval", [cp])):
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = cp
@@ -34,7 +34,7 @@ def _bind():
 
 
 HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status",
-                "kth_pre_filter", "kth_pre_filter_batch", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_eval"]
+                "kth_pre_filter", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_eval"]
 
 
 def _result(raw):
@@ -93,6 +93,10 @@ class Plugin:
 
     def prefilter_batch(self, pods):
         return _result(self._L.kth_pre_filter_batch(self._h, json.dumps(list(pods)).encode()))
+
+    def admit_queue(self, pods):
+        """PreFilter -> Reserve for a sorted queue with the one-pod-per-cycle semantics, in few device passes."""
+        return _result(self._L.kth_admit_queue(self._h, json.dumps(list(pods)).encode()))
 
     def reserve(self, pod):
         return _result(self._L.kth_reserve(self._h, json.dumps(pod).encode()))

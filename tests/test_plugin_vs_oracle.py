@@ -173,6 +173,47 @@ def test_random_world(oracle, seed):
     dut.close()
 
 
+@pytest.mark.parametrize("seed", [11, 18, 19])
+def test_admit_queue_equals_one_pod_per_cycle(oracle, seed):
+    """kth_admit_queue == the scheduler's cycle (PreFilter, on Success Reserve) run pod by pod on the oracle: same verdict for
+    every pod of the queue, same reservations afterwards -- in far fewer device passes than pods."""
+    from kube_throttler_b200 import host
+
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i}" for i in range(5)]
+    for n in nss:
+        both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+    throttles = [rand_throttle(rng, i, nss) for i in range(40)]
+    for t in throttles:  # roomy thresholds: the queue has to fill them up pod by pod
+        thr = t["spec"]["threshold"]
+        if "resourceCounts" in thr:
+            thr["resourceCounts"]["pod"] = rng.choice([2, 5, 9, 40])
+        if "cpu" in thr.get("resourceRequests", {}):
+            thr["resourceRequests"]["cpu"] = rng.choice(["1", "2500m", "7", "30"])
+        t["spec"].pop("temporaryThresholdOverrides", None)
+    both(*throttles)
+    both(*[rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(40)])
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    queue = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(150)]
+    want = []
+    for p in queue:  # one pod per scheduling cycle
+        r = ref.prefilter(p)
+        if r["code"] == "Success":
+            assert ref.reserve(p)["code"] == "Success"
+        want.append(norm_prefilter(r))
+    got = dut.admit_queue(queue)
+    assert [norm_prefilter(x["preFilter"]) for x in got["results"]] == want
+    assert got["admitted"] == sum(w["code"] == "Success" for w in want) > 5
+    assert 1 < got["rounds"] < len(queue) / 2, got["rounds"]  # conflicts force several passes, far fewer than pods
+    for t in throttles:
+        k, nn = t["kind"], t["metadata"].get("namespace", "") + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (nn, a, b)
+    dut.close()
+
+
 def test_delete_events(oracle):
     """Pod and throttle deletes (informer DeleteFunc): the row becomes a tombstone and is reused; used sums follow."""
     from kube_throttler_b200 import host

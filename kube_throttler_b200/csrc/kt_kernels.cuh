@@ -173,6 +173,7 @@ struct PdlSync {
   __device__ __forceinline__ void wait_reconciled(const PartExchange&, bool = true) const { pdl_wait_primary(); }
   __device__ __forceinline__ void wait_matched() const {}  // same CTA: a barrier already ordered the rows
   __device__ __forceinline__ void wait_finalized() const { pdl_wait_primary(); }
+  __device__ __forceinline__ void signal_finalized() const {}  // the kernel boundary is the signal
 };
 // ... or counters inside the one fused kernel (plus the peers' epochs when the sums are exchanged over NVLink)
 struct FlagSync {
@@ -203,6 +204,7 @@ struct FlagSync {
   }
   __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match); }
   __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin); }
+  __device__ __forceinline__ void signal_finalized() const { cta_signal(&s->fin_done); }
 };
 
 // ---- label -> table row ---------------------------------------------------------------------------
@@ -712,8 +714,6 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     for (int i = 0; i < 7; ++i) { v += pv[i]; h += ph[i]; }
     used_val = (long long)v;
     used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
-    px.zero[i_val] = 0ull;
-    if (is_res) px.zero[i_has] = 0ull;
   }
   if (trace_row && threadIdx.x == 0 && used_val == 0x7fffffffffffffffll) trace_row[6] = 1;  // the loads have landed
   stamp(6);
@@ -751,19 +751,13 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   const bool s4c = is_cnt && thr_has && (on_equal ? au + 1 >= thr : au + 1 > thr);        // S4 (counts always present: the pod)
   const uint32_t m_s1c = group_mask(s1c), m_s4c = group_mask(s4c);
 
+  // the constants the decide tiles are waiting for go out FIRST and are signalled right away; the status columns (only the
+  // host reads them) and the re-zeroing of the partial sums follow, off the critical path
   if (is_res) {
-    if (out.used) out.used[col] = used_val;
-    if (out.calc_thr) out.calc_thr[col] = calc_val;
     long long* thrv = reinterpret_cast<long long*>(check + (size_t)t * (16 + 16 * R) + 16);
     thrv[r] = thr;
     thrv[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
   } else if (is_cnt) {
-    if (out.used_cnt) out.used_cnt[t] = used_val;
-    if (out.calc_cnt) out.calc_cnt[t] = calc_val;
-    if (out.used_present) out.used_present[t] = m_used;
-    if (out.throttled) out.throttled[t] = m_throttled;
-    if (out.calc_present) out.calc_present[t] = m_calc;
-    if (out.override_active) out.override_active[t] = active_found;
     CheckHdr h;
     h.thr_has = m_thr & ~KT_COUNT_BIT;
     h.m2 = m_st & ~KT_COUNT_BIT;
@@ -772,6 +766,21 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
                 ((m_s3 & KT_COUNT_BIT) ? 4u : 0u) | ((m_s4c & KT_COUNT_BIT) ? 8u : 0u);
     if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
     *reinterpret_cast<CheckHdr*>(check + (size_t)t * (16 + 16 * R)) = h;
+  }
+  sync.signal_finalized();
+  if (is_res) {
+    if (out.used) out.used[col] = used_val;
+    if (out.calc_thr) out.calc_thr[col] = calc_val;
+    px.zero[col] = 0ull;
+    px.zero[(size_t)(R + r) * M + t] = 0ull;
+  } else if (is_cnt) {
+    if (out.used_cnt) out.used_cnt[t] = used_val;
+    if (out.calc_cnt) out.calc_cnt[t] = calc_val;
+    if (out.used_present) out.used_present[t] = m_used;
+    if (out.throttled) out.throttled[t] = m_throttled;
+    if (out.calc_present) out.calc_present[t] = m_calc;
+    if (out.override_active) out.override_active[t] = active_found;
+    px.zero[(size_t)2 * R * M + t] = 0ull;
   }
   stamp(7);
 }
@@ -1037,7 +1046,6 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(c
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
     finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
-    cta_signal(&a.sync->fin_done);
   } else {
     check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
   }

@@ -214,6 +214,39 @@ def test_admit_queue_equals_one_pod_per_cycle(oracle, seed):
     dut.close()
 
 
+def test_engine_limits_grow(oracle):
+    """More label slots / resource columns / namespace labels than the engine was created with: the host layer re-creates
+    the engine with larger limits and re-uploads its caches; decisions stay identical to the oracle's."""
+    from kube_throttler_b200 import host
+    from test_scenarios import pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("default"), throttle("default", "t", {"a": "1"}, pod_cnt=3, cpu="1"))
+    both(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    assert norm_status(ref.status("t", "default")) == norm_status(dut.status("t", "default"))
+    # 11 labels (> 8 slots), 6 resource names (> 4 columns), a namespace with 6 labels (> 4 slots)
+    many = {f"k{i}": "v" for i in range(10)}
+    many["a"] = "1"
+    big = pod("default", "p1", "200m", many, node="n", phase="Running",
+              requests={"memory": "1Gi", "nvidia.com/gpu": "1", "ephemeral-storage": "10Gi", "example.com/foo": "2", "hugepages-2Mi": "4Mi"})
+    both(big, namespace("wide", {f"l{i}": "x" for i in range(5)}),
+         {"kind": "ClusterThrottle", "metadata": {"name": "c"}, "spec": {"throttlerName": THROTTLER, "threshold": {"resourceRequests": {"example.com/foo": "3", "memory": "1536Mi"}},
+                                                                       "selector": {"selectorTerms": [{"podSelector": {"matchLabels": {"k9": "v"}}, "namespaceSelector": {}}]}}})
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    for name, ns in (("t", "default"), ("c", "")):
+        assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns))
+    assert rl_values_of(dut.status("c")["used"]) == {"cpu": Fraction(1, 5), "memory": 2**30, "nvidia.com/gpu": 1, "ephemeral-storage": 10 * 2**30, "example.com/foo": 2, "hugepages-2Mi": 4 * 2**20}
+    for p in (pod("default", "q0", "100m", many, requests={"example.com/foo": "2"}), pod("default", "q1", "600m", {"a": "1"}), pod("wide", "q2", "1", many, requests={"memory": "600Mi"})):
+        assert norm_prefilter(ref.prefilter(p)) == norm_prefilter(dut.prefilter(p))
+    dut.close()
+
+
+def rl_values_of(amount):
+    return {k: q(v) for k, v in amount.get("resourceRequests", {}).items()}
+
+
 def test_delete_events(oracle):
     """Pod and throttle deletes (informer DeleteFunc): the row becomes a tombstone and is reused; used sums follow."""
     from kube_throttler_b200 import host

@@ -256,19 +256,23 @@ __device__ __forceinline__ uint32_t rows_touch(const PodRows<REG>& r) {
 // Translate eight label slots (one chunk) of a pod row.  No predicates: the device label columns are
 // padded to a multiple of eight slots with KT_LABEL_EMPTY, keydir has a sentinel entry at [n_keydir]
 // and valrow a sentinel at [0], so every load is unconditional and the addresses are one IMAD.WIDE each.
-__device__ __forceinline__ void translate8(const TableView& tb, const int64_t* __restrict__ lp, int64_t n, uint32_t (&out)[8]) {
-  int64_t lab[8];
+__device__ __forceinline__ void load_labels8(const int64_t* __restrict__ lp, int64_t n, int64_t (&lab)[8]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     lab[k] = __ldg(lp);
     lp += n;
   }
-  uint4 ke[8];
+}
+// first hop: the key directory entries {other roff, vmin, vcnt, off (~0: hashed values)}
+__device__ __forceinline__ void translate8_keys(const TableView& tb, const int64_t (&lab)[8], uint4 (&ke)[8]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t key = (uint32_t)((uint64_t)lab[k] >> 32);
-    ke[k] = __ldg(&tb.keydir[min(key, tb.n_keydir)]);  // {other roff | hashed flag in w, vmin, vcnt, off}
+    ke[k] = __ldg(&tb.keydir[min(key, tb.n_keydir)]);
   }
+}
+// second hop: the value rows, then the (rare, serial) hashed fallback for sparse dictionary ids
+__device__ __forceinline__ void translate8_rows(const TableView& tb, const int64_t (&lab)[8], const uint4 (&ke)[8], uint32_t (&out)[8]) {
   uint32_t vr[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -281,7 +285,7 @@ __device__ __forceinline__ void translate8(const TableView& tb, const int64_t* _
     out[k] = vr[k] != kOtherRoff ? vr[k] : ke[k].x;
     hashed |= ke[k].w;
   }
-  if (tb.n_keydir == 0 || (hashed >> 31)) {  // offsets never reach 2^31; the hashed flag is w = ~0  // sparse dictionary ids: rare, serial
+  if (tb.n_keydir == 0 || (hashed >> 31)) {  // offsets never reach 2^31; the hashed flag is off = ~0
     const uint32_t row_bytes = (uint32_t)tb.TPpad * 8u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -290,6 +294,13 @@ __device__ __forceinline__ void translate8(const TableView& tb, const int64_t* _
         out[k] = (uint32_t)hash_lookup(tb.hash, tb.hash_mask, tb.rows - 1, key, val) * row_bytes;
     }
   }
+}
+__device__ __forceinline__ void translate8(const TableView& tb, const int64_t* __restrict__ lp, int64_t n, uint32_t (&out)[8]) {
+  int64_t lab[8];
+  uint4 ke[8];
+  load_labels8(lp, n, lab);
+  translate8_keys(tb, lab, ke);
+  translate8_rows(tb, lab, ke, out);
 }
 
 // labels: device columns [Lpad][n] with Lpad = L rounded up to 8.
@@ -429,23 +440,26 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
-  // ---- all of the pod row's loads are issued before anything waits on them ----
+  // ---- all of the pod row's loads are issued before anything waits on them; the two dependent chains that follow
+  // (labels -> key directory -> value rows, namespace -> word-list offsets -> word indices) are interleaved hop by hop
+  // so that their L2 latencies overlap instead of adding up ----
   const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
   const int ns = __ldg(&pods.ns[pc]);
   const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-  {  // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
+  int64_t lab[8];
+  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+  long long rq[RT > 0 ? RT : 1];
+  if constexpr (RT > 0) {
     const int64_t* rp = pods.req + pc;
-    for (int r = 0; r < R; ++r) {
-      const long long v = __ldg(rp);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      rq[r] = r < R ? __ldg(rp) : 0;
       rp += pods.n;
-      s_req[r * TILE + tid] = ((present >> r) & 1) ? v : 0;
     }
-    s_present[tid] = present & ~KT_COUNT_BIT;
   }
-  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
-  {  // zero the tile's bitmap rows (contiguous: pod-major) and the CTA accumulators
+  {  // zero the tile's bitmap rows (contiguous: pod-major) and the CTA accumulators while the loads are in flight
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* dst = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
     const int nvec = (int)rows_here * (Wp / 4);
@@ -459,8 +473,27 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
                        (unsigned)ns < (unsigned)tb.NS;
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
   int j = 0, hi = 0;
-  if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }  // hop 1 of the word list
+  uint4 ke[8];
+  if constexpr (REG) translate8_keys(tb, lab, ke);                                // hop 1 of the labels
+  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;                          // hop 2 of the word list
+  int nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;                  // (the word after it is fetched one step ahead)
+  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);                      // hop 2 of the labels
+  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+  // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
+  if constexpr (RT > 0) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+      if (r < R) s_req[r * TILE + tid] = ((present >> r) & 1) ? rq[r] : 0;
+  } else {
+    const int64_t* rp = pods.req + pc;
+    for (int r = 0; r < R; ++r) {
+      const long long v = __ldg(rp);
+      rp += pods.n;
+      s_req[r * TILE + tid] = ((present >> r) & 1) ? v : 0;
+    }
+  }
+  s_present[tid] = present & ~KT_COUNT_BIT;
   if (trace_row && threadIdx.x == 0 && (rows_touch(rows) | (uint32_t)cur) == 0x12345u) trace_row[4] = 1;  // forces the loads to have landed
   stamp(4);
   __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
@@ -481,7 +514,8 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
       if (word) bitmap[p * Wp + w] = word;
       ++j;
-      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+      cur = nxt;
+      nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;
     }
     const uint32_t aword = alive ? word : 0u;
     if (!__any_sync(kFull, aword != 0u)) continue;
@@ -825,7 +859,8 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-  stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+  int64_t lab[8];
+  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
   {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
@@ -834,12 +869,19 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
     for (int i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
+  // the two dependent chains (labels -> key directory -> value rows, namespace -> offsets -> word indices) hop by hop
   int lo = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+  uint4 ke[8];
+  if constexpr (REG) translate8_keys(tb, lab, ke);
+  int wcur = lo < hi ? __ldg(&tb.nsw_idx[lo]) : 0;
+  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);
+  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
-    const int w = __ldg(&tb.nsw_idx[j]);
+    const int w = wcur;
+    if (j + 1 < hi) wcur = __ldg(&tb.nsw_idx[j + 1]);  // one step ahead of its use
     const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
     if (word) bitmap[p * Wp + w] = word;
   }
@@ -1026,7 +1068,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
   unsigned long long t_start = 0;

@@ -266,6 +266,15 @@ int kt_get_match_rows(kt_ctx* ctx, int kind, int64_t k, const int64_t* rows, uin
 int kt_get_check(kt_ctx* ctx, uint32_t* codes /*[p][2*words_per_row]*/, uint8_t* admit /*[p]*/);
 int kt_get_timing(kt_ctx* ctx, kt_timing* out);
 
+/* ---- host-only introspection (no device needed) -------------------------------- */
+/* Compiles a selector table exactly as kt_upload_throttles does and hands the bit-sliced match tables back, so that the
+ * table compiler can be checked on a machine without a GPU (tests/test_tables_cpu.py evaluates them with numpy).
+ * Every output pointer may be NULL; sizes come back in dims[12] = {M, W, Wp, TPpad, B, rows, NS, n_keydir, n_valrow,
+ * n_nsw, max_ns_words, hash_slots}.  First call with NULL arrays to size them.  The tables are never evaluated here. */
+int kt_debug_compile_tables(const kt_limits* limits, int32_t m, const kt_throttle_cols* cols, const kt_selector_table* sel,
+                            int32_t n_ns, const int64_t* ns_labels, int32_t dims[12], uint32_t* table, uint32_t* need,
+                            uint32_t* nsmask, int32_t* nsw_off, int32_t* nsw_idx, uint32_t* keydir, uint32_t* valrow, uint32_t* hash);
+
 /* ---- multi-GPU (row-sharded snapshot, one context per GPU) --------------------- */
 /* Each context holds a row shard of both pod kinds and a replica of the throttles; the
  * only exchange is one int64 sum all-reduce of the per-throttle partials between the

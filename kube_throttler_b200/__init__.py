@@ -45,7 +45,7 @@ EXPORTS = [
     "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
     "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
-    "kt_comm_init", "kt_comm_destroy",
+    "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
 
@@ -91,6 +91,8 @@ def lib():
         L.kt_comm_unique_id.argtypes = [vp]
         L.kt_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.kt_comm_destroy.argtypes = [vp]
+        L.kt_debug_compile_tables.argtypes = [C.POINTER(abi.Limits), C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable), C.c_int32, vp,
+                                              vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -934,6 +934,25 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   return KT_OK;
 }
 
+int kt_debug_compile_tables(const kt_limits* lim, int32_t m, const kt_throttle_cols* cols, const kt_selector_table* sel, int32_t n_ns,
+                            const int64_t* ns_labels, int32_t dims[12], uint32_t* table, uint32_t* need, uint32_t* nsmask, int32_t* nsw_off,
+                            int32_t* nsw_idx, uint32_t* keydir, uint32_t* valrow, uint32_t* hash) {
+  if (!lim || !dims) return KT_ERR_INVALID;
+  SelectorSpec spec;
+  HostTables ht;
+  if (!copy_selector_spec(m, cols, sel, &spec).empty()) return KT_ERR_INVALID;
+  if (!compile_tables(*lim, spec, n_ns, ns_labels, &ht).empty()) return KT_ERR_INVALID;
+  const int32_t d[12] = {ht.M, ht.W, ht.Wp, ht.TPpad, ht.B, ht.rows, ht.NS, ht.n_keydir, (int32_t)ht.valrow.size(), (int32_t)ht.nsw_idx.size(),
+                         ht.max_ns_words, (int32_t)(ht.hash_mask + 1)};
+  std::memcpy(dims, d, sizeof d);
+  auto put = [](auto* dst, const auto& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  put(table, ht.table); put(need, ht.need); put(nsmask, ht.nsmask); put(nsw_off, ht.nsw_off); put(nsw_idx, ht.nsw_idx);
+  put(keydir, ht.keydir); put(valrow, ht.valrow); put(hash, ht.hash);
+  return KT_OK;
+}
+
 int kt_comm_unique_id(uint8_t uid[128]) {
   if (!uid) return KT_ERR_INVALID;
   if (load_nccl()) return KT_ERR_NCCL;

@@ -279,6 +279,10 @@ int kt_debug_compile_tables(const kt_limits* limits, int32_t m, const kt_throttl
 /* Each context holds a row shard of both pod kinds and a replica of the throttles; the
  * only exchange is one int64 sum all-reduce of the per-throttle partials between the
  * reconcile and finalize kernels.  uid is an ncclUniqueId (128 bytes) created on rank 0. */
+/* With a communicator, kt_evaluate is COLLECTIVE: every rank must call it the same number of times.  The exchange happens
+ * inside the pass (finalize tiles read the peers' partial sums over NVLink from IPC-mapped windows; one ncclAllReduce between
+ * the kernels when the GPUs cannot map each other).  A rank that never arrives does not wedge the others: the in-kernel wait
+ * gives up after two seconds and the next kt_get_* / kt_sync returns KT_ERR_STATE. */
 int kt_comm_unique_id(uint8_t uid[128]);
 int kt_comm_init(kt_ctx* ctx, const uint8_t uid[128], int nranks, int rank);
 int kt_comm_destroy(kt_ctx* ctx);

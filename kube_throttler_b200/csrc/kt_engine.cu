@@ -134,6 +134,7 @@ struct kt_ctx {
   DevBuf d_trace;  // optional per-CTA trace rows of the fused pass
   bool trace = false;
   uint32_t trace_roles[4] = {0, 0, 0, 0};
+  PassSync* last_sync = nullptr;  // counters of the last fused pass: its error flag is checked when results are fetched
   bool fused = true;  // one-launch pass (k_pass) when the whole pass is asked for; three PDL-chained kernels otherwise
   DevBuf d_check;  // [M][16+16R]
   // per-throttle outputs of the reconcile half: ONE device block (and one pinned host mirror) so that kt_get_reconcile
@@ -205,6 +206,20 @@ int recompile_tables(kt_ctx* c) {
   if ((rc = upload_vec(c, c->d_nsw_idx, c->ht.nsw_idx))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors may be rebuilt right after
   return KT_OK;
+}
+
+// After a fused pass has completed: did one of its in-kernel waits give up (a peer rank never arrived)?
+int check_pass_error(kt_ctx* c) {
+  if (!c->last_sync || !c->evaluated) return KT_OK;
+  unsigned err = 0;
+  KT_CUDA(c, cudaMemcpyAsync(&err, &c->last_sync->error, sizeof err, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (!err) return KT_OK;
+  KT_CUDA(c, cudaMemsetAsync(c->last_sync, 0, sizeof(PassSync) - 3 * sizeof(unsigned), c->stream));  // re-arm the counters, keep the epochs
+  KT_CUDA(c, cudaMemsetAsync(&c->last_sync->error, 0, sizeof(unsigned), c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->evaluated = false;
+  return fail(c, KT_ERR_STATE, "the pass timed out waiting for a peer rank (or for its own tiles): results are void");
 }
 
 TableView table_view(const kt_ctx* c) {
@@ -507,7 +522,7 @@ int kt_sync(kt_ctx* c) {
   int rc = set_device(c);
   if (rc) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
-  return KT_OK;
+  return check_pass_error(c);
 }
 
 void* kt_host_alloc(size_t bytes) {
@@ -799,6 +814,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
       c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
     }
     KT_CUDA(c, dispatch_pass(c, a));
+    c->last_sync = (multi && !c->p2p_failed) ? a.sync : nullptr;  // only a pass that waits for OTHER ranks can time out
     c->last = kt_timing{};
     c->last.launches = 1;
     c->evaluated = true;
@@ -867,6 +883,7 @@ int kt_get_reconcile(kt_ctx* c, const kt_reconcile_out* o) {
   if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_reconcile before kt_evaluate");
   int rc = set_device(c);
   if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
   const size_t m = (size_t)c->M, R = (size_t)c->lim.n_resources;
   // one copy of the whole block into the pinned mirror, then plain host copies into the caller's columns
   if (c->out_bytes) KT_CUDA(c, cudaMemcpyAsync(c->h_out, c->d_out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -927,6 +944,7 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check before kt_evaluate");
   int rc = set_device(c);
   if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
   const int64_t P = c->pods[KT_PODS_PENDING].n;
   if (codes && P > 0) KT_CUDA(c, cudaMemcpyAsync(codes, c->d_codes.p, (size_t)P * 2 * c->ht.Wp * 4, cudaMemcpyDeviceToHost, c->stream));
   if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));

@@ -129,7 +129,7 @@ struct PassSync {
   unsigned exited;    // CTAs that are done with everything; the last one re-arms the counters
   unsigned epoch;     // multi-GPU: last pass whose partial sums this rank has published (peers poll it over NVLink)
   unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
-  unsigned pad;
+  unsigned error;        // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
 };
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -148,9 +148,28 @@ __device__ __forceinline__ void cta_signal(unsigned* counter) {
     atomicAdd(counter, 1u);
   }
 }
-__device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target) {
-  if (threadIdx.x == 0)
-    while (ld_acquire_gpu(counter) < target) __nanosleep(40);
+// No wait spins forever: a rank that died (or a bug) must not wedge the GPU.  After kSpinTimeoutNs the waiter records the
+// failure and goes on; the pass's results are then meaningless and the host says so (KT_ERR_STATE).
+constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;
+__device__ __forceinline__ unsigned long long spin_clock_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+template <class Done>
+__device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsigned sleep_ns) {
+  if (done()) return;
+  const unsigned long long t0 = spin_clock_ns();
+  while (!done()) {
+    __nanosleep(sleep_ns);
+    if (spin_clock_ns() - t0 > kSpinTimeoutNs) {
+      *reinterpret_cast<volatile unsigned*>(error_flag) = 1u;
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target, unsigned* error_flag) {
+  if (threadIdx.x == 0) spin_until([&] { return ld_acquire_gpu(counter) >= target; }, error_flag, 40);
   __syncthreads();
 }
 
@@ -182,7 +201,7 @@ struct FlagSync {
   // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
-      while (ld_acquire_gpu(&s->rec_done) < n_rec) __nanosleep(40);
+      spin_until([&] { return ld_acquire_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
       if (px.npeers > 0) {
         if (first_tile) {
           // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
@@ -191,19 +210,19 @@ struct FlagSync {
           *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
           // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
           for (int i = 0; i < px.npeers; ++i)
-            while ((int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) < 0) __nanosleep(20);
+            spin_until([&] { return (int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
           // ... and tell the other finalize tiles of this rank
           __threadfence();
           *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
         } else {
-          while ((int)(ld_acquire_gpu(&px.sync->peers_epoch) - px.epoch) < 0) __nanosleep(40);
+          spin_until([&] { return (int)(ld_acquire_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
         }
       }
     }
     __syncthreads();
   }
-  __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match); }
-  __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin); }
+  __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match, &s->error); }
+  __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin, &s->error); }
   __device__ __forceinline__ void signal_finalized() const { cta_signal(&s->fin_done); }
 };
 

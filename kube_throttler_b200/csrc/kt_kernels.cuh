@@ -158,13 +158,16 @@ __device__ __forceinline__ unsigned long long spin_clock_ns() {
 }
 template <class Done>
 __device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsigned sleep_ns) {
-  if (done()) return;
-  const unsigned long long t0 = spin_clock_ns();
-  while (!done()) {
+  unsigned long long t0 = 0;
+  for (unsigned polls = 0; !done(); ++polls) {
     __nanosleep(sleep_ns);
-    if (spin_clock_ns() - t0 > kSpinTimeoutNs) {
-      *reinterpret_cast<volatile unsigned*>(error_flag) = 1u;
-      return;
+    if ((polls & 255u) == 255u) {  // the clock is only consulted now and then: the common wait is a few polls long
+      const unsigned long long t = spin_clock_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kSpinTimeoutNs) {
+        *reinterpret_cast<volatile unsigned*>(error_flag) = 1u;
+        return;
+      }
     }
   }
 }

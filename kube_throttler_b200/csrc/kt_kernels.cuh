@@ -131,16 +131,21 @@ struct PassSync {
   unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
   unsigned error;        // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
 };
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+// Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as a
+// fence, when the awaited value has been seen.  An acquire LOAD per poll would invalidate the SM's L1 on every iteration
+// (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it.
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void cta_signal(unsigned* counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -172,7 +177,10 @@ __device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsi
   }
 }
 __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target, unsigned* error_flag) {
-  if (threadIdx.x == 0) spin_until([&] { return ld_acquire_gpu(counter) >= target; }, error_flag, 40);
+  if (threadIdx.x == 0) {
+    spin_until([&] { return ld_relaxed_gpu(counter) >= target; }, error_flag, 40);
+    fence_acquire_gpu();
+  }
   __syncthreads();
 }
 
@@ -204,7 +212,8 @@ struct FlagSync {
   // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
-      spin_until([&] { return ld_acquire_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
+      spin_until([&] { return ld_relaxed_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
+      fence_acquire_gpu();
       if (px.npeers > 0) {
         if (first_tile) {
           // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
@@ -213,12 +222,14 @@ struct FlagSync {
           *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
           // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
           for (int i = 0; i < px.npeers; ++i)
-            spin_until([&] { return (int)(ld_acquire_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
+            spin_until([&] { return (int)(ld_relaxed_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
+          fence_acquire_sys();
           // ... and tell the other finalize tiles of this rank
           __threadfence();
           *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
         } else {
-          spin_until([&] { return (int)(ld_acquire_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
+          spin_until([&] { return (int)(ld_relaxed_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
+          fence_acquire_gpu();
         }
       }
     }
@@ -545,12 +556,14 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
     // lane b now owns throttle w*32+b and the set of this warp's pods that matched it.
     uint32_t T = warp_transpose32(aword, lane);
     int slot = -1;
-    if (lane == 0) {
+    if (lane == 0) {  // open addressing from w mod S: one probe in the common case, at most S
+      int s = (int)((unsigned)w % (unsigned)S);
 #pragma unroll 1
-      for (int s = 0; s < S; ++s) {
+      for (int probes = 0; probes < S; ++probes) {
         int k = *reinterpret_cast<volatile int*>(&s_key[s]);
         if (k == -1) k = atomicCAS(&s_key[s], -1, w);
         if (k == -1 || k == w) { slot = s; break; }
+        s = s + 1 == S ? 0 : s + 1;
       }
     }
     slot = __shfl_sync(kFull, slot, 0);

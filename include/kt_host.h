@@ -91,11 +91,20 @@ const char* kth_unreserve(kth_plugin* p, const char* pod_json);
  * {"amount":{...},"pods":["ns/name",...]} -- reserved_resource_amounts.go:113-126. */
 const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn);
 
+/* The controllers' Prometheus gauges in text exposition format (throttle_metrics.go:27-131,
+ * clusterthrottle_metrics.go:27-131, metrics_recorder.go:25-67): throttle_* families labelled {name,namespace,resource,uid},
+ * clusterthrottle_* families labelled {name,resource,uid}; spec threshold / status.throttled / status.used /
+ * status.calculatedThreshold, counts as the pod count (0 when nil), cpu as MilliValue, other resources as Value.  Series are
+ * recorded when kth_reconcile_all handles a throttle and, like a GaugeVec's, are never dropped.  What the Go build would
+ * feed legacyregistry with (or serve next to it). */
+const char* kth_metrics(kth_plugin* p);
+
 /* Host-only helpers of the packer, exposed so that they can be pinned against the reference's unit
  * tests without a GPU: {"fn":"ParseQuantity","value":..} | {"fn":"PodRequestResourceList","pod":{..}} |
  * {"fn":"ResourceAmountOfPod","pod":{..}} | {"fn":"ParseRFC3339","value":..} |
  * {"fn":"OverrideMessages","throttle":{..}} | {"fn":"NextOverrideHappensIn","throttle":{..},"now":..} | {"fn":"ValidateSelector","selector":{..}} |
- * {"fn":"CanonicalQuantity","value":..}.  Never touches a device. */
+ * {"fn":"CanonicalQuantity","value":..} | {"fn":"ThrottleMetrics","throttle":{..spec+status..}} | {"fn":"ScaledValue","value":..,"scale":n} |
+ * {"fn":"FormatFloat","value":..}.  Never touches a device. */
 const char* kth_eval(const char* request_json);
 
 #ifdef __cplusplus

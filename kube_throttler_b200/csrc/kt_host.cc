@@ -8,6 +8,8 @@
 // Nothing in this file decides whether a pod matches a selector or compares a quantity with a threshold:
 // that is the device's job (kt_evaluate); this file packs, calls, and spells the results.
 #include <algorithm>
+#include <charconv>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -270,7 +272,7 @@ struct Term {
 };
 struct ThrottleObj {
   int kind = KT_KIND_THROTTLE;
-  std::string ns, name, throttler_name;
+  std::string ns, name, uid, throttler_name;
   ResAmount threshold;
   std::vector<Override> overrides;
   std::vector<Term> terms;
@@ -796,6 +798,109 @@ struct kth_plugin {
   }
 
   // ---- reconcile: every throttle in one device pass ------------------------------------------------
+  // ---- gauges (throttle_metrics.go / clusterthrottle_metrics.go / metrics_recorder.go) --------------------------
+  // A GaugeVec keeps every series it was ever given: reconcile records the throttle it just handled, nothing is deleted
+  // when a throttle or one of its resource names goes away.  family -> (label pairs sorted by name, rendered) -> value.
+  std::map<std::string, std::map<std::string, double>> gauges;
+  static std::string label_escape(const std::string& v) {
+    std::string o;
+    for (char c : v) {
+      if (c == '\\') o += "\\\\";
+      else if (c == '"') o += "\\\"";
+      else if (c == '\n') o += "\\n";
+      else o += c;
+    }
+    return o;
+  }
+  void record_metrics(const ThrottleObj& o) {
+    const bool cluster = o.kind == KT_KIND_CLUSTERTHROTTLE;
+    const std::string prefix = cluster ? "clusterthrottle_" : "throttle_";
+    auto series = [&](const std::string& resource) {  // client_golang sorts the label pairs by name
+      std::string l = "name=\"" + label_escape(o.name) + "\"";
+      if (!cluster) l += ",namespace=\"" + label_escape(o.ns) + "\"";
+      l += ",resource=\"" + label_escape(resource) + "\",uid=\"" + label_escape(o.uid) + "\"";
+      return l;
+    };
+    auto counts = [&](const std::string& fam, bool has, long long pod) {  // recordResourceCounts: nil -> 0
+      gauges[prefix + fam][series("pod")] = has ? (double)pod : 0.0;
+    };
+    auto requests = [&](const std::string& fam, const ResAmount& a) {  // recordResourceRequests: cpu in milli, the rest in units
+      for (auto& kv : a.requests) {
+        const std::string& rn = cols[(size_t)kv.first].name;
+        gauges[prefix + fam][series(rn)] = (double)kt::quantity_scaled_value(kv.second, rn == "cpu" ? -3 : 0);
+      }
+    };
+    counts("spec_threshold_resourceCounts", o.threshold.has_counts, o.threshold.pod);
+    requests("spec_threshold_resourceRequests", o.threshold);
+    gauges[prefix + "status_throttled_resourceCounts"][series("pod")] = o.st_thr_pod ? 1.0 : 0.0;
+    if (!o.st_thr_req_nil)
+      for (auto& kv : o.st_thr_req) gauges[prefix + "status_throttled_resourceRequests"][series(cols[(size_t)kv.first].name)] = kv.second ? 1.0 : 0.0;
+    counts("status_used_resourceCounts", o.st_used.has_counts, o.st_used.pod);
+    requests("status_used_resourceRequests", o.st_used);
+    counts("status_calculated_threshold_resourceCounts", o.st_calc.has_counts, o.st_calc.pod);
+    requests("status_calculated_threshold_resourceRequests", o.st_calc);
+  }
+  // expfmt's writeFloat: shortcuts for 0, 1 and -1, else strconv.AppendFloat(f, 'g', -1, 64) -- the shortest digits that
+  // round-trip, in %e form when the decimal exponent is < -4 or >= 6 (Go's 'g' decides with precision 6 in shortest mode,
+  // so 1000000 prints as 1e+06 and 536870912 as 5.36870912e+08), else in %f form with no padding.
+  static std::string go_float(double f) {
+    if (f == 0) return "0";
+    if (f == 1) return "1";
+    if (f == -1) return "-1";
+    if (f != f) return "NaN";
+    if (f > 1.7976931348623157e308) return "+Inf";
+    if (f < -1.7976931348623157e308) return "-Inf";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);  // shortest round-trip digits, d.ddde[+-]XX
+    std::string sci(buf, r.ptr);
+    const size_t epos = sci.find('e');
+    std::string mant = sci.substr(0, epos);
+    const int exp = std::atoi(sci.c_str() + epos + 1);
+    const bool neg = mant[0] == '-';
+    if (neg) mant.erase(0, 1);
+    std::string digits;
+    for (char c : mant)
+      if (c != '.') digits += c;
+    std::string out = neg ? "-" : "";
+    if (exp < -4 || exp >= 6) {  // %e with the shortest digits and an exponent of at least two digits
+      out += digits.substr(0, 1);
+      if (digits.size() > 1) out += "." + digits.substr(1);
+      out += exp < 0 ? "e-" : "e+";
+      const int a = exp < 0 ? -exp : exp;
+      if (a < 10) out += "0";
+      out += std::to_string(a);
+      return out;
+    }
+    if (exp >= 0) {  // %f with just the digits needed
+      if ((int)digits.size() <= exp + 1) return out + digits + std::string((size_t)(exp + 1) - digits.size(), '0');
+      return out + digits.substr(0, (size_t)exp + 1) + "." + digits.substr((size_t)exp + 1);
+    }
+    return out + "0." + std::string((size_t)(-exp - 1), '0') + digits;
+  }
+  std::string metrics_text() const {
+    static const std::pair<const char*, const char*> kHelp[] = {
+        {"spec_threshold_resourceCounts", "threshold on specific resourceCounts of the %s"},
+        {"spec_threshold_resourceRequests", "threshold on specific resourceRequests of the %s"},
+        {"status_calculated_threshold_resourceCounts", "calculated threshold on specific resourceCounts of the %s"},
+        {"status_calculated_threshold_resourceRequests", "calculated threshold on specific resourceRequests of the %s"},
+        {"status_throttled_resourceCounts", "resourceCounts of the %s is throttled or not on specific resource (1=throttled, 0=not throttled)"},
+        {"status_throttled_resourceRequests", "resourceRequests of the %s is throttled or not on specific resource (1=throttled, 0=not throttled)"},
+        {"status_used_resourceCounts", "used resource counts of the %s"},
+        {"status_used_resourceRequests", "used amount of resource requests of the %s"},
+    };
+    std::string out;
+    for (const char* prefix : {"clusterthrottle_", "throttle_"})  // families in name order, as Gather returns them
+      for (auto& h : kHelp) {
+        auto it = gauges.find(std::string(prefix) + h.first);
+        if (it == gauges.end() || it->second.empty()) continue;
+        std::string help = h.second;
+        help.replace(help.find("%s"), 2, "throttle");  // both recorders say "throttle" (clusterthrottle_metrics.go:44-100)
+        out += "# HELP " + it->first + " " + help + "\n# TYPE " + it->first + " gauge\n";
+        for (auto& sv : it->second) out += it->first + "{" + sv.first + "} " + go_float(sv.second) + "\n";
+      }
+    return out;
+  }
+
   std::string reconcile_all(const std::string& now_s) {
     GoTime now;
     std::string e = parse_rfc3339(now_s, &now);
@@ -871,6 +976,7 @@ struct kth_plugin {
       o.st_thr_req_nil = thr_nil;
       if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
       o.st_used = nu;
+      record_metrics(o);  // both branches of the status comparison record (throttle_controller.go:159,187)
       if (status_changed) changed.push_back(o.nn());
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
@@ -1184,6 +1290,7 @@ struct kth_plugin {
     const Node& md = v["metadata"];
     o.ns = kind == KT_KIND_THROTTLE ? md["namespace"].str() : "";
     o.name = md["name"].str();
+    o.uid = md["uid"].str();
     const Node& spec = v["spec"];
     o.throttler_name = spec["throttlerName"].str();
     o.threshold = res_amount(spec["threshold"]);
@@ -1367,6 +1474,20 @@ std::string eval_request(const Node& req) {
     w.begin_obj().key("have").boolean(have).key("nanos").num((long long)d).end_obj();
     return w.out;
   }
+  if (fn == "ThrottleMetrics") {  // recordThrottleMetrics / recordClusterThrottleMetrics of one manifest (spec + status)
+    scratch.apply_throttle(req["throttle"], req["throttle"]["kind"].str("Throttle") == "ClusterThrottle" ? KT_KIND_CLUSTERTHROTTLE : KT_KIND_THROTTLE);
+    scratch.record_metrics(scratch.throttles[0]);
+    w.begin_obj().key("text").str(scratch.metrics_text()).end_obj();
+    return w.out;
+  }
+  if (fn == "FormatFloat") {
+    w.begin_obj().key("text").str(kth_plugin::go_float(std::strtod(req["value"].scalar().c_str(), nullptr))).end_obj();
+    return w.out;
+  }
+  if (fn == "ScaledValue") {
+    w.begin_obj().key("value").num((long long)kt::quantity_scaled_value(kt::parse_quantity(req["value"].scalar()), (int)req["scale"].integer(0))).end_obj();
+    return w.out;
+  }
   if (fn == "ValidateSelector") {
     const CompiledSelector c = compile_selector(req["selector"]);
     w.begin_obj().key("valid").boolean(c.error.empty());
@@ -1482,6 +1603,9 @@ const char* kth_unreserve(kth_plugin* p, const char* pod_json) {
 }
 const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn) {
   return guarded(p, [&]() { return p->reserved_json(kind, throttle_nn ? throttle_nn : ""); });
+}
+const char* kth_metrics(kth_plugin* p) {
+  return guarded(p, [&]() -> std::string { return p->metrics_text(); });
 }
 const char* kth_eval(const char* request_json) {
   try {

@@ -195,6 +195,31 @@ inline int64_t quantity_at_scale(const Quantity& q, int scale_exp, bool* ok) {
   return (int64_t)v;
 }
 
+// Quantity.ScaledValue(scale) (MilliValue = scale -3, Value = scale 0): the value in units of 10^scale, rounded AWAY from
+// zero when it is not a whole number of them (apimachinery amount.go "rounding up"); saturates at the int64 range, where the
+// reference's result is unspecified.
+inline int64_t quantity_scaled_value(const Quantity& q, int scale) {
+  if (q.is_zero()) return 0;
+  const int up = q.exp - scale;
+  i128 v = q.mant;
+  if (up >= 0) {
+    for (int i = 0; i < up; ++i) {
+      if (v > ((i128)INT64_MAX) || v < -((i128)INT64_MAX)) break;  // already beyond int64: saturates below
+      v *= 10;
+    }
+  } else {
+    bool inexact = false;
+    for (int i = 0; i < -up && v != 0; ++i) {
+      if (v % 10 != 0) inexact = true;
+      v /= 10;
+    }
+    if (inexact || (v == 0 && q.mant != 0)) v += q.mant > 0 ? 1 : -1;
+  }
+  if (v > (i128)INT64_MAX) return INT64_MAX;
+  if (v < (i128)INT64_MIN) return INT64_MIN;
+  return (int64_t)v;
+}
+
 // Plain decimal spelling of v * 10^scale_exp ("0.5", "1", "536870912"): what the status JSON carries.
 inline std::string decimal_string(i128 v, int scale_exp) {
   const bool neg = v < 0;

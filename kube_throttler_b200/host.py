@@ -25,7 +25,7 @@ def _bind():
     L.kth_free.restype = None
     for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_reconcile_all", [vp, cp]),
                        ("kth_get_status", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
-                       ("kth_admit_queue", [vp, cp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_eval", [cp])):
+                       ("kth_admit_queue", [vp, cp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_metrics", [vp]), ("kth_eval", [cp])):
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = cp
@@ -34,7 +34,7 @@ def _bind():
 
 
 HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status",
-                "kth_pre_filter", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_eval"]
+                "kth_pre_filter", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
 
 
 def _result(raw):
@@ -103,6 +103,13 @@ class Plugin:
 
     def unreserve(self, pod):
         return _result(self._L.kth_unreserve(self._h, json.dumps(pod).encode()))
+
+    def metrics(self) -> str:
+        """The controllers' gauges as Prometheus text exposition (throttle_metrics.go, clusterthrottle_metrics.go)."""
+        text = self._L.kth_metrics(self._h).decode()
+        if text.startswith('{"error"'):
+            raise RuntimeError(json.loads(text)["error"])
+        return text
 
     def reserved(self, kind: str, thr_nn: str):
         return _result(self._L.kth_reserved(self._h, 0 if kind == "Throttle" else 1, thr_nn.encode()))

@@ -126,3 +126,72 @@ def test_new_plugin_needs_a_gpu_or_fails(host, kt):
         with pytest.raises(kt.KtError) as e:
             host.Plugin()
         assert e.value.code == kt.abi.ERR_CUDA
+
+
+# ---- gauges (throttle_metrics.go, clusterthrottle_metrics.go, metrics_recorder.go) ----------------------------------------
+# The reference has no test for its recorders (parity unpinned by reference vectors); these pin the recorder's rules as
+# the code states them -- counts nil -> 0, cpu as MilliValue, other resources as Value (both round up), label sets, family
+# names -- and Go's float spelling ('g', shortest) that the Prometheus text format uses.
+
+@pytest.mark.parametrize("value,text", [
+    ("0", "0"), ("1", "1"), ("-1", "-1"), ("2", "2"), ("200", "200"), ("999999", "999999"), ("1000000", "1e+06"), ("1234567", "1.234567e+06"),
+    ("536870912", "5.36870912e+08"), ("1073741824", "1.073741824e+09"), ("1.5", "1.5"), ("0.0001", "0.0001"), ("0.00001", "1e-05"),
+    ("-2.5", "-2.5"), ("1e21", "1e+21"), ("9007199254740993", "9.007199254740992e+15"),
+])
+def test_gauge_value_spelling(host, value, text):
+    assert host.eval_host("FormatFloat", value=value)["text"] == text
+
+
+@pytest.mark.parametrize("q,scale,want", [
+    ("500m", -3, 500), ("1", -3, 1000), ("1.1", -3, 1100), ("100n", -3, 1), ("0.0001", -3, 1), ("512Mi", 0, 536870912), ("1500m", 0, 2),
+    ("0.5", 0, 1), ("-1500m", 0, -2), ("0", 0, 0), ("3", 0, 3), ("1Ei", 0, 2**60),
+])
+def test_scaled_value_rounds_up(host, q, scale, want):
+    """Quantity.MilliValue / Value = ScaledValue(-3 / 0): rounded away from zero (apimachinery v0.26.4 amount.go)."""
+    assert host.eval_host("ScaledValue", value=q, scale=scale)["value"] == want
+
+
+def _series(text):
+    out = {}
+    for line in text.splitlines():
+        if line and not line.startswith("#"):
+            k, v = line.rsplit(" ", 1)
+            out[k] = v
+    return out
+
+
+def test_throttle_metrics_of_one_object(host):
+    thr = {"kind": "Throttle", "metadata": {"name": "t1", "namespace": "default", "uid": "u-1"},
+           "spec": {"throttlerName": "kube-throttler", "threshold": {"resourceCounts": {"pod": 5}, "resourceRequests": {"cpu": "200m", "memory": "1Gi"}}},
+           "status": {"calculatedThreshold": {"threshold": {"resourceRequests": {"cpu": "700m"}}, "calculatedAt": "2026-01-01T00:00:00Z"},
+                      "throttled": {"resourceCounts": {"pod": False}, "resourceRequests": {"cpu": True}},
+                      "used": {"resourceCounts": {"pod": 3}, "resourceRequests": {"cpu": "1500m", "memory": "512Mi", "example.com/dongle": "2500m"}}}}
+    text = host.eval_host("ThrottleMetrics", throttle=thr)["text"]
+    s = _series(text)
+    lab = lambda r: '{name="t1",namespace="default",resource="%s",uid="u-1"}' % r  # noqa: E731  (label pairs sorted by name)
+    assert s["throttle_spec_threshold_resourceCounts" + lab("pod")] == "5"
+    assert s["throttle_spec_threshold_resourceRequests" + lab("cpu")] == "200"            # MilliValue
+    assert s["throttle_spec_threshold_resourceRequests" + lab("memory")] == "1.073741824e+09"
+    assert s["throttle_status_calculated_threshold_resourceCounts" + lab("pod")] == "0"    # nil counts record 0
+    assert s["throttle_status_calculated_threshold_resourceRequests" + lab("cpu")] == "700"
+    assert "throttle_status_calculated_threshold_resourceRequests" + lab("memory") not in s
+    assert s["throttle_status_throttled_resourceCounts" + lab("pod")] == "0"
+    assert s["throttle_status_throttled_resourceRequests" + lab("cpu")] == "1"
+    assert s["throttle_status_used_resourceCounts" + lab("pod")] == "3"
+    assert s["throttle_status_used_resourceRequests" + lab("cpu")] == "1500"
+    assert s["throttle_status_used_resourceRequests" + lab("memory")] == "5.36870912e+08"
+    assert s["throttle_status_used_resourceRequests" + lab("example.com/dongle")] == "3"  # Value() rounds 2.5 up
+    assert "# TYPE throttle_status_used_resourceRequests gauge" in text
+    assert "# HELP throttle_status_used_resourceCounts used resource counts of the throttle" in text
+    fams = [l.split()[2] for l in text.splitlines() if l.startswith("# TYPE")]
+    assert fams == sorted(fams) and len(fams) == 8
+
+
+def test_clusterthrottle_metrics_have_no_namespace_label(host):
+    thr = {"kind": "ClusterThrottle", "metadata": {"name": 'c"1', "uid": "u-2"},
+           "spec": {"throttlerName": "kube-throttler", "threshold": {"resourceRequests": {"nvidia.com/gpu": "8"}}}}
+    s = _series(host.eval_host("ThrottleMetrics", throttle=thr)["text"])
+    assert s['clusterthrottle_spec_threshold_resourceRequests{name="c\\"1",resource="nvidia.com/gpu",uid="u-2"}'] == "8"
+    assert s['clusterthrottle_spec_threshold_resourceCounts{name="c\\"1",resource="pod",uid="u-2"}'] == "0"
+    assert not any(k.startswith("throttle_") for k in s)
+    assert not any("resourceRequests" in k and "status" in k for k in s)  # nil maps record nothing

@@ -289,3 +289,41 @@ def test_column_scale_refinement():
     r = w.prefilter(pod("default", "y", "899900000n", {"a": "1"}))
     assert r["reasons"] == ["throttle[insufficient]=default/t"]
     w.close()
+
+
+def test_gauges_follow_reconcile():
+    """kth_metrics: series are recorded by reconcile (throttle_controller.go:159,187), only for reconciled (responsible)
+    throttles, and stay after the throttle is deleted (a GaugeVec never drops a series)."""
+    from kube_throttler_b200 import host
+    from test_scenarios import clthrottle, pod, throttle
+
+    w = host.Plugin(THROTTLER, SCHED)
+    t = throttle("default", "t", {"a": "1"}, pod_cnt=2, cpu="1")
+    t["metadata"]["uid"] = "uid-t"
+    w.apply(namespace("default"), t, throttle("default", "other", {"a": "1"}, cpu="1", throttler="someone-else"),
+            clthrottle("c", {"kubernetes.io/metadata.name": "default"}, {"a": "1"}, cpu="250m"))
+    assert w.metrics() == ""  # nothing reconciled yet
+    for i in range(3):
+        w.apply(pod("default", f"p{i}", "100m", {"a": "1"}, node="n", phase="Running"))
+    w.reconcile_all(NOW)
+    s = {}
+    for line in w.metrics().splitlines():
+        if not line.startswith("#"):
+            k, v = line.rsplit(" ", 1)
+            s[k] = v
+    lt = '{name="t",namespace="default",resource="%s",uid="uid-t"}'
+    assert s["throttle_status_used_resourceCounts" + lt % "pod"] == "3"
+    assert s["throttle_status_used_resourceRequests" + lt % "cpu"] == "300"
+    assert s["throttle_status_throttled_resourceCounts" + lt % "pod"] == "1"
+    assert s["throttle_status_throttled_resourceRequests" + lt % "cpu"] == "0"
+    assert s["throttle_status_calculated_threshold_resourceRequests" + lt % "cpu"] == "1000"
+    assert s["throttle_spec_threshold_resourceCounts" + lt % "pod"] == "2"
+    lc = '{name="c",resource="%s",uid=""}'
+    assert s["clusterthrottle_status_used_resourceRequests" + lc % "cpu"] == "300"
+    assert s["clusterthrottle_status_throttled_resourceRequests" + lc % "cpu"] == "1"
+    assert s["clusterthrottle_spec_threshold_resourceCounts" + lc % "pod"] == "0"
+    assert not any('name="other"' in k for k in s)  # not ours: never enqueued, never recorded
+    w.delete("Throttle", "t", "default")
+    w.reconcile_all(NOW)
+    assert "throttle_status_used_resourceCounts" + lt % "pod" in w.metrics()
+    w.close()

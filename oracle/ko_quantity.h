@@ -80,7 +80,8 @@ inline Quantity ParseQuantity(const std::string& str) {
     while (pos < end && str[pos] >= '0' && str[pos] <= '9') ++pos;
     denom = str.substr(ds, pos - ds);
   }
-  if (num.empty() && denom.empty()) throw QuantityError("quantities must match the regular expression: " + str);
+  // parseQuantityString turns an empty numerator into "0" and accepts an empty denominator ("1." and "." are both legal,
+  // see its "we currently allow 1.G" note): ".", "-" and "+" are all zero.
   std::string suffix = str.substr(pos);
 
   int base = 10, exponent = 0;

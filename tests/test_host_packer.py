@@ -195,3 +195,22 @@ def test_clusterthrottle_metrics_have_no_namespace_label(host):
     assert s['clusterthrottle_spec_threshold_resourceCounts{name="c\\"1",resource="pod",uid="u-2"}'] == "0"
     assert not any(k.startswith("throttle_") for k in s)
     assert not any("resourceRequests" in k and "status" in k for k in s)  # nil maps record nothing
+
+
+@pytest.mark.parametrize("s,want", [
+    (".", 0), ("-", 0), ("+", 0), ("-.", 0), (".m", 0), (".Ki", 0), ("m", 0), ("Ki", 0), ("e3", 0), ("00", 0), ("0.0", 0), ("-0", 0),
+    ("000.500", Fraction(1, 2)), ("1.", 1), ("1.G", 10**9), ("5.m", Fraction(1, 200)), ("1E", 10**18), ("12E", 12 * 10**18), ("+1e3", 1000),
+])
+def test_degenerate_quantity_spellings(host, oracle, s, want):
+    """parseQuantityString (apimachinery v0.26.4 quantity.go) replaces an empty numerator by "0" and allows an empty
+    denominator ("we currently allow 1.G"), so these all parse.  Product and oracle, written independently, agree."""
+    assert Fraction(host.eval_host("ParseQuantity", value=s)["decimal"]) == want
+    assert Fraction(oracle.call("ParseQuantity", value=s)["decimal"]) == want
+
+
+@pytest.mark.parametrize("s", ["1Ee", "1ee3", "1e3e", "1.5.5", "..", "1,5", "1 m", "0x10"])
+def test_malformed_quantities_rejected_by_both(host, oracle, s):
+    with pytest.raises(RuntimeError):
+        host.eval_host("ParseQuantity", value=s)
+    with pytest.raises(RuntimeError):
+        oracle.call("ParseQuantity", value=s)

@@ -255,7 +255,7 @@ def test_parse_quantity(oracle, s, want):
     assert Fraction(oracle.call("ParseQuantity", value=s)["decimal"]) == want
 
 
-@pytest.mark.parametrize("s", ["", "abc", "1x", "1Kii", "--1", "1e", "1e1.5", "."])
+@pytest.mark.parametrize("s", ["", "abc", "1x", "1Kii", "--1", "1e", "1e1.5", "..", "1.5.5", "1,5"])
 def test_parse_quantity_errors(oracle, s):
     with pytest.raises(RuntimeError):
         oracle.call("ParseQuantity", value=s)

@@ -120,7 +120,7 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 // Tiles are handed out by a ticket counter, reconcile tiles first, then finalize, then check tiles: a CTA that
 // waits on a counter can only be waiting for tiles with SMALLER tickets, which are already running on some SM,
 // so the waits cannot deadlock whatever the residency.  Signals are fence + relaxed add (release pattern) by
-// thread 0 after a CTA barrier; waits are acquire loads by thread 0 followed by a CTA barrier.
+// thread 0 after a CTA barrier; waits are relaxed polls + one acquire fence by thread 0 followed by a CTA barrier.
 struct PassSync {
   unsigned ticket;    // next tile
   unsigned rec_done;  // reconcile tiles finished (their REDs are performed at L2)

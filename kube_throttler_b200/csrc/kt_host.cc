@@ -469,11 +469,11 @@ struct kth_plugin {
   }
   bool should_count_in(const PodObj& p) const { return p.scheduler_name == target_scheduler && !p.node_name.empty(); }
 
-  int32_t ns_id(const std::string& name) {
-    const uint32_t id = ns_dict.id(name);
+  int32_t ns_id(const std::string& ns_name) {
+    const uint32_t id = ns_dict.id(ns_name);
     if (namespaces.size() <= id) {
       namespaces.resize(id + 1);
-      namespaces[id].name = name;
+      namespaces[id].name = ns_name;
       namespaces_dirty = throttles_dirty = true;  // Throttle namespace equality is part of the compiled tables
     }
     return (int32_t)id;

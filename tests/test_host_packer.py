@@ -214,3 +214,54 @@ def test_malformed_quantities_rejected_by_both(host, oracle, s):
         host.eval_host("ParseQuantity", value=s)
     with pytest.raises(RuntimeError):
         oracle.call("ParseQuantity", value=s)
+
+
+# ---- randomised differential checks: the product's packer and the oracle were written independently ----------------------
+
+def _rand_quantity(rng):
+    kind = rng.random()
+    if kind < 0.35:
+        s = str(rng.randrange(0, 5000)) + rng.choice(["", "m", "m", "k", "Ki", "Mi", "Gi", "M", "G", "u", "n"])
+    elif kind < 0.7:
+        s = f"{rng.randrange(0, 400)}.{rng.randrange(0, 10 ** rng.randrange(1, 5)):0{rng.randrange(1, 5)}d}" + rng.choice(["", "", "m", "Ki", "Mi", "Gi", "k"])
+    elif kind < 0.85:
+        s = f"{rng.randrange(1, 999)}e{rng.randrange(-6, 7)}"
+    else:
+        s = rng.choice(["0", "00", "0.0", ".5", "5.", "1e0", "+3", "-2", "-1500m", "100n", "1n", "0.0000000004", "1.0000000005", "15Ei", "8191Pi"])
+    return s
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_quantities_agree_with_the_oracle(host, oracle, seed):
+    import random
+
+    rng = random.Random(1000 + seed)
+    for _ in range(250):
+        s = _rand_quantity(rng)
+        a, b = host.eval_host("ParseQuantity", value=s), oracle.call("ParseQuantity", value=s)
+        assert Fraction(a["decimal"]) == Fraction(b["decimal"]), s
+        assert a["format"] == b["format"], s
+        canon = host.eval_host("CanonicalQuantity", value=s)["canonical"]  # re-parsing the canonical spelling gives the value back
+        assert Fraction(host.eval_host("ParseQuantity", value=canon)["decimal"]) == Fraction(a["decimal"]), (s, canon)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_pods_request_lists_agree_with_the_oracle(host, oracle, seed):
+    """PodRequestResourceList over random container / initContainer / overhead shapes (resourcelist.go:27-46)."""
+    import random
+
+    rng = random.Random(2000 + seed)
+    names = ["cpu", "memory", "nvidia.com/gpu", "ephemeral-storage", "example.com/x"]
+
+    def reqs():
+        return {n: _rand_quantity(rng).lstrip("-") or "0" for n in rng.sample(names, rng.randrange(0, 4))}
+
+    for _ in range(60):
+        spec = {"containers": [{"name": f"c{i}", "resources": {"requests": reqs()}} for i in range(rng.randrange(0, 4))]}
+        if rng.random() < 0.5:
+            spec["initContainers"] = [{"name": f"i{i}", "resources": {"requests": reqs()}} for i in range(rng.randrange(1, 3))]
+        if rng.random() < 0.3:
+            spec["overhead"] = reqs()
+        pod = {"kind": "Pod", "metadata": {"name": "p", "namespace": "d"}, "spec": spec}
+        got, want = rl_values(host.eval_host("PodRequestResourceList", pod=pod)), rl_values(oracle.call("PodRequestResourceList", pod=pod))
+        assert got == want, pod

@@ -265,3 +265,29 @@ def test_random_pods_request_lists_agree_with_the_oracle(host, oracle, seed):
         pod = {"kind": "Pod", "metadata": {"name": "p", "namespace": "d"}, "spec": spec}
         got, want = rl_values(host.eval_host("PodRequestResourceList", pod=pod)), rl_values(oracle.call("PodRequestResourceList", pod=pod))
         assert got == want, pod
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_selectors_validate_like_the_oracle(host, oracle, seed):
+    """LabelSelectorAsSelector accepts / rejects the same selectors in both implementations (operators, value counts, key and
+    value syntax).  PARITY UNPINNED by reference tests; both follow apimachinery v0.26.4 validation rules independently."""
+    import random
+
+    rng = random.Random(3000 + seed)
+    keys = ["app", "tier", "example.com/role", "a" * 63, "a" * 64, "-bad", "bad-", "a/b/c", "/x", "Ex_Ample.com/k", "exa_mple.com/k", "k.", "", "x y"]
+    vals = ["db", "", "a" * 63, "a" * 64, "bad value", "-x", "x-", "x_y.z", "9"]
+    ops = ["In", "NotIn", "Exists", "DoesNotExist", "Bogus", "in", ""]
+    disagreements = []
+    for _ in range(150):
+        sel = {}
+        if rng.random() < 0.6:
+            sel["matchLabels"] = {rng.choice(keys): rng.choice(vals) for _ in range(rng.randrange(0, 3))}
+        if rng.random() < 0.7:
+            sel["matchExpressions"] = [{"key": rng.choice(keys), "operator": rng.choice(ops), "values": [rng.choice(vals) for _ in range(rng.randrange(0, 3))]}
+                                       for _ in range(rng.randrange(0, 3))]
+        got = host.eval_host("ValidateSelector", selector=sel)["valid"]
+        ref = oracle.call("ThrottleSelector.MatchesToPod", selector={"selectorTerms": [{"podSelector": sel}]},
+                          pod={"metadata": {"name": "p", "namespace": "d", "labels": {"app": "db"}}, "spec": {}})
+        if got != ("error" not in ref):
+            disagreements.append((sel, got, ref))
+    assert not disagreements, disagreements[:3]

@@ -291,3 +291,22 @@ def test_random_selectors_validate_like_the_oracle(host, oracle, seed):
         if got != ("error" not in ref):
             disagreements.append((sel, got, ref))
     assert not disagreements, disagreements[:3]
+
+
+def test_random_timestamps_parse_like_the_oracle(host, oracle):
+    """time.Parse(time.RFC3339, s) over well-formed and malformed spellings (month / day / hour ranges, leap days, fractional
+    seconds with '.' and ',', zone offsets with and without colon, lower-case separators): value and Go's error text agree."""
+    import random
+
+    rng = random.Random(7)
+    for _ in range(600):
+        y = rng.choice([1, 1969, 1970, 1999, 2000, 2021, 2024, 2026, 2100, 9999])
+        mo, d = rng.choice([0, 1, 2, 2, 2, 6, 12, 13]), rng.choice([0, 1, 28, 29, 30, 31, 32])
+        h, mi, sec = rng.choice([0, 12, 23, 24, 25]), rng.choice([0, 30, 59, 60]), rng.choice([0, 30, 59, 60, 61])
+        frac = rng.choice(["", "", ".5", ".123456789", ".1234567891", ".", ",5", ".000"])
+        tz = rng.choice(["Z", "Z", "+09:00", "-07:00", "+00:00", "+24:00", "+09:60", "+0900", "z", "", " Z", "+9:00", "-00:00", "+23:59"])
+        s = f"{y:04d}-{mo:02d}-{d:02d}{rng.choice('TTTt ')}{h:02d}:{mi:02d}:{sec:02d}{frac}{tz}"
+        got, want = host.eval_host("ParseRFC3339", value=s), oracle.call("ParseRFC3339", value=s)
+        assert got.get("error") == want.get("error"), s
+        if "error" not in want:
+            assert (got["unix"], got["nsec"]) == (want["unix"], want["nsec"]), s

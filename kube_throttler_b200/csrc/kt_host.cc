@@ -369,14 +369,24 @@ struct kth_plugin {
   int column(const std::string& rname) {
     int c = col_dict.find(rname);
     if (c >= 0) return c;
+    // refuse BEFORE interning: the object that brought the name is rejected, the plugin stays usable
+    if ((int)cols.size() >= KT_MAX_RESOURCES) fail("more than " + std::to_string(KT_MAX_RESOURCES) + " distinct resource names (" + rname + ")");
     c = (int)col_dict.id(rname);
     ResourceColumn rc;
     rc.name = rname;
     rc.scale_exp = rname == "cpu" ? -3 : 0;  // milli-cpu, whole units / bytes elsewhere; refined on demand
     cols.push_back(rc);
-    if ((int)cols.size() > KT_MAX_RESOURCES) fail("more than 31 distinct resource names");
     if (ctx && (int)cols.size() > lim.n_resources) drop_engine();
     return c;
+  }
+  // An object that is refused (a limit, a malformed quantity) must not leave resource names behind that only it mentioned:
+  // kth_apply undoes the interning that happened since it started.
+  void rollback_columns(size_t n0) {
+    while (cols.size() > n0) {
+      col_dict.ids.erase(col_dict.names.back());
+      col_dict.names.pop_back();
+      cols.pop_back();
+    }
   }
   void note_quantity(int c, const Quantity& q) {
     const int need = kt::quantity_min_exp(q);
@@ -454,8 +464,8 @@ struct kth_plugin {
     p.request = pod_request_resource_list(spec);
     p.live = true;
     if ((int)p.labels.size() > max_labels) {
+      if ((int)p.labels.size() > KT_MAX_LABEL_SLOTS) fail("pod " + p.nn() + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS) + " labels");
       max_labels = (int)p.labels.size();
-      if (max_labels > KT_MAX_LABEL_SLOTS) fail("pod " + p.nn() + " has more than 32 labels");
       if (ctx && max_labels > lim.label_slots) drop_engine();
     }
     return p;
@@ -1272,14 +1282,16 @@ struct kth_plugin {
   }
   void apply_namespace(const Node& v) {
     const std::string nm = v["metadata"]["name"].str();
+    const Node& lab = v["metadata"]["labels"];
+    // refuse before touching any state: the object is rejected, the plugin stays usable
+    if ((int)lab.obj.size() > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS) + " labels");
     const int32_t id = ns_id(nm);
     NamespaceObj& n = namespaces[(size_t)id];
     n.exists = true;
     n.labels.clear();
-    for (auto& kv : v["metadata"]["labels"].obj) n.labels.emplace_back(kv.first, kv.second->str());
+    for (auto& kv : lab.obj) n.labels.emplace_back(kv.first, kv.second->str());
     if ((int)n.labels.size() > max_ns_labels) {
       max_ns_labels = (int)n.labels.size();
-      if (max_ns_labels > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than 32 labels");
       if (ctx && max_ns_labels > lim.ns_label_slots) drop_engine();
     }
     namespaces_dirty = true;
@@ -1309,39 +1321,39 @@ struct kth_plugin {
       o.terms.push_back(std::move(term));
     }
     o.live = true;
-    const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
-    auto it = thr_index.find(key);
+    // the status the manifest carries, parsed BEFORE anything is committed: a manifest that is refused leaves no trace
     const Node& st = v["status"];
-    if (it == thr_index.end()) {
-      thr_index[key] = (int)throttles.size();
-      throttles.push_back(std::move(o));
-      it = thr_index.find(key);
-    } else {  // spec update: the status subresource is kept unless the manifest carries one
-      ThrottleObj& old = throttles[(size_t)it->second];
-      o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
-      o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
-      old = std::move(o);
-    }
-    if (st.is(Node::Obj)) {
-      ThrottleObj& x = throttles[(size_t)it->second];
+    const bool has_status = st.is(Node::Obj);
+    if (has_status) {
       const Node& ct = st["calculatedThreshold"];
-      x.st_calc = res_amount(ct["threshold"]);
-      x.st_calc_at_set = false;
-      x.st_calc_at = 0;
+      o.st_calc = res_amount(ct["threshold"]);
+      o.st_calc_at_set = false;
+      o.st_calc_at = 0;
       if (ct["calculatedAt"].is(Node::Str) && !ct["calculatedAt"].text.empty()) {
         GoTime at;
         const std::string e = parse_rfc3339(ct["calculatedAt"].text, &at);
         if (!e.empty()) fail(e);
-        x.st_calc_at_set = !at.zero;
-        x.st_calc_at = at.sec;
+        o.st_calc_at_set = !at.zero;
+        o.st_calc_at = at.sec;
       }
-      x.st_messages.clear();
-      for (auto& mnode : ct["messages"].arr) x.st_messages.push_back(mnode->str());
-      x.st_thr_pod = st["throttled"]["resourceCounts"]["pod"].boolean(false);
-      x.st_thr_req.clear();
-      x.st_thr_req_nil = !st["throttled"]["resourceRequests"].is(Node::Obj);
-      for (auto& kv : st["throttled"]["resourceRequests"].obj) x.st_thr_req[column(kv.first)] = kv.second->boolean(false);
-      x.st_used = res_amount(st["used"]);
+      for (auto& mnode : ct["messages"].arr) o.st_messages.push_back(mnode->str());
+      o.st_thr_pod = st["throttled"]["resourceCounts"]["pod"].boolean(false);
+      o.st_thr_req_nil = !st["throttled"]["resourceRequests"].is(Node::Obj);
+      for (auto& kv : st["throttled"]["resourceRequests"].obj) o.st_thr_req[column(kv.first)] = kv.second->boolean(false);
+      o.st_used = res_amount(st["used"]);
+    }
+    const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
+    auto it = thr_index.find(key);
+    if (it == thr_index.end()) {
+      thr_index[key] = (int)throttles.size();
+      throttles.push_back(std::move(o));
+    } else {  // spec update: the status subresource is kept unless the manifest carries one
+      ThrottleObj& old = throttles[(size_t)it->second];
+      if (!has_status) {
+        o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
+        o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
+      }
+      old = std::move(o);
     }
     throttles_dirty = status_dirty = reserved_dirty = true;
   }
@@ -1541,11 +1553,17 @@ const char* kth_apply(kth_plugin* p, const char* manifest_json) {
   return guarded(p, [&]() -> std::string {
     ktjson::NodePtr v = ktjson::parse(manifest_json);
     const std::string kind = (*v)["kind"].str();
-    if (kind == "Pod") p->apply_pod(*v);
-    else if (kind == "Namespace") p->apply_namespace(*v);
-    else if (kind == "Throttle") p->apply_throttle(*v, KT_KIND_THROTTLE);
-    else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
-    else fail("unsupported kind: " + kind);
+    const size_t n_cols = p->cols.size();
+    try {
+      if (kind == "Pod") p->apply_pod(*v);
+      else if (kind == "Namespace") p->apply_namespace(*v);
+      else if (kind == "Throttle") p->apply_throttle(*v, KT_KIND_THROTTLE);
+      else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
+      else fail("unsupported kind: " + kind);
+    } catch (...) {
+      p->rollback_columns(n_cols);  // the refused object's resource names go with it
+      throw;
+    }
     return "{\"ok\":true}";
   });
 }

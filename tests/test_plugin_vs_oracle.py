@@ -327,3 +327,26 @@ def test_gauges_follow_reconcile():
     w.reconcile_all(NOW)
     assert "throttle_status_used_resourceCounts" + lt % "pod" in w.metrics()
     w.close()
+
+
+def test_objects_beyond_the_limits_are_rejected_not_fatal():
+    """A pod with more labels than KT_MAX_LABEL_SLOTS (32), a namespace likewise, or a 32nd distinct resource name is refused with
+    an error for THAT object; the plugin keeps serving (the limits are checked before any state is touched)."""
+    from kube_throttler_b200 import host
+    from test_scenarios import pod, throttle
+
+    w = host.Plugin(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        w.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}, node="n", phase="Running"))
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        w.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
+    with pytest.raises(RuntimeError, match="distinct resource names"):
+        w.apply(pod("default", "greedy", "100m", {"a": "1"}, node="n", phase="Running", requests={f"example.com/r{i}": "1" for i in range(40)}))
+    w.reconcile_all(NOW)
+    s = w.status("t", "default")
+    assert s["used"]["resourceCounts"]["pod"] == 1 and q(s["used"]["resourceRequests"]["cpu"]) == Fraction(3, 10)
+    assert w.prefilter(pod("default", "x", "800m", {"a": "1"}))["reasons"] == ["throttle[insufficient]=default/t"]
+    assert w.prefilter(pod("default", "y", "700m", {"a": "1"}))["code"] == "Success"
+    w.close()

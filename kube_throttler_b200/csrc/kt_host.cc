@@ -382,6 +382,7 @@ struct kth_plugin {
   // An object that is refused (a limit, a malformed quantity) must not leave resource names behind that only it mentioned:
   // kth_apply undoes the interning that happened since it started.
   void rollback_columns(size_t n0) {
+    if (cols.size() > n0) totals_valid = false;
     while (cols.size() > n0) {
       col_dict.ids.erase(col_dict.names.back());
       col_dict.names.pop_back();
@@ -392,6 +393,7 @@ struct kth_plugin {
     const int need = kt::quantity_min_exp(q);
     if (need < cols[c].scale_exp) {  // a finer value than the column holds: every row of the column is re-packed
       cols[c].scale_exp = need;
+      totals_valid = false;  // the running column totals were counted in the coarser unit
       pods_full_upload = throttles_dirty = status_dirty = reserved_dirty = true;
     }
     if (q.format == Quantity::BinarySI) cols[c].format = Quantity::BinarySI;
@@ -564,17 +566,34 @@ struct kth_plugin {
       dirty_rows.clear();
     }
   }
-  // int64 adds (and the NCCL sum) wrap silently: prove per column that they cannot (DESIGN.md "Quantity columns")
+  // int64 adds (and the NCCL sum) wrap silently: prove per column that they cannot (DESIGN.md "Quantity columns").
+  // The per-column totals of |value| are kept up to date by the pod events (totals_add), so a sync after a few events does
+  // not walk the whole pod table again; they are recounted only after a column changed its unit.
+  std::vector<__int128> col_abs;
+  bool totals_valid = false;
+  void totals_add(const PodObj& p, int sign) {
+    if (!totals_valid || !p.live) return;
+    if (col_abs.size() < cols.size()) col_abs.resize(cols.size(), 0);
+    for (auto& kv : p.request) {
+      bool ok;
+      const int64_t v = kt::quantity_at_scale(kv.second, cols[(size_t)kv.first].scale_exp, &ok);
+      if (!ok) { totals_valid = false; return; }  // the full recount reports it
+      col_abs[(size_t)kv.first] += (v < 0 ? -(__int128)v : (__int128)v) * sign;
+    }
+  }
   void overflow_check() {
-    std::vector<__int128> total(cols.size(), 0);
-    for (auto& p : pods)
-      if (p.live)
-        for (auto& kv : p.request) {
-          const int64_t v = at_scale(kv.first, kv.second);
-          total[kv.first] += v < 0 ? -(__int128)v : v;
-        }
-    for (size_t c = 0; c < cols.size(); ++c)
-      if (total[c] >= ((__int128)1 << 62)) fail("resource '" + cols[c].name + "': the column sum can overflow int64 at scale 1e" + std::to_string(cols[c].scale_exp));
+    if (!totals_valid) {
+      col_abs.assign(cols.size(), 0);
+      for (auto& p : pods)
+        if (p.live)
+          for (auto& kv : p.request) {
+            const int64_t v = at_scale(kv.first, kv.second);
+            col_abs[(size_t)kv.first] += v < 0 ? -(__int128)v : v;
+          }
+      totals_valid = true;
+    }
+    for (size_t c = 0; c < cols.size() && c < col_abs.size(); ++c)
+      if (col_abs[c] >= ((__int128)1 << 62)) fail("resource '" + cols[c].name + "': the column sum can overflow int64 at scale 1e" + std::to_string(cols[c].scale_exp));
   }
 
   void sync_namespaces() {
@@ -1236,35 +1255,50 @@ struct kth_plugin {
       else { row = (int64_t)pods.size(); pods.emplace_back(); }
       p.row = row;
       pod_index[p.nn()] = row;
+      totals_add(p, +1);
       pods[(size_t)row] = std::move(p);
       dirty_rows.insert(row);
       return;
     }
-    PodObj& old = pods[(size_t)it->second];
-    p.row = old.row;
-    // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
-    // then the pod's reservation moves from (old \ new) to (new \ old) throttles
-    const bool relevant = should_count_in(old) || should_count_in(p);
-    if (relevant && !throttles.empty() && old.labels != p.labels) {
-      PendingResult r = check_pending({old, p}, 0);
-      for (int kind = 0; kind < 2; ++kind) {
-        if (!controller_error(old, r, 0, kind).empty() || !controller_error(p, r, 1, kind).empty()) continue;  // HandleError + return
-        const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
-        for (int t : a)
-          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), p.nn()); reserved_dirty = true; }
-        for (int t : b)
-          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), p); reserved_dirty = true; }
-      }
-    }
-    const int64_t row = old.row;
+    // The informer's copy is replaced FIRST: the pass below only asks which throttles the old and the new pod match, which
+    // does not depend on the running rows, and an update that repairs a snapshot the packer refuses (column overflow) must
+    // not be refused for it.
+    const int64_t row = it->second;
+    const PodObj old = pods[(size_t)row];
+    p.row = row;
+    totals_add(old, -1);
+    totals_add(p, +1);
     pods[(size_t)row] = std::move(p);
     dirty_rows.insert(row);
+    const PodObj& cur = pods[(size_t)row];
+    // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
+    // then the pod's reservation moves from (old \ new) to (new \ old) throttles
+    const bool relevant = should_count_in(old) || should_count_in(cur);
+    if (relevant && !throttles.empty() && old.labels != cur.labels) {
+      const PodObj now = cur;  // check_pending may re-create the engine; keep value copies
+      PendingResult r = check_pending({old, now}, 0);
+      for (int kind = 0; kind < 2; ++kind) {
+        if (!controller_error(old, r, 0, kind).empty() || !controller_error(now, r, 1, kind).empty()) continue;  // HandleError + return
+        const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
+        for (int t : a)
+          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), now.nn()); reserved_dirty = true; }
+        for (int t : b)
+          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), now); reserved_dirty = true; }
+      }
+    }
   }
   void delete_pod(const std::string& ns, const std::string& pname) {
     auto it = pod_index.find(ns + "/" + pname);
     if (it == pod_index.end()) return;
     const int64_t row = it->second;
-    PodObj old = pods[(size_t)row];
+    const PodObj old = pods[(size_t)row];
+    // the row goes first (see apply_pod): a delete that repairs a refused snapshot must not be refused for it
+    totals_add(old, -1);
+    pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
+    pods[(size_t)row].row = row;
+    pod_index.erase(it);
+    free_rows.push_back(row);
+    dirty_rows.insert(row);
     // DeleteFunc (:509-515): a scheduled pod that disappears is un-reserved from its affected throttles
     if (should_count_in(old) && !old.node_name.empty() && !throttles.empty()) {
       PendingResult r = check_pending({old}, 0);
@@ -1274,11 +1308,6 @@ struct kth_plugin {
           if (cache[kind].remove(throttles[(size_t)t].nn(), old.nn())) reserved_dirty = true;
       }
     }
-    pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
-    pods[(size_t)row].row = row;
-    pod_index.erase(it);
-    free_rows.push_back(row);
-    dirty_rows.insert(row);
   }
   void apply_namespace(const Node& v) {
     const std::string nm = v["metadata"]["name"].str();

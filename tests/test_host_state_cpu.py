@@ -140,3 +140,25 @@ def test_pod_delete_and_reapply_reuse_rows(world):
     assert world.delete("Pod", "nope", "default") == {"ok": True}   # deleting what is not there is not an error (DeleteFunc of a stale key)
     world.apply(pod("default", "p9", "1", {"a": "1"}, node="n", phase="Running"), pod("default", "p0", "200m", {"a": "2"}, node="n", phase="Running"))
     assert world.delete("Throttle", "nope", "default") == {"ok": True}
+
+
+def test_column_overflow_is_proved_incrementally(host_on_oracle):
+    """The packer refuses a snapshot whose column sum could wrap int64 (sum of |v| >= 2^62).  The per-column totals follow the
+    pod events, so the proof does not walk the pod table at every sync; it has to notice an overflow that an update or a new
+    pod brings about and to forget it when the pod goes away.  (Host layer over the oracle-backed engine double.)"""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    w.apply(pod("default", "p1", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))  # 2^61 + 2^61
+    with pytest.raises(RuntimeError, match="can overflow int64"):
+        w.reconcile_all("2026-01-01T00:00:00Z")
+    w.apply(pod("default", "p1", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "1Ei"}))  # update shrinks it
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    w.apply(pod("default", "p2", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "1Ei"}))  # 2^61 + 2^60 + 2^60
+    with pytest.raises(RuntimeError, match="can overflow int64"):
+        w.reconcile_all("2026-01-01T00:00:00Z")
+    w.delete("Pod", "p0", "default")
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    assert w.status("t", "default")["used"]["resourceRequests"]["memory"] == str(2**61)
+    w.close()

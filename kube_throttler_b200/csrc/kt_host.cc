@@ -286,6 +286,7 @@ struct ThrottleObj {
   bool st_thr_req_nil = true;
   ResAmount st_used;
   bool live = false;
+  bool metrics_pending = false;  // reconciled since its gauges were last written into the registry (see record_metrics)
   std::string nn() const { return ns + "/" + name; }
   std::string selector_error() const {  // the first podSelector that LabelSelectorAsSelector rejects
     for (auto& t : terms)
@@ -830,6 +831,10 @@ struct kth_plugin {
   // ---- gauges (throttle_metrics.go / clusterthrottle_metrics.go / metrics_recorder.go) --------------------------
   // A GaugeVec keeps every series it was ever given: reconcile records the throttle it just handled, nothing is deleted
   // when a throttle or one of its resource names goes away.  family -> (label pairs sorted by name, rendered) -> value.
+  // Rendering ~20 label sets per throttle is 3 us of string work -- a hundred times the device pass for 1000 throttles -- so
+  // reconcile only MARKS the throttle (metrics_pending); the registry is brought up to date when somebody looks at it
+  // (kth_metrics) and, so that the values are the ones of the last reconcile and nothing newer, right before the object
+  // changes under it (a spec or status update, a delete).
   std::map<std::string, std::map<std::string, double>> gauges;
   static std::string label_escape(const std::string& v) {
     std::string o;
@@ -905,6 +910,10 @@ struct kth_plugin {
       return out + digits.substr(0, (size_t)exp + 1) + "." + digits.substr((size_t)exp + 1);
     }
     return out + "0." + std::string((size_t)(-exp - 1), '0') + digits;
+  }
+  void flush_metrics() {
+    for (auto& o : throttles)
+      if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }
   }
   std::string metrics_text() const {
     static const std::pair<const char*, const char*> kHelp[] = {
@@ -1005,7 +1014,7 @@ struct kth_plugin {
       o.st_thr_req_nil = thr_nil;
       if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
       o.st_used = nu;
-      record_metrics(o);  // both branches of the status comparison record (throttle_controller.go:159,187)
+      o.metrics_pending = true;  // both branches of the status comparison record (throttle_controller.go:159,187); see record_metrics
       if (status_changed) changed.push_back(o.nn());
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
@@ -1378,6 +1387,7 @@ struct kth_plugin {
       throttles.push_back(std::move(o));
     } else {  // spec update: the status subresource is kept unless the manifest carries one
       ThrottleObj& old = throttles[(size_t)it->second];
+      if (old.metrics_pending) record_metrics(old);  // the gauges keep the values of the last reconcile, not of this update
       if (!has_status) {
         o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
         o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
@@ -1392,6 +1402,7 @@ struct kth_plugin {
     if (it == thr_index.end()) return;
     // the column is kept (device order is insertion order) but can never match or be reconciled again
     ThrottleObj& o = throttles[(size_t)it->second];
+    if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }  // its series outlive it, as a GaugeVec's do
     o.live = false;
     o.terms.clear();
     cache[kind].by_thr.erase(nn);
@@ -1652,7 +1663,10 @@ const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn) {
   return guarded(p, [&]() { return p->reserved_json(kind, throttle_nn ? throttle_nn : ""); });
 }
 const char* kth_metrics(kth_plugin* p) {
-  return guarded(p, [&]() -> std::string { return p->metrics_text(); });
+  return guarded(p, [&]() -> std::string {
+    p->flush_metrics();
+    return p->metrics_text();
+  });
 }
 const char* kth_eval(const char* request_json) {
   try {

@@ -328,6 +328,13 @@ def test_gauges_follow_reconcile(new_plugin):
     assert s["clusterthrottle_status_throttled_resourceRequests" + lc % "cpu"] == "1"
     assert s["clusterthrottle_spec_threshold_resourceCounts" + lc % "pod"] == "0"
     assert not any('name="other"' in k for k in s)  # not ours: never enqueued, never recorded
+    # a spec edit does not move the spec gauge until the next reconcile records it (the recorder runs inside reconcile)
+    t2 = throttle("default", "t", {"a": "1"}, pod_cnt=7, cpu="1")
+    t2["metadata"]["uid"] = "uid-t"
+    w.apply(t2)
+    assert f'throttle_spec_threshold_resourceCounts{lt % "pod"} 2' in w.metrics()
+    w.reconcile_all(NOW)
+    assert f'throttle_spec_threshold_resourceCounts{lt % "pod"} 7' in w.metrics()
     w.delete("Throttle", "t", "default")
     w.reconcile_all(NOW)
     assert "throttle_status_used_resourceCounts" + lt % "pod" in w.metrics()

@@ -310,3 +310,15 @@ def test_random_timestamps_parse_like_the_oracle(host, oracle):
         assert got.get("error") == want.get("error"), s
         if "error" not in want:
             assert (got["unix"], got["nsec"]) == (want["unix"], want["nsec"]), s
+
+
+def test_manifest_parser_refuses_pathological_json(host):
+    """kth_* take manifests as JSON text: nesting is bounded (the parser recurses), malformed input is an error, not a crash."""
+    L = host._bind()
+    deep = b'{"fn":"PodRequestResourceList","pod":{"spec":{},"x":' + b"[" * 300 + b"]" * 300 + b"}}"
+    assert b"nested too deeply" in L.kth_eval(deep)
+    ok = b'{"fn":"PodRequestResourceList","pod":{"spec":{},"x":' + b"[" * 200 + b"]" * 200 + b"}}"
+    assert L.kth_eval(ok) == b"{}"
+    for bad in (b"", b"{", b'{"fn":', b'{"fn":"ParseQuantity","value":"1"} trailing', b'{"fn":"ParseQuantity","value":"\\u12"}', b"[" * 100000):
+        out = L.kth_eval(bad)
+        assert out.startswith(b'{"error"'), bad[:40]

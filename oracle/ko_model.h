@@ -840,12 +840,15 @@ struct World {
     return "";
   }
 
+  // Every key is reconciled on its own in the reference (workqueue items; an error re-queues that key and nothing else,
+  // controller.go:95-122): a failing throttle does not keep the others from being reconciled.  Returns the first error.
   std::string reconcileAll(const Time& now) {
+    std::string first;
     for (auto& t : throttles)
-      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty() && first.empty()) first = e; }
     for (auto& t : clusterThrottles)
-      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
-    return "";
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty() && first.empty()) first = e; }
+    return first;
   }
 
   // ---- affectedThrottles: throttle_controller.go:248-269 ----

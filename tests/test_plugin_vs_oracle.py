@@ -361,3 +361,45 @@ def test_objects_beyond_the_limits_are_rejected_not_fatal(new_plugin):
     assert w.prefilter(pod("default", "x", "800m", {"a": "1"}))["reasons"] == ["throttle[insufficient]=default/t"]
     assert w.prefilter(pod("default", "y", "700m", {"a": "1"}))["code"] == "Success"
     w.close()
+
+
+def test_selector_errors_q9(oracle, new_plugin):
+    """Q9: a podSelector that LabelSelectorAsSelector rejects makes PreFilter return framework.Error with the conversion error
+    for every pod the controller would have asked it about (plugin.go:154-156,166-168), and keeps that throttle -- only that
+    one -- from being reconciled; a namespaceSelector that fails to convert is swallowed and simply never matches
+    (clusterthrottle_selector.go:65-67,74-76)."""
+    from test_scenarios import pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    bad = {"matchExpressions": [{"key": "a", "operator": "In", "values": []}]}
+    spec = lambda terms: {"throttlerName": THROTTLER, "threshold": {"resourceRequests": {"cpu": "1"}}, "selector": {"selectorTerms": terms}}
+    both(namespace("default", {"team": "x"}), namespace("other", {"team": "y"}), throttle("default", "ok", {"a": "1"}, cpu="1"),
+         {"kind": "ClusterThrottle", "metadata": {"name": "cbadns"}, "spec": spec([{"namespaceSelector": bad, "podSelector": {"matchLabels": {"a": "1"}}}])},
+         pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"), pod("other", "p1", "300m", {"a": "1"}, node="n", phase="Running"))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    for name, ns in (("ok", "default"), ("cbadns", "")):
+        assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns))
+    assert "resourceCounts" not in dut.status("cbadns")["used"]  # the swallowed namespace-selector error: nothing ever matches
+    probes = [pod("default", "x", "100m", {"a": "1"}), pod("other", "y", "100m", {"a": "1"}), pod("default", "z", "100m", {"q": "1"})]
+    for p in probes:
+        assert norm_prefilter(ref.prefilter(p)) == norm_prefilter(dut.prefilter(p))
+
+    def verdict(w, p):  # what the scheduler sees of an Error status: the code and the message
+        r = w.prefilter(p)
+        return r["code"], r["reasons"]
+
+    both({"kind": "Throttle", "metadata": {"namespace": "default", "name": "bad"}, "spec": spec([{"podSelector": bad}])})
+    with pytest.raises(RuntimeError, match="values set can't be empty"):
+        ref.reconcile_all(NOW)      # the oracle reports the failing key; the others were reconciled all the same
+    dut.reconcile_all(NOW)
+    assert norm_status(ref.status("ok", "default")) == norm_status(dut.status("ok", "default"))
+    assert norm_status(ref.status("bad", "default")) == norm_status(dut.status("bad", "default"))  # untouched: never reconciled
+    for p in probes:
+        assert verdict(ref, p) == verdict(dut, p)
+    assert verdict(dut, probes[0])[0] == "Error" and verdict(dut, probes[1])[0] != "Error"  # only the namespace of the broken Throttle
+    both({"kind": "ClusterThrottle", "metadata": {"name": "cbadpod"}, "spec": spec([{"namespaceSelector": {"matchLabels": {"team": "y"}}, "podSelector": bad}])})
+    for p in probes:
+        assert verdict(ref, p) == verdict(dut, p)
+    assert verdict(dut, probes[1])[0] == "Error"  # its namespaceSelector picks "other": pods there now get the conversion error
+    dut.close()

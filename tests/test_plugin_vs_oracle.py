@@ -403,3 +403,47 @@ def test_selector_errors_q9(oracle, new_plugin):
         assert verdict(ref, p) == verdict(dut, p)
     assert verdict(dut, probes[1])[0] == "Error"  # its namespaceSelector picks "other": pods there now get the conversion error
     dut.close()
+
+
+def test_selector_error_behind_a_valid_term(oracle, new_plugin):
+    """MatchesToPod walks the terms in order and returns at the first match (throttle_selector.go:30-42): a term that does not
+    convert only hurts the pods that get as far as it.  A Throttle {valid term, broken term} is reconciled as long as every
+    counted pod of its namespace matches the valid term, stops being reconciled when one does not, and PreFilter fails only for
+    the pods that reach the broken term."""
+    from test_scenarios import pod
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    bad = {"matchExpressions": [{"key": "a", "operator": "Exists", "values": ["x"]}]}
+    mixed = {"kind": "Throttle", "metadata": {"namespace": "default", "name": "mixed"},
+             "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 2}, "resourceRequests": {"cpu": "1"}},
+                      "selector": {"selectorTerms": [{"podSelector": {"matchLabels": {"a": "1"}}}, {"podSelector": bad}, {"podSelector": {"matchLabels": {"b": "1"}}}]}}}
+    both(namespace("default"), namespace("other"), mixed)
+
+    def reconcile_both():
+        try:
+            ref.reconcile_all(NOW)
+            ok = True
+        except RuntimeError:
+            ok = False
+        dut.reconcile_all(NOW)
+        assert norm_status(ref.status("mixed", "default")) == norm_status(dut.status("mixed", "default"))
+        return ok
+
+    assert reconcile_both()  # no pod has asked the selector anything yet
+    assert dut.status("mixed", "default")["calculatedThreshold"]["calculatedAtSet"] is True
+    both(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"), pod("default", "p1", "300m", {"a": "1", "b": "1"}, node="n", phase="Succeeded"),
+         pod("other", "elsewhere", "300m", {"c": "1"}, node="n", phase="Running"), pod("default", "unscheduled", "300m", {"c": "1"}))
+    assert reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 1
+    both(pod("default", "p2", "300m", {"b": "1"}, node="n", phase="Running"))  # matches only the term BEHIND the broken one
+    assert not reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 1  # untouched
+    for p in (pod("default", "x", "100m", {"a": "1"}), pod("default", "y", "100m", {"b": "1"}), pod("default", "z", "100m", {}), pod("other", "w", "100m", {"b": "1"})):
+        a, b = ref.prefilter(p), dut.prefilter(p)
+        assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+    both(pod("default", "p2", "300m", {"a": "1", "b": "1"}, node="n", phase="Running"))  # relabelled: now the valid term takes it
+    both(pod("default", "p3", "400m", {"a": "1"}, node="n", phase="Running"))
+    assert reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 3 and dut.status("mixed", "default")["throttled"]["resourceCounts"]["pod"] is True
+    dut.close()

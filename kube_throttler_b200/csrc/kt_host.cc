@@ -339,6 +339,7 @@ struct PodObj {
   std::string scheduler_name, node_name, phase;
   std::map<int, Quantity> request;  // PodRequestResourceList (resource id -> quantity); ResourceAmountOfPod adds Counts{1}
   int64_t row = -1;                 // slot in the running-pod table
+  uint64_t seq = 0;                 // order of first appearance (the informer-cache order the oracle iterates in; Q8)
   bool live = false;
   std::string nn() const { return ns + "/" + name; }
 };
@@ -436,6 +437,7 @@ struct kth_plugin {
   std::unordered_map<std::string, int64_t> pod_index;
   std::vector<int64_t> free_rows;
   std::set<int64_t> dirty_rows;
+  uint64_t next_pod_seq = 1;
   int64_t row_capacity = 0;  // rows the device table currently holds
   bool pods_full_upload = true;
 
@@ -1050,6 +1052,36 @@ struct kth_plugin {
     const int Wp = kt_match_words(ctx);
     std::vector<uint32_t> words(rows.size() * (size_t)Wp);
     if (!rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)rows.size(), rows.data(), words.data()), "kt_get_match_rows");
+    // Q8 (throttle_controller.go:241, `terminatedPods = append(nonterminatedPods, pod)`): the THROTTLE controller's list of
+    // terminated affected pods ends up holding only the LAST terminated match of the namespace, so of the finished pods that
+    // still hold a reservation only that one is un-reserved; the others keep it until the pod is deleted.  (Which pod is "last"
+    // is the informer's map order in the reference; the oracle and this code take the order of first appearance.)  Needed only
+    // when a finished pod holds a reservation: then the match rows of the finished counted pods say who is last per throttle.
+    std::vector<char> row_finished(rows.size(), 0);
+    bool any_finished_reserved = false;
+    for (size_t i = 0; i < rows.size(); ++i) {
+      const PodObj& p = pods[(size_t)rows[i]];
+      row_finished[i] = p.live && !(pod_flags(p) & KT_POD_NOT_FINISHED);
+      any_finished_reserved |= row_finished[i] != 0;
+    }
+    std::vector<int64_t> fin_rows;
+    std::vector<uint32_t> fin_words;
+    if (any_finished_reserved) {
+      for (auto& p : pods)
+        if (p.live && should_count_in(p) && !(pod_flags(p) & KT_POD_NOT_FINISHED)) fin_rows.push_back(p.row);
+      fin_words.resize(fin_rows.size() * (size_t)Wp);
+      if (!fin_rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)fin_rows.size(), fin_rows.data(), fin_words.data()), "kt_get_match_rows");
+    }
+    auto last_finished_match = [&](size_t t, const std::string& ns) -> int64_t {  // row of the last finished pod of ns that matches t
+      int64_t best = -1;
+      uint64_t best_seq = 0;
+      for (size_t i = 0; i < fin_rows.size(); ++i) {
+        const PodObj& p = pods[(size_t)fin_rows[i]];
+        if (p.ns != ns || !((fin_words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)) continue;
+        if (best < 0 || p.seq > best_seq) { best = p.row; best_seq = p.seq; }
+      }
+      return best;
+    };
 
     // A Throttle with a podSelector term that does not convert: affectedPods (throttle_controller.go:221-246) only fails -- and
     // the reconcile with it -- when some counted pod of the namespace actually REACHES that term, i.e. matches none of the
@@ -1119,12 +1151,20 @@ struct kth_plugin {
       if (status_changed) changed.push_back(o.nn());
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
-      // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache
+      // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache -- except, for a
+      // Throttle, the finished ones the reference's list loses (Q8)
       auto it = cache[o.kind].by_thr.find(o.nn());
-      if (it != cache[o.kind].by_thr.end())
-        for (size_t i = 0; i < rows.size(); ++i)
-          if ((words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)
-            if (it->second.erase(row_pod[i])) reserved_dirty = true;
+      if (it != cache[o.kind].by_thr.end()) {
+        int64_t last_fin = -2;  // computed on first need
+        for (size_t i = 0; i < rows.size(); ++i) {
+          if (!((words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)) continue;
+          if (o.kind == KT_KIND_THROTTLE && row_finished[i]) {
+            if (last_fin == -2) last_fin = last_finished_match(t, o.ns);
+            if (rows[i] != last_fin) continue;
+          }
+          if (it->second.erase(row_pod[i])) reserved_dirty = true;
+        }
+      }
     }
     status_dirty = true;
     w.key("reconciled").num(reconciled).key("changed").begin_arr();
@@ -1364,6 +1404,7 @@ struct kth_plugin {
       if (!free_rows.empty()) { row = free_rows.back(); free_rows.pop_back(); }
       else { row = (int64_t)pods.size(); pods.emplace_back(); }
       p.row = row;
+      p.seq = next_pod_seq++;
       pod_index[p.nn()] = row;
       totals_add(p, +1);
       pods[(size_t)row] = std::move(p);
@@ -1376,6 +1417,7 @@ struct kth_plugin {
     const int64_t row = it->second;
     const PodObj old = pods[(size_t)row];
     p.row = row;
+    p.seq = old.seq;
     totals_add(old, -1);
     totals_add(p, +1);
     pods[(size_t)row] = std::move(p);

@@ -447,3 +447,36 @@ def test_selector_error_behind_a_valid_term(oracle, new_plugin):
     assert reconcile_both()
     assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 3 and dut.status("mixed", "default")["throttled"]["resourceCounts"]["pod"] is True
     dut.close()
+
+
+def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
+    """Q8: `terminatedPods = append(nonterminatedPods, pod)` (throttle_controller.go:241) leaves only the LAST finished match in
+    the Throttle controller's list, so a reconcile un-reserves the running pods it observes and one finished pod; the other
+    finished pods keep their reservation (and keep counting against later pods).  ClusterThrottles (correct code,
+    clusterthrottle_controller.go:266) un-reserve all of them."""
+    from test_scenarios import clthrottle, pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="10"), clthrottle("c", {"kubernetes.io/metadata.name": "default"}, {"a": "1"}, cpu="10"))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    queue = [pod("default", f"q{i}", "1", {"a": "1"}) for i in range(4)]
+    for p in queue:
+        assert ref.prefilter(p)["code"] == dut.prefilter(p)["code"] == "Success"
+        assert ref.reserve(p)["code"] == dut.reserve(p)["code"] == "Success"
+    # q0 and q2 ran to completion before the next reconcile, q1 is running, q3 is still only reserved
+    both(dict(queue[0], spec=dict(queue[0]["spec"], nodeName="n"), status={"phase": "Succeeded"}),
+         dict(queue[1], spec=dict(queue[1]["spec"], nodeName="n"), status={"phase": "Running"}),
+         dict(queue[2], spec=dict(queue[2]["spec"], nodeName="n"), status={"phase": "Failed"}))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    for kind, nn in (("Throttle", "default/t"), ("ClusterThrottle", "/c")):
+        a, b = ref.reserved(kind, nn), dut.reserved(kind, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (nn, a, b)
+    assert sorted(dut.reserved("Throttle", "default/t")["pods"]) == ["default/q0", "default/q3"]  # q2 (the last finished one) and q1 left
+    assert dut.reserved("ClusterThrottle", "/c")["pods"] == ["default/q3"]
+    for name, ns in (("t", "default"), ("c", "")):
+        assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns))
+    probe = pod("default", "x", "7500m", {"a": "1"})  # used 1 (q1) + reserved: 2 on the Throttle, 1 on the ClusterThrottle
+    assert norm_prefilter(ref.prefilter(probe)) == norm_prefilter(dut.prefilter(probe))
+    assert dut.prefilter(probe)["reasons"] == ["throttle[insufficient]=default/t"]
+    dut.close()

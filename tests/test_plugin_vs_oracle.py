@@ -533,6 +533,9 @@ def run_event_stream(oracle, new_plugin, seed):
         elif op < 0.88:
             n = rng.choice(nss); log.append(("relabel-ns", n))
             both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+        elif op < 0.94 and len(pods) > 20:
+            p = pods.pop(rng.randrange(len(pods))); log.append(("delete-pod", p["metadata"]["name"]))  # informer Delete event
+            ref.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"]), dut.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"])
         else:
             p = rand_pod(rng, rng.choice(nss), f"n{step}", True); pods.append(p); log.append(("new-pod", p["metadata"]["name"]))
             both(p)
@@ -556,7 +559,7 @@ def run_event_stream(oracle, new_plugin, seed):
 @pytest.mark.parametrize("seed", range(6))
 def test_event_stream_chaos(oracle, new_plugin, seed):
     """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve,
-    binds (some pods finish at once), Unreserve, pod relabels (reservation moves), throttle spec edits, namespace relabels, new
-    pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
+    binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, namespace
+    relabels, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
     the end must agree.  (tools/chaos_host.py runs more seeds on the CPU double.)"""
     run_event_stream(oracle, new_plugin, seed)

@@ -1561,7 +1561,8 @@ struct kth_plugin {
     if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }  // its series outlive it, as a GaugeVec's do
     o.live = false;
     o.terms.clear();
-    cache[kind].by_thr.erase(nn);
+    // The reservation cache keeps the entry: reserved_resource_amounts.go has no way to drop a throttle, so what was reserved on
+    // this name is still counted if a throttle of the same name comes back (until those pods are observed or deleted).
     thr_index.erase(it);
     throttles_dirty = status_dirty = reserved_dirty = true;
     broken_valid = false;

@@ -1113,6 +1113,26 @@ struct World {
     upsertPod(std::move(p));
   }
 
+  // ---- throttle informer Delete event (throttle_controller.go:417-424, clusterthrottle_controller.go:447-454): the key is
+  // enqueued, its reconcile finds nothing (:96-101).  The reservation cache is NOT told (reserved_resource_amounts.go has no
+  // way to drop a throttle's entry): whatever was reserved on that name is still there if a throttle of the same name comes back.
+  void deleteThrottle(bool cluster, const std::string& ns, const std::string& name) {
+    if (!cluster) {
+      auto it = thrIndex.find(ns + "/" + name);
+      if (it == thrIndex.end()) return;
+      throttles.erase(throttles.begin() + (std::ptrdiff_t)it->second);
+      thrIndex.clear();
+      thrByNs.clear();
+      for (size_t i = 0; i < throttles.size(); ++i) { thrIndex[throttles[i]->NN()] = i; thrByNs[throttles[i]->ns].push_back(i); }
+    } else {
+      auto it = clthrIndex.find(name);
+      if (it == clthrIndex.end()) return;
+      clusterThrottles.erase(clusterThrottles.begin() + (std::ptrdiff_t)it->second);
+      clthrIndex.clear();
+      for (size_t i = 0; i < clusterThrottles.size(); ++i) clthrIndex[clusterThrottles[i]->name] = i;
+    }
+  }
+
   // ---- pod informer Delete event (throttle_controller.go:508-531, clusterthrottle_controller.go:536-559): both controllers
   // un-reserve a counted, scheduled pod from its affected throttles (errors are only logged); the informer's store has
   // dropped the pod either way. ----

@@ -61,6 +61,8 @@ def lib():
         L.ko_world_apply.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_world_delete_pod.restype = C.c_char_p
         L.ko_world_delete_pod.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ko_world_delete_namespace.restype = C.c_char_p
+        L.ko_world_delete_namespace.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_world_delete_throttle.restype = C.c_char_p
         L.ko_world_delete_throttle.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         L.ko_world_reconcile_all.argtypes = [C.c_void_p, C.c_char_p]
@@ -124,6 +126,8 @@ class World:
             return self._json(lib().ko_world_delete_pod(self._h, namespace.encode(), name.encode()))
         if kind in ("Throttle", "ClusterThrottle"):
             return self._json(lib().ko_world_delete_throttle(self._h, 0 if kind == "Throttle" else 1, namespace.encode(), name.encode()))
+        if kind == "Namespace":
+            return self._json(lib().ko_world_delete_namespace(self._h, name.encode()))
         raise NotImplementedError("the oracle does not model deletes of " + kind)
 
     def reconcile_all(self, now="2026-01-01T00:00:00Z"):

@@ -873,6 +873,15 @@ struct World {
     nsIndex[n.name] = namespaces.size();
     namespaces.push_back(std::make_unique<Namespace>(std::move(n)));
   }
+  // namespace informer Delete event: no handler is registered (clusterthrottle_controller.go:429); the lister just stops
+  // returning it, so ClusterThrottle checks of pods in it fail with "not found" (:273-276) and its pods leave affectedPods.
+  void deleteNamespace(const std::string& name) {
+    auto it = nsIndex.find(name);
+    if (it == nsIndex.end()) return;
+    namespaces.erase(namespaces.begin() + (std::ptrdiff_t)it->second);
+    nsIndex.clear();
+    for (size_t i = 0; i < namespaces.size(); ++i) nsIndex[namespaces[i]->name] = i;
+  }
   // keepStatus: a manifest without .status is a spec edit -- the status subresource survives it (CRD status subresource)
   void upsertThrottle(Throttle t, bool keepStatus = false) {
     if (t.kind == KindThrottle) {

@@ -351,7 +351,7 @@ def test_objects_beyond_the_limits_are_rejected_not_fatal(new_plugin):
     w.apply(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
     with pytest.raises(RuntimeError, match="more than 32 labels"):
         w.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}, node="n", phase="Running"))
-    with pytest.raises(RuntimeError, match="more than 32 labels"):
+    with pytest.raises(RuntimeError, match="more than 31 labels"):
         w.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
     with pytest.raises(RuntimeError, match="distinct resource names"):
         w.apply(pod("default", "greedy", "100m", {"a": "1"}, node="n", phase="Running", requests={f"example.com/r{i}": "1" for i in range(40)}))
@@ -532,9 +532,12 @@ def run_event_stream(oracle, new_plugin, seed):
             throttles[i] = t
             gone.discard(i)
             both(t)
-        elif op < 0.88:
-            n = rng.choice(nss); log.append(("relabel-ns", n))
+        elif op < 0.86:
+            n = rng.choice(nss); log.append(("relabel-ns", n))  # also what brings a deleted namespace back
             both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+        elif op < 0.88:
+            n = rng.choice(nss); log.append(("delete-ns", n))  # the lister stops returning it; its pods and throttles stay
+            ref.delete("Namespace", n), dut.delete("Namespace", n)
         elif op < 0.91 and len(gone) < 5:
             i = rng.randrange(len(throttles)); log.append(("delete-throttle", i))  # its reservations stay in the cache (no way to drop them)
             if i not in gone:
@@ -569,6 +572,45 @@ def run_event_stream(oracle, new_plugin, seed):
 def test_event_stream_chaos(oracle, new_plugin, seed):
     """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve,
     binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, throttle deletes
-    and re-creations, namespace relabels, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
+    and re-creations, namespace relabels and deletes, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
     the end must agree.  (tools/chaos_host.py runs more seeds on the CPU double.)"""
     run_event_stream(oracle, new_plugin, seed)
+
+
+def test_pods_of_a_namespace_the_lister_does_not_hold(oracle, new_plugin):
+    """ClusterThrottleController.affectedPods walks the namespaces the lister returns (clusterthrottle_controller.go:227): pods of
+    a namespace that was never seen, or was deleted, are not counted by ANY ClusterThrottle -- not even one whose namespaceSelector
+    is empty -- while a namespaced Throttle (which never asks about the namespace) still counts them; PreFilter for such a pod
+    fails in the ClusterThrottle controller with "not found" (:273-276)."""
+    from test_scenarios import pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    everywhere = {"kind": "ClusterThrottle", "metadata": {"name": "everywhere"},
+                  "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 10}},
+                           "selector": {"selectorTerms": [{"namespaceSelector": {}, "podSelector": {"matchLabels": {"a": "1"}}}]}}}
+    notprod = {"kind": "ClusterThrottle", "metadata": {"name": "notprod"},
+               "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 10}},
+                        "selector": {"selectorTerms": [{"namespaceSelector": {"matchExpressions": [{"key": "env", "operator": "NotIn", "values": ["prod"]}]},
+                                                        "podSelector": {}}]}}}
+    both(namespace("seen", {"env": "dev"}), everywhere, notprod, throttle("ghost", "local", {"a": "1"}, pod_cnt=10),
+         pod("seen", "p0", "100m", {"a": "1"}, node="n", phase="Running"), pod("ghost", "p1", "100m", {"a": "1"}, node="n", phase="Running"))
+
+    def settle_and_compare():
+        ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+        for name, ns in (("everywhere", ""), ("notprod", ""), ("local", "ghost")):
+            assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns)), name
+        for p in (pod("seen", "x", "100m", {"a": "1"}), pod("ghost", "y", "100m", {"a": "1"})):
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 1 and dut.status("local", "ghost")["used"]["resourceCounts"]["pod"] == 1
+    assert dut.prefilter(pod("ghost", "y", "100m", {"a": "1"}))["code"] == "Error"
+    both(namespace("ghost", {"env": "dev"}))           # the namespace shows up
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 2 and dut.status("notprod")["used"]["resourceCounts"]["pod"] == 2
+    ref.delete("Namespace", "seen"), dut.delete("Namespace", "seen")   # and another one goes away
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 1
+    dut.close()

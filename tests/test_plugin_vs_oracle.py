@@ -518,11 +518,19 @@ def run_event_stream(oracle, new_plugin, seed):
                 both(dict(p, spec=dict(p["spec"], nodeName="node-2"), status={"phase": rng.choice(["Running", "Running", "Succeeded"])}))
             else:
                 ref.unreserve(p); dut.unreserve(p)
-        elif op < 0.7:
+        elif op < 0.64:
             p = rng.choice(pods); log.append(("relabel", p["metadata"]["name"]))
             p["metadata"]["labels"] = rand_labels(rng)
             if rng.random() < 0.3: p["status"] = {"phase": rng.choice(["Running", "Succeeded", "Failed"])}
             both(p)
+        elif op < 0.68:
+            i = rng.randrange(len(pods)); log.append(("mutate-pod", pods[i]["metadata"]["name"]))  # anything may change: requests, scheduler, node, phase
+            pods[i] = rand_pod(rng, pods[i]["metadata"]["namespace"], pods[i]["metadata"]["name"], True)
+            both(pods[i])
+        elif op < 0.7 and reserved:
+            p = rng.choice(reserved); log.append(("re-reserve", p["metadata"]["name"]))  # addPod overwrites the amount it kept
+            p["spec"]["containers"][0]["resources"]["requests"]["cpu"] = rng.choice(CPUS)
+            assert ref.reserve(p)["code"] == dut.reserve(p)["code"]
         elif op < 0.8:
             i = rng.randrange(len(throttles)); log.append(("edit-throttle", i))
             t = rand_throttle(rng, i, nss)

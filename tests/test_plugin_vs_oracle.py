@@ -505,6 +505,23 @@ def run_event_stream(oracle, new_plugin, seed):
             try: ref.reconcile_all(now)
             except RuntimeError: pass
             dut.reconcile_all(now)
+        elif op < 0.23:
+            batch = rng.sample(pending, 6); log.append(("prefilter-batch", [p["metadata"]["name"] for p in batch]))
+            want = [ref.prefilter(p) for p in batch]
+            got = dut.prefilter_batch(batch)  # one device pass for the lot: independent checks against the same snapshot
+            assert [(a["code"], a["reasons"]) for a in want] == [(b["code"], b["reasons"]) for b in got], (seed, step, log[-5:])
+        elif op < 0.27:
+            names = {p["metadata"]["name"] for p in reserved}
+            queue = [p for p in rng.sample(pending, 8) if p["metadata"]["name"] not in names]; log.append(("admit-queue", len(queue)))
+            want = []
+            for p in queue:  # the scheduler's cycle, pod by pod
+                r = ref.prefilter(p)
+                if r["code"] == "Success":
+                    assert ref.reserve(p)["code"] == "Success"
+                want.append((r["code"], r["reasons"]))
+            got = dut.admit_queue(queue)
+            assert [(x["preFilter"]["code"], x["preFilter"]["reasons"]) for x in got["results"]] == want, (seed, step, log[-5:])
+            reserved.extend(p for p, w in zip(queue, want) if w[0] == "Success")
         elif op < 0.45:
             p = rng.choice(pending); log.append(("prefilter", p["metadata"]["name"]))
             a, b = ref.prefilter(p), dut.prefilter(p)
@@ -578,7 +595,8 @@ def run_event_stream(oracle, new_plugin, seed):
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 8, 17])  # 8 and 17: a throttle is deleted and comes back while pods are reserved on it
 def test_event_stream_chaos(oracle, new_plugin, seed):
-    """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve,
+    """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve, batched
+    PreFilter and queue admission,
     binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, throttle deletes
     and re-creations, namespace relabels and deletes, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
     the end must agree.  (tools/chaos_host.py runs more seeds on the CPU double.)"""

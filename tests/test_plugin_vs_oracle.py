@@ -554,6 +554,11 @@ def run_event_stream(oracle, new_plugin, seed):
             t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
             if t["kind"] == "Throttle":
                 for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+                if t["spec"]["selector"]["selectorTerms"] and rng.random() < 0.15:  # a podSelector that does not convert, at a random position (Q9)
+                    rng.choice(t["spec"]["selector"]["selectorTerms"])["podSelector"] = rng.choice([
+                        {"matchExpressions": [{"key": "team", "operator": "In", "values": []}]},
+                        {"matchExpressions": [{"key": "env", "operator": "Exists", "values": ["a"]}]},
+                        {"matchLabels": {"bad key!": "x"}}])
             throttles[i] = t
             gone.discard(i)
             both(t)

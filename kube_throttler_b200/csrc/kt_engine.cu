@@ -45,11 +45,14 @@ struct DevBuf {
 struct PodStore {
   int64_t n = 0;
   DevBuf labels, req, present, flags, ns;
+  DevBuf roff;              // [Lpad][n] u32: the labels as row offsets into the current selector tables (k_translate_rows)
+  bool roff_valid = false;  // false after a full upload or a table compile; row deltas translate their own rows
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
-    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release();
+    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release();
+    roff_valid = false;
     c_labels.release(); c_req.release(); c_meta.release();
     t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
   }
@@ -205,6 +208,7 @@ int recompile_tables(kt_ctx* c) {
   if ((rc = upload_vec(c, c->d_nsw_off, c->ht.nsw_off))) return rc;
   if ((rc = upload_vec(c, c->d_nsw_idx, c->ht.nsw_idx))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors may be rebuilt right after
+  for (auto& s : c->pods) s.roff_valid = false;  // row offsets point into the tables that were just replaced
   return KT_OK;
 }
 
@@ -241,12 +245,32 @@ TableView table_view(const kt_ctx* c) {
 PodView pod_view(const PodStore& s) {
   PodView v;
   v.labels = s.labels.as<int64_t>();
+  v.roff = s.roff.as<uint32_t>();
   v.req = s.req.as<int64_t>();
   v.present = s.present.as<uint32_t>();
   v.flags = s.flags.as<uint32_t>();
   v.ns = s.ns.as<int32_t>();
   v.n = s.n;
   return v;
+}
+
+// Label columns -> row offsets of the current tables, for every row (rows_dev == nullptr) or for k listed rows.
+int translate_rows(kt_ctx* c, PodStore& s, int64_t k, const int64_t* rows_dev) {
+  const int Lpad = (c->lim.label_slots + 7) & ~7;
+  if (k <= 0) return KT_OK;
+  k_translate_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, rows_dev, table_view(c), Lpad, s.n, s.labels.as<int64_t>(), s.roff.as<uint32_t>());
+  KT_CUDA(c, cudaGetLastError());
+  return KT_OK;
+}
+// Before a pass: the store's row offsets must match its labels and the current tables.
+int ensure_roff(kt_ctx* c, PodStore& s) {
+  if (s.roff_valid || !c->have_throttles) return KT_OK;
+  const int Lpad = (c->lim.label_slots + 7) & ~7;
+  KT_CUDA(c, s.roff.reserve((size_t)Lpad * s.n * 4 + 16));
+  int rc = translate_rows(c, s, s.n, nullptr);
+  if (rc) return rc;
+  s.roff_valid = true;
+  return KT_OK;
 }
 
 // ---- peer exchange window ------------------------------------------------------------------------------
@@ -557,6 +581,7 @@ int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const 
   if ((rc = upload(c, s.flags, flags, (size_t)n))) return rc;
   if ((rc = upload(c, s.ns, ns_id, (size_t)n))) return rc;
   s.n = n;
+  s.roff_valid = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -591,6 +616,7 @@ int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, con
     KT_CUDA(c, cudaGetLastError());
   }
   s.n = n;
+  s.roff_valid = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -618,6 +644,8 @@ int kt_update_pod_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, cons
                                                                      s.labels.as<int64_t>(), s.req.as<int64_t>(), s.present.as<uint32_t>(),
                                                                      s.flags.as<uint32_t>(), s.ns.as<int32_t>());
   KT_CUDA(c, cudaGetLastError());
+  // the delta keeps the store's row offsets current: only the scattered rows are translated again (same stream, after the scatter)
+  if (s.roff_valid && (rc = translate_rows(c, s, k, s.t_rows.as<int64_t>()))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   c->evaluated = false;
   return KT_OK;
@@ -744,6 +772,8 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   KT_CUDA(c, pend.bitmap.reserve((size_t)pend.n * Wp * 4 + 16));
   KT_CUDA(c, c->d_codes.reserve((size_t)pend.n * 2 * Wp * 4 + 16));
   KT_CUDA(c, c->d_admit.reserve((size_t)pend.n + 16));
+  if (do_rec && (rc = ensure_roff(c, run))) return rc;   // no-ops unless rows or tables changed since the last pass
+  if (do_chk && (rc = ensure_roff(c, pend))) return rc;
   const TableView tb = table_view(c);
   int launches = 0;
   const bool tm = c->timing;

@@ -41,7 +41,8 @@ constexpr int kDecidePrefetch = 3;   // match words per warp whose check constan
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
-  const int64_t* labels;    // [L][n]
+  const int64_t* labels;    // [Lpad][n] keyId<<32 | valId (the snapshot as uploaded; re-translated when the tables change)
+  const uint32_t* roff;     // [Lpad][n] the same labels as row offsets into the CURRENT selector tables (k_translate_rows)
   const int64_t* req;       // [R][n]
   const uint32_t* present;  // [n]
   const uint32_t* flags;    // [n]
@@ -336,18 +337,24 @@ __device__ __forceinline__ void translate8(const TableView& tb, const int64_t* _
   translate8_rows(tb, lab, ke, out);
 }
 
-// labels: device columns [Lpad][n] with Lpad = L rounded up to 8.
+// The pass does not translate: label -> row offset is done once per (pod row, table version) by k_translate_rows, at
+// upload / update / table-compile time, and the pass reads the [Lpad][n] u32 offsets (half the bytes of the label column and
+// no dependent dictionary hops on the tile's critical path).
 template <bool REG>
-__device__ __forceinline__ void stage_rows(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, int L, PodRows<REG>& rows) {
+__device__ __forceinline__ void load_rows(const uint32_t* __restrict__ roff, int64_t n, int64_t p, int L, PodRows<REG>& rows) {
+  const uint32_t* rp = roff + p;
   if constexpr (REG) {
-    translate8(tb, labels + p, n, rows.off);
-  } else {
-#pragma unroll 1
-    for (int i0 = 0; i0 < L; i0 += 8) {
-      uint32_t o[8];
-      translate8(tb, labels + (int64_t)i0 * n + p, n, o);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) rows.col[(i0 + k) * rows.stride] = o[k];  // the column has Lpad entries
+    for (int k = 0; k < 8; ++k) {
+      rows.off[k] = __ldg(rp);
+      rp += n;
+    }
+  } else {
+    const int Lpad = (L + 7) & ~7;
+#pragma unroll 4
+    for (int i = 0; i < Lpad; ++i) {
+      rows.col[i * rows.stride] = __ldg(rp);
+      rp += n;
     }
   }
 }
@@ -473,16 +480,14 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
-  // ---- all of the pod row's loads are issued before anything waits on them; the two dependent chains that follow
-  // (labels -> key directory -> value rows, namespace -> word-list offsets -> word indices) are interleaved hop by hop
-  // so that their L2 latencies overlap instead of adding up ----
+  // ---- all of the pod row's loads are issued before anything waits on them; the one dependent chain that follows
+  // (namespace -> word-list offsets -> word indices) runs under their latency ----
   const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
   const int ns = __ldg(&pods.ns[pc]);
   const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-  int64_t lab[8];
-  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+  load_rows<REG>(pods.roff, pods.n, pc, L, rows);
   long long rq[RT > 0 ? RT : 1];
   if constexpr (RT > 0) {
     const int64_t* rp = pods.req + pc;
@@ -507,12 +512,8 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
   int j = 0, hi = 0;
   if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }  // hop 1 of the word list
-  uint4 ke[8];
-  if constexpr (REG) translate8_keys(tb, lab, ke);                                // hop 1 of the labels
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;                          // hop 2 of the word list
   int nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;                  // (the word after it is fetched one step ahead)
-  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);                      // hop 2 of the labels
-  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
 #pragma unroll
@@ -894,8 +895,7 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-  int64_t lab[8];
-  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+  load_rows<REG>(pods.roff, pods.n, pc, L, rows);
   {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
@@ -904,14 +904,9 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
     for (int i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
-  // the two dependent chains (labels -> key directory -> value rows, namespace -> offsets -> word indices) hop by hop
   int lo = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  uint4 ke[8];
-  if constexpr (REG) translate8_keys(tb, lab, ke);
   int wcur = lo < hi ? __ldg(&tb.nsw_idx[lo]) : 0;
-  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);
-  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
@@ -1161,6 +1156,24 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* 
   d_present[row] = present[i];
   d_flags[row] = flags[i];
   d_ns[row] = ns[i];
+}
+
+// Label columns -> row offsets into the CURRENT selector tables: every row (rows == nullptr, k == n) after an upload or a
+// table compile, or the k listed rows after a row delta.  One lane per pod row, coalesced column accesses; the two
+// dictionary hops per label that used to sit on every pass's critical path are paid here, once per change.
+__global__ void __launch_bounds__(256) k_translate_rows(int64_t k, const int64_t* __restrict__ rows, const TableView tb, int Lpad, int64_t n,
+                                                        const int64_t* __restrict__ labels, uint32_t* __restrict__ roff) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const int64_t p = rows ? rows[i] : i;
+  if (p < 0 || p >= n) return;
+#pragma unroll 1
+  for (int i0 = 0; i0 < Lpad; i0 += 8) {
+    uint32_t o[8];
+    translate8(tb, labels + (int64_t)i0 * n + p, n, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) roff[(int64_t)(i0 + j) * n + p] = o[j];
+  }
 }
 
 // Compact transfer rows -> the int64 HBM columns (kt_upload_pods_compact).  One lane per pod row; every column access is

@@ -132,9 +132,10 @@ struct PassSync {
   unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
   unsigned error;        // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
 };
-// Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as a
-// fence, when the awaited value has been seen.  An acquire LOAD per poll would invalidate the SM's L1 on every iteration
-// (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it.
+// Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as one
+// acquire load of the same counter after the awaited value has been seen.  An acquire load per poll would invalidate the
+// SM's L1 on every iteration (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it; an
+// acquire FENCE instead of the final load also waits for the thread's own outstanding memory operations.
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -145,8 +146,16 @@ __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cta_signal(unsigned* counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -180,7 +189,7 @@ __device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsi
 __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target, unsigned* error_flag) {
   if (threadIdx.x == 0) {
     spin_until([&] { return ld_relaxed_gpu(counter) >= target; }, error_flag, 40);
-    fence_acquire_gpu();
+    (void)ld_acquire_gpu(counter);  // the counter only grows within a pass: this reads a value >= target and acquires it
   }
   __syncthreads();
 }
@@ -214,7 +223,7 @@ struct FlagSync {
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
       spin_until([&] { return ld_relaxed_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
-      fence_acquire_gpu();
+      (void)ld_acquire_gpu(&s->rec_done);
       if (px.npeers > 0) {
         if (first_tile) {
           // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
@@ -222,15 +231,16 @@ struct FlagSync {
           __threadfence_system();
           *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
           // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
-          for (int i = 0; i < px.npeers; ++i)
+          for (int i = 0; i < px.npeers; ++i) {
             spin_until([&] { return (int)(ld_relaxed_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
-          fence_acquire_sys();
+            (void)ld_acquire_sys(&px.peer_sync[i]->epoch);  // epochs only grow
+          }
           // ... and tell the other finalize tiles of this rank
           __threadfence();
           *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
         } else {
           spin_until([&] { return (int)(ld_relaxed_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
-          fence_acquire_gpu();
+          (void)ld_acquire_gpu(&px.sync->peers_epoch);
         }
       }
     }

@@ -264,7 +264,7 @@ int translate_rows(kt_ctx* c, PodStore& s, int64_t k, const int64_t* rows_dev) {
 }
 // Before a pass: the store's row offsets must match its labels and the current tables.
 int ensure_roff(kt_ctx* c, PodStore& s) {
-  if (s.roff_valid || !c->have_throttles) return KT_OK;
+  if (!KT_PRETRANSLATED || s.roff_valid || !c->have_throttles) return KT_OK;
   const int Lpad = (c->lim.label_slots + 7) & ~7;
   KT_CUDA(c, s.roff.reserve((size_t)Lpad * s.n * 4 + 16));
   int rc = translate_rows(c, s, s.n, nullptr);

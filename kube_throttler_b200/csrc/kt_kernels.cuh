@@ -30,12 +30,25 @@ namespace kt {
 #ifndef KT_TILE_RECONCILE
 #define KT_TILE_RECONCILE 128
 #endif
+// ---- experiment switches (tools/sweep_variants.sh builds one library per setting; A/B on the same box) ----
+#ifndef KT_WAIT_MODE       // how a wait acquires: 0 relaxed polls + acquire fence, 1 relaxed polls + one acquire load, 2 acquire polls
+#define KT_WAIT_MODE 1
+#endif
+#ifndef KT_PRETRANSLATED   // 1: the pass reads row offsets translated at upload time (k_translate_rows); 0: it translates labels itself
+#define KT_PRETRANSLATED 1
+#endif
+#ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
+#define KT_PASS_THREADS 896
+#endif
+#ifndef KT_SLOT_CAP        // upper bound on the per-CTA accumulator slots (shared memory vs straight-to-HBM atomics)
+#define KT_SLOT_CAP 32
+#endif
 #ifndef KT_HEAVY_PODS
 #define KT_HEAVY_PODS 6
 #endif
 constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one lane per pod)
 constexpr int kTileCheck = 64;       // pending pods per CTA
-constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
+constexpr int kMaxSlots = KT_SLOT_CAP;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kDecidePrefetch = 3;   // match words per warp whose check constants the decide tile stages in one go
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
@@ -156,6 +169,19 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// One poll of a counter, and what closes a successful wait, per KT_WAIT_MODE.
+__device__ __forceinline__ unsigned poll_gpu(const unsigned* p) { return KT_WAIT_MODE == 2 ? ld_acquire_gpu(p) : ld_relaxed_gpu(p); }
+__device__ __forceinline__ unsigned poll_sys(const unsigned* p) { return KT_WAIT_MODE == 2 ? ld_acquire_sys(p) : ld_relaxed_sys(p); }
+__device__ __forceinline__ void acquire_gpu(const unsigned* p) {
+  if (KT_WAIT_MODE == 0) fence_acquire_gpu();
+  else if (KT_WAIT_MODE == 1) (void)ld_acquire_gpu(p);
+}
+__device__ __forceinline__ void acquire_sys(const unsigned* p) {
+  if (KT_WAIT_MODE == 0) fence_acquire_sys();
+  else if (KT_WAIT_MODE == 1) (void)ld_acquire_sys(p);
+}
 __device__ __forceinline__ void cta_signal(unsigned* counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -188,8 +214,8 @@ __device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsi
 }
 __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target, unsigned* error_flag) {
   if (threadIdx.x == 0) {
-    spin_until([&] { return ld_relaxed_gpu(counter) >= target; }, error_flag, 40);
-    (void)ld_acquire_gpu(counter);  // the counter only grows within a pass: this reads a value >= target and acquires it
+    spin_until([&] { return poll_gpu(counter) >= target; }, error_flag, 40);
+    acquire_gpu(counter);  // the counter only grows within a pass: an acquire load here reads a value >= target
   }
   __syncthreads();
 }
@@ -222,8 +248,8 @@ struct FlagSync {
   // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
-      spin_until([&] { return ld_relaxed_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
-      (void)ld_acquire_gpu(&s->rec_done);
+      spin_until([&] { return poll_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
+      acquire_gpu(&s->rec_done);
       if (px.npeers > 0) {
         if (first_tile) {
           // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
@@ -232,15 +258,15 @@ struct FlagSync {
           *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
           // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
           for (int i = 0; i < px.npeers; ++i) {
-            spin_until([&] { return (int)(ld_relaxed_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
-            (void)ld_acquire_sys(&px.peer_sync[i]->epoch);  // epochs only grow
+            spin_until([&] { return (int)(poll_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
+            acquire_sys(&px.peer_sync[i]->epoch);  // epochs only grow
           }
           // ... and tell the other finalize tiles of this rank
           __threadfence();
           *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
         } else {
-          spin_until([&] { return (int)(ld_relaxed_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
-          (void)ld_acquire_gpu(&px.sync->peers_epoch);
+          spin_until([&] { return (int)(poll_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
+          acquire_gpu(&px.sync->peers_epoch);
         }
       }
     }
@@ -345,6 +371,22 @@ __device__ __forceinline__ void translate8(const TableView& tb, const int64_t* _
   load_labels8(lp, n, lab);
   translate8_keys(tb, lab, ke);
   translate8_rows(tb, lab, ke, out);
+}
+
+// labels: device columns [Lpad][n] with Lpad = L rounded up to 8.
+template <bool REG>
+__device__ __forceinline__ void stage_rows(const TableView& tb, const int64_t* __restrict__ labels, int64_t n, int64_t p, int L, PodRows<REG>& rows) {
+  if constexpr (REG) {
+    translate8(tb, labels + p, n, rows.off);
+  } else {
+#pragma unroll 1
+    for (int i0 = 0; i0 < L; i0 += 8) {
+      uint32_t o[8];
+      translate8(tb, labels + (int64_t)i0 * n + p, n, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rows.col[(i0 + k) * rows.stride] = o[k];  // the column has Lpad entries
+    }
+  }
 }
 
 // The pass does not translate: label -> row offset is done once per (pod row, table version) by k_translate_rows, at
@@ -497,7 +539,12 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
+#if KT_PRETRANSLATED
   load_rows<REG>(pods.roff, pods.n, pc, L, rows);
+#else
+  int64_t lab[8];
+  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+#endif
   long long rq[RT > 0 ? RT : 1];
   if constexpr (RT > 0) {
     const int64_t* rp = pods.req + pc;
@@ -522,8 +569,16 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
   int j = 0, hi = 0;
   if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }  // hop 1 of the word list
+#if !KT_PRETRANSLATED
+  uint4 ke[8];
+  if constexpr (REG) translate8_keys(tb, lab, ke);                                // hop 1 of the labels
+#endif
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;                          // hop 2 of the word list
   int nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;                  // (the word after it is fetched one step ahead)
+#if !KT_PRETRANSLATED
+  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);                      // hop 2 of the labels
+  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+#endif
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
 #pragma unroll
@@ -905,7 +960,12 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
+#if KT_PRETRANSLATED
   load_rows<REG>(pods.roff, pods.n, pc, L, rows);
+#else
+  int64_t lab[8];
+  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+#endif
   {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
@@ -916,7 +976,15 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   }
   int lo = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+#if !KT_PRETRANSLATED
+  uint4 ke[8];
+  if constexpr (REG) translate8_keys(tb, lab, ke);
+#endif
   int wcur = lo < hi ? __ldg(&tb.nsw_idx[lo]) : 0;
+#if !KT_PRETRANSLATED
+  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);
+  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+#endif
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
@@ -1108,7 +1176,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
   unsigned long long t_start = 0;

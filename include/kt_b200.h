@@ -218,6 +218,24 @@ int kt_upload_pods(kt_ctx* ctx, int kind, int64_t n,
 int kt_upload_pods_compact(kt_ctx* ctx, int kind, int64_t n, int32_t val_bits, const uint32_t* labels32 /*[L][n]*/,
                            const int32_t* req32 /*[R][n]*/, const int32_t* req_shift /*[R]*/,
                            const uint32_t* present /*[n]*/, const uint32_t* meta /*[n]*/);
+/* The same rows, smaller still (36 bytes per row at L=8, R=4): labels as 16-bit indices into a dictionary of the distinct
+ * (key, value) PAIRS the snapshot uses, presence folded into the meta word.  A packer that interns label pairs (the informer
+ * cache of a real cluster has a few thousand distinct pairs) sends 2 bytes per label slot.
+ *   pairs[n_pairs]   keyId << 32 | valId, n_pairs <= 65535
+ *   labels16[L][n]   index into pairs, 0xFFFF = empty slot
+ *   req32, req_shift as in kt_upload_pods_compact
+ *   meta[n]          ns_id | flags << ns_bits | present << (ns_bits + 3);  ns_bits + 3 + R <= 32, ns_id < 2^ns_bits
+ * Expanded on the device into the int64 columns of kt_upload_pods: HBM layout and results unchanged. */
+typedef struct {
+  int32_t n_pairs;
+  int32_t ns_bits;
+  const int64_t* pairs;      /* [n_pairs] */
+  const uint16_t* labels16;  /* [L][n] */
+  const int32_t* req32;      /* [R][n] */
+  const int32_t* req_shift;  /* [R] */
+  const uint32_t* meta;      /* [n] */
+} kt_packed_pods;
+int kt_upload_pods_packed(kt_ctx* ctx, int kind, int64_t n, const kt_packed_pods* rows);
 /* With async uploads on, kt_upload_pods / kt_upload_pods_compact return as soon as the copies are QUEUED: the caller must
  * keep the host buffers alive and unchanged until kt_sync or any kt_get_* has returned.  Saves one stream
  * synchronisation per upload on the latency-sensitive end-to-end path.  Off by default. */

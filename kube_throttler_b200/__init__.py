@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
 
 EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
-    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
+    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
     "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
@@ -76,6 +76,7 @@ def lib():
         L.kt_upload_pods.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         L.kt_set_async_uploads.argtypes = [vp, C.c_int]
         L.kt_upload_pods_compact.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
+        L.kt_upload_pods_packed.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(abi.PackedPodsStruct)]
         L.kt_update_pod_rows.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.kt_upload_namespaces.argtypes = [vp, C.c_int32, vp]
         L.kt_upload_throttles.argtypes = [vp, C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable)]
@@ -189,6 +190,12 @@ class Engine:
         self._ck(self._L.kt_upload_pods_compact(self._h, kind, cp.n, cp.val_bits, abi.ptr(cp.labels32), abi.ptr(cp.req32), abi.ptr(cp.req_shift),
                                                 abi.ptr(cp.present), abi.ptr(cp.meta)))
         self.n[kind] = cp.n
+
+    def upload_pods_packed(self, kind: int, pk: "abi.PackedPodCols"):
+        """kt_upload_pods_packed: 36 bytes per row (L=8, R=4): 16-bit label-pair indices, presence inside the meta word."""
+        st = pk.struct()
+        self._ck(self._L.kt_upload_pods_packed(self._h, kind, pk.n, C.byref(st)))
+        self.n[kind] = pk.n
 
     def update_pod_rows(self, kind: int, rows: np.ndarray, pods: PodCols):
         rows = np.ascontiguousarray(rows, np.int64)

@@ -48,12 +48,13 @@ struct PodStore {
   DevBuf roff;              // [Lpad][n] u32: the labels as row offsets into the current selector tables (k_translate_rows)
   bool roff_valid = false;  // false after a full upload or a table compile; row deltas translate their own rows
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
+  DevBuf c_pairs;                  // label-pair dictionary of the packed transfer format (kt_upload_pods_packed)
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
     labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release();
     roff_valid = false;
-    c_labels.release(); c_req.release(); c_meta.release();
+    c_labels.release(); c_req.release(); c_meta.release(); c_pairs.release();
     t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
   }
 };
@@ -613,6 +614,45 @@ int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, con
     k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, val_bits, s.c_labels.as<uint32_t>(), s.c_req.as<int32_t>(), sh,
                                                                       s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(), s.req.as<int64_t>(),
                                                                       s.flags.as<uint32_t>(), s.ns.as<int32_t>());
+    KT_CUDA(c, cudaGetLastError());
+  }
+  s.n = n;
+  s.roff_valid = false;
+  c->evaluated = false;
+  if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
+  return KT_OK;
+}
+
+int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* pk) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (n < 0 || !pk || !pk->req_shift || (n > 0 && (!pk->labels16 || !pk->req32 || !pk->meta))) return fail(c, KT_ERR_INVALID, "null packed pod columns");
+  const int L = c->lim.label_slots, R = c->lim.n_resources, Lpad = (L + 7) & ~7;
+  if (pk->n_pairs < 0 || pk->n_pairs > 65535 || (pk->n_pairs > 0 && !pk->pairs)) return fail(c, KT_ERR_INVALID, "n_pairs %d outside 0..65535", pk->n_pairs);
+  if (pk->ns_bits < 1 || pk->ns_bits + 3 + R > 32) return fail(c, KT_ERR_INVALID, "ns_bits %d: ns_bits + 3 + R must fit 32 bits", pk->ns_bits);
+  for (int r = 0; r < R; ++r)
+    if (pk->req_shift[r] < 0 || pk->req_shift[r] > 32) return fail(c, KT_ERR_INVALID, "req_shift[%d] = %d outside 0..32", r, pk->req_shift[r]);
+  int rc = set_device(c);
+  if (rc) return rc;
+  PodStore& s = c->pods[kind];
+  KT_CUDA(c, s.labels.reserve((size_t)Lpad * n * 8 + 16));
+  KT_CUDA(c, s.req.reserve((size_t)R * n * 8 + 16));
+  KT_CUDA(c, s.present.reserve((size_t)n * 4 + 16));
+  KT_CUDA(c, s.flags.reserve((size_t)n * 4 + 16));
+  KT_CUDA(c, s.ns.reserve((size_t)n * 4 + 16));
+  // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
+  KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
+  if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (rc = upload(c, s.c_req, pk->req32, (size_t)R * n)) ||
+      (rc = upload(c, s.c_meta, pk->meta, (size_t)n)))
+    return rc;
+  if (n > 0) {
+    ReqShifts sh{};
+    for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)pk->req_shift[r];
+    k_unpack_packed<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, pk->ns_bits, pk->n_pairs, s.c_pairs.as<int64_t>(), s.c_labels.as<uint16_t>(),
+                                                                        s.c_req.as<int32_t>(), sh, s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(),
+                                                                        s.req.as<int64_t>(), s.present.as<uint32_t>(), s.flags.as<uint32_t>(), s.ns.as<int32_t>());
     KT_CUDA(c, cudaGetLastError());
   }
   s.n = n;

@@ -1219,6 +1219,31 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   }
 }
 
+struct ReqShifts { unsigned char s[32]; };  // per-column left shift of the 32-bit transfer requests (by value, in the launch arguments)
+
+// Packed transfer rows (kt_upload_pods_packed: 16-bit label-pair indices, presence inside the meta word) -> the int64 HBM
+// columns.  One lane per pod row, coalesced; the pair dictionary (a few KB) stays in L1.
+__global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpad, int R, int ns_bits, int n_pairs, const int64_t* __restrict__ pairs,
+                                                       const uint16_t* __restrict__ labels16, const int32_t* __restrict__ req32, const ReqShifts req_shift,
+                                                       const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
+                                                       uint32_t* __restrict__ present, uint32_t* __restrict__ flags, int32_t* __restrict__ ns) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int s = 0; s < Lpad; ++s) {
+    int64_t lab = KT_LABEL_EMPTY;
+    if (s < L) {
+      const uint32_t c = __ldg(&labels16[(int64_t)s * n + p]);
+      if (c != 0xffffu && (int)c < n_pairs) lab = __ldg(&pairs[c]);
+    }
+    labels[(int64_t)s * n + p] = lab;
+  }
+  for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
+  const uint32_t m = __ldg(&meta[p]);
+  ns[p] = (int32_t)(m & ((1u << ns_bits) - 1u));
+  flags[p] = (m >> ns_bits) & 7u;
+  present[p] = (m >> (ns_bits + 3)) & (R >= 32 ? 0xffffffffu : ((1u << R) - 1u));
+}
+
 // Row-level delta: scatter k packed rows into the resident columns (pod informer Add/Update/Delete).
 __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* __restrict__ rows, int L, int R, int64_t n,
                                                       const int64_t* __restrict__ labels, const int64_t* __restrict__ req,
@@ -1256,7 +1281,6 @@ __global__ void __launch_bounds__(256) k_translate_rows(int64_t k, const int64_t
 
 // Compact transfer rows -> the int64 HBM columns (kt_upload_pods_compact).  One lane per pod row; every column access is
 // coalesced.  Lpad - L padding label rows are filled with KT_LABEL_EMPTY here as well.
-struct ReqShifts { unsigned char s[32]; };
 __global__ void __launch_bounds__(256) k_unpack_rows(int64_t n, int L, int Lpad, int R, int val_bits, const uint32_t* __restrict__ labels32,
                                                      const int32_t* __restrict__ req32, const ReqShifts req_shift,
                                                      const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,

@@ -229,3 +229,23 @@ def test_no_gpu_error_contract(kt):
         eng.evaluate(0)
     assert e.value.code == abi.ERR_STATE
     eng.close()
+
+
+def test_packed_upload_equals_wide_upload(kt, oracle):
+    """kt_upload_pods_packed (16-bit label-pair indices, presence in the meta word) expands to exactly the int64 columns
+    kt_upload_pods would have copied: same bits out."""
+    for kw in (dict(config="C3", m=300, n=6000, p=800), dict(config="C2", m=200, n=5000, p=700, L=12), dict(config="C2", m=40, n=70, p=33, R=1, L=3),
+               dict(config="C4", m=500, n=3000, p=400)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        for kind, pods in ((abi.PODS_RUNNING, snap.running), (abi.PODS_PENDING, snap.pending)):
+            pk = abi.packed_pods(pods)
+            assert pk.nbytes < 0.65 * sum(a.nbytes for a in (pods.labels, pods.req, pods.present, pods.flags, pods.ns_id))
+            eng.upload_pods_packed(kind, pk)
+        eng.evaluate(snap.now)
+        got = eng.download()
+        eng.close()
+        want = oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
+        assert_same(snap, got, want)

@@ -362,13 +362,30 @@ def main():
         eng.get_check(codes_b.array, admit_b.array)
         eng.get_reconcile(out)
 
+    # The check result comes back as admit[p] + the NON-ZERO code words (kt_get_check_sparse): what PreFilter needs of it.
+    # A list that overflows falls back to the dense rows inside the timed step.
+    sparse_cap = 4 * snap.pending.n + 1024
+    ent_b = kt.Pinned((sparse_cap, 3), np.uint32)
+    sparse_counts = []
+
+    def fetch_check():
+        n = eng.get_check_sparse(admit_b.array, ent_b.array)
+        sparse_counts.append(n)
+        if n > sparse_cap:
+            eng.get_check(codes_b.array, None)
+
     def e2e_step():
-        if not packed:
-            return e2e_step_compact() if compact else e2e_step_wide()
-        eng.upload_pods_packed(abi.PODS_RUNNING, packed[0])
-        eng.upload_pods_packed(abi.PODS_PENDING, packed[1])
+        if packed:
+            eng.upload_pods_packed(abi.PODS_RUNNING, packed[0])
+            eng.upload_pods_packed(abi.PODS_PENDING, packed[1])
+        elif compact:
+            eng.upload_pods_compact(abi.PODS_RUNNING, compact[0])
+            eng.upload_pods_compact(abi.PODS_PENDING, compact[1])
+        else:
+            eng.upload_pods(abi.PODS_RUNNING, hr)
+            eng.upload_pods(abi.PODS_PENDING, hp)
         eng.evaluate(snap.now)
-        eng.get_check(codes_b.array, admit_b.array)
+        fetch_check()
         eng.get_reconcile(out)
 
     # what the host link of this box can do at all (pinned, one 64 MiB copy each way): the floor of any e2e number
@@ -402,9 +419,14 @@ def main():
 
     e2e_wide_value = time_e2e(e2e_step_wide)
     eng.set_async_uploads(True)  # the pinned columns live for the whole run: no need to wait for each copy before queueing the next
-    e2e_compact_value = time_e2e(e2e_step_compact) if compact and packed else None
+    e2e_compact_value = time_e2e(e2e_step_compact) if compact else None
+    eng.set_sparse_check(sparse_cap)
     e2e_value = time_e2e(e2e_step)
+    eng.set_sparse_check(0)
     eng.set_async_uploads(False)
+    d2h_dense = d2h
+    n_sparse = max(sparse_counts) if sparse_counts else 0
+    d2h = d2h - codes_b.array.nbytes + (12 * min(n_sparse + n_sparse // 4 + 256, sparse_cap) + 4 if n_sparse <= sparse_cap else 12 * sparse_cap + 4 + codes_b.array.nbytes)  # the fetch asks for the last count + 25 % + 256 entries
     admit_frac = float(admit_b.array.mean())
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded, ~seconds ----------------
@@ -430,9 +452,10 @@ def main():
                        "admit_fraction": admit_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
-                    "path": ("kt_upload_pods_packed x2" if packed else "kt_upload_pods_compact x2" if compact else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check + kt_get_reconcile (pinned host buffers)",
+                    "path": ("kt_upload_pods_packed x2" if packed else "kt_upload_pods_compact x2" if compact else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)",
+                    "sparse_check_entries": n_sparse,
                     "wide_int64_upload": {"value": e2e_wide_value, "h2d_bytes_per_step": h2d_wide},
-                    "compact_upload": {"value": e2e_compact_value, "h2d_bytes_per_step": h2d_compact},
+                    "compact_upload_dense_codes": {"value": e2e_compact_value, "h2d_bytes_per_step": h2d_compact, "d2h_bytes_per_step": d2h_dense},
                     "host_link_gbs": link, "link_floor_value": checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world},
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_s_timed_region": t_wall,

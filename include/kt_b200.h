@@ -282,6 +282,16 @@ int kt_get_match_rows(kt_ctx* ctx, int kind, int64_t k, const int64_t* rows, uin
  * admit[p] = 1 iff every affected throttle is KT_CHECK_NOT_THROTTLED (plugin.go:177-180).
  * Either pointer may be NULL. */
 int kt_get_check(kt_ctx* ctx, uint32_t* codes /*[p][2*words_per_row]*/, uint8_t* admit /*[p]*/);
+/* The same result without the zeros.  A PreFilter caller needs the admit bit of every pod and, for the rejected ones, which
+ * throttles said what (plugin.go:182-213): at C2 that is ~10^4 non-zero code words out of 6.4*10^5.
+ * kt_set_sparse_check(cap_entries > 0) makes every later pass ALSO append each non-zero code word to a device list of at most
+ * cap_entries entries (0 switches it off again; the dense rows are always written).  kt_get_check_sparse copies admit[p]
+ * and the entries {pending row, word index j in [0, 2*words_per_row), codes word}: the word is what kt_get_check would have
+ * delivered at codes[row*2*words_per_row + j].  Entries are unordered.  *count is the number of non-zero words of the pass;
+ * when it exceeds cap (or the device capacity) only the first min(cap, cap_entries) were delivered and the caller should
+ * read the dense rows instead. */
+int kt_set_sparse_check(kt_ctx* ctx, int64_t cap_entries);
+int kt_get_check_sparse(kt_ctx* ctx, uint8_t* admit /*[p]*/, uint32_t* entries /*[cap][3]*/, int64_t cap, int64_t* count);
 int kt_get_timing(kt_ctx* ctx, kt_timing* out);
 
 /* ---- host-only introspection (no device needed) -------------------------------- */

@@ -44,7 +44,7 @@ EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
     "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
@@ -77,6 +77,8 @@ def lib():
         L.kt_set_async_uploads.argtypes = [vp, C.c_int]
         L.kt_upload_pods_compact.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
         L.kt_upload_pods_packed.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(abi.PackedPodsStruct)]
+        L.kt_set_sparse_check.argtypes = [vp, C.c_int64]
+        L.kt_get_check_sparse.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.kt_update_pod_rows.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.kt_upload_namespaces.argtypes = [vp, C.c_int32, vp]
         L.kt_upload_throttles.argtypes = [vp, C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable)]
@@ -264,6 +266,17 @@ class Engine:
 
     def get_check(self, codes: Optional[np.ndarray], admit: Optional[np.ndarray]):
         self._ck(self._L.kt_get_check(self._h, abi.ptr(codes), abi.ptr(admit)))
+
+    def set_sparse_check(self, cap_entries: int):
+        """Later passes also append every non-zero code word to a device list (0: off)."""
+        self._ck(self._L.kt_set_sparse_check(self._h, cap_entries))
+
+    def get_check_sparse(self, admit: Optional[np.ndarray], entries: np.ndarray) -> int:
+        """admit[p] and the non-zero code words as rows {pending row, word index, codes}; returns their total number
+        (more than entries.shape[0]: read the dense rows with get_check instead)."""
+        n = C.c_int64(0)
+        self._ck(self._L.kt_get_check_sparse(self._h, abi.ptr(admit), abi.ptr(entries), entries.shape[0], C.byref(n)))
+        return int(n.value)
 
     def get_reconcile(self, out: PassResult):
         rec = out.reconcile_out()

@@ -150,6 +150,10 @@ struct kt_ctx {
   size_t o_off[8] = {};
   bool async_uploads = false;  // kt_set_async_uploads
   DevBuf d_codes, d_admit;
+  DevBuf d_sparse;              // kt_set_sparse_check: {count u32, pad to 16 B, entries [cap][3] u32}
+  uint32_t sparse_cap = 0;      // 0: off
+  uint32_t sparse_guess = 1024; // entries fetched together with the count (adapts to the last pass)
+  uint32_t* h_sparse_count = nullptr;  // pinned
   bool evaluated = false;
   // multi-GPU
   void* comm = nullptr;
@@ -396,12 +400,21 @@ cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, 
   return launch(c, k_reconcile<TPC, B, RT, REG>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, S, REG, kTileReconcile), false, pv, tb, L, R, S,
                 c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), c->d_part.as<unsigned long long>());
 }
+SparseOut sparse_view(const kt_ctx* c) {
+  SparseOut sp{nullptr, nullptr, 0};
+  if (c->sparse_cap) {
+    sp.count = c->d_sparse.as<uint32_t>();
+    sp.ent = c->d_sparse.as<uint32_t>() + 4;
+    sp.cap = c->sparse_cap;
+  }
+  return sp;
+}
 template <int TPC, int B, bool REG>
 cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
   return launch(c, k_check<TPC, B, REG>, blocks, kTileCheck, check_smem_bytes(L, R, REG, kTileCheck), pdl, pv, tb, L, R,
                 (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
-                c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>());
+                c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>(), sparse_view(c));
 }
 template <int TPC, int B, int RT, bool REG>
 cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
@@ -492,6 +505,8 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
                    &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_sparse_count) cudaFreeHost(c->h_sparse_count);
+  c->d_sparse.release();
   for (DevBuf* b : all) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -872,6 +887,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     a.run = pod_view(run); a.pend = pod_view(pend); a.tb = tb; a.tv = tv; a.out = ov; a.px = px;
     a.run_bitmap = run.bitmap.as<uint32_t>(); a.pend_bitmap = pend.bitmap.as<uint32_t>(); a.codes = c->d_codes.as<uint32_t>();
     a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = px.sync;
+    a.sparse = sparse_view(c);
     a.now = (long long)now; a.eval_flags = flags; a.L = c->lim.label_slots; a.R = R; a.S = reconcile_slots(c); a.G = G;
     a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
     a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
@@ -920,6 +936,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   if (do_chk && pend.n > 0) {
     const PodView pv = pod_view(pend);
     const unsigned blocks = (unsigned)((pend.n + kTileCheck - 1) / kTileCheck);
+    if (c->sparse_cap) KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 4, c->stream));  // k_check appends; nobody in it can clear first
     KT_CUDA(c, dispatch_check(c, pv, tb, blocks, /*pdl=*/!tm && M > 0));
     ++launches;
   }
@@ -1019,6 +1036,52 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   if (codes && P > 0) KT_CUDA(c, cudaMemcpyAsync(codes, c->d_codes.p, (size_t)P * 2 * c->ht.Wp * 4, cudaMemcpyDeviceToHost, c->stream));
   if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_set_sparse_check(kt_ctx* c, int64_t cap_entries) {
+  if (!c || cap_entries < 0 || cap_entries > (int64_t)1 << 28) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = set_device(c);
+  if (rc) return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->sparse_cap = 0;
+  if (cap_entries == 0) return KT_OK;
+  KT_CUDA(c, c->d_sparse.reserve(16 + (size_t)cap_entries * 12));
+  KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 16, c->stream));
+  if (!c->h_sparse_count) KT_CUDA(c, cudaHostAlloc((void**)&c->h_sparse_count, 16, cudaHostAllocDefault));
+  c->sparse_cap = (uint32_t)cap_entries;
+  c->evaluated = false;  // the list belongs to a pass that ran with it switched on
+  return KT_OK;
+}
+
+int kt_get_check_sparse(kt_ctx* c, uint8_t* admit, uint32_t* entries, int64_t cap, int64_t* count) {
+  if (!c || !count || cap < 0 || (cap > 0 && !entries)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check_sparse before kt_evaluate");
+  if (!c->sparse_cap) return fail(c, KT_ERR_STATE, "kt_get_check_sparse without kt_set_sparse_check");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
+  const int64_t P = c->pods[KT_PODS_PENDING].n;
+  const int64_t room = cap < (int64_t)c->sparse_cap ? cap : (int64_t)c->sparse_cap;
+  // one round trip in the common case: the count and as many entries as the last pass produced (plus slack) together
+  int64_t first = c->sparse_guess < room ? c->sparse_guess : room;
+  if (P == 0) first = 0;
+  if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaMemcpyAsync(c->h_sparse_count, c->d_sparse.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (first > 0) KT_CUDA(c, cudaMemcpyAsync(entries, c->d_sparse.as<uint32_t>() + 4, (size_t)first * 12, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int64_t total = P > 0 ? (int64_t)*c->h_sparse_count : 0;
+  *count = total;  // may exceed cap / the device capacity: the caller then reads the dense rows (kt_get_check)
+  const int64_t have = total < room ? total : room;
+  if (have > first) {
+    KT_CUDA(c, cudaMemcpyAsync(entries + 3 * first, c->d_sparse.as<uint32_t>() + 4 + 3 * first, (size_t)(have - first) * 12, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int64_t g = total + total / 4 + 256;
+  if (g > (int64_t)c->sparse_cap) g = c->sparse_cap;
+  c->sparse_guess = (uint32_t)g;
   return KT_OK;
 }
 

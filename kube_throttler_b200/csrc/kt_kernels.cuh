@@ -944,6 +944,24 @@ __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, 
   return match > decide ? match : decide;
 }
 
+// Optional sparse copy of the check result (kt_set_sparse_check): every NON-ZERO 32-bit code word is also appended to a list
+// as {pending row, word index within the row's 2*Wp code words, the 16 codes}.  At C2 that is ~10k entries (116 KB) where the
+// dense code rows are 2.56 MB, which is what a host that only needs the reasons of the rejected pods wants to download.
+// count keeps counting beyond cap (the host then falls back to the dense rows); entries are unordered.
+struct SparseOut {
+  uint32_t* count;  // nullptr: off
+  uint32_t* ent;    // [cap][3]
+  uint32_t cap;
+};
+__device__ __forceinline__ void sparse_append(const SparseOut& sp, uint32_t row, uint32_t widx, uint32_t word) {
+  const uint32_t i = atomicAdd(sp.count, 1u);
+  if (i < sp.cap) {
+    sp.ent[3 * (size_t)i] = row;
+    sp.ent[3 * (size_t)i + 1] = widx;
+    sp.ent[3 * (size_t)i + 2] = word;
+  }
+}
+
 // Phase 1 of the pending check, no dependency on the running pods: selector match of TILE pending pods ->
 // affectedThrottles bitmap rows (throttle_controller.go:248-269); also clears the tile's code rows.
 template <int TPC, int B, bool REG, int TILE>
@@ -1002,7 +1020,8 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 template <int TILE, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ check,
                                                   const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync) {
+                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
+                                                  const SparseOut sp = SparseOut{nullptr, nullptr, 0}) {
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
   unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][KS][32][rec]
@@ -1097,6 +1116,10 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     }
     if (c0) codes[p * 2 * Wp + 2 * w] = c0;
     if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+    if (sp.count) {
+      if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
+      if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
+    }
   };
   auto stage = [&](uint32_t any, int w, unsigned char* recs) {  // lane = throttle
     if ((any >> lane) & 1) {
@@ -1137,11 +1160,11 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
 template <int TPC, int B, bool REG>
 __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
                                                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                      unsigned char* __restrict__ admit) {
+                                                      unsigned char* __restrict__ admit, SparseOut sparse /* count zeroed by the host before the launch */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
   __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
-  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{});
+  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1162,6 +1185,7 @@ struct PassArgs {
   uint32_t* codes;
   unsigned char* admit;
   unsigned char* check;
+  SparseOut sparse;
   PassSync* sync;
   long long now;
   uint32_t eval_flags;
@@ -1188,6 +1212,8 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   unsigned tile = s_ticket;
   const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
   if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+    // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
+    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
   } else if ((tile -= a.n_chk) < a.n_rec) {
@@ -1197,7 +1223,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   } else if ((tile -= a.n_rec) < a.n_fin) {
     finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();

@@ -249,3 +249,37 @@ def test_packed_upload_equals_wide_upload(kt, oracle):
         eng.close()
         want = oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
         assert_same(snap, got, want)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_sparse_check_equals_nonzero_words_of_the_dense_rows(kt, oracle, fused):
+    """kt_get_check_sparse: exactly the non-zero code words of kt_get_check, each once, plus the same admit bits; a list
+    that is too small reports the true count so that the caller can fall back to the dense rows."""
+    for kw in (dict(config="C2", m=300, n=8000, p=1500), dict(config="C3", m=200, n=3000, p=700), dict(config="C2", m=40, n=70, p=33, R=1, L=3)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        eng.set_sparse_check(4 * snap.pending.n + 64)
+        if not fused:
+            eng.enable_timing(True)  # per-kernel events: the three chained kernels instead of the one fused launch
+        for _ in range(2):  # twice: the counter is cleared by the pass itself
+            eng.evaluate(snap.now)
+            got = eng.download()
+            Wp = got.words_per_row
+            ent = np.zeros((4 * snap.pending.n + 64, 3), np.uint32)
+            admit = np.zeros(snap.pending.n, np.uint8)
+            cnt = eng.get_check_sparse(admit, ent)
+            dense = got.codes.reshape(snap.pending.n, 2 * Wp)
+            rows, widx = np.nonzero(dense)
+            assert cnt == rows.shape[0]
+            want = sorted(zip(rows.tolist(), widx.tolist(), dense[rows, widx].tolist()))
+            assert sorted(map(tuple, ent[:cnt].tolist())) == want
+            assert np.array_equal(admit, got.admit)
+        small = np.zeros((max(cnt // 2, 1), 3), np.uint32)
+        assert eng.get_check_sparse(None, small) == cnt  # truncated: the count still says how many there are
+        eng.set_sparse_check(0)
+        eng.evaluate(snap.now)
+        with pytest.raises(Exception):
+            eng.get_check_sparse(None, small)
+        eng.close()

@@ -176,6 +176,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def pin_to_gpu_local_cpus(dev_index):
+    """Pinned buffers are placed on the NUMA node of the allocating thread: keep this process on the CPUs that sit next to
+    its GPU (sysfs local_cpulist of the PCI function), as a deployment would.  Best effort; returns what was done."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(dev_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local cpulist)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} GPU-local cpus"
+    except Exception as e:  # noqa: BLE001 -- diagnostics only
+        return f"unchanged ({type(e).__name__})"
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,6 +219,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    host_affinity = pin_to_gpu_local_cpus(local_rank)
     # NCCL prints its version banner on stdout at communicator creation; stdout belongs to the ONE JSON line of rank 0,
     # so file descriptor 1 points at stderr until the communicators exist
     saved_stdout = None
@@ -343,8 +367,17 @@ def main():
         packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), pin(c.req32), pin(c.req_shift), pin(c.meta)) for c in (pr, pp_))
     except ValueError:
         pass
+    packed_wc = None
     if packed:
         h2d = sum(c.nbytes for c in packed)
+
+        def pin_wc(a):  # write-combined: the CPU only writes these, the device reads them
+            b = kt.Pinned(a.shape, a.dtype, upload_only=True)
+            b.array[...] = a
+            pinned.append(b)
+            return b.array
+
+        packed_wc = tuple(abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), pin_wc(c.req32), pin(c.req_shift), pin_wc(c.meta)) for c in packed)
     elif compact:
         h2d = h2d_compact
 
@@ -374,10 +407,13 @@ def main():
         if n > sparse_cap:
             eng.get_check(codes_b.array, None)
 
+    use_wc = [False]
+
     def e2e_step():
         if packed:
-            eng.upload_pods_packed(abi.PODS_RUNNING, packed[0])
-            eng.upload_pods_packed(abi.PODS_PENDING, packed[1])
+            src = packed_wc if use_wc[0] else packed
+            eng.upload_pods_packed(abi.PODS_RUNNING, src[0])
+            eng.upload_pods_packed(abi.PODS_PENDING, src[1])
         elif compact:
             eng.upload_pods_compact(abi.PODS_RUNNING, compact[0])
             eng.upload_pods_compact(abi.PODS_PENDING, compact[1])
@@ -422,6 +458,12 @@ def main():
     e2e_compact_value = time_e2e(e2e_step_compact) if compact else None
     eng.set_sparse_check(sparse_cap)
     e2e_value = time_e2e(e2e_step)
+    e2e_pinned_value, upload_memory = e2e_value, "pinned"
+    if packed_wc:
+        use_wc[0] = True
+        e2e_wc_value = time_e2e(e2e_step)
+        if e2e_wc_value > e2e_value:
+            e2e_value, upload_memory = e2e_wc_value, "pinned write-combined"
     eng.set_sparse_check(0)
     eng.set_async_uploads(False)
     d2h_dense = d2h
@@ -453,7 +495,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
                     "path": ("kt_upload_pods_packed x2" if packed else "kt_upload_pods_compact x2" if compact else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)",
-                    "sparse_check_entries": n_sparse,
+                    "sparse_check_entries": n_sparse, "upload_memory": upload_memory, "pinned_upload_value": e2e_pinned_value, "host_affinity": host_affinity,
                     "wide_int64_upload": {"value": e2e_wide_value, "h2d_bytes_per_step": h2d_wide},
                     "compact_upload_dense_codes": {"value": e2e_compact_value, "h2d_bytes_per_step": h2d_compact, "d2h_bytes_per_step": d2h_dense},
                     "host_link_gbs": link, "link_floor_value": checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world},

@@ -196,6 +196,10 @@ int kt_enable_trace(kt_ctx* ctx, int on);
 int64_t kt_get_trace(kt_ctx* ctx, uint64_t* rows /*[cap][8]*/, int64_t cap, uint32_t roles[4]);
 /* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost). */
 void* kt_host_alloc(size_t bytes);
+/* The same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only ever WRITES, front to back, and the device
+ * reads (upload columns).  The device's reads need no cache snooping on the host, which some platforms reward with a faster
+ * host-to-device link; CPU reads of such memory are very slow.  Freed with kt_host_free. */
+void* kt_host_alloc_upload(size_t bytes);
 void kt_host_free(void* p);
 
 /* ---- snapshot upload (host -> HBM) --------------------------------------------- */

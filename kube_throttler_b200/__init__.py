@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
 
 EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
-    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
+    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_alloc_upload", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
     "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
@@ -71,6 +71,8 @@ def lib():
         L.kt_get_trace.restype = C.c_int64
         L.kt_host_alloc.argtypes = [C.c_size_t]
         L.kt_host_alloc.restype = vp
+        L.kt_host_alloc_upload.argtypes = [C.c_size_t]
+        L.kt_host_alloc_upload.restype = vp
         L.kt_host_free.argtypes = [vp]
         L.kt_host_free.restype = None
         L.kt_upload_pods.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
@@ -104,11 +106,11 @@ class Pinned:
     """Pinned (cudaHostAlloc) host buffer exposed as a numpy array: `.array`.  Keep the object alive
     while the array is in use."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, upload_only: bool = False):
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         nbytes = max(count * dtype.itemsize, 1)
-        self._ptr = lib().kt_host_alloc(nbytes)
+        self._ptr = (lib().kt_host_alloc_upload if upload_only else lib().kt_host_alloc)(nbytes)  # upload_only: write-combined
         if not self._ptr:
             raise KtError(abi.ERR_CUDA, "kt_host_alloc failed")
         self._buf = (C.c_char * nbytes).from_address(self._ptr)

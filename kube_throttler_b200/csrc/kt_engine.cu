@@ -570,6 +570,11 @@ void* kt_host_alloc(size_t bytes) {
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
   return p;
 }
+void* kt_host_alloc_upload(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined) != cudaSuccess) return nullptr;
+  return p;
+}
 void kt_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }

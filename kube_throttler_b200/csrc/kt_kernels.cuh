@@ -40,6 +40,9 @@ namespace kt {
 #ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
 #define KT_PASS_THREADS 896
 #endif
+#ifndef KT_DECIDE_WORDS    // match words per warp whose check constants a decide tile stages at once: its shared memory (10 KB per word at
+#define KT_DECIDE_WORDS 3  // R=4) is what every CTA of the fused pass is launched with, i.e. it bounds the reconcile tiles' residency too
+#endif
 #ifndef KT_SLOT_CAP        // upper bound on the per-CTA accumulator slots (shared memory vs straight-to-HBM atomics)
 #define KT_SLOT_CAP 32
 #endif
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 __host__ __device__ inline int decide_stage_words(int R, int tile) {
   const size_t per_word = (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);
   int ks = (int)((40u << 10) / per_word);
-  return ks < 1 ? 1 : (ks > 3 ? 3 : ks);
+  return ks < 1 ? 1 : (ks > KT_DECIDE_WORDS ? KT_DECIDE_WORDS : ks);
 }
 __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
   const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                                                        // check_match_tile

@@ -286,6 +286,7 @@ struct ThrottleObj {
   bool st_thr_req_nil = true;
   ResAmount st_used;
   bool live = false;
+  bool metrics_pending = false;  // reconciled since its gauges were last written into the registry (see record_metrics)
   std::string nn() const { return ns + "/" + name; }
   std::string selector_error() const {  // the first podSelector that LabelSelectorAsSelector rejects
     for (auto& t : terms)
@@ -369,19 +370,31 @@ struct kth_plugin {
   int column(const std::string& rname) {
     int c = col_dict.find(rname);
     if (c >= 0) return c;
+    // refuse BEFORE interning: the object that brought the name is rejected, the plugin stays usable
+    if ((int)cols.size() >= KT_MAX_RESOURCES) fail("more than " + std::to_string(KT_MAX_RESOURCES) + " distinct resource names (" + rname + ")");
     c = (int)col_dict.id(rname);
     ResourceColumn rc;
     rc.name = rname;
     rc.scale_exp = rname == "cpu" ? -3 : 0;  // milli-cpu, whole units / bytes elsewhere; refined on demand
     cols.push_back(rc);
-    if ((int)cols.size() > KT_MAX_RESOURCES) fail("more than 31 distinct resource names");
     if (ctx && (int)cols.size() > lim.n_resources) drop_engine();
     return c;
+  }
+  // An object that is refused (a limit, a malformed quantity) must not leave resource names behind that only it mentioned:
+  // kth_apply undoes the interning that happened since it started.
+  void rollback_columns(size_t n0) {
+    if (cols.size() > n0) totals_valid = false;
+    while (cols.size() > n0) {
+      col_dict.ids.erase(col_dict.names.back());
+      col_dict.names.pop_back();
+      cols.pop_back();
+    }
   }
   void note_quantity(int c, const Quantity& q) {
     const int need = kt::quantity_min_exp(q);
     if (need < cols[c].scale_exp) {  // a finer value than the column holds: every row of the column is re-packed
       cols[c].scale_exp = need;
+      totals_valid = false;  // the running column totals were counted in the coarser unit
       pods_full_upload = throttles_dirty = status_dirty = reserved_dirty = true;
     }
     if (q.format == Quantity::BinarySI) cols[c].format = Quantity::BinarySI;
@@ -454,8 +467,8 @@ struct kth_plugin {
     p.request = pod_request_resource_list(spec);
     p.live = true;
     if ((int)p.labels.size() > max_labels) {
+      if ((int)p.labels.size() > KT_MAX_LABEL_SLOTS) fail("pod " + p.nn() + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS) + " labels");
       max_labels = (int)p.labels.size();
-      if (max_labels > KT_MAX_LABEL_SLOTS) fail("pod " + p.nn() + " has more than 32 labels");
       if (ctx && max_labels > lim.label_slots) drop_engine();
     }
     return p;
@@ -469,11 +482,11 @@ struct kth_plugin {
   }
   bool should_count_in(const PodObj& p) const { return p.scheduler_name == target_scheduler && !p.node_name.empty(); }
 
-  int32_t ns_id(const std::string& name) {
-    const uint32_t id = ns_dict.id(name);
+  int32_t ns_id(const std::string& ns_name) {
+    const uint32_t id = ns_dict.id(ns_name);
     if (namespaces.size() <= id) {
       namespaces.resize(id + 1);
-      namespaces[id].name = name;
+      namespaces[id].name = ns_name;
       namespaces_dirty = throttles_dirty = true;  // Throttle namespace equality is part of the compiled tables
     }
     return (int32_t)id;
@@ -554,17 +567,34 @@ struct kth_plugin {
       dirty_rows.clear();
     }
   }
-  // int64 adds (and the NCCL sum) wrap silently: prove per column that they cannot (DESIGN.md "Quantity columns")
+  // int64 adds (and the NCCL sum) wrap silently: prove per column that they cannot (DESIGN.md "Quantity columns").
+  // The per-column totals of |value| are kept up to date by the pod events (totals_add), so a sync after a few events does
+  // not walk the whole pod table again; they are recounted only after a column changed its unit.
+  std::vector<__int128> col_abs;
+  bool totals_valid = false;
+  void totals_add(const PodObj& p, int sign) {
+    if (!totals_valid || !p.live) return;
+    if (col_abs.size() < cols.size()) col_abs.resize(cols.size(), 0);
+    for (auto& kv : p.request) {
+      bool ok;
+      const int64_t v = kt::quantity_at_scale(kv.second, cols[(size_t)kv.first].scale_exp, &ok);
+      if (!ok) { totals_valid = false; return; }  // the full recount reports it
+      col_abs[(size_t)kv.first] += (v < 0 ? -(__int128)v : (__int128)v) * sign;
+    }
+  }
   void overflow_check() {
-    std::vector<__int128> total(cols.size(), 0);
-    for (auto& p : pods)
-      if (p.live)
-        for (auto& kv : p.request) {
-          const int64_t v = at_scale(kv.first, kv.second);
-          total[kv.first] += v < 0 ? -(__int128)v : v;
-        }
-    for (size_t c = 0; c < cols.size(); ++c)
-      if (total[c] >= ((__int128)1 << 62)) fail("resource '" + cols[c].name + "': the column sum can overflow int64 at scale 1e" + std::to_string(cols[c].scale_exp));
+    if (!totals_valid) {
+      col_abs.assign(cols.size(), 0);
+      for (auto& p : pods)
+        if (p.live)
+          for (auto& kv : p.request) {
+            const int64_t v = at_scale(kv.first, kv.second);
+            col_abs[(size_t)kv.first] += v < 0 ? -(__int128)v : v;
+          }
+      totals_valid = true;
+    }
+    for (size_t c = 0; c < cols.size() && c < col_abs.size(); ++c)
+      if (col_abs[c] >= ((__int128)1 << 62)) fail("resource '" + cols[c].name + "': the column sum can overflow int64 at scale 1e" + std::to_string(cols[c].scale_exp));
   }
 
   void sync_namespaces() {
@@ -801,6 +831,10 @@ struct kth_plugin {
   // ---- gauges (throttle_metrics.go / clusterthrottle_metrics.go / metrics_recorder.go) --------------------------
   // A GaugeVec keeps every series it was ever given: reconcile records the throttle it just handled, nothing is deleted
   // when a throttle or one of its resource names goes away.  family -> (label pairs sorted by name, rendered) -> value.
+  // Rendering ~20 label sets per throttle is 3 us of string work -- a hundred times the device pass for 1000 throttles -- so
+  // reconcile only MARKS the throttle (metrics_pending); the registry is brought up to date when somebody looks at it
+  // (kth_metrics) and, so that the values are the ones of the last reconcile and nothing newer, right before the object
+  // changes under it (a spec or status update, a delete).
   std::map<std::string, std::map<std::string, double>> gauges;
   static std::string label_escape(const std::string& v) {
     std::string o;
@@ -876,6 +910,10 @@ struct kth_plugin {
       return out + digits.substr(0, (size_t)exp + 1) + "." + digits.substr((size_t)exp + 1);
     }
     return out + "0." + std::string((size_t)(-exp - 1), '0') + digits;
+  }
+  void flush_metrics() {
+    for (auto& o : throttles)
+      if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }
   }
   std::string metrics_text() const {
     static const std::pair<const char*, const char*> kHelp[] = {
@@ -976,7 +1014,7 @@ struct kth_plugin {
       o.st_thr_req_nil = thr_nil;
       if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
       o.st_used = nu;
-      record_metrics(o);  // both branches of the status comparison record (throttle_controller.go:159,187)
+      o.metrics_pending = true;  // both branches of the status comparison record (throttle_controller.go:159,187); see record_metrics
       if (status_changed) changed.push_back(o.nn());
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
@@ -1226,35 +1264,50 @@ struct kth_plugin {
       else { row = (int64_t)pods.size(); pods.emplace_back(); }
       p.row = row;
       pod_index[p.nn()] = row;
+      totals_add(p, +1);
       pods[(size_t)row] = std::move(p);
       dirty_rows.insert(row);
       return;
     }
-    PodObj& old = pods[(size_t)it->second];
-    p.row = old.row;
-    // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
-    // then the pod's reservation moves from (old \ new) to (new \ old) throttles
-    const bool relevant = should_count_in(old) || should_count_in(p);
-    if (relevant && !throttles.empty() && old.labels != p.labels) {
-      PendingResult r = check_pending({old, p}, 0);
-      for (int kind = 0; kind < 2; ++kind) {
-        if (!controller_error(old, r, 0, kind).empty() || !controller_error(p, r, 1, kind).empty()) continue;  // HandleError + return
-        const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
-        for (int t : a)
-          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), p.nn()); reserved_dirty = true; }
-        for (int t : b)
-          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), p); reserved_dirty = true; }
-      }
-    }
-    const int64_t row = old.row;
+    // The informer's copy is replaced FIRST: the pass below only asks which throttles the old and the new pod match, which
+    // does not depend on the running rows, and an update that repairs a snapshot the packer refuses (column overflow) must
+    // not be refused for it.
+    const int64_t row = it->second;
+    const PodObj old = pods[(size_t)row];
+    p.row = row;
+    totals_add(old, -1);
+    totals_add(p, +1);
     pods[(size_t)row] = std::move(p);
     dirty_rows.insert(row);
+    const PodObj& cur = pods[(size_t)row];
+    // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
+    // then the pod's reservation moves from (old \ new) to (new \ old) throttles
+    const bool relevant = should_count_in(old) || should_count_in(cur);
+    if (relevant && !throttles.empty() && old.labels != cur.labels) {
+      const PodObj now = cur;  // check_pending may re-create the engine; keep value copies
+      PendingResult r = check_pending({old, now}, 0);
+      for (int kind = 0; kind < 2; ++kind) {
+        if (!controller_error(old, r, 0, kind).empty() || !controller_error(now, r, 1, kind).empty()) continue;  // HandleError + return
+        const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
+        for (int t : a)
+          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), now.nn()); reserved_dirty = true; }
+        for (int t : b)
+          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), now); reserved_dirty = true; }
+      }
+    }
   }
   void delete_pod(const std::string& ns, const std::string& pname) {
     auto it = pod_index.find(ns + "/" + pname);
     if (it == pod_index.end()) return;
     const int64_t row = it->second;
-    PodObj old = pods[(size_t)row];
+    const PodObj old = pods[(size_t)row];
+    // the row goes first (see apply_pod): a delete that repairs a refused snapshot must not be refused for it
+    totals_add(old, -1);
+    pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
+    pods[(size_t)row].row = row;
+    pod_index.erase(it);
+    free_rows.push_back(row);
+    dirty_rows.insert(row);
     // DeleteFunc (:509-515): a scheduled pod that disappears is un-reserved from its affected throttles
     if (should_count_in(old) && !old.node_name.empty() && !throttles.empty()) {
       PendingResult r = check_pending({old}, 0);
@@ -1264,22 +1317,19 @@ struct kth_plugin {
           if (cache[kind].remove(throttles[(size_t)t].nn(), old.nn())) reserved_dirty = true;
       }
     }
-    pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
-    pods[(size_t)row].row = row;
-    pod_index.erase(it);
-    free_rows.push_back(row);
-    dirty_rows.insert(row);
   }
   void apply_namespace(const Node& v) {
     const std::string nm = v["metadata"]["name"].str();
+    const Node& lab = v["metadata"]["labels"];
+    // refuse before touching any state: the object is rejected, the plugin stays usable
+    if ((int)lab.obj.size() > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS) + " labels");
     const int32_t id = ns_id(nm);
     NamespaceObj& n = namespaces[(size_t)id];
     n.exists = true;
     n.labels.clear();
-    for (auto& kv : v["metadata"]["labels"].obj) n.labels.emplace_back(kv.first, kv.second->str());
+    for (auto& kv : lab.obj) n.labels.emplace_back(kv.first, kv.second->str());
     if ((int)n.labels.size() > max_ns_labels) {
       max_ns_labels = (int)n.labels.size();
-      if (max_ns_labels > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than 32 labels");
       if (ctx && max_ns_labels > lim.ns_label_slots) drop_engine();
     }
     namespaces_dirty = true;
@@ -1309,39 +1359,40 @@ struct kth_plugin {
       o.terms.push_back(std::move(term));
     }
     o.live = true;
-    const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
-    auto it = thr_index.find(key);
+    // the status the manifest carries, parsed BEFORE anything is committed: a manifest that is refused leaves no trace
     const Node& st = v["status"];
-    if (it == thr_index.end()) {
-      thr_index[key] = (int)throttles.size();
-      throttles.push_back(std::move(o));
-      it = thr_index.find(key);
-    } else {  // spec update: the status subresource is kept unless the manifest carries one
-      ThrottleObj& old = throttles[(size_t)it->second];
-      o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
-      o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
-      old = std::move(o);
-    }
-    if (st.is(Node::Obj)) {
-      ThrottleObj& x = throttles[(size_t)it->second];
+    const bool has_status = st.is(Node::Obj);
+    if (has_status) {
       const Node& ct = st["calculatedThreshold"];
-      x.st_calc = res_amount(ct["threshold"]);
-      x.st_calc_at_set = false;
-      x.st_calc_at = 0;
+      o.st_calc = res_amount(ct["threshold"]);
+      o.st_calc_at_set = false;
+      o.st_calc_at = 0;
       if (ct["calculatedAt"].is(Node::Str) && !ct["calculatedAt"].text.empty()) {
         GoTime at;
         const std::string e = parse_rfc3339(ct["calculatedAt"].text, &at);
         if (!e.empty()) fail(e);
-        x.st_calc_at_set = !at.zero;
-        x.st_calc_at = at.sec;
+        o.st_calc_at_set = !at.zero;
+        o.st_calc_at = at.sec;
       }
-      x.st_messages.clear();
-      for (auto& mnode : ct["messages"].arr) x.st_messages.push_back(mnode->str());
-      x.st_thr_pod = st["throttled"]["resourceCounts"]["pod"].boolean(false);
-      x.st_thr_req.clear();
-      x.st_thr_req_nil = !st["throttled"]["resourceRequests"].is(Node::Obj);
-      for (auto& kv : st["throttled"]["resourceRequests"].obj) x.st_thr_req[column(kv.first)] = kv.second->boolean(false);
-      x.st_used = res_amount(st["used"]);
+      for (auto& mnode : ct["messages"].arr) o.st_messages.push_back(mnode->str());
+      o.st_thr_pod = st["throttled"]["resourceCounts"]["pod"].boolean(false);
+      o.st_thr_req_nil = !st["throttled"]["resourceRequests"].is(Node::Obj);
+      for (auto& kv : st["throttled"]["resourceRequests"].obj) o.st_thr_req[column(kv.first)] = kv.second->boolean(false);
+      o.st_used = res_amount(st["used"]);
+    }
+    const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
+    auto it = thr_index.find(key);
+    if (it == thr_index.end()) {
+      thr_index[key] = (int)throttles.size();
+      throttles.push_back(std::move(o));
+    } else {  // spec update: the status subresource is kept unless the manifest carries one
+      ThrottleObj& old = throttles[(size_t)it->second];
+      if (old.metrics_pending) record_metrics(old);  // the gauges keep the values of the last reconcile, not of this update
+      if (!has_status) {
+        o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
+        o.st_thr_pod = old.st_thr_pod; o.st_thr_req = old.st_thr_req; o.st_thr_req_nil = old.st_thr_req_nil; o.st_used = old.st_used;
+      }
+      old = std::move(o);
     }
     throttles_dirty = status_dirty = reserved_dirty = true;
   }
@@ -1351,6 +1402,7 @@ struct kth_plugin {
     if (it == thr_index.end()) return;
     // the column is kept (device order is insertion order) but can never match or be reconciled again
     ThrottleObj& o = throttles[(size_t)it->second];
+    if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }  // its series outlive it, as a GaugeVec's do
     o.live = false;
     o.terms.clear();
     cache[kind].by_thr.erase(nn);
@@ -1541,11 +1593,17 @@ const char* kth_apply(kth_plugin* p, const char* manifest_json) {
   return guarded(p, [&]() -> std::string {
     ktjson::NodePtr v = ktjson::parse(manifest_json);
     const std::string kind = (*v)["kind"].str();
-    if (kind == "Pod") p->apply_pod(*v);
-    else if (kind == "Namespace") p->apply_namespace(*v);
-    else if (kind == "Throttle") p->apply_throttle(*v, KT_KIND_THROTTLE);
-    else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
-    else fail("unsupported kind: " + kind);
+    const size_t n_cols = p->cols.size();
+    try {
+      if (kind == "Pod") p->apply_pod(*v);
+      else if (kind == "Namespace") p->apply_namespace(*v);
+      else if (kind == "Throttle") p->apply_throttle(*v, KT_KIND_THROTTLE);
+      else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
+      else fail("unsupported kind: " + kind);
+    } catch (...) {
+      p->rollback_columns(n_cols);  // the refused object's resource names go with it
+      throw;
+    }
     return "{\"ok\":true}";
   });
 }
@@ -1605,7 +1663,10 @@ const char* kth_reserved(kth_plugin* p, int kind, const char* throttle_nn) {
   return guarded(p, [&]() { return p->reserved_json(kind, throttle_nn ? throttle_nn : ""); });
 }
 const char* kth_metrics(kth_plugin* p) {
-  return guarded(p, [&]() -> std::string { return p->metrics_text(); });
+  return guarded(p, [&]() -> std::string {
+    p->flush_metrics();
+    return p->metrics_text();
+  });
 }
 const char* kth_eval(const char* request_json) {
   try {

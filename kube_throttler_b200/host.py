@@ -14,8 +14,10 @@ import json
 from . import KtError, abi, lib
 
 
-def _bind():
-    L = lib()
+def _bind(L=None):
+    """Declare the kt_host.h prototypes on a loaded library: the product's (default), or any other build of kt_host.cc that
+    exports them (tests link the host layer against engine test doubles to check its bookkeeping without a device)."""
+    L = L if L is not None else lib()
     if getattr(L, "_kth_bound", False):
         return L
     vp, cp = C.c_void_p, C.c_char_p
@@ -52,8 +54,8 @@ def eval_host(fn: str, **kw):
 class Plugin:
     """kubethrottler.NewPlugin(configuration, handle) -- fails without a GPU (there is no CPU path)."""
 
-    def __init__(self, name="kube-throttler", target_scheduler_name="my-scheduler", device=0, **extra_args):
-        self._L = _bind()
+    def __init__(self, name="kube-throttler", target_scheduler_name="my-scheduler", device=0, library=None, **extra_args):
+        self._L = _bind(library)
         self._h = C.c_void_p()
         args = dict(extra_args, name=name, targetSchedulerName=target_scheduler_name)
         rc = self._L.kth_new_plugin(C.byref(self._h), json.dumps(args).encode(), device)

@@ -214,3 +214,99 @@ def test_malformed_quantities_rejected_by_both(host, oracle, s):
         host.eval_host("ParseQuantity", value=s)
     with pytest.raises(RuntimeError):
         oracle.call("ParseQuantity", value=s)
+
+
+# ---- randomised differential checks: the product's packer and the oracle were written independently ----------------------
+
+def _rand_quantity(rng):
+    kind = rng.random()
+    if kind < 0.35:
+        s = str(rng.randrange(0, 5000)) + rng.choice(["", "m", "m", "k", "Ki", "Mi", "Gi", "M", "G", "u", "n"])
+    elif kind < 0.7:
+        s = f"{rng.randrange(0, 400)}.{rng.randrange(0, 10 ** rng.randrange(1, 5)):0{rng.randrange(1, 5)}d}" + rng.choice(["", "", "m", "Ki", "Mi", "Gi", "k"])
+    elif kind < 0.85:
+        s = f"{rng.randrange(1, 999)}e{rng.randrange(-6, 7)}"
+    else:
+        s = rng.choice(["0", "00", "0.0", ".5", "5.", "1e0", "+3", "-2", "-1500m", "100n", "1n", "0.0000000004", "1.0000000005", "15Ei", "8191Pi"])
+    return s
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_quantities_agree_with_the_oracle(host, oracle, seed):
+    import random
+
+    rng = random.Random(1000 + seed)
+    for _ in range(250):
+        s = _rand_quantity(rng)
+        a, b = host.eval_host("ParseQuantity", value=s), oracle.call("ParseQuantity", value=s)
+        assert Fraction(a["decimal"]) == Fraction(b["decimal"]), s
+        assert a["format"] == b["format"], s
+        canon = host.eval_host("CanonicalQuantity", value=s)["canonical"]  # re-parsing the canonical spelling gives the value back
+        assert Fraction(host.eval_host("ParseQuantity", value=canon)["decimal"]) == Fraction(a["decimal"]), (s, canon)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_pods_request_lists_agree_with_the_oracle(host, oracle, seed):
+    """PodRequestResourceList over random container / initContainer / overhead shapes (resourcelist.go:27-46)."""
+    import random
+
+    rng = random.Random(2000 + seed)
+    names = ["cpu", "memory", "nvidia.com/gpu", "ephemeral-storage", "example.com/x"]
+
+    def reqs():
+        return {n: _rand_quantity(rng).lstrip("-") or "0" for n in rng.sample(names, rng.randrange(0, 4))}
+
+    for _ in range(60):
+        spec = {"containers": [{"name": f"c{i}", "resources": {"requests": reqs()}} for i in range(rng.randrange(0, 4))]}
+        if rng.random() < 0.5:
+            spec["initContainers"] = [{"name": f"i{i}", "resources": {"requests": reqs()}} for i in range(rng.randrange(1, 3))]
+        if rng.random() < 0.3:
+            spec["overhead"] = reqs()
+        pod = {"kind": "Pod", "metadata": {"name": "p", "namespace": "d"}, "spec": spec}
+        got, want = rl_values(host.eval_host("PodRequestResourceList", pod=pod)), rl_values(oracle.call("PodRequestResourceList", pod=pod))
+        assert got == want, pod
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_selectors_validate_like_the_oracle(host, oracle, seed):
+    """LabelSelectorAsSelector accepts / rejects the same selectors in both implementations (operators, value counts, key and
+    value syntax).  PARITY UNPINNED by reference tests; both follow apimachinery v0.26.4 validation rules independently."""
+    import random
+
+    rng = random.Random(3000 + seed)
+    keys = ["app", "tier", "example.com/role", "a" * 63, "a" * 64, "-bad", "bad-", "a/b/c", "/x", "Ex_Ample.com/k", "exa_mple.com/k", "k.", "", "x y"]
+    vals = ["db", "", "a" * 63, "a" * 64, "bad value", "-x", "x-", "x_y.z", "9"]
+    ops = ["In", "NotIn", "Exists", "DoesNotExist", "Bogus", "in", ""]
+    disagreements = []
+    for _ in range(150):
+        sel = {}
+        if rng.random() < 0.6:
+            sel["matchLabels"] = {rng.choice(keys): rng.choice(vals) for _ in range(rng.randrange(0, 3))}
+        if rng.random() < 0.7:
+            sel["matchExpressions"] = [{"key": rng.choice(keys), "operator": rng.choice(ops), "values": [rng.choice(vals) for _ in range(rng.randrange(0, 3))]}
+                                       for _ in range(rng.randrange(0, 3))]
+        got = host.eval_host("ValidateSelector", selector=sel)["valid"]
+        ref = oracle.call("ThrottleSelector.MatchesToPod", selector={"selectorTerms": [{"podSelector": sel}]},
+                          pod={"metadata": {"name": "p", "namespace": "d", "labels": {"app": "db"}}, "spec": {}})
+        if got != ("error" not in ref):
+            disagreements.append((sel, got, ref))
+    assert not disagreements, disagreements[:3]
+
+
+def test_random_timestamps_parse_like_the_oracle(host, oracle):
+    """time.Parse(time.RFC3339, s) over well-formed and malformed spellings (month / day / hour ranges, leap days, fractional
+    seconds with '.' and ',', zone offsets with and without colon, lower-case separators): value and Go's error text agree."""
+    import random
+
+    rng = random.Random(7)
+    for _ in range(600):
+        y = rng.choice([1, 1969, 1970, 1999, 2000, 2021, 2024, 2026, 2100, 9999])
+        mo, d = rng.choice([0, 1, 2, 2, 2, 6, 12, 13]), rng.choice([0, 1, 28, 29, 30, 31, 32])
+        h, mi, sec = rng.choice([0, 12, 23, 24, 25]), rng.choice([0, 30, 59, 60]), rng.choice([0, 30, 59, 60, 61])
+        frac = rng.choice(["", "", ".5", ".123456789", ".1234567891", ".", ",5", ".000"])
+        tz = rng.choice(["Z", "Z", "+09:00", "-07:00", "+00:00", "+24:00", "+09:60", "+0900", "z", "", " Z", "+9:00", "-00:00", "+23:59"])
+        s = f"{y:04d}-{mo:02d}-{d:02d}{rng.choice('TTTt ')}{h:02d}:{mi:02d}:{sec:02d}{frac}{tz}"
+        got, want = host.eval_host("ParseRFC3339", value=s), oracle.call("ParseRFC3339", value=s)
+        assert got.get("error") == want.get("error"), s
+        if "error" not in want:
+            assert (got["unix"], got["nsec"]) == (want["unix"], want["nsec"]), s

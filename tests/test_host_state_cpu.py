@@ -1,0 +1,164 @@
+"""The host layer's bookkeeping (kt_host.cc: informer events, limits, dictionaries, status JSON, gauges) on the CPU.
+
+kt_host.cc is compiled here against a TEST DOUBLE of the device engine (tests/host_stub/engine_stub.cc) that accepts uploads
+and fails every call that would need a device pass -- nothing is evaluated on the CPU, and a test that strays into PreFilter /
+reconcile gets the engine's error.  What this covers without a GPU: which manifests are accepted or refused, that a refused
+manifest leaves no trace, status round trips through Apply, tombstones, gauges of applied statuses."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import pytest
+
+from test_scenarios import SCHED, THROTTLER, namespace, pod, throttle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRCS = [os.path.join(ROOT, "kube_throttler_b200", "csrc", "kt_host.cc"), os.path.join(ROOT, "tests", "host_stub", "engine_stub.cc")]
+DEPS = SRCS + [os.path.join(ROOT, "kube_throttler_b200", "csrc", f) for f in ("kt_json.h", "kt_quantity.h")] + \
+    [os.path.join(ROOT, "include", f) for f in ("kt_b200.h", "kt_host.h")]
+OUT = os.path.join(ROOT, "tests", "_build", "libkt_hoststub.so")
+
+
+@pytest.fixture(scope="module")
+def stub():
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(f) for f in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", OUT] + SRCS, check=True)
+    L = C.CDLL(OUT)
+    vp, cp = C.c_void_p, C.c_char_p
+    L.kth_new_plugin.argtypes = [C.POINTER(vp), cp, C.c_int]
+    L.kth_free.argtypes = [vp]
+    L.kth_free.restype = None
+    for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_get_status", [vp, cp, cp]), ("kth_metrics", [vp]),
+                       ("kth_pre_filter", [vp, cp]), ("kth_reconcile_all", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp])):
+        getattr(L, name).argtypes = args
+        getattr(L, name).restype = cp
+    return L
+
+
+class World:
+    def __init__(self, L):
+        self.L, self.h = L, C.c_void_p()
+        assert L.kth_new_plugin(C.byref(self.h), json.dumps({"name": THROTTLER, "targetSchedulerName": SCHED}).encode(), 0) == 0
+
+    def _res(self, raw):
+        out = json.loads(raw.decode())
+        if isinstance(out, dict) and set(out) == {"error"}:
+            raise RuntimeError(out["error"])
+        return out
+
+    def apply(self, *manifests):
+        for m in manifests:
+            self._res(self.L.kth_apply(self.h, json.dumps(m).encode()))
+
+    def delete(self, kind, name, ns=""):
+        return self._res(self.L.kth_delete(self.h, kind.encode(), ns.encode(), name.encode()))
+
+    def status(self, name, ns=""):
+        return self._res(self.L.kth_get_status(self.h, ns.encode(), name.encode()))
+
+    def prefilter(self, p):
+        return self._res(self.L.kth_pre_filter(self.h, json.dumps(p).encode()))
+
+    def close(self):
+        self.L.kth_free(self.h)
+
+
+@pytest.fixture
+def world(stub):
+    w = World(stub)
+    yield w
+    w.close()
+
+
+STATUS = {"calculatedThreshold": {"threshold": {"resourceRequests": {"cpu": "700m"}}, "calculatedAt": "2026-01-01T00:00:00Z", "messages": ["m"]},
+          "throttled": {"resourceCounts": {"pod": False}, "resourceRequests": {"cpu": True}},
+          "used": {"resourceCounts": {"pod": 3}, "resourceRequests": {"cpu": "1500m", "memory": "512Mi"}}}
+
+
+def test_status_round_trips_and_survives_a_spec_update(world):
+    t = throttle("default", "t", {"a": "1"}, pod_cnt=5, cpu="1")
+    world.apply(namespace("default"), dict(t, status=STATUS))
+    s = world.status("t", "default")
+    assert s["calculatedThreshold"]["threshold"] == {"resourceRequests": {"cpu": "0.7"}} and s["calculatedThreshold"]["calculatedAtSet"] is True
+    assert s["calculatedThreshold"]["messages"] == ["m"] and s["throttled"] == {"resourceCounts": {"pod": False}, "resourceRequests": {"cpu": True}}
+    assert s["used"] == {"resourceCounts": {"pod": 3}, "resourceRequests": {"cpu": "1.5", "memory": "536870912"}}
+    world.apply(throttle("default", "t", {"a": "2"}, cpu="2"))        # spec update without a status: the status subresource is kept
+    assert world.status("t", "default") == s
+    world.apply(dict(throttle("default", "t", {"a": "2"}, cpu="2"), status={}))  # an explicit (empty) status replaces it
+    s2 = world.status("t", "default")
+    assert s2["used"] == {} and s2["calculatedThreshold"]["calculatedAtSet"] is False and "messages" not in s2["calculatedThreshold"]
+
+
+def test_refused_manifests_leave_no_trace(world):
+    world.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    before = world.status("t", "default")
+    bad_time = dict(throttle("default", "t", {"a": "1"}, cpu="3", extra={"example.com/only-here": "1"}),
+                    status=dict(STATUS, calculatedThreshold={"threshold": {}, "calculatedAt": "yesterday"}))
+    with pytest.raises(RuntimeError, match="parsing time"):
+        world.apply(bad_time)
+    assert world.status("t", "default") == before                     # neither the new spec nor its status was committed
+    with pytest.raises(RuntimeError, match="quantit"):
+        world.apply(throttle("default", "t2", {"a": "1"}, cpu="1x"))
+    with pytest.raises(RuntimeError, match="not found"):
+        world.status("t2", "default")
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        world.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}))
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        world.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
+    # a 32nd resource name is refused -- and the 30 names the refused pod had already brought along go with it: afterwards
+    # thirty OTHER new names still fit
+    with pytest.raises(RuntimeError, match="distinct resource names"):
+        world.apply(pod("default", "greedy", "100m", {"a": "1"}, requests={f"example.com/r{i}": "1" for i in range(40)}))
+    world.apply(pod("default", "modest", "100m", {"a": "1"}, requests={f"example.com/s{i}": "1" for i in range(30)}))
+    with pytest.raises(RuntimeError, match="distinct resource names"):
+        world.apply(pod("default", "one-more", "100m", {"a": "1"}, requests={"example.com/the-32nd": "1"}))
+    with pytest.raises(RuntimeError, match="unsupported kind"):
+        world.apply({"kind": "Deployment", "metadata": {"name": "d"}})
+
+
+def test_device_dependent_calls_fail_loudly_on_the_stub(world):
+    """Nothing under kt_host.cc can answer a PreFilter or run a reconcile without the engine."""
+    world.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"), pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running"))
+    with pytest.raises(RuntimeError, match="kt_evaluate"):
+        world.prefilter(pod("default", "x", "100m", {"a": "1"}))
+    with pytest.raises(RuntimeError, match="kt_evaluate"):
+        world._res(world.L.kth_reconcile_all(world.h, b"2026-01-01T00:00:00Z"))
+
+
+def test_gauges_are_only_recorded_by_reconcile(world):
+    world.apply(namespace("default"), dict(throttle("default", "t", {"a": "1"}, cpu="1"), status=STATUS))
+    assert world.L.kth_metrics(world.h).decode() == ""  # an applied status is the informer's copy, not a reconcile
+
+
+def test_pod_delete_and_reapply_reuse_rows(world):
+    world.apply(namespace("default"))
+    for i in range(4):
+        world.apply(pod("default", f"p{i}", "100m", {"a": "1"}, node="n", phase="Running"))
+    assert world.delete("Pod", "p1", "default") == {"ok": True}
+    assert world.delete("Pod", "nope", "default") == {"ok": True}   # deleting what is not there is not an error (DeleteFunc of a stale key)
+    world.apply(pod("default", "p9", "1", {"a": "1"}, node="n", phase="Running"), pod("default", "p0", "200m", {"a": "2"}, node="n", phase="Running"))
+    assert world.delete("Throttle", "nope", "default") == {"ok": True}
+
+
+def test_column_overflow_is_proved_incrementally(host_on_oracle):
+    """The packer refuses a snapshot whose column sum could wrap int64 (sum of |v| >= 2^62).  The per-column totals follow the
+    pod events, so the proof does not walk the pod table at every sync; it has to notice an overflow that an update or a new
+    pod brings about and to forget it when the pod goes away.  (Host layer over the oracle-backed engine double.)"""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    w.apply(pod("default", "p1", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))  # 2^61 + 2^61
+    with pytest.raises(RuntimeError, match="can overflow int64"):
+        w.reconcile_all("2026-01-01T00:00:00Z")
+    w.apply(pod("default", "p1", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "1Ei"}))  # update shrinks it
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    w.apply(pod("default", "p2", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "1Ei"}))  # 2^61 + 2^60 + 2^60
+    with pytest.raises(RuntimeError, match="can overflow int64"):
+        w.reconcile_all("2026-01-01T00:00:00Z")
+    w.delete("Pod", "p0", "default")
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
+    assert w.status("t", "default")["used"]["resourceRequests"]["memory"] == str(2**61)
+    w.close()

@@ -11,7 +11,18 @@ import pytest
 from test_oracle_kat import q
 from test_scenarios import NOW, SCHED, THROTTLER, namespace
 
-pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["host-on-oracle", pytest.param("b200", marks=pytest.mark.gpu)])
+def new_plugin(request):
+    """NewPlugin on the product (GPU), or on the product's host layer over the engine test double that evaluates with the
+    columnar oracle (CPU; conftest.host_on_oracle): the latter checks kt_host.cc against the OBJECT-level oracle -- packing,
+    scales, status bookkeeping, reservations, reasons -- and says nothing about the kernels."""
+    if request.param == "host-on-oracle":
+        return request.getfixturevalue("host_on_oracle")
+    from kube_throttler_b200 import host  # fails loudly without the CUDA library / a GPU
+
+    return host.Plugin
 
 KEYS = ["app", "tier", "team", "env", "zone"]
 VALS = ["a", "b", "c", "d"]
@@ -112,11 +123,10 @@ def norm_prefilter(r):
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
-def test_random_world(oracle, seed):
-    from kube_throttler_b200 import host
+def test_random_world(oracle, new_plugin, seed):
 
     rng = random.Random(seed)
-    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
     both = lambda *m: (ref.apply(*m), dut.apply(*m))
     nss = [f"ns{i}" for i in range(5)]
     for n in nss:
@@ -174,13 +184,12 @@ def test_random_world(oracle, seed):
 
 
 @pytest.mark.parametrize("seed", [11, 18, 19])
-def test_admit_queue_equals_one_pod_per_cycle(oracle, seed):
+def test_admit_queue_equals_one_pod_per_cycle(oracle, new_plugin, seed):
     """kth_admit_queue == the scheduler's cycle (PreFilter, on Success Reserve) run pod by pod on the oracle: same verdict for
     every pod of the queue, same reservations afterwards -- in far fewer device passes than pods."""
-    from kube_throttler_b200 import host
 
     rng = random.Random(seed)
-    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
     both = lambda *m: (ref.apply(*m), dut.apply(*m))
     nss = [f"ns{i}" for i in range(5)]
     for n in nss:
@@ -214,13 +223,12 @@ def test_admit_queue_equals_one_pod_per_cycle(oracle, seed):
     dut.close()
 
 
-def test_engine_limits_grow(oracle):
+def test_engine_limits_grow(oracle, new_plugin):
     """More label slots / resource columns / namespace labels than the engine was created with: the host layer re-creates
     the engine with larger limits and re-uploads its caches; decisions stay identical to the oracle's."""
-    from kube_throttler_b200 import host
     from test_scenarios import pod, throttle
 
-    ref, dut = oracle.World(THROTTLER, SCHED), host.Plugin(THROTTLER, SCHED)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
     both = lambda *m: (ref.apply(*m), dut.apply(*m))
     both(namespace("default"), throttle("default", "t", {"a": "1"}, pod_cnt=3, cpu="1"))
     both(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
@@ -247,12 +255,11 @@ def rl_values_of(amount):
     return {k: q(v) for k, v in amount.get("resourceRequests", {}).items()}
 
 
-def test_delete_events(oracle):
+def test_delete_events(oracle, new_plugin):
     """Pod and throttle deletes (informer DeleteFunc): the row becomes a tombstone and is reused; used sums follow."""
-    from kube_throttler_b200 import host
     from test_scenarios import pod, throttle
 
-    w = host.Plugin(THROTTLER, SCHED)
+    w = new_plugin(THROTTLER, SCHED)
     w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
     for i in range(5):
         w.apply(pod("default", f"p{i}", "100m", {"a": "1"}, node="n", phase="Running"))
@@ -272,12 +279,11 @@ def test_delete_events(oracle):
     w.close()
 
 
-def test_column_scale_refinement():
+def test_column_scale_refinement(new_plugin):
     """A quantity finer than the column's scale (cpu below 1m) re-packs the column at a finer power of ten; sums stay exact."""
-    from kube_throttler_b200 import host
     from test_scenarios import pod, throttle
 
-    w = host.Plugin(THROTTLER, SCHED)
+    w = new_plugin(THROTTLER, SCHED)
     w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
     w.apply(pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running"))
     w.reconcile_all(NOW)
@@ -291,13 +297,12 @@ def test_column_scale_refinement():
     w.close()
 
 
-def test_gauges_follow_reconcile():
+def test_gauges_follow_reconcile(new_plugin):
     """kth_metrics: series are recorded by reconcile (throttle_controller.go:159,187), only for reconciled (responsible)
     throttles, and stay after the throttle is deleted (a GaugeVec never drops a series)."""
-    from kube_throttler_b200 import host
     from test_scenarios import clthrottle, pod, throttle
 
-    w = host.Plugin(THROTTLER, SCHED)
+    w = new_plugin(THROTTLER, SCHED)
     t = throttle("default", "t", {"a": "1"}, pod_cnt=2, cpu="1")
     t["metadata"]["uid"] = "uid-t"
     w.apply(namespace("default"), t, throttle("default", "other", {"a": "1"}, cpu="1", throttler="someone-else"),
@@ -323,7 +328,36 @@ def test_gauges_follow_reconcile():
     assert s["clusterthrottle_status_throttled_resourceRequests" + lc % "cpu"] == "1"
     assert s["clusterthrottle_spec_threshold_resourceCounts" + lc % "pod"] == "0"
     assert not any('name="other"' in k for k in s)  # not ours: never enqueued, never recorded
+    # a spec edit does not move the spec gauge until the next reconcile records it (the recorder runs inside reconcile)
+    t2 = throttle("default", "t", {"a": "1"}, pod_cnt=7, cpu="1")
+    t2["metadata"]["uid"] = "uid-t"
+    w.apply(t2)
+    assert f'throttle_spec_threshold_resourceCounts{lt % "pod"} 2' in w.metrics()
+    w.reconcile_all(NOW)
+    assert f'throttle_spec_threshold_resourceCounts{lt % "pod"} 7' in w.metrics()
     w.delete("Throttle", "t", "default")
     w.reconcile_all(NOW)
     assert "throttle_status_used_resourceCounts" + lt % "pod" in w.metrics()
+    w.close()
+
+
+def test_objects_beyond_the_limits_are_rejected_not_fatal(new_plugin):
+    """A pod with more labels than KT_MAX_LABEL_SLOTS (32), a namespace likewise, or a 32nd distinct resource name is refused with
+    an error for THAT object; the plugin keeps serving (the limits are checked before any state is touched)."""
+    from test_scenarios import pod, throttle
+
+    w = new_plugin(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        w.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}, node="n", phase="Running"))
+    with pytest.raises(RuntimeError, match="more than 32 labels"):
+        w.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
+    with pytest.raises(RuntimeError, match="distinct resource names"):
+        w.apply(pod("default", "greedy", "100m", {"a": "1"}, node="n", phase="Running", requests={f"example.com/r{i}": "1" for i in range(40)}))
+    w.reconcile_all(NOW)
+    s = w.status("t", "default")
+    assert s["used"]["resourceCounts"]["pod"] == 1 and q(s["used"]["resourceRequests"]["cpu"]) == Fraction(3, 10)
+    assert w.prefilter(pod("default", "x", "800m", {"a": "1"}))["reasons"] == ["throttle[insufficient]=default/t"]
+    assert w.prefilter(pod("default", "y", "700m", {"a": "1"}))["code"] == "Success"
     w.close()

@@ -64,11 +64,15 @@ def namespace(name, labels=None):
     return {"kind": "Namespace", "metadata": {"name": name, "labels": l}}
 
 
-@pytest.fixture(params=["oracle", pytest.param("b200", marks=pytest.mark.gpu)])
+@pytest.fixture(params=["oracle", "host-on-oracle", pytest.param("b200", marks=pytest.mark.gpu)])
 def new_world(request, oracle):
-    """Constructor of a plugin world: NewPlugin(name, targetSchedulerName) on either implementation."""
+    """Constructor of a plugin world: NewPlugin(name, targetSchedulerName) on the object-level oracle, on the product's HOST layer
+    over an engine test double that evaluates with the columnar oracle (CPU: checks kt_host.cc, not the kernels), or on the
+    product itself (GPU)."""
     if request.param == "oracle":
         return oracle.World
+    if request.param == "host-on-oracle":
+        return request.getfixturevalue("host_on_oracle")
     from kube_throttler_b200 import host  # the product path: fails loudly without the CUDA library / a GPU
 
     return host.Plugin

@@ -67,6 +67,13 @@ const char* kth_reconcile_all(kth_plugin* p, const char* now_rfc3339);
  *  "used":{"resourceCounts":{"pod":n},"resourceRequests":{name:"decimal"}}} */
 const char* kth_get_status(kth_plugin* p, const char* ns, const char* name);
 
+/* The same status as the `status` subresource the reference's UpdateStatus sends (throttle_controller.go:157-173):
+ * encoding/json of v1alpha1.ThrottleStatus -- fields in declaration order, map keys sorted, nil / empty members omitted,
+ * quantities in their canonical spelling (resource.Quantity.String: "500m", "1", "512Mi"; util_throttle_test.go:169-177 asserts
+ * them), calculatedAt as RFC3339 UTC or null.  What the Go build hands to
+ * ScheduleV1alpha1().Throttles(ns).UpdateStatus for every name kth_reconcile_all lists under "changed". */
+const char* kth_get_status_manifest(kth_plugin* p, const char* ns, const char* name);
+
 /* PreFilter(ctx, state, pod) -- plugin.go:148-215.
  * {"code":"Success"|"UnschedulableAndUnresolvable"|"Error","reasons":[...],"event":{...}?,
  *  "throttle":{"active":[..],"insufficient":[..],"podRequestsExceedsThreshold":[..],"affected":[..]},

@@ -9,6 +9,7 @@
 // that is the device's job (kt_evaluate); this file packs, calls, and spells the results.
 #include <algorithm>
 #include <charconv>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -74,6 +75,24 @@ long long days_from_civil(long long y, unsigned m, unsigned d) {
   const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
   const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
   return era * 146097 + (long long)doe - 719468;
+}
+// metav1.Time marshals as UTC RFC3339 with second precision ("2006-01-02T15:04:05Z")
+std::string format_rfc3339_utc(long long unix_sec) {
+  long long days = unix_sec >= 0 ? unix_sec / 86400 : -((-unix_sec + 86399) / 86400);
+  const long long rem = unix_sec - days * 86400;
+  days += 719468;  // civil_from_days (H. Hinnant), the inverse of days_from_civil above
+  const long long era = (days >= 0 ? days : days - 146096) / 146097;
+  const unsigned doe = (unsigned)(days - era * 146097);
+  const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  long long y = (long long)yoe + era * 400;
+  const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const unsigned mp = (5 * doy + 2) / 153;
+  const unsigned d = doy - (153 * mp + 2) / 5 + 1;
+  const unsigned m = mp < 10 ? mp + 3 : mp - 9;
+  y += m <= 2;
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%04lld-%02u-%02uT%02d:%02d:%02dZ", y, m, d, (int)(rem / 3600), (int)(rem % 3600 / 60), (int)(rem % 60));
+  return buf;
 }
 // Layout-driven: the RFC3339 layout "2006-01-02T15:04:05Z07:00" is a list of chunks; the first chunk that
 // fails to parse produces `cannot parse "<rest>" as "<chunk>"` exactly as time.Parse reports it.
@@ -1436,6 +1455,56 @@ struct kth_plugin {
     w.end_obj();
     return w.out;
   }
+  // ---- the status subresource exactly as the reference's UpdateStatus would send it (encoding/json of v1alpha1.ThrottleStatus:
+  // throttle_types.go:113-117, resource_amount.go:27-44, calculated_threshold.go:24-30): struct fields in declaration order,
+  // map keys sorted, nil / empty maps and nil counts omitted, quantities in their canonical spelling (Quantity.String), the
+  // zero time as null.
+  void amount_manifest(Writer& w, const ResAmount& a, bool column_format) const {
+    w.begin_obj();
+    if (a.has_counts) w.key("resourceCounts").begin_obj().key("pod").num(a.pod).end_obj();
+    if (!a.requests.empty()) {
+      std::map<std::string, std::string> byname;
+      for (auto& kv : a.requests) {
+        const ResourceColumn& c = cols[(size_t)kv.first];
+        // a parsed quantity keeps its own format; a sum takes the format its first addend had -- the column's, here
+        byname[c.name] = kt::canonical_string(kv.second.mant, kv.second.exp, column_format ? c.format : kv.second.format);
+      }
+      w.key("resourceRequests").begin_obj();
+      for (auto& kv : byname) w.key(kv.first).str(kv.second);
+      w.end_obj();
+    }
+    w.end_obj();
+  }
+  std::string status_manifest_json(const std::string& ns, const std::string& tname) {
+    auto it = thr_index.find(ns.empty() ? "C:/" + tname : "T:" + ns + "/" + tname);
+    if (it == thr_index.end()) fail("throttle " + ns + "/" + tname + " not found");
+    const ThrottleObj& o = throttles[(size_t)it->second];
+    Writer w;
+    w.begin_obj().key("calculatedThreshold").begin_obj().key("threshold");
+    amount_manifest(w, o.st_calc, false);
+    w.key("calculatedAt");
+    if (o.st_calc_at_set) w.str(format_rfc3339_utc(o.st_calc_at));
+    else w.raw("null");
+    if (!o.st_messages.empty()) {
+      w.key("messages").begin_arr();
+      for (auto& m : o.st_messages) w.str(m);
+      w.end_arr();
+    }
+    w.end_obj();
+    w.key("throttled").begin_obj().key("resourceCounts").begin_obj().key("pod").boolean(o.st_thr_pod).end_obj();
+    if (!o.st_thr_req.empty()) {
+      std::map<std::string, bool> byname;
+      for (auto& kv : o.st_thr_req) byname[cols[(size_t)kv.first].name] = kv.second;
+      w.key("resourceRequests").begin_obj();
+      for (auto& kv : byname) w.key(kv.first).boolean(kv.second);
+      w.end_obj();
+    }
+    w.end_obj();
+    w.key("used");
+    amount_manifest(w, o.st_used, true);
+    w.end_obj();
+    return w.out;
+  }
   std::string reserved_json(int kind, const std::string& nn) {
     Writer w;
     ResAmount total;
@@ -1625,6 +1694,9 @@ const char* kth_reconcile_all(kth_plugin* p, const char* now_rfc3339) {
 }
 const char* kth_get_status(kth_plugin* p, const char* ns, const char* name) {
   return guarded(p, [&]() { return p->status_json(ns ? ns : "", name ? name : ""); });
+}
+const char* kth_get_status_manifest(kth_plugin* p, const char* ns, const char* name) {
+  return guarded(p, [&]() -> std::string { return p->status_manifest_json(ns ? ns : "", name ? name : ""); });
 }
 const char* kth_pre_filter(kth_plugin* p, const char* pod_json) {
   return guarded(p, [&]() {

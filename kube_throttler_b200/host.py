@@ -26,7 +26,7 @@ def _bind(L=None):
     L.kth_free.argtypes = [vp]
     L.kth_free.restype = None
     for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_reconcile_all", [vp, cp]),
-                       ("kth_get_status", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
+                       ("kth_get_status", [vp, cp, cp]), ("kth_get_status_manifest", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
                        ("kth_admit_queue", [vp, cp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_metrics", [vp]), ("kth_eval", [cp])):
         fn = getattr(L, name)
         fn.argtypes = args
@@ -35,7 +35,7 @@ def _bind(L=None):
     return L
 
 
-HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status",
+HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status", "kth_get_status_manifest",
                 "kth_pre_filter", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
 
 
@@ -88,6 +88,12 @@ class Plugin:
 
     def status(self, name, namespace=""):
         return _result(self._L.kth_get_status(self._h, namespace.encode(), name.encode()))
+
+    def status_manifest(self, name, namespace="") -> str:
+        """The status subresource as the reference's UpdateStatus would send it (raw JSON text: key order and spellings matter)."""
+        raw = self._L.kth_get_status_manifest(self._h, namespace.encode(), name.encode()).decode()
+        _result(raw.encode())  # raises on {"error": ...}
+        return raw
 
     # plugin
     def prefilter(self, pod):

@@ -162,3 +162,31 @@ def test_column_overflow_is_proved_incrementally(host_on_oracle):
     assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 1
     assert w.status("t", "default")["used"]["resourceRequests"]["memory"] == str(2**61)
     w.close()
+
+
+def test_status_manifest_is_what_update_status_would_send(host_on_oracle):
+    """kth_get_status_manifest: encoding/json of v1alpha1.ThrottleStatus -- declaration order, sorted map keys, canonical
+    quantities (the integration suite asserts "500m", "1", ... through Quantity.String, util_throttle_test.go:169-177), RFC3339."""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, pod_cnt=2, cpu="1", extra={"memory": "1Gi"}),
+            throttle("default", "empty", {"a": "zzz"}, cpu="200m"))
+    assert w.status_manifest("t", "default") == '{"calculatedThreshold":{"threshold":{},"calculatedAt":null},"throttled":{"resourceCounts":{"pod":false}},"used":{}}'
+    w.apply(pod("default", "p0", "250m", {"a": "1"}, node="n", phase="Running", requests={"memory": "512Mi"}),
+            pod("default", "p1", "250m", {"a": "1"}, node="n", phase="Running", requests={"memory": "512Mi", "example.com/x": "1500m"}))
+    w.reconcile_all("2026-01-01T00:00:00Z")
+    assert w.status_manifest("t", "default") == (
+        '{"calculatedThreshold":{"threshold":{"resourceCounts":{"pod":2},"resourceRequests":{"cpu":"1","memory":"1Gi"}},"calculatedAt":"2026-01-01T00:00:00Z"},'
+        '"throttled":{"resourceCounts":{"pod":true},"resourceRequests":{"cpu":false,"memory":true}},'
+        '"used":{"resourceCounts":{"pod":2},"resourceRequests":{"cpu":"500m","example.com/x":"1500m","memory":"1Gi"}}}')
+    # no matched pod: used stays the zero ResourceAmount (Q3), the threshold map has one entry
+    assert w.status_manifest("empty", "default") == (
+        '{"calculatedThreshold":{"threshold":{"resourceRequests":{"cpu":"200m"}},"calculatedAt":"2026-01-01T00:00:00Z"},'
+        '"throttled":{"resourceCounts":{"pod":false},"resourceRequests":{"cpu":false}},"used":{}}')
+    # the suite's spellings: 20 x 50m == "1", 900m stays "900m"
+    w.apply(throttle("default", "u", {"b": "1"}, cpu="1"))
+    for i in range(20):
+        w.apply(pod("default", f"q{i}", "50m", {"b": "1"}, node="n", phase="Running"))
+    w.reconcile_all("2019-02-01T09:00:00+09:00")
+    m = json.loads(w.status_manifest("u", "default"))
+    assert m["used"] == {"resourceCounts": {"pod": 20}, "resourceRequests": {"cpu": "1"}} and m["calculatedThreshold"]["calculatedAt"] == "2019-02-01T00:00:00Z"
+    w.close()

@@ -175,15 +175,19 @@ int64_t clamp_ns(__int128 v) {
 }
 
 // ---- label selector validation (metav1.LabelSelectorAsSelector -> labels.NewRequirement) -----------
+// The messages are the ones a scheduler operator reads in the PreFilter Error status, so they are restated in full:
+// k8s.io/apimachinery v0.26.4 pkg/labels/selector.go (NewRequirement, validateLabelKey/Value), pkg/util/validation
+// (IsQualifiedName, IsDNS1123Subdomain, IsValidLabelValue, RegexError), pkg/util/validation/field (Invalid: %q / %#v of the
+// value) and pkg/util/errors (aggregate: "[a, b]", duplicates dropped).  No reference test pins them.
 bool is_alnum(char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
-bool valid_name_part(const std::string& s) {  // [A-Za-z0-9]([-A-Za-z0-9_.]*[A-Za-z0-9])?, at most 63 chars
-  if (s.empty() || s.size() > 63 || !is_alnum(s.front()) || !is_alnum(s.back())) return false;
+bool qualified_name_re(const std::string& s) {  // ([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]
+  if (s.empty() || !is_alnum(s.front()) || !is_alnum(s.back())) return false;
   for (char c : s)
     if (!is_alnum(c) && c != '-' && c != '_' && c != '.') return false;
   return true;
 }
-bool valid_dns_subdomain(const std::string& s) {
-  if (s.empty() || s.size() > 253) return false;
+bool dns1123_subdomain_re(const std::string& s) {  // [a-z0-9]([-a-z0-9]*[a-z0-9])?(\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*
+  if (s.empty()) return false;
   size_t b = 0;
   while (true) {
     size_t e = s.find('.', b);
@@ -197,26 +201,89 @@ bool valid_dns_subdomain(const std::string& s) {
     b = e + 1;
   }
 }
-std::string validate_label_key(const std::string& k) {
-  const size_t slash = k.find('/');
-  std::string name = k, prefix;
-  if (slash != std::string::npos) {
-    if (k.find('/', slash + 1) != std::string::npos) return "a qualified name must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character with an optional DNS subdomain prefix and '/'";
-    prefix = k.substr(0, slash);
-    name = k.substr(slash + 1);
-    if (prefix.empty()) return "prefix part must be non-empty";
-    if (!valid_dns_subdomain(prefix)) return "prefix part a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with an alphanumeric character";
+std::string regex_error(const std::string& msg, const std::string& fmt, std::initializer_list<const char*> examples) {  // validation.RegexError
+  std::string out = msg + " (e.g. ";
+  bool first = true;
+  for (const char* ex : examples) {
+    if (!first) out += " or ";
+    first = false;
+    out += std::string("'") + ex + "', ";
   }
-  if (name.empty()) return "name part must be non-empty";
-  if (name.size() > 63) return "name part must be no more than 63 characters";
-  if (!valid_name_part(name)) return "name part must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
-  return "";
+  return out + "regex used for validation is '" + fmt + "')";
 }
-std::string validate_label_value(const std::string& v) {
-  if (v.empty()) return "";
-  if (v.size() > 63) return "must be no more than 63 characters";
-  if (!valid_name_part(v)) return "a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
-  return "";
+const char* kQualifiedNameMsg = "must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
+const char* kQualifiedNameFmt = "([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]";
+std::vector<std::string> is_qualified_name(const std::string& value) {  // validation.IsQualifiedName
+  std::vector<std::string> errs;
+  std::string name = value;
+  const size_t slash = value.find('/');
+  if (slash != std::string::npos) {
+    if (value.find('/', slash + 1) != std::string::npos)
+      return {"a qualified name " + regex_error(kQualifiedNameMsg, kQualifiedNameFmt, {"MyName", "my.name", "123-abc"}) +
+              " with an optional DNS subdomain prefix and '/' (e.g. 'example.com/MyName')"};
+    const std::string prefix = value.substr(0, slash);
+    name = value.substr(slash + 1);
+    if (prefix.empty()) errs.push_back("prefix part must be non-empty");
+    else {
+      if (prefix.size() > 253) errs.push_back("prefix part must be no more than 253 characters");
+      if (!dns1123_subdomain_re(prefix))
+        errs.push_back("prefix part " + regex_error("a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with an alphanumeric character",
+                                                    "[a-z0-9]([-a-z0-9]*[a-z0-9])?(\\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*", {"example.com"}));
+    }
+  }
+  if (name.empty()) errs.push_back("name part must be non-empty");
+  else if (name.size() > 63) errs.push_back("name part must be no more than 63 characters");
+  if (!qualified_name_re(name)) errs.push_back("name part " + regex_error(kQualifiedNameMsg, kQualifiedNameFmt, {"MyName", "my.name", "123-abc"}));
+  return errs;
+}
+std::vector<std::string> is_valid_label_value(const std::string& v) {  // validation.IsValidLabelValue
+  std::vector<std::string> errs;
+  if (v.size() > 63) errs.push_back("must be no more than 63 characters");
+  if (!v.empty() && !qualified_name_re(v))
+    errs.push_back(regex_error("a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character",
+                               "(([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9])?", {"MyValue", "my_value", "12345"}));
+  return errs;
+}
+std::string go_quote(const std::string& v) {  // %q
+  std::string o = "\"";
+  for (unsigned char c : v) {
+    if (c == '"') o += "\\\"";
+    else if (c == '\\') o += "\\\\";
+    else if (c == '\n') o += "\\n";
+    else if (c == '\t') o += "\\t";
+    else if (c == '\r') o += "\\r";
+    else if (c < 0x20 || c == 0x7f) { char b[8]; std::snprintf(b, sizeof b, "\\x%02x", c); o += b; }
+    else o += (char)c;
+  }
+  return o + "\"";
+}
+std::string go_sharp_v(const std::vector<std::string>& vals) {  // %#v of a []string
+  if (vals.empty()) return "[]string(nil)";
+  std::string o = "[]string{";
+  for (size_t i = 0; i < vals.size(); ++i) o += (i ? ", " : "") + go_quote(vals[i]);
+  return o + "}";
+}
+std::string join(const std::vector<std::string>& v, const char* sep) {
+  std::string o;
+  for (size_t i = 0; i < v.size(); ++i) o += (i ? sep : "") + v[i];
+  return o;
+}
+// labels.NewRequirement's error for one requirement ("" when it is fine): every complaint, key first, aggregated
+std::string requirement_error(const std::string& key, uint8_t op, bool equals, const std::vector<std::string>& vals) {
+  std::vector<std::string> all;
+  auto add = [&](const std::string& m) { if (std::find(all.begin(), all.end(), m) == all.end()) all.push_back(m); };
+  std::vector<std::string> e = is_qualified_name(key);
+  if (!e.empty()) add("key: Invalid value: " + go_quote(key) + ": " + join(e, "; "));
+  if (!equals && (op == KT_OP_IN || op == KT_OP_NOTIN) && vals.empty())
+    add("values: Invalid value: " + go_sharp_v(vals) + ": for 'in', 'notin' operators, values set can't be empty");
+  if ((op == KT_OP_EXISTS || op == KT_OP_DOESNOTEXIST) && !vals.empty())
+    add("values: Invalid value: " + go_sharp_v(vals) + ": values set must be empty for exists and does not exist");
+  for (size_t i = 0; i < vals.size(); ++i) {
+    e = is_valid_label_value(vals[i]);
+    if (!e.empty()) add("values[" + std::to_string(i) + "][" + key + "]: Invalid value: " + go_quote(vals[i]) + ": " + join(e, "; "));
+  }
+  if (all.empty()) return "";
+  return all.size() == 1 ? all[0] : "[" + join(all, ", ") + "]";
 }
 
 struct Requirement {
@@ -231,7 +298,7 @@ struct CompiledSelector {
 CompiledSelector compile_selector(const Node& sel) {
   CompiledSelector out;
   if (!sel.is(Node::Obj)) return out;
-  auto add = [&](const std::string& key, const std::string& opname, std::vector<std::string> values) {
+  auto add = [&](const std::string& key, const std::string& opname, std::vector<std::string> values, bool equals) {
     if (!out.error.empty()) return;
     Requirement r;
     r.key = key;
@@ -239,26 +306,20 @@ CompiledSelector compile_selector(const Node& sel) {
     else if (opname == "NotIn") r.op = KT_OP_NOTIN;
     else if (opname == "Exists") r.op = KT_OP_EXISTS;
     else if (opname == "DoesNotExist") r.op = KT_OP_DOESNOTEXIST;
-    else { out.error = "\"" + opname + "\" is not a valid label selector operator"; return; }
-    if ((r.op == KT_OP_IN || r.op == KT_OP_NOTIN) && values.empty()) { out.error = "values: Invalid value: []string(nil): for 'in', 'notin' operators, values set can't be empty"; return; }
-    if ((r.op == KT_OP_EXISTS || r.op == KT_OP_DOESNOTEXIST) && !values.empty()) { out.error = "values: Invalid value: []string{...}: values set must be empty for exists and does not exist"; return; }
-    std::string e = validate_label_key(key);
-    if (!e.empty()) { out.error = "key: Invalid value: \"" + key + "\": " + e; return; }
-    for (auto& v : values) {
-      e = validate_label_value(v);
-      if (!e.empty()) { out.error = "values[0][" + key + "]: Invalid value: \"" + v + "\": " + e; return; }
-    }
+    else { out.error = go_quote(opname) + " is not a valid label selector operator"; return; }
+    out.error = requirement_error(key, r.op, equals, values);
+    if (!out.error.empty()) return;
     r.values = std::move(values);
     out.reqs.push_back(std::move(r));
   };
   // matchLabels first, keys sorted (LabelSelectorAsSelector iterates a sorted key list), then matchExpressions in order
   std::map<std::string, std::string> ml;
   for (auto& kv : sel["matchLabels"].obj) ml[kv.first] = kv.second->str();
-  for (auto& kv : ml) add(kv.first, "In", {kv.second});
+  for (auto& kv : ml) add(kv.first, "In", {kv.second}, true);  // selection.Equals: exactly one value
   for (auto& e : sel["matchExpressions"].arr) {
     std::vector<std::string> vals;
     for (auto& v : (*e)["values"].arr) vals.push_back(v->str());
-    add((*e)["key"].str(), (*e)["operator"].str(), std::move(vals));
+    add((*e)["key"].str(), (*e)["operator"].str(), std::move(vals), false);
   }
   if (!out.error.empty()) out.reqs.clear();
   return out;
@@ -278,6 +339,7 @@ struct PodObj {
   std::string scheduler_name, node_name, phase;
   std::map<int, Quantity> request;  // PodRequestResourceList (resource id -> quantity); ResourceAmountOfPod adds Counts{1}
   int64_t row = -1;                 // slot in the running-pod table
+  uint64_t seq = 0;                 // order of first appearance (the informer-cache order the oracle iterates in; Q8)
   bool live = false;
   std::string nn() const { return ns + "/" + name; }
 };
@@ -375,6 +437,7 @@ struct kth_plugin {
   std::unordered_map<std::string, int64_t> pod_index;
   std::vector<int64_t> free_rows;
   std::set<int64_t> dirty_rows;
+  uint64_t next_pod_seq = 1;
   int64_t row_capacity = 0;  // rows the device table currently holds
   bool pods_full_upload = true;
 
@@ -989,6 +1052,57 @@ struct kth_plugin {
     const int Wp = kt_match_words(ctx);
     std::vector<uint32_t> words(rows.size() * (size_t)Wp);
     if (!rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)rows.size(), rows.data(), words.data()), "kt_get_match_rows");
+    // Q8 (throttle_controller.go:241, `terminatedPods = append(nonterminatedPods, pod)`): the THROTTLE controller's list of
+    // terminated affected pods ends up holding only the LAST terminated match of the namespace, so of the finished pods that
+    // still hold a reservation only that one is un-reserved; the others keep it until the pod is deleted.  (Which pod is "last"
+    // is the informer's map order in the reference; the oracle and this code take the order of first appearance.)  Needed only
+    // when a finished pod holds a reservation: then the match rows of the finished counted pods say who is last per throttle.
+    std::vector<char> row_finished(rows.size(), 0);
+    bool any_finished_reserved = false;
+    for (size_t i = 0; i < rows.size(); ++i) {
+      const PodObj& p = pods[(size_t)rows[i]];
+      row_finished[i] = p.live && !(pod_flags(p) & KT_POD_NOT_FINISHED);
+      any_finished_reserved |= row_finished[i] != 0;
+    }
+    std::vector<int64_t> fin_rows;
+    std::vector<uint32_t> fin_words;
+    if (any_finished_reserved) {
+      for (auto& p : pods)
+        if (p.live && should_count_in(p) && !(pod_flags(p) & KT_POD_NOT_FINISHED)) fin_rows.push_back(p.row);
+      fin_words.resize(fin_rows.size() * (size_t)Wp);
+      if (!fin_rows.empty()) check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)fin_rows.size(), fin_rows.data(), fin_words.data()), "kt_get_match_rows");
+    }
+    auto last_finished_match = [&](size_t t, const std::string& ns) -> int64_t {  // row of the last finished pod of ns that matches t
+      int64_t best = -1;
+      uint64_t best_seq = 0;
+      for (size_t i = 0; i < fin_rows.size(); ++i) {
+        const PodObj& p = pods[(size_t)fin_rows[i]];
+        if (p.ns != ns || !((fin_words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)) continue;
+        if (best < 0 || p.seq > best_seq) { best = p.row; best_seq = p.seq; }
+      }
+      return best;
+    };
+
+    // A Throttle with a podSelector term that does not convert: affectedPods (throttle_controller.go:221-246) only fails -- and
+    // the reconcile with it -- when some counted pod of the namespace actually REACHES that term, i.e. matches none of the
+    // valid terms before it (those are what the device column holds, sync_throttles).  The rows of the namespace's counted
+    // pods tell.  ClusterThrottles: see DESIGN.md "Known deviations" (their terms carry their own namespace scope).
+    std::vector<char> selector_fails(m, 0);
+    for (size_t t = 0; t < m; ++t) {
+      const ThrottleObj& o = throttles[t];
+      if (!o.live || o.throttler_name != name || o.selector_error().empty()) continue;
+      selector_fails[t] = 1;
+      if (o.kind != KT_KIND_THROTTLE) continue;
+      std::vector<int64_t> ns_rows;
+      for (auto& p : pods)
+        if (p.live && p.ns == o.ns && should_count_in(p)) ns_rows.push_back(p.row);
+      selector_fails[t] = 0;
+      if (ns_rows.empty()) continue;  // nobody to ask the selector about: no error
+      std::vector<uint32_t> w((size_t)ns_rows.size() * (size_t)Wp);
+      check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)ns_rows.size(), ns_rows.data(), w.data()), "kt_get_match_rows");
+      for (size_t i = 0; i < ns_rows.size() && !selector_fails[t]; ++i)
+        if (!((w[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)) selector_fails[t] = 1;
+    }
 
     int reconciled = 0;
     std::vector<std::string> changed;
@@ -996,7 +1110,7 @@ struct kth_plugin {
     for (size_t t = 0; t < m; ++t) {
       ThrottleObj& o = throttles[t];
       if (!o.live || o.throttler_name != name) continue;   // only responsible throttles are ever enqueued (:403-425)
-      if (!o.selector_error().empty()) continue;            // affectedPods fails -> reconcile returns the error, status untouched
+      if (selector_fails[t]) continue;                      // affectedPods fails -> reconcile returns the error, status untouched
       ++reconciled;
       ResAmount nu;  // used := ResourceAmount{}; used = used.Add(ResourceAmountOfPod(p)) ...
       if (used_present[t] & KT_COUNT_BIT) {
@@ -1037,12 +1151,20 @@ struct kth_plugin {
       if (status_changed) changed.push_back(o.nn());
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
-      // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache
+      // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache -- except, for a
+      // Throttle, the finished ones the reference's list loses (Q8)
       auto it = cache[o.kind].by_thr.find(o.nn());
-      if (it != cache[o.kind].by_thr.end())
-        for (size_t i = 0; i < rows.size(); ++i)
-          if ((words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)
-            if (it->second.erase(row_pod[i])) reserved_dirty = true;
+      if (it != cache[o.kind].by_thr.end()) {
+        int64_t last_fin = -2;  // computed on first need
+        for (size_t i = 0; i < rows.size(); ++i) {
+          if (!((words[i * (size_t)Wp + (t >> 5)] >> (t & 31)) & 1)) continue;
+          if (o.kind == KT_KIND_THROTTLE && row_finished[i]) {
+            if (last_fin == -2) last_fin = last_finished_match(t, o.ns);
+            if (rows[i] != last_fin) continue;
+          }
+          if (it->second.erase(row_pod[i])) reserved_dirty = true;
+        }
+      }
     }
     status_dirty = true;
     w.key("reconciled").num(reconciled).key("changed").begin_arr();
@@ -1282,6 +1404,7 @@ struct kth_plugin {
       if (!free_rows.empty()) { row = free_rows.back(); free_rows.pop_back(); }
       else { row = (int64_t)pods.size(); pods.emplace_back(); }
       p.row = row;
+      p.seq = next_pod_seq++;
       pod_index[p.nn()] = row;
       totals_add(p, +1);
       pods[(size_t)row] = std::move(p);
@@ -1294,6 +1417,7 @@ struct kth_plugin {
     const int64_t row = it->second;
     const PodObj old = pods[(size_t)row];
     p.row = row;
+    p.seq = old.seq;
     totals_add(old, -1);
     totals_add(p, +1);
     pods[(size_t)row] = std::move(p);

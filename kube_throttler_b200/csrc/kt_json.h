@@ -56,6 +56,12 @@ class Parser {
 
  private:
   const char* p_;
+  int depth_ = 0;  // nesting of the value being parsed: bounded, the parser recurses
+  struct Nest {
+    Parser& p;
+    explicit Nest(Parser& q) : p(q) { if (++p.depth_ > 256) p.fail("nested too deeply"); }
+    ~Nest() { --p.depth_; }
+  };
   [[noreturn]] void fail(const char* what) { throw std::runtime_error(std::string("json: ") + what); }
   void ws() {
     while (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r') ++p_;
@@ -122,6 +128,7 @@ class Parser {
     return out;
   }
   NodePtr value() {
+    Nest nest(*this);
     ws();
     auto n = std::make_shared<Node>();
     if (*p_ == '{') {

@@ -15,6 +15,7 @@
 // semantics (pkg/apis/meta/v1/helpers.go LabelSelectorAsSelector, pkg/labels/selector.go).
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -263,6 +264,120 @@ inline bool label_key_ok(const std::string& k) {
   return dns1123_subdomain_ok(prefix) && name_part_ok(name);
 }
 inline bool label_value_ok(const std::string& v) { return v.empty() || name_part_ok(v); }
+
+// ---- the error TEXT of labels.NewRequirement (apimachinery v0.26.4): what PreFilter's Error status carries -------------
+// field.Invalid(path, value, detail).Error() = `<path>: Invalid value: <%q or %#v of value>: <detail>`; the details are
+// validation.IsQualifiedName / IsValidLabelValue messages joined with "; " (each regex complaint with RegexError's
+// "(e.g. ..., regex used for validation is '...')" tail); several field errors aggregate to "[a, b]".
+inline std::string QuoteGo(const std::string& s) {
+  std::string out(1, '"');
+  char buf[8];
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': out += "\\\""; break;
+      case '\\': out += "\\\\"; break;
+      case '\n': out += "\\n"; break;
+      case '\r': out += "\\r"; break;
+      case '\t': out += "\\t"; break;
+      default:
+        if (c < 0x20 || c == 0x7f) { std::snprintf(buf, sizeof buf, "\\x%02x", c); out += buf; }
+        else out.push_back((char)c);
+    }
+  }
+  out.push_back('"');
+  return out;
+}
+inline std::string SharpVStrings(const std::vector<std::string>& v) {
+  if (v.empty()) return "[]string(nil)";
+  std::string out = "[]string{";
+  bool first = true;
+  for (auto& x : v) {
+    if (!first) out += ", ";
+    first = false;
+    out += QuoteGo(x);
+  }
+  return out + "}";
+}
+inline std::string RegexErrorText(std::string msg, const char* fmt, const std::vector<const char*>& examples) {
+  msg += " (e.g. ";
+  for (size_t i = 0; i < examples.size(); ++i) {
+    if (i > 0) msg += " or ";
+    msg += "'";
+    msg += examples[i];
+    msg += "', ";
+  }
+  msg += "regex used for validation is '";
+  msg += fmt;
+  msg += "')";
+  return msg;
+}
+inline bool regex_name(const std::string& s) {  // ([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9], no length rule
+  if (s.empty() || !is_alnum(s.front()) || !is_alnum(s.back())) return false;
+  for (char c : s)
+    if (!(is_alnum(c) || c == '-' || c == '_' || c == '.')) return false;
+  return true;
+}
+inline bool regex_subdomain(const std::string& s) {  // dns1123SubdomainFmt alone (the length rule is a separate complaint)
+  size_t start = 0;
+  while (true) {
+    size_t dot = s.find('.', start);
+    std::string lab = s.substr(start, dot == std::string::npos ? std::string::npos : dot - start);
+    if (lab.empty()) return false;
+    auto la = [](char c) { return (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9'); };
+    if (!la(lab.front()) || !la(lab.back())) return false;
+    for (char c : lab)
+      if (!(la(c) || c == '-')) return false;
+    if (dot == std::string::npos) return true;
+    start = dot + 1;
+  }
+}
+static const char* const kQNameMsg = "must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character";
+static const char* const kQNameFmt = "([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]";
+inline std::vector<std::string> QualifiedNameErrors(const std::string& value) {
+  std::vector<std::string> errs;
+  std::vector<std::string> parts;
+  size_t b = 0;
+  while (true) {
+    size_t e = value.find('/', b);
+    parts.push_back(value.substr(b, e == std::string::npos ? std::string::npos : e - b));
+    if (e == std::string::npos) break;
+    b = e + 1;
+  }
+  std::string name;
+  if (parts.size() == 1) name = parts[0];
+  else if (parts.size() == 2) {
+    const std::string& prefix = parts[0];
+    name = parts[1];
+    if (prefix.empty()) errs.push_back("prefix part must be non-empty");
+    else {
+      if (prefix.size() > 253) errs.push_back("prefix part must be no more than 253 characters");
+      if (!regex_subdomain(prefix))
+        errs.push_back("prefix part " + RegexErrorText("a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with an alphanumeric character",
+                                                       "[a-z0-9]([-a-z0-9]*[a-z0-9])?(\\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*", {"example.com"}));
+    }
+  } else {
+    errs.push_back("a qualified name " + RegexErrorText(kQNameMsg, kQNameFmt, {"MyName", "my.name", "123-abc"}) +
+                   " with an optional DNS subdomain prefix and '/' (e.g. 'example.com/MyName')");
+    return errs;
+  }
+  if (name.empty()) errs.push_back("name part must be non-empty");
+  else if (name.size() > 63) errs.push_back("name part must be no more than 63 characters");
+  if (!regex_name(name)) errs.push_back("name part " + RegexErrorText(kQNameMsg, kQNameFmt, {"MyName", "my.name", "123-abc"}));
+  return errs;
+}
+inline std::vector<std::string> LabelValueErrors(const std::string& v) {
+  std::vector<std::string> errs;
+  if (v.size() > 63) errs.push_back("must be no more than 63 characters");
+  if (!v.empty() && !regex_name(v))
+    errs.push_back(RegexErrorText("a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character",
+                                  "(([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9])?", {"MyValue", "my_value", "12345"}));
+  return errs;
+}
+inline std::string JoinStr(const std::vector<std::string>& v, const char* sep) {
+  std::string out;
+  for (size_t i = 0; i < v.size(); ++i) { if (i) out += sep; out += v[i]; }
+  return out;
+}
 }  // namespace detail
 
 // A compiled requirement (labels.Requirement).  "=" from matchLabels is selection.Equals, same
@@ -289,15 +404,24 @@ struct Requirement {
 inline std::vector<Requirement> LabelSelectorAsSelector(const LabelSelector& ps, SelectorError* err) {
   std::vector<Requirement> reqs;
   auto add = [&](const std::string& key, Requirement::Op op, const std::vector<std::string>& vals, bool equals) {
-    if (!detail::label_key_ok(key)) { err->failed = true; err->msg = "key: Invalid value: \"" + key + "\""; return; }
-    if ((op == Requirement::In || op == Requirement::NotIn) && !equals && vals.empty()) {
-      err->failed = true; err->msg = "values: Invalid value: []string(nil): for 'in', 'notin' operators, values set can't be empty"; return;
+    // labels.NewRequirement: the key first, then the value count for the operator, then every value; all complaints are kept
+    std::vector<std::string> all;
+    auto keep = [&](std::string m) { if (std::find(all.begin(), all.end(), m) == all.end()) all.push_back(std::move(m)); };
+    std::vector<std::string> ke = detail::QualifiedNameErrors(key);
+    if (!ke.empty()) keep("key: Invalid value: " + detail::QuoteGo(key) + ": " + detail::JoinStr(ke, "; "));
+    if ((op == Requirement::In || op == Requirement::NotIn) && !equals && vals.empty())
+      keep("values: Invalid value: " + detail::SharpVStrings(vals) + ": for 'in', 'notin' operators, values set can't be empty");
+    if ((op == Requirement::Exists || op == Requirement::DoesNotExist) && !vals.empty())
+      keep("values: Invalid value: " + detail::SharpVStrings(vals) + ": values set must be empty for exists and does not exist");
+    for (size_t i = 0; i < vals.size(); ++i) {
+      std::vector<std::string> ve = detail::LabelValueErrors(vals[i]);
+      if (!ve.empty()) keep("values[" + std::to_string(i) + "][" + key + "]: Invalid value: " + detail::QuoteGo(vals[i]) + ": " + detail::JoinStr(ve, "; "));
     }
-    if ((op == Requirement::Exists || op == Requirement::DoesNotExist) && !vals.empty()) {
-      err->failed = true; err->msg = "values: Invalid value: values set must be empty for exists and does not exist"; return;
+    if (!all.empty()) {
+      err->failed = true;
+      err->msg = all.size() == 1 ? all[0] : "[" + detail::JoinStr(all, ", ") + "]";
+      return;
     }
-    for (auto& v : vals)
-      if (!detail::label_value_ok(v)) { err->failed = true; err->msg = "values[0][" + key + "]: Invalid value: \"" + v + "\""; return; }
     Requirement r;
     r.key = key;
     r.op = op;
@@ -314,7 +438,7 @@ inline std::vector<Requirement> LabelSelectorAsSelector(const LabelSelector& ps,
     else if (e.op == "NotIn") op = Requirement::NotIn;
     else if (e.op == "Exists") op = Requirement::Exists;
     else if (e.op == "DoesNotExist") op = Requirement::DoesNotExist;
-    else { err->failed = true; err->msg = "\"" + e.op + "\" is not a valid label selector operator"; return {}; }
+    else { err->failed = true; err->msg = detail::QuoteGo(e.op) + " is not a valid label selector operator"; return {}; }
     add(e.key, op, e.values, false);
     if (err->failed) return {};
   }
@@ -840,12 +964,15 @@ struct World {
     return "";
   }
 
+  // Every key is reconciled on its own in the reference (workqueue items; an error re-queues that key and nothing else,
+  // controller.go:95-122): a failing throttle does not keep the others from being reconciled.  Returns the first error.
   std::string reconcileAll(const Time& now) {
+    std::string first;
     for (auto& t : throttles)
-      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty() && first.empty()) first = e; }
     for (auto& t : clusterThrottles)
-      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty()) return e; }
-    return "";
+      if (isResponsibleFor(*t)) { std::string e = reconcile(*t, now); if (!e.empty() && first.empty()) first = e; }
+    return first;
   }
 
   // ---- affectedThrottles: throttle_controller.go:248-269 ----

@@ -361,3 +361,122 @@ def test_objects_beyond_the_limits_are_rejected_not_fatal(new_plugin):
     assert w.prefilter(pod("default", "x", "800m", {"a": "1"}))["reasons"] == ["throttle[insufficient]=default/t"]
     assert w.prefilter(pod("default", "y", "700m", {"a": "1"}))["code"] == "Success"
     w.close()
+
+
+def test_selector_errors_q9(oracle, new_plugin):
+    """Q9: a podSelector that LabelSelectorAsSelector rejects makes PreFilter return framework.Error with the conversion error
+    for every pod the controller would have asked it about (plugin.go:154-156,166-168), and keeps that throttle -- only that
+    one -- from being reconciled; a namespaceSelector that fails to convert is swallowed and simply never matches
+    (clusterthrottle_selector.go:65-67,74-76)."""
+    from test_scenarios import pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    bad = {"matchExpressions": [{"key": "a", "operator": "In", "values": []}]}
+    spec = lambda terms: {"throttlerName": THROTTLER, "threshold": {"resourceRequests": {"cpu": "1"}}, "selector": {"selectorTerms": terms}}
+    both(namespace("default", {"team": "x"}), namespace("other", {"team": "y"}), throttle("default", "ok", {"a": "1"}, cpu="1"),
+         {"kind": "ClusterThrottle", "metadata": {"name": "cbadns"}, "spec": spec([{"namespaceSelector": bad, "podSelector": {"matchLabels": {"a": "1"}}}])},
+         pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"), pod("other", "p1", "300m", {"a": "1"}, node="n", phase="Running"))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    for name, ns in (("ok", "default"), ("cbadns", "")):
+        assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns))
+    assert "resourceCounts" not in dut.status("cbadns")["used"]  # the swallowed namespace-selector error: nothing ever matches
+    probes = [pod("default", "x", "100m", {"a": "1"}), pod("other", "y", "100m", {"a": "1"}), pod("default", "z", "100m", {"q": "1"})]
+    for p in probes:
+        assert norm_prefilter(ref.prefilter(p)) == norm_prefilter(dut.prefilter(p))
+
+    def verdict(w, p):  # what the scheduler sees of an Error status: the code and the message
+        r = w.prefilter(p)
+        return r["code"], r["reasons"]
+
+    both({"kind": "Throttle", "metadata": {"namespace": "default", "name": "bad"}, "spec": spec([{"podSelector": bad}])})
+    with pytest.raises(RuntimeError, match="values set can't be empty"):
+        ref.reconcile_all(NOW)      # the oracle reports the failing key; the others were reconciled all the same
+    dut.reconcile_all(NOW)
+    assert norm_status(ref.status("ok", "default")) == norm_status(dut.status("ok", "default"))
+    assert norm_status(ref.status("bad", "default")) == norm_status(dut.status("bad", "default"))  # untouched: never reconciled
+    for p in probes:
+        assert verdict(ref, p) == verdict(dut, p)
+    assert verdict(dut, probes[0])[0] == "Error" and verdict(dut, probes[1])[0] != "Error"  # only the namespace of the broken Throttle
+    both({"kind": "ClusterThrottle", "metadata": {"name": "cbadpod"}, "spec": spec([{"namespaceSelector": {"matchLabels": {"team": "y"}}, "podSelector": bad}])})
+    for p in probes:
+        assert verdict(ref, p) == verdict(dut, p)
+    assert verdict(dut, probes[1])[0] == "Error"  # its namespaceSelector picks "other": pods there now get the conversion error
+    dut.close()
+
+
+def test_selector_error_behind_a_valid_term(oracle, new_plugin):
+    """MatchesToPod walks the terms in order and returns at the first match (throttle_selector.go:30-42): a term that does not
+    convert only hurts the pods that get as far as it.  A Throttle {valid term, broken term} is reconciled as long as every
+    counted pod of its namespace matches the valid term, stops being reconciled when one does not, and PreFilter fails only for
+    the pods that reach the broken term."""
+    from test_scenarios import pod
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    bad = {"matchExpressions": [{"key": "a", "operator": "Exists", "values": ["x"]}]}
+    mixed = {"kind": "Throttle", "metadata": {"namespace": "default", "name": "mixed"},
+             "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 2}, "resourceRequests": {"cpu": "1"}},
+                      "selector": {"selectorTerms": [{"podSelector": {"matchLabels": {"a": "1"}}}, {"podSelector": bad}, {"podSelector": {"matchLabels": {"b": "1"}}}]}}}
+    both(namespace("default"), namespace("other"), mixed)
+
+    def reconcile_both():
+        try:
+            ref.reconcile_all(NOW)
+            ok = True
+        except RuntimeError:
+            ok = False
+        dut.reconcile_all(NOW)
+        assert norm_status(ref.status("mixed", "default")) == norm_status(dut.status("mixed", "default"))
+        return ok
+
+    assert reconcile_both()  # no pod has asked the selector anything yet
+    assert dut.status("mixed", "default")["calculatedThreshold"]["calculatedAtSet"] is True
+    both(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"), pod("default", "p1", "300m", {"a": "1", "b": "1"}, node="n", phase="Succeeded"),
+         pod("other", "elsewhere", "300m", {"c": "1"}, node="n", phase="Running"), pod("default", "unscheduled", "300m", {"c": "1"}))
+    assert reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 1
+    both(pod("default", "p2", "300m", {"b": "1"}, node="n", phase="Running"))  # matches only the term BEHIND the broken one
+    assert not reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 1  # untouched
+    for p in (pod("default", "x", "100m", {"a": "1"}), pod("default", "y", "100m", {"b": "1"}), pod("default", "z", "100m", {}), pod("other", "w", "100m", {"b": "1"})):
+        a, b = ref.prefilter(p), dut.prefilter(p)
+        assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+    both(pod("default", "p2", "300m", {"a": "1", "b": "1"}, node="n", phase="Running"))  # relabelled: now the valid term takes it
+    both(pod("default", "p3", "400m", {"a": "1"}, node="n", phase="Running"))
+    assert reconcile_both()
+    assert dut.status("mixed", "default")["used"]["resourceCounts"]["pod"] == 3 and dut.status("mixed", "default")["throttled"]["resourceCounts"]["pod"] is True
+    dut.close()
+
+
+def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
+    """Q8: `terminatedPods = append(nonterminatedPods, pod)` (throttle_controller.go:241) leaves only the LAST finished match in
+    the Throttle controller's list, so a reconcile un-reserves the running pods it observes and one finished pod; the other
+    finished pods keep their reservation (and keep counting against later pods).  ClusterThrottles (correct code,
+    clusterthrottle_controller.go:266) un-reserve all of them."""
+    from test_scenarios import clthrottle, pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="10"), clthrottle("c", {"kubernetes.io/metadata.name": "default"}, {"a": "1"}, cpu="10"))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    queue = [pod("default", f"q{i}", "1", {"a": "1"}) for i in range(4)]
+    for p in queue:
+        assert ref.prefilter(p)["code"] == dut.prefilter(p)["code"] == "Success"
+        assert ref.reserve(p)["code"] == dut.reserve(p)["code"] == "Success"
+    # q0 and q2 ran to completion before the next reconcile, q1 is running, q3 is still only reserved
+    both(dict(queue[0], spec=dict(queue[0]["spec"], nodeName="n"), status={"phase": "Succeeded"}),
+         dict(queue[1], spec=dict(queue[1]["spec"], nodeName="n"), status={"phase": "Running"}),
+         dict(queue[2], spec=dict(queue[2]["spec"], nodeName="n"), status={"phase": "Failed"}))
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    for kind, nn in (("Throttle", "default/t"), ("ClusterThrottle", "/c")):
+        a, b = ref.reserved(kind, nn), dut.reserved(kind, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (nn, a, b)
+    assert sorted(dut.reserved("Throttle", "default/t")["pods"]) == ["default/q0", "default/q3"]  # q2 (the last finished one) and q1 left
+    assert dut.reserved("ClusterThrottle", "/c")["pods"] == ["default/q3"]
+    for name, ns in (("t", "default"), ("c", "")):
+        assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns))
+    probe = pod("default", "x", "7500m", {"a": "1"})  # used 1 (q1) + reserved: 2 on the Throttle, 1 on the ClusterThrottle
+    assert norm_prefilter(ref.prefilter(probe)) == norm_prefilter(dut.prefilter(probe))
+    assert dut.prefilter(probe)["reasons"] == ["throttle[insufficient]=default/t"]
+    dut.close()

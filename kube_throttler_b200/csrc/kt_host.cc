@@ -444,6 +444,8 @@ struct kth_plugin {
   std::vector<ThrottleObj> throttles;  // column order == device order (both kinds interleaved, insertion order)
   std::unordered_map<std::string, int> thr_index;  // "T:ns/name" | "C:/name"
   bool throttles_dirty = true, namespaces_dirty = true, status_dirty = true, reserved_dirty = true;
+  std::vector<size_t> broken;  // columns of the throttles with a podSelector that does not convert (controller_error)
+  bool broken_valid = false;
 
   ReservationCache cache[2];  // one per controller (controller.go:34-50)
   int max_labels = 0, max_ns_labels = 0;
@@ -1206,10 +1208,14 @@ struct kth_plugin {
     check(kt_get_match_bitmap(ctx, KT_PODS_PENDING, out.bitmap.data()), "kt_get_match_bitmap");
     return out;
   }
-  std::vector<int> affected(const PendingResult& r, size_t i, int kind) const {
+  std::vector<int> affected(const PendingResult& r, size_t i, int kind) const {  // the set bits of the pod's match row, in column order
     std::vector<int> out;
-    for (size_t t = 0; t < throttles.size(); ++t)
-      if (throttles[t].kind == kind && ((r.bitmap[i * (size_t)r.Wp + (t >> 5)] >> (t & 31)) & 1)) out.push_back((int)t);
+    const uint32_t* row = &r.bitmap[i * (size_t)r.Wp];
+    for (int w = 0; w < r.Wp; ++w)
+      for (uint32_t bits = row[w]; bits; bits &= bits - 1) {
+        const size_t t = (size_t)w * 32 + (size_t)__builtin_ctz(bits);
+        if (t < throttles.size() && throttles[t].kind == kind) out.push_back((int)t);
+      }
     return out;
   }
   // affectedThrottles / affectedClusterThrottles error paths that never reach the device:
@@ -1219,7 +1225,13 @@ struct kth_plugin {
       const int id = ns_dict.find(pod.ns);
       if (id < 0 || !namespaces[(size_t)id].exists) return "namespace \"" + pod.ns + "\" not found";  // namespaceInformer.Lister().Get (clusterthrottle_controller.go:273-276)
     }
-    for (size_t t = 0; t < throttles.size(); ++t) {
+    if (!broken_valid) {  // the throttles whose podSelector does not convert: usually none, so not a walk over all of them per pod
+      broken.clear();
+      for (size_t t = 0; t < throttles.size(); ++t)
+        if (throttles[t].live && !throttles[t].selector_error().empty()) broken.push_back(t);
+      broken_valid = true;
+    }
+    for (size_t t : broken) {
       const ThrottleObj& o = throttles[t];
       if (!o.live || o.kind != kind || o.throttler_name != name) continue;
       const std::string e = o.selector_error();
@@ -1538,6 +1550,7 @@ struct kth_plugin {
       old = std::move(o);
     }
     throttles_dirty = status_dirty = reserved_dirty = true;
+    broken_valid = false;
   }
   void delete_throttle(int kind, const std::string& ns, const std::string& tname) {
     const std::string nn = (kind == KT_KIND_THROTTLE ? ns : std::string()) + "/" + tname;
@@ -1551,6 +1564,7 @@ struct kth_plugin {
     cache[kind].by_thr.erase(nn);
     thr_index.erase(it);
     throttles_dirty = status_dirty = reserved_dirty = true;
+    broken_valid = false;
   }
 
   std::string status_json(const std::string& ns, const std::string& tname) {

@@ -62,6 +62,7 @@ def test_c1_example(kt, oracle):
     dict(config="C2", m=40, n=70, p=33, R=1),                             # ragged: partial tiles, partial last word
     dict(config="C3", m=200, n=5000, p=700, L=12),                        # L > 8: label rows staged in shared memory
     dict(config="C2", m=200, n=5000, p=700, L=12, q_max=6),               # terms with > 3 required keys: 6-bit counters
+    dict(config="C3", m=120, n=2000, p=300, R=31, L=16),                  # the limits: every resource bit in use, two label chunks
     dict(config="C3", m=64, n=3000, p=400, L=3, R=2),                     # fewer label slots than a chunk
 ])
 def test_scaled_configs(kt, oracle, kw):

@@ -363,8 +363,13 @@ def main():
     # indices, presence inside the meta word)
     packed = None
     try:
-        pr, pp_ = abi.packed_pods(r), abi.packed_pods(p)
-        packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), pin(c.req32), pin(c.req_shift), pin(c.meta)) for c in (pr, pp_))
+        try:  # request columns as 1- or 2-byte dictionary codes when every column has at most 65536 distinct values
+            pr, pp_ = abi.packed_pods(r, code_requests=True), abi.packed_pods(p, code_requests=True)
+            packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), None, None, pin(c.meta), pin(c.req_dict), pin(c.req_dict_off),
+                                             pin(c.req_code_bytes), pin(c.req_codes)) for c in (pr, pp_))
+        except ValueError:
+            pr, pp_ = abi.packed_pods(r), abi.packed_pods(p)
+            packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), pin(c.req32), pin(c.req_shift), pin(c.meta)) for c in (pr, pp_))
     except ValueError:
         pass
     packed_wc = None
@@ -377,7 +382,9 @@ def main():
             pinned.append(b)
             return b.array
 
-        packed_wc = tuple(abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), pin_wc(c.req32), pin(c.req_shift), pin_wc(c.meta)) for c in packed)
+        packed_wc = tuple(abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), None, None, pin_wc(c.meta), pin_wc(c.req_dict), pin(c.req_dict_off),
+                                            pin(c.req_code_bytes), pin_wc(c.req_codes)) if c.coded else
+                          abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), pin_wc(c.req32), pin(c.req_shift), pin_wc(c.meta)) for c in packed)
     elif compact:
         h2d = h2d_compact
 

@@ -238,6 +238,17 @@ typedef struct {
   const int32_t* req32;      /* [R][n] */
   const int32_t* req_shift;  /* [R] */
   const uint32_t* meta;      /* [n] */
+  /* Optional, instead of req32 / req_shift (both may then be NULL): dictionary-coded request columns.  Pods come from a few
+   * templates, so a column of 10^5 requests holds a few dozen distinct values: 1 byte per value instead of 4.
+   *   req_dict[...]          the distinct values, column after column (exact int64, the engine's own unit)
+   *   req_dict_off[R+1]      column r's values are req_dict[req_dict_off[r] .. req_dict_off[r+1])
+   *   req_code_bytes[R]      1 or 2: width of column r's codes (at most 256 / 65536 distinct values)
+   *   req_codes              the code columns one after another, column r = n little-endian codes of req_code_bytes[r] bytes,
+   *                          each column padded to a multiple of 4 bytes */
+  const int64_t* req_dict;
+  const int32_t* req_dict_off;
+  const uint8_t* req_code_bytes;
+  const uint8_t* req_codes;
 } kt_packed_pods;
 int kt_upload_pods_packed(kt_ctx* ctx, int kind, int64_t n, const kt_packed_pods* rows);
 /* With async uploads on, kt_upload_pods / kt_upload_pods_compact return as soon as the copies are QUEUED: the caller must

@@ -49,12 +49,13 @@ struct PodStore {
   bool roff_valid = false;  // false after a full upload or a table compile; row deltas translate their own rows
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
   DevBuf c_pairs;                  // label-pair dictionary of the packed transfer format (kt_upload_pods_packed)
+  DevBuf c_dict;                   // request-value dictionaries of the same format
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
     labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release();
     roff_valid = false;
-    c_labels.release(); c_req.release(); c_meta.release(); c_pairs.release();
+    c_labels.release(); c_req.release(); c_meta.release(); c_pairs.release(); c_dict.release();
     t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
   }
 };
@@ -647,14 +648,35 @@ int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* 
   if (!c) return KT_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
-  if (n < 0 || !pk || !pk->req_shift || (n > 0 && (!pk->labels16 || !pk->req32 || !pk->meta))) return fail(c, KT_ERR_INVALID, "null packed pod columns");
+  if (n < 0 || !pk || (n > 0 && (!pk->labels16 || !pk->meta))) return fail(c, KT_ERR_INVALID, "null packed pod columns");
+  const bool coded = pk->req_codes != nullptr;
+  if (coded ? (!pk->req_dict_off || !pk->req_code_bytes) : (!pk->req_shift || (n > 0 && !pk->req32)))
+    return fail(c, KT_ERR_INVALID, "packed pod rows need either req32 + req_shift or req_codes + req_dict_off + req_code_bytes");
   const int L = c->lim.label_slots, R = c->lim.n_resources, Lpad = (L + 7) & ~7;
+  ReqCodes rc{};
+  size_t code_bytes = 0, dict_len = 0;
+  if (coded) {
+    for (int r = 0; r < R; ++r) {
+      const int b = pk->req_code_bytes[r];
+      const int64_t d0 = pk->req_dict_off[r], d1 = pk->req_dict_off[r + 1];
+      if ((b != 1 && b != 2) || d0 < 0 || d1 < d0 || d1 - d0 > (b == 1 ? 256 : 65536)) return fail(c, KT_ERR_INVALID, "request dictionary of column %d is malformed", r);
+      rc.col_off[r] = (uint32_t)code_bytes;
+      rc.dict_off[r] = (uint32_t)d0;
+      rc.dict_len[r] = (uint32_t)(d1 - d0);
+      rc.bytes[r] = (unsigned char)b;
+      code_bytes += ((size_t)n * (size_t)b + 3) & ~(size_t)3;
+      if (code_bytes >= ((size_t)1 << 32)) return fail(c, KT_ERR_LIMIT, "request code columns exceed 4 GiB");
+    }
+    dict_len = (size_t)pk->req_dict_off[R];
+    if (dict_len > 0 && !pk->req_dict) return fail(c, KT_ERR_INVALID, "null request dictionary");
+  }
   if (pk->n_pairs < 0 || pk->n_pairs > 65535 || (pk->n_pairs > 0 && !pk->pairs)) return fail(c, KT_ERR_INVALID, "n_pairs %d outside 0..65535", pk->n_pairs);
   if (pk->ns_bits < 1 || pk->ns_bits + 3 + R > 32) return fail(c, KT_ERR_INVALID, "ns_bits %d: ns_bits + 3 + R must fit 32 bits", pk->ns_bits);
-  for (int r = 0; r < R; ++r)
-    if (pk->req_shift[r] < 0 || pk->req_shift[r] > 32) return fail(c, KT_ERR_INVALID, "req_shift[%d] = %d outside 0..32", r, pk->req_shift[r]);
-  int rc = set_device(c);
-  if (rc) return rc;
+  if (!coded)
+    for (int r = 0; r < R; ++r)
+      if (pk->req_shift[r] < 0 || pk->req_shift[r] > 32) return fail(c, KT_ERR_INVALID, "req_shift[%d] = %d outside 0..32", r, pk->req_shift[r]);
+  int err = set_device(c);
+  if (err) return err;
   PodStore& s = c->pods[kind];
   KT_CUDA(c, s.labels.reserve((size_t)Lpad * n * 8 + 16));
   KT_CUDA(c, s.req.reserve((size_t)R * n * 8 + 16));
@@ -664,14 +686,20 @@ int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* 
   // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
   KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
   if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (rc = upload(c, s.c_req, pk->req32, (size_t)R * n)) ||
-      (rc = upload(c, s.c_meta, pk->meta, (size_t)n)))
-    return rc;
+  if ((err = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (err = upload(c, s.c_meta, pk->meta, (size_t)n))) return err;
+  if (coded) {
+    if ((err = upload(c, s.c_req, pk->req_codes, code_bytes)) || (err = upload(c, s.c_dict, pk->req_dict, dict_len))) return err;
+    rc.codes = s.c_req.as<unsigned char>();
+    rc.dict = s.c_dict.as<int64_t>();
+  } else if ((err = upload(c, s.c_req, pk->req32, (size_t)R * n))) {
+    return err;
+  }
   if (n > 0) {
     ReqShifts sh{};
-    for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)pk->req_shift[r];
+    if (!coded)
+      for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)pk->req_shift[r];
     k_unpack_packed<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, pk->ns_bits, pk->n_pairs, s.c_pairs.as<int64_t>(), s.c_labels.as<uint16_t>(),
-                                                                        s.c_req.as<int32_t>(), sh, s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(),
+                                                                        s.c_req.as<int32_t>(), sh, rc, s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(),
                                                                         s.req.as<int64_t>(), s.present.as<uint32_t>(), s.flags.as<uint32_t>(), s.ns.as<int32_t>());
     KT_CUDA(c, cudaGetLastError());
   }

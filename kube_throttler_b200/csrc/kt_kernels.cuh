@@ -1250,11 +1250,21 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
 
 struct ReqShifts { unsigned char s[32]; };  // per-column left shift of the 32-bit transfer requests (by value, in the launch arguments)
 
+// dictionary-coded request columns of the packed transfer format (by value in the launch arguments; codes == nullptr: not used)
+struct ReqCodes {
+  const unsigned char* codes;   // the code columns, one after another
+  const int64_t* dict;          // the value dictionaries, one after another
+  uint32_t col_off[32];         // byte offset of column r inside codes (multiples of 4)
+  uint32_t dict_off[32];        // first dictionary entry of column r
+  uint32_t dict_len[32];
+  unsigned char bytes[32];      // 1 or 2
+};
+
 // Packed transfer rows (kt_upload_pods_packed: 16-bit label-pair indices, presence inside the meta word) -> the int64 HBM
 // columns.  One lane per pod row, coalesced; the pair dictionary (a few KB) stays in L1.
 __global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpad, int R, int ns_bits, int n_pairs, const int64_t* __restrict__ pairs,
                                                        const uint16_t* __restrict__ labels16, const int32_t* __restrict__ req32, const ReqShifts req_shift,
-                                                       const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
+                                                       const ReqCodes rc, const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
                                                        uint32_t* __restrict__ present, uint32_t* __restrict__ flags, int32_t* __restrict__ ns) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -1266,7 +1276,15 @@ __global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpa
     }
     labels[(int64_t)s * n + p] = lab;
   }
-  for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
+  if (rc.codes) {
+    for (int r = 0; r < R; ++r) {
+      const unsigned char* col = rc.codes + rc.col_off[r];
+      const uint32_t code = rc.bytes[r] == 1 ? (uint32_t)__ldg(&col[p]) : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(col) + p);
+      req[(int64_t)r * n + p] = code < rc.dict_len[r] ? __ldg(&rc.dict[rc.dict_off[r] + code]) : 0;
+    }
+  } else {
+    for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
+  }
   const uint32_t m = __ldg(&meta[p]);
   ns[p] = (int32_t)(m & ((1u << ns_bits) - 1u));
   flags[p] = (m >> ns_bits) & 7u;

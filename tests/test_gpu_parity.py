@@ -241,15 +241,17 @@ def test_packed_upload_equals_wide_upload(kt, oracle):
         snap = synth.generate(kw.pop("config"), **kw)
         eng = kt.Engine(snap.R, snap.L, snap.LN)
         eng.upload_snapshot(snap)
-        for kind, pods in ((abi.PODS_RUNNING, snap.running), (abi.PODS_PENDING, snap.pending)):
-            pk = abi.packed_pods(pods)
-            assert pk.nbytes < 0.65 * sum(a.nbytes for a in (pods.labels, pods.req, pods.present, pods.flags, pods.ns_id))
-            eng.upload_pods_packed(kind, pk)
-        eng.evaluate(snap.now)
-        got = eng.download()
+        want = None
+        for coded in (False, True):  # int32 request columns, then dictionary-coded ones
+            for kind, pods in ((abi.PODS_RUNNING, snap.running), (abi.PODS_PENDING, snap.pending)):
+                pk = abi.packed_pods(pods, code_requests=coded)
+                assert pk.nbytes < 0.65 * sum(a.nbytes for a in (pods.labels, pods.req, pods.present, pods.flags, pods.ns_id))
+                eng.upload_pods_packed(kind, pk)
+            eng.evaluate(snap.now)
+            got = eng.download()
+            want = want or oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
+            assert_same(snap, got, want)
         eng.close()
-        want = oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
-        assert_same(snap, got, want)
 
 
 @pytest.mark.parametrize("fused", [True, False])

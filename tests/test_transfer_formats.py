@@ -20,6 +20,26 @@ def test_packed_round_trip(kw):
             assert np.array_equal(getattr(back, f), getattr(pods, f)), f
         assert pk.labels16.dtype == np.uint16 and pk.meta.dtype == np.uint32 and pk.req32.dtype == np.int32
         assert pk.ns_bits + 3 + pods.req.shape[0] <= 32
+        coded = abi.packed_pods(pods, code_requests=True)  # dictionary-coded request columns: same rows, fewer bytes
+        back = coded.unpack()
+        for f in FIELDS:
+            assert np.array_equal(getattr(back, f), getattr(pods, f)), f
+        assert coded.req32 is None and coded.req_codes.dtype == np.uint8 and coded.req_codes.shape[0] % 4 == 0
+        assert coded.nbytes <= pk.nbytes + 8 * int(coded.req_dict.shape[0]) + 64
+
+
+def test_coded_requests_pick_the_code_width_per_column():
+    pods = synth.generate("C2", m=20, n=3000, p=5).running
+    pods.req[1] = np.arange(3000, dtype=np.int64) * 7 - 11   # 3000 distinct values, negatives included: 2-byte codes
+    pk = abi.packed_pods(pods, code_requests=True)
+    assert list(pk.req_code_bytes) == [1, 2, 1, 1]
+    assert np.array_equal(pk.unpack().req, pods.req)
+    pods.req[2, :] = 0                                        # a constant column: one dictionary entry
+    assert np.array_equal(abi.packed_pods(pods, code_requests=True).unpack().req, pods.req)
+    big = synth.generate("C2", m=10, n=70000, p=3).running
+    big.req[0] = np.arange(70000, dtype=np.int64)
+    with pytest.raises(ValueError):
+        abi.packed_pods(big, code_requests=True)
 
 
 def test_packed_refuses_what_it_cannot_carry():

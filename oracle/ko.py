@@ -59,6 +59,8 @@ def lib():
         L.ko_world_new.argtypes = [C.c_char_p, C.c_char_p]
         L.ko_world_free.argtypes = [C.c_void_p]
         L.ko_world_apply.argtypes = [C.c_void_p, C.c_char_p]
+        L.ko_world_delete_pod.restype = C.c_char_p
+        L.ko_world_delete_pod.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.ko_world_reconcile_all.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_world_get_status.restype = C.c_char_p
         L.ko_world_get_status.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
@@ -113,6 +115,12 @@ class World:
     def apply(self, *manifests):
         for m in manifests:
             self._json(lib().ko_world_apply(self._h, json.dumps(m).encode()))
+
+    def delete(self, kind, name, namespace=""):
+        """Informer Delete event; only pods are modelled (host.Plugin.delete has the same signature)."""
+        if kind != "Pod":
+            raise NotImplementedError("the oracle models pod deletes only")
+        return self._json(lib().ko_world_delete_pod(self._h, namespace.encode(), name.encode()))
 
     def reconcile_all(self, now="2026-01-01T00:00:00Z"):
         return self._json(lib().ko_world_reconcile_all(self._h, now.encode()))

@@ -326,6 +326,16 @@ void* ko_world_new(const char* throttler_name, const char* target_scheduler_name
 }
 void ko_world_free(void* h) { delete (KoWorld*)h; }
 
+// pod informer Delete event
+const char* ko_world_delete_pod(void* h, const char* ns, const char* name) {
+  try {
+    ((KoWorld*)h)->w.deletePod(ns ? ns : "", name ? name : "");
+    return ret(Value::object());
+  } catch (const std::exception& e) {
+    return ret(err_obj(e.what()));
+  }
+}
+
 // apply one manifest (kind: Pod | Namespace | Throttle | ClusterThrottle); upsert by name
 const char* ko_world_apply(void* h, const char* json) {
   try {

@@ -1112,6 +1112,21 @@ struct World {
     }
     upsertPod(std::move(p));
   }
+
+  // ---- pod informer Delete event (throttle_controller.go:508-531, clusterthrottle_controller.go:536-559): both controllers
+  // un-reserve a counted, scheduled pod from its affected throttles (errors are only logged); the informer's store has
+  // dropped the pod either way. ----
+  void deletePod(const std::string& ns, const std::string& name) {
+    auto it = podIndex.find(ns + "/" + name);
+    if (it == podIndex.end()) return;
+    const size_t idx = it->second;
+    const Pod old = *pods[idx];
+    if (shouldCountIn(old) && isScheduled(old)) Unreserve(old);
+    podIndex.erase(it);
+    auto& list = podsByNs[ns];
+    list.erase(std::remove(list.begin(), list.end(), idx), list.end());
+    pods[idx].reset();  // the slot is never looked at again: every walk goes through podsByNs / podIndex
+  }
 };
 
 }  // namespace ko

@@ -480,3 +480,86 @@ def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
     assert norm_prefilter(ref.prefilter(probe)) == norm_prefilter(dut.prefilter(probe))
     assert dut.prefilter(probe)["reasons"] == ["throttle[insufficient]=default/t"]
     dut.close()
+
+
+# ---- random EVENT STREAMS: informer events, scheduling cycles and reconciles interleaved at random ---------------------------
+TIMES = ["2026-01-01T00:00:00Z", "2026-01-15T12:00:00Z", "2026-03-01T12:00:00Z", "2025-12-31T23:59:59Z"]
+def run_event_stream(oracle, new_plugin, seed):
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i}" for i in range(4)]
+    for n in nss: both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+    throttles = [rand_throttle(rng, i, nss) for i in range(14)]
+    both(*throttles)
+    pods = [rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(60)]
+    both(*pods)
+    pending = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(40)]
+    reserved = []
+    log = []
+    for step in range(60):
+        op = rng.random()
+        if op < 0.2:
+            now = rng.choice(TIMES); log.append(("reconcile", now))
+            try: ref.reconcile_all(now)
+            except RuntimeError: pass
+            dut.reconcile_all(now)
+        elif op < 0.45:
+            p = rng.choice(pending); log.append(("prefilter", p["metadata"]["name"]))
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert (a["code"], a["reasons"]) == (b["code"], b["reasons"]), (seed, step, log[-5:], a, b)
+            if a["code"] == "Success" and rng.random() < 0.7:
+                assert ref.reserve(p)["code"] == dut.reserve(p)["code"]
+                reserved.append(p)
+        elif op < 0.55 and reserved:
+            p = reserved.pop(rng.randrange(len(reserved))); log.append(("bind-or-unreserve", p["metadata"]["name"]))
+            if rng.random() < 0.6:
+                both(dict(p, spec=dict(p["spec"], nodeName="node-2"), status={"phase": rng.choice(["Running", "Running", "Succeeded"])}))
+            else:
+                ref.unreserve(p); dut.unreserve(p)
+        elif op < 0.7:
+            p = rng.choice(pods); log.append(("relabel", p["metadata"]["name"]))
+            p["metadata"]["labels"] = rand_labels(rng)
+            if rng.random() < 0.3: p["status"] = {"phase": rng.choice(["Running", "Succeeded", "Failed"])}
+            both(p)
+        elif op < 0.8:
+            i = rng.randrange(len(throttles)); log.append(("edit-throttle", i))
+            t = rand_throttle(rng, i, nss)
+            t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
+            if t["kind"] == "Throttle":
+                for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+            throttles[i] = t
+            both(t)
+        elif op < 0.88:
+            n = rng.choice(nss); log.append(("relabel-ns", n))
+            both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+        elif op < 0.94 and len(pods) > 20:
+            p = pods.pop(rng.randrange(len(pods))); log.append(("delete-pod", p["metadata"]["name"]))  # informer Delete event
+            ref.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"]), dut.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"])
+        else:
+            p = rand_pod(rng, rng.choice(nss), f"n{step}", True); pods.append(p); log.append(("new-pod", p["metadata"]["name"]))
+            both(p)
+    for now in (TIMES[1],):
+        try: ref.reconcile_all(now)
+        except RuntimeError: pass
+        dut.reconcile_all(now)
+    for t in throttles:
+        ns = t["metadata"].get("namespace", "")
+        a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+        assert norm_status(a) == norm_status(b), (seed, "status", t["metadata"], a, b)
+        k, nn = t["kind"], ns + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]), (seed, "reserved", nn, a, b)
+    for p in pending:
+        a, b = ref.prefilter(p), dut.prefilter(p)
+        assert (a["code"], a["reasons"]) == (b["code"], b["reasons"]), (seed, "final", a, b)
+    dut.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_event_stream_chaos(oracle, new_plugin, seed):
+    """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve,
+    binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, namespace
+    relabels, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
+    the end must agree.  (tools/chaos_host.py runs more seeds on the CPU double.)"""
+    run_event_stream(oracle, new_plugin, seed)

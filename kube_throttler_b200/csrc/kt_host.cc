@@ -376,6 +376,9 @@ struct ThrottleObj {
   }
 };
 
+// label key of the internal "this namespace exists" marker: not a legal label key, so it cannot collide with a real one
+const char* const kNsExistsKey = "\x01kt/exists";
+
 struct NamespaceObj {
   std::string name;
   std::vector<std::pair<std::string, std::string>> labels;
@@ -595,7 +598,7 @@ struct kth_plugin {
     lim.abi_version = KT_ABI_VERSION;
     lim.n_resources = round_up(std::max<int>(1, (int)cols.size()), {4, 8, 16, 31});
     lim.label_slots = round_up(std::max(1, max_labels), {8, 16, 32});
-    lim.ns_label_slots = round_up(std::max(1, max_ns_labels), {4, 8, 16, 32});
+    lim.ns_label_slots = round_up(std::max(1, max_ns_labels + 1), {4, 8, 16, 32});  // + the internal "exists" label
     const int rc = kt_create(&ctx, device, &lim);
     if (rc != KT_OK) { ctx = nullptr; fail("kt_create failed (" + std::to_string(rc) + "): no usable CUDA device -- there is no CPU path"); }
   }
@@ -690,6 +693,10 @@ struct kth_plugin {
     for (size_t i = 0; i < n; ++i) {
       int s = 0;
       for (auto& kv : namespaces[i].labels) lab[(size_t)(s++) * n + i] = labels.encode(kv.first, kv.second);
+      // A namespace the lister does not hold (never seen, or deleted) is not in the list affectedPods walks
+      // (clusterthrottle_controller.go:227) -- no ClusterThrottle term may match it, not even one whose namespaceSelector is
+      // empty.  Existing namespaces carry one internal label (a key no real label can have) that every term requires.
+      if (namespaces[i].exists) lab[(size_t)(s++) * n + i] = labels.encode(kNsExistsKey, "1");
     }
     check(kt_upload_namespaces(ctx, (int32_t)n, lab.data()), "kt_upload_namespaces");
     namespaces_dirty = false;
@@ -763,7 +770,15 @@ struct kth_plugin {
         term_flags.push_back(term.ns_sel.error.empty() ? 0 : KT_TERM_NS_INVALID);  // Q9: swallowed, the term is false
         push_reqs(term.pod_sel.reqs);
         pod_req_off.push_back((int32_t)req_key.size());
-        ns_reqs_of_term.push_back(o.kind == KT_KIND_CLUSTERTHROTTLE && term.ns_sel.error.empty() ? term.ns_sel.reqs : std::vector<Requirement>{});
+        std::vector<Requirement> nsr;
+        if (o.kind == KT_KIND_CLUSTERTHROTTLE && term.ns_sel.error.empty()) {
+          nsr = term.ns_sel.reqs;
+          Requirement ex;  // the namespace must be one the lister holds (sync_namespaces)
+          ex.key = kNsExistsKey;
+          ex.op = KT_OP_EXISTS;
+          nsr.push_back(std::move(ex));
+        }
+        ns_reqs_of_term.push_back(std::move(nsr));
       }
       term_off[t + 1] = (int32_t)term_flags.size();
     }
@@ -1477,7 +1492,8 @@ struct kth_plugin {
     const std::string nm = v["metadata"]["name"].str();
     const Node& lab = v["metadata"]["labels"];
     // refuse before touching any state: the object is rejected, the plugin stays usable
-    if ((int)lab.obj.size() > KT_MAX_LABEL_SLOTS) fail("namespace " + nm + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS) + " labels");
+    if ((int)lab.obj.size() > KT_MAX_LABEL_SLOTS - 1)  // one slot is the internal "exists" label
+      fail("namespace " + nm + " has more than " + std::to_string(KT_MAX_LABEL_SLOTS - 1) + " labels");
     const int32_t id = ns_id(nm);
     NamespaceObj& n = namespaces[(size_t)id];
     n.exists = true;
@@ -1485,7 +1501,7 @@ struct kth_plugin {
     for (auto& kv : lab.obj) n.labels.emplace_back(kv.first, kv.second->str());
     if ((int)n.labels.size() > max_ns_labels) {
       max_ns_labels = (int)n.labels.size();
-      if (ctx && max_ns_labels > lim.ns_label_slots) drop_engine();
+      if (ctx && max_ns_labels + 1 > lim.ns_label_slots) drop_engine();
     }
     namespaces_dirty = true;
   }
@@ -1561,7 +1577,8 @@ struct kth_plugin {
     if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }  // its series outlive it, as a GaugeVec's do
     o.live = false;
     o.terms.clear();
-    cache[kind].by_thr.erase(nn);
+    // The reservation cache keeps the entry: reserved_resource_amounts.go has no way to drop a throttle, so what was reserved on
+    // this name is still counted if a throttle of the same name comes back (until those pods are observed or deleted).
     thr_index.erase(it);
     throttles_dirty = status_dirty = reserved_dirty = true;
     broken_valid = false;

@@ -61,6 +61,10 @@ def lib():
         L.ko_world_apply.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_world_delete_pod.restype = C.c_char_p
         L.ko_world_delete_pod.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ko_world_delete_namespace.restype = C.c_char_p
+        L.ko_world_delete_namespace.argtypes = [C.c_void_p, C.c_char_p]
+        L.ko_world_delete_throttle.restype = C.c_char_p
+        L.ko_world_delete_throttle.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         L.ko_world_reconcile_all.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_world_get_status.restype = C.c_char_p
         L.ko_world_get_status.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
@@ -117,10 +121,14 @@ class World:
             self._json(lib().ko_world_apply(self._h, json.dumps(m).encode()))
 
     def delete(self, kind, name, namespace=""):
-        """Informer Delete event; only pods are modelled (host.Plugin.delete has the same signature)."""
-        if kind != "Pod":
-            raise NotImplementedError("the oracle models pod deletes only")
-        return self._json(lib().ko_world_delete_pod(self._h, namespace.encode(), name.encode()))
+        """Informer Delete event of a Pod, Throttle or ClusterThrottle (host.Plugin.delete has the same signature)."""
+        if kind == "Pod":
+            return self._json(lib().ko_world_delete_pod(self._h, namespace.encode(), name.encode()))
+        if kind in ("Throttle", "ClusterThrottle"):
+            return self._json(lib().ko_world_delete_throttle(self._h, 0 if kind == "Throttle" else 1, namespace.encode(), name.encode()))
+        if kind == "Namespace":
+            return self._json(lib().ko_world_delete_namespace(self._h, name.encode()))
+        raise NotImplementedError("the oracle does not model deletes of " + kind)
 
     def reconcile_all(self, now="2026-01-01T00:00:00Z"):
         return self._json(lib().ko_world_reconcile_all(self._h, now.encode()))

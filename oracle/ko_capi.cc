@@ -336,6 +336,25 @@ const char* ko_world_delete_pod(void* h, const char* ns, const char* name) {
   }
 }
 
+const char* ko_world_delete_namespace(void* h, const char* name) {
+  try {
+    ((KoWorld*)h)->w.deleteNamespace(name ? name : "");
+    return ret(Value::object());
+  } catch (const std::exception& e) {
+    return ret(err_obj(e.what()));
+  }
+}
+
+// throttle / clusterthrottle informer Delete event (kind 0 = Throttle, 1 = ClusterThrottle)
+const char* ko_world_delete_throttle(void* h, int kind, const char* ns, const char* name) {
+  try {
+    ((KoWorld*)h)->w.deleteThrottle(kind != 0, ns ? ns : "", name ? name : "");
+    return ret(Value::object());
+  } catch (const std::exception& e) {
+    return ret(err_obj(e.what()));
+  }
+}
+
 // apply one manifest (kind: Pod | Namespace | Throttle | ClusterThrottle); upsert by name
 const char* ko_world_apply(void* h, const char* json) {
   try {

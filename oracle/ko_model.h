@@ -873,6 +873,15 @@ struct World {
     nsIndex[n.name] = namespaces.size();
     namespaces.push_back(std::make_unique<Namespace>(std::move(n)));
   }
+  // namespace informer Delete event: no handler is registered (clusterthrottle_controller.go:429); the lister just stops
+  // returning it, so ClusterThrottle checks of pods in it fail with "not found" (:273-276) and its pods leave affectedPods.
+  void deleteNamespace(const std::string& name) {
+    auto it = nsIndex.find(name);
+    if (it == nsIndex.end()) return;
+    namespaces.erase(namespaces.begin() + (std::ptrdiff_t)it->second);
+    nsIndex.clear();
+    for (size_t i = 0; i < namespaces.size(); ++i) nsIndex[namespaces[i]->name] = i;
+  }
   // keepStatus: a manifest without .status is a spec edit -- the status subresource survives it (CRD status subresource)
   void upsertThrottle(Throttle t, bool keepStatus = false) {
     if (t.kind == KindThrottle) {
@@ -1111,6 +1120,26 @@ struct World {
       }
     }
     upsertPod(std::move(p));
+  }
+
+  // ---- throttle informer Delete event (throttle_controller.go:417-424, clusterthrottle_controller.go:447-454): the key is
+  // enqueued, its reconcile finds nothing (:96-101).  The reservation cache is NOT told (reserved_resource_amounts.go has no
+  // way to drop a throttle's entry): whatever was reserved on that name is still there if a throttle of the same name comes back.
+  void deleteThrottle(bool cluster, const std::string& ns, const std::string& name) {
+    if (!cluster) {
+      auto it = thrIndex.find(ns + "/" + name);
+      if (it == thrIndex.end()) return;
+      throttles.erase(throttles.begin() + (std::ptrdiff_t)it->second);
+      thrIndex.clear();
+      thrByNs.clear();
+      for (size_t i = 0; i < throttles.size(); ++i) { thrIndex[throttles[i]->NN()] = i; thrByNs[throttles[i]->ns].push_back(i); }
+    } else {
+      auto it = clthrIndex.find(name);
+      if (it == clthrIndex.end()) return;
+      clusterThrottles.erase(clusterThrottles.begin() + (std::ptrdiff_t)it->second);
+      clthrIndex.clear();
+      for (size_t i = 0; i < clusterThrottles.size(); ++i) clthrIndex[clusterThrottles[i]->name] = i;
+    }
   }
 
   // ---- pod informer Delete event (throttle_controller.go:508-531, clusterthrottle_controller.go:536-559): both controllers

@@ -105,7 +105,7 @@ def test_refused_manifests_leave_no_trace(world):
         world.status("t2", "default")
     with pytest.raises(RuntimeError, match="more than 32 labels"):
         world.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}))
-    with pytest.raises(RuntimeError, match="more than 32 labels"):
+    with pytest.raises(RuntimeError, match="more than 31 labels"):
         world.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
     # a 32nd resource name is refused -- and the 30 names the refused pod had already brought along go with it: afterwards
     # thirty OTHER new names still fit

@@ -351,7 +351,7 @@ def test_objects_beyond_the_limits_are_rejected_not_fatal(new_plugin):
     w.apply(pod("default", "p0", "300m", {"a": "1"}, node="n", phase="Running"))
     with pytest.raises(RuntimeError, match="more than 32 labels"):
         w.apply(pod("default", "fat", "100m", {f"k{i}": "v" for i in range(33)}, node="n", phase="Running"))
-    with pytest.raises(RuntimeError, match="more than 32 labels"):
+    with pytest.raises(RuntimeError, match="more than 31 labels"):
         w.apply(namespace("fat-ns", {f"l{i}": "x" for i in range(33)}))
     with pytest.raises(RuntimeError, match="distinct resource names"):
         w.apply(pod("default", "greedy", "100m", {"a": "1"}, node="n", phase="Running", requests={f"example.com/r{i}": "1" for i in range(40)}))
@@ -496,6 +496,7 @@ def run_event_stream(oracle, new_plugin, seed):
     both(*pods)
     pending = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(40)]
     reserved = []
+    gone = set()  # indices of throttles that are deleted right now (an edit brings them back under the same name)
     log = []
     for step in range(60):
         op = rng.random()
@@ -504,6 +505,23 @@ def run_event_stream(oracle, new_plugin, seed):
             try: ref.reconcile_all(now)
             except RuntimeError: pass
             dut.reconcile_all(now)
+        elif op < 0.23:
+            batch = rng.sample(pending, 6); log.append(("prefilter-batch", [p["metadata"]["name"] for p in batch]))
+            want = [ref.prefilter(p) for p in batch]
+            got = dut.prefilter_batch(batch)  # one device pass for the lot: independent checks against the same snapshot
+            assert [(a["code"], a["reasons"]) for a in want] == [(b["code"], b["reasons"]) for b in got], (seed, step, log[-5:])
+        elif op < 0.27:
+            names = {p["metadata"]["name"] for p in reserved}
+            queue = [p for p in rng.sample(pending, 8) if p["metadata"]["name"] not in names]; log.append(("admit-queue", len(queue)))
+            want = []
+            for p in queue:  # the scheduler's cycle, pod by pod
+                r = ref.prefilter(p)
+                if r["code"] == "Success":
+                    assert ref.reserve(p)["code"] == "Success"
+                want.append((r["code"], r["reasons"]))
+            got = dut.admit_queue(queue)
+            assert [(x["preFilter"]["code"], x["preFilter"]["reasons"]) for x in got["results"]] == want, (seed, step, log[-5:])
+            reserved.extend(p for p, w in zip(queue, want) if w[0] == "Success")
         elif op < 0.45:
             p = rng.choice(pending); log.append(("prefilter", p["metadata"]["name"]))
             a, b = ref.prefilter(p), dut.prefilter(p)
@@ -517,23 +535,46 @@ def run_event_stream(oracle, new_plugin, seed):
                 both(dict(p, spec=dict(p["spec"], nodeName="node-2"), status={"phase": rng.choice(["Running", "Running", "Succeeded"])}))
             else:
                 ref.unreserve(p); dut.unreserve(p)
-        elif op < 0.7:
+        elif op < 0.64:
             p = rng.choice(pods); log.append(("relabel", p["metadata"]["name"]))
             p["metadata"]["labels"] = rand_labels(rng)
             if rng.random() < 0.3: p["status"] = {"phase": rng.choice(["Running", "Succeeded", "Failed"])}
             both(p)
+        elif op < 0.68:
+            i = rng.randrange(len(pods)); log.append(("mutate-pod", pods[i]["metadata"]["name"]))  # anything may change: requests, scheduler, node, phase
+            pods[i] = rand_pod(rng, pods[i]["metadata"]["namespace"], pods[i]["metadata"]["name"], True)
+            both(pods[i])
+        elif op < 0.7 and reserved:
+            p = rng.choice(reserved); log.append(("re-reserve", p["metadata"]["name"]))  # addPod overwrites the amount it kept
+            p["spec"]["containers"][0]["resources"]["requests"]["cpu"] = rng.choice(CPUS)
+            assert ref.reserve(p)["code"] == dut.reserve(p)["code"]
         elif op < 0.8:
             i = rng.randrange(len(throttles)); log.append(("edit-throttle", i))
             t = rand_throttle(rng, i, nss)
             t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
             if t["kind"] == "Throttle":
                 for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+                if t["spec"]["selector"]["selectorTerms"] and rng.random() < 0.15:  # a podSelector that does not convert, at a random position (Q9)
+                    rng.choice(t["spec"]["selector"]["selectorTerms"])["podSelector"] = rng.choice([
+                        {"matchExpressions": [{"key": "team", "operator": "In", "values": []}]},
+                        {"matchExpressions": [{"key": "env", "operator": "Exists", "values": ["a"]}]},
+                        {"matchLabels": {"bad key!": "x"}}])
             throttles[i] = t
+            gone.discard(i)
             both(t)
-        elif op < 0.88:
-            n = rng.choice(nss); log.append(("relabel-ns", n))
+        elif op < 0.86:
+            n = rng.choice(nss); log.append(("relabel-ns", n))  # also what brings a deleted namespace back
             both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
-        elif op < 0.94 and len(pods) > 20:
+        elif op < 0.88:
+            n = rng.choice(nss); log.append(("delete-ns", n))  # the lister stops returning it; its pods and throttles stay
+            ref.delete("Namespace", n), dut.delete("Namespace", n)
+        elif op < 0.91 and len(gone) < 5:
+            i = rng.randrange(len(throttles)); log.append(("delete-throttle", i))  # its reservations stay in the cache (no way to drop them)
+            if i not in gone:
+                gone.add(i)
+                md = throttles[i]["metadata"]
+                ref.delete(throttles[i]["kind"], md["name"], md.get("namespace", "")), dut.delete(throttles[i]["kind"], md["name"], md.get("namespace", ""))
+        elif op < 0.95 and len(pods) > 20:
             p = pods.pop(rng.randrange(len(pods))); log.append(("delete-pod", p["metadata"]["name"]))  # informer Delete event
             ref.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"]), dut.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"])
         else:
@@ -543,10 +584,11 @@ def run_event_stream(oracle, new_plugin, seed):
         try: ref.reconcile_all(now)
         except RuntimeError: pass
         dut.reconcile_all(now)
-    for t in throttles:
+    for i, t in enumerate(throttles):
         ns = t["metadata"].get("namespace", "")
-        a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
-        assert norm_status(a) == norm_status(b), (seed, "status", t["metadata"], a, b)
+        if i not in gone:
+            a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+            assert norm_status(a) == norm_status(b), (seed, "status", t["metadata"], a, b)
         k, nn = t["kind"], ns + "/" + t["metadata"]["name"]
         a, b = ref.reserved(k, nn), dut.reserved(k, nn)
         assert sorted(a["pods"]) == sorted(b["pods"]), (seed, "reserved", nn, a, b)
@@ -556,10 +598,50 @@ def run_event_stream(oracle, new_plugin, seed):
     dut.close()
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 8, 17])  # 8 and 17: a throttle is deleted and comes back while pods are reserved on it
 def test_event_stream_chaos(oracle, new_plugin, seed):
-    """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve,
-    binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, namespace
-    relabels, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
+    """Sixty random steps per seed -- reconciles at different clock times (override windows open and close), PreFilter + Reserve, batched
+    PreFilter and queue admission,
+    binds (some pods finish at once), Unreserve, pod relabels (reservation moves), pod deletes, throttle spec edits, throttle deletes
+    and re-creations, namespace relabels and deletes, new pods -- applied to the oracle and to the plugin alike; every verdict on the way and every status, reservation and verdict at
     the end must agree.  (tools/chaos_host.py runs more seeds on the CPU double.)"""
     run_event_stream(oracle, new_plugin, seed)
+
+
+def test_pods_of_a_namespace_the_lister_does_not_hold(oracle, new_plugin):
+    """ClusterThrottleController.affectedPods walks the namespaces the lister returns (clusterthrottle_controller.go:227): pods of
+    a namespace that was never seen, or was deleted, are not counted by ANY ClusterThrottle -- not even one whose namespaceSelector
+    is empty -- while a namespaced Throttle (which never asks about the namespace) still counts them; PreFilter for such a pod
+    fails in the ClusterThrottle controller with "not found" (:273-276)."""
+    from test_scenarios import pod, throttle
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    everywhere = {"kind": "ClusterThrottle", "metadata": {"name": "everywhere"},
+                  "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 10}},
+                           "selector": {"selectorTerms": [{"namespaceSelector": {}, "podSelector": {"matchLabels": {"a": "1"}}}]}}}
+    notprod = {"kind": "ClusterThrottle", "metadata": {"name": "notprod"},
+               "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 10}},
+                        "selector": {"selectorTerms": [{"namespaceSelector": {"matchExpressions": [{"key": "env", "operator": "NotIn", "values": ["prod"]}]},
+                                                        "podSelector": {}}]}}}
+    both(namespace("seen", {"env": "dev"}), everywhere, notprod, throttle("ghost", "local", {"a": "1"}, pod_cnt=10),
+         pod("seen", "p0", "100m", {"a": "1"}, node="n", phase="Running"), pod("ghost", "p1", "100m", {"a": "1"}, node="n", phase="Running"))
+
+    def settle_and_compare():
+        ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+        for name, ns in (("everywhere", ""), ("notprod", ""), ("local", "ghost")):
+            assert norm_status(ref.status(name, ns)) == norm_status(dut.status(name, ns)), name
+        for p in (pod("seen", "x", "100m", {"a": "1"}), pod("ghost", "y", "100m", {"a": "1"})):
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 1 and dut.status("local", "ghost")["used"]["resourceCounts"]["pod"] == 1
+    assert dut.prefilter(pod("ghost", "y", "100m", {"a": "1"}))["code"] == "Error"
+    both(namespace("ghost", {"env": "dev"}))           # the namespace shows up
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 2 and dut.status("notprod")["used"]["resourceCounts"]["pod"] == 2
+    ref.delete("Namespace", "seen"), dut.delete("Namespace", "seen")   # and another one goes away
+    settle_and_compare()
+    assert dut.status("everywhere")["used"]["resourceCounts"]["pod"] == 1
+    dut.close()

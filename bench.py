@@ -176,6 +176,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def pin_to_gpu_local_cpus(dev_index):
+    """Pinned buffers are placed on the NUMA node of the allocating thread: keep this process on the CPUs that sit next to
+    its GPU (sysfs local_cpulist of the PCI function), as a deployment would.  Best effort; returns what was done."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(dev_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local cpulist)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} GPU-local cpus"
+    except Exception as e:  # noqa: BLE001 -- diagnostics only
+        return f"unchanged ({type(e).__name__})"
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,6 +219,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    host_affinity = pin_to_gpu_local_cpus(local_rank)
     # NCCL prints its version banner on stdout at communicator creation; stdout belongs to the ONE JSON line of rank 0,
     # so file descriptor 1 points at stderr until the communicators exist
     saved_stdout = None
@@ -334,8 +358,35 @@ def main():
     except ValueError:
         pass
     h2d_wide = h2d
-    if compact:
-        h2d = sum(c.nbytes for c in compact)
+    h2d_compact = sum(c.nbytes for c in compact) if compact else None
+    # ... and smaller still when the snapshot uses at most 65535 distinct label pairs (kt_upload_pods_packed: 16-bit pair
+    # indices, presence inside the meta word)
+    packed = None
+    try:
+        try:  # request columns as 1- or 2-byte dictionary codes when every column has at most 65536 distinct values
+            pr, pp_ = abi.packed_pods(r, code_requests=True), abi.packed_pods(p, code_requests=True)
+            packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), None, None, pin(c.meta), pin(c.req_dict), pin(c.req_dict_off),
+                                             pin(c.req_code_bytes), pin(c.req_codes)) for c in (pr, pp_))
+        except ValueError:
+            pr, pp_ = abi.packed_pods(r), abi.packed_pods(p)
+            packed = tuple(abi.PackedPodCols(c.ns_bits, pin(c.pairs), pin(c.labels16), pin(c.req32), pin(c.req_shift), pin(c.meta)) for c in (pr, pp_))
+    except ValueError:
+        pass
+    packed_wc = None
+    if packed:
+        h2d = sum(c.nbytes for c in packed)
+
+        def pin_wc(a):  # write-combined: the CPU only writes these, the device reads them
+            b = kt.Pinned(a.shape, a.dtype, upload_only=True)
+            b.array[...] = a
+            pinned.append(b)
+            return b.array
+
+        packed_wc = tuple(abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), None, None, pin_wc(c.meta), pin_wc(c.req_dict), pin(c.req_dict_off),
+                                            pin(c.req_code_bytes), pin_wc(c.req_codes)) if c.coded else
+                          abi.PackedPodCols(c.ns_bits, pin_wc(c.pairs), pin_wc(c.labels16), pin_wc(c.req32), pin(c.req_shift), pin_wc(c.meta)) for c in packed)
+    elif compact:
+        h2d = h2d_compact
 
     def e2e_step_wide():
         eng.upload_pods(abi.PODS_RUNNING, hr)
@@ -344,13 +395,40 @@ def main():
         eng.get_check(codes_b.array, admit_b.array)
         eng.get_reconcile(out)
 
-    def e2e_step():
-        if not compact:
-            return e2e_step_wide()
+    def e2e_step_compact():
         eng.upload_pods_compact(abi.PODS_RUNNING, compact[0])
         eng.upload_pods_compact(abi.PODS_PENDING, compact[1])
         eng.evaluate(snap.now)
         eng.get_check(codes_b.array, admit_b.array)
+        eng.get_reconcile(out)
+
+    # The check result comes back as admit[p] + the NON-ZERO code words (kt_get_check_sparse): what PreFilter needs of it.
+    # A list that overflows falls back to the dense rows inside the timed step.
+    sparse_cap = 4 * snap.pending.n + 1024
+    ent_b = kt.Pinned((sparse_cap, 3), np.uint32)
+    sparse_counts = []
+
+    def fetch_check():
+        n = eng.get_check_sparse(admit_b.array, ent_b.array)
+        sparse_counts.append(n)
+        if n > sparse_cap:
+            eng.get_check(codes_b.array, None)
+
+    use_wc = [False]
+
+    def e2e_step():
+        if packed:
+            src = packed_wc if use_wc[0] else packed
+            eng.upload_pods_packed(abi.PODS_RUNNING, src[0])
+            eng.upload_pods_packed(abi.PODS_PENDING, src[1])
+        elif compact:
+            eng.upload_pods_compact(abi.PODS_RUNNING, compact[0])
+            eng.upload_pods_compact(abi.PODS_PENDING, compact[1])
+        else:
+            eng.upload_pods(abi.PODS_RUNNING, hr)
+            eng.upload_pods(abi.PODS_PENDING, hp)
+        eng.evaluate(snap.now)
+        fetch_check()
         eng.get_reconcile(out)
 
     # what the host link of this box can do at all (pinned, one 64 MiB copy each way): the floor of any e2e number
@@ -384,8 +462,63 @@ def main():
 
     e2e_wide_value = time_e2e(e2e_step_wide)
     eng.set_async_uploads(True)  # the pinned columns live for the whole run: no need to wait for each copy before queueing the next
+    e2e_compact_value = time_e2e(e2e_step_compact) if compact else None
+    eng.set_sparse_check(sparse_cap)
     e2e_value = time_e2e(e2e_step)
+    e2e_pinned_value, upload_memory = e2e_value, "pinned"
+    if packed_wc:
+        use_wc[0] = True
+        e2e_wc_value = time_e2e(e2e_step)
+        if e2e_wc_value > e2e_value:
+            e2e_value, upload_memory = e2e_wc_value, "pinned write-combined"
+    # Double-buffered steps: a second context (own stream, own snapshot buffers) takes the NEXT step's upload while this
+    # step's pass runs and its results come back -- H2D, the pass and D2H of consecutive steps overlap; every step still
+    # copies its inputs in and its results out.  Single GPU only (a second context would need a second peer window set).
+    e2e_pipelined_value = None
+    if world == 1:
+        try:
+            eng2 = kt.Engine(snap.R, snap.L, snap.LN, device=local_rank)
+            stream2 = torch.cuda.Stream()
+            eng2.set_stream(stream2.cuda_stream)
+            eng2.upload_snapshot(snap)
+            eng2.set_async_uploads(True)
+            eng2.set_sparse_check(sparse_cap)
+            engines = (eng, eng2)
+            src_cols = (packed_wc if use_wc[0] and upload_memory != "pinned" else packed) or compact
+            turn = [0]
+
+            def upload(e):
+                if packed:
+                    e.upload_pods_packed(abi.PODS_RUNNING, src_cols[0])
+                    e.upload_pods_packed(abi.PODS_PENDING, src_cols[1])
+                elif compact:
+                    e.upload_pods_compact(abi.PODS_RUNNING, src_cols[0])
+                    e.upload_pods_compact(abi.PODS_PENDING, src_cols[1])
+                else:
+                    e.upload_pods(abi.PODS_RUNNING, hr)
+                    e.upload_pods(abi.PODS_PENDING, hp)
+
+            def e2e_step_pipelined():
+                cur, nxt = engines[turn[0] & 1], engines[(turn[0] + 1) & 1]
+                upload(nxt)                 # queued on the other context's stream; returns at once
+                cur.evaluate(snap.now)      # the rows this context received one step ago
+                n = cur.get_check_sparse(admit_b.array, ent_b.array)
+                if n > sparse_cap:
+                    cur.get_check(codes_b.array, None)
+                cur.get_reconcile(out)
+                turn[0] += 1
+
+            upload(engines[0])
+            e2e_pipelined_value = time_e2e(e2e_step_pipelined)
+            eng2.sync()
+            eng2.close()
+        except Exception as e:  # noqa: BLE001 -- the serial number stands
+            print(f"pipelined e2e unavailable: {e}", file=sys.stderr)
+    eng.set_sparse_check(0)
     eng.set_async_uploads(False)
+    d2h_dense = d2h
+    n_sparse = max(sparse_counts) if sparse_counts else 0
+    d2h = d2h - codes_b.array.nbytes + (12 * min(n_sparse + n_sparse // 4 + 256, sparse_cap) + 4 if n_sparse <= sparse_cap else 12 * sparse_cap + 4 + codes_b.array.nbytes)  # the fetch asks for the last count + 25 % + 256 entries
     admit_frac = float(admit_b.array.mean())
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded, ~seconds ----------------
@@ -411,8 +544,11 @@ def main():
                        "admit_fraction": admit_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
-                    "path": ("kt_upload_pods_compact x2" if compact else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check + kt_get_reconcile (pinned host buffers)",
+                    "path": ("kt_upload_pods_packed x2" if packed else "kt_upload_pods_compact x2" if compact else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)",
+                    "double_buffered": {"value": e2e_pipelined_value, "note": "two contexts alternate: step k+1's upload overlaps step k's pass and download"},
+                    "sparse_check_entries": n_sparse, "upload_memory": upload_memory, "pinned_upload_value": e2e_pinned_value, "host_affinity": host_affinity,
                     "wide_int64_upload": {"value": e2e_wide_value, "h2d_bytes_per_step": h2d_wide},
+                    "compact_upload_dense_codes": {"value": e2e_compact_value, "h2d_bytes_per_step": h2d_compact, "d2h_bytes_per_step": d2h_dense},
                     "host_link_gbs": link, "link_floor_value": checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world},
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_s_timed_region": t_wall,

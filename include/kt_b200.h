@@ -196,6 +196,10 @@ int kt_enable_trace(kt_ctx* ctx, int on);
 int64_t kt_get_trace(kt_ctx* ctx, uint64_t* rows /*[cap][8]*/, int64_t cap, uint32_t roles[4]);
 /* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost). */
 void* kt_host_alloc(size_t bytes);
+/* The same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only ever WRITES, front to back, and the device
+ * reads (upload columns).  The device's reads need no cache snooping on the host, which some platforms reward with a faster
+ * host-to-device link; CPU reads of such memory are very slow.  Freed with kt_host_free. */
+void* kt_host_alloc_upload(size_t bytes);
 void kt_host_free(void* p);
 
 /* ---- snapshot upload (host -> HBM) --------------------------------------------- */
@@ -218,6 +222,35 @@ int kt_upload_pods(kt_ctx* ctx, int kind, int64_t n,
 int kt_upload_pods_compact(kt_ctx* ctx, int kind, int64_t n, int32_t val_bits, const uint32_t* labels32 /*[L][n]*/,
                            const int32_t* req32 /*[R][n]*/, const int32_t* req_shift /*[R]*/,
                            const uint32_t* present /*[n]*/, const uint32_t* meta /*[n]*/);
+/* The same rows, smaller still (36 bytes per row at L=8, R=4): labels as 16-bit indices into a dictionary of the distinct
+ * (key, value) PAIRS the snapshot uses, presence folded into the meta word.  A packer that interns label pairs (the informer
+ * cache of a real cluster has a few thousand distinct pairs) sends 2 bytes per label slot.
+ *   pairs[n_pairs]   keyId << 32 | valId, n_pairs <= 65535
+ *   labels16[L][n]   index into pairs, 0xFFFF = empty slot
+ *   req32, req_shift as in kt_upload_pods_compact
+ *   meta[n]          ns_id | flags << ns_bits | present << (ns_bits + 3);  ns_bits + 3 + R <= 32, ns_id < 2^ns_bits
+ * Expanded on the device into the int64 columns of kt_upload_pods: HBM layout and results unchanged. */
+typedef struct {
+  int32_t n_pairs;
+  int32_t ns_bits;
+  const int64_t* pairs;      /* [n_pairs] */
+  const uint16_t* labels16;  /* [L][n] */
+  const int32_t* req32;      /* [R][n] */
+  const int32_t* req_shift;  /* [R] */
+  const uint32_t* meta;      /* [n] */
+  /* Optional, instead of req32 / req_shift (both may then be NULL): dictionary-coded request columns.  Pods come from a few
+   * templates, so a column of 10^5 requests holds a few dozen distinct values: 1 byte per value instead of 4.
+   *   req_dict[...]          the distinct values, column after column (exact int64, the engine's own unit)
+   *   req_dict_off[R+1]      column r's values are req_dict[req_dict_off[r] .. req_dict_off[r+1])
+   *   req_code_bytes[R]      1 or 2: width of column r's codes (at most 256 / 65536 distinct values)
+   *   req_codes              the code columns one after another, column r = n little-endian codes of req_code_bytes[r] bytes,
+   *                          each column padded to a multiple of 4 bytes */
+  const int64_t* req_dict;
+  const int32_t* req_dict_off;
+  const uint8_t* req_code_bytes;
+  const uint8_t* req_codes;
+} kt_packed_pods;
+int kt_upload_pods_packed(kt_ctx* ctx, int kind, int64_t n, const kt_packed_pods* rows);
 /* With async uploads on, kt_upload_pods / kt_upload_pods_compact return as soon as the copies are QUEUED: the caller must
  * keep the host buffers alive and unchanged until kt_sync or any kt_get_* has returned.  Saves one stream
  * synchronisation per upload on the latency-sensitive end-to-end path.  Off by default. */
@@ -264,6 +297,16 @@ int kt_get_match_rows(kt_ctx* ctx, int kind, int64_t k, const int64_t* rows, uin
  * admit[p] = 1 iff every affected throttle is KT_CHECK_NOT_THROTTLED (plugin.go:177-180).
  * Either pointer may be NULL. */
 int kt_get_check(kt_ctx* ctx, uint32_t* codes /*[p][2*words_per_row]*/, uint8_t* admit /*[p]*/);
+/* The same result without the zeros.  A PreFilter caller needs the admit bit of every pod and, for the rejected ones, which
+ * throttles said what (plugin.go:182-213): at C2 that is ~10^4 non-zero code words out of 6.4*10^5.
+ * kt_set_sparse_check(cap_entries > 0) makes every later pass ALSO append each non-zero code word to a device list of at most
+ * cap_entries entries (0 switches it off again; the dense rows are always written).  kt_get_check_sparse copies admit[p]
+ * and the entries {pending row, word index j in [0, 2*words_per_row), codes word}: the word is what kt_get_check would have
+ * delivered at codes[row*2*words_per_row + j].  Entries are unordered.  *count is the number of non-zero words of the pass;
+ * when it exceeds cap (or the device capacity) only the first min(cap, cap_entries) were delivered and the caller should
+ * read the dense rows instead. */
+int kt_set_sparse_check(kt_ctx* ctx, int64_t cap_entries);
+int kt_get_check_sparse(kt_ctx* ctx, uint8_t* admit /*[p]*/, uint32_t* entries /*[cap][3]*/, int64_t cap, int64_t* count);
 int kt_get_timing(kt_ctx* ctx, kt_timing* out);
 
 /* ---- host-only introspection (no device needed) -------------------------------- */

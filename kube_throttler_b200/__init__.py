@@ -42,9 +42,9 @@ def build(force: bool = False) -> str:
 
 EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
-    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
+    "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_alloc_upload", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
@@ -71,11 +71,16 @@ def lib():
         L.kt_get_trace.restype = C.c_int64
         L.kt_host_alloc.argtypes = [C.c_size_t]
         L.kt_host_alloc.restype = vp
+        L.kt_host_alloc_upload.argtypes = [C.c_size_t]
+        L.kt_host_alloc_upload.restype = vp
         L.kt_host_free.argtypes = [vp]
         L.kt_host_free.restype = None
         L.kt_upload_pods.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         L.kt_set_async_uploads.argtypes = [vp, C.c_int]
         L.kt_upload_pods_compact.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
+        L.kt_upload_pods_packed.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(abi.PackedPodsStruct)]
+        L.kt_set_sparse_check.argtypes = [vp, C.c_int64]
+        L.kt_get_check_sparse.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.kt_update_pod_rows.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.kt_upload_namespaces.argtypes = [vp, C.c_int32, vp]
         L.kt_upload_throttles.argtypes = [vp, C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable)]
@@ -101,11 +106,11 @@ class Pinned:
     """Pinned (cudaHostAlloc) host buffer exposed as a numpy array: `.array`.  Keep the object alive
     while the array is in use."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, upload_only: bool = False):
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         nbytes = max(count * dtype.itemsize, 1)
-        self._ptr = lib().kt_host_alloc(nbytes)
+        self._ptr = (lib().kt_host_alloc_upload if upload_only else lib().kt_host_alloc)(nbytes)  # upload_only: write-combined
         if not self._ptr:
             raise KtError(abi.ERR_CUDA, "kt_host_alloc failed")
         self._buf = (C.c_char * nbytes).from_address(self._ptr)
@@ -190,6 +195,12 @@ class Engine:
                                                 abi.ptr(cp.present), abi.ptr(cp.meta)))
         self.n[kind] = cp.n
 
+    def upload_pods_packed(self, kind: int, pk: "abi.PackedPodCols"):
+        """kt_upload_pods_packed: 36 bytes per row (L=8, R=4): 16-bit label-pair indices, presence inside the meta word."""
+        st = pk.struct()
+        self._ck(self._L.kt_upload_pods_packed(self._h, kind, pk.n, C.byref(st)))
+        self.n[kind] = pk.n
+
     def update_pod_rows(self, kind: int, rows: np.ndarray, pods: PodCols):
         rows = np.ascontiguousarray(rows, np.int64)
         self._ck(self._L.kt_update_pod_rows(self._h, kind, rows.shape[0], abi.ptr(rows), abi.ptr(pods.labels), abi.ptr(pods.req),
@@ -257,6 +268,17 @@ class Engine:
 
     def get_check(self, codes: Optional[np.ndarray], admit: Optional[np.ndarray]):
         self._ck(self._L.kt_get_check(self._h, abi.ptr(codes), abi.ptr(admit)))
+
+    def set_sparse_check(self, cap_entries: int):
+        """Later passes also append every non-zero code word to a device list (0: off)."""
+        self._ck(self._L.kt_set_sparse_check(self._h, cap_entries))
+
+    def get_check_sparse(self, admit: Optional[np.ndarray], entries: np.ndarray) -> int:
+        """admit[p] and the non-zero code words as rows {pending row, word index, codes}; returns their total number
+        (more than entries.shape[0]: read the dense rows with get_check instead)."""
+        n = C.c_int64(0)
+        self._ck(self._L.kt_get_check_sparse(self._h, abi.ptr(admit), abi.ptr(entries), entries.shape[0], C.byref(n)))
+        return int(n.value)
 
     def get_reconcile(self, out: PassResult):
         rec = out.reconcile_out()

@@ -164,6 +164,127 @@ def compact_pods(pods: PodCols, val_bits: int = 20) -> CompactPodCols:
     return CompactPodCols(val_bits, np.ascontiguousarray(lab32), np.ascontiguousarray(req32), shift, np.ascontiguousarray(pods.present, np.uint32), meta)
 
 
+class PackedPodsStruct(C.Structure):
+    """kt_packed_pods (include/kt_b200.h)"""
+    _fields_ = [("n_pairs", C.c_int32), ("ns_bits", C.c_int32), ("pairs", C.c_void_p), ("labels16", C.c_void_p), ("req32", C.c_void_p),
+                ("req_shift", C.c_void_p), ("meta", C.c_void_p), ("req_dict", C.c_void_p), ("req_dict_off", C.c_void_p),
+                ("req_code_bytes", C.c_void_p), ("req_codes", C.c_void_p)]
+
+
+@dataclass
+class PackedPodCols:
+    """The packed transfer format of kt_upload_pods_packed: 16-bit indices into a dictionary of label pairs, presence in meta."""
+    ns_bits: int
+    pairs: np.ndarray      # [n_pairs] i64
+    labels16: np.ndarray   # [L][n] u16
+    req32: Optional[np.ndarray]      # [R][n] i32            } either these two ...
+    req_shift: Optional[np.ndarray]  # [R] i32               }
+    meta: np.ndarray       # [n] u32 = ns_id | flags << ns_bits | present << (ns_bits + 3)
+    req_dict: Optional[np.ndarray] = None        # i64, the columns' distinct values one after another   } ... or these four
+    req_dict_off: Optional[np.ndarray] = None    # [R+1] i32                                                }
+    req_code_bytes: Optional[np.ndarray] = None  # [R] u8: 1 or 2                                           }
+    req_codes: Optional[np.ndarray] = None       # u8 buffer: the code columns, each padded to 4 bytes      }
+
+    @property
+    def n(self) -> int:
+        return int(self.meta.shape[0])
+
+    @property
+    def coded(self) -> bool:
+        return self.req_codes is not None
+
+    @property
+    def nbytes(self) -> int:
+        cols = (self.pairs, self.labels16, self.meta) + ((self.req_dict, self.req_dict_off, self.req_code_bytes, self.req_codes) if self.coded
+                                                         else (self.req32, self.req_shift))
+        return sum(a.nbytes for a in cols)
+
+    def struct(self) -> PackedPodsStruct:
+        if self.coded:
+            return PackedPodsStruct(int(self.pairs.shape[0]), self.ns_bits, ptr(self.pairs), ptr(self.labels16), None, None, ptr(self.meta),
+                                    ptr(self.req_dict), ptr(self.req_dict_off), ptr(self.req_code_bytes), ptr(self.req_codes))
+        return PackedPodsStruct(int(self.pairs.shape[0]), self.ns_bits, ptr(self.pairs), ptr(self.labels16), ptr(self.req32), ptr(self.req_shift), ptr(self.meta),
+                                None, None, None, None)
+
+    def unpack(self, Lpad: int | None = None) -> "PodCols":
+        """What k_unpack_packed writes into HBM, in numpy (test-side mirror of the device expansion)."""
+        L, n = self.labels16.shape
+        idx = self.labels16.astype(np.int64)
+        lab = np.where(idx == 0xFFFF, LABEL_EMPTY, self.pairs[np.minimum(idx, max(len(self.pairs) - 1, 0))] if len(self.pairs) else LABEL_EMPTY)
+        if self.coded:
+            R = int(self.req_code_bytes.shape[0])
+            req = np.zeros((R, n), np.int64)
+            off = 0
+            for r in range(R):
+                b = int(self.req_code_bytes[r])
+                codes = np.frombuffer(self.req_codes.tobytes()[off:off + n * b], dtype=np.uint8 if b == 1 else "<u2").astype(np.int64)
+                d = self.req_dict[int(self.req_dict_off[r]):int(self.req_dict_off[r + 1])]
+                req[r] = d[codes] if n else 0
+                off += (n * b + 3) // 4 * 4
+        else:
+            R = self.req32.shape[0]
+            req = self.req32.astype(np.int64) << self.req_shift.astype(np.int64)[:, None]
+        m = self.meta.astype(np.uint64)
+        ns = (m & np.uint64((1 << self.ns_bits) - 1)).astype(np.int32)
+        flags = ((m >> np.uint64(self.ns_bits)) & np.uint64(7)).astype(np.uint32)
+        present = ((m >> np.uint64(self.ns_bits + 3)) & np.uint64((1 << R) - 1)).astype(np.uint32)
+        return PodCols(np.ascontiguousarray(lab, np.int64).reshape(L, n), np.ascontiguousarray(req), present, flags, ns)
+
+
+def packed_pods(pods: PodCols, code_requests: bool = False) -> PackedPodCols:
+    """Wide int64 pod columns -> packed transfer columns, exactly (raises ValueError when the snapshot uses more than 65535
+    distinct label pairs, a request column does not fit int32 in any power-of-two unit, or namespace / flags / presence do
+    not fit one meta word).  code_requests: dictionary-code the request columns (1 or 2 bytes per value; ValueError when a column
+    has more than 65536 distinct values).  Pure repacking; nothing is evaluated."""
+    lab = pods.labels
+    empty = lab == LABEL_EMPTY
+    pairs, inv = np.unique(lab[~empty], return_inverse=True)
+    if pairs.shape[0] > 65535:
+        raise ValueError(f"{pairs.shape[0]} distinct label pairs do not fit 16-bit indices")
+    lab16 = np.full(lab.shape, 0xFFFF, np.uint16)
+    lab16[~empty] = inv.astype(np.uint16)
+    R = pods.req.shape[0]
+    shift = np.zeros(R, np.int32)
+    req32 = np.zeros(pods.req.shape, np.int32)
+    coded = None
+    if code_requests:
+        dicts, offs, widths, chunks = [], [0], [], []
+        for r in range(R):
+            vals, inv = np.unique(pods.req[r], return_inverse=True)
+            if vals.shape[0] > 65536:
+                raise ValueError(f"resource column {r} has {vals.shape[0]} distinct values: no 16-bit codes")
+            b = 1 if vals.shape[0] <= 256 else 2
+            raw = inv.astype(np.uint8 if b == 1 else "<u2").tobytes()
+            chunks.append(raw + b"\0" * (-len(raw) % 4))
+            dicts.append(vals.astype(np.int64))
+            offs.append(offs[-1] + vals.shape[0])
+            widths.append(b)
+        coded = (np.ascontiguousarray(np.concatenate(dicts) if dicts else np.zeros(0, np.int64)), np.asarray(offs, np.int32), np.asarray(widths, np.uint8),
+                 np.frombuffer(b"".join(chunks), dtype=np.uint8).copy())
+    else:
+        for r in range(R):
+            col = pods.req[r]
+            nz = col[col != 0]
+            sh = 0
+            if nz.size:
+                low = int(np.bitwise_or.reduce(nz))
+                sh = min((low & -low).bit_length() - 1, 32)
+                if np.abs(nz >> sh).max() >= 2**31:
+                    raise ValueError(f"resource column {r} does not fit int32 even after dropping {sh} common zero bits")
+            shift[r] = sh
+            req32[r] = (col >> sh).astype(np.int32)
+    ns_bits = 32 - 3 - R
+    if ns_bits < 1:
+        raise ValueError(f"R={R}: presence does not fit the meta word")
+    if pods.n and (int(pods.ns_id.max()) >= 1 << ns_bits or int(pods.ns_id.min()) < 0 or int(pods.flags.max()) > 7 or int(pods.present.max()) >> R):
+        raise ValueError("namespace id / flags / presence do not fit the packed meta word")
+    meta = (pods.ns_id.astype(np.uint32) | (pods.flags.astype(np.uint32) << np.uint32(ns_bits)) |
+            (pods.present.astype(np.uint32) << np.uint32(ns_bits + 3))).astype(np.uint32)
+    if coded:
+        return PackedPodCols(ns_bits, np.ascontiguousarray(pairs, np.int64), np.ascontiguousarray(lab16), None, None, meta, *coded)
+    return PackedPodCols(ns_bits, np.ascontiguousarray(pairs, np.int64), np.ascontiguousarray(lab16), np.ascontiguousarray(req32), shift, meta)
+
+
 @dataclass
 class Snapshot:
     """Everything one pass consumes, as the int64/u32 columns of include/kt_b200.h."""

@@ -45,12 +45,17 @@ struct DevBuf {
 struct PodStore {
   int64_t n = 0;
   DevBuf labels, req, present, flags, ns;
+  DevBuf roff;              // [Lpad][n] u32: the labels as row offsets into the current selector tables (k_translate_rows)
+  bool roff_valid = false;  // false after a full upload or a table compile; row deltas translate their own rows
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
+  DevBuf c_pairs;                  // label-pair dictionary of the packed transfer format (kt_upload_pods_packed)
+  DevBuf c_dict;                   // request-value dictionaries of the same format
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
-    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release();
-    c_labels.release(); c_req.release(); c_meta.release();
+    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release();
+    roff_valid = false;
+    c_labels.release(); c_req.release(); c_meta.release(); c_pairs.release(); c_dict.release();
     t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
   }
 };
@@ -146,6 +151,10 @@ struct kt_ctx {
   size_t o_off[8] = {};
   bool async_uploads = false;  // kt_set_async_uploads
   DevBuf d_codes, d_admit;
+  DevBuf d_sparse;              // kt_set_sparse_check: {count u32, pad to 16 B, entries [cap][3] u32}
+  uint32_t sparse_cap = 0;      // 0: off
+  uint32_t sparse_guess = 1024; // entries fetched together with the count (adapts to the last pass)
+  uint32_t* h_sparse_count = nullptr;  // pinned
   bool evaluated = false;
   // multi-GPU
   void* comm = nullptr;
@@ -205,6 +214,7 @@ int recompile_tables(kt_ctx* c) {
   if ((rc = upload_vec(c, c->d_nsw_off, c->ht.nsw_off))) return rc;
   if ((rc = upload_vec(c, c->d_nsw_idx, c->ht.nsw_idx))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors may be rebuilt right after
+  for (auto& s : c->pods) s.roff_valid = false;  // row offsets point into the tables that were just replaced
   return KT_OK;
 }
 
@@ -241,12 +251,32 @@ TableView table_view(const kt_ctx* c) {
 PodView pod_view(const PodStore& s) {
   PodView v;
   v.labels = s.labels.as<int64_t>();
+  v.roff = s.roff.as<uint32_t>();
   v.req = s.req.as<int64_t>();
   v.present = s.present.as<uint32_t>();
   v.flags = s.flags.as<uint32_t>();
   v.ns = s.ns.as<int32_t>();
   v.n = s.n;
   return v;
+}
+
+// Label columns -> row offsets of the current tables, for every row (rows_dev == nullptr) or for k listed rows.
+int translate_rows(kt_ctx* c, PodStore& s, int64_t k, const int64_t* rows_dev) {
+  const int Lpad = (c->lim.label_slots + 7) & ~7;
+  if (k <= 0) return KT_OK;
+  k_translate_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, rows_dev, table_view(c), Lpad, s.n, s.labels.as<int64_t>(), s.roff.as<uint32_t>());
+  KT_CUDA(c, cudaGetLastError());
+  return KT_OK;
+}
+// Before a pass: the store's row offsets must match its labels and the current tables.
+int ensure_roff(kt_ctx* c, PodStore& s) {
+  if (!KT_PRETRANSLATED || s.roff_valid || !c->have_throttles) return KT_OK;
+  const int Lpad = (c->lim.label_slots + 7) & ~7;
+  KT_CUDA(c, s.roff.reserve((size_t)Lpad * s.n * 4 + 16));
+  int rc = translate_rows(c, s, s.n, nullptr);
+  if (rc) return rc;
+  s.roff_valid = true;
+  return KT_OK;
 }
 
 // ---- peer exchange window ------------------------------------------------------------------------------
@@ -371,12 +401,21 @@ cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, 
   return launch(c, k_reconcile<TPC, B, RT, REG>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, S, REG, kTileReconcile), false, pv, tb, L, R, S,
                 c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), c->d_part.as<unsigned long long>());
 }
+SparseOut sparse_view(const kt_ctx* c) {
+  SparseOut sp{nullptr, nullptr, 0};
+  if (c->sparse_cap) {
+    sp.count = c->d_sparse.as<uint32_t>();
+    sp.ent = c->d_sparse.as<uint32_t>() + 4;
+    sp.cap = c->sparse_cap;
+  }
+  return sp;
+}
 template <int TPC, int B, bool REG>
 cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
   return launch(c, k_check<TPC, B, REG>, blocks, kTileCheck, check_smem_bytes(L, R, REG, kTileCheck), pdl, pv, tb, L, R,
                 (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
-                c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>());
+                c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>(), sparse_view(c));
 }
 template <int TPC, int B, int RT, bool REG>
 cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
@@ -467,6 +506,8 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
                    &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_sparse_count) cudaFreeHost(c->h_sparse_count);
+  c->d_sparse.release();
   for (DevBuf* b : all) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -530,6 +571,11 @@ void* kt_host_alloc(size_t bytes) {
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
   return p;
 }
+void* kt_host_alloc_upload(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined) != cudaSuccess) return nullptr;
+  return p;
+}
 void kt_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
@@ -557,6 +603,7 @@ int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const 
   if ((rc = upload(c, s.flags, flags, (size_t)n))) return rc;
   if ((rc = upload(c, s.ns, ns_id, (size_t)n))) return rc;
   s.n = n;
+  s.roff_valid = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -591,6 +638,73 @@ int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, con
     KT_CUDA(c, cudaGetLastError());
   }
   s.n = n;
+  s.roff_valid = false;
+  c->evaluated = false;
+  if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
+  return KT_OK;
+}
+
+int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* pk) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
+  if (n < 0 || !pk || (n > 0 && (!pk->labels16 || !pk->meta))) return fail(c, KT_ERR_INVALID, "null packed pod columns");
+  const bool coded = pk->req_codes != nullptr;
+  if (coded ? (!pk->req_dict_off || !pk->req_code_bytes) : (!pk->req_shift || (n > 0 && !pk->req32)))
+    return fail(c, KT_ERR_INVALID, "packed pod rows need either req32 + req_shift or req_codes + req_dict_off + req_code_bytes");
+  const int L = c->lim.label_slots, R = c->lim.n_resources, Lpad = (L + 7) & ~7;
+  ReqCodes rc{};
+  size_t code_bytes = 0, dict_len = 0;
+  if (coded) {
+    for (int r = 0; r < R; ++r) {
+      const int b = pk->req_code_bytes[r];
+      const int64_t d0 = pk->req_dict_off[r], d1 = pk->req_dict_off[r + 1];
+      if ((b != 1 && b != 2) || d0 < 0 || d1 < d0 || d1 - d0 > (b == 1 ? 256 : 65536)) return fail(c, KT_ERR_INVALID, "request dictionary of column %d is malformed", r);
+      rc.col_off[r] = (uint32_t)code_bytes;
+      rc.dict_off[r] = (uint32_t)d0;
+      rc.dict_len[r] = (uint32_t)(d1 - d0);
+      rc.bytes[r] = (unsigned char)b;
+      code_bytes += ((size_t)n * (size_t)b + 3) & ~(size_t)3;
+      if (code_bytes >= ((size_t)1 << 32)) return fail(c, KT_ERR_LIMIT, "request code columns exceed 4 GiB");
+    }
+    dict_len = (size_t)pk->req_dict_off[R];
+    if (dict_len > 0 && !pk->req_dict) return fail(c, KT_ERR_INVALID, "null request dictionary");
+  }
+  if (pk->n_pairs < 0 || pk->n_pairs > 65535 || (pk->n_pairs > 0 && !pk->pairs)) return fail(c, KT_ERR_INVALID, "n_pairs %d outside 0..65535", pk->n_pairs);
+  if (pk->ns_bits < 1 || pk->ns_bits + 3 + R > 32) return fail(c, KT_ERR_INVALID, "ns_bits %d: ns_bits + 3 + R must fit 32 bits", pk->ns_bits);
+  if (!coded)
+    for (int r = 0; r < R; ++r)
+      if (pk->req_shift[r] < 0 || pk->req_shift[r] > 32) return fail(c, KT_ERR_INVALID, "req_shift[%d] = %d outside 0..32", r, pk->req_shift[r]);
+  int err = set_device(c);
+  if (err) return err;
+  PodStore& s = c->pods[kind];
+  KT_CUDA(c, s.labels.reserve((size_t)Lpad * n * 8 + 16));
+  KT_CUDA(c, s.req.reserve((size_t)R * n * 8 + 16));
+  KT_CUDA(c, s.present.reserve((size_t)n * 4 + 16));
+  KT_CUDA(c, s.flags.reserve((size_t)n * 4 + 16));
+  KT_CUDA(c, s.ns.reserve((size_t)n * 4 + 16));
+  // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
+  KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
+  if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
+  if ((err = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (err = upload(c, s.c_meta, pk->meta, (size_t)n))) return err;
+  if (coded) {
+    if ((err = upload(c, s.c_req, pk->req_codes, code_bytes)) || (err = upload(c, s.c_dict, pk->req_dict, dict_len))) return err;
+    rc.codes = s.c_req.as<unsigned char>();
+    rc.dict = s.c_dict.as<int64_t>();
+  } else if ((err = upload(c, s.c_req, pk->req32, (size_t)R * n))) {
+    return err;
+  }
+  if (n > 0) {
+    ReqShifts sh{};
+    if (!coded)
+      for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)pk->req_shift[r];
+    k_unpack_packed<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, pk->ns_bits, pk->n_pairs, s.c_pairs.as<int64_t>(), s.c_labels.as<uint16_t>(),
+                                                                        s.c_req.as<int32_t>(), sh, rc, s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(),
+                                                                        s.req.as<int64_t>(), s.present.as<uint32_t>(), s.flags.as<uint32_t>(), s.ns.as<int32_t>());
+    KT_CUDA(c, cudaGetLastError());
+  }
+  s.n = n;
+  s.roff_valid = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -618,6 +732,8 @@ int kt_update_pod_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, cons
                                                                      s.labels.as<int64_t>(), s.req.as<int64_t>(), s.present.as<uint32_t>(),
                                                                      s.flags.as<uint32_t>(), s.ns.as<int32_t>());
   KT_CUDA(c, cudaGetLastError());
+  // the delta keeps the store's row offsets current: only the scattered rows are translated again (same stream, after the scatter)
+  if (s.roff_valid && (rc = translate_rows(c, s, k, s.t_rows.as<int64_t>()))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   c->evaluated = false;
   return KT_OK;
@@ -744,6 +860,8 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   KT_CUDA(c, pend.bitmap.reserve((size_t)pend.n * Wp * 4 + 16));
   KT_CUDA(c, c->d_codes.reserve((size_t)pend.n * 2 * Wp * 4 + 16));
   KT_CUDA(c, c->d_admit.reserve((size_t)pend.n + 16));
+  if (do_rec && (rc = ensure_roff(c, run))) return rc;   // no-ops unless rows or tables changed since the last pass
+  if (do_chk && (rc = ensure_roff(c, pend))) return rc;
   const TableView tb = table_view(c);
   int launches = 0;
   const bool tm = c->timing;
@@ -802,6 +920,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     a.run = pod_view(run); a.pend = pod_view(pend); a.tb = tb; a.tv = tv; a.out = ov; a.px = px;
     a.run_bitmap = run.bitmap.as<uint32_t>(); a.pend_bitmap = pend.bitmap.as<uint32_t>(); a.codes = c->d_codes.as<uint32_t>();
     a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = px.sync;
+    a.sparse = sparse_view(c);
     a.now = (long long)now; a.eval_flags = flags; a.L = c->lim.label_slots; a.R = R; a.S = reconcile_slots(c); a.G = G;
     a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
     a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
@@ -850,6 +969,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   if (do_chk && pend.n > 0) {
     const PodView pv = pod_view(pend);
     const unsigned blocks = (unsigned)((pend.n + kTileCheck - 1) / kTileCheck);
+    if (c->sparse_cap) KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 4, c->stream));  // k_check appends; nobody in it can clear first
     KT_CUDA(c, dispatch_check(c, pv, tb, blocks, /*pdl=*/!tm && M > 0));
     ++launches;
   }
@@ -949,6 +1069,52 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   if (codes && P > 0) KT_CUDA(c, cudaMemcpyAsync(codes, c->d_codes.p, (size_t)P * 2 * c->ht.Wp * 4, cudaMemcpyDeviceToHost, c->stream));
   if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_set_sparse_check(kt_ctx* c, int64_t cap_entries) {
+  if (!c || cap_entries < 0 || cap_entries > (int64_t)1 << 28) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = set_device(c);
+  if (rc) return rc;
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->sparse_cap = 0;
+  if (cap_entries == 0) return KT_OK;
+  KT_CUDA(c, c->d_sparse.reserve(16 + (size_t)cap_entries * 12));
+  KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 16, c->stream));
+  if (!c->h_sparse_count) KT_CUDA(c, cudaHostAlloc((void**)&c->h_sparse_count, 16, cudaHostAllocDefault));
+  c->sparse_cap = (uint32_t)cap_entries;
+  c->evaluated = false;  // the list belongs to a pass that ran with it switched on
+  return KT_OK;
+}
+
+int kt_get_check_sparse(kt_ctx* c, uint8_t* admit, uint32_t* entries, int64_t cap, int64_t* count) {
+  if (!c || !count || cap < 0 || (cap > 0 && !entries)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check_sparse before kt_evaluate");
+  if (!c->sparse_cap) return fail(c, KT_ERR_STATE, "kt_get_check_sparse without kt_set_sparse_check");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
+  const int64_t P = c->pods[KT_PODS_PENDING].n;
+  const int64_t room = cap < (int64_t)c->sparse_cap ? cap : (int64_t)c->sparse_cap;
+  // one round trip in the common case: the count and as many entries as the last pass produced (plus slack) together
+  int64_t first = c->sparse_guess < room ? c->sparse_guess : room;
+  if (P == 0) first = 0;
+  if (admit && P > 0) KT_CUDA(c, cudaMemcpyAsync(admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaMemcpyAsync(c->h_sparse_count, c->d_sparse.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (first > 0) KT_CUDA(c, cudaMemcpyAsync(entries, c->d_sparse.as<uint32_t>() + 4, (size_t)first * 12, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int64_t total = P > 0 ? (int64_t)*c->h_sparse_count : 0;
+  *count = total;  // may exceed cap / the device capacity: the caller then reads the dense rows (kt_get_check)
+  const int64_t have = total < room ? total : room;
+  if (have > first) {
+    KT_CUDA(c, cudaMemcpyAsync(entries + 3 * first, c->d_sparse.as<uint32_t>() + 4 + 3 * first, (size_t)(have - first) * 12, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int64_t g = total + total / 4 + 256;
+  if (g > (int64_t)c->sparse_cap) g = c->sparse_cap;
+  c->sparse_guess = (uint32_t)g;
   return KT_OK;
 }
 

@@ -30,18 +30,35 @@ namespace kt {
 #ifndef KT_TILE_RECONCILE
 #define KT_TILE_RECONCILE 128
 #endif
+// ---- experiment switches (tools/sweep_variants.sh builds one library per setting; A/B on the same box) ----
+#ifndef KT_WAIT_MODE       // how a wait acquires: 0 relaxed polls + acquire fence, 1 relaxed polls + one acquire load, 2 acquire polls
+#define KT_WAIT_MODE 1
+#endif
+#ifndef KT_PRETRANSLATED   // 1: the pass reads row offsets translated at upload time (k_translate_rows); 0: it translates labels itself
+#define KT_PRETRANSLATED 1
+#endif
+#ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
+#define KT_PASS_THREADS 896
+#endif
+#ifndef KT_DECIDE_WORDS    // match words per warp whose check constants a decide tile stages at once: its shared memory (10 KB per word at
+#define KT_DECIDE_WORDS 3  // R=4) is what every CTA of the fused pass is launched with, i.e. it bounds the reconcile tiles' residency too
+#endif
+#ifndef KT_SLOT_CAP        // upper bound on the per-CTA accumulator slots (shared memory vs straight-to-HBM atomics)
+#define KT_SLOT_CAP 32
+#endif
 #ifndef KT_HEAVY_PODS
 #define KT_HEAVY_PODS 6
 #endif
 constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one lane per pod)
 constexpr int kTileCheck = 64;       // pending pods per CTA
-constexpr int kMaxSlots = 32;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
+constexpr int kMaxSlots = KT_SLOT_CAP;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kDecidePrefetch = 3;   // match words per warp whose check constants the decide tile stages in one go
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
-  const int64_t* labels;    // [L][n]
+  const int64_t* labels;    // [Lpad][n] keyId<<32 | valId (the snapshot as uploaded; re-translated when the tables change)
+  const uint32_t* roff;     // [Lpad][n] the same labels as row offsets into the CURRENT selector tables (k_translate_rows)
   const int64_t* req;       // [R][n]
   const uint32_t* present;  // [n]
   const uint32_t* flags;    // [n]
@@ -131,9 +148,10 @@ struct PassSync {
   unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
   unsigned error;        // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
 };
-// Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as a
-// fence, when the awaited value has been seen.  An acquire LOAD per poll would invalidate the SM's L1 on every iteration
-// (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it.
+// Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as one
+// acquire load of the same counter after the awaited value has been seen.  An acquire load per poll would invalidate the
+// SM's L1 on every iteration (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it; an
+// acquire FENCE instead of the final load also waits for the thread's own outstanding memory operations.
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -144,8 +162,29 @@ __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// One poll of a counter, and what closes a successful wait, per KT_WAIT_MODE.
+__device__ __forceinline__ unsigned poll_gpu(const unsigned* p) { return KT_WAIT_MODE == 2 ? ld_acquire_gpu(p) : ld_relaxed_gpu(p); }
+__device__ __forceinline__ unsigned poll_sys(const unsigned* p) { return KT_WAIT_MODE == 2 ? ld_acquire_sys(p) : ld_relaxed_sys(p); }
+__device__ __forceinline__ void acquire_gpu(const unsigned* p) {
+  if (KT_WAIT_MODE == 0) fence_acquire_gpu();
+  else if (KT_WAIT_MODE == 1) (void)ld_acquire_gpu(p);
+}
+__device__ __forceinline__ void acquire_sys(const unsigned* p) {
+  if (KT_WAIT_MODE == 0) fence_acquire_sys();
+  else if (KT_WAIT_MODE == 1) (void)ld_acquire_sys(p);
+}
 __device__ __forceinline__ void cta_signal(unsigned* counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -178,8 +217,8 @@ __device__ __forceinline__ void spin_until(Done done, unsigned* error_flag, unsi
 }
 __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsigned target, unsigned* error_flag) {
   if (threadIdx.x == 0) {
-    spin_until([&] { return ld_relaxed_gpu(counter) >= target; }, error_flag, 40);
-    fence_acquire_gpu();
+    spin_until([&] { return poll_gpu(counter) >= target; }, error_flag, 40);
+    acquire_gpu(counter);  // the counter only grows within a pass: an acquire load here reads a value >= target
   }
   __syncthreads();
 }
@@ -212,8 +251,8 @@ struct FlagSync {
   // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
   __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
     if (threadIdx.x == 0) {
-      spin_until([&] { return ld_relaxed_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
-      fence_acquire_gpu();
+      spin_until([&] { return poll_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
+      acquire_gpu(&s->rec_done);
       if (px.npeers > 0) {
         if (first_tile) {
           // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
@@ -221,15 +260,16 @@ struct FlagSync {
           __threadfence_system();
           *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
           // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
-          for (int i = 0; i < px.npeers; ++i)
-            spin_until([&] { return (int)(ld_relaxed_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
-          fence_acquire_sys();
+          for (int i = 0; i < px.npeers; ++i) {
+            spin_until([&] { return (int)(poll_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
+            acquire_sys(&px.peer_sync[i]->epoch);  // epochs only grow
+          }
           // ... and tell the other finalize tiles of this rank
           __threadfence();
           *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
         } else {
-          spin_until([&] { return (int)(ld_relaxed_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
-          fence_acquire_gpu();
+          spin_until([&] { return (int)(poll_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
+          acquire_gpu(&px.sync->peers_epoch);
         }
       }
     }
@@ -348,6 +388,28 @@ __device__ __forceinline__ void stage_rows(const TableView& tb, const int64_t* _
       translate8(tb, labels + (int64_t)i0 * n + p, n, o);
 #pragma unroll
       for (int k = 0; k < 8; ++k) rows.col[(i0 + k) * rows.stride] = o[k];  // the column has Lpad entries
+    }
+  }
+}
+
+// The pass does not translate: label -> row offset is done once per (pod row, table version) by k_translate_rows, at
+// upload / update / table-compile time, and the pass reads the [Lpad][n] u32 offsets (half the bytes of the label column and
+// no dependent dictionary hops on the tile's critical path).
+template <bool REG>
+__device__ __forceinline__ void load_rows(const uint32_t* __restrict__ roff, int64_t n, int64_t p, int L, PodRows<REG>& rows) {
+  const uint32_t* rp = roff + p;
+  if constexpr (REG) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      rows.off[k] = __ldg(rp);
+      rp += n;
+    }
+  } else {
+    const int Lpad = (L + 7) & ~7;
+#pragma unroll 4
+    for (int i = 0; i < Lpad; ++i) {
+      rows.col[i * rows.stride] = __ldg(rp);
+      rp += n;
     }
   }
 }
@@ -473,16 +535,19 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
-  // ---- all of the pod row's loads are issued before anything waits on them; the two dependent chains that follow
-  // (labels -> key directory -> value rows, namespace -> word-list offsets -> word indices) are interleaved hop by hop
-  // so that their L2 latencies overlap instead of adding up ----
+  // ---- all of the pod row's loads are issued before anything waits on them; the one dependent chain that follows
+  // (namespace -> word-list offsets -> word indices) runs under their latency ----
   const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
   const int ns = __ldg(&pods.ns[pc]);
   const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
+#if KT_PRETRANSLATED
+  load_rows<REG>(pods.roff, pods.n, pc, L, rows);
+#else
   int64_t lab[8];
   if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+#endif
   long long rq[RT > 0 ? RT : 1];
   if constexpr (RT > 0) {
     const int64_t* rp = pods.req + pc;
@@ -507,12 +572,16 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
   int j = 0, hi = 0;
   if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }  // hop 1 of the word list
+#if !KT_PRETRANSLATED
   uint4 ke[8];
   if constexpr (REG) translate8_keys(tb, lab, ke);                                // hop 1 of the labels
+#endif
   int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;                          // hop 2 of the word list
   int nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;                  // (the word after it is fetched one step ahead)
+#if !KT_PRETRANSLATED
   if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);                      // hop 2 of the labels
   else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+#endif
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
 #pragma unroll
@@ -870,12 +939,30 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 __host__ __device__ inline int decide_stage_words(int R, int tile) {
   const size_t per_word = (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);
   int ks = (int)((40u << 10) / per_word);
-  return ks < 1 ? 1 : (ks > 3 ? 3 : ks);
+  return ks < 1 ? 1 : (ks > KT_DECIDE_WORDS ? KT_DECIDE_WORDS : ks);
 }
 __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
   const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                                                        // check_match_tile
   const size_t decide = (size_t)R * tile * 8 + (size_t)decide_stage_words(R, tile) * (tile / 32) * 32 * (16 + 16 * (size_t)R);  // check_decide_tile
   return match > decide ? match : decide;
+}
+
+// Optional sparse copy of the check result (kt_set_sparse_check): every NON-ZERO 32-bit code word is also appended to a list
+// as {pending row, word index within the row's 2*Wp code words, the 16 codes}.  At C2 that is ~10k entries (116 KB) where the
+// dense code rows are 2.56 MB, which is what a host that only needs the reasons of the rejected pods wants to download.
+// count keeps counting beyond cap (the host then falls back to the dense rows); entries are unordered.
+struct SparseOut {
+  uint32_t* count;  // nullptr: off
+  uint32_t* ent;    // [cap][3]
+  uint32_t cap;
+};
+__device__ __forceinline__ void sparse_append(const SparseOut& sp, uint32_t row, uint32_t widx, uint32_t word) {
+  const uint32_t i = atomicAdd(sp.count, 1u);
+  if (i < sp.cap) {
+    sp.ent[3 * (size_t)i] = row;
+    sp.ent[3 * (size_t)i + 1] = widx;
+    sp.ent[3 * (size_t)i + 2] = word;
+  }
 }
 
 // Phase 1 of the pending check, no dependency on the running pods: selector match of TILE pending pods ->
@@ -894,8 +981,12 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
+#if KT_PRETRANSLATED
+  load_rows<REG>(pods.roff, pods.n, pc, L, rows);
+#else
   int64_t lab[8];
   if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
+#endif
   {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
@@ -904,14 +995,17 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
     for (int i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
-  // the two dependent chains (labels -> key directory -> value rows, namespace -> offsets -> word indices) hop by hop
   int lo = 0, hi = 0;
   if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
+#if !KT_PRETRANSLATED
   uint4 ke[8];
   if constexpr (REG) translate8_keys(tb, lab, ke);
+#endif
   int wcur = lo < hi ? __ldg(&tb.nsw_idx[lo]) : 0;
+#if !KT_PRETRANSLATED
   if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);
   else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
+#endif
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
 #pragma unroll 1
   for (int j = lo; j < hi; ++j) {
@@ -929,7 +1023,8 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 template <int TILE, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ check,
                                                   const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync) {
+                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
+                                                  const SparseOut sp = SparseOut{nullptr, nullptr, 0}) {
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
   unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][KS][32][rec]
@@ -1024,6 +1119,10 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     }
     if (c0) codes[p * 2 * Wp + 2 * w] = c0;
     if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+    if (sp.count) {
+      if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
+      if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
+    }
   };
   auto stage = [&](uint32_t any, int w, unsigned char* recs) {  // lane = throttle
     if ((any >> lane) & 1) {
@@ -1064,11 +1163,11 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
 template <int TPC, int B, bool REG>
 __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
                                                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
-                                                      unsigned char* __restrict__ admit) {
+                                                      unsigned char* __restrict__ admit, SparseOut sparse /* count zeroed by the host before the launch */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
   __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
-  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{});
+  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1089,6 +1188,7 @@ struct PassArgs {
   uint32_t* codes;
   unsigned char* admit;
   unsigned char* check;
+  SparseOut sparse;
   PassSync* sync;
   long long now;
   uint32_t eval_flags;
@@ -1103,7 +1203,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
   unsigned long long t_start = 0;
@@ -1115,6 +1215,8 @@ __global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(c
   unsigned tile = s_ticket;
   const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
   if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+    // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
+    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
   } else if ((tile -= a.n_chk) < a.n_rec) {
@@ -1124,7 +1226,7 @@ __global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(c
   } else if ((tile -= a.n_rec) < a.n_fin) {
     finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -1146,6 +1248,49 @@ __global__ void __launch_bounds__(kTileReconcile, 896 / kTileReconcile) k_pass(c
   }
 }
 
+struct ReqShifts { unsigned char s[32]; };  // per-column left shift of the 32-bit transfer requests (by value, in the launch arguments)
+
+// dictionary-coded request columns of the packed transfer format (by value in the launch arguments; codes == nullptr: not used)
+struct ReqCodes {
+  const unsigned char* codes;   // the code columns, one after another
+  const int64_t* dict;          // the value dictionaries, one after another
+  uint32_t col_off[32];         // byte offset of column r inside codes (multiples of 4)
+  uint32_t dict_off[32];        // first dictionary entry of column r
+  uint32_t dict_len[32];
+  unsigned char bytes[32];      // 1 or 2
+};
+
+// Packed transfer rows (kt_upload_pods_packed: 16-bit label-pair indices, presence inside the meta word) -> the int64 HBM
+// columns.  One lane per pod row, coalesced; the pair dictionary (a few KB) stays in L1.
+__global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpad, int R, int ns_bits, int n_pairs, const int64_t* __restrict__ pairs,
+                                                       const uint16_t* __restrict__ labels16, const int32_t* __restrict__ req32, const ReqShifts req_shift,
+                                                       const ReqCodes rc, const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
+                                                       uint32_t* __restrict__ present, uint32_t* __restrict__ flags, int32_t* __restrict__ ns) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int s = 0; s < Lpad; ++s) {
+    int64_t lab = KT_LABEL_EMPTY;
+    if (s < L) {
+      const uint32_t c = __ldg(&labels16[(int64_t)s * n + p]);
+      if (c != 0xffffu && (int)c < n_pairs) lab = __ldg(&pairs[c]);
+    }
+    labels[(int64_t)s * n + p] = lab;
+  }
+  if (rc.codes) {
+    for (int r = 0; r < R; ++r) {
+      const unsigned char* col = rc.codes + rc.col_off[r];
+      const uint32_t code = rc.bytes[r] == 1 ? (uint32_t)__ldg(&col[p]) : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(col) + p);
+      req[(int64_t)r * n + p] = code < rc.dict_len[r] ? __ldg(&rc.dict[rc.dict_off[r] + code]) : 0;
+    }
+  } else {
+    for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
+  }
+  const uint32_t m = __ldg(&meta[p]);
+  ns[p] = (int32_t)(m & ((1u << ns_bits) - 1u));
+  flags[p] = (m >> ns_bits) & 7u;
+  present[p] = (m >> (ns_bits + 3)) & (R >= 32 ? 0xffffffffu : ((1u << R) - 1u));
+}
+
 // Row-level delta: scatter k packed rows into the resident columns (pod informer Add/Update/Delete).
 __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* __restrict__ rows, int L, int R, int64_t n,
                                                       const int64_t* __restrict__ labels, const int64_t* __restrict__ req,
@@ -1163,9 +1308,26 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* 
   d_ns[row] = ns[i];
 }
 
+// Label columns -> row offsets into the CURRENT selector tables: every row (rows == nullptr, k == n) after an upload or a
+// table compile, or the k listed rows after a row delta.  One lane per pod row, coalesced column accesses; the two
+// dictionary hops per label that used to sit on every pass's critical path are paid here, once per change.
+__global__ void __launch_bounds__(256) k_translate_rows(int64_t k, const int64_t* __restrict__ rows, const TableView tb, int Lpad, int64_t n,
+                                                        const int64_t* __restrict__ labels, uint32_t* __restrict__ roff) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const int64_t p = rows ? rows[i] : i;
+  if (p < 0 || p >= n) return;
+#pragma unroll 1
+  for (int i0 = 0; i0 < Lpad; i0 += 8) {
+    uint32_t o[8];
+    translate8(tb, labels + (int64_t)i0 * n + p, n, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) roff[(int64_t)(i0 + j) * n + p] = o[j];
+  }
+}
+
 // Compact transfer rows -> the int64 HBM columns (kt_upload_pods_compact).  One lane per pod row; every column access is
 // coalesced.  Lpad - L padding label rows are filled with KT_LABEL_EMPTY here as well.
-struct ReqShifts { unsigned char s[32]; };
 __global__ void __launch_bounds__(256) k_unpack_rows(int64_t n, int L, int Lpad, int R, int val_bits, const uint32_t* __restrict__ labels32,
                                                      const int32_t* __restrict__ req32, const ReqShifts req_shift,
                                                      const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,

@@ -62,6 +62,7 @@ def test_c1_example(kt, oracle):
     dict(config="C2", m=40, n=70, p=33, R=1),                             # ragged: partial tiles, partial last word
     dict(config="C3", m=200, n=5000, p=700, L=12),                        # L > 8: label rows staged in shared memory
     dict(config="C2", m=200, n=5000, p=700, L=12, q_max=6),               # terms with > 3 required keys: 6-bit counters
+    dict(config="C3", m=120, n=2000, p=300, R=31, L=16),                  # the limits: every resource bit in use, two label chunks
     dict(config="C3", m=64, n=3000, p=400, L=3, R=2),                     # fewer label slots than a chunk
 ])
 def test_scaled_configs(kt, oracle, kw):
@@ -229,3 +230,59 @@ def test_no_gpu_error_contract(kt):
         eng.evaluate(0)
     assert e.value.code == abi.ERR_STATE
     eng.close()
+
+
+def test_packed_upload_equals_wide_upload(kt, oracle):
+    """kt_upload_pods_packed (16-bit label-pair indices, presence in the meta word) expands to exactly the int64 columns
+    kt_upload_pods would have copied: same bits out."""
+    for kw in (dict(config="C3", m=300, n=6000, p=800), dict(config="C2", m=200, n=5000, p=700, L=12), dict(config="C2", m=40, n=70, p=33, R=1, L=3),
+               dict(config="C4", m=500, n=3000, p=400)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        want = None
+        for coded in (False, True):  # int32 request columns, then dictionary-coded ones
+            for kind, pods in ((abi.PODS_RUNNING, snap.running), (abi.PODS_PENDING, snap.pending)):
+                pk = abi.packed_pods(pods, code_requests=coded)
+                assert pk.nbytes < 0.65 * sum(a.nbytes for a in (pods.labels, pods.req, pods.present, pods.flags, pods.ns_id))
+                eng.upload_pods_packed(kind, pk)
+            eng.evaluate(snap.now)
+            got = eng.download()
+            want = want or oracle.columnar_evaluate(snap, words_per_row=got.words_per_row)
+            assert_same(snap, got, want)
+        eng.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_sparse_check_equals_nonzero_words_of_the_dense_rows(kt, oracle, fused):
+    """kt_get_check_sparse: exactly the non-zero code words of kt_get_check, each once, plus the same admit bits; a list
+    that is too small reports the true count so that the caller can fall back to the dense rows."""
+    for kw in (dict(config="C2", m=300, n=8000, p=1500), dict(config="C3", m=200, n=3000, p=700), dict(config="C2", m=40, n=70, p=33, R=1, L=3)):
+        kw = dict(kw)
+        snap = synth.generate(kw.pop("config"), **kw)
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        eng.set_sparse_check(4 * snap.pending.n + 64)
+        if not fused:
+            eng.enable_timing(True)  # per-kernel events: the three chained kernels instead of the one fused launch
+        for _ in range(2):  # twice: the counter is cleared by the pass itself
+            eng.evaluate(snap.now)
+            got = eng.download()
+            Wp = got.words_per_row
+            ent = np.zeros((4 * snap.pending.n + 64, 3), np.uint32)
+            admit = np.zeros(snap.pending.n, np.uint8)
+            cnt = eng.get_check_sparse(admit, ent)
+            dense = got.codes.reshape(snap.pending.n, 2 * Wp)
+            rows, widx = np.nonzero(dense)
+            assert cnt == rows.shape[0]
+            want = sorted(zip(rows.tolist(), widx.tolist(), dense[rows, widx].tolist()))
+            assert sorted(map(tuple, ent[:cnt].tolist())) == want
+            assert np.array_equal(admit, got.admit)
+        small = np.zeros((max(cnt // 2, 1), 3), np.uint32)
+        assert eng.get_check_sparse(None, small) == cnt  # truncated: the count still says how many there are
+        eng.set_sparse_check(0)
+        eng.evaluate(snap.now)
+        with pytest.raises(Exception):
+            eng.get_check_sparse(None, small)
+        eng.close()

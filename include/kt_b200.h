@@ -78,6 +78,11 @@ typedef enum kt_pod_kind {
 /* term flags */
 #define KT_TERM_NS_INVALID 1u /* namespaceSelector conversion error => term is false (Q9,
                                  clusterthrottle_selector.go:63-77) */
+#define KT_TERM_POD_INVALID 2u /* podSelector conversion error: the term matches no pod, and for the pods that
+                                  reach it (Throttle: its namespace; ClusterThrottle: the namespaces its
+                                  namespaceSelector matches) no later term is looked at either -- MatchesToPod
+                                  returned the error (throttle_selector.go:30-42, clusterthrottle_selector.go:45-87);
+                                  the host turns "reached it" into framework.Error (plugin.go:154-156) */
 
 /* override flags */
 #define KT_OVR_PARSE_ERROR 1u /* begin/end failed time.Parse: entry skipped (throttle_types.go:80-84) */

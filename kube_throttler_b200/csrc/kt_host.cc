@@ -399,6 +399,13 @@ struct ReservationCache {
     if (it == by_thr.end()) return false;
     return it->second.erase(pod_nn) != 0;
   }
+  // the pod leaves EVERY throttle's reservation: what the event handlers fall back on when the pass that would have named the
+  // pod's affected throttles cannot run (a superset of them; a pod is only ever reserved on throttles it matched)
+  bool remove_everywhere(const std::string& pod_nn) {
+    bool any = false;
+    for (auto& kv : by_thr) any = (kv.second.erase(pod_nn) != 0) || any;
+    return any;
+  }
 };
 
 struct ResourceColumn {
@@ -451,6 +458,8 @@ struct kth_plugin {
   bool broken_valid = false;
 
   ReservationCache cache[2];  // one per controller (controller.go:34-50)
+  bool apply_committed = false;  // kth_apply: the object was stored; whatever fails afterwards must not roll its resource names back
+  std::string apply_warning;     // kth_apply: a committed object whose follow-up pass failed
   int max_labels = 0, max_ns_labels = 0;
 
   // ---- resource columns / scales ----------------------------------------------------------------
@@ -766,9 +775,11 @@ struct kth_plugin {
       }
       ovr_off[t + 1] = (int32_t)ovr_begin.size();
       for (auto& term : o.terms) {
-        if (!term.pod_sel.error.empty()) break;  // the reference returns this error before looking at later terms
-        term_flags.push_back(term.ns_sel.error.empty() ? 0 : KT_TERM_NS_INVALID);  // Q9: swallowed, the term is false
-        push_reqs(term.pod_sel.reqs);
+        // a podSelector that does not convert: the term matches nobody and shadows the LATER terms for exactly the pods that
+        // reach it (KT_TERM_POD_INVALID; the table compiler scopes that by namespace / namespaceSelector)
+        term_flags.push_back((term.ns_sel.error.empty() ? 0 : KT_TERM_NS_INVALID) |  // Q9: swallowed, the term is false
+                             (term.pod_sel.error.empty() ? 0 : KT_TERM_POD_INVALID));
+        push_reqs(term.pod_sel.reqs);  // (none when the selector is broken)
         pod_req_off.push_back((int32_t)req_key.size());
         std::vector<Requirement> nsr;
         if (o.kind == KT_KIND_CLUSTERTHROTTLE && term.ns_sel.error.empty()) {
@@ -1108,12 +1119,21 @@ struct kth_plugin {
     for (size_t t = 0; t < m; ++t) {
       const ThrottleObj& o = throttles[t];
       if (!o.live || o.throttler_name != name || o.selector_error().empty()) continue;
-      selector_fails[t] = 1;
-      if (o.kind != KT_KIND_THROTTLE) continue;
+      // the counted pods a broken term is in the way of: the Throttle's namespace, or -- per term -- the namespaces a
+      // ClusterThrottle term's namespaceSelector matches (clusterthrottle_controller.go:224-270 walks exactly those pods)
       std::vector<int64_t> ns_rows;
-      for (auto& p : pods)
-        if (p.live && p.ns == o.ns && should_count_in(p)) ns_rows.push_back(p.row);
-      selector_fails[t] = 0;
+      std::map<std::string, bool> ns_reaches;
+      for (auto& p : pods) {
+        if (!p.live || !should_count_in(p)) continue;
+        if (o.kind == KT_KIND_THROTTLE) {
+          if (p.ns != o.ns) continue;
+        } else {
+          auto f = ns_reaches.find(p.ns);
+          if (f == ns_reaches.end()) f = ns_reaches.emplace(p.ns, !reachable_selector_error(o, p.ns).empty()).first;
+          if (!f->second) continue;
+        }
+        ns_rows.push_back(p.row);
+      }
       if (ns_rows.empty()) continue;  // nobody to ask the selector about: no error
       std::vector<uint32_t> w((size_t)ns_rows.size() * (size_t)Wp);
       check(kt_get_match_rows(ctx, KT_PODS_RUNNING, (int64_t)ns_rows.size(), ns_rows.data(), w.data()), "kt_get_match_rows");
@@ -1249,11 +1269,49 @@ struct kth_plugin {
     for (size_t t : broken) {
       const ThrottleObj& o = throttles[t];
       if (!o.live || o.kind != kind || o.throttler_name != name) continue;
-      const std::string e = o.selector_error();
-      if (e.empty()) continue;
       if (kind == KT_KIND_THROTTLE && o.ns != pod.ns) continue;
+      const std::string e = reachable_selector_error(o, pod.ns);
+      if (e.empty()) continue;  // no broken term is in this pod's way (ClusterThrottle terms carry their own namespace scope)
       if ((r.bitmap[i * (size_t)r.Wp + (t >> 5)] >> (t & 31)) & 1) continue;  // an earlier, valid term already matched
       return e;
+    }
+    return "";
+  }
+  // labels.Selector.Matches on a namespace's labels (the compiled namespaceSelector of a ClusterThrottle term).  Namespaces, not
+  // pods: the same evaluation the table compiler does for the device's per-namespace masks (kt_tables.cc ns_term_matches).
+  static bool ns_selector_matches(const CompiledSelector& sel, const NamespaceObj& ns) {
+    for (auto& rq : sel.reqs) {
+      const std::string* val = nullptr;
+      for (auto& kv : ns.labels)
+        if (kv.first == rq.key) { val = &kv.second; break; }
+      const bool in_set = val && std::find(rq.values.begin(), rq.values.end(), *val) != rq.values.end();
+      bool ok = false;
+      switch (rq.op) {
+        case KT_OP_IN: ok = val && in_set; break;
+        case KT_OP_NOTIN: ok = !val || !in_set; break;
+        case KT_OP_EXISTS: ok = val != nullptr; break;
+        default: ok = val == nullptr; break;  // DoesNotExist
+      }
+      if (!ok) return false;
+    }
+    return true;
+  }
+  // The podSelector conversion error a pod of namespace `ns` runs into when MatchesToPod walks o's terms in order, "" if it
+  // reaches none: every broken term of a Throttle is in the way of its namespace's pods (throttle_selector.go:30-42); a
+  // ClusterThrottle term checks its namespaceSelector FIRST and is skipped where that does not match -- or does not convert,
+  // Q9 -- (clusterthrottle_selector.go:71-87).  Whether a valid term BEFORE it already matched the pod is the device's bit.
+  std::string reachable_selector_error(const ThrottleObj& o, const std::string& ns) const {
+    const NamespaceObj* nso = nullptr;
+    if (o.kind == KT_KIND_CLUSTERTHROTTLE) {
+      const int id = ns_dict.find(ns);
+      if (id < 0 || !namespaces[(size_t)id].exists) return "";
+      nso = &namespaces[(size_t)id];
+    }
+    for (auto& t : o.terms) {
+      if (t.pod_sel.error.empty()) continue;
+      if (o.kind == KT_KIND_THROTTLE) return t.pod_sel.error;
+      if (!t.ns_sel.error.empty()) continue;
+      if (ns_selector_matches(t.ns_sel, *nso)) return t.pod_sel.error;
     }
     return "";
   }
@@ -1455,7 +1513,18 @@ struct kth_plugin {
     const bool relevant = should_count_in(old) || should_count_in(cur);
     if (relevant && !throttles.empty() && old.labels != cur.labels) {
       const PodObj now = cur;  // check_pending may re-create the engine; keep value copies
-      PendingResult r = check_pending({old, now}, 0);
+      // From here on the update IS committed (pods[row] holds the new object, resource names it brought stay interned): the
+      // reference's UpdateFunc cannot refuse an event either -- when it fails to work out the throttles it logs and returns
+      // (utilruntime.HandleError, throttle_controller.go:470-483).  A pass that throws (refused snapshot, engine error) is
+      // reported as a warning of a SUCCESSFUL apply, and nothing is rolled back.
+      apply_committed = true;
+      PendingResult r;
+      try {
+        r = check_pending({old, now}, 0);
+      } catch (const std::exception& e) {
+        apply_warning = std::string("pod updated; reservation move skipped: ") + e.what();
+        return;
+      }
       for (int kind = 0; kind < 2; ++kind) {
         if (!controller_error(old, r, 0, kind).empty() || !controller_error(now, r, 1, kind).empty()) continue;  // HandleError + return
         const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
@@ -1480,7 +1549,16 @@ struct kth_plugin {
     dirty_rows.insert(row);
     // DeleteFunc (:509-515): a scheduled pod that disappears is un-reserved from its affected throttles
     if (should_count_in(old) && !old.node_name.empty() && !throttles.empty()) {
-      PendingResult r = check_pending({old}, 0);
+      PendingResult r;
+      try {
+        r = check_pending({old}, 0);
+      } catch (...) {
+        // the pod is gone whatever happens to the pass: its reservations must not outlive it (reconcile only un-reserves pods
+        // that are still in the index) -- without the device's answer it leaves every throttle's reservation, a superset
+        for (int kind = 0; kind < 2; ++kind)
+          if (cache[kind].remove_everywhere(old.nn())) reserved_dirty = true;
+        throw;
+      }
       for (int kind = 0; kind < 2; ++kind) {
         if (!controller_error(old, r, 0, kind).empty()) continue;
         for (int t : affected(r, 0, kind))
@@ -1818,6 +1896,8 @@ const char* kth_apply(kth_plugin* p, const char* manifest_json) {
     ktjson::NodePtr v = ktjson::parse(manifest_json);
     const std::string kind = (*v)["kind"].str();
     const size_t n_cols = p->cols.size();
+    p->apply_committed = false;
+    p->apply_warning.clear();
     try {
       if (kind == "Pod") p->apply_pod(*v);
       else if (kind == "Namespace") p->apply_namespace(*v);
@@ -1825,8 +1905,13 @@ const char* kth_apply(kth_plugin* p, const char* manifest_json) {
       else if (kind == "ClusterThrottle") p->apply_throttle(*v, KT_KIND_CLUSTERTHROTTLE);
       else fail("unsupported kind: " + kind);
     } catch (...) {
-      p->rollback_columns(n_cols);  // the refused object's resource names go with it
+      if (!p->apply_committed) p->rollback_columns(n_cols);  // the refused object's resource names go with it
       throw;
+    }
+    if (!p->apply_warning.empty()) {
+      Writer w;
+      w.begin_obj().key("ok").raw("true").key("warning").str(p->apply_warning).end_obj();
+      return w.out;
     }
     return "{\"ok\":true}";
   });

@@ -200,19 +200,39 @@ std::string compile_tables(const kt_limits& lim, const SelectorSpec& s, int32_t 
     if (s.kind[t] == KT_KIND_THROTTLE && s.ns_id[t] >= 0) NS = std::max(NS, s.ns_id[t] + 1);
   h.NS = NS;
   h.nsmask.assign((size_t)NS * h.W * TPp, 0);
+  // A term whose podSelector does not convert (KT_TERM_POD_INVALID) matches nobody, and MatchesToPod returns its error before it
+  // looks at any LATER term -- but only for pods that get as far as that term: every pod of the namespace for a Throttle
+  // (throttle_selector.go:30-42), the pods of the namespaces its namespaceSelector matches for a ClusterThrottle
+  // (clusterthrottle_selector.go:45-56,71-87).  So the later terms are switched off exactly there: a pod's bit is then
+  // "some valid term BEFORE the error matched", which is what the host needs to tell a match from the error.
+  std::vector<uint8_t> blocked;
   for (int32_t t = 0; t < M; ++t) {
     bool live = (s.flags[t] & KT_THR_RESPONSIBLE) && !(s.flags[t] & KT_THR_SELECTOR_ERROR);
     if (!live) continue;
     const int32_t w = t >> 5;
     const uint32_t bit = 1u << (t & 31);
+    bool any_blocked = false;
     for (int32_t term = s.term_off[t], sidx = 0; term < s.term_off[t + 1]; ++term, ++sidx) {
+      if (s.term_flags[term] & KT_TERM_POD_INVALID) {
+        if (!any_blocked) blocked.assign((size_t)NS, 0);
+        any_blocked = true;
+        if (s.kind[t] == KT_KIND_THROTTLE) {
+          const int32_t ns = s.ns_id[t];
+          if (ns >= 0 && ns < NS) blocked[(size_t)ns] = 1;
+        } else {
+          for (int32_t ns = 0; ns < n_ns; ++ns)
+            if (ns_term_matches(s, term, ns_labels, n_ns, ns, lim.ns_label_slots)) blocked[(size_t)ns] = 1;
+        }
+        continue;
+      }
       if (unsat[(size_t)t * TP + sidx]) continue;
       if (s.kind[t] == KT_KIND_THROTTLE) {
         int32_t ns = s.ns_id[t];
-        if (ns >= 0 && ns < NS) h.nsmask[((size_t)ns * h.W + w) * TPp + sidx] |= bit;
+        if (ns >= 0 && ns < NS && !(any_blocked && blocked[(size_t)ns])) h.nsmask[((size_t)ns * h.W + w) * TPp + sidx] |= bit;
       } else {
         for (int32_t ns = 0; ns < n_ns; ++ns)
-          if (ns_term_matches(s, term, ns_labels, n_ns, ns, lim.ns_label_slots)) h.nsmask[((size_t)ns * h.W + w) * TPp + sidx] |= bit;
+          if (!(any_blocked && blocked[(size_t)ns]) && ns_term_matches(s, term, ns_labels, n_ns, ns, lim.ns_label_slots))
+            h.nsmask[((size_t)ns * h.W + w) * TPp + sidx] |= bit;
       }
     }
   }

@@ -76,8 +76,10 @@ class Plugin:
 
     # informer events
     def apply(self, *manifests):
+        out = None
         for m in manifests:
-            _result(self._L.kth_apply(self._h, json.dumps(m).encode()))
+            out = _result(self._L.kth_apply(self._h, json.dumps(m).encode()))
+        return out  # {"ok": true} -- plus "warning" when a stored pod update could not move its reservations
 
     def delete(self, kind, name, namespace=""):
         _result(self._L.kth_delete(self._h, kind.encode(), namespace.encode(), name.encode()))

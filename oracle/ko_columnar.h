@@ -106,6 +106,9 @@ inline bool throttle_matches(const ColumnarInput& in, int32_t t, const PodCols& 
   }
   for (int32_t term = in.sel.term_off[t]; term < in.sel.term_off[t + 1]; ++term) {
     if (in.thr.kind[t] == KT_KIND_CLUSTERTHROTTLE && !term_ns_match(in, term, ns)) continue;
+    // podSelector conversion error: MatchesToPod returns (false, err) here and never looks at the later terms
+    // (throttle_selector.go:30-42, clusterthrottle_selector.go:45-56); the error itself is the host's business
+    if (in.sel.term_flags[term] & KT_TERM_POD_INVALID) return false;
     if (term_pod_match(in.sel, term, pods, p, in.lim.label_slots)) return true;
   }
   return false;

@@ -139,6 +139,22 @@ def test_c2_full_size(kt, oracle):
     np.testing.assert_array_equal(got.used_cnt[live], cnt[live])
 
 
+@pytest.mark.parametrize("config,kw", [
+    ("C2", dict(sort_by_namespace=False)),   # arrival-order rows: the multi-word / direct-RED path at full size
+    ("C3", dict()),                          # 600 Throttles + 400 ClusterThrottles with namespace selectors, R=8
+    ("C3", dict(sort_by_namespace=False)),
+    ("C4", dict()),                          # 5k throttles, temporaryThresholdOverrides active on 20 %
+    ("C5", dict()),                          # 10k x 1M x 100k on ONE GPU (1.9 GB); the columnar oracle needs ~1 min
+])
+def test_baseline_configs_full_size(kt, oracle, config, kw):
+    """Every BASELINE.json config at its FULL size on one device, every output bit against the columnar oracle
+    (C1 and sorted C2 are test_c1_example / test_c2_full_size)."""
+    snap = synth.generate(config, **kw)
+    got, want = run_both(kt, oracle, snap)
+    assert_same(snap, got, want)
+    assert got.pend_bitmap.any() and got.run_bitmap.any()
+
+
 def test_repeat_pass_is_idempotent(kt):
     """The partial-sum buffer is consumed and re-zeroed by every pass: two passes give identical results."""
     snap = synth.generate("C2", m=200, n=5000, p=500)

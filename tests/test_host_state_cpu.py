@@ -190,3 +190,45 @@ def test_status_manifest_is_what_update_status_would_send(host_on_oracle):
     m = json.loads(w.status_manifest("u", "default"))
     assert m["used"] == {"resourceCounts": {"pod": 20}, "resourceRequests": {"cpu": "1"}} and m["calculatedThreshold"]["calculatedAt"] == "2019-02-01T00:00:00Z"
     w.close()
+
+
+def test_pod_update_is_committed_even_when_its_follow_up_pass_is_refused(host_on_oracle):
+    """An informer update cannot be refused half-way: the pod is stored BEFORE the pass that moves its reservations, so when that
+    pass throws (here: the snapshot's memory column can overflow) the apply succeeds with a warning and the resource names the
+    new object brought stay interned -- rolling them back would leave the stored pod pointing at column ids that a later
+    resource name re-uses (`foo` aliased to `bar`)."""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="1"))
+    w.apply(pod("default", "p0", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))
+    w.apply(pod("default", "p1", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))
+    out = w.apply(pod("default", "p1", "100m", {"a": "2"}, node="n", phase="Running", requests={"memory": "2Ei", "example.com/foo": "1"}))
+    assert out["ok"] is True and "can overflow int64" in out["warning"]
+    w.delete("Pod", "p0", "default")  # the snapshot is provable again
+    bar = throttle("default", "tbar", {"a": "2"}, cpu="1")
+    bar["spec"]["threshold"]["resourceRequests"] = {"example.com/bar": "5"}
+    w.apply(bar)
+    assert w.reconcile_all("2026-01-01T00:00:00Z")["reconciled"] == 2
+    used = w.status("tbar", "default")["used"]
+    assert used["resourceCounts"]["pod"] == 1
+    assert used["resourceRequests"]["example.com/foo"] == "1" and "example.com/bar" not in used["resourceRequests"]
+    w.close()
+
+
+def test_deleted_pod_never_keeps_a_reservation(host_on_oracle):
+    """DeleteFunc un-reserves the pod from its affected throttles (throttle_controller.go:509-515).  When the pass that would name
+    them cannot run, the pod still must not stay in the reservation cache (reconcile only un-reserves pods it can still see)."""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"), throttle("default", "t", {"a": "1"}, cpu="10"))
+    w.reconcile_all("2026-01-01T00:00:00Z")
+    q0 = pod("default", "q0", "1", {"a": "1"})
+    assert w.prefilter(q0)["code"] == "Success" and w.reserve(q0)["code"] == "Success"
+    w.apply(dict(q0, spec=dict(q0["spec"], nodeName="n")))  # scheduled, not yet observed by a reconcile: still reserved
+    assert "default/q0" in w.reserved("Throttle", "default/t")["pods"]
+    w.apply(pod("default", "p0", "100m", {"b": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}),
+            pod("default", "p1", "100m", {"b": "1"}, node="n", phase="Running", requests={"memory": "2Ei"}))
+    with pytest.raises(RuntimeError, match="can overflow int64"):
+        w.delete("Pod", "q0", "default")
+    w.delete("Pod", "p1", "default")
+    assert "default/q0" not in w.reserved("Throttle", "default/t")["pods"]
+    assert w.prefilter(pod("default", "q1", "9500m", {"a": "1"}))["code"] == "Success"  # nothing reserved any more
+    w.close()

@@ -449,6 +449,62 @@ def test_selector_error_behind_a_valid_term(oracle, new_plugin):
     dut.close()
 
 
+def test_clusterthrottle_selector_error_is_scoped_by_its_namespace_selector(oracle, new_plugin):
+    """ClusterThrottleSelectorTerm.MatchesToPod checks the term's namespaceSelector FIRST (clusterthrottle_selector.go:71-87): a
+    podSelector that does not convert only hurts pods of the namespaces that term selects, and only those that no EARLIER valid term
+    took; pods elsewhere go on to the LATER terms.  One malformed ClusterThrottle scoped to one namespace must not fail PreFilter
+    cluster-wide, and it is still reconciled as long as no counted pod runs into the broken term."""
+    from test_scenarios import pod
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    bad = {"matchExpressions": [{"key": "a", "operator": "Exists", "values": ["x"]}]}
+    everywhere = {}
+    only_x = {"matchLabels": {"team": "x"}}
+    mixed = {"kind": "ClusterThrottle", "metadata": {"name": "mixed"},
+             "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 3}, "resourceRequests": {"cpu": "2"}},
+                      "selector": {"selectorTerms": [{"namespaceSelector": everywhere, "podSelector": {"matchLabels": {"a": "1"}}},
+                                                     {"namespaceSelector": only_x, "podSelector": bad},
+                                                     {"namespaceSelector": everywhere, "podSelector": {"matchLabels": {"b": "1"}}}]}}}
+    both(namespace("nx", {"team": "x"}), namespace("ny", {"team": "y"}), mixed)
+
+    def reconcile_both():
+        try:
+            ref.reconcile_all(NOW)
+            ok = True
+        except RuntimeError:
+            ok = False
+        dut.reconcile_all(NOW)
+        assert norm_status(ref.status("mixed")) == norm_status(dut.status("mixed"))
+        return ok
+
+    def same_verdicts():
+        out = []
+        for p in (pod("nx", "x", "100m", {"a": "1"}), pod("nx", "y", "100m", {"b": "1"}), pod("nx", "z", "100m", {}),
+                  pod("ny", "x", "100m", {"a": "1"}), pod("ny", "y", "100m", {"b": "1"}), pod("ny", "z", "100m", {})):
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert (a["code"], a["reasons"]) == (b["code"], b["reasons"]), (p["metadata"], a, b)
+            out.append(b["code"])
+        return out
+
+    assert reconcile_both()
+    # nx: the valid first term saves a=1, everything else runs into the broken term; ny never sees it
+    assert same_verdicts() == ["Success", "Error", "Error", "Success", "Success", "Success"]
+    both(pod("nx", "p0", "300m", {"a": "1"}, node="n", phase="Running"), pod("ny", "p1", "300m", {"b": "1"}, node="n", phase="Running"),
+         pod("ny", "p2", "300m", {"c": "1"}, node="n", phase="Running"))
+    assert reconcile_both()  # nobody in nx reaches the broken term; ny's b=1 pod is counted through the term BEHIND it
+    assert dut.status("mixed")["used"]["resourceCounts"]["pod"] == 2
+    both(pod("nx", "p3", "300m", {"b": "1"}, node="n", phase="Running"))  # in nx, not taken by the first term: the broken one is next
+    assert not reconcile_both()
+    assert dut.status("mixed")["used"]["resourceCounts"]["pod"] == 2  # untouched
+    same_verdicts()
+    both(pod("nx", "p3", "300m", {"a": "1", "b": "1"}, node="n", phase="Running"))  # relabelled: the first term takes it
+    assert reconcile_both()
+    assert dut.status("mixed")["used"]["resourceCounts"]["pod"] == 3 and dut.status("mixed")["throttled"]["resourceCounts"]["pod"] is True
+    same_verdicts()
+    dut.close()
+
+
 def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
     """Q8: `terminatedPods = append(nonterminatedPods, pod)` (throttle_controller.go:241) leaves only the LAST finished match in
     the Throttle controller's list, so a reconcile un-reserves the running pods it observes and one finished pod; the other

@@ -134,14 +134,16 @@ struct kt_ctx {
   bool have_reserved = false;
   DevBuf d_reserved, d_reserved_present, d_reserved_cnt;
   // pass state / outputs
-  DevBuf d_part;   // [2R+1][M] u64, zero outside of kt_evaluate
+  DevBuf d_part;   // 2 x [2R+1][M] u64 by pass parity: a reconciling pass adds into one half and leaves the other zeroed for its successor
+  size_t part_stride = 0;  // bytes between the two halves
+  unsigned part_parity = 0;  // half that holds the sums of the last reconcile
   DevBuf d_sync;   // PassSync counters of the fused pass (zero between launches)
   DevBuf d_trace;  // optional per-CTA trace rows of the fused pass
   bool trace = false;
   uint32_t trace_roles[4] = {0, 0, 0, 0};
   PassSync* last_sync = nullptr;  // counters of the last fused pass: its error flag is checked when results are fetched
   bool fused = true;  // one-launch pass (k_pass) when the whole pass is asked for; three PDL-chained kernels otherwise
-  DevBuf d_check;  // [M][16+16R]
+  DevBuf d_pre;    // [M] pre-records, finalize tiles -> decide tiles (kt_kernels.cuh pre_record_bytes)
   // per-throttle outputs of the reconcile half: ONE device block (and one pinned host mirror) so that kt_get_reconcile
   // is a single D2H copy; o_off[i] = byte offset of {used, used_cnt, calc_thr, calc_cnt, used_present, throttled,
   // calc_present, override_active}
@@ -159,14 +161,16 @@ struct kt_ctx {
   // multi-GPU
   void* comm = nullptr;
   int nranks = 1, rank = 0;
-  // peer exchange window: [PassSync | partial sums, even passes | partial sums, odd passes], mapped by every rank.
-  // The fused pass does the all-reduce itself: finalize tiles pull the peers' partial sums over NVLink.
+  // peer exchange window: [PassSync | this rank's sums, even / odd passes | all ranks' totals, even / odd passes], mapped by
+  // every rank.  The fused pass does the all-reduce itself: finalize tiles ADD this rank's sums into every rank's totals
+  // over NVLink and raise a per-rank flag (kt_kernels.cuh PartExchange).
   void* win = nullptr;
   size_t win_part_bytes = 0;  // bytes of ONE partial-sum buffer in the current window
   void* peer_win[8] = {};     // peer_win[r] for r != rank (IPC-opened or raw)
   bool peer_ipc[8] = {};
   bool p2p_failed = false;    // no peer access between the GPUs: stay on the NCCL path
   unsigned epoch = 0;         // passes exchanged through the window so far
+  bool win_stale = false;     // the throttle set changed: the window's buffers are laid out for another M -> rebuilt (collectively) before the next pass
 };
 
 namespace {
@@ -225,7 +229,7 @@ int check_pass_error(kt_ctx* c) {
   KT_CUDA(c, cudaMemcpyAsync(&err, &c->last_sync->error, sizeof err, cudaMemcpyDeviceToHost, c->stream));
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
   if (!err) return KT_OK;
-  KT_CUDA(c, cudaMemsetAsync(c->last_sync, 0, sizeof(PassSync) - 3 * sizeof(unsigned), c->stream));  // re-arm the counters, keep the epochs
+  KT_CUDA(c, cudaMemsetAsync(c->last_sync, 0, kPassSyncRearm * sizeof(unsigned), c->stream));  // re-arm the counters, keep the ranks' flags
   KT_CUDA(c, cudaMemsetAsync(&c->last_sync->error, 0, sizeof(unsigned), c->stream));
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
   c->evaluated = false;
@@ -295,16 +299,17 @@ void release_window(kt_ctx* c) {
 // (re)allocate this rank's window, exchange the IPC handles with one ncclAllGather, map the peers' windows.
 // Returns KT_OK with c->p2p_failed set when the GPUs cannot reach each other (the caller then uses NCCL).
 int ensure_window(kt_ctx* c, size_t part_bytes) {
-  if (c->p2p_failed || (c->win && c->win_part_bytes >= part_bytes)) return KT_OK;
+  if (c->p2p_failed || (c->win && !c->win_stale && c->win_part_bytes >= part_bytes)) return KT_OK;
+  c->win_stale = false;
   if (!g_nccl.AllGather || c->nranks > 8) { c->p2p_failed = true; return KT_OK; }
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
   release_window(c);
-  const size_t want = part_bytes + part_bytes / 4 + 4096;
+  const size_t want = (part_bytes + part_bytes / 4 + 4096 + 255) & ~(size_t)255;
   PeerInfo mine{};
   mine.pid = (long long)getpid();
   mine.device = c->device;
   void* w = nullptr;
-  if (cudaMalloc(&w, kWinHeader + 2 * want) == cudaSuccess && cudaMemset(w, 0, kWinHeader + 2 * want) == cudaSuccess &&
+  if (cudaMalloc(&w, kWinHeader + 4 * want) == cudaSuccess && cudaMemset(w, 0, kWinHeader + 4 * want) == cudaSuccess &&
       cudaIpcGetMemHandle(&mine.handle, w) == cudaSuccess) {
     mine.ok = 1;
     mine.ptr = (unsigned long long)w;
@@ -396,10 +401,10 @@ int reconcile_slots(const kt_ctx* c) {
   return s;
 }
 template <int TPC, int B, int RT, bool REG>
-cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+cudaError_t launch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned long long* part, unsigned blocks) {
   const int L = c->lim.label_slots, R = c->lim.n_resources, S = reconcile_slots(c);
   return launch(c, k_reconcile<TPC, B, RT, REG>, blocks, kTileReconcile, reconcile_smem_bytes(L, R, S, REG, kTileReconcile), false, pv, tb, L, R, S,
-                c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), c->d_part.as<unsigned long long>());
+                c->pods[KT_PODS_RUNNING].bitmap.as<uint32_t>(), part);
 }
 SparseOut sparse_view(const kt_ctx* c) {
   SparseOut sp{nullptr, nullptr, 0};
@@ -411,10 +416,10 @@ SparseOut sparse_view(const kt_ctx* c) {
   return sp;
 }
 template <int TPC, int B, bool REG>
-cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
+cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, const PartExchange& px, unsigned blocks, bool pdl) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
   return launch(c, k_check<TPC, B, REG>, blocks, kTileCheck, check_smem_bytes(L, R, REG, kTileCheck), pdl, pv, tb, L, R,
-                (const unsigned char*)c->d_check.as<unsigned char>(), c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
+                (const unsigned char*)c->d_pre.as<unsigned char>(), px, c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
                 c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>(), sparse_view(c));
 }
 template <int TPC, int B, int RT, bool REG>
@@ -438,26 +443,26 @@ cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
   if (b2) return launch_pass<2, 2, 0, false>(c, a);
   return launch_pass<2, 6, 0, false>(c, a);
 }
-cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks) {
+cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned long long* part, unsigned blocks) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
   const int R = c->lim.n_resources;
   const bool fast = c->lim.label_slots <= 8 && b2 && R <= 8;
   if (fast) {
-    if (t1) return R <= 4 ? launch_reconcile<1, 2, 4, true>(c, pv, tb, blocks) : launch_reconcile<1, 2, 8, true>(c, pv, tb, blocks);
-    return R <= 4 ? launch_reconcile<2, 2, 4, true>(c, pv, tb, blocks) : launch_reconcile<2, 2, 8, true>(c, pv, tb, blocks);
+    if (t1) return R <= 4 ? launch_reconcile<1, 2, 4, true>(c, pv, tb, part, blocks) : launch_reconcile<1, 2, 8, true>(c, pv, tb, part, blocks);
+    return R <= 4 ? launch_reconcile<2, 2, 4, true>(c, pv, tb, part, blocks) : launch_reconcile<2, 2, 8, true>(c, pv, tb, part, blocks);
   }
-  if (t1 && b2) return launch_reconcile<1, 2, 0, false>(c, pv, tb, blocks);
-  if (t1) return launch_reconcile<1, 6, 0, false>(c, pv, tb, blocks);
-  if (b2) return launch_reconcile<2, 2, 0, false>(c, pv, tb, blocks);
-  return launch_reconcile<2, 6, 0, false>(c, pv, tb, blocks);
+  if (t1 && b2) return launch_reconcile<1, 2, 0, false>(c, pv, tb, part, blocks);
+  if (t1) return launch_reconcile<1, 6, 0, false>(c, pv, tb, part, blocks);
+  if (b2) return launch_reconcile<2, 2, 0, false>(c, pv, tb, part, blocks);
+  return launch_reconcile<2, 6, 0, false>(c, pv, tb, part, blocks);
 }
-cudaError_t dispatch_check(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned blocks, bool pdl) {
+cudaError_t dispatch_check(kt_ctx* c, const PodView& pv, const TableView& tb, const PartExchange& px, unsigned blocks, bool pdl) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
-  if (c->lim.label_slots <= 8 && b2) return t1 ? launch_check<1, 2, true>(c, pv, tb, blocks, pdl) : launch_check<2, 2, true>(c, pv, tb, blocks, pdl);
-  if (t1 && b2) return launch_check<1, 2, false>(c, pv, tb, blocks, pdl);
-  if (t1) return launch_check<1, 6, false>(c, pv, tb, blocks, pdl);
-  if (b2) return launch_check<2, 2, false>(c, pv, tb, blocks, pdl);
-  return launch_check<2, 6, false>(c, pv, tb, blocks, pdl);
+  if (c->lim.label_slots <= 8 && b2) return t1 ? launch_check<1, 2, true>(c, pv, tb, px, blocks, pdl) : launch_check<2, 2, true>(c, pv, tb, px, blocks, pdl);
+  if (t1 && b2) return launch_check<1, 2, false>(c, pv, tb, px, blocks, pdl);
+  if (t1) return launch_check<1, 6, false>(c, pv, tb, px, blocks, pdl);
+  if (b2) return launch_check<2, 2, false>(c, pv, tb, px, blocks, pdl);
+  return launch_check<2, 6, false>(c, pv, tb, px, blocks, pdl);
 }
 
 }  // namespace
@@ -504,7 +509,7 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
-                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_check, &c->d_out, &c->d_codes, &c->d_admit};
+                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_sparse_count) cudaFreeHost(c->h_sparse_count);
   c->d_sparse.release();
@@ -778,9 +783,12 @@ int kt_upload_throttles(kt_ctx* c, int32_t m, const kt_throttle_cols* cols, cons
     return rc;
   // per-throttle pass state
   const size_t part_bytes = (size_t)(2 * R + 1) * m * sizeof(unsigned long long);
-  KT_CUDA(c, c->d_part.reserve(part_bytes + 16));
+  c->part_stride = (part_bytes + 255) & ~(size_t)255;
+  KT_CUDA(c, c->d_part.reserve(2 * c->part_stride + 16));
   KT_CUDA(c, cudaMemsetAsync(c->d_part.p, 0, c->d_part.cap, c->stream));
-  KT_CUDA(c, c->d_check.reserve((size_t)m * (16 + 16 * R) + 16));
+  c->part_parity = 0;
+  c->win_stale = c->win != nullptr;  // laid out for the previous M
+  KT_CUDA(c, c->d_pre.reserve((size_t)m * pre_record_bytes(R) + 16));
   {
     const size_t sizes[8] = {(size_t)R * m * 8, (size_t)m * 8, (size_t)R * m * 8, (size_t)m * 8, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m};
     size_t at = 0;
@@ -888,29 +896,37 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
                          reinterpret_cast<int64_t*>(ob + c->o_off[3]), reinterpret_cast<uint8_t*>(ob + c->o_off[7])};
   int G = 1;
   while (G < R + 1) G <<= 1;  // finalize lanes per throttle: resources + the pod count, padded to a power of two
+  // partial sums: a reconciling pass takes the half its predecessor left zeroed and zeroes the other one for its successor
+  if (do_rec) c->part_parity ^= 1u;
   PartExchange px{};
-  px.mine = px.zero = c->d_part.as<unsigned long long>();
+  px.mine = px.total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)c->part_parity * c->part_stride);
+  px.zero_mine = px.zero_total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
   px.sync = c->d_sync.as<PassSync>();
+  px.rank = c->rank;
 
   // ---- the whole pass in one launch (k_pass), both halves asked for.  With several ranks the all-reduce happens
-  // inside it: finalize tiles pull the peers' partial sums over NVLink from the exchange windows. ----
+  // inside it: finalize tiles add this rank's partial sums into every rank's totals over NVLink (exchange windows). ----
   const bool multi = c->comm && c->nranks > 1;
   const bool whole = c->fused && !tm && do_rec && do_chk && M > 0 && run.n > 0 && pend.n > 0;
   if (whole && multi) {
     if ((rc = ensure_window(c, (size_t)(2 * R + 1) * M * 8))) return rc;
     if (!c->p2p_failed) {
-      unsigned char* base = reinterpret_cast<unsigned char*>(c->win);
       const unsigned epoch = ++c->epoch;
+      const size_t mine_off = kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes, zmine_off = kWinHeader + (size_t)((epoch + 1) & 1) * c->win_part_bytes;
+      const size_t total_off = mine_off + 2 * c->win_part_bytes, ztotal_off = zmine_off + 2 * c->win_part_bytes;
+      unsigned char* base = reinterpret_cast<unsigned char*>(c->win);
       px.sync = reinterpret_cast<PassSync*>(base);
-      px.mine = reinterpret_cast<unsigned long long*>(base + kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes);
-      px.zero = reinterpret_cast<unsigned long long*>(base + kWinHeader + (size_t)((epoch + 1) & 1) * c->win_part_bytes);
+      px.mine = reinterpret_cast<unsigned long long*>(base + mine_off);
+      px.total = reinterpret_cast<unsigned long long*>(base + total_off);
+      px.zero_mine = reinterpret_cast<unsigned long long*>(base + zmine_off);
+      px.zero_total = reinterpret_cast<unsigned long long*>(base + ztotal_off);
       px.epoch = epoch;
       px.npeers = 0;
       for (int r = 0; r < c->nranks; ++r) {
         if (r == c->rank) continue;
-        const unsigned char* pb = reinterpret_cast<const unsigned char*>(c->peer_win[r]);
-        px.peer[px.npeers] = reinterpret_cast<const unsigned long long*>(pb + kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes);
-        px.peer_sync[px.npeers] = reinterpret_cast<const PassSync*>(pb);
+        unsigned char* pb = reinterpret_cast<unsigned char*>(c->peer_win[r]);
+        px.peer_total[px.npeers] = reinterpret_cast<unsigned long long*>(pb + total_off);
+        px.peer_sync[px.npeers] = reinterpret_cast<PassSync*>(pb);
         ++px.npeers;
       }
     }
@@ -919,7 +935,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     PassArgs a{};
     a.run = pod_view(run); a.pend = pod_view(pend); a.tb = tb; a.tv = tv; a.out = ov; a.px = px;
     a.run_bitmap = run.bitmap.as<uint32_t>(); a.pend_bitmap = pend.bitmap.as<uint32_t>(); a.codes = c->d_codes.as<uint32_t>();
-    a.admit = c->d_admit.as<unsigned char>(); a.check = c->d_check.as<unsigned char>(); a.sync = px.sync;
+    a.admit = c->d_admit.as<unsigned char>(); a.pre = c->d_pre.as<unsigned char>(); a.sync = px.sync;
     a.sparse = sparse_view(c);
     a.now = (long long)now; a.eval_flags = flags; a.L = c->lim.label_slots; a.R = R; a.S = reconcile_slots(c); a.G = G;
     a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
@@ -941,20 +957,24 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   }
 
   // ---- separate kernels, PDL-chained: partial passes (SKIP_*), per-kernel timing, NCCL all-reduce in between ----
-  px = PartExchange{};
-  px.mine = px.zero = c->d_part.as<unsigned long long>();
-  px.sync = c->d_sync.as<PassSync>();
+  if (px.npeers > 0) {  // the window was set up but the one-launch pass is not taken after all: this rank's own buffers
+    px = PartExchange{};
+    px.mine = px.total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)c->part_parity * c->part_stride);
+    px.zero_mine = px.zero_total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
+    px.sync = c->d_sync.as<PassSync>();
+    px.rank = c->rank;
+  }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   if (do_rec && run.n > 0 && M > 0) {
     const PodView pv = pod_view(run);
     const unsigned blocks = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
-    KT_CUDA(c, dispatch_reconcile(c, pv, tb, blocks));
+    KT_CUDA(c, dispatch_reconcile(c, pv, tb, px.mine, blocks));
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   if (do_rec && multi && M > 0) {
     // the single exchange of the pass: int64 sum of the per-throttle partials over NVLink
-    int e = g_nccl.AllReduce(c->d_part.p, c->d_part.p, (size_t)(2 * R + 1) * M, kNcclInt64, kNcclSum, c->comm, c->stream);
+    int e = g_nccl.AllReduce(px.mine, px.mine, (size_t)(2 * R + 1) * M, kNcclInt64, kNcclSum, c->comm, c->stream);
     if (e != 0) return fail(c, KT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
@@ -962,7 +982,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     // PDL: overlaps its launch + override merge with the tail of k_reconcile (or of the all-reduce kernel)
     const long long lanes = (long long)M * G;
     KT_CUDA(c, launch(c, k_finalize, (unsigned)((lanes + 127) / 128), 128, 0, /*pdl=*/!tm, tv, M, R, G, (long long)now, flags, px, ov,
-                      c->d_check.as<unsigned char>()));
+                      c->d_pre.as<unsigned char>()));
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
@@ -970,7 +990,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     const PodView pv = pod_view(pend);
     const unsigned blocks = (unsigned)((pend.n + kTileCheck - 1) / kTileCheck);
     if (c->sparse_cap) KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 4, c->stream));  // k_check appends; nobody in it can clear first
-    KT_CUDA(c, dispatch_check(c, pv, tb, blocks, /*pdl=*/!tm && M > 0));
+    KT_CUDA(c, dispatch_check(c, pv, tb, px, blocks, /*pdl=*/!tm && M > 0));
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));

@@ -139,15 +139,20 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 // so the waits cannot deadlock whatever the residency.  Signals are fence + relaxed add (release pattern) by
 // thread 0 after a CTA barrier; waits are relaxed polls + one acquire fence by thread 0 followed by a CTA barrier.
 struct PassSync {
-  unsigned ticket;    // next tile
-  unsigned rec_done;  // reconcile tiles finished (their REDs are performed at L2)
-  unsigned fin_done;  // finalize tiles finished (check constants written)
+  // counters of ONE pass, re-armed by its last CTA (everything before `error`)
+  unsigned ticket;      // next tile
+  unsigned rec_done;    // reconcile tiles finished (their REDs are performed at L2)
+  unsigned prep_done;   // finalize tiles that have written their throttles' pre-records (nothing to wait for: early)
   unsigned match_done;  // pending-match tiles finished (affectedThrottles rows written)
-  unsigned exited;    // CTAs that are done with everything; the last one re-arms the counters
-  unsigned epoch;     // multi-GPU: last pass whose partial sums this rank has published (peers poll it over NVLink)
-  unsigned peers_epoch;  // multi-GPU: last pass for which this rank has seen every peer's publication (polled locally)
-  unsigned error;        // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
+  unsigned pushed;      // multi-GPU: finalize tiles of this rank that have added their partial sums into every rank's totals
+  unsigned exited;      // CTAs that are done with everything; the last one re-arms the counters
+  unsigned error;       // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
+  unsigned pad;
+  // multi-GPU, never re-armed (pass numbers only grow): flag[src] = last pass whose partial sums rank `src` has added into THIS
+  // rank's totals -- written over NVLink by src's last finalize tile, polled locally
+  unsigned flag[8];
 };
+constexpr int kPassSyncRearm = 6;  // leading counters the last CTA out (or the host, after a timed-out pass) zeroes
 // Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as one
 // acquire load of the same counter after the awaited value has been seen.  An acquire load per poll would invalidate the
 // SM's L1 on every iteration (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it; an
@@ -223,61 +228,76 @@ __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsig
   __syncthreads();
 }
 
-// Where the per-throttle partial sums of this pass live.  Single GPU / NCCL path: mine == zero, no peers
-// (the all-reduce already happened in place).  Peer path: every rank pulls the other ranks' buffers over
-// NVLink inside its finalize tiles; buffers alternate by pass parity so that a rank can re-zero the buffer
-// of the NEXT pass while slower peers may still be reading the current one.
+// Where the per-throttle partial sums of a pass live.  Buffers come in pairs indexed by pass parity: the pass that follows
+// may start adding into the other buffer while readers of this one are still at work, and every pass leaves the OTHER
+// parity's buffers zeroed for its successor (they were last read one whole pass ago).
+// Single GPU / NCCL path: total == mine (NCCL all-reduces in place), no peers.
+// Peer path: the all-reduce is a PUSH inside the pass -- once this rank's reconcile tiles are done, its finalize tiles add
+// its partial sums into the `total` buffer of EVERY rank (red.add over NVLink, posted, no round trip) and the last of them
+// raises flag[rank] everywhere; a reader of `total` waits, locally, until all ranks' flags carry this pass's number.
 struct PartExchange {
-  unsigned long long* mine;   // this pass's partial sums of this rank
-  unsigned long long* zero;   // buffer to leave zeroed for a later pass
-  const unsigned long long* peer[7];
-  const PassSync* peer_sync[7];
-  PassSync* sync;             // this rank's counters (epoch is what the peers poll)
-  int npeers;
-  unsigned epoch;             // this pass
+  unsigned long long* mine;        // this rank's partial sums of this pass (reconcile tiles RED here)
+  unsigned long long* total;       // sums over all ranks (what decide / status read)
+  unsigned long long* zero_mine;   // other parity: left zeroed for the next pass
+  unsigned long long* zero_total;
+  unsigned long long* peer_total[7];
+  PassSync* peer_sync[7];
+  PassSync* sync;                  // this rank's counters and flags
+  int npeers, rank;
+  unsigned epoch;                  // this pass's number
 };
+
+__device__ __forceinline__ void red_add_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // How a dependent role waits for its producer: programmatic dependent launch between separate kernels ...
 struct PdlSync {
-  __device__ __forceinline__ void wait_reconciled(const PartExchange&, bool = true) const { pdl_wait_primary(); }
-  __device__ __forceinline__ void wait_matched() const {}  // same CTA: a barrier already ordered the rows
-  __device__ __forceinline__ void wait_finalized() const { pdl_wait_primary(); }
-  __device__ __forceinline__ void signal_finalized() const {}  // the kernel boundary is the signal
+  __device__ __forceinline__ void wait_reconciled() const { pdl_wait_primary(); }
+  __device__ __forceinline__ void wait_totals(const PartExchange&) const { pdl_wait_primary(); }  // k_finalize is complete: so is everything before it
+  __device__ __forceinline__ void wait_matched() const {}   // same CTA: a barrier already ordered the rows
+  __device__ __forceinline__ void wait_prepped() const {}   // covered by wait_totals (k_check's primary is k_finalize)
+  __device__ __forceinline__ void signal_prepped() const {}
+  __device__ __forceinline__ void exchange_done(const PartExchange&) const {}
 };
-// ... or counters inside the one fused kernel (plus the peers' epochs when the sums are exchanged over NVLink)
+// ... or counters inside the one fused kernel (plus the ranks' flags when the sums are exchanged over NVLink)
 struct FlagSync {
   PassSync* s;
   unsigned n_rec, n_fin, n_match;
-  // first_tile: the finalize tile with the smallest ticket does the talking to the peers for the whole rank
-  __device__ __forceinline__ void wait_reconciled(const PartExchange& px, bool first_tile = true) const {
+  __device__ __forceinline__ void wait_reconciled() const { cta_wait_at_least(&s->rec_done, n_rec, &s->error); }
+  // the sums of every rank are in px.total
+  __device__ __forceinline__ void wait_totals(const PartExchange& px) const {
+    if (px.npeers == 0) { wait_reconciled(); return; }
     if (threadIdx.x == 0) {
-      spin_until([&] { return poll_gpu(&s->rec_done) >= n_rec; }, &s->error, 40);
-      acquire_gpu(&s->rec_done);
-      if (px.npeers > 0) {
-        if (first_tile) {
-          // publish: this rank's partial sums of pass `epoch` are complete (its reconcile tiles fenced their REDs at L2,
-          // which is where the peers read them) ...
-          __threadfence_system();
-          *reinterpret_cast<volatile unsigned*>(&px.sync->epoch) = px.epoch;
-          // ... wait until every peer has published the same pass (one poller per rank keeps the links quiet) ...
-          for (int i = 0; i < px.npeers; ++i) {
-            spin_until([&] { return (int)(poll_sys(&px.peer_sync[i]->epoch) - px.epoch) >= 0; }, &s->error, 20);
-            acquire_sys(&px.peer_sync[i]->epoch);  // epochs only grow
-          }
-          // ... and tell the other finalize tiles of this rank
-          __threadfence();
-          *reinterpret_cast<volatile unsigned*>(&px.sync->peers_epoch) = px.epoch;
-        } else {
-          spin_until([&] { return (int)(poll_gpu(&px.sync->peers_epoch) - px.epoch) >= 0; }, &s->error, 40);
-          acquire_gpu(&px.sync->peers_epoch);
-        }
+      for (int src = 0; src <= px.npeers; ++src) {
+        const unsigned* f = &s->flag[src];
+        spin_until([&] { return (int)(poll_gpu(f) - px.epoch) >= 0; }, &s->error, 40);  // written remotely, polled in local memory
+        acquire_sys(f);  // pass numbers only grow
       }
     }
     __syncthreads();
   }
   __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match, &s->error); }
-  __device__ __forceinline__ void wait_finalized() const { cta_wait_at_least(&s->fin_done, n_fin, &s->error); }
-  __device__ __forceinline__ void signal_finalized() const { cta_signal(&s->fin_done); }
+  __device__ __forceinline__ void wait_prepped() const { cta_wait_at_least(&s->prep_done, n_fin, &s->error); }
+  __device__ __forceinline__ void signal_prepped() const { cta_signal(&s->prep_done); }
+  // this finalize tile has issued its adds into every rank's totals: once ALL of this rank's tiles have, the flags go up
+  __device__ __forceinline__ void exchange_done(const PartExchange& px) const {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();  // this CTA's remote adds are performed before the count below can be observed
+      if (atomicAdd(&s->pushed, 1u) == n_fin - 1) {
+        __threadfence_system();  // ... and, through the count, every other tile's
+        for (int i = 0; i < px.npeers; ++i) st_release_sys_u32(&px.peer_sync[i]->flag[px.rank], px.epoch);
+        st_release_sys_u32(&s->flag[px.rank], px.epoch);
+      }
+    }
+  }
 };
 
 // ---- label -> table row ---------------------------------------------------------------------------
@@ -747,17 +767,31 @@ __global__ void __launch_bounds__(kTileReconcile, 768 / kTileReconcile) k_reconc
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finalize: a group of G = 2^g >= R+1 lanes per throttle; lane r < R owns resource r, lane R owns the
-// pod count.  Every Quantity compare of the reconcile tail and of CheckThrottledFor's constants is one
-// lane's scalar work, the per-throttle bitmasks are assembled with a ballot.  Consumes (and re-zeroes)
-// the partial sums.
+// Finalize tiles: a group of G = 2^g >= R+1 lanes per throttle; lane r < R owns resource r, lane R owns the pod count.
+// Two halves:
+//   prep    (no dependency on the running pods, done and signalled at once) CalculateThreshold(now), the threshold
+//           CheckThrottledFor uses, what is already used before this pass's sums (observed status.used in GIVEN_STATUS mode,
+//           the reservations) -> one PRE-RECORD per throttle.  The decide tiles turn it into the 4-step check's constants
+//           themselves, adding this pass's sums: finalize is NOT a stage of the pass's critical path.
+//   status  (after the reconcile tiles) used / throttled / calculated threshold columns for the host; with peers, the
+//           all-reduce: this rank's sums are ADDED into every rank's totals over NVLink (push), then the flags go up.
 // ------------------------------------------------------------------------------------------------
+// Pre-record of one throttle: PreHdr, int64 thrv[R] (thresholds), int64 base[R] (given used + reserved), thr_cnt, base_cnt.
+struct __align__(16) PreHdr {
+  uint32_t thr_has;   // threshold has resource r / KT_COUNT_BIT: has resourceCounts
+  uint32_t base_has;  // `base` is present (Go map has the key / Counts != nil)
+  uint32_t st_thr;    // GIVEN_STATUS: the observed status.throttled
+  uint32_t flags;     // kPre*
+};
+constexpr uint32_t kPreLive = 1u, kPreE3 = 2u, kPreOnEqual = 4u, kPreGiven = 8u;
+__host__ __device__ inline size_t pre_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }
+
 template <class Sync>
 __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int R, int G, long long now, uint32_t eval_flags, const PartExchange& px,
-                                              const ReconcileView& out, unsigned char* __restrict__ check /* [M][16 + 16R] */, int tile_index,
+                                              const ReconcileView& out, unsigned char* __restrict__ pre /* [M][pre_record_bytes(R)] */, int tile_index,
                                               const Sync& sync, unsigned long long* trace_row = nullptr) {
-  // optional stage stamps (kt_enable_trace): [4] thresholds loaded, waiting; [5] partial sums of every rank complete;
-  // [6] sums read (peers over NVLink); [7] constants written
+  // optional stage stamps (kt_enable_trace): [4] pre-records written; [5] this rank's reconcile tiles done; [6] sums of every
+  // rank read; [7] status columns written
   auto stamp = [&](int k) {
     if (trace_row && threadIdx.x == 0) {
       unsigned long long t;
@@ -775,10 +809,21 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   const bool is_res = in_range && r < R, is_cnt = in_range && r == R;
   const uint32_t mybit = r < R ? (1u << r) : KT_COUNT_BIT;
   const size_t col = (size_t)r * M + t;  // resource lanes: index into [R][M] columns
+  const size_t i_val = is_res ? col : (size_t)2 * R * M + t;  // this lane's sum in a partial-sum buffer
+  const size_t i_has = (size_t)(R + r) * M + t;               // resource lanes: its presence flag
 
-  // ---- independent of the running pods: CalculateThreshold(now) ----
-  // merged active overrides REPLACE spec.threshold; per resource name the first active override wins
-  // (throttle_types.go:65-106)
+  // the other parity's buffers are left zeroed for the next pass -- before anything of this pass is signalled to anybody
+  if (is_res) {
+    px.zero_mine[col] = 0ull;
+    px.zero_mine[i_has] = 0ull;
+    if (px.npeers > 0) { px.zero_total[col] = 0ull; px.zero_total[i_has] = 0ull; }
+  } else if (is_cnt) {
+    px.zero_mine[i_val] = 0ull;
+    if (px.npeers > 0) px.zero_total[i_val] = 0ull;
+  }
+
+  // ---- CalculateThreshold(now): merged active overrides REPLACE spec.threshold; per resource name the first active
+  // override wins (throttle_types.go:65-106) ----
   uint32_t tflags = 0;
   bool spec_has = false, calc_has = false, active_found = false;
   long long spec_val = 0, calc_val = 0;
@@ -801,75 +846,30 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     calc_has = active_found ? ov_has : spec_has;
     calc_val = active_found ? ov_val : spec_val;
   }
-  // GIVEN_STATUS: what PreFilter sees is the informer copy of .status (throttle_types.go:128-132)
-  bool g_thr_has = false, g_su_has = false, g_st_thr = false;
-  long long g_thr = 0, g_su = 0;
+  // the threshold CheckThrottledFor compares with (throttle_types.go:128-132): this pass's, or -- GIVEN_STATUS, what
+  // PreFilter sees -- the informer copy's status.calculatedThreshold when calculatedAt is set, else spec.threshold
+  bool thr_has = calc_has, base_has = false, g_st_thr = false;
+  long long thr = calc_val, base = 0;
   if (given && (is_res || is_cnt)) {
-    if (tv.st_calculated[t]) {  // calculatedAt != zero => status.calculatedThreshold.threshold
-      g_thr_has = tv.st_calc_present[t] & mybit;
-      g_thr = is_res ? tv.st_calc_thr[col] : tv.st_calc_cnt[t];
+    if (tv.st_calculated[t]) {
+      thr_has = tv.st_calc_present[t] & mybit;
+      thr = is_res ? tv.st_calc_thr[col] : tv.st_calc_cnt[t];
     } else {
-      g_thr_has = spec_has;
-      g_thr = spec_val;
+      thr_has = spec_has;
+      thr = spec_val;
     }
-    g_su_has = tv.st_used_present[t] & mybit;
-    g_su = is_res ? tv.st_used[col] : tv.st_used_cnt[t];
+    if (tv.st_used_present[t] & mybit) {  // alreadyUsed starts from status.used ...
+      base_has = true;
+      base = is_res ? tv.st_used[col] : tv.st_used_cnt[t];
+    }
     g_st_thr = tv.st_throttled[t] & mybit;
   }
-  bool res_has = false;
-  long long res_val = 0;
-  if ((is_res || is_cnt) && tv.reserved_present) {
-    res_has = tv.reserved_present[t] & mybit;
-    if (res_has) res_val = is_res ? (tv.reserved ? tv.reserved[col] : 0) : (tv.reserved_cnt ? tv.reserved_cnt[t] : 0);
+  if ((is_res || is_cnt) && tv.reserved_present && (tv.reserved_present[t] & mybit)) {  // ... + reserved: presence is the union
+    base_has = true;
+    base += is_res ? (tv.reserved ? tv.reserved[col] : 0) : (tv.reserved_cnt ? tv.reserved_cnt[t] : 0);
   }
   const bool is_throttle_kind = in_range ? tv.kind[t] == KT_KIND_THROTTLE : true;
-
-  stamp(4);
-  sync.wait_reconciled(px, tile_index == 0);  // the partial sums (of every rank) are complete and visible
-  stamp(5);
-
-  // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count; with peers the
-  // all-reduce happens right here: every rank adds up the same buffers over NVLink (uncached loads) ----
-  long long used_val = 0;
-  bool used_has = false;
-  if (is_res || is_cnt) {
-    const size_t i_val = is_res ? col : (size_t)2 * R * M + t;
-    const size_t i_has = (size_t)(R + r) * M + t;  // resource lanes only
-    unsigned long long v = __ldcg(&px.mine[i_val]);
-    unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
-    // peer windows are not cached in this GPU's L2; ld.cg keeps them out of L1 as well and, unlike volatile loads, lets
-    // all of a lane's peer loads be in flight together (one NVLink round trip instead of 2 x npeers)
-    unsigned long long pv[7], ph[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      pv[i] = ph[i] = 0ull;
-      if (i < px.npeers) {
-        pv[i] = __ldcg(&px.peer[i][i_val]);
-        if (is_res) ph[i] = __ldcg(&px.peer[i][i_has]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) { v += pv[i]; h += ph[i]; }
-    used_val = (long long)v;
-    used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
-  }
-  if (trace_row && threadIdx.x == 0 && used_val == 0x7fffffffffffffffll) trace_row[6] = 1;  // the loads have landed
-  stamp(6);
   const bool live = (tflags & KT_THR_RESPONSIBLE) && !(tflags & KT_THR_SELECTOR_ERROR);
-  // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
-  const bool throttled = live && calc_has && used_has && used_val >= calc_val;
-
-  // ---- constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55) ----
-  const bool thr_has = given ? g_thr_has : calc_has;
-  const long long thr = given ? g_thr : calc_val;
-  const bool su_has = given ? g_su_has : used_has;
-  const long long su = given ? g_su : used_val;
-  const bool st_thr = given ? g_st_thr : throttled;
-  // alreadyUsed = {} + status.used + reserved : absent values are 0, presence is the union
-  const bool au_has = su_has || res_has;
-  const long long au = (su_has ? su : 0) + res_val;
-  const bool e3 = is_throttle_kind ? true : on_equal;  // Q1: Throttle hard-codes true (:143)
-  const bool s3 = thr_has && au_has && (e3 ? au >= thr : au > thr);
 
   // ---- per-throttle masks: one ballot each, bit (lane - gbase) = resource r, bit R = count ----
   const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
@@ -878,39 +878,71 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     const uint32_t g = (__ballot_sync(kFull, pred) >> gbase) & gmask;
     return (g & rmask) | (((g >> R) & 1u) ? KT_COUNT_BIT : 0u);
   };
+  const uint32_t m_thr = group_mask(thr_has), m_base = group_mask(base_has), m_st = group_mask(g_st_thr);
+  {
+    unsigned char* rec = pre + (size_t)t * pre_record_bytes(R);
+    long long* vals = reinterpret_cast<long long*>(rec + 16);  // thrv[R], base[R], thr_cnt, base_cnt
+    if (is_res) {
+      vals[r] = thr;
+      vals[R + r] = base;
+    } else if (is_cnt) {
+      PreHdr h;
+      h.thr_has = m_thr;
+      h.base_has = m_base;
+      h.st_thr = m_st;
+      // Q1: S3 compares with >= for a Throttle whatever the caller says (throttle_types.go:143), a ClusterThrottle passes
+      // isThrottledOnEqual on (clusterthrottle_types.go:45)
+      h.flags = (live ? kPreLive : 0u) | ((is_throttle_kind || on_equal) ? kPreE3 : 0u) | (on_equal ? kPreOnEqual : 0u) | (given ? kPreGiven : 0u);
+      *reinterpret_cast<PreHdr*>(rec) = h;
+      vals[2 * R] = thr;
+      vals[2 * R + 1] = base;
+    }
+  }
+  sync.signal_prepped();
+  stamp(4);
+
+  sync.wait_reconciled();  // this rank's partial sums are complete and visible
+  stamp(5);
+  // ---- used (this pass): resource lanes read sum + presence flag, the count lane the pod count.  With peers the
+  // all-reduce happens right here, as a push: the lane adds its value into every rank's totals ----
+  long long used_val = 0;
+  bool used_has = false;
+  if (px.npeers > 0) {
+    if (is_res || is_cnt) {
+      const unsigned long long v = __ldcg(&px.mine[i_val]);
+      const unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
+      if (v) {
+        atomicAdd(&px.total[i_val], v);
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          if (i < px.npeers) red_add_sys_u64(&px.peer_total[i][i_val], v);
+      }
+      if (h) {  // presence travels as a flag: any rank that saw the key stores the same 1
+        px.total[i_has] = 1ull;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          if (i < px.npeers) st_relaxed_sys_u64(&px.peer_total[i][i_has], 1ull);
+      }
+    }
+    sync.exchange_done(px);
+    sync.wait_totals(px);
+  }
+  if (is_res || is_cnt) {
+    const unsigned long long v = __ldcg(&px.total[i_val]);
+    const unsigned long long h = is_res ? __ldcg(&px.total[i_has]) : 0ull;
+    used_val = (long long)v;
+    used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
+  }
+  if (trace_row && threadIdx.x == 0 && used_val == 0x7fffffffffffffffll) trace_row[6] = 1;  // the loads have landed
+  stamp(6);
+  // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
+  const bool throttled = live && calc_has && used_has && used_val >= calc_val;
   const uint32_t m_used = group_mask(used_has);
   const uint32_t m_throttled = group_mask(throttled);
   const uint32_t m_calc = group_mask(calc_has);
-  const uint32_t m_thr = group_mask(thr_has);
-  const uint32_t m_st = group_mask(st_thr);
-  const uint32_t m_s3 = group_mask(s3);
-  // count-lane specials of the 4-step check
-  const bool s1c = is_cnt && thr_has && 1 > thr;                                           // S1: pod count 1 > threshold (Q4)
-  const bool s4c = is_cnt && thr_has && (on_equal ? au + 1 >= thr : au + 1 > thr);        // S4 (counts always present: the pod)
-  const uint32_t m_s1c = group_mask(s1c), m_s4c = group_mask(s4c);
-
-  // the constants the decide tiles are waiting for go out FIRST and are signalled right away; the status columns (only the
-  // host reads them) and the re-zeroing of the partial sums follow, off the critical path
-  if (is_res) {
-    long long* thrv = reinterpret_cast<long long*>(check + (size_t)t * (16 + 16 * R) + 16);
-    thrv[r] = thr;
-    thrv[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
-  } else if (is_cnt) {
-    CheckHdr h;
-    h.thr_has = m_thr & ~KT_COUNT_BIT;
-    h.m2 = m_st & ~KT_COUNT_BIT;
-    h.m3 = m_s3 & ~KT_COUNT_BIT;
-    h.cntbits = (on_equal ? 16u : 0u) | ((m_s1c & KT_COUNT_BIT) ? 1u : 0u) | ((m_st & KT_COUNT_BIT) ? 2u : 0u) |
-                ((m_s3 & KT_COUNT_BIT) ? 4u : 0u) | ((m_s4c & KT_COUNT_BIT) ? 8u : 0u);
-    if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
-    *reinterpret_cast<CheckHdr*>(check + (size_t)t * (16 + 16 * R)) = h;
-  }
-  sync.signal_finalized();
   if (is_res) {
     if (out.used) out.used[col] = used_val;
     if (out.calc_thr) out.calc_thr[col] = calc_val;
-    px.zero[col] = 0ull;
-    px.zero[(size_t)(R + r) * M + t] = 0ull;
   } else if (is_cnt) {
     if (out.used_cnt) out.used_cnt[t] = used_val;
     if (out.calc_cnt) out.calc_cnt[t] = calc_val;
@@ -918,15 +950,14 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     if (out.throttled) out.throttled[t] = m_throttled;
     if (out.calc_present) out.calc_present[t] = m_calc;
     if (out.override_active) out.override_active[t] = active_found;
-    px.zero[(size_t)2 * R * M + t] = 0ull;
   }
   stamp(7);
 }
 
 __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R, int G, long long now, uint32_t eval_flags, PartExchange px,
-                                                  ReconcileView out, unsigned char* __restrict__ check) {
+                                                  ReconcileView out, unsigned char* __restrict__ pre) {
   pdl_launch_dependents();  // k_check can start matching the pending pods right away
-  finalize_tile(tv, M, R, G, now, eval_flags, px, out, check, blockIdx.x, PdlSync{});
+  finalize_tile(tv, M, R, G, now, eval_flags, px, out, pre, blockIdx.x, PdlSync{});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1021,8 +1052,8 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 // throttles are staged in shared memory by the warp (lane = throttle), so the per-pair work is shared-memory compares
 // instead of dependent global gathers.
 template <int TILE, class Sync>
-__device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ check,
-                                                  const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
+__device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
+                                                  const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                   unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
                                                   const SparseOut sp = SparseOut{nullptr, nullptr, 0}) {
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
@@ -1076,7 +1107,8 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     }
   }
 
-  sync.wait_finalized();  // the check constants are written
+  sync.wait_prepped();     // the pre-records are written (early: they depend on nothing)
+  sync.wait_totals(px);    // the sums of every running pod (of every rank) are in px.total
 
   unsigned char ok = 1;
   // one lane's verdicts on the throttles of one word, from the staged records
@@ -1124,12 +1156,62 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
     }
   };
-  auto stage = [&](uint32_t any, int w, unsigned char* recs) {  // lane = throttle
-    if ((any >> lane) & 1) {
-      const uint4* src = reinterpret_cast<const uint4*>(check + (size_t)(w * 32 + lane) * rec);
-      uint4* dst = reinterpret_cast<uint4*>(recs + (size_t)lane * rec);
-      for (int q = 0; q <= R; ++q) dst[q] = __ldcg(&src[q]);
+  // lane = throttle: the constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55) for
+  // throttle w*32+lane, from its pre-record and this pass's sums -- what a finalize stage between reconcile and decide used
+  // to hand over.  alreadyUsed = status.used + reserved (absent values are 0, presence is the union); in GIVEN_STATUS mode
+  // status.used and status.throttled are the observed ones and the sums are not looked at.
+  const int M = tb.M;
+  auto stage = [&](uint32_t any, int w, unsigned char* recs) {
+    if (!((any >> lane) & 1)) return;
+    const int t = w * 32 + lane;
+    const unsigned char* src = pre + (size_t)t * pre_record_bytes(R);
+    const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));  // written earlier in this launch by another SM: L2 is the point of coherence
+    PreHdr ph;
+    ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
+    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
+    const bool live = ph.flags & kPreLive, e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
+    unsigned char* dst = recs + (size_t)lane * rec;
+    long long* thrv = reinterpret_cast<long long*>(dst + 16);
+    CheckHdr h;
+    h.thr_has = h.m2 = h.m3 = 0;
+    for (int r = 0; r < R; ++r) {
+      const long long thr = __ldcg(&pv[r]);
+      long long au = __ldcg(&pv[R + r]);
+      const bool has = (ph.thr_has >> r) & 1;
+      bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
+      if (!given) {
+        const long long used = (long long)__ldcg(&px.total[(size_t)r * M + t]);
+        const bool used_has = __ldcg(&px.total[(size_t)(R + r) * M + t]) != 0ull;
+        au += used;
+        au_has = au_has || used_has;
+        m2 = has && used_has && used >= thr;  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
+      }
+      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+      thrv[r] = thr;
+      thrv[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+      h.thr_has |= (has ? 1u : 0u) << r;
+      h.m2 |= (m2 ? 1u : 0u) << r;
+      h.m3 |= (s3 ? 1u : 0u) << r;
     }
+    {  // the pod count: the pending pod itself counts 1
+      const long long thr = __ldcg(&pv[2 * R]);
+      long long au = __ldcg(&pv[2 * R + 1]);
+      const bool has = ph.thr_has & KT_COUNT_BIT;
+      bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
+      if (!given) {
+        const long long used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
+        const bool used_has = used > 0;  // Counts stays nil with zero counted pods (Q3)
+        au += used;
+        au_has = au_has || used_has;
+        m2 = has && used_has && used >= thr;
+      }
+      const bool s1 = has && 1 > thr;                                             // S1: pod count 1 > threshold (Q4)
+      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+      const bool s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);           // S4 (counts always present: the pod)
+      h.cntbits = (on_equal ? 16u : 0u) | (s1 ? 1u : 0u) | (m2 ? 2u : 0u) | (s3 ? 4u : 0u) | (s4 ? 8u : 0u);
+    }
+    if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
+    *reinterpret_cast<CheckHdr*>(dst) = h;
   };
 #pragma unroll
   for (int k = 0; k < kDecidePrefetch; ++k)
@@ -1161,13 +1243,13 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
 
 // k_check: both phases of one tile in one CTA (the PDL-chained path: phase 1 overlaps k_reconcile / k_finalize).
 template <int TPC, int B, bool REG>
-__global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ check,
+__global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb, int L, int R, const unsigned char* __restrict__ pre, const PartExchange px,
                                                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                       unsigned char* __restrict__ admit, SparseOut sparse /* count zeroed by the host before the launch */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
   __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
-  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), check, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
+  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), pre, px, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1187,13 +1269,15 @@ struct PassArgs {
   uint32_t* pend_bitmap;
   uint32_t* codes;
   unsigned char* admit;
-  unsigned char* check;
+  unsigned char* pre;   // [M] pre-records (finalize tiles -> decide tiles)
   SparseOut sparse;
   PassSync* sync;
   long long now;
   uint32_t eval_flags;
   int L, R, S, G;
-  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]
+  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]; a tile only ever
+                                 // waits for SMALLER tickets (decide: match, finalize's prep half, reconcile -- with peers the finalize
+                                 // tiles' push) or for other GPUs, whose tiles are subject to the same order
   unsigned long long* trace;     // optional (kt_enable_trace): per CTA 8 x u64 {ticket, sm, t_start, t_end, 4 stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1224,9 +1308,9 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
                                     a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
-    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.check, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
+    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.check, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -1241,8 +1325,9 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
     if (atomicAdd(&a.sync->exited, 1u) == total - 1) {
       a.sync->ticket = 0;
       a.sync->rec_done = 0;
-      a.sync->fin_done = 0;
+      a.sync->prep_done = 0;
       a.sync->match_done = 0;
+      a.sync->pushed = 0;
       a.sync->exited = 0;
     }
   }

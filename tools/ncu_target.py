@@ -11,7 +11,12 @@ from kube_throttler_b200 import synth
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-snap = synth.generate(cfg, calibrate=cfg in ("C1", "C2"))
+scale = int(os.environ.get("KT_ROWS_SCALE", "1"))
+if scale > 1:
+    base = synth.CONFIGS[cfg]
+    snap = synth.generate(cfg, n=base["n"] * scale, p=base["p"] * scale, calibrate=False)
+else:
+    snap = synth.generate(cfg, calibrate=cfg in ("C1", "C2"))
 eng = kt.Engine(snap.R, snap.L, snap.LN)
 eng.upload_snapshot(snap)
 fused = len(sys.argv) > 3 and sys.argv[3] == "fused"

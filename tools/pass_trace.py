@@ -36,6 +36,10 @@ for it in range(4):
         lo += int(n)
         st, en = (r[:, 2] - t0) / 1e3, (r[:, 3] - t0) / 1e3
         print(f"  {name:9s} n={int(n):4d}  start {st.min():6.1f}..{st.max():6.1f}  end {en.min():6.1f}..{en.max():6.1f}  median dur {np.median(en - st):6.1f} us")
+        if name == "finalize":
+            stages = [(r[:, k].astype(np.float64) - t0) / 1e3 for k in (4, 5, 6, 7)]
+            print("            finalize stages since pass start (median / max us): pre-records %.1f/%.1f | reconcile seen %.1f/%.1f | sums read %.1f/%.1f | status written %.1f/%.1f"
+                  % tuple(v for x in stages for v in (np.median(x), x.max())))
         if name == "reconcile":
             stages = [(r[:, k].astype(np.float64) - r[:, 2].astype(np.float64)) / 1e3 for k in (4, 5, 6, 7)]
             print("            reconcile stages since tile start (median us): rows loaded+translated %.1f | barrier %.1f | words+sums %.1f | sweep %.1f"

@@ -46,6 +46,7 @@ struct PodStore {
   int64_t n = 0;
   DevBuf labels, req, present, flags, ns;
   DevBuf roff;              // [Lpad][n] u32: the labels as row offsets into the current selector tables (k_translate_rows)
+  DevBuf winfo;             // [n] u32: the words that can apply to the row's namespace (winfo_pack), same life cycle as roff
   bool roff_valid = false;  // false after a full upload or a table compile; row deltas translate their own rows
   DevBuf c_labels, c_req, c_meta;  // staging of the compact transfer format (kt_upload_pods_compact)
   DevBuf c_pairs;                  // label-pair dictionary of the packed transfer format (kt_upload_pods_packed)
@@ -53,7 +54,7 @@ struct PodStore {
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
   void release() {
-    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release();
+    labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release(); winfo.release();
     roff_valid = false;
     c_labels.release(); c_req.release(); c_meta.release(); c_pairs.release(); c_dict.release();
     t_rows.release(); t_labels.release(); t_req.release(); t_present.release(); t_flags.release(); t_ns.release(); t_words.release();
@@ -256,6 +257,7 @@ PodView pod_view(const PodStore& s) {
   PodView v;
   v.labels = s.labels.as<int64_t>();
   v.roff = s.roff.as<uint32_t>();
+  v.winfo = s.winfo.as<uint32_t>();
   v.req = s.req.as<int64_t>();
   v.present = s.present.as<uint32_t>();
   v.flags = s.flags.as<uint32_t>();
@@ -268,15 +270,17 @@ PodView pod_view(const PodStore& s) {
 int translate_rows(kt_ctx* c, PodStore& s, int64_t k, const int64_t* rows_dev) {
   const int Lpad = (c->lim.label_slots + 7) & ~7;
   if (k <= 0) return KT_OK;
-  k_translate_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, rows_dev, table_view(c), Lpad, s.n, s.labels.as<int64_t>(), s.roff.as<uint32_t>());
+  k_translate_rows<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, rows_dev, table_view(c), Lpad, s.n, s.labels.as<int64_t>(), s.ns.as<int32_t>(),
+                                                                          s.roff.as<uint32_t>(), s.winfo.as<uint32_t>());
   KT_CUDA(c, cudaGetLastError());
   return KT_OK;
 }
 // Before a pass: the store's row offsets must match its labels and the current tables.
 int ensure_roff(kt_ctx* c, PodStore& s) {
-  if (!KT_PRETRANSLATED || s.roff_valid || !c->have_throttles) return KT_OK;
+  if (s.roff_valid || !c->have_throttles) return KT_OK;
   const int Lpad = (c->lim.label_slots + 7) & ~7;
   KT_CUDA(c, s.roff.reserve((size_t)Lpad * s.n * 4 + 16));
+  KT_CUDA(c, s.winfo.reserve((size_t)s.n * 4 + 16));
   int rc = translate_rows(c, s, s.n, nullptr);
   if (rc) return rc;
   s.roff_valid = true;
@@ -551,7 +555,7 @@ int64_t kt_get_trace(kt_ctx* c, uint64_t* rows, int64_t cap, uint32_t roles[4]) 
   if (!c->trace || !c->d_trace.p || total == 0) return 0;
   const int64_t n = total < cap ? total : cap;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
+  if (n > 0) KT_CUDA(c, cudaMemcpy(rows, c->d_trace.p, (size_t)n * kTraceRow * 8, cudaMemcpyDeviceToHost));
   return n;
 }
 
@@ -943,8 +947,8 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     a.n_chk = (unsigned)((pend.n + kTileReconcile - 1) / kTileReconcile);
     if (c->trace) {
       const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;
-      KT_CUDA(c, c->d_trace.reserve(rows * 64));
-      KT_CUDA(c, cudaMemsetAsync(c->d_trace.p, 0, rows * 64, c->stream));
+      KT_CUDA(c, c->d_trace.reserve(rows * kTraceRow * 8));
+      KT_CUDA(c, cudaMemsetAsync(c->d_trace.p, 0, rows * kTraceRow * 8, c->stream));
       a.trace = c->d_trace.as<unsigned long long>();
       c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
     }

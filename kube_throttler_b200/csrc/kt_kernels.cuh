@@ -34,9 +34,6 @@ namespace kt {
 #ifndef KT_WAIT_MODE       // how a wait acquires: 0 relaxed polls + acquire fence, 1 relaxed polls + one acquire load, 2 acquire polls
 #define KT_WAIT_MODE 1
 #endif
-#ifndef KT_PRETRANSLATED   // 1: the pass reads row offsets translated at upload time (k_translate_rows); 0: it translates labels itself
-#define KT_PRETRANSLATED 1
-#endif
 #ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
 #define KT_PASS_THREADS 896
 #endif
@@ -54,11 +51,29 @@ constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = KT_SLOT_CAP;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kDecidePrefetch = 3;   // match words per warp whose check constants the decide tile stages in one go
+#ifndef KT_STAGE_CHUNK
+#define KT_STAGE_CHUNK 2
+#endif
+constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record values and sums a decide lane requests together
+constexpr int kTraceRow = 16;        // u64 per CTA of the optional in-kernel trace: {ticket, sm, t_start, t_end, 12 stage stamps}
+
+// Word info of a pod row (k_translate_rows; valid for the tables it was computed with): the words whose namespace mask is
+// non-zero for the pod's namespace are the only ones the pod can match anything in.  Namespace-scoped Throttles give 1-3 of
+// them, so the first two travel INLINE with the row -- the pass starts gathering table rows as soon as the row has landed,
+// instead of two dependent hops (namespace -> list offsets -> word indices) later.
+//   bits 0..11 first word, 12..23 second word, 24..31 count: 0..2 everything is inline; 3..254 the rest comes from the
+//   namespace's list (nsw_off / nsw_idx); kWinfoList: tables with more than 4096 words, nothing is inline
+constexpr uint32_t kWinfoList = 0xffu;
+__host__ __device__ inline uint32_t winfo_pack(int cnt, int w0, int w1, int W) {
+  if (W > 4096) return kWinfoList << 24;
+  return (uint32_t)(w0 & 0xfff) | ((uint32_t)(w1 & 0xfff) << 12) | ((uint32_t)(cnt > 254 ? 254 : cnt) << 24);
+}
 constexpr int kHeavyPods = KT_HEAVY_PODS;        // a throttle matching more pods of a warp than this is summed by the whole warp
 
 struct PodView {
   const int64_t* labels;    // [Lpad][n] keyId<<32 | valId (the snapshot as uploaded; re-translated when the tables change)
   const uint32_t* roff;     // [Lpad][n] the same labels as row offsets into the CURRENT selector tables (k_translate_rows)
+  const uint32_t* winfo;    // [n] the 32-throttle words that can apply to the pod's namespace: first two inline + count (k_translate_rows)
   const int64_t* req;       // [R][n]
   const uint32_t* present;  // [n]
   const uint32_t* flags;    // [n]
@@ -78,6 +93,28 @@ struct TableView {
   const int32_t* nsw_off;   // [NS+1]
   const int32_t* nsw_idx;
   int32_t M, W, Wp, TPpad, B, rows, NS;
+};
+
+// A lane's walk over its namespace's words in ascending order.
+struct WordCursor {
+  int cnt, inl, lo, w0, w1;
+  __device__ __forceinline__ void init(const TableView& tb, uint32_t winfo, int ns, bool on) {
+    const int c8 = on ? (int)(winfo >> 24) : 0;
+    w0 = (int)(winfo & 0xfffu);
+    w1 = (int)((winfo >> 12) & 0xfffu);
+    cnt = c8;
+    inl = c8 == (int)kWinfoList ? 0 : (c8 < 2 ? c8 : 2);
+    lo = 0;
+    if (c8 > 2) {  // rare with namespaced Throttles: the list itself
+      lo = __ldg(&tb.nsw_off[ns]);
+      cnt = __ldg(&tb.nsw_off[ns + 1]) - lo;
+    }
+  }
+  __device__ __forceinline__ int at(const TableView& tb, int k) const {
+    if (k >= cnt) return 0x7fffffff;
+    if (k < inl) return k == 0 ? w0 : w1;
+    return __ldg(&tb.nsw_idx[lo + k]);
+  }
 };
 
 // Per-throttle constants of the 4-step check, produced by k_finalize, gathered per matched pair.
@@ -532,7 +569,8 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
                                                unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */,
                                                unsigned char* smem_raw, int64_t tile_index, unsigned long long* trace_row = nullptr) {
   constexpr int TILE = kTileReconcile;
-  // optional stage stamps of warp 0 (kt_enable_trace): [4] rows loaded+translated, [5] barrier passed, [6] words done, [7] sweep done
+  // optional stage stamps of warp 0 (kt_enable_trace): [4] the pod rows have landed, [5] first two words evaluated, [6] barrier
+  // passed, [7] words + sums done, [8] sweep done
   auto stamp = [&](int k) {
     if (trace_row && threadIdx.x == 0) {
       unsigned long long t;
@@ -555,19 +593,15 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
-  // ---- all of the pod row's loads are issued before anything waits on them; the one dependent chain that follows
-  // (namespace -> word-list offsets -> word indices) runs under their latency ----
+  // ---- everything the lane needs of its pod row is requested at once: ONE trip to HBM, and nothing else is waited for
+  // before the table gathers of the first two words go out ----
+  const uint32_t winfo = __ldg(&pods.winfo[pc]);
   const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
   const int ns = __ldg(&pods.ns[pc]);
   const uint32_t present = __ldg(&pods.present[pc]);
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-#if KT_PRETRANSLATED
   load_rows<REG>(pods.roff, pods.n, pc, L, rows);
-#else
-  int64_t lab[8];
-  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
-#endif
   long long rq[RT > 0 ? RT : 1];
   if constexpr (RT > 0) {
     const int64_t* rp = pods.req + pc;
@@ -590,18 +624,15 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const bool counted = (flags & (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) == (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED) &&
                        (unsigned)ns < (unsigned)tb.NS;
   const bool alive = counted && (flags & KT_POD_NOT_FINISHED);  // isNotFinished (pod_util.go:26-28)
-  int j = 0, hi = 0;
-  if (counted) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }  // hop 1 of the word list
-#if !KT_PRETRANSLATED
-  uint4 ke[8];
-  if constexpr (REG) translate8_keys(tb, lab, ke);                                // hop 1 of the labels
-#endif
-  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;                          // hop 2 of the word list
-  int nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;                  // (the word after it is fetched one step ahead)
-#if !KT_PRETRANSLATED
-  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);                      // hop 2 of the labels
-  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
-#endif
+  WordCursor wc;
+  wc.init(tb, winfo, ns, counted);
+  if (trace_row && threadIdx.x == 0 && (rows_touch(rows) | winfo) == 0x12345u) trace_row[4] = 1;  // forces the loads to have landed
+  stamp(4);
+  // phase 1 -- the lane's first two words, back to back and independent of the other lanes (a match word only needs the
+  // lane's own row): their 2 x Lpad table gathers are all in flight together
+  uint32_t m0 = 0, m1 = 0;
+  if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+  if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
 #pragma unroll
@@ -616,28 +647,35 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
     }
   }
   s_present[tid] = present & ~KT_COUNT_BIT;
-  if (trace_row && threadIdx.x == 0 && (rows_touch(rows) | (uint32_t)cur) == 0x12345u) trace_row[4] = 1;  // forces the loads to have landed
-  stamp(4);
-  __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
   stamp(5);
+  __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
+  stamp(6);
+  if (m0) bitmap[p * Wp + wc.w0] = m0;
+  if (m1) bitmap[p * Wp + wc.w1] = m1;
 
   unsigned long long* part_used = part;
   unsigned long long* part_pres = part + (size_t)R * tb.M;
   unsigned long long* part_cnt = part + (size_t)2 * R * tb.M;
 
-  // Words in ascending order, warp-uniform: lanes whose namespace has word w evaluate it, the others idle.
-  // Namespace-clustered rows (the reference's pod informer is namespace-indexed) make this 1-3 rounds.
+  // phase 2 -- the segmented sums, word by word in ascending order, warp-uniform: lanes whose namespace has word w bring
+  // their match word (already known for their first two), the others idle.  Namespace-clustered rows (the reference's pod
+  // informer is namespace-indexed) make this 1-3 rounds.
+  int k = 0;
+  int cur = wc.at(tb, 0);
 #pragma unroll 1
   while (true) {
     const int w = __reduce_min_sync(kFull, cur);
     if (w == 0x7fffffff) break;
     uint32_t word = 0;
     if (cur == w) {
-      word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
-      if (word) bitmap[p * Wp + w] = word;
-      ++j;
-      cur = nxt;
-      nxt = j + 1 < hi ? __ldg(&tb.nsw_idx[j + 1]) : 0x7fffffff;
+      if (k < wc.inl) {
+        word = k == 0 ? m0 : m1;
+      } else {
+        word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
+        if (word) bitmap[p * Wp + w] = word;
+      }
+      ++k;
+      cur = wc.at(tb, k);
     }
     const uint32_t aword = alive ? word : 0u;
     if (!__any_sync(kFull, aword != 0u)) continue;
@@ -738,7 +776,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       }
     }
   }
-  stamp(6);
+  stamp(7);
   __syncthreads();
   // CTA accumulators -> HBM partials: one RED per (throttle, resource) the tile touched.
   for (int idx = tid; idx < S * 32; idx += TILE) {
@@ -755,7 +793,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;  // idempotent flag
     }
   }
-  stamp(7);
+  stamp(8);
 }
 
 template <int TPC, int B, int RT, bool REG>
@@ -1009,15 +1047,11 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes never store
+  const uint32_t winfo = __ldg(&pods.winfo[pc]);
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-#if KT_PRETRANSLATED
   load_rows<REG>(pods.roff, pods.n, pc, L, rows);
-#else
-  int64_t lab[8];
-  if constexpr (REG) load_labels8(pods.labels + pc, pods.n, lab);
-#endif
   {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
@@ -1026,22 +1060,17 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
     for (int i = tid; i < nvec; i += TILE) d0[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * nvec; i += TILE) d1[i] = make_uint4(0, 0, 0, 0);
   }
-  int lo = 0, hi = 0;
-  if ((unsigned)ns < (unsigned)tb.NS) { lo = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-#if !KT_PRETRANSLATED
-  uint4 ke[8];
-  if constexpr (REG) translate8_keys(tb, lab, ke);
-#endif
-  int wcur = lo < hi ? __ldg(&tb.nsw_idx[lo]) : 0;
-#if !KT_PRETRANSLATED
-  if constexpr (REG) translate8_rows(tb, lab, ke, rows.off);
-  else stage_rows<REG>(tb, pods.labels, pods.n, pc, L, rows);
-#endif
+  WordCursor wc;
+  wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
+  uint32_t m0 = 0, m1 = 0;  // the first two words: all their table gathers in flight together
+  if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+  if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
   __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
+  if (m0) bitmap[p * Wp + wc.w0] = m0;
+  if (m1) bitmap[p * Wp + wc.w1] = m1;
 #pragma unroll 1
-  for (int j = lo; j < hi; ++j) {
-    const int w = wcur;
-    if (j + 1 < hi) wcur = __ldg(&tb.nsw_idx[j + 1]);  // one step ahead of its use
+  for (int k = wc.inl; k < wc.cnt; ++k) {
+    const int w = wc.at(tb, k);
     const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
     if (word) bitmap[p * Wp + w] = word;
   }
@@ -1055,7 +1084,16 @@ template <int TILE, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
                                                   const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                   unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
-                                                  const SparseOut sp = SparseOut{nullptr, nullptr, 0}) {
+                                                  const SparseOut sp = SparseOut{nullptr, nullptr, 0}, unsigned long long* trace_row = nullptr) {
+  // optional stage stamps (kt_enable_trace): [4] match rows visible, [5] own words fetched, [6] sums of every rank visible,
+  // [7] decided
+  auto stamp = [&](int k) {
+    if (trace_row && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace_row[k] = t;
+    }
+  };
   const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
   unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][KS][32][rec]
@@ -1079,36 +1117,47 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (v != 0) nz |= 1u << r;
     }
   }
-  int j = 0, hi = 0;
-  if ((unsigned)ns < (unsigned)tb.NS) { j = __ldg(&tb.nsw_off[ns]); hi = __ldg(&tb.nsw_off[ns + 1]); }
-  // Everything that can be known before finalize is done is worked out now: the pod's match words, and the warp's
-  // first KS words in the warp-uniform order with the set of throttles any lane needs of each.  After the wait only the
-  // constants are missing, and the records of all KS words are staged with ONE round trip to L2.
+  const uint32_t winfo = __ldg(&pods.winfo[pc]);
+  WordCursor wc;
+  wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
+  // Everything that can be known before the sums exist is worked out now: the pod's match words, and the warp's first KS
+  // words in the warp-uniform order with the set of throttles any lane needs of each.  After the wait only the sums are
+  // missing, and the constants of all KS words are built with ONE round trip to L2.
   sync.wait_matched();
-  int cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+  stamp(4);
+  int k = 0;
+  int cur = wc.at(tb, 0);
   int pw[kDecidePrefetch];         // warp-uniform word index
   uint32_t pany[kDecidePrefetch];  // throttles of that word some lane matched
   uint32_t pword[kDecidePrefetch]; // this lane's match word
+  // the next (up to) KS words of the warp, their match words fetched together
+  auto gather_words = [&]() {
 #pragma unroll
-  for (int k = 0; k < kDecidePrefetch; ++k) {
-    pw[k] = 0x7fffffff;
-    pany[k] = 0;
-    pword[k] = 0;
-    if (k < KS) {
-      pw[k] = __reduce_min_sync(kFull, cur);
-      if (pw[k] != 0x7fffffff) {
-        if (cur == pw[k]) {
-          pword[k] = __ldcg(&bitmap[p * Wp + pw[k]]);
-          ++j;
-          cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
+    for (int q = 0; q < kDecidePrefetch; ++q) {
+      pw[q] = 0x7fffffff;
+      pany[q] = 0;
+      pword[q] = 0;
+      if (q < KS) {
+        pw[q] = __reduce_min_sync(kFull, cur);
+        if (pw[q] != 0x7fffffff) {
+          if (cur == pw[q]) {
+            pword[q] = __ldcg(&bitmap[p * Wp + pw[q]]);
+            ++k;
+            cur = wc.at(tb, k);
+          }
         }
-        pany[k] = __reduce_or_sync(kFull, pword[k]);
       }
     }
-  }
+#pragma unroll
+    for (int q = 0; q < kDecidePrefetch; ++q)
+      if (q < KS && pw[q] != 0x7fffffff) pany[q] = __reduce_or_sync(kFull, pword[q]);
+  };
+  gather_words();
+  stamp(5);
 
   sync.wait_prepped();     // the pre-records are written (early: they depend on nothing)
   sync.wait_totals(px);    // the sums of every running pod (of every rank) are in px.total
+  stamp(6);
 
   unsigned char ok = 1;
   // one lane's verdicts on the throttles of one word, from the staged records
@@ -1165,79 +1214,85 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     if (!((any >> lane) & 1)) return;
     const int t = w * 32 + lane;
     const unsigned char* src = pre + (size_t)t * pre_record_bytes(R);
+    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
+    // every load below depends on t alone: header, count values and the first chunk of resources go out together
     const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));  // written earlier in this launch by another SM: L2 is the point of coherence
+    const long long c_thr = __ldcg(&pv[2 * R]);
+    long long c_au = __ldcg(&pv[2 * R + 1]);
+    const long long c_used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);  // zero / stale in GIVEN_STATUS mode: ignored below
     PreHdr ph;
     ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
-    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
     const bool live = ph.flags & kPreLive, e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
     unsigned char* dst = recs + (size_t)lane * rec;
     long long* thrv = reinterpret_cast<long long*>(dst + 16);
     CheckHdr h;
     h.thr_has = h.m2 = h.m3 = 0;
-    for (int r = 0; r < R; ++r) {
-      const long long thr = __ldcg(&pv[r]);
-      long long au = __ldcg(&pv[R + r]);
-      const bool has = (ph.thr_has >> r) & 1;
-      bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
-      if (!given) {
-        const long long used = (long long)__ldcg(&px.total[(size_t)r * M + t]);
-        const bool used_has = __ldcg(&px.total[(size_t)(R + r) * M + t]) != 0ull;
-        au += used;
-        au_has = au_has || used_has;
-        m2 = has && used_has && used >= thr;  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
+#pragma unroll 1
+    for (int r0 = 0; r0 < R; r0 += kStageChunk) {
+      long long thr[kStageChunk], au[kStageChunk];
+      unsigned long long used[kStageChunk], uhas[kStageChunk];
+#pragma unroll
+      for (int q = 0; q < kStageChunk; ++q) {
+        const int r = r0 + q < R ? r0 + q : R - 1;  // clamped: the loads stay unconditional (and in flight together)
+        thr[q] = __ldcg(&pv[r]);
+        au[q] = __ldcg(&pv[R + r]);
+        used[q] = __ldcg(&px.total[(size_t)r * M + t]);
+        uhas[q] = __ldcg(&px.total[(size_t)(R + r) * M + t]);
       }
-      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
-      thrv[r] = thr;
-      thrv[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
-      h.thr_has |= (has ? 1u : 0u) << r;
-      h.m2 |= (m2 ? 1u : 0u) << r;
-      h.m3 |= (s3 ? 1u : 0u) << r;
+#pragma unroll
+      for (int q = 0; q < kStageChunk; ++q) {
+        const int r = r0 + q;
+        if (r < R) {
+          const bool has = (ph.thr_has >> r) & 1;
+          bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
+          long long a = au[q];
+          if (!given) {
+            const bool used_has = uhas[q] != 0ull;
+            a += (long long)used[q];
+            au_has = au_has || used_has;
+            m2 = has && used_has && (long long)used[q] >= thr[q];  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
+          }
+          const bool s3 = has && au_has && (e3 ? a >= thr[q] : a > thr[q]);
+          thrv[r] = thr[q];
+          thrv[R + r] = thr[q] - a;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+          h.thr_has |= (has ? 1u : 0u) << r;
+          h.m2 |= (m2 ? 1u : 0u) << r;
+          h.m3 |= (s3 ? 1u : 0u) << r;
+        }
+      }
     }
     {  // the pod count: the pending pod itself counts 1
-      const long long thr = __ldcg(&pv[2 * R]);
-      long long au = __ldcg(&pv[2 * R + 1]);
       const bool has = ph.thr_has & KT_COUNT_BIT;
       bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
       if (!given) {
-        const long long used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
-        const bool used_has = used > 0;  // Counts stays nil with zero counted pods (Q3)
-        au += used;
+        const bool used_has = c_used > 0;  // Counts stays nil with zero counted pods (Q3)
+        c_au += c_used;
         au_has = au_has || used_has;
-        m2 = has && used_has && used >= thr;
+        m2 = has && used_has && c_used >= c_thr;
       }
-      const bool s1 = has && 1 > thr;                                             // S1: pod count 1 > threshold (Q4)
-      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
-      const bool s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);           // S4 (counts always present: the pod)
+      const bool s1 = has && 1 > c_thr;                                               // S1: pod count 1 > threshold (Q4)
+      const bool s3 = has && au_has && (e3 ? c_au >= c_thr : c_au > c_thr);
+      const bool s4 = has && (on_equal ? c_au + 1 >= c_thr : c_au + 1 > c_thr);       // S4 (counts always present: the pod)
       h.cntbits = (on_equal ? 16u : 0u) | (s1 ? 1u : 0u) | (m2 ? 2u : 0u) | (s3 ? 4u : 0u) | (s4 ? 8u : 0u);
     }
     if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
     *reinterpret_cast<CheckHdr*>(dst) = h;
   };
-#pragma unroll
-  for (int k = 0; k < kDecidePrefetch; ++k)
-    if (k < KS && pany[k]) stage(pany[k], pw[k], my_chk + (size_t)k * 32 * rec);
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < kDecidePrefetch; ++k)
-    if (k < KS && pword[k]) decide_word(pword[k], pw[k], my_chk + (size_t)k * 32 * rec);
-  // pods with more words than were prefetched (ClusterThrottle-heavy namespaces): one word at a time
+  // KS words at a time: constants staged (lane = throttle), then every lane decides its own pairs
 #pragma unroll 1
   while (true) {
-    const int w = __reduce_min_sync(kFull, cur);
-    if (w == 0x7fffffff) break;
-    uint32_t word = 0;
-    if (cur == w) {
-      word = __ldcg(&bitmap[p * Wp + w]);
-      ++j;
-      cur = j < hi ? __ldg(&tb.nsw_idx[j]) : 0x7fffffff;
-    }
-    const uint32_t any = __reduce_or_sync(kFull, word);
-    if (!any) continue;
+#pragma unroll
+    for (int q = 0; q < kDecidePrefetch; ++q)
+      if (q < KS && pany[q]) stage(pany[q], pw[q], my_chk + (size_t)q * 32 * rec);
     __syncwarp();
-    stage(any, w, my_chk);
+#pragma unroll
+    for (int q = 0; q < kDecidePrefetch; ++q)
+      if (q < KS && pword[q]) decide_word(pword[q], pw[q], my_chk + (size_t)q * 32 * rec);
+    if (__reduce_min_sync(kFull, cur) == 0x7fffffff) break;  // pods with more words than fit one round (ClusterThrottle-heavy namespaces)
     __syncwarp();
-    if (word) decide_word(word, w, my_chk);
+    gather_words();
   }
+  stamp(7);
   if (valid) admit[p] = ok;
 }
 
@@ -1278,7 +1333,7 @@ struct PassArgs {
   unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]; a tile only ever
                                  // waits for SMALLER tickets (decide: match, finalize's prep half, reconcile -- with peers the finalize
                                  // tiles' push) or for other GPUs, whose tiles are subject to the same order
-  unsigned long long* trace;     // optional (kt_enable_trace): per CTA 8 x u64 {ticket, sm, t_start, t_end, 4 stage stamps} in globaltimer ns
+  unsigned long long* trace;     // optional (kt_enable_trace): per CTA kTraceRow x u64 {ticket, sm, t_start, t_end, stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -1305,12 +1360,13 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
     cta_signal(&a.sync->match_done);
   } else if ((tile -= a.n_chk) < a.n_rec) {
     reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile,
-                                    a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
+                                    a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
-    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * 8 : nullptr);
+    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse,
+                                      a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -1318,7 +1374,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
     if (a.trace) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* row = a.trace + (size_t)s_ticket * 8;
+      unsigned long long* row = a.trace + (size_t)s_ticket * kTraceRow;
       row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
     }
     const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
@@ -1397,11 +1453,23 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t k, const int64_t* 
 // table compile, or the k listed rows after a row delta.  One lane per pod row, coalesced column accesses; the two
 // dictionary hops per label that used to sit on every pass's critical path are paid here, once per change.
 __global__ void __launch_bounds__(256) k_translate_rows(int64_t k, const int64_t* __restrict__ rows, const TableView tb, int Lpad, int64_t n,
-                                                        const int64_t* __restrict__ labels, uint32_t* __restrict__ roff) {
+                                                        const int64_t* __restrict__ labels, const int32_t* __restrict__ ns_col, uint32_t* __restrict__ roff,
+                                                        uint32_t* __restrict__ winfo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k) return;
   const int64_t p = rows ? rows[i] : i;
   if (p < 0 || p >= n) return;
+  {  // the words that can apply to the row's namespace (see winfo_pack)
+    const int ns = ns_col[p];
+    int cnt = 0, w0 = 0, w1 = 0;
+    if ((unsigned)ns < (unsigned)tb.NS) {
+      const int lo = __ldg(&tb.nsw_off[ns]);
+      cnt = __ldg(&tb.nsw_off[ns + 1]) - lo;
+      if (cnt > 0) w0 = __ldg(&tb.nsw_idx[lo]);
+      if (cnt > 1) w1 = __ldg(&tb.nsw_idx[lo + 1]);
+    }
+    winfo[p] = cnt == 0 ? 0u : winfo_pack(cnt, w0, w1, tb.W);
+  }
 #pragma unroll 1
   for (int i0 = 0; i0 < Lpad; i0 += 8) {
     uint32_t o[8];

@@ -1,5 +1,6 @@
-"""Per-role timeline of the fused pass (k_pass) from the in-kernel trace: when each role's tiles start and end
-relative to the first CTA.  python tools/pass_trace.py [C2]"""
+"""Per-role timeline of the fused pass (k_pass) from the in-kernel trace: when each role's tiles start and end relative to
+the first CTA, the stage stamps of every role (median / p90 / max since pass start) and the slowest tiles of each role.
+python tools/pass_trace.py [C2] [sorted|unsorted]"""
 import os
 import sys
 
@@ -12,13 +13,20 @@ import kube_throttler_b200 as kt
 from kube_throttler_b200 import synth
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-snap = synth.generate(cfg, calibrate=cfg in ("C1", "C2"))
+sort = not (len(sys.argv) > 2 and sys.argv[2] == "unsorted")
+snap = synth.generate(cfg, sort_by_namespace=sort)
 eng = kt.Engine(snap.R, snap.L, snap.LN)
 eng.upload_snapshot(snap)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 s = torch.cuda.Stream()
 eng.set_stream(s.cuda_stream)
 eng.enable_trace(True)
+STAGES = {
+    "match": [],
+    "reconcile": ["rows landed", "2 words evaluated", "barrier", "words+sums", "sweep"],
+    "finalize": ["pre-records", "reconcile seen", "sums read", "status written"],
+    "decide": ["match rows seen", "own words", "sums seen", "decided"],
+}
 for it in range(4):
     with torch.cuda.stream(s):
         if it >= 2:
@@ -27,21 +35,25 @@ for it in range(4):
         eng.evaluate(snap.now)
     torch.cuda.synchronize()
     rows, roles = eng.trace()
+    rows = rows.astype(np.float64)
     t0 = rows[:, 2].min()
-    names = ["match", "reconcile", "finalize", "decide"]
     lo = 0
     print(f"pass {it} ({'cold' if it >= 2 else 'warm'} L2): span {(rows[:, 3].max() - t0) / 1e3:.1f} us, {len(rows)} CTAs on {len(set(rows[:, 1]))} SMs")
-    for name, n in zip(names, roles):
+    for name, n in zip(STAGES, roles):
         r = rows[lo:lo + int(n)]
         lo += int(n)
+        if not len(r):
+            continue
         st, en = (r[:, 2] - t0) / 1e3, (r[:, 3] - t0) / 1e3
-        print(f"  {name:9s} n={int(n):4d}  start {st.min():6.1f}..{st.max():6.1f}  end {en.min():6.1f}..{en.max():6.1f}  median dur {np.median(en - st):6.1f} us")
-        if name == "finalize":
-            stages = [(r[:, k].astype(np.float64) - t0) / 1e3 for k in (4, 5, 6, 7)]
-            print("            finalize stages since pass start (median / max us): pre-records %.1f/%.1f | reconcile seen %.1f/%.1f | sums read %.1f/%.1f | status written %.1f/%.1f"
-                  % tuple(v for x in stages for v in (np.median(x), x.max())))
-        if name == "reconcile":
-            stages = [(r[:, k].astype(np.float64) - r[:, 2].astype(np.float64)) / 1e3 for k in (4, 5, 6, 7)]
-            print("            reconcile stages since tile start (median us): rows loaded+translated %.1f | barrier %.1f | words+sums %.1f | sweep %.1f"
-                  % tuple(np.median(x) for x in stages))
+        print(f"  {name:9s} n={int(n):4d}  start {st.min():5.1f}..{st.max():5.1f}  end med {np.median(en):5.1f} p90 {np.percentile(en, 90):5.1f} max {en.max():5.1f}  dur med {np.median(en - st):5.1f}")
+        for k, label in enumerate(STAGES[name]):
+            x = (r[:, 4 + k] - t0) / 1e3
+            x = x[r[:, 4 + k] > 0]
+            if len(x):
+                print(f"            {label:18s} since pass start: med {np.median(x):5.1f}  p90 {np.percentile(x, 90):5.1f}  max {x.max():5.1f}")
+        if it == 3:
+            worst = np.argsort(-en)[:4]
+            for i in worst:
+                stamps = " ".join(f"{(r[i, 4 + k] - t0) / 1e3:5.1f}" if r[i, 4 + k] > 0 else "    -" for k in range(len(STAGES[name])))
+                print(f"            slowest: tile {i:4d} sm {int(r[i, 1]):3d} start {st[i]:5.1f} end {en[i]:5.1f} | {stamps}")
 eng.close()

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 for round in 1 2; do
   for so in build/variants/*.so; do
-    KT_B200_LIB=$PWD/$so python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 1 "$@" 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline'].get('chained_kernel_ms') or {}; print('round $round', '$so', 'pass_us %.2f' % (d['ms_per_step']*1e3), 'e2e %.3g' % d['e2e']['value'], {a: round(b*1e3,1) for a,b in k.items()})"
+    KT_B200_LIB=$PWD/$so python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extras --e2e-steps 1 "$@" 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline'].get('chained_kernel_ms') or {}; print('round $round', '$so', 'pass_us %.2f' % (d['ms_per_step']*1e3), 'flush_us %.2f' % (d['roofline']['other_timing']['ms_per_step']*1e3), 'e2e %.3g' % d['e2e']['value'], {a: round(b*1e3,1) for a,b in k.items()})"
   done
 done

@@ -312,6 +312,19 @@ int kt_get_check(kt_ctx* ctx, uint32_t* codes /*[p][2*words_per_row]*/, uint8_t*
  * read the dense rows instead. */
 int kt_set_sparse_check(kt_ctx* ctx, int64_t cap_entries);
 int kt_get_check_sparse(kt_ctx* ctx, uint8_t* admit /*[p]*/, uint32_t* entries /*[cap][3]*/, int64_t cap, int64_t* count);
+/* The check result of k listed pending rows only (a PreFilter caller that wants the reasons of ONE rejected pod after a pass
+ * over the whole queue): codes[i][2*words_per_row] and admit[i] of rows[i].  Either output may be NULL. */
+int kt_get_check_rows(kt_ctx* ctx, int64_t k, const int64_t* rows, uint32_t* codes /*[k][2*words_per_row]*/, uint8_t* admit /*[k]*/);
+
+/* Device-side status diff (replaces the apiequality.Semantic.DeepEqual(thr.Status, *newStatus) of every reconcile,
+ * throttle_controller.go:157 / clusterthrottle_controller.go:160): when an observed status is uploaded (kt_upload_status) every
+ * reconciling pass compares what it computed -- used (values and presence), throttled, the calculated threshold (a status whose
+ * calculatedAt is unset always differs) -- with it, per responsible throttle, inside the pass.  kt_get_changed delivers how many
+ * throttles differ, up to cap of their indices (unordered) and, when flags != NULL, one byte per throttle; kt_get_reconcile_rows
+ * the status columns of k listed throttles only, shaped [R][k] / [k] -- so that the download after a reconcile is proportional
+ * to what changed, not to M.  Messages and calculatedAt stay on the host (they depend on the spec and the clock alone). */
+int kt_get_changed(kt_ctx* ctx, int32_t* idx /*[cap]*/, int64_t cap, int64_t* count, uint8_t* flags /*[m] or NULL*/);
+int kt_get_reconcile_rows(kt_ctx* ctx, int64_t k, const int32_t* idx, const kt_reconcile_out* out /* columns shaped for k throttles */);
 int kt_get_timing(kt_ctx* ctx, kt_timing* out);
 
 /* ---- host-only introspection (no device needed) -------------------------------- */

@@ -83,6 +83,28 @@ const char* kth_pre_filter(kth_plugin* p, const char* pod_json);
  * result a JSON array of PreFilter results (each pod checked against the same snapshot, independently). */
 const char* kth_pre_filter_batch(kth_plugin* p, const char* pods_json);
 
+/* ---- the scheduling queue, resident on the device -------------------------------------------------------------------
+ * Pods the pod informer delivered (kth_apply) that are this scheduler's to place -- spec.schedulerName == targetSchedulerName,
+ * no spec.nodeName yet, not finished -- are kept packed in the device's pending table as well, row by row, like the running
+ * pods.  PreFilter / Reserve / Unreserve for such a pod can then be addressed BY KEY: no manifest crosses the boundary, nothing
+ * is parsed, packed or uploaded per call.  ONE device pass answers for the whole queue; its verdicts are cached on the host and
+ * stay good per pod until something that pod's verdict depends on changes (its own row, any throttle / namespace object, the
+ * status or the reservations of a throttle IT is affected by).  In the scheduler's PreFilter -> Reserve -> next pod cycle a
+ * PreFilter therefore only costs a device pass when the pod shares a throttle with what was just reserved.
+ * Results have the shape of kth_pre_filter / kth_reserve.  A pod the informer holds that is not queued (already bound, other
+ * scheduler) is checked like a manifest; an unknown key is an {"error": ...}. */
+const char* kth_pre_filter_key(kth_plugin* p, const char* ns, const char* name);
+const char* kth_reserve_key(kth_plugin* p, const char* ns, const char* name);
+const char* kth_unreserve_key(kth_plugin* p, const char* ns, const char* name);
+/* PreFilter of EVERY queued pod in (at most) one device pass, no JSON: verdicts[row] = 0 free row, 1 Success,
+ * 2 UnschedulableAndUnresolvable, 3 Error, for rows [0, min(cap, rows)); returns the number of queue rows (or -1, see
+ * kth_last_error).  kth_queue_row gives the row of a queued pod (-1: not queued); rows are stable while the pod stays queued. */
+int64_t kth_pre_filter_queue(kth_plugin* p, uint8_t* verdicts, int64_t cap);
+int64_t kth_queue_row(kth_plugin* p, const char* ns, const char* name);
+const char* kth_last_error(void);
+/* {"queued":n,"rows":r,"passes":device passes over the queue so far,"hits":by-key calls answered from cached verdicts} */
+const char* kth_queue_stats(kth_plugin* p);
+
 /* Queue-ordered admission: PreFilter and, on Success, Reserve for every pod of a SORTED scheduling queue, with exactly
  * the results the scheduler gets admitting them one per cycle (each admitted pod raises the reservations the next one is
  * checked against, plugin.go:148-238) -- but in as few device passes as the conflicts between the pods allow: a pass

@@ -44,7 +44,7 @@ EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
     "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_alloc_upload", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_check_rows", "kt_get_changed", "kt_get_reconcile_rows", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
@@ -81,6 +81,9 @@ def lib():
         L.kt_upload_pods_packed.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(abi.PackedPodsStruct)]
         L.kt_set_sparse_check.argtypes = [vp, C.c_int64]
         L.kt_get_check_sparse.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.kt_get_check_rows.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.kt_get_changed.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64), vp]
+        L.kt_get_reconcile_rows.argtypes = [vp, C.c_int64, vp, C.POINTER(abi.ReconcileOut)]
         L.kt_update_pod_rows.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.kt_upload_namespaces.argtypes = [vp, C.c_int32, vp]
         L.kt_upload_throttles.argtypes = [vp, C.c_int32, C.POINTER(abi.ThrottleCols), C.POINTER(abi.SelectorTable)]
@@ -280,6 +283,32 @@ class Engine:
         n = C.c_int64(0)
         self._ck(self._L.kt_get_check_sparse(self._h, abi.ptr(admit), abi.ptr(entries), entries.shape[0], C.byref(n)))
         return int(n.value)
+
+    def get_check_rows(self, rows: np.ndarray):
+        """(codes[k][2W], admit[k]) of the listed pending rows."""
+        rows = np.ascontiguousarray(rows, np.int64)
+        codes = np.zeros((rows.shape[0], 2 * self.words_per_row), np.uint32)
+        admit = np.zeros(rows.shape[0], np.uint8)
+        self._ck(self._L.kt_get_check_rows(self._h, rows.shape[0], abi.ptr(rows), abi.ptr(codes), abi.ptr(admit)))
+        return codes, admit
+
+    def get_changed(self):
+        """(sorted indices of the throttles whose status this pass changes, flags[m]) -- the device-side diff against kt_upload_status."""
+        idx = np.zeros(max(self.m, 1), np.int32)
+        flags = np.zeros(max(self.m, 1), np.uint8)
+        n = C.c_int64(0)
+        self._ck(self._L.kt_get_changed(self._h, abi.ptr(idx), idx.shape[0], C.byref(n), abi.ptr(flags)))
+        return np.sort(idx[: int(n.value)]), flags[: self.m]
+
+    def get_reconcile_rows(self, idx: np.ndarray) -> PassResult:
+        """Status columns of the listed throttles only (shaped for len(idx) throttles)."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        k, R, z = idx.shape[0], self.R, np.zeros
+        out = PassResult(self.words_per_row, z((R, k), np.int64), z(k, np.uint32), z(k, np.int64), z(k, np.uint32), z((R, k), np.int64), z(k, np.uint32),
+                         z(k, np.int64), z(k, np.uint8), z((0, 1), np.uint32), z((0, 1), np.uint32), z((0, 1), np.uint32), z(0, np.uint8))
+        rec = out.reconcile_out()
+        self._ck(self._L.kt_get_reconcile_rows(self._h, k, abi.ptr(idx), C.byref(rec)))
+        return out
 
     def get_reconcile(self, out: PassResult):
         rec = out.reconcile_out()

@@ -144,6 +144,9 @@ struct kt_ctx {
   uint32_t trace_roles[4] = {0, 0, 0, 0};
   PassSync* last_sync = nullptr;  // counters of the last fused pass: its error flag is checked when results are fetched
   bool fused = true;  // one-launch pass (k_pass) when the whole pass is asked for; three PDL-chained kernels otherwise
+  DevBuf d_changed;  // device-side status diff: {count[2] u32 by pass parity, pad to 16 B, idx[M] i32, flag[M] u8}
+  unsigned diff_parity = 0;
+  bool have_diff = false;  // the last pass produced a diff (an observed status was uploaded)
   DevBuf d_pre;    // [M] pre-records, finalize tiles -> decide tiles (kt_kernels.cuh pre_record_bytes)
   // per-throttle outputs of the reconcile half: ONE device block (and one pinned host mirror) so that kt_get_reconcile
   // is a single D2H copy; o_off[i] = byte offset of {used, used_cnt, calc_thr, calc_cnt, used_present, throttled,
@@ -173,6 +176,10 @@ struct kt_ctx {
   unsigned epoch = 0;         // passes exchanged through the window so far
   bool win_stale = false;     // the throttle set changed: the window's buffers are laid out for another M -> rebuilt (collectively) before the next pass
 };
+
+#ifndef KT_PASS_PDL  // 1: k_pass is launched with programmatic stream serialization (its launch overlaps the previous kernel's tail)
+#define KT_PASS_PDL 1
+#endif
 
 namespace {
 
@@ -432,7 +439,7 @@ cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
   size_t smem = reconcile_smem_bytes(L, R, a.S, REG, kTileReconcile);
   const size_t smem_chk = check_smem_bytes(L, R, REG, kTileReconcile);
   if (smem_chk > smem) smem = smem_chk;
-  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin, kTileReconcile, smem, false, a);
+  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }
 cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
@@ -513,7 +520,7 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
-                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_out, &c->d_codes, &c->d_admit};
+                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_changed, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_sparse_count) cudaFreeHost(c->h_sparse_count);
   c->d_sparse.release();
@@ -793,6 +800,9 @@ int kt_upload_throttles(kt_ctx* c, int32_t m, const kt_throttle_cols* cols, cons
   c->part_parity = 0;
   c->win_stale = c->win != nullptr;  // laid out for the previous M
   KT_CUDA(c, c->d_pre.reserve((size_t)m * pre_record_bytes(R) + 16));
+  KT_CUDA(c, c->d_changed.reserve(16 + (size_t)m * 5 + 16));
+  KT_CUDA(c, cudaMemsetAsync(c->d_changed.p, 0, 16, c->stream));
+  c->have_diff = false;
   {
     const size_t sizes[8] = {(size_t)R * m * 8, (size_t)m * 8, (size_t)R * m * 8, (size_t)m * 8, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m};
     size_t at = 0;
@@ -884,7 +894,7 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   tv.ovr_off = c->d_ovr_off.as<int32_t>(); tv.ovr_begin = c->d_ovr_begin.as<int64_t>(); tv.ovr_end = c->d_ovr_end.as<int64_t>();
   tv.ovr_flags = c->d_ovr_flags.as<uint8_t>(); tv.ovr_thr = c->d_ovr_thr.as<int64_t>(); tv.ovr_present = c->d_ovr_present.as<uint32_t>();
   tv.ovr_cnt = c->d_ovr_cnt.as<int64_t>(); tv.n_ovr = c->n_ovr;
-  if (given) {
+  if (c->have_status) {  // GIVEN_STATUS reads it as the check's input; any reconciling pass diffs its outputs against it
     tv.st_calculated = c->d_st_calculated.as<uint8_t>(); tv.st_calc_thr = c->d_st_calc_thr.as<int64_t>();
     tv.st_calc_present = c->d_st_calc_present.as<uint32_t>(); tv.st_calc_cnt = c->d_st_calc_cnt.as<int64_t>();
     tv.st_used = c->d_st_used.as<int64_t>(); tv.st_used_present = c->d_st_used_present.as<uint32_t>();
@@ -895,9 +905,18 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
     tv.reserved_cnt = c->d_reserved_cnt.as<int64_t>();
   }
   unsigned char* ob = c->d_out.as<unsigned char>();
-  const ReconcileView ov{reinterpret_cast<int64_t*>(ob + c->o_off[0]), reinterpret_cast<uint32_t*>(ob + c->o_off[4]), reinterpret_cast<int64_t*>(ob + c->o_off[1]),
-                         reinterpret_cast<uint32_t*>(ob + c->o_off[5]), reinterpret_cast<int64_t*>(ob + c->o_off[2]), reinterpret_cast<uint32_t*>(ob + c->o_off[6]),
-                         reinterpret_cast<int64_t*>(ob + c->o_off[3]), reinterpret_cast<uint8_t*>(ob + c->o_off[7])};
+  ReconcileView ov{reinterpret_cast<int64_t*>(ob + c->o_off[0]), reinterpret_cast<uint32_t*>(ob + c->o_off[4]), reinterpret_cast<int64_t*>(ob + c->o_off[1]),
+                   reinterpret_cast<uint32_t*>(ob + c->o_off[5]), reinterpret_cast<int64_t*>(ob + c->o_off[2]), reinterpret_cast<uint32_t*>(ob + c->o_off[6]),
+                   reinterpret_cast<int64_t*>(ob + c->o_off[3]), reinterpret_cast<uint8_t*>(ob + c->o_off[7]), nullptr, nullptr, nullptr, nullptr};
+  c->have_diff = c->have_status && do_rec && M > 0;
+  if (c->have_diff) {
+    c->diff_parity ^= 1u;
+    uint32_t* cnt = c->d_changed.as<uint32_t>();
+    ov.changed_count = cnt + c->diff_parity;
+    ov.changed_count_next = cnt + (c->diff_parity ^ 1u);
+    ov.changed_idx = reinterpret_cast<int32_t*>(c->d_changed.as<unsigned char>() + 16);
+    ov.changed_flag = c->d_changed.as<unsigned char>() + 16 + (size_t)M * 4;
+  }
   int G = 1;
   while (G < R + 1) G <<= 1;  // finalize lanes per throttle: resources + the pod count, padded to a power of two
   // partial sums: a reconciling pass takes the half its predecessor left zeroed and zeroes the other one for its successor
@@ -1044,6 +1063,93 @@ int kt_get_reconcile(kt_ctx* c, const kt_reconcile_out* o) {
   put(o->throttled, 5, m * 4);
   put(o->calc_present, 6, m * 4);
   put(o->override_active, 7, m);
+  return KT_OK;
+}
+
+int kt_get_changed(kt_ctx* c, int32_t* idx, int64_t cap, int64_t* count, uint8_t* flags) {
+  if (!c || !count || cap < 0 || (cap > 0 && !idx)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_changed before kt_evaluate");
+  if (!c->have_diff) return fail(c, KT_ERR_STATE, "kt_get_changed: the last pass had no observed status to diff against (kt_upload_status) or did not reconcile");
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
+  uint32_t n = 0;
+  KT_CUDA(c, cudaMemcpyAsync(&n, c->d_changed.as<uint32_t>() + c->diff_parity, 4, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  *count = n;
+  const int64_t have = (int64_t)n < cap ? (int64_t)n : cap;
+  if (have > 0) KT_CUDA(c, cudaMemcpyAsync(idx, c->d_changed.as<unsigned char>() + 16, (size_t)have * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (flags && c->M > 0) KT_CUDA(c, cudaMemcpyAsync(flags, c->d_changed.as<unsigned char>() + 16 + (size_t)c->M * 4, (size_t)c->M, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KT_OK;
+}
+
+int kt_get_reconcile_rows(kt_ctx* c, int64_t k, const int32_t* idx, const kt_reconcile_out* o) {
+  if (!c || !o || k < 0 || (k > 0 && !idx)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_reconcile_rows before kt_evaluate");
+  if (k == 0) return KT_OK;
+  const int R = c->lim.n_resources, M = c->M;
+  for (int64_t i = 0; i < k; ++i)
+    if (idx[i] < 0 || idx[i] >= M) return fail(c, KT_ERR_INVALID, "throttle %d out of range [0,%d)", idx[i], M);
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
+  // one packed block per call: {used[R][k], calc_thr[R][k], used_cnt[k], calc_cnt[k], used_present[k], throttled[k], calc_present[k], override_active[k]}
+  const size_t bytes = (size_t)k * ((size_t)2 * R * 8 + 16 + 12 + 1);
+  PodStore& s = c->pods[KT_PODS_RUNNING];  // its grow-only staging buffers serve small gathers
+  KT_CUDA(c, s.t_rows.reserve((size_t)k * 4 + 16));
+  KT_CUDA(c, s.t_words.reserve(bytes + 64));
+  if (c->h_out_cap < bytes + 64) {
+    if (c->h_out) cudaFreeHost(c->h_out);
+    c->h_out = nullptr;
+    c->h_out_cap = 0;
+    KT_CUDA(c, cudaHostAlloc(&c->h_out, bytes + 64, cudaHostAllocDefault));
+    c->h_out_cap = bytes + 64;
+  }
+  KT_CUDA(c, cudaMemcpyAsync(s.t_rows.p, idx, (size_t)k * 4, cudaMemcpyHostToDevice, c->stream));
+  unsigned char* ob = c->d_out.as<unsigned char>();
+  const ReconcileView ov{reinterpret_cast<int64_t*>(ob + c->o_off[0]), reinterpret_cast<uint32_t*>(ob + c->o_off[4]), reinterpret_cast<int64_t*>(ob + c->o_off[1]),
+                         reinterpret_cast<uint32_t*>(ob + c->o_off[5]), reinterpret_cast<int64_t*>(ob + c->o_off[2]), reinterpret_cast<uint32_t*>(ob + c->o_off[6]),
+                         reinterpret_cast<int64_t*>(ob + c->o_off[3]), reinterpret_cast<uint8_t*>(ob + c->o_off[7]), nullptr, nullptr, nullptr, nullptr};
+  k_gather_status<<<(unsigned)((k + 127) / 128), 128, 0, c->stream>>>(k, s.t_rows.as<int32_t>(), R, M, ov, s.t_words.as<unsigned char>());
+  KT_CUDA(c, cudaGetLastError());
+  KT_CUDA(c, cudaMemcpyAsync(c->h_out, s.t_words.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const unsigned char* hb = reinterpret_cast<const unsigned char*>(c->h_out);
+  size_t at = 0;
+  auto take = [&](void* dst, size_t n) {
+    if (dst) std::memcpy(dst, hb + at, n);
+    at += n;
+  };
+  take(o->used, (size_t)R * k * 8); take(o->calc_thr, (size_t)R * k * 8); take(o->used_cnt, (size_t)k * 8); take(o->calc_cnt, (size_t)k * 8);
+  take(o->used_present, (size_t)k * 4); take(o->throttled, (size_t)k * 4); take(o->calc_present, (size_t)k * 4); take(o->override_active, (size_t)k);
+  return KT_OK;
+}
+
+int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t* rows, uint32_t* codes, uint8_t* admit) {
+  if (!c || k < 0 || (k > 0 && !rows)) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check_rows before kt_evaluate");
+  if (k == 0) return KT_OK;
+  PodStore& s = c->pods[KT_PODS_PENDING];
+  for (int64_t i = 0; i < k; ++i)
+    if (rows[i] < 0 || rows[i] >= s.n) return fail(c, KT_ERR_INVALID, "row %lld out of range [0,%lld)", (long long)rows[i], (long long)s.n);
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = check_pass_error(c))) return rc;
+  const int Wc = 2 * c->ht.Wp;
+  KT_CUDA(c, s.t_rows.reserve((size_t)k * 8));
+  KT_CUDA(c, s.t_words.reserve((size_t)k * Wc * 4 + (size_t)k + 64));
+  KT_CUDA(c, cudaMemcpyAsync(s.t_rows.p, rows, (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+  unsigned char* adm = s.t_words.as<unsigned char>() + (size_t)k * Wc * 4;
+  k_gather_rows<<<(unsigned)((k + 7) / 8), 256, 0, c->stream>>>(k, s.t_rows.as<int64_t>(), Wc, c->d_codes.as<uint32_t>(), s.t_words.as<uint32_t>());
+  k_gather_bytes<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(k, s.t_rows.as<int64_t>(), c->d_admit.as<unsigned char>(), adm);
+  KT_CUDA(c, cudaGetLastError());
+  if (codes) KT_CUDA(c, cudaMemcpyAsync(codes, s.t_words.p, (size_t)k * Wc * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (admit) KT_CUDA(c, cudaMemcpyAsync(admit, adm, (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
   return KT_OK;
 }
 

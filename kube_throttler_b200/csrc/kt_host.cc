@@ -339,6 +339,7 @@ struct PodObj {
   std::string scheduler_name, node_name, phase;
   std::map<int, Quantity> request;  // PodRequestResourceList (resource id -> quantity); ResourceAmountOfPod adds Counts{1}
   int64_t row = -1;                 // slot in the running-pod table
+  int64_t pend_row = -1;            // slot in the resident scheduling-queue table (pods that are ours to schedule and not bound yet)
   uint64_t seq = 0;                 // order of first appearance (the informer-cache order the oracle iterates in; Q8)
   bool live = false;
   std::string nn() const { return ns + "/" + name; }
@@ -458,6 +459,37 @@ struct kth_plugin {
   bool broken_valid = false;
 
   ReservationCache cache[2];  // one per controller (controller.go:34-50)
+
+  // ---- the scheduling queue, resident on the device ------------------------------------------------------------------
+  // Every pod the informer delivered that is ours to schedule (schedulerName == target, no nodeName yet, not finished) also
+  // has a row in the device's PENDING table, maintained by the pod events like the running table.  PreFilter for such a pod
+  // is addressed by key (kth_pre_filter_key): nothing is parsed, packed or uploaded for it, and ONE pass over the table
+  // answers for the whole queue.  Rows [0, pend_capacity) are the queue, rows behind them are scratch rows for pods that
+  // are NOT in the informer cache (the manifest arguments of kth_pre_filter / kth_reserve / kth_pre_filter_batch).
+  std::vector<int64_t> pend_pod;   // queue row -> pods[] slot, -1: free
+  std::vector<int64_t> pend_free;
+  std::set<int64_t> pend_dirty;    // queue rows to (re)pack
+  int64_t pend_capacity = 0, scratch_capacity = 0, scratch_used = 0;
+  bool pend_full_upload = true;
+  // Verdicts of the last pass over the queue, kept until something they depend on changes: a PreFilter verdict depends on the
+  // pod's own row, the throttle set / selectors / namespaces (anything that recompiles tables: everything is void), and -- per
+  // throttle -- the informer copy of its status and its reservations.  The last two are tracked per throttle (`dirty`): a
+  // cached verdict stays good as long as none of the pod's affected throttles is dirty, so the scheduler's
+  // PreFilter -> Reserve -> PreFilter(next pod) cycle only pays a device pass when consecutive pods share a throttle.
+  struct QueueCache {
+    bool valid = false;
+    int Wp = 0;
+    std::vector<uint8_t> admit, row_ok;             // [pend_capacity]; row_ok: the row's verdict belongs to the pod now in the row
+    std::vector<uint32_t> bitmap;                   // [pend_capacity][Wp] affectedThrottles rows
+    std::unordered_map<int64_t, std::vector<std::pair<uint32_t, uint32_t>>> codes;  // row -> non-zero {code word index, word}
+    std::vector<uint32_t> dirty;                    // [Wp] throttles whose status / reservations changed since the pass
+    uint64_t passes = 0, hits = 0;
+  } queue;
+  void queue_void() { queue.valid = false; }
+  void throttle_state_changed(size_t t) {  // status or reservations of throttle column t
+    if (queue.valid && (t >> 5) < queue.dirty.size()) queue.dirty[t >> 5] |= 1u << (t & 31);
+  }
+  void reservation_changed(size_t t) { reserved_dirty = true; throttle_state_changed(t); }
   bool apply_committed = false;  // kth_apply: the object was stored; whatever fails afterwards must not roll its resource names back
   std::string apply_warning;     // kth_apply: a committed object whose follow-up pass failed
   int max_labels = 0, max_ns_labels = 0;
@@ -491,7 +523,7 @@ struct kth_plugin {
     if (need < cols[c].scale_exp) {  // a finer value than the column holds: every row of the column is re-packed
       cols[c].scale_exp = need;
       totals_valid = false;  // the running column totals were counted in the coarser unit
-      pods_full_upload = throttles_dirty = status_dirty = reserved_dirty = true;
+      pods_full_upload = pend_full_upload = throttles_dirty = status_dirty = reserved_dirty = true;
     }
     if (q.format == Quantity::BinarySI) cols[c].format = Quantity::BinarySI;
   }
@@ -577,6 +609,32 @@ struct kth_plugin {
     return f;
   }
   bool should_count_in(const PodObj& p) const { return p.scheduler_name == target_scheduler && !p.node_name.empty(); }
+  // in the scheduling queue: ours to schedule, not bound, not finished
+  bool is_queued(const PodObj& p) const {
+    return p.live && p.scheduler_name == target_scheduler && p.node_name.empty() && p.phase != "Succeeded" && p.phase != "Failed";
+  }
+  // after pods[slot] changed: keep the resident queue table in step
+  void queue_update(int64_t slot) {
+    PodObj& p = pods[(size_t)slot];
+    if (is_queued(p)) {
+      if (p.pend_row < 0) {
+        if (!pend_free.empty()) { p.pend_row = pend_free.back(); pend_free.pop_back(); }
+        else { p.pend_row = (int64_t)pend_pod.size(); pend_pod.push_back(-1); }
+        pend_pod[(size_t)p.pend_row] = slot;
+      }
+      pend_dirty.insert(p.pend_row);
+      if ((size_t)p.pend_row < queue.row_ok.size()) queue.row_ok[(size_t)p.pend_row] = 0;
+    } else if (p.pend_row >= 0) {
+      queue_release(p.pend_row);
+      p.pend_row = -1;
+    }
+  }
+  void queue_release(int64_t row) {
+    pend_pod[(size_t)row] = -1;
+    pend_free.push_back(row);
+    pend_dirty.insert(row);
+    if ((size_t)row < queue.row_ok.size()) queue.row_ok[(size_t)row] = 0;
+  }
 
   int32_t ns_id(const std::string& ns_name) {
     const uint32_t id = ns_dict.id(ns_name);
@@ -592,7 +650,9 @@ struct kth_plugin {
   void drop_engine() {
     if (ctx) kt_destroy(ctx);
     ctx = nullptr;
-    pods_full_upload = throttles_dirty = namespaces_dirty = status_dirty = reserved_dirty = true;
+    sparse_cap = 0;
+    queue.valid = false;
+    pods_full_upload = pend_full_upload = throttles_dirty = namespaces_dirty = status_dirty = reserved_dirty = true;
   }
   void check(int rc, const char* what) {
     if (rc != KT_OK) fail(std::string(what) + ": " + (ctx ? kt_last_error(ctx) : "no engine") + " (" + std::to_string(rc) + ")");
@@ -1185,7 +1245,11 @@ struct kth_plugin {
       if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
       o.st_used = nu;
       o.metrics_pending = true;  // both branches of the status comparison record (throttle_controller.go:159,187); see record_metrics
-      if (status_changed) changed.push_back(o.nn());
+      if (status_changed) {
+        changed.push_back(o.nn());
+        throttle_state_changed(t);  // PreFilter reads this status: cached verdicts of the pods it affects are void
+        status_dirty = true;
+      }
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
       // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache -- except, for a
@@ -1199,11 +1263,10 @@ struct kth_plugin {
             if (last_fin == -2) last_fin = last_finished_match(t, o.ns);
             if (rows[i] != last_fin) continue;
           }
-          if (it->second.erase(row_pod[i])) reserved_dirty = true;
+          if (it->second.erase(row_pod[i])) reservation_changed(t);
         }
       }
     }
-    status_dirty = true;
     w.key("reconciled").num(reconciled).key("changed").begin_arr();
     for (auto& c : changed) w.str(c);
     w.end_arr();
@@ -1214,38 +1277,172 @@ struct kth_plugin {
   }
 
   // ---- pending pods: one device pass for a batch ----------------------------------------------------------
+  struct RowView {  // one pending pod's share of a pass: affectedThrottles row, 2-bit check codes, admit bit
+    const uint32_t* bitmap;
+    const uint32_t* codes;
+    uint8_t admit;
+    int Wp;
+  };
   struct PendingResult {
     std::vector<uint32_t> bitmap, codes;
     std::vector<uint8_t> admit;
     int Wp = 0;
+    RowView row(size_t i) const { return RowView{bitmap.data() + i * (size_t)Wp, codes.data() + i * 2 * (size_t)Wp, admit.empty() ? (uint8_t)1 : admit[i], Wp}; }
   };
-  PendingResult check_pending(const std::vector<PodObj>& batch, uint32_t extra_flags) {
+  // The device's PENDING table = the resident queue rows + `k` scratch rows holding `batch` (pods that are not in the informer
+  // cache).  Brings it up to date with row deltas; a full upload only when a capacity grows or the packing changed.
+  void sync_pending(const std::vector<PodObj>& batch) {
+    const int L = lim.label_slots, R = lim.n_resources;
+    const int64_t k = (int64_t)batch.size();
+    int64_t want_q = std::max<int64_t>(64, pend_capacity), want_s = std::max<int64_t>(16, scratch_capacity);
+    while (want_q < (int64_t)pend_pod.size()) want_q *= 2;
+    while (want_s < k) want_s *= 2;
+    if (want_q != pend_capacity || want_s != scratch_capacity) pend_full_upload = true;
+    PodObj tomb;
+    auto queue_pod = [&](int64_t row) -> const PodObj& {
+      const int64_t slot = row < (int64_t)pend_pod.size() ? pend_pod[(size_t)row] : -1;
+      return slot >= 0 ? pods[(size_t)slot] : tomb;
+    };
+    if (pend_full_upload) {
+      const size_t n = (size_t)(want_q + want_s);
+      std::vector<int64_t> lab((size_t)L * n), req((size_t)R * n);
+      std::vector<uint32_t> present(n), flags(n);
+      std::vector<int32_t> nsid(n);
+      for (int64_t i = 0; i < want_q; ++i) pack_pod(queue_pod(i), lab, req, present, flags, nsid, n, (size_t)i);
+      for (int64_t i = 0; i < want_s; ++i) pack_pod(i < k ? batch[(size_t)i] : tomb, lab, req, present, flags, nsid, n, (size_t)(want_q + i));
+      if (namespaces_dirty || throttles_dirty) { sync_all(); sync_status(); sync_reserved(); }  // packing introduced new namespace ids
+      check(kt_upload_pods(ctx, KT_PODS_PENDING, (int64_t)n, lab.data(), req.data(), present.data(), flags.data(), nsid.data()), "kt_upload_pods(pending)");
+      pend_capacity = want_q;
+      scratch_capacity = want_s;
+      pend_full_upload = false;
+      pend_dirty.clear();
+      queue.valid = false;
+    } else {
+      std::vector<int64_t> rows(pend_dirty.begin(), pend_dirty.end());
+      const int64_t n_scratch = std::max(k, scratch_used);  // this batch, and what the last one left behind
+      for (int64_t i = 0; i < n_scratch; ++i) rows.push_back(pend_capacity + i);
+      const size_t n = rows.size();
+      if (n) {
+        std::vector<int64_t> lab((size_t)L * n), req((size_t)R * n);
+        std::vector<uint32_t> present(n), flags(n);
+        std::vector<int32_t> nsid(n);
+        for (size_t i = 0; i < n; ++i) {
+          const int64_t row = rows[i];
+          pack_pod(row < pend_capacity ? queue_pod(row) : (row - pend_capacity < k ? batch[(size_t)(row - pend_capacity)] : tomb), lab, req, present, flags, nsid, n, i);
+        }
+        if (namespaces_dirty || throttles_dirty) { sync_all(); sync_status(); sync_reserved(); }
+        check(kt_update_pod_rows(ctx, KT_PODS_PENDING, (int64_t)n, rows.data(), lab.data(), req.data(), present.data(), flags.data(), nsid.data()),
+              "kt_update_pod_rows(pending)");
+      }
+      pend_dirty.clear();
+    }
+    scratch_used = k;
+  }
+  // One pass over the PENDING table (queue + scratch rows): PreFilter reads the informer copy of .status; reconcile is a
+  // separate event (KT_EVAL_GIVEN_STATUS).  Afterwards the device holds the verdicts of every queue row at this state.
+  void run_pending_pass(const std::vector<PodObj>& batch, uint32_t extra_flags) {
+    const bool tables_change = throttles_dirty || namespaces_dirty;
     sync_all();
     sync_status();
     sync_reserved();
-    const int L = lim.label_slots, R = lim.n_resources;
+    if (tables_change) queue.valid = false;
+    sync_pending(batch);
+    if (throttles.empty()) return;
+    check(kt_evaluate(ctx, 0, KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE | extra_flags), "kt_evaluate");
+  }
+  // Bring the host copy of the queue's verdicts up to date (admit bits, affectedThrottles rows, non-zero check codes).
+  void fetch_queue_results() {
+    const int Wp = kt_match_words(ctx);
+    const size_t n = (size_t)pend_capacity, all = (size_t)(pend_capacity + scratch_capacity);
+    queue.Wp = Wp;
+    queue.codes.clear();
+    queue.dirty.assign((size_t)Wp, 0);
+    queue.admit.assign(all, 1);
+    queue.bitmap.assign(all * (size_t)Wp, 0);
+    if (!throttles.empty()) {
+      std::vector<uint32_t> ent((size_t)sparse_cap * 3);
+      int64_t cnt = 0;
+      check(kt_get_check_sparse(ctx, queue.admit.data(), ent.data(), (int64_t)sparse_cap, &cnt), "kt_get_check_sparse");
+      if (cnt > (int64_t)sparse_cap) {  // more rejected pairs than the list holds: the dense rows
+        std::vector<uint32_t> dense(all * 2 * (size_t)Wp);
+        check(kt_get_check(ctx, dense.data(), nullptr), "kt_get_check");
+        for (size_t row = 0; row < n; ++row)
+          for (size_t j = 0; j < 2 * (size_t)Wp; ++j)
+            if (dense[row * 2 * Wp + j]) queue.codes[(int64_t)row].emplace_back((uint32_t)j, dense[row * 2 * Wp + j]);
+      } else {
+        for (int64_t i = 0; i < cnt; ++i)
+          if (ent[3 * i] < n) queue.codes[(int64_t)ent[3 * i]].emplace_back(ent[3 * i + 1], ent[3 * i + 2]);
+      }
+      check(kt_get_match_bitmap(ctx, KT_PODS_PENDING, queue.bitmap.data()), "kt_get_match_bitmap");
+    }
+    queue.admit.resize(n);
+    queue.bitmap.resize(n * (size_t)Wp);
+    queue.row_ok.assign(n, 1);
+    queue.valid = true;
+    ++queue.passes;
+  }
+  uint32_t sparse_cap = 0;
+  void ensure_sparse() {
+    const uint32_t want = (uint32_t)std::min<int64_t>(4 * (pend_capacity + scratch_capacity) + 1024, (int64_t)1 << 26);
+    if (want > sparse_cap) {
+      check(kt_set_sparse_check(ctx, (int64_t)want), "kt_set_sparse_check");
+      sparse_cap = want;
+    }
+  }
+  // Is the cached verdict of queue row `row` still the truth?
+  bool queue_row_current(int64_t row) const {
+    if (!queue.valid || throttles_dirty || namespaces_dirty || pend_full_upload) return false;
+    if (row < 0 || (size_t)row >= queue.row_ok.size() || !queue.row_ok[(size_t)row] || pend_dirty.count(row)) return false;
+    const uint32_t* bm = &queue.bitmap[(size_t)row * (size_t)queue.Wp];
+    for (int w = 0; w < queue.Wp; ++w)
+      if (bm[w] & queue.dirty[(size_t)w]) return false;
+    return true;
+  }
+  // One pass for the whole resident queue, results cached on the host.
+  void refresh_queue() {
+    run_pending_pass({}, 0);
+    if (!throttles.empty()) {
+      const uint32_t before = sparse_cap;
+      ensure_sparse();
+      if (sparse_cap != before) check(kt_evaluate(ctx, 0, KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE), "kt_evaluate");  // the list exists from this pass on
+    }
+    fetch_queue_results();
+  }
+
+  PendingResult check_pending(const std::vector<PodObj>& batch, uint32_t extra_flags) {
     const size_t k = batch.size();
-    std::vector<int64_t> lab((size_t)L * k), req((size_t)R * k);
-    std::vector<uint32_t> present(k), flags(k);
-    std::vector<int32_t> nsid(k);
-    for (size_t i = 0; i < k; ++i) pack_pod(batch[i], lab, req, present, flags, nsid, k, i);
-    if (namespaces_dirty || throttles_dirty) { sync_all(); sync_status(); sync_reserved(); }  // packing introduced new namespace ids
-    check(kt_upload_pods(ctx, KT_PODS_PENDING, (int64_t)k, lab.data(), req.data(), present.data(), flags.data(), nsid.data()), "kt_upload_pods(pending)");
+    run_pending_pass(batch, extra_flags);
     PendingResult out;
     out.Wp = kt_match_words(ctx);
     out.bitmap.assign(k * (size_t)out.Wp, 0);
     out.codes.assign(k * 2 * (size_t)out.Wp, 0);
     out.admit.assign(k, 1);
     if (throttles.empty() || k == 0) return out;
-    // PreFilter reads the informer copy of .status; reconcile is a separate event (KT_EVAL_GIVEN_STATUS)
-    check(kt_evaluate(ctx, 0, KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE | extra_flags), "kt_evaluate");
-    check(kt_get_check(ctx, out.codes.data(), out.admit.data()), "kt_get_check");
-    check(kt_get_match_bitmap(ctx, KT_PODS_PENDING, out.bitmap.data()), "kt_get_match_bitmap");
+    std::vector<int64_t> rows(k);
+    for (size_t i = 0; i < k; ++i) rows[i] = pend_capacity + (int64_t)i;
+    check(kt_get_check_rows(ctx, (int64_t)k, rows.data(), out.codes.data(), out.admit.data()), "kt_get_check_rows");
+    check(kt_get_match_rows(ctx, KT_PODS_PENDING, (int64_t)k, rows.data(), out.bitmap.data()), "kt_get_match_rows");
     return out;
   }
-  std::vector<int> affected(const PendingResult& r, size_t i, int kind) const {  // the set bits of the pod's match row, in column order
+  // PreFilter of a pod of the resident queue: from the cached verdicts when they are current, else after ONE pass that
+  // refreshes the whole queue's.
+  PendingResult queue_result(int64_t row) {
+    if (!queue_row_current(row)) refresh_queue();
+    else ++queue.hits;
+    PendingResult out;
+    out.Wp = queue.Wp;
+    out.bitmap.assign(&queue.bitmap[(size_t)row * (size_t)queue.Wp], &queue.bitmap[(size_t)row * (size_t)queue.Wp] + queue.Wp);
+    out.codes.assign(2 * (size_t)queue.Wp, 0);
+    out.admit.assign(1, queue.admit[(size_t)row]);
+    auto it = queue.codes.find(row);
+    if (it != queue.codes.end())
+      for (auto& e : it->second) out.codes[e.first] = e.second;
+    return out;
+  }
+  std::vector<int> affected(const PendingResult& r, size_t i, int kind) const { return affected(r.row(i), kind); }
+  std::vector<int> affected(const RowView& r, int kind) const {  // the set bits of the pod's match row, in column order
     std::vector<int> out;
-    const uint32_t* row = &r.bitmap[i * (size_t)r.Wp];
+    const uint32_t* row = r.bitmap;
     for (int w = 0; w < r.Wp; ++w)
       for (uint32_t bits = row[w]; bits; bits &= bits - 1) {
         const size_t t = (size_t)w * 32 + (size_t)__builtin_ctz(bits);
@@ -1255,7 +1452,8 @@ struct kth_plugin {
   }
   // affectedThrottles / affectedClusterThrottles error paths that never reach the device:
   // an invalid podSelector (MatchesToPod returns the error) and a namespace the informer does not know.
-  std::string controller_error(const PodObj& pod, const PendingResult& r, size_t i, int kind) {
+  std::string controller_error(const PodObj& pod, const PendingResult& r, size_t i, int kind) { return controller_error(pod, r.row(i), kind); }
+  std::string controller_error(const PodObj& pod, const RowView& r, int kind) {
     if (kind == KT_KIND_CLUSTERTHROTTLE) {
       const int id = ns_dict.find(pod.ns);
       if (id < 0 || !namespaces[(size_t)id].exists) return "namespace \"" + pod.ns + "\" not found";  // namespaceInformer.Lister().Get (clusterthrottle_controller.go:273-276)
@@ -1272,7 +1470,7 @@ struct kth_plugin {
       if (kind == KT_KIND_THROTTLE && o.ns != pod.ns) continue;
       const std::string e = reachable_selector_error(o, pod.ns);
       if (e.empty()) continue;  // no broken term is in this pod's way (ClusterThrottle terms carry their own namespace scope)
-      if ((r.bitmap[i * (size_t)r.Wp + (t >> 5)] >> (t & 31)) & 1) continue;  // an earlier, valid term already matched
+      if ((r.bitmap[t >> 5] >> (t & 31)) & 1) continue;  // an earlier, valid term already matched
       return e;
     }
     return "";
@@ -1327,15 +1525,16 @@ struct kth_plugin {
     return s;
   }
   // plugin.go:148-215
-  void prefilter_json(Writer& w, const PodObj& pod, const PendingResult& r, size_t i) {
+  void prefilter_json(Writer& w, const PodObj& pod, const PendingResult& r, size_t i) { prefilter_json(w, pod, r.row(i)); }
+  void prefilter_json(Writer& w, const PodObj& pod, const RowView& r) {
     std::vector<int> bucket[2][4], aff[2];
     std::string err;
     for (int kind = 0; kind < 2 && err.empty(); ++kind) {  // throttleCtr first, then clusterThrottleCtr (plugin.go:153,165)
-      err = controller_error(pod, r, i, kind);
+      err = controller_error(pod, r, kind);
       if (!err.empty()) break;
-      aff[kind] = affected(r, i, kind);
+      aff[kind] = affected(r, kind);
       for (int t : aff[kind]) {
-        const uint32_t code = (r.codes[i * 2 * (size_t)r.Wp + ((size_t)t >> 4)] >> (2 * (t & 15))) & 3u;
+        const uint32_t code = (r.codes[(size_t)t >> 4] >> (2 * (t & 15))) & 3u;
         bucket[kind][code].push_back(t);
       }
     }
@@ -1390,18 +1589,21 @@ struct kth_plugin {
   std::string reserve_json(const Node& pod_node, bool reserve) {
     PodObj pod = pod_from(pod_node);
     PendingResult r = check_pending({pod}, 0);
+    return reserve_result(pod, r.row(0), reserve);
+  }
+  std::string reserve_result(const PodObj& pod, const RowView& r, bool reserve) {
     std::vector<std::string> errs;
     const char* ctl[2] = {"ThrottleController", "ClusterThrottleController"};
     for (int kind = 0; kind < 2; ++kind) {
-      const std::string e = controller_error(pod, r, 0, kind);
+      const std::string e = controller_error(pod, r, kind);
       if (!e.empty()) {
         errs.push_back(std::string(reserve ? "Failed to reserve pod=" : "Failed to unreserve pod ") + pod.nn() + " in " + ctl[kind] + ": " + e);
         continue;
       }
-      for (int t : affected(r, 0, kind)) {
+      for (int t : affected(r, kind)) {
         if (reserve) cache[kind].add(throttles[(size_t)t].nn(), pod);
         else cache[kind].remove(throttles[(size_t)t].nn(), pod.nn());
-        reserved_dirty = true;
+        reservation_changed((size_t)t);
       }
     }
     Writer w;
@@ -1415,6 +1617,57 @@ struct kth_plugin {
     }
     w.end_obj();
     return w.out;
+  }
+
+  // ---- the same calls for pods of the resident queue, addressed by key ----------------------------------------
+  const PodObj& informer_pod(const std::string& ns, const std::string& pname) const {
+    auto it = pod_index.find(ns + "/" + pname);
+    if (it == pod_index.end()) fail("pod " + ns + "/" + pname + " is not in the informer cache");
+    return pods[(size_t)it->second];
+  }
+  std::string pre_filter_key(const std::string& ns, const std::string& pname) {
+    const PodObj pod = informer_pod(ns, pname);  // (value copy: a pass may re-create the engine and re-pack)
+    Writer w;
+    if (pod.pend_row < 0) {  // known to the informer but not waiting to be scheduled: checked like a manifest
+      PendingResult r = check_pending({pod}, 0);
+      prefilter_json(w, pod, r.row(0));
+    } else {
+      PendingResult r = queue_result(pod.pend_row);
+      prefilter_json(w, pod, r.row(0));
+    }
+    return w.out;
+  }
+  std::string reserve_key(const std::string& ns, const std::string& pname, bool reserve) {
+    const PodObj pod = informer_pod(ns, pname);
+    // which throttles the pod affects does not depend on statuses or reservations: the cached row serves as long as the pod's
+    // own row and the tables are what they were
+    PendingResult r = pod.pend_row >= 0 ? queue_result(pod.pend_row) : check_pending({pod}, 0);
+    return reserve_result(pod, r.row(0), reserve);
+  }
+  // PreFilter of the WHOLE resident queue: one verdict byte per queue row (0 free row, 1 Success, 2 UnschedulableAndUnresolvable,
+  // 3 Error); at most one device pass, none when every cached verdict is current.
+  int64_t pre_filter_queue(uint8_t* verdicts, int64_t cap) {
+    const int64_t n = (int64_t)pend_pod.size();
+    bool current = queue.valid;
+    for (int64_t row = 0; row < n && current; ++row)
+      if (pend_pod[(size_t)row] >= 0 && !queue_row_current(row)) current = false;
+    if (!current) refresh_queue();
+    else ++queue.hits;
+    if (!broken_valid) { PendingResult none; none.Wp = queue.Wp; none.bitmap.assign((size_t)queue.Wp, 0); none.codes.assign(2 * (size_t)queue.Wp, 0); controller_error(PodObj(), none.row(0), KT_KIND_THROTTLE); }
+    const std::vector<uint32_t> no_codes(2 * (size_t)queue.Wp, 0);
+    for (int64_t row = 0; row < n && row < cap; ++row) {
+      const int64_t slot = pend_pod[(size_t)row];
+      if (slot < 0) { verdicts[row] = 0; continue; }
+      uint8_t v = queue.admit[(size_t)row] ? 1 : 2;
+      const PodObj& pod = pods[(size_t)slot];
+      const int nsid = ns_dict.find(pod.ns);
+      if (!broken.empty() || nsid < 0 || !namespaces[(size_t)nsid].exists) {  // the error paths that never reach the device
+        const RowView rv{&queue.bitmap[(size_t)row * (size_t)queue.Wp], no_codes.data(), queue.admit[(size_t)row], queue.Wp};
+        if (!controller_error(pod, rv, KT_KIND_THROTTLE).empty() || !controller_error(pod, rv, KT_KIND_CLUSTERTHROTTLE).empty()) v = 3;
+      }
+      verdicts[row] = v;
+    }
+    return n;
   }
 
   // ---- queue-ordered admission ----------------------------------------------------------------------------
@@ -1465,8 +1718,7 @@ struct kth_plugin {
         if (reserve_error) continue;
         ++admitted;
         for (int kind = 0; kind < 2; ++kind)
-          for (int t : affected(r, k, kind)) cache[kind].add(throttles[(size_t)t].nn(), batch[k]);
-        reserved_dirty = true;
+          for (int t : affected(r, k, kind)) { cache[kind].add(throttles[(size_t)t].nn(), batch[k]); reservation_changed((size_t)t); }
         for (size_t w2 = 0; w2 < W; ++w2) dirty[w2] |= row[w2];
       }
       undecided.swap(next);
@@ -1494,6 +1746,7 @@ struct kth_plugin {
       totals_add(p, +1);
       pods[(size_t)row] = std::move(p);
       dirty_rows.insert(row);
+      queue_update(row);
       return;
     }
     // The informer's copy is replaced FIRST: the pass below only asks which throttles the old and the new pod match, which
@@ -1503,10 +1756,12 @@ struct kth_plugin {
     const PodObj old = pods[(size_t)row];
     p.row = row;
     p.seq = old.seq;
+    p.pend_row = old.pend_row;
     totals_add(old, -1);
     totals_add(p, +1);
     pods[(size_t)row] = std::move(p);
     dirty_rows.insert(row);
+    queue_update(row);
     const PodObj& cur = pods[(size_t)row];
     // UpdateFunc (throttle_controller.go:459-507): the throttle assignment can only change with labels / namespace;
     // then the pod's reservation moves from (old \ new) to (new \ old) throttles
@@ -1529,9 +1784,9 @@ struct kth_plugin {
         if (!controller_error(old, r, 0, kind).empty() || !controller_error(now, r, 1, kind).empty()) continue;  // HandleError + return
         const std::vector<int> a = affected(r, 0, kind), b = affected(r, 1, kind);
         for (int t : a)
-          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), now.nn()); reserved_dirty = true; }
+          if (std::find(b.begin(), b.end(), t) == b.end()) { cache[kind].remove(throttles[(size_t)t].nn(), now.nn()); reservation_changed((size_t)t); }
         for (int t : b)
-          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), now); reserved_dirty = true; }
+          if (std::find(a.begin(), a.end(), t) == a.end()) { cache[kind].add(throttles[(size_t)t].nn(), now); reservation_changed((size_t)t); }
       }
     }
   }
@@ -1542,6 +1797,7 @@ struct kth_plugin {
     const PodObj old = pods[(size_t)row];
     // the row goes first (see apply_pod): a delete that repairs a refused snapshot must not be refused for it
     totals_add(old, -1);
+    if (old.pend_row >= 0) queue_release(old.pend_row);
     pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
     pods[(size_t)row].row = row;
     pod_index.erase(it);
@@ -1556,13 +1812,13 @@ struct kth_plugin {
         // the pod is gone whatever happens to the pass: its reservations must not outlive it (reconcile only un-reserves pods
         // that are still in the index) -- without the device's answer it leaves every throttle's reservation, a superset
         for (int kind = 0; kind < 2; ++kind)
-          if (cache[kind].remove_everywhere(old.nn())) reserved_dirty = true;
+          if (cache[kind].remove_everywhere(old.nn())) { reserved_dirty = true; queue_void(); }
         throw;
       }
       for (int kind = 0; kind < 2; ++kind) {
         if (!controller_error(old, r, 0, kind).empty()) continue;
         for (int t : affected(r, 0, kind))
-          if (cache[kind].remove(throttles[(size_t)t].nn(), old.nn())) reserved_dirty = true;
+          if (cache[kind].remove(throttles[(size_t)t].nn(), old.nn())) reservation_changed((size_t)t);
       }
     }
   }
@@ -1945,6 +2201,40 @@ const char* kth_pre_filter(kth_plugin* p, const char* pod_json) {
     kth_plugin::PendingResult r = p->check_pending(batch, 0);  // PreFilter passes isThrottledOnEqual = false
     Writer w;
     p->prefilter_json(w, batch[0], r, 0);
+    return w.out;
+  });
+}
+const char* kth_pre_filter_key(kth_plugin* p, const char* ns, const char* name) {
+  return guarded(p, [&]() { return p->pre_filter_key(ns ? ns : "", name ? name : ""); });
+}
+const char* kth_reserve_key(kth_plugin* p, const char* ns, const char* name) {
+  return guarded(p, [&]() { return p->reserve_key(ns ? ns : "", name ? name : "", true); });
+}
+const char* kth_unreserve_key(kth_plugin* p, const char* ns, const char* name) {
+  return guarded(p, [&]() { return p->reserve_key(ns ? ns : "", name ? name : "", false); });
+}
+int64_t kth_queue_row(kth_plugin* p, const char* ns, const char* name) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->pod_index.find(std::string(ns ? ns : "") + "/" + (name ? name : ""));
+  return it == p->pod_index.end() ? -1 : p->pods[(size_t)it->second].pend_row;
+}
+int64_t kth_pre_filter_queue(kth_plugin* p, uint8_t* verdicts, int64_t cap) {
+  if (!p || cap < 0 || (cap > 0 && !verdicts)) return -1;
+  std::lock_guard<std::mutex> lk(p->mu);
+  try {
+    return p->pre_filter_queue(verdicts, cap);
+  } catch (const std::exception& e) {
+    ret(err_json(e.what()));  // kth_last_error
+    return -1;
+  }
+}
+const char* kth_last_error(void) { return g_ret.c_str(); }
+const char* kth_queue_stats(kth_plugin* p) {
+  return guarded(p, [&]() -> std::string {
+    Writer w;
+    w.begin_obj().key("queued").num((long long)(p->pend_pod.size() - p->pend_free.size())).key("rows").num((long long)p->pend_pod.size());
+    w.key("passes").num((long long)p->queue.passes).key("hits").num((long long)p->queue.hits).end_obj();
     return w.out;
   });
 }

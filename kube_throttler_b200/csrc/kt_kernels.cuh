@@ -37,9 +37,6 @@ namespace kt {
 #ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
 #define KT_PASS_THREADS 896
 #endif
-#ifndef KT_DECIDE_WORDS    // match words per warp whose check constants a decide tile stages at once: its shared memory (10 KB per word at
-#define KT_DECIDE_WORDS 3  // R=4) is what every CTA of the fused pass is launched with, i.e. it bounds the reconcile tiles' residency too
-#endif
 #ifndef KT_SLOT_CAP        // upper bound on the per-CTA accumulator slots (shared memory vs straight-to-HBM atomics)
 #define KT_SLOT_CAP 32
 #endif
@@ -50,7 +47,6 @@ constexpr int kTileReconcile = KT_TILE_RECONCILE;  // running pods per CTA (one 
 constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = KT_SLOT_CAP;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kDecidePrefetch = 3;   // match words per warp whose check constants the decide tile stages in one go
 #ifndef KT_STAGE_CHUNK
 #define KT_STAGE_CHUNK 2
 #endif
@@ -164,6 +160,13 @@ struct ReconcileView {  // device-resident kt_reconcile_out
   uint32_t* calc_present;
   int64_t* calc_cnt;
   uint8_t* override_active;
+  // device-side status diff (throttle_controller.go:157-173 only writes a status that differs from the informer
+  // copy): with an observed status uploaded, every responsible throttle whose used / throttled / calculated threshold of THIS
+  // pass differs from it is appended to a list (unordered) and flagged; null: no diff
+  uint32_t* changed_count;       // this pass's counter
+  uint32_t* changed_count_next;  // the other parity's: left zeroed for the next pass
+  int32_t* changed_idx;          // [M]
+  uint8_t* changed_flag;         // [M]
 };
 
 // ---- programmatic dependent launch (PTX griddepcontrol; both are no-ops in a plain launch) -------
@@ -299,7 +302,7 @@ struct PdlSync {
   __device__ __forceinline__ void wait_reconciled() const { pdl_wait_primary(); }
   __device__ __forceinline__ void wait_totals(const PartExchange&) const { pdl_wait_primary(); }  // k_finalize is complete: so is everything before it
   __device__ __forceinline__ void wait_matched() const {}   // same CTA: a barrier already ordered the rows
-  __device__ __forceinline__ void wait_prepped() const {}   // covered by wait_totals (k_check's primary is k_finalize)
+  __device__ __forceinline__ void wait_prepped() const { pdl_wait_primary(); }  // k_check's primary is k_finalize: complete, and everything before it
   __device__ __forceinline__ void signal_prepped() const {}
   __device__ __forceinline__ void exchange_done(const PartExchange&) const {}
 };
@@ -989,6 +992,28 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     if (out.calc_present) out.calc_present[t] = m_calc;
     if (out.override_active) out.override_active[t] = active_found;
   }
+  if (out.changed_count) {  // uniform across the grid
+    // what reconcile would write differs from the informer copy?  (Messages / calculatedAt are the host's business.)
+    bool diff = false;
+    if (live && (is_res || is_cnt)) {
+      const bool o_used_has = tv.st_used_present[t] & mybit, o_thr = tv.st_throttled[t] & mybit;
+      const long long o_used = is_res ? tv.st_used[col] : tv.st_used_cnt[t];
+      diff = used_has != o_used_has || (used_has && used_val != o_used) || throttled != o_thr;
+      if (!tv.st_calculated[t]) {
+        diff = true;  // calculatedThreshold was never written: this reconcile stamps it
+      } else {
+        const bool o_calc_has = tv.st_calc_present[t] & mybit;
+        const long long o_calc = is_res ? tv.st_calc_thr[col] : tv.st_calc_cnt[t];
+        diff = diff || calc_has != o_calc_has || (calc_has && calc_val != o_calc);
+      }
+    }
+    const uint32_t m_diff = group_mask(diff);
+    if (is_cnt) {
+      out.changed_flag[t] = m_diff != 0u;
+      if (m_diff) out.changed_idx[atomicAdd(out.changed_count, 1u)] = t;
+    }
+    if (tile_index == 0 && threadIdx.x == 0) *out.changed_count_next = 0u;
+  }
   stamp(7);
 }
 
@@ -1004,15 +1029,16 @@ __global__ void __launch_bounds__(128) k_finalize(ThrottleView tv, int M, int R,
 // constants of a word's 32 throttles are staged in shared memory by the warp (lane = throttle) so the
 // per-pair work is shared-memory compares instead of dependent global gathers.
 // ------------------------------------------------------------------------------------------------
-// KS = match words per warp whose constants are staged together (1..kDecidePrefetch, bounded by shared memory)
+// Decide tiles stage the check constants of the words their pods touch ONCE PER CTA: every warp proposes up to KS words per
+// round, the CTA's distinct words get one staging slot each (32 throttle records), the slots are spread over the warps.
+__host__ __device__ inline size_t decide_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }  // == pre_record_bytes: staged raw, finished in place
 __host__ __device__ inline int decide_stage_words(int R, int tile) {
-  const size_t per_word = (size_t)(tile / 32) * 32 * (16 + 16 * (size_t)R);
-  int ks = (int)((40u << 10) / per_word);
-  return ks < 1 ? 1 : (ks > KT_DECIDE_WORDS ? KT_DECIDE_WORDS : ks);
+  return (size_t)(tile / 32) * 2 * 32 * decide_record_bytes(R) <= (48u << 10) ? 2 : 1;
 }
 __host__ __device__ inline size_t check_smem_bytes(int L, int R, bool reg_rows, int tile) {
   const size_t match = reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4;                                                        // check_match_tile
-  const size_t decide = (size_t)R * tile * 8 + (size_t)decide_stage_words(R, tile) * (tile / 32) * 32 * (16 + 16 * (size_t)R);  // check_decide_tile
+  const int slots = (tile / 32) * decide_stage_words(R, tile);
+  const size_t decide = (size_t)R * tile * 8 + (size_t)slots * 32 * decide_record_bytes(R) + (size_t)slots * 8 + 16;             // check_decide_tile
   return match > decide ? match : decide;
 }
 
@@ -1076,17 +1102,19 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   }
 }
 
-// Phase 2, after finalize: the 4-step CheckThrottledFor per (pending pod, affected throttle), 2-bit codes and the admit
-// bit.  Everything that does not depend on the reconcile is loaded before the wait.  The constants of a word's 32
-// throttles are staged in shared memory by the warp (lane = throttle), so the per-pair work is shared-memory compares
-// instead of dependent global gathers.
+// Phase 2: the 4-step CheckThrottledFor per (pending pod, affected throttle), 2-bit codes and the admit bit.
+// Everything that does not depend on the reconcile is done before the wait: the pod's requests and match words, which
+// words the CTA needs, and the PRE-RECORDS of those words' throttles (thresholds, observed status, reservations) copied
+// into the CTA's staging slots.  After the wait one lane per (slot, throttle) fetches that throttle's sums -- one trip to
+// L2 for the whole CTA -- and finishes the record in place (what a finalize stage between reconcile and decide used to
+// hand over); then every lane decides its own pairs from shared memory.
 template <int TILE, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
                                                   const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                   unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
                                                   const SparseOut sp = SparseOut{nullptr, nullptr, 0}, unsigned long long* trace_row = nullptr) {
-  // optional stage stamps (kt_enable_trace): [4] match rows visible, [5] own words fetched, [6] sums of every rank visible,
-  // [7] decided
+  // optional stage stamps (kt_enable_trace): [4] match rows visible, [5] words claimed + pre-records staged, [6] sums of every
+  // rank visible, [7] constants finished, [8] decided
   auto stamp = [&](int k) {
     if (trace_row && threadIdx.x == 0) {
       unsigned long long t;
@@ -1094,17 +1122,22 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       trace_row[k] = t;
     }
   };
-  const size_t rec = 16 + 16 * (size_t)R;  // bytes per throttle record: CheckHdr, thrv[R], head[R]
+  constexpr int WARPS = TILE / 32;
+  const size_t rec = decide_record_bytes(R);  // per throttle: CheckHdr (PreHdr while raw), thrv[R], head[R] (base[R] while raw), thr_cnt, base_cnt
+  const int SLOTS = WARPS * KS;
   long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][TILE]
-  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [warps][KS][32][rec]
-  const int tid = threadIdx.x, lane = tid & 31;
-  unsigned char* my_chk = s_chk + (size_t)(tid >> 5) * KS * 32 * rec;
+  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [SLOTS][32][rec]
+  int* s_key = reinterpret_cast<int*>(s_chk + (size_t)SLOTS * 32 * rec);              // [SLOTS] word index or -1
+  uint32_t* s_any = reinterpret_cast<uint32_t*>(s_key + SLOTS);                       // [SLOTS] throttles of the word some lane of the CTA matched
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Wp = tb.Wp;
+  const int M = tb.M;
   const int64_t p = tile_index * TILE + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;
   const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
   const uint32_t present = __ldg(&pods.present[pc]);
+  const uint32_t winfo = __ldg(&pods.winfo[pc]);
   // ResourceAmountOfPod(pod): the non-zero requests are the only ones IsThrottledFor looks at (Q5)
   uint32_t nz = 0;
   {
@@ -1117,50 +1150,19 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (v != 0) nz |= 1u << r;
     }
   }
-  const uint32_t winfo = __ldg(&pods.winfo[pc]);
+  if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
   WordCursor wc;
   wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
-  // Everything that can be known before the sums exist is worked out now: the pod's match words, and the warp's first KS
-  // words in the warp-uniform order with the set of throttles any lane needs of each.  After the wait only the sums are
-  // missing, and the constants of all KS words are built with ONE round trip to L2.
+  __syncthreads();  // the slot table is initialised
   sync.wait_matched();
+  sync.wait_prepped();  // the pre-records are written (early: they depend on nothing)
   stamp(4);
-  int k = 0;
-  int cur = wc.at(tb, 0);
-  int pw[kDecidePrefetch];         // warp-uniform word index
-  uint32_t pany[kDecidePrefetch];  // throttles of that word some lane matched
-  uint32_t pword[kDecidePrefetch]; // this lane's match word
-  // the next (up to) KS words of the warp, their match words fetched together
-  auto gather_words = [&]() {
-#pragma unroll
-    for (int q = 0; q < kDecidePrefetch; ++q) {
-      pw[q] = 0x7fffffff;
-      pany[q] = 0;
-      pword[q] = 0;
-      if (q < KS) {
-        pw[q] = __reduce_min_sync(kFull, cur);
-        if (pw[q] != 0x7fffffff) {
-          if (cur == pw[q]) {
-            pword[q] = __ldcg(&bitmap[p * Wp + pw[q]]);
-            ++k;
-            cur = wc.at(tb, k);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < kDecidePrefetch; ++q)
-      if (q < KS && pw[q] != 0x7fffffff) pany[q] = __reduce_or_sync(kFull, pword[q]);
-  };
-  gather_words();
-  stamp(5);
-
-  sync.wait_prepped();     // the pre-records are written (early: they depend on nothing)
-  sync.wait_totals(px);    // the sums of every running pod (of every rank) are in px.total
-  stamp(6);
 
   unsigned char ok = 1;
-  // one lane's verdicts on the throttles of one word, from the staged records
+  int k = 0;
+  int cur = wc.at(tb, 0);
+  bool sums_awaited = false;
+  // one lane's verdicts on the throttles of one word, from the finished records of its slot
   auto decide_word = [&](uint32_t word, int w, const unsigned char* recs) {
     uint32_t c0 = 0, c1 = 0;
     while (word) {
@@ -1205,56 +1207,53 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
     }
   };
-  // lane = throttle: the constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55) for
-  // throttle w*32+lane, from its pre-record and this pass's sums -- what a finalize stage between reconcile and decide used
-  // to hand over.  alreadyUsed = status.used + reserved (absent values are 0, presence is the union); in GIVEN_STATUS mode
+  // lane = throttle of slot `slot`: the raw pre-record into the slot (nothing here depends on the running pods)
+  auto stage_pre = [&](int slot) {
+    const int w = s_key[slot];
+    if (w < 0 || !((s_any[slot] >> lane) & 1)) return;
+    const uint4* src = reinterpret_cast<const uint4*>(pre + (size_t)(w * 32 + lane) * rec);  // written earlier in this launch by another SM:
+    uint4* dst = reinterpret_cast<uint4*>(s_chk + ((size_t)slot * 32 + lane) * rec);         // __ldcg, L2 is the point of coherence
+    for (int q = 0; q < R + 2; ++q) dst[q] = __ldcg(&src[q]);
+  };
+  // ... and, once the sums exist, the constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55)
+  // in place.  alreadyUsed = status.used + reserved (absent values are 0, presence is the union); in GIVEN_STATUS mode
   // status.used and status.throttled are the observed ones and the sums are not looked at.
-  const int M = tb.M;
-  auto stage = [&](uint32_t any, int w, unsigned char* recs) {
-    if (!((any >> lane) & 1)) return;
+  auto stage_post = [&](int slot) {
+    const int w = s_key[slot];
+    if (w < 0 || !((s_any[slot] >> lane) & 1)) return;
     const int t = w * 32 + lane;
-    const unsigned char* src = pre + (size_t)t * pre_record_bytes(R);
-    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
-    // every load below depends on t alone: header, count values and the first chunk of resources go out together
-    const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));  // written earlier in this launch by another SM: L2 is the point of coherence
-    const long long c_thr = __ldcg(&pv[2 * R]);
-    long long c_au = __ldcg(&pv[2 * R + 1]);
-    const long long c_used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);  // zero / stale in GIVEN_STATUS mode: ignored below
-    PreHdr ph;
-    ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
+    unsigned char* dst = s_chk + ((size_t)slot * 32 + lane) * rec;
+    long long* vals = reinterpret_cast<long long*>(dst + 16);  // thrv[R], base[R] -> head[R], thr_cnt, base_cnt
+    const PreHdr ph = *reinterpret_cast<const PreHdr*>(dst);
     const bool live = ph.flags & kPreLive, e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
-    unsigned char* dst = recs + (size_t)lane * rec;
-    long long* thrv = reinterpret_cast<long long*>(dst + 16);
+    const long long c_used = given ? 0 : (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
     CheckHdr h;
     h.thr_has = h.m2 = h.m3 = 0;
 #pragma unroll 1
     for (int r0 = 0; r0 < R; r0 += kStageChunk) {
-      long long thr[kStageChunk], au[kStageChunk];
       unsigned long long used[kStageChunk], uhas[kStageChunk];
 #pragma unroll
       for (int q = 0; q < kStageChunk; ++q) {
-        const int r = r0 + q < R ? r0 + q : R - 1;  // clamped: the loads stay unconditional (and in flight together)
-        thr[q] = __ldcg(&pv[r]);
-        au[q] = __ldcg(&pv[R + r]);
-        used[q] = __ldcg(&px.total[(size_t)r * M + t]);
-        uhas[q] = __ldcg(&px.total[(size_t)(R + r) * M + t]);
+        const int r = r0 + q < R ? r0 + q : R - 1;  // clamped: the loads stay unconditional and in flight together
+        used[q] = given ? 0ull : __ldcg(&px.total[(size_t)r * M + t]);
+        uhas[q] = given ? 0ull : __ldcg(&px.total[(size_t)(R + r) * M + t]);
       }
 #pragma unroll
       for (int q = 0; q < kStageChunk; ++q) {
         const int r = r0 + q;
         if (r < R) {
+          const long long thr = vals[r];
+          long long au = vals[R + r];
           const bool has = (ph.thr_has >> r) & 1;
           bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
-          long long a = au[q];
           if (!given) {
             const bool used_has = uhas[q] != 0ull;
-            a += (long long)used[q];
+            au += (long long)used[q];
             au_has = au_has || used_has;
-            m2 = has && used_has && (long long)used[q] >= thr[q];  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
+            m2 = has && used_has && (long long)used[q] >= thr;  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
           }
-          const bool s3 = has && au_has && (e3 ? a >= thr[q] : a > thr[q]);
-          thrv[r] = thr[q];
-          thrv[R + r] = thr[q] - a;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+          const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+          vals[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
           h.thr_has |= (has ? 1u : 0u) << r;
           h.m2 |= (m2 ? 1u : 0u) << r;
           h.m3 |= (s3 ? 1u : 0u) << r;
@@ -1262,37 +1261,88 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       }
     }
     {  // the pod count: the pending pod itself counts 1
+      const long long thr = vals[2 * R];
+      long long au = vals[2 * R + 1];
       const bool has = ph.thr_has & KT_COUNT_BIT;
       bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
       if (!given) {
         const bool used_has = c_used > 0;  // Counts stays nil with zero counted pods (Q3)
-        c_au += c_used;
+        au += c_used;
         au_has = au_has || used_has;
-        m2 = has && used_has && c_used >= c_thr;
+        m2 = has && used_has && c_used >= thr;
       }
-      const bool s1 = has && 1 > c_thr;                                               // S1: pod count 1 > threshold (Q4)
-      const bool s3 = has && au_has && (e3 ? c_au >= c_thr : c_au > c_thr);
-      const bool s4 = has && (on_equal ? c_au + 1 >= c_thr : c_au + 1 > c_thr);       // S4 (counts always present: the pod)
+      const bool s1 = has && 1 > thr;                                           // S1: pod count 1 > threshold (Q4)
+      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+      const bool s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);         // S4 (counts always present: the pod)
       h.cntbits = (on_equal ? 16u : 0u) | (s1 ? 1u : 0u) | (m2 ? 2u : 0u) | (s3 ? 4u : 0u) | (s4 ? 8u : 0u);
     }
     if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
     *reinterpret_cast<CheckHdr*>(dst) = h;
   };
-  // KS words at a time: constants staged (lane = throttle), then every lane decides its own pairs
+
 #pragma unroll 1
   while (true) {
+    // 1. every warp's next (up to) KS words in its warp-uniform order, the lanes' match words fetched together; each word
+    // claims a staging slot of the CTA (open addressing; WARPS * KS slots always suffice for one round)
+    int pw[2], pslot[2];
+    uint32_t pword[2];
 #pragma unroll
-    for (int q = 0; q < kDecidePrefetch; ++q)
-      if (q < KS && pany[q]) stage(pany[q], pw[q], my_chk + (size_t)q * 32 * rec);
-    __syncwarp();
+    for (int q = 0; q < 2; ++q) {
+      pw[q] = 0x7fffffff;
+      pslot[q] = -1;
+      pword[q] = 0;
+      if (q < KS) {
+        pw[q] = __reduce_min_sync(kFull, cur);
+        if (pw[q] != 0x7fffffff && cur == pw[q]) {
+          pword[q] = __ldcg(&bitmap[p * Wp + pw[q]]);
+          ++k;
+          cur = wc.at(tb, k);
+        }
+      }
+    }
 #pragma unroll
-    for (int q = 0; q < kDecidePrefetch; ++q)
-      if (q < KS && pword[q]) decide_word(pword[q], pw[q], my_chk + (size_t)q * 32 * rec);
-    if (__reduce_min_sync(kFull, cur) == 0x7fffffff) break;  // pods with more words than fit one round (ClusterThrottle-heavy namespaces)
-    __syncwarp();
-    gather_words();
+    for (int q = 0; q < 2; ++q) {
+      if (q < KS && pw[q] != 0x7fffffff) {
+        const uint32_t any = __reduce_or_sync(kFull, pword[q]);
+        if (any) {
+          int slot = -1;
+          if (lane == 0) {
+            int sidx = (int)((unsigned)pw[q] % (unsigned)SLOTS);
+#pragma unroll 1
+            for (int probes = 0; probes < SLOTS; ++probes) {
+              int key = *reinterpret_cast<volatile int*>(&s_key[sidx]);
+              if (key == -1) key = atomicCAS(&s_key[sidx], -1, pw[q]);
+              if (key == -1 || key == pw[q]) { slot = sidx; break; }
+              sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
+            }
+            atomicOr(&s_any[slot], any);
+          }
+          pslot[q] = __shfl_sync(kFull, slot, 0);
+        }
+      }
+    }
+    __syncthreads();
+    // 2. the slots are spread over the warps: pre-records now, the sums after the (first) wait
+    for (int slot = warp; slot < SLOTS; slot += WARPS) stage_pre(slot);
+    stamp(5);
+    if (!sums_awaited) {
+      sync.wait_totals(px);  // the sums of every running pod (of every rank) are in px.total
+      sums_awaited = true;
+      stamp(6);
+    }
+    for (int slot = warp; slot < SLOTS; slot += WARPS) stage_post(slot);
+    __syncthreads();
+    stamp(7);
+    // 3. every lane decides its own pairs
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (q < KS && pword[q] && pslot[q] >= 0) decide_word(pword[q], pw[q], s_chk + (size_t)pslot[q] * 32 * rec);
+    const int more = __syncthreads_or(cur != 0x7fffffff);  // pods with more words than fit one round (ClusterThrottle-heavy namespaces)
+    if (!more) break;
+    if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
+    __syncthreads();
   }
-  stamp(7);
+  stamp(8);
   if (valid) admit[p] = ok;
 }
 
@@ -1346,6 +1396,13 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
   unsigned long long t_start = 0;
+  // Launched with programmatic stream serialization: the NEXT launch in the stream (normally the next pass) may have its CTAs
+  // placed while this one still runs -- they sit in the wait below until this grid has completed and flushed, so nothing of
+  // theirs (tickets, counters, sums) can mix with ours; what overlaps is their launch latency.  Every CTA releases the
+  // dependents at once: a grid whose CTAs are not all resident yet cannot be overtaken (the dependents only start when ALL
+  // our CTAs have started), so the tiles we still owe always find an SM.
+  pdl_launch_dependents();
+  pdl_wait_primary();
   if (threadIdx.x == 0) {
     s_ticket = atomicAdd(&a.sync->ticket, 1u);
     if (a.trace) t_start = globaltimer_ns();
@@ -1500,6 +1557,38 @@ __global__ void __launch_bounds__(256) k_unpack_rows(int64_t n, int L, int Lpad,
   const uint32_t m = __ldg(&meta[p]);
   ns[p] = (int32_t)(m & 0x1fffffffu);
   flags[p] = m >> 29;
+}
+
+// Status columns of k listed throttles -> one packed block {used[R][k], calc_thr[R][k], used_cnt[k], calc_cnt[k],
+// used_present[k], throttled[k], calc_present[k], override_active[k]} (kt_get_reconcile_rows: the download is proportional
+// to what changed, not to M).
+__global__ void __launch_bounds__(128) k_gather_status(int64_t k, const int32_t* __restrict__ idx, int R, int M, const ReconcileView src,
+                                                       unsigned char* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const int t = idx[i];
+  long long* used = reinterpret_cast<long long*>(out);
+  long long* calc = used + (size_t)R * k;
+  long long* used_cnt = calc + (size_t)R * k;
+  long long* calc_cnt = used_cnt + k;
+  uint32_t* used_present = reinterpret_cast<uint32_t*>(calc_cnt + k);
+  uint32_t* throttled = used_present + k;
+  uint32_t* calc_present = throttled + k;
+  unsigned char* ovr = reinterpret_cast<unsigned char*>(calc_present + k);
+  for (int r = 0; r < R; ++r) {
+    used[(size_t)r * k + i] = src.used[(size_t)r * M + t];
+    calc[(size_t)r * k + i] = src.calc_thr[(size_t)r * M + t];
+  }
+  used_cnt[i] = src.used_cnt[t];
+  calc_cnt[i] = src.calc_cnt[t];
+  used_present[i] = src.used_present[t];
+  throttled[i] = src.throttled[t];
+  calc_present[i] = src.calc_present[t];
+  ovr[i] = src.override_active[t];
+}
+__global__ void __launch_bounds__(256) k_gather_bytes(int64_t k, const int64_t* __restrict__ rows, const unsigned char* __restrict__ src, unsigned char* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) out[i] = src[rows[i]];
 }
 
 // Gather k bitmap rows (one warp-wide strided copy per row).

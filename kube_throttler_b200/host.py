@@ -27,16 +27,22 @@ def _bind(L=None):
     L.kth_free.restype = None
     for name, args in (("kth_apply", [vp, cp]), ("kth_delete", [vp, cp, cp, cp]), ("kth_reconcile_all", [vp, cp]),
                        ("kth_get_status", [vp, cp, cp]), ("kth_get_status_manifest", [vp, cp, cp]), ("kth_pre_filter", [vp, cp]), ("kth_pre_filter_batch", [vp, cp]),
-                       ("kth_admit_queue", [vp, cp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_metrics", [vp]), ("kth_eval", [cp])):
+                       ("kth_admit_queue", [vp, cp]), ("kth_pre_filter_key", [vp, cp, cp]), ("kth_reserve_key", [vp, cp, cp]), ("kth_unreserve_key", [vp, cp, cp]),
+                       ("kth_queue_stats", [vp]), ("kth_reserve", [vp, cp]), ("kth_unreserve", [vp, cp]), ("kth_reserved", [vp, C.c_int, cp]), ("kth_metrics", [vp]), ("kth_eval", [cp])):
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = cp
+    L.kth_pre_filter_queue.argtypes = [vp, C.c_void_p, C.c_int64]
+    L.kth_pre_filter_queue.restype = C.c_int64
+    L.kth_queue_row.argtypes = [vp, cp, cp]
+    L.kth_queue_row.restype = C.c_int64
+    L.kth_last_error.restype = cp
     L._kth_bound = True
     return L
 
 
 HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status", "kth_get_status_manifest",
-                "kth_pre_filter", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
+                "kth_pre_filter", "kth_pre_filter_key", "kth_reserve_key", "kth_unreserve_key", "kth_pre_filter_queue", "kth_queue_row", "kth_queue_stats", "kth_last_error", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
 
 
 def _result(raw):
@@ -100,6 +106,35 @@ class Plugin:
     # plugin
     def prefilter(self, pod):
         return _result(self._L.kth_pre_filter(self._h, json.dumps(pod).encode()))
+
+    # the same for pods the informer already delivered (kth_apply), addressed by key: the resident scheduling queue
+    def prefilter_key(self, namespace, name):
+        return _result(self._L.kth_pre_filter_key(self._h, namespace.encode(), name.encode()))
+
+    def reserve_key(self, namespace, name):
+        return _result(self._L.kth_reserve_key(self._h, namespace.encode(), name.encode()))
+
+    def unreserve_key(self, namespace, name):
+        return _result(self._L.kth_unreserve_key(self._h, namespace.encode(), name.encode()))
+
+    def prefilter_queue(self):
+        """One verdict byte per queue row (0 free, 1 Success, 2 UnschedulableAndUnresolvable, 3 Error) in at most one device pass."""
+        import numpy as np
+
+        n = self._L.kth_pre_filter_queue(self._h, None, 0)
+        if n < 0:
+            _result(self._L.kth_last_error())
+        out = np.zeros(max(n, 1), np.uint8)
+        n = self._L.kth_pre_filter_queue(self._h, out.ctypes.data, out.shape[0])
+        if n < 0:
+            _result(self._L.kth_last_error())
+        return out[:n]
+
+    def queue_row(self, namespace, name) -> int:
+        return int(self._L.kth_queue_row(self._h, namespace.encode(), name.encode()))
+
+    def queue_stats(self):
+        return _result(self._L.kth_queue_stats(self._h))
 
     def prefilter_batch(self, pods):
         return _result(self._L.kth_pre_filter_batch(self._h, json.dumps(list(pods)).encode()))

@@ -64,6 +64,7 @@ struct kt_ctx {
   std::vector<int64_t> o_used, o_used_cnt, o_calc_thr, o_calc_cnt;
   std::vector<uint32_t> o_used_present, o_throttled, o_calc_present, run_bitmap, pend_bitmap, codes;
   std::vector<uint8_t> o_ovr_active, admit;
+  int64_t sparse_cap = 0;
   int32_t words() const { const int32_t w = (m + 31) / 32; const int32_t p = (w + 3) / 4 * 4; return p < 4 ? 4 : p; }
 };
 
@@ -223,6 +224,42 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   const size_t P = (size_t)c->pods[KT_PODS_PENDING].n, Wp = (size_t)c->words();
   if (codes && P) std::memcpy(codes, c->codes.data(), P * 2 * Wp * 4);
   if (admit && P) std::memcpy(admit, c->admit.data(), P);
+  return KT_OK;
+}
+int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t* rows, uint32_t* codes, uint8_t* admit) {
+  if (!c || k < 0 || (k > 0 && !rows)) return KT_ERR_INVALID;
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check_rows before kt_evaluate");
+  const size_t Wc = 2 * (size_t)c->words();
+  for (int64_t i = 0; i < k; ++i) {
+    if (rows[i] < 0 || rows[i] >= c->pods[KT_PODS_PENDING].n) return fail(c, KT_ERR_INVALID, "row out of range");
+    if (codes) std::memcpy(codes + (size_t)i * Wc, c->codes.data() + (size_t)rows[i] * Wc, Wc * 4);
+    if (admit) admit[i] = c->admit[(size_t)rows[i]];
+  }
+  return KT_OK;
+}
+// the sparse list of the double: the non-zero code words of the dense rows, in row order
+int kt_set_sparse_check(kt_ctx* c, int64_t cap) {
+  if (!c || cap < 0) return KT_ERR_INVALID;
+  c->sparse_cap = cap;
+  c->evaluated = false;
+  return KT_OK;
+}
+int kt_get_check_sparse(kt_ctx* c, uint8_t* admit, uint32_t* entries, int64_t cap, int64_t* count) {
+  if (!c || !count) return KT_ERR_INVALID;
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_check_sparse before kt_evaluate");
+  if (!c->sparse_cap) return fail(c, KT_ERR_STATE, "kt_get_check_sparse without kt_set_sparse_check");
+  const size_t P = (size_t)c->pods[KT_PODS_PENDING].n, Wc = 2 * (size_t)c->words();
+  if (admit && P) std::memcpy(admit, c->admit.data(), P);
+  int64_t n = 0;
+  const int64_t room = cap < c->sparse_cap ? cap : c->sparse_cap;
+  for (size_t row = 0; row < P; ++row)
+    for (size_t j = 0; j < Wc; ++j) {
+      const uint32_t word = c->codes[row * Wc + j];
+      if (!word) continue;
+      if (n < room) { entries[3 * n] = (uint32_t)row; entries[3 * n + 1] = (uint32_t)j; entries[3 * n + 2] = word; }
+      ++n;
+    }
+  *count = n;
   return KT_OK;
 }
 }

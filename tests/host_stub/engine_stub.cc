@@ -60,4 +60,17 @@ int kt_get_check(kt_ctx* c, uint32_t* codes, uint8_t* admit) {
   if (admit) std::memset(admit, 1, P);
   return KT_OK;
 }
+int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t*, uint32_t* codes, uint8_t* admit) {
+  if (!pass_ok()) return KT_ERR_CUDA;
+  if (codes) std::memset(codes, 0, (size_t)k * 2 * words(c) * 4);
+  if (admit) std::memset(admit, 1, (size_t)k);
+  return KT_OK;
+}
+int kt_set_sparse_check(kt_ctx*, int64_t) { return KT_OK; }
+int kt_get_check_sparse(kt_ctx* c, uint8_t* admit, uint32_t*, int64_t, int64_t* count) {
+  if (!pass_ok()) return KT_ERR_CUDA;
+  if (admit) std::memset(admit, 1, (size_t)c->n[KT_PODS_PENDING]);
+  *count = 0;
+  return KT_OK;
+}
 }

@@ -303,3 +303,56 @@ def test_sparse_check_equals_nonzero_words_of_the_dense_rows(kt, oracle, fused):
         with pytest.raises(Exception):
             eng.get_check_sparse(None, small)
         eng.close()
+
+
+def test_device_side_status_diff(kt, oracle):
+    """with an observed status uploaded, the reconciling pass itself says which throttles' status it changes
+    (throttle_controller.go:157 DeepEqual) -- compared here with a numpy diff of the oracle's outputs against the same observed
+    status -- and kt_get_reconcile_rows / kt_get_check_rows deliver exactly the listed rows of the full downloads."""
+    snap = synth.generate("C4", m=700, n=9000, p=1200)
+    fresh = oracle.columnar_evaluate(snap)
+    rng = np.random.default_rng(11)
+    m, R = snap.m, snap.R
+    st = dict(calculated=(rng.random(m) < 0.9).astype(np.uint8), calc_thr=fresh.calc_thr.copy(), calc_present=fresh.calc_present.copy(),
+              calc_cnt=fresh.calc_cnt.copy(), used=fresh.used.copy(), used_present=fresh.used_present.copy(),
+              used_cnt=fresh.used_cnt.copy(), throttled=fresh.throttled.copy())
+    # the informer copy lags: other sums on a fifth of the throttles, a flipped throttled bit, a stale threshold, a lost key
+    a, b, c_, d = (rng.random(m) < 0.2), (rng.random(m) < 0.05), (rng.random(m) < 0.05), (rng.random(m) < 0.05)
+    st["used"][0, a] += 7
+    st["throttled"][b] ^= 1
+    st["calc_thr"][min(1, R - 1), c_] += 1
+    st["used_present"][d] &= ~np.uint32(1)
+    snap.status = st
+    snap.normalize()
+    eng = kt.Engine(snap.R, snap.L, snap.LN)
+    eng.upload_snapshot(snap)
+    for _ in range(2):  # twice: the list counter re-arms itself
+        eng.evaluate(snap.now)
+        got = eng.download()
+        idx, flags = eng.get_changed()
+        live = _live(snap)
+        pm = lambda x: x[None, :] if x.ndim == 1 else x
+        differs = np.zeros(m, bool)
+        R_bits = (np.uint32(1) << np.arange(R, dtype=np.uint32))[:, None]
+        for name_v, name_p, cnt in (("used", "used_present", "used_cnt"), ("calc_thr", "calc_present", "calc_cnt")):
+            gp, sp = getattr(got, name_p), st[name_p]
+            differs |= gp != sp
+            has = (gp[None, :] & R_bits) != 0
+            differs |= ((getattr(got, name_v) != st[name_v]) & has).any(axis=0)
+            differs |= (getattr(got, cnt) != st[cnt]) & ((gp & abi.COUNT_BIT) != 0)
+        differs |= got.throttled != st["throttled"]
+        differs |= st["calculated"] == 0
+        differs &= live
+        np.testing.assert_array_equal(flags.astype(bool), differs)
+        np.testing.assert_array_equal(idx, np.nonzero(differs)[0])
+        assert 0 < idx.shape[0] < m
+        rows = eng.get_reconcile_rows(idx)
+        for f in ("used", "calc_thr"):
+            np.testing.assert_array_equal(getattr(rows, f), getattr(got, f)[:, idx], err_msg=f)
+        for f in ("used_present", "used_cnt", "throttled", "calc_present", "calc_cnt", "override_active"):
+            np.testing.assert_array_equal(getattr(rows, f), getattr(got, f)[idx], err_msg=f)
+        pick = np.sort(rng.choice(snap.pending.n, size=77, replace=False)).astype(np.int64)
+        codes, admit = eng.get_check_rows(pick)
+        np.testing.assert_array_equal(codes, got.codes[pick])
+        np.testing.assert_array_equal(admit, got.admit[pick])
+    eng.close()

@@ -183,6 +183,92 @@ def test_random_world(oracle, new_plugin, seed):
     dut.close()
 
 
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_resident_queue_by_key(oracle, new_plugin, seed):
+    """Pods the informer delivered that are waiting to be scheduled live in the device's pending table; PreFilter / Reserve /
+    Unreserve address them BY KEY (kth_pre_filter_key, ...) and must say exactly what the manifest calls -- and the oracle's
+    per-pod PreFilter -- say, through every kind of event that can change a verdict: reservations, reconciles, relabelled pods,
+    throttle edits, pods leaving the queue.  Verdicts are served from the cached queue pass whenever nothing a pod depends on
+    changed (the stats say so)."""
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i}" for i in range(4)]
+    both(*[namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}) for n in nss])
+    throttles = [rand_throttle(rng, i, nss) for i in range(30)]
+    both(*throttles)
+    both(*[rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(200)])
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    queue = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(90)]
+    both(*queue)  # the informer delivers the pending pods: they are resident from here on
+    key = lambda p: (p["metadata"]["namespace"], p["metadata"]["name"])
+
+    def compare(pods):
+        for p in pods:
+            want = norm_prefilter(ref.prefilter(p))
+            assert norm_prefilter(dut.prefilter_key(*key(p))) == want, key(p)
+            assert norm_prefilter(dut.prefilter(p)) == want  # the manifest entry point, same pod
+        return [ref.prefilter(p)["code"] for p in pods]
+
+    codes = compare(queue)
+    verdicts = dut.prefilter_queue()
+    names = {"Success": 1, "UnschedulableAndUnresolvable": 2, "Error": 3}
+    queued = 0
+    for p, c in zip(queue, codes):
+        row = dut.queue_row(*key(p))
+        if row < 0:  # another scheduler's pod: known to the informer, not in OUR queue (by-key calls check it like a manifest)
+            assert p["spec"]["schedulerName"] != SCHED
+            continue
+        queued += 1
+        assert verdicts[row] == names[c], key(p)
+    assert queued > len(queue) // 2 and (verdicts != 0).sum() >= queued  # (+ the "running" pods of the world that have no node yet)
+    before = dut.queue_stats()
+    compare(queue[:30])  # nothing changed: no further device pass over the queue for the by-key calls
+    after = dut.queue_stats()
+    assert after["hits"] >= before["hits"] + 28 and after["passes"] <= before["passes"] + 1  # (the first manifest call may grow the scratch rows)
+
+    # the scheduler's cycle: PreFilter -> Reserve by key, in queue order; every Reserve must be visible to the next PreFilter
+    admitted = []
+    for p in queue[:40]:
+        a, b = ref.prefilter(p), dut.prefilter_key(*key(p))
+        assert norm_prefilter(a) == norm_prefilter(b), key(p)
+        if a["code"] == "Success":
+            assert ref.reserve(p)["code"] == dut.reserve_key(*key(p))["code"] == "Success"
+            admitted.append(p)
+    assert admitted
+    for t in throttles:
+        k, nn = t["kind"], t["metadata"].get("namespace", "") + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (nn, a, b)
+    compare(queue)
+    # bind half of the admitted pods (they leave the queue), un-reserve one, relabel some queued pods, edit a throttle, reconcile
+    for i, p in enumerate(admitted):
+        if i % 2 == 0:
+            both(dict(p, spec=dict(p["spec"], nodeName="node-1"), status={"phase": "Running"}))
+            assert dut.queue_row(*key(p)) == -1  # bound: it left the queue
+    ref.unreserve(admitted[1]), dut.unreserve_key(*key(admitted[1]))
+    still = [p for i, p in enumerate(queue) if not (p in admitted and admitted.index(p) % 2 == 0)]
+    for p in rng.sample(still, 12):
+        p["metadata"]["labels"] = rand_labels(rng)
+        both(p)
+    compare(still)
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    compare(still)
+    throttles[3]["spec"]["threshold"] = {"resourceCounts": {"pod": 0}}
+    both(throttles[3])
+    compare(still[:30])
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    compare(still)
+    gone = still[5]
+    ref.delete("Pod", gone["metadata"]["name"], gone["metadata"]["namespace"]), dut.delete("Pod", gone["metadata"]["name"], gone["metadata"]["namespace"])
+    with pytest.raises(RuntimeError, match="not in the informer cache"):
+        dut.prefilter_key(*key(gone))
+    newcomers = [rand_pod(rng, rng.choice(nss), f"n{i}", False) for i in range(80)]  # the queue outgrows its first capacity
+    both(*newcomers)
+    compare(newcomers + still[6:20])
+    dut.close()
+
+
 @pytest.mark.parametrize("seed", [11, 18, 19])
 def test_admit_queue_equals_one_pod_per_cycle(oracle, new_plugin, seed):
     """kth_admit_queue == the scheduler's cycle (PreFilter, on Success Reserve) run pod by pod on the oracle: same verdict for

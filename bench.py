@@ -450,6 +450,28 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
         eng.evaluate(snap.now)
         fetch(eng)
 
+    # ONE call per step (kt_step_submit: packed uploads + pass + result copies queued; kt_step_wait: one synchronisation); the
+    # results land in the library's pinned block (status columns, admit bits, non-zero code words) and are read from there
+    structs = {}
+
+    def step_args(cols):
+        key = id(cols)
+        if key not in structs:
+            structs[key] = [(c.n, c.struct()) for c in cols]  # the ctypes views of the pinned columns are built once
+        return structs[key]
+
+    import ctypes as C
+    seen = []
+
+    def consume(res):  # the caller looks at its result: the admit bits (a 10 KB read) and the count of rejected pairs
+        sparse_counts.append(int(res.n_sparse))
+        seen.append(C.cast(res.admit, C.POINTER(C.c_uint8))[0])
+
+    def step_one_call():
+        a_ = step_args(src[0])
+        eng.step_submit(a_[0], a_[1], snap.now)
+        consume(eng.step_wait())
+
     # what the host link of this box can do at all (pinned, one 64 MiB copy each way): the floor of any e2e number
     probe_h, probe_d = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
     link = {}
@@ -479,20 +501,22 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
     wide_value = time_steps(step_wide)
     eng.set_async_uploads(True)  # the pinned columns live for the whole run: no need to wait for each copy before queueing the next
     eng.set_sparse_check(sparse_cap)
-    value = pinned_value = time_steps(step)
+    separate_calls_value = time_steps(step) if packed else None
+    value = pinned_value = time_steps(step_one_call) if packed else time_steps(step)
     upload_memory = "pinned"
     if packed_wc:
         src[0] = packed_wc
-        wc_value = time_steps(step)
+        wc_value = time_steps(step_one_call)
         if wc_value > value:
             value, upload_memory = wc_value, "pinned write-combined"
         else:
             src[0] = packed
-    # Double-buffered steps: a second context (own stream, own snapshot buffers) takes the NEXT step's upload while this
-    # step's pass runs and its results come back -- H2D, the pass and D2H of consecutive steps overlap; every step still
-    # copies its inputs in and its results out.  Single GPU only (a second context would need a second peer window set).
+    serial_value = value
+    # Double-buffered steps: a second context (own stream, own snapshot buffers) is handed the NEXT step while this step's
+    # pass runs and its results come back -- H2D, the pass and D2H of consecutive steps overlap; every step still copies its
+    # inputs in and its results out and is waited for.  Single GPU only (a second context would need a second peer window set).
     pipelined = None
-    if world == 1:
+    if world == 1 and packed:
         try:
             eng2 = kt.Engine(snap.R, snap.L, snap.LN, device=bench.local_rank)
             stream2 = torch.cuda.Stream()
@@ -501,20 +525,23 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
             eng2.set_async_uploads(True)
             eng2.set_sparse_check(sparse_cap)
             pair, turn = (eng, eng2), [0]
+            a_ = step_args(src[0])
+            pair[0].step_submit(a_[0], a_[1], snap.now)
 
             def step_pipelined():
                 cur, nxt = pair[turn[0] & 1], pair[(turn[0] + 1) & 1]
-                upload(nxt, src[0])     # queued on the other context's stream; returns at once
-                cur.evaluate(snap.now)  # the rows this context received one step ago
-                fetch(cur)
+                nxt.step_submit(a_[0], a_[1], snap.now)  # step k+1 is queued on the other context's stream ...
+                consume(cur.step_wait())                  # ... while step k finishes
                 turn[0] += 1
 
-            upload(pair[0], src[0])
             pipelined = time_steps(step_pipelined)
+            pair[turn[0] & 1].step_wait()
             eng2.sync()
             eng2.close()
         except Exception as e:  # noqa: BLE001 -- the serial number stands
             print(f"pipelined e2e unavailable: {e}", file=sys.stderr)
+    if pipelined and pipelined > value:
+        value = pipelined
     eng.set_sparse_check(0)
     eng.set_async_uploads(False)
     n_sparse = max(sparse_counts) if sparse_counts else 0
@@ -522,8 +549,12 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
     d2h = d2h_dense - codes_b.array.nbytes + (12 * min(n_sparse + n_sparse // 4 + 256, sparse_cap) + 4 if n_sparse <= sparse_cap else 12 * sparse_cap + 4 + codes_b.array.nbytes)
     floor = checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-            "path": ("kt_upload_pods_packed x2" if packed else "kt_upload_pods x2") + " (async) + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)",
+            "path": (("kt_step_submit (kt_upload_pods_packed x2 + kt_evaluate + result copies) + kt_step_wait, pinned host buffers; " +
+                      ("two contexts alternating: step k+1 is submitted before step k is waited for" if pipelined and value == pipelined else "one context, serial"))
+                     if packed else "kt_upload_pods x2 + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)"),
+            "serial": {"value": serial_value, "note": "one context: submit, wait, submit, ..."},
             "double_buffered": {"value": pipelined, "note": "two contexts alternate: step k+1's upload overlaps step k's pass and download"},
+            "separate_calls": {"value": separate_calls_value, "note": "kt_upload_pods_packed x2 + kt_evaluate + kt_get_check_sparse + kt_get_reconcile, one context"},
             "sparse_check_entries": n_sparse, "upload_memory": upload_memory, "pinned_upload_value": pinned_value, "host_affinity": bench.host_affinity,
             "wide_int64_upload": {"value": wide_value, "h2d_bytes_per_step": h2d_wide, "d2h_bytes_per_step": d2h_dense},
             "host_link_gbs": link, "link_floor_value": floor, "frac_of_link_floor": value / floor,

@@ -285,6 +285,25 @@ int kt_set_reserved(kt_ctx* ctx, const int64_t* reserved /*[R][m]*/,
  * the context stream unless a getter is called; kt_sync() waits. */
 int kt_evaluate(kt_ctx* ctx, int64_t now_unix_ns, uint32_t flags);
 
+/* ---- one end-to-end step in one call --------------------------------------------- */
+/* A caller that hands over a fresh snapshot every pass (host buffers in, results out) pays for every boundary crossing and
+ * every stream synchronisation.  kt_step_submit queues ONE whole step on the context's stream -- the packed pod rows of
+ * either kind (NULL: keep the resident rows), the pass, the results into one library-owned pinned block: per-throttle status
+ * columns, admit bits, the non-zero check-code words (needs kt_set_sparse_check) -- and returns; kt_step_wait blocks until
+ * the block has landed and points `out` into it (valid until the next kt_step_submit on this context).  One synchronisation
+ * per step; two contexts submitting alternately overlap one step's upload with the other's pass and download.
+ * The host buffers of a submitted step must stay untouched until its kt_step_wait has returned. */
+typedef struct kt_step_result {
+  int64_t n_pending;        /* rows of admit[] */
+  int64_t n_sparse;         /* non-zero code words of the pass; entries holds min(n_sparse, cap of kt_set_sparse_check) of them */
+  const uint8_t* admit;     /* [n_pending] */
+  const uint32_t* entries;  /* [..][3] {pending row, code word index, codes} as kt_get_check_sparse */
+  kt_reconcile_out status;  /* pointers into the block, shaped as kt_get_reconcile fills them */
+} kt_step_result;
+int kt_step_submit(kt_ctx* ctx, int64_t n_running, const kt_packed_pods* running, int64_t n_pending, const kt_packed_pods* pending,
+                   int64_t now_unix_ns, uint32_t flags);
+int kt_step_wait(kt_ctx* ctx, kt_step_result* out);
+
 /* ---- results (HBM -> host) ------------------------------------------------------ */
 int kt_get_reconcile(kt_ctx* ctx, const kt_reconcile_out* out);
 /* words_per_row = kt_match_words(ctx); bitmap rows are pod-major: bit (t&31) of

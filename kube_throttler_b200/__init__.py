@@ -44,7 +44,7 @@ EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
     "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_alloc_upload", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_check_rows", "kt_get_changed", "kt_get_reconcile_rows", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_check_rows", "kt_get_changed", "kt_get_reconcile_rows", "kt_step_submit", "kt_step_wait", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
@@ -81,6 +81,8 @@ def lib():
         L.kt_upload_pods_packed.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(abi.PackedPodsStruct)]
         L.kt_set_sparse_check.argtypes = [vp, C.c_int64]
         L.kt_get_check_sparse.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.kt_step_submit.argtypes = [vp, C.c_int64, C.POINTER(abi.PackedPodsStruct), C.c_int64, C.POINTER(abi.PackedPodsStruct), C.c_int64, C.c_uint32]
+        L.kt_step_wait.argtypes = [vp, C.POINTER(abi.StepResult)]
         L.kt_get_check_rows.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.kt_get_changed.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64), vp]
         L.kt_get_reconcile_rows.argtypes = [vp, C.c_int64, vp, C.POINTER(abi.ReconcileOut)]
@@ -283,6 +285,30 @@ class Engine:
         n = C.c_int64(0)
         self._ck(self._L.kt_get_check_sparse(self._h, abi.ptr(admit), abi.ptr(entries), entries.shape[0], C.byref(n)))
         return int(n.value)
+
+    # -- one end-to-end step in one call ----------------------------------------------------------
+    def step_submit(self, running, pending, now: int, flags: int = abi.EVAL_FRESH_STATUS):
+        """Queue packed uploads (abi.PackedPodCols or a prepared (n, struct) pair; None keeps the resident rows) + the pass + the
+        result copies; returns at once.  The host columns must stay untouched until step_wait()."""
+        def prep(x):
+            if x is None:
+                return 0, None
+            if isinstance(x, tuple):
+                return x
+            return x.n, x.struct()
+        (nr, sr), (np_, sp) = prep(running), prep(pending)
+        self._ck(self._L.kt_step_submit(self._h, nr, C.byref(sr) if sr is not None else None, np_, C.byref(sp) if sp is not None else None, now, flags))
+        if running is not None:
+            self.n[abi.PODS_RUNNING] = nr
+        if pending is not None:
+            self.n[abi.PODS_PENDING] = np_
+
+    def step_wait(self) -> "abi.StepResult":
+        """Block until the submitted step's results have landed; the returned struct points into the library's pinned block
+        (valid until the next step_submit): .admit [n_pending] u8, .entries [n_sparse][3] u32, .status columns."""
+        res = abi.StepResult()
+        self._ck(self._L.kt_step_wait(self._h, C.byref(res)))
+        return res
 
     def get_check_rows(self, rows: np.ndarray):
         """(codes[k][2W], admit[k]) of the listed pending rows."""

@@ -67,6 +67,10 @@ class ReconcileOut(C.Structure):
                 ("calc_cnt", C.c_void_p), ("override_active", C.c_void_p)]
 
 
+class StepResult(C.Structure):  # kt_step_result
+    _fields_ = [("n_pending", C.c_int64), ("n_sparse", C.c_int64), ("admit", C.c_void_p), ("entries", C.c_void_p), ("status", ReconcileOut)]
+
+
 class Timing(C.Structure):
     _fields_ = [("reconcile_ms", C.c_float), ("allreduce_ms", C.c_float), ("finalize_ms", C.c_float),
                 ("check_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32)]

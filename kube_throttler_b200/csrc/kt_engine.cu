@@ -156,6 +156,12 @@ struct kt_ctx {
   size_t h_out_cap = 0, out_bytes = 0;
   size_t o_off[8] = {};
   bool async_uploads = false;  // kt_set_async_uploads
+  // kt_step_submit / kt_step_wait: one pinned result block, one event
+  void* h_step = nullptr;
+  size_t h_step_cap = 0, step_off[3] = {};
+  cudaEvent_t ev_step = nullptr;
+  int64_t step_first = 0;
+  bool step_pending = false;
   DevBuf d_codes, d_admit;
   DevBuf d_sparse;              // kt_set_sparse_check: {count u32, pad to 16 B, entries [cap][3] u32}
   uint32_t sparse_cap = 0;      // 0: off
@@ -522,6 +528,8 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
                    &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_changed, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_step) cudaFreeHost(c->h_step);
+  if (c->ev_step) cudaEventDestroy(c->ev_step);
   if (c->h_sparse_count) cudaFreeHost(c->h_sparse_count);
   c->d_sparse.release();
   for (DevBuf* b : all) b->release();
@@ -660,9 +668,13 @@ int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, con
   return KT_OK;
 }
 
+static int upload_pods_packed_locked(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* pk);
 int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* pk) {
   if (!c) return KT_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
+  return upload_pods_packed_locked(c, kind, n, pk);
+}
+static int upload_pods_packed_locked(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* pk) {
   if (kind != KT_PODS_RUNNING && kind != KT_PODS_PENDING) return fail(c, KT_ERR_INVALID, "bad pod kind %d", kind);
   if (n < 0 || !pk || (n > 0 && (!pk->labels16 || !pk->meta))) return fail(c, KT_ERR_INVALID, "null packed pod columns");
   const bool coded = pk->req_codes != nullptr;
@@ -714,13 +726,24 @@ int kt_upload_pods_packed(kt_ctx* c, int kind, int64_t n, const kt_packed_pods* 
     ReqShifts sh{};
     if (!coded)
       for (int r = 0; r < R; ++r) sh.s[r] = (unsigned char)pk->req_shift[r];
+    // with tables in place the rows are translated (labels -> table row offsets, namespace -> word info) in the same kernel:
+    // one launch and one read of the labels less per upload
+    const bool fuse = c->have_throttles;
+    if (fuse) {
+      KT_CUDA(c, s.roff.reserve((size_t)Lpad * n * 4 + 16));
+      KT_CUDA(c, s.winfo.reserve((size_t)n * 4 + 16));
+    }
     k_unpack_packed<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, L, Lpad, R, pk->ns_bits, pk->n_pairs, s.c_pairs.as<int64_t>(), s.c_labels.as<uint16_t>(),
                                                                         s.c_req.as<int32_t>(), sh, rc, s.c_meta.as<uint32_t>(), s.labels.as<int64_t>(),
-                                                                        s.req.as<int64_t>(), s.present.as<uint32_t>(), s.flags.as<uint32_t>(), s.ns.as<int32_t>());
+                                                                        s.req.as<int64_t>(), s.present.as<uint32_t>(), s.flags.as<uint32_t>(), s.ns.as<int32_t>(),
+                                                                        fuse ? 1 : 0, fuse ? table_view(c) : TableView{}, s.roff.as<uint32_t>(), s.winfo.as<uint32_t>());
     KT_CUDA(c, cudaGetLastError());
+    s.n = n;
+    s.roff_valid = fuse;
+  } else {
+    s.n = n;
+    s.roff_valid = false;
   }
-  s.n = n;
-  s.roff_valid = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -865,9 +888,13 @@ int kt_set_reserved(kt_ctx* c, const int64_t* reserved, const uint32_t* present,
 
 int32_t kt_match_words(const kt_ctx* c) { return c && c->have_throttles ? c->ht.Wp : 0; }
 
+static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags);
 int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   if (!c) return KT_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
+  return evaluate_locked(c, now, flags);
+}
+static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   if (!c->have_throttles) return fail(c, KT_ERR_STATE, "kt_evaluate before kt_upload_throttles");
   const bool given = flags & KT_EVAL_GIVEN_STATUS;
   const bool do_rec = !(flags & KT_EVAL_SKIP_RECONCILE), do_chk = !(flags & KT_EVAL_SKIP_CHECK);
@@ -1020,6 +1047,81 @@ int kt_evaluate(kt_ctx* c, int64_t now, uint32_t flags) {
   c->last = kt_timing{};
   c->last.launches = launches;
   c->evaluated = true;
+  return KT_OK;
+}
+
+// ---- one end-to-end step in one call ------------------------------------------------------------------------------------
+int kt_step_submit(kt_ctx* c, int64_t n_running, const kt_packed_pods* running, int64_t n_pending, const kt_packed_pods* pending, int64_t now, uint32_t flags) {
+  if (!c) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->sparse_cap) return fail(c, KT_ERR_STATE, "kt_step_submit needs kt_set_sparse_check (the check result travels as admit bits + non-zero code words)");
+  const bool saved = c->async_uploads;
+  c->async_uploads = true;  // nothing in a step waits for the host before kt_step_wait
+  int rc = KT_OK;
+  if (running) rc = upload_pods_packed_locked(c, KT_PODS_RUNNING, n_running, running);
+  if (!rc && pending) rc = upload_pods_packed_locked(c, KT_PODS_PENDING, n_pending, pending);
+  if (!rc) rc = evaluate_locked(c, now, flags);
+  c->async_uploads = saved;
+  if (rc) return rc;
+  // results -> ONE pinned block: [status block | admit | sparse count | first entries]
+  const int64_t P = c->pods[KT_PODS_PENDING].n;
+  const size_t off_admit = (c->out_bytes + 63) & ~(size_t)63, off_cnt = (off_admit + (size_t)P + 63) & ~(size_t)63, off_ent = off_cnt + 16;
+  const size_t need = off_ent + (size_t)c->sparse_cap * 12 + 64;
+  if (c->h_step_cap < need) {
+    if (c->h_step) cudaFreeHost(c->h_step);
+    c->h_step = nullptr;
+    c->h_step_cap = 0;
+    KT_CUDA(c, cudaHostAlloc(&c->h_step, need, cudaHostAllocDefault));
+    c->h_step_cap = need;
+  }
+  if (!c->ev_step) KT_CUDA(c, cudaEventCreateWithFlags(&c->ev_step, cudaEventDisableTiming));
+  unsigned char* hb = reinterpret_cast<unsigned char*>(c->h_step);
+  if (c->out_bytes) KT_CUDA(c, cudaMemcpyAsync(hb, c->d_out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (P > 0) KT_CUDA(c, cudaMemcpyAsync(hb + off_admit, c->d_admit.p, (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  int64_t first = c->sparse_guess < c->sparse_cap ? c->sparse_guess : c->sparse_cap;
+  if (P == 0) first = 0;
+  // the count and the entries sit next to each other on the device ({count, pad to 16 B, entries}): one copy
+  KT_CUDA(c, cudaMemcpyAsync(hb + off_cnt, c->d_sparse.p, 16 + (size_t)first * 12, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaEventRecord(c->ev_step, c->stream));
+  c->step_first = first;
+  c->step_off[0] = off_admit; c->step_off[1] = off_cnt; c->step_off[2] = off_ent;
+  c->step_pending = true;
+  return KT_OK;
+}
+
+int kt_step_wait(kt_ctx* c, kt_step_result* out) {
+  if (!c || !out) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->step_pending) return fail(c, KT_ERR_STATE, "kt_step_wait without kt_step_submit");
+  int rc = set_device(c);
+  if (rc) return rc;
+  KT_CUDA(c, cudaEventSynchronize(c->ev_step));
+  c->step_pending = false;
+  if ((rc = check_pass_error(c))) return rc;
+  unsigned char* hb = reinterpret_cast<unsigned char*>(c->h_step);
+  const int64_t P = c->pods[KT_PODS_PENDING].n;
+  const int64_t total = P > 0 ? (int64_t)*reinterpret_cast<uint32_t*>(hb + c->step_off[1]) : 0;
+  const int64_t have = total < (int64_t)c->sparse_cap ? total : (int64_t)c->sparse_cap;
+  if (have > c->step_first) {  // more rejected pairs than the last pass had: fetch the rest
+    KT_CUDA(c, cudaMemcpyAsync(hb + c->step_off[2] + (size_t)c->step_first * 12, c->d_sparse.as<unsigned char>() + 16 + (size_t)c->step_first * 12,
+                               (size_t)(have - c->step_first) * 12, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int64_t g = total + total / 4 + 256;
+  if (g > (int64_t)c->sparse_cap) g = c->sparse_cap;
+  c->sparse_guess = (uint32_t)g;
+  out->n_pending = P;
+  out->n_sparse = total;
+  out->admit = hb + c->step_off[0];
+  out->entries = reinterpret_cast<const uint32_t*>(hb + c->step_off[2]);
+  out->status.used = reinterpret_cast<int64_t*>(hb + c->o_off[0]);
+  out->status.used_cnt = reinterpret_cast<int64_t*>(hb + c->o_off[1]);
+  out->status.calc_thr = reinterpret_cast<int64_t*>(hb + c->o_off[2]);
+  out->status.calc_cnt = reinterpret_cast<int64_t*>(hb + c->o_off[3]);
+  out->status.used_present = reinterpret_cast<uint32_t*>(hb + c->o_off[4]);
+  out->status.throttled = reinterpret_cast<uint32_t*>(hb + c->o_off[5]);
+  out->status.calc_present = reinterpret_cast<uint32_t*>(hb + c->o_off[6]);
+  out->status.override_active = reinterpret_cast<uint8_t*>(hb + c->o_off[7]);
   return KT_OK;
 }
 

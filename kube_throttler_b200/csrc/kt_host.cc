@@ -446,7 +446,25 @@ struct kth_plugin {
 
   std::vector<PodObj> pods;  // slot == device row of the running-pod table
   std::unordered_map<std::string, int64_t> pod_index;
-  std::vector<int64_t> free_rows;
+  // Row arenas: the device kernels walk a warp's 32 rows word by word (kt_kernels.cuh reconcile_tile), which is one or two
+  // rounds when the rows share a namespace and one round per row when they do not.  The reference's pod informer is indexed
+  // by namespace (plugin.go:81-84); here a namespace owns whole chunks of kArenaChunk consecutive rows, a new pod takes a free
+  // slot of its namespace's chunks (or opens a new chunk), a deleted pod's slot goes back to ITS namespace -- so rows stay
+  // namespace-clustered under any churn, at the price of < kArenaChunk tombstone rows per namespace.
+  static constexpr int64_t kArenaChunk = 32;
+  std::unordered_map<std::string, std::vector<int64_t>> ns_free_rows;
+  int64_t alloc_row(const std::string& ns) {
+    std::vector<int64_t>& f = ns_free_rows[ns];
+    if (f.empty()) {
+      const int64_t base = (int64_t)pods.size();
+      pods.resize((size_t)(base + kArenaChunk));
+      for (int64_t i = 0; i < kArenaChunk; ++i) pods[(size_t)(base + i)].row = base + i;
+      for (int64_t i = kArenaChunk - 1; i >= 0; --i) f.push_back(base + i);  // handed out front to back
+    }
+    const int64_t row = f.back();
+    f.pop_back();
+    return row;
+  }
   std::set<int64_t> dirty_rows;
   uint64_t next_pod_seq = 1;
   int64_t row_capacity = 0;  // rows the device table currently holds
@@ -1737,9 +1755,7 @@ struct kth_plugin {
     PodObj p = pod_from(v);
     auto it = pod_index.find(p.nn());
     if (it == pod_index.end()) {
-      int64_t row;
-      if (!free_rows.empty()) { row = free_rows.back(); free_rows.pop_back(); }
-      else { row = (int64_t)pods.size(); pods.emplace_back(); }
+      const int64_t row = alloc_row(p.ns);
       p.row = row;
       p.seq = next_pod_seq++;
       pod_index[p.nn()] = row;
@@ -1801,7 +1817,7 @@ struct kth_plugin {
     pods[(size_t)row] = PodObj();  // tombstone row: flags == 0, no labels
     pods[(size_t)row].row = row;
     pod_index.erase(it);
-    free_rows.push_back(row);
+    ns_free_rows[old.ns].push_back(row);  // the slot stays with its namespace's arena
     dirty_rows.insert(row);
     // DeleteFunc (:509-515): a scheduled pod that disappears is un-reserved from its affected throttles
     if (should_count_in(old) && !old.node_name.empty() && !throttles.empty()) {

@@ -106,12 +106,24 @@ struct WordCursor {
       cnt = __ldg(&tb.nsw_off[ns + 1]) - lo;
     }
   }
+  __device__ __forceinline__ int at_inline0() const { return inl > 0 ? w0 : 0x40000000 + lo; }  // a per-namespace key for clustering tests
   __device__ __forceinline__ int at(const TableView& tb, int k) const {
     if (k >= cnt) return 0x7fffffff;
     if (k < inl) return k == 0 ? w0 : w1;
     return __ldg(&tb.nsw_idx[lo + k]);
   }
 };
+
+#ifndef KT_SCATTER_WORDS  // a warp whose lanes start in more distinct words than this takes the per-lane paths
+#define KT_SCATTER_WORDS 6
+#endif
+// Do the lanes of this warp live in many different namespaces (rows in arrival order)?  Judged by their first words.
+__device__ __forceinline__ bool warp_is_scattered(const WordCursor& wc) {
+  const int key = wc.cnt > 0 ? wc.at_inline0() : -1;
+  const unsigned same = __match_any_sync(kFull, key);
+  const bool leader = key >= 0 && (__ffs(same) - 1) == (int)(threadIdx.x & 31);
+  return __popc(__ballot_sync(kFull, leader)) > KT_SCATTER_WORDS;
+}
 
 // Per-throttle constants of the 4-step check, produced by k_finalize, gathered per matched pair.
 // Followed in memory by int64 thrv[R] (S1 thresholds) and int64 head[R] (S4: threshold - used - reserved).
@@ -660,6 +672,35 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   unsigned long long* part_pres = part + (size_t)R * tb.M;
   unsigned long long* part_cnt = part + (size_t)2 * R * tb.M;
 
+  // Rows in ARRIVAL order (no two lanes of the warp in the same namespace): the word-by-word rounds below would run once per
+  // lane for a handful of matches each.  Such a warp adds its pods' requests straight to the per-throttle sums in L2, one
+  // RED per (matched throttle, resource) -- slower per match than the transposed sums, but no rounds.
+  if (warp_is_scattered(wc)) {
+#pragma unroll 1
+    for (int kk = 0; kk < wc.cnt; ++kk) {
+      const int w = wc.at(tb, kk);
+      uint32_t word;
+      if (kk < wc.inl) {
+        word = kk == 0 ? m0 : m1;
+      } else {
+        word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
+        if (word) bitmap[p * Wp + w] = word;
+      }
+      if (!alive) continue;
+      while (word) {
+        const int t = w * 32 + __ffs(word) - 1;
+        word &= word - 1;
+        atomicAdd(&part_cnt[t], 1ull);
+        for (int r = 0; r < R; ++r)
+          if ((present >> r) & 1) {
+            const unsigned long long v = (unsigned long long)s_req[r * TILE + tid];
+            if (v) atomicAdd(&part_used[(size_t)r * tb.M + t], v);
+            part_pres[(size_t)r * tb.M + t] = 1ull;  // idempotent flag
+          }
+      }
+    }
+    wc.cnt = 0;  // nothing left for the rounds below (the warp still takes part in the CTA's barriers and sweep)
+  }
   // phase 2 -- the segmented sums, word by word in ascending order, warp-uniform: lanes whose namespace has word w bring
   // their match word (already known for their first two), the others idle.  Namespace-clustered rows (the reference's pod
   // informer is namespace-indexed) make this 1-3 rounds.
@@ -1280,6 +1321,82 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     *reinterpret_cast<CheckHdr*>(dst) = h;
   };
 
+  // Pending rows in ARRIVAL order (a different namespace in every lane): staging 32-throttle records word by word would take
+  // one round per lane.  Such a warp checks its pairs one by one instead, every constant fetched from L2 -- the same 4 steps,
+  // without the staging (done below, once the sums exist); it proposes no words to the CTA's rounds.
+  const bool scattered = warp_is_scattered(wc);
+  if (scattered) cur = 0x7fffffff;
+  auto pair_direct = [&](int t) -> uint32_t {
+    const unsigned char* src = pre + (size_t)t * rec;
+    const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));
+    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
+    PreHdr ph;
+    ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
+    if (!(ph.flags & kPreLive)) return KT_CHECK_NOT_THROTTLED;
+    const bool e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
+    bool s1, s2, s3, s4;
+    {  // the pod count: the pending pod itself counts 1
+      const long long thr = __ldcg(&pv[2 * R]);
+      long long au = __ldcg(&pv[2 * R + 1]);
+      const bool has = ph.thr_has & KT_COUNT_BIT;
+      bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
+      if (!given) {
+        const long long used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
+        const bool used_has = used > 0;
+        au += used;
+        au_has = au_has || used_has;
+        m2 = has && used_has && used >= thr;
+      }
+      s1 = has && 1 > thr;
+      s2 = m2;
+      s3 = has && au_has && (e3 ? au >= thr : au > thr);
+      s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);
+    }
+    for (uint32_t c = nz; c;) {  // IsThrottledFor only looks at the pod's non-zero requests (Q5)
+      const int r = __ffs(c) - 1;
+      c &= c - 1;
+      const long long thr = __ldcg(&pv[r]);
+      long long au = __ldcg(&pv[R + r]);
+      const bool has = (ph.thr_has >> r) & 1;
+      bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
+      if (!given) {
+        const long long used = (long long)__ldcg(&px.total[(size_t)r * M + t]);
+        const bool used_has = __ldcg(&px.total[(size_t)(R + r) * M + t]) != 0ull;
+        au += used;
+        au_has = au_has || used_has;
+        m2 = has && used_has && used >= thr;
+      }
+      const long long v = s_req[r * TILE + tid];
+      s1 = s1 || (has && v > thr);
+      s2 = s2 || m2;
+      s3 = s3 || (has && au_has && (e3 ? au >= thr : au > thr));
+      s4 = s4 || (has && (on_equal ? v >= thr - au : v > thr - au));
+    }
+    return s1 ? KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD : ((s2 || s3) ? KT_CHECK_ACTIVE : (s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED));
+  };
+  auto decide_scattered = [&]() {
+#pragma unroll 1
+    for (int kk = 0; kk < wc.cnt; ++kk) {
+      const int w = wc.at(tb, kk);
+      uint32_t word = __ldcg(&bitmap[p * Wp + w]);
+      uint32_t c0 = 0, c1 = 0;
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const uint32_t code = pair_direct(w * 32 + b);
+        if (code) ok = 0;
+        if (b < 16) c0 |= code << (2 * b);
+        else c1 |= code << (2 * (b - 16));
+      }
+      if (c0) codes[p * 2 * Wp + 2 * w] = c0;
+      if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+      if (sp.count) {
+        if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
+        if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
+      }
+    }
+  };
+
 #pragma unroll 1
   while (true) {
     // 1. every warp's next (up to) KS words in its warp-uniform order, the lanes' match words fetched together; each word
@@ -1331,6 +1448,7 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       stamp(6);
     }
     for (int slot = warp; slot < SLOTS; slot += WARPS) stage_post(slot);
+    if (scattered && k == 0) { decide_scattered(); k = 1; }  // (k is otherwise unused by a scattered warp: marks "done")
     __syncthreads();
     stamp(7);
     // 3. every lane decides its own pairs
@@ -1463,16 +1581,33 @@ struct ReqCodes {
 __global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpad, int R, int ns_bits, int n_pairs, const int64_t* __restrict__ pairs,
                                                        const uint16_t* __restrict__ labels16, const int32_t* __restrict__ req32, const ReqShifts req_shift,
                                                        const ReqCodes rc, const uint32_t* __restrict__ meta, int64_t* __restrict__ labels, int64_t* __restrict__ req,
-                                                       uint32_t* __restrict__ present, uint32_t* __restrict__ flags, int32_t* __restrict__ ns) {
+                                                       uint32_t* __restrict__ present, uint32_t* __restrict__ flags, int32_t* __restrict__ ns,
+                                                       int translate, const TableView tb, uint32_t* __restrict__ roff, uint32_t* __restrict__ winfo) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  for (int s = 0; s < Lpad; ++s) {
-    int64_t lab = KT_LABEL_EMPTY;
-    if (s < L) {
-      const uint32_t c = __ldg(&labels16[(int64_t)s * n + p]);
-      if (c != 0xffffu && (int)c < n_pairs) lab = __ldg(&pairs[c]);
+  // labels in chunks of eight slots; with `translate` the chunk goes through the label dictionary while it is in registers
+  // (what k_translate_rows would do in a second launch, re-reading the int64 columns this kernel has just written)
+#pragma unroll 1
+  for (int s0 = 0; s0 < Lpad; s0 += 8) {
+    int64_t lab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int s = s0 + j;
+      lab[j] = KT_LABEL_EMPTY;
+      if (s < L) {
+        const uint32_t c = __ldg(&labels16[(int64_t)s * n + p]);
+        if (c != 0xffffu && (int)c < n_pairs) lab[j] = __ldg(&pairs[c]);
+      }
+      labels[(int64_t)s * n + p] = lab[j];
     }
-    labels[(int64_t)s * n + p] = lab;
+    if (translate) {
+      uint4 ke[8];
+      uint32_t o[8];
+      translate8_keys(tb, lab, ke);
+      translate8_rows(tb, lab, ke, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) roff[(int64_t)(s0 + j) * n + p] = o[j];
+    }
   }
   if (rc.codes) {
     for (int r = 0; r < R; ++r) {
@@ -1484,9 +1619,20 @@ __global__ void __launch_bounds__(256) k_unpack_packed(int64_t n, int L, int Lpa
     for (int r = 0; r < R; ++r) req[(int64_t)r * n + p] = (int64_t)__ldg(&req32[(int64_t)r * n + p]) << req_shift.s[r];
   }
   const uint32_t m = __ldg(&meta[p]);
-  ns[p] = (int32_t)(m & ((1u << ns_bits) - 1u));
+  const int my_ns = (int32_t)(m & ((1u << ns_bits) - 1u));
+  ns[p] = my_ns;
   flags[p] = (m >> ns_bits) & 7u;
   present[p] = (m >> (ns_bits + 3)) & (R >= 32 ? 0xffffffffu : ((1u << R) - 1u));
+  if (translate) {  // the words that can apply to the row's namespace (see winfo_pack)
+    int cnt = 0, w0 = 0, w1 = 0;
+    if ((unsigned)my_ns < (unsigned)tb.NS) {
+      const int lo = __ldg(&tb.nsw_off[my_ns]);
+      cnt = __ldg(&tb.nsw_off[my_ns + 1]) - lo;
+      if (cnt > 0) w0 = __ldg(&tb.nsw_idx[lo]);
+      if (cnt > 1) w1 = __ldg(&tb.nsw_idx[lo + 1]);
+    }
+    winfo[p] = cnt == 0 ? 0u : winfo_pack(cnt, w0, w1, tb.W);
+  }
 }
 
 // Row-level delta: scatter k packed rows into the resident columns (pod informer Add/Update/Delete).

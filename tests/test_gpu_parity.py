@@ -356,3 +356,56 @@ def test_device_side_status_diff(kt, oracle):
         np.testing.assert_array_equal(codes, got.codes[pick])
         np.testing.assert_array_equal(admit, got.admit[pick])
     eng.close()
+
+
+def test_step_api_equals_separate_calls(kt, oracle):
+    """kt_step_submit / kt_step_wait: one call queues packed uploads + pass + result copies, one synchronisation delivers the
+    status columns, admit bits and non-zero code words in one pinned block -- the same bits as the separate calls, step
+    after step, also with two contexts alternating (double buffering) and with the resident rows kept (NULL uploads)."""
+    import ctypes as C
+
+    def view(ptr, dtype, shape):
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape).copy()
+
+    snaps = [synth.generate("C2", m=300, n=8000, p=1500), synth.generate("C2", m=300, n=8000, p=1500, seed=77)]
+    want = []
+    engines = []
+    for snap in snaps:
+        eng = kt.Engine(snap.R, snap.L, snap.LN)
+        eng.upload_snapshot(snap)
+        eng.set_sparse_check(4 * snap.pending.n + 64)
+        engines.append(eng)
+        got = None
+    packed = [[abi.packed_pods(pods, code_requests=True) for pods in (s_.running, s_.pending)] for s_ in snaps]
+    for it in range(4):
+        for eng, snap, pk in zip(engines, snaps, packed):  # both submitted before either is waited for
+            if it == 3:
+                eng.step_submit(None, None, snap.now)  # resident rows
+            else:
+                eng.step_submit(pk[0], pk[1], snap.now)
+        for eng, snap in zip(engines, snaps):
+            res = eng.step_wait()
+            W = eng.words_per_row
+            ref = oracle.columnar_evaluate(snap, words_per_row=W)
+            P, m, R = snap.pending.n, snap.m, snap.R
+            assert res.n_pending == P
+            np.testing.assert_array_equal(view(res.admit, np.uint8, (P,)), ref.admit)
+            ent = view(res.entries, np.uint32, (int(res.n_sparse), 3))
+            dense = np.zeros((P, 2 * W), np.uint32)
+            dense[ent[:, 0], ent[:, 1]] = ent[:, 2]
+            np.testing.assert_array_equal(dense, ref.codes)
+            assert len({(a, b) for a, b in ent[:, :2].tolist()}) == ent.shape[0]
+            live = _live(snap)
+            st = res.status
+            np.testing.assert_array_equal(view(st.used, np.int64, (R, m))[:, live], ref.used[:, live])
+            np.testing.assert_array_equal(view(st.used_cnt, np.int64, (m,))[live], ref.used_cnt[live])
+            np.testing.assert_array_equal(view(st.used_present, np.uint32, (m,))[live], ref.used_present[live])
+            np.testing.assert_array_equal(view(st.throttled, np.uint32, (m,))[live], ref.throttled[live])
+            np.testing.assert_array_equal(view(st.calc_thr, np.int64, (R, m)), ref.calc_thr)
+            np.testing.assert_array_equal(view(st.calc_present, np.uint32, (m,)), ref.calc_present)
+    for eng in engines:
+        eng.close()

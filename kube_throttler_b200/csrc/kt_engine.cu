@@ -53,6 +53,10 @@ struct PodStore {
   DevBuf c_dict;                   // request-value dictionaries of the same format
   DevBuf t_rows, t_labels, t_req, t_present, t_flags, t_ns, t_words;  // grow-only staging of row deltas / row gathers
   DevBuf bitmap;  // [n][Wp]
+  // The passes MAINTAIN the bitmap (and, for pending rows, the check codes): they store the words of each row's namespace list
+  // and nothing else.  Whatever can leave a stale non-zero word outside those lists -- new rows, a row delta, new tables, a
+  // buffer that was just allocated -- clears this flag; the next pass zeroes the buffers once before it runs.
+  bool bitmap_clean = false;
   void release() {
     labels.release(); req.release(); present.release(); flags.release(); ns.release(); bitmap.release(); roff.release(); winfo.release();
     roff_valid = false;
@@ -232,7 +236,7 @@ int recompile_tables(kt_ctx* c) {
   if ((rc = upload_vec(c, c->d_nsw_off, c->ht.nsw_off))) return rc;
   if ((rc = upload_vec(c, c->d_nsw_idx, c->ht.nsw_idx))) return rc;
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors may be rebuilt right after
-  for (auto& s : c->pods) s.roff_valid = false;  // row offsets point into the tables that were just replaced
+  for (auto& s : c->pods) s.roff_valid = s.bitmap_clean = false;  // row offsets point into the tables that were just replaced; word lists changed
   return KT_OK;
 }
 
@@ -276,6 +280,7 @@ PodView pod_view(const PodStore& s) {
   v.flags = s.flags.as<uint32_t>();
   v.ns = s.ns.as<int32_t>();
   v.n = s.n;
+  v.zero_fill = s.bitmap_clean ? 0 : 1;
   return v;
 }
 
@@ -627,7 +632,7 @@ int kt_upload_pods(kt_ctx* c, int kind, int64_t n, const int64_t* labels, const 
   if ((rc = upload(c, s.flags, flags, (size_t)n))) return rc;
   if ((rc = upload(c, s.ns, ns_id, (size_t)n))) return rc;
   s.n = n;
-  s.roff_valid = false;
+  s.roff_valid = s.bitmap_clean = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -662,7 +667,7 @@ int kt_upload_pods_compact(kt_ctx* c, int kind, int64_t n, int32_t val_bits, con
     KT_CUDA(c, cudaGetLastError());
   }
   s.n = n;
-  s.roff_valid = false;
+  s.roff_valid = s.bitmap_clean = false;
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   return KT_OK;
@@ -740,9 +745,10 @@ static int upload_pods_packed_locked(kt_ctx* c, int kind, int64_t n, const kt_pa
     KT_CUDA(c, cudaGetLastError());
     s.n = n;
     s.roff_valid = fuse;
+    s.bitmap_clean = false;
   } else {
     s.n = n;
-    s.roff_valid = false;
+    s.roff_valid = s.bitmap_clean = false;
   }
   c->evaluated = false;
   if (!c->async_uploads) KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
@@ -773,6 +779,7 @@ int kt_update_pod_rows(kt_ctx* c, int kind, int64_t k, const int64_t* rows, cons
   KT_CUDA(c, cudaGetLastError());
   // the delta keeps the store's row offsets current: only the scattered rows are translated again (same stream, after the scatter)
   if (s.roff_valid && (rc = translate_rows(c, s, k, s.t_rows.as<int64_t>()))) return rc;
+  s.bitmap_clean = false;  // a row that changed namespace (or stopped being counted) leaves words behind: the next pass zero-fills
   KT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers as soon as we return
   c->evaluated = false;
   return KT_OK;
@@ -905,9 +912,14 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   const int R = c->lim.n_resources, M = c->M, Wp = c->ht.Wp;
   PodStore& run = c->pods[KT_PODS_RUNNING];
   PodStore& pend = c->pods[KT_PODS_PENDING];
-  KT_CUDA(c, run.bitmap.reserve((size_t)run.n * Wp * 4 + 16));
-  KT_CUDA(c, pend.bitmap.reserve((size_t)pend.n * Wp * 4 + 16));
-  KT_CUDA(c, c->d_codes.reserve((size_t)pend.n * 2 * Wp * 4 + 16));
+  {
+    const void* b0 = run.bitmap.p; const void* b1 = pend.bitmap.p; const void* b2 = c->d_codes.p;
+    KT_CUDA(c, run.bitmap.reserve((size_t)run.n * Wp * 4 + 16));
+    KT_CUDA(c, pend.bitmap.reserve((size_t)pend.n * Wp * 4 + 16));
+    KT_CUDA(c, c->d_codes.reserve((size_t)pend.n * 2 * Wp * 4 + 16));
+    if (run.bitmap.p != b0) run.bitmap_clean = false;
+    if (pend.bitmap.p != b1 || c->d_codes.p != b2) pend.bitmap_clean = false;
+  }
   KT_CUDA(c, c->d_admit.reserve((size_t)pend.n + 16));
   if (do_rec && (rc = ensure_roff(c, run))) return rc;   // no-ops unless rows or tables changed since the last pass
   if (do_chk && (rc = ensure_roff(c, pend))) return rc;
@@ -999,6 +1011,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
       c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
     }
     KT_CUDA(c, dispatch_pass(c, a));
+    run.bitmap_clean = pend.bitmap_clean = true;  // zero-filled (if need be) and written by this pass: maintained from here on
     c->last_sync = (multi && !c->p2p_failed) ? a.sync : nullptr;  // only a pass that waits for OTHER ranks can time out
     c->last = kt_timing{};
     c->last.launches = 1;
@@ -1019,6 +1032,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
     const PodView pv = pod_view(run);
     const unsigned blocks = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
     KT_CUDA(c, dispatch_reconcile(c, pv, tb, px.mine, blocks));
+    run.bitmap_clean = true;
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -1041,6 +1055,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
     const unsigned blocks = (unsigned)((pend.n + kTileCheck - 1) / kTileCheck);
     if (c->sparse_cap) KT_CUDA(c, cudaMemsetAsync(c->d_sparse.p, 0, 4, c->stream));  // k_check appends; nobody in it can clear first
     KT_CUDA(c, dispatch_check(c, pv, tb, px, blocks, /*pdl=*/!tm && M > 0));
+    pend.bitmap_clean = true;
     ++launches;
   }
   if (tm) KT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));

@@ -35,7 +35,7 @@ namespace kt {
 #define KT_WAIT_MODE 1
 #endif
 #ifndef KT_PASS_THREADS    // resident threads per SM the fused pass is compiled for (register cap = 65536 / this)
-#define KT_PASS_THREADS 896
+#define KT_PASS_THREADS 768
 #endif
 #ifndef KT_SLOT_CAP        // upper bound on the per-CTA accumulator slots (shared memory vs straight-to-HBM atomics)
 #define KT_SLOT_CAP 32
@@ -51,6 +51,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 #define KT_STAGE_CHUNK 2
 #endif
 constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record values and sums a decide lane requests together
+constexpr int kPropose = 4;          // words a warp of a decide tile may propose to its CTA's staging table per round
 constexpr int kTraceRow = 16;        // u64 per CTA of the optional in-kernel trace: {ticket, sm, t_start, t_end, 12 stage stamps}
 
 // Word info of a pod row (k_translate_rows; valid for the tables it was computed with): the words whose namespace mask is
@@ -75,6 +76,8 @@ struct PodView {
   const uint32_t* flags;    // [n]
   const int32_t* ns;        // [n]
   int64_t n;
+  int zero_fill;            // 1: this pass zeroes the rows' bitmap (and code) rows itself -- the rows or the tables changed since the last
+                            // pass, stale words may sit outside the namespaces' word lists; 0: the rows are maintained word by word
 };
 
 struct TableView {
@@ -626,11 +629,16 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
       rp += pods.n;
     }
   }
-  {  // zero the tile's bitmap rows (contiguous: pod-major) and the CTA accumulators while the loads are in flight
-    const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
-    uint4* dst = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
-    const int nvec = (int)rows_here * (Wp / 4);
-    for (int i = tid; i < nvec; i += TILE) dst[i] = make_uint4(0, 0, 0, 0);
+  // The match bitmap is maintained, not rebuilt: a row can only ever be non-zero in the words of its namespace's list, so a
+  // pass stores exactly those words (zero or not) and never touches the rest of the row -- which the engine zeroed when the
+  // rows or the tables last changed (kt_engine.cu bitmap_clean).  Half of the pass's memory traffic used to be that zero-fill.
+  {  // the CTA accumulators are zeroed while the loads are in flight
+    if (pods.zero_fill) {  // first pass over new rows / new tables: the tile's bitmap rows (contiguous: pod-major) as well
+      const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
+      uint4* dst = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
+      const int nvec = (int)rows_here * (Wp / 4);
+      for (int i = tid; i < nvec; i += TILE) dst[i] = make_uint4(0, 0, 0, 0);
+    }
     for (int i = tid; i < S * R * 32; i += TILE) s_used[i] = 0ull;
     for (int i = tid; i < S * 32; i += TILE) { s_cnt[i] = 0u; s_pres[i] = 0u; }
     if (tid < S) s_key[tid] = -1;
@@ -663,10 +671,10 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   }
   s_present[tid] = present & ~KT_COUNT_BIT;
   stamp(5);
-  __syncthreads();  // bitmap zero-fill before the patch stores; accumulators initialised
+  __syncthreads();  // accumulators initialised
   stamp(6);
-  if (m0) bitmap[p * Wp + wc.w0] = m0;
-  if (m1) bitmap[p * Wp + wc.w1] = m1;
+  if (valid && wc.inl > 0) bitmap[p * Wp + wc.w0] = m0;
+  if (valid && wc.inl > 1) bitmap[p * Wp + wc.w1] = m1;
 
   unsigned long long* part_used = part;
   unsigned long long* part_pres = part + (size_t)R * tb.M;
@@ -684,7 +692,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
         word = kk == 0 ? m0 : m1;
       } else {
         word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
-        if (word) bitmap[p * Wp + w] = word;
+        bitmap[p * Wp + w] = word;
       }
       if (!alive) continue;
       while (word) {
@@ -716,7 +724,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
         word = k == 0 ? m0 : m1;
       } else {
         word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
-        if (word) bitmap[p * Wp + w] = word;
+        bitmap[p * Wp + w] = word;
       }
       ++k;
       cur = wc.at(tb, k);
@@ -1119,7 +1127,9 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
   load_rows<REG>(pods.roff, pods.n, pc, L, rows);
-  {
+  // neither the bitmap rows nor the code rows are zero-filled pass after pass: both are maintained word by word (see
+  // reconcile_tile) -- except on the first pass over new rows / new tables
+  if (pods.zero_fill) {
     const int64_t rows_here = pods.n - tile0 < TILE ? pods.n - tile0 : TILE;
     uint4* d0 = reinterpret_cast<uint4*>(bitmap + tile0 * Wp);
     uint4* d1 = reinterpret_cast<uint4*>(codes + tile0 * 2 * Wp);
@@ -1132,14 +1142,13 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   uint32_t m0 = 0, m1 = 0;  // the first two words: all their table gathers in flight together
   if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
   if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
-  __syncthreads();  // zero-fill before the patch stores (rows of a tile are written by all its lanes)
-  if (m0) bitmap[p * Wp + wc.w0] = m0;
-  if (m1) bitmap[p * Wp + wc.w1] = m1;
+  if (pods.zero_fill) __syncthreads();  // zero-fill before the word stores (rows of a tile are zeroed by all its lanes)
+  if (wc.inl > 0) bitmap[p * Wp + wc.w0] = m0;
+  if (wc.inl > 1) bitmap[p * Wp + wc.w1] = m1;
 #pragma unroll 1
   for (int k = wc.inl; k < wc.cnt; ++k) {
     const int w = wc.at(tb, k);
-    const uint32_t word = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
-    if (word) bitmap[p * Wp + w] = word;
+    bitmap[p * Wp + w] = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, w);
   }
 }
 
@@ -1241,8 +1250,9 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (b < 16) c0 |= code << (2 * b);
       else c1 |= code << (2 * (b - 16));
     }
-    if (c0) codes[p * 2 * Wp + 2 * w] = c0;
-    if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+    // unconditional: the code rows are maintained word by word -- a pair that was rejected by the previous pass and is not any
+    // more must read 0 again (codes can only be non-zero where match bits are, and those do not move between passes)
+    *reinterpret_cast<uint2*>(&codes[p * 2 * Wp + 2 * w]) = make_uint2(c0, c1);
     if (sp.count) {
       if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
       if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
@@ -1388,8 +1398,7 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
         if (b < 16) c0 |= code << (2 * b);
         else c1 |= code << (2 * (b - 16));
       }
-      if (c0) codes[p * 2 * Wp + 2 * w] = c0;
-      if (c1) codes[p * 2 * Wp + 2 * w + 1] = c1;
+      *reinterpret_cast<uint2*>(&codes[p * 2 * Wp + 2 * w]) = make_uint2(c0, c1);
       if (sp.count) {
         if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
         if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
@@ -1399,42 +1408,54 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
 
 #pragma unroll 1
   while (true) {
-    // 1. every warp's next (up to) KS words in its warp-uniform order, the lanes' match words fetched together; each word
-    // claims a staging slot of the CTA (open addressing; WARPS * KS slots always suffice for one round)
-    int pw[2], pslot[2];
-    uint32_t pword[2];
+    // 1. every warp's next words in its warp-uniform order -- up to kPropose of them, as long as the CTA's slot table has room
+    // (open addressing; a word another warp already claimed costs nothing).  Warps of one namespace share their slots, so a
+    // namespace with three or four words is still ONE round.
+    int pw[kPropose], pslot[kPropose];
+    uint32_t pword[kPropose];
+    {
+      int tk = k, tcur = cur;
+      uint32_t mine = 0;  // rounds q in which this lane's next word is the warp's
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      pw[q] = 0x7fffffff;
-      pslot[q] = -1;
-      pword[q] = 0;
-      if (q < KS) {
-        pw[q] = __reduce_min_sync(kFull, cur);
-        if (pw[q] != 0x7fffffff && cur == pw[q]) {
-          pword[q] = __ldcg(&bitmap[p * Wp + pw[q]]);
-          ++k;
-          cur = wc.at(tb, k);
+      for (int q = 0; q < kPropose; ++q) {
+        pw[q] = __reduce_min_sync(kFull, tcur);
+        pslot[q] = -1;
+        pword[q] = 0;
+        if (pw[q] != 0x7fffffff && tcur == pw[q]) {
+          mine |= 1u << q;
+          ++tk;
+          tcur = wc.at(tb, tk);
         }
       }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (q < KS && pw[q] != 0x7fffffff) {
-        const uint32_t any = __reduce_or_sync(kFull, pword[q]);
-        if (any) {
-          int slot = -1;
-          if (lane == 0) {
-            int sidx = (int)((unsigned)pw[q] % (unsigned)SLOTS);
+      int nq = 0;
+      if (lane == 0) {
 #pragma unroll 1
-            for (int probes = 0; probes < SLOTS; ++probes) {
-              int key = *reinterpret_cast<volatile int*>(&s_key[sidx]);
-              if (key == -1) key = atomicCAS(&s_key[sidx], -1, pw[q]);
-              if (key == -1 || key == pw[q]) { slot = sidx; break; }
-              sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
-            }
-            atomicOr(&s_any[slot], any);
+        for (; nq < kPropose && pw[nq] != 0x7fffffff; ++nq) {
+          int sidx = (int)((unsigned)pw[nq] % (unsigned)SLOTS), got = -1;
+#pragma unroll 1
+          for (int probes = 0; probes < SLOTS; ++probes) {
+            int key = *reinterpret_cast<volatile int*>(&s_key[sidx]);
+            if (key == -1) key = atomicCAS(&s_key[sidx], -1, pw[nq]);
+            if (key == -1 || key == pw[nq]) { got = sidx; break; }
+            sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
           }
-          pslot[q] = __shfl_sync(kFull, slot, 0);
+          if (got < 0) break;  // table full: the rest waits for the next round
+          pslot[nq] = got;
+        }
+      }
+      nq = __shfl_sync(kFull, nq, 0);
+#pragma unroll
+      for (int q = 0; q < kPropose; ++q) {
+        pslot[q] = __shfl_sync(kFull, pslot[q], 0);
+        if (q < nq && ((mine >> q) & 1)) pword[q] = __ldcg(&bitmap[p * Wp + pw[q]]);  // all of the lane's words in flight together
+      }
+      k += __popc(mine & ((1u << nq) - 1u));
+      cur = wc.at(tb, k);
+#pragma unroll
+      for (int q = 0; q < kPropose; ++q) {
+        if (q < nq) {
+          const uint32_t any = __reduce_or_sync(kFull, pword[q]);
+          if (lane == 0 && any) atomicOr(&s_any[pslot[q]], any);
         }
       }
     }
@@ -1453,8 +1474,8 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
     stamp(7);
     // 3. every lane decides its own pairs
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (q < KS && pword[q] && pslot[q] >= 0) decide_word(pword[q], pw[q], s_chk + (size_t)pslot[q] * 32 * rec);
+    for (int q = 0; q < kPropose; ++q)
+      if (pword[q] && pslot[q] >= 0) decide_word(pword[q], pw[q], s_chk + (size_t)pslot[q] * 32 * rec);
     const int more = __syncthreads_or(cur != 0x7fffffff);  // pods with more words than fit one round (ClusterThrottle-heavy namespaces)
     if (!more) break;
     if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }

@@ -285,6 +285,19 @@ int kt_set_reserved(kt_ctx* ctx, const int64_t* reserved /*[R][m]*/,
  * the context stream unless a getter is called; kt_sync() waits. */
 int kt_evaluate(kt_ctx* ctx, int64_t now_unix_ns, uint32_t flags);
 
+/* ---- queue-ordered greedy admission ------------------------------------------------ */
+/* The scheduler admits one pod per cycle: PreFilter, then -- on Success -- Reserve, so that every admitted pod raises the
+ * reservations the next one is checked against (plugin.go:148-238, reserved_resource_amounts.go:66-136).  kt_admit_queue runs
+ * that sequence for the pending rows [first, first + count) taken IN ROW ORDER as one sorted queue, entirely on the device:
+ * per-throttle prefix sums over the requests of the admitted pods before each pod, iterated to the fixpoint (see
+ * csrc/kt_admit.cuh; a handful of rounds, each costing the host one 8-byte read).  PreFilter's view applies: the observed status
+ * (kt_upload_status) + the uploaded reservations (kt_set_reserved), isThrottledOnEqual from `flags` (KT_EVAL_ON_EQUAL or 0).
+ * Afterwards admit[row] says which rows were admitted and codes[row] holds the 2-bit codes each REJECTED row saw at its turn
+ * (kt_get_check / kt_get_check_rows); the pending match rows (kt_get_match_rows) name the throttles an admitted pod must be
+ * reserved on by the caller's reservation cache.  Requests must be non-negative (the fixpoint relies on the checks being
+ * monotone in the reserved amounts). */
+int kt_admit_queue(kt_ctx* ctx, int64_t first, int64_t count, uint32_t flags, int32_t* rounds, int64_t* admitted);
+
 /* ---- one end-to-end step in one call --------------------------------------------- */
 /* A caller that hands over a fresh snapshot every pass (host buffers in, results out) pays for every boundary crossing and
  * every stream synchronisation.  kt_step_submit queues ONE whole step on the context's stream -- the packed pod rows of

@@ -44,7 +44,7 @@ EXPORTS = [
     "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_sync", "kt_enable_timing",
     "kt_enable_trace", "kt_get_trace", "kt_host_alloc", "kt_host_alloc_upload", "kt_host_free", "kt_upload_pods", "kt_upload_pods_compact", "kt_upload_pods_packed", "kt_set_async_uploads", "kt_update_pod_rows", "kt_upload_namespaces",
     "kt_upload_throttles", "kt_upload_status", "kt_set_reserved", "kt_evaluate", "kt_get_reconcile",
-    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_check_rows", "kt_get_changed", "kt_get_reconcile_rows", "kt_step_submit", "kt_step_wait", "kt_get_timing", "kt_comm_unique_id",
+    "kt_match_words", "kt_get_match_bitmap", "kt_get_match_rows", "kt_get_check", "kt_set_sparse_check", "kt_get_check_sparse", "kt_get_check_rows", "kt_get_changed", "kt_get_reconcile_rows", "kt_step_submit", "kt_step_wait", "kt_admit_queue", "kt_get_timing", "kt_comm_unique_id",
     "kt_comm_init", "kt_comm_destroy", "kt_debug_compile_tables",
 ]
 
@@ -83,6 +83,7 @@ def lib():
         L.kt_get_check_sparse.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.kt_step_submit.argtypes = [vp, C.c_int64, C.POINTER(abi.PackedPodsStruct), C.c_int64, C.POINTER(abi.PackedPodsStruct), C.c_int64, C.c_uint32]
         L.kt_step_wait.argtypes = [vp, C.POINTER(abi.StepResult)]
+        L.kt_admit_queue.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.kt_get_check_rows.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.kt_get_changed.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64), vp]
         L.kt_get_reconcile_rows.argtypes = [vp, C.c_int64, vp, C.POINTER(abi.ReconcileOut)]
@@ -309,6 +310,12 @@ class Engine:
         res = abi.StepResult()
         self._ck(self._L.kt_step_wait(self._h, C.byref(res)))
         return res
+
+    def admit_queue(self, first: int, count: int, flags: int = 0):
+        """Queue-ordered greedy admission of the pending rows [first, first + count) on the device: (rounds, admitted)."""
+        rounds, admitted = C.c_int32(0), C.c_int64(0)
+        self._ck(self._L.kt_admit_queue(self._h, first, count, flags, C.byref(rounds), C.byref(admitted)))
+        return int(rounds.value), int(admitted.value)
 
     def get_check_rows(self, rows: np.ndarray):
         """(codes[k][2W], admit[k]) of the listed pending rows."""

@@ -14,6 +14,7 @@
 
 #include "../../include/kt_b200.h"
 #include "kt_kernels.cuh"
+#include "kt_admit.cuh"
 #include "kt_tables.h"
 
 namespace {
@@ -151,6 +152,7 @@ struct kt_ctx {
   DevBuf d_changed;  // device-side status diff: {count[2] u32 by pass parity, pad to 16 B, idx[M] i32, flag[M] u8}
   unsigned diff_parity = 0;
   bool have_diff = false;  // the last pass produced a diff (an observed status was uploaded)
+  DevBuf d_adm_cnt2, d_adm_off, d_adm_pod, d_adm_state, d_adm_fail, d_adm_counters;  // kt_admit_queue (kt_admit.cuh)
   DevBuf d_pre;    // [M] pre-records, finalize tiles -> decide tiles (kt_kernels.cuh pre_record_bytes)
   // per-throttle outputs of the reconcile half: ONE device block (and one pinned host mirror) so that kt_get_reconcile
   // is a single D2H copy; o_off[i] = byte offset of {used, used_cnt, calc_thr, calc_cnt, used_present, throttled,
@@ -531,7 +533,8 @@ void kt_destroy(kt_ctx* c) {
                    &c->d_thr_present, &c->d_thr_cnt, &c->d_ovr_off, &c->d_ovr_begin, &c->d_ovr_end, &c->d_ovr_flags, &c->d_ovr_thr,
                    &c->d_ovr_present, &c->d_ovr_cnt, &c->d_st_calculated, &c->d_st_calc_thr, &c->d_st_calc_present, &c->d_st_calc_cnt,
                    &c->d_st_used, &c->d_st_used_present, &c->d_st_used_cnt, &c->d_st_throttled, &c->d_reserved, &c->d_reserved_present,
-                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_changed, &c->d_out, &c->d_codes, &c->d_admit};
+                   &c->d_reserved_cnt, &c->d_part, &c->d_sync, &c->d_trace, &c->d_pre, &c->d_changed, &c->d_adm_cnt2, &c->d_adm_off, &c->d_adm_pod,
+                   &c->d_adm_state, &c->d_adm_fail, &c->d_adm_counters, &c->d_out, &c->d_codes, &c->d_admit};
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_step) cudaFreeHost(c->h_step);
   if (c->ev_step) cudaEventDestroy(c->ev_step);
@@ -1062,6 +1065,70 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   c->last = kt_timing{};
   c->last.launches = launches;
   c->evaluated = true;
+  return KT_OK;
+}
+
+// ---- queue-ordered greedy admission on the device (kt_admit.cuh) ----------------------------------------------------
+int kt_admit_queue(kt_ctx* c, int64_t first, int64_t count, uint32_t flags, int32_t* rounds_out, int64_t* admitted_out) {
+  if (!c || first < 0 || count < 0) return KT_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->have_throttles) return fail(c, KT_ERR_STATE, "kt_admit_queue before kt_upload_throttles");
+  if (!c->have_status) return fail(c, KT_ERR_STATE, "kt_admit_queue checks against the observed status: kt_upload_status first");
+  PodStore& pend = c->pods[KT_PODS_PENDING];
+  if (first + count > pend.n) return fail(c, KT_ERR_INVALID, "queue rows [%lld, %lld) outside the pending table (%lld rows)", (long long)first, (long long)(first + count), (long long)pend.n);
+  // 1. one pending-only pass: affectedThrottles rows, pre-records (PreFilter's view: observed status + reservations); its
+  // order-free codes are overwritten below for the queue rows
+  int rc = evaluate_locked(c, 0, KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE | (flags & KT_EVAL_ON_EQUAL));
+  if (rc) return rc;
+  if (rounds_out) *rounds_out = 0;
+  if (admitted_out) *admitted_out = 0;
+  if (count == 0 || c->M == 0) return KT_OK;
+  const int R = c->lim.n_resources, M = c->M;
+  AdmitView a{};
+  a.first = first; a.count = count; a.req = pend.req.as<int64_t>(); a.present = pend.present.as<uint32_t>(); a.bitmap = pend.bitmap.as<uint32_t>();
+  a.n = pend.n; a.Wp = c->ht.Wp; a.W = c->ht.W; a.M = M; a.R = R; a.pre = c->d_pre.as<unsigned char>();
+  a.nblk = (int)((count + kAdmitBlock - 1) / kAdmitBlock);
+  KT_CUDA(c, c->d_adm_cnt2.reserve((size_t)a.nblk * M * 4 + 16));
+  KT_CUDA(c, c->d_adm_off.reserve((size_t)(M + 1) * 4 + 16));
+  KT_CUDA(c, c->d_adm_state.reserve((size_t)count + 16));
+  KT_CUDA(c, c->d_adm_fail.reserve((size_t)count * 4 + 16));
+  KT_CUDA(c, c->d_adm_counters.reserve(16));
+  a.cnt2 = c->d_adm_cnt2.as<int32_t>(); a.tl_off = c->d_adm_off.as<int32_t>(); a.state = c->d_adm_state.as<uint8_t>();
+  a.fail = c->d_adm_fail.as<uint32_t>(); a.counters = c->d_adm_counters.as<uint32_t>();
+  a.codes = c->d_codes.as<uint32_t>(); a.admit = c->d_admit.as<unsigned char>();
+  // 2. every throttle's toucher list (CSR over the queue, built once)
+  const unsigned warps = (unsigned)a.nblk * (unsigned)a.W;
+  k_admit_count<<<(warps + 3) / 4, 128, 0, c->stream>>>(a);
+  k_admit_lengths<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(a);
+  k_admit_starts<<<1, 1024, 0, c->stream>>>(a);
+  KT_CUDA(c, cudaGetLastError());
+  int32_t nnz = 0;
+  KT_CUDA(c, cudaMemcpyAsync(&nnz, a.tl_off + M, 4, cudaMemcpyDeviceToHost, c->stream));
+  KT_CUDA(c, cudaStreamSynchronize(c->stream));
+  KT_CUDA(c, c->d_adm_pod.reserve((size_t)nnz * 4 + 16));
+  a.tl_pod = c->d_adm_pod.as<int32_t>();
+  k_admit_fill<<<(warps + 3) / 4, 128, 0, c->stream>>>(a);
+  KT_CUDA(c, cudaMemsetAsync(a.state, 0, (size_t)count, c->stream));
+  // 3. rounds: until a round STARTED with nobody undecided (its loads were exact, and so are the codes it wrote)
+  uint32_t counters[2] = {(uint32_t)count, 0};
+  int rounds = 0;
+  while (true) {
+    const uint32_t undecided_before = counters[0];
+    k_admit_begin<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(a);
+    const unsigned blocks = (unsigned)((M + 3) / 4);
+    if (R <= 4) k_admit_round<4><<<blocks, 128, 0, c->stream>>>(a);
+    else if (R <= 8) k_admit_round<8><<<blocks, 128, 0, c->stream>>>(a);
+    else k_admit_round<32><<<blocks, 128, 0, c->stream>>>(a);
+    k_admit_update<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(a);
+    KT_CUDA(c, cudaGetLastError());
+    KT_CUDA(c, cudaMemcpyAsync(counters, a.counters, 8, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(c, cudaStreamSynchronize(c->stream));
+    ++rounds;
+    if (undecided_before == 0) break;
+    if (rounds > count + 2) return fail(c, KT_ERR_STATE, "kt_admit_queue did not converge (negative requests in the queue?)");
+  }
+  if (rounds_out) *rounds_out = rounds;
+  if (admitted_out) *admitted_out = counters[1];
   return KT_OK;
 }
 

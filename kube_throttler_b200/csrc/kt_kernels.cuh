@@ -118,7 +118,7 @@ struct WordCursor {
 };
 
 #ifndef KT_SCATTER_WORDS  // a warp whose lanes start in more distinct words than this takes the per-lane paths
-#define KT_SCATTER_WORDS 6
+#define KT_SCATTER_WORDS 32  // 32 = never: measured slower than the rounds at C2 in arrival order (profiles/README.md r2); the product keeps rows clustered (kt_host.cc row arenas)
 #endif
 // Do the lanes of this warp live in many different namespaces (rows in arrival order)?  Judged by their first words.
 __device__ __forceinline__ bool warp_is_scattered(const WordCursor& wc) {

@@ -333,7 +333,9 @@ int ensure_window(kt_ctx* c, size_t part_bytes) {
   mine.pid = (long long)getpid();
   mine.device = c->device;
   void* w = nullptr;
-  if (cudaMalloc(&w, kWinHeader + 4 * want) == cudaSuccess && cudaMemset(w, 0, kWinHeader + 4 * want) == cudaSuccess &&
+  // [header | this rank's sums x2 parities | all-rank totals x2 | slots x2 parities x nranks: 16 bytes per value (two tagged words)]
+  const size_t win_bytes = kWinHeader + 4 * want + 2 * (size_t)c->nranks * 2 * want;
+  if (cudaMalloc(&w, win_bytes) == cudaSuccess && cudaMemset(w, 0, win_bytes) == cudaSuccess &&
       cudaIpcGetMemHandle(&mine.handle, w) == cudaSuccess) {
     mine.ok = 1;
     mine.ptr = (unsigned long long)w;
@@ -965,7 +967,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   if (do_rec) c->part_parity ^= 1u;
   PartExchange px{};
   px.mine = px.total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)c->part_parity * c->part_stride);
-  px.zero_mine = px.zero_total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
+  px.zero_mine = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
   px.sync = c->d_sync.as<PassSync>();
   px.rank = c->rank;
 
@@ -976,22 +978,25 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   if (whole && multi) {
     if ((rc = ensure_window(c, (size_t)(2 * R + 1) * M * 8))) return rc;
     if (!c->p2p_failed) {
-      const unsigned epoch = ++c->epoch;
+      unsigned epoch = ++c->epoch;
+      if (epoch == 0) epoch = c->epoch = 1;  // 0 is what an untouched slot carries
       const size_t mine_off = kWinHeader + (size_t)(epoch & 1) * c->win_part_bytes, zmine_off = kWinHeader + (size_t)((epoch + 1) & 1) * c->win_part_bytes;
-      const size_t total_off = mine_off + 2 * c->win_part_bytes, ztotal_off = zmine_off + 2 * c->win_part_bytes;
+      const size_t total_off = mine_off + 2 * c->win_part_bytes;
+      const size_t slots_off = kWinHeader + 4 * c->win_part_bytes + (size_t)(epoch & 1) * c->nranks * 2 * c->win_part_bytes;
       unsigned char* base = reinterpret_cast<unsigned char*>(c->win);
       px.sync = reinterpret_cast<PassSync*>(base);
       px.mine = reinterpret_cast<unsigned long long*>(base + mine_off);
       px.total = reinterpret_cast<unsigned long long*>(base + total_off);
       px.zero_mine = reinterpret_cast<unsigned long long*>(base + zmine_off);
-      px.zero_total = reinterpret_cast<unsigned long long*>(base + ztotal_off);
+      px.slots = reinterpret_cast<unsigned long long*>(base + slots_off);
+      px.len = (unsigned)((2 * R + 1) * M);
       px.epoch = epoch;
       px.npeers = 0;
       for (int r = 0; r < c->nranks; ++r) {
         if (r == c->rank) continue;
         unsigned char* pb = reinterpret_cast<unsigned char*>(c->peer_win[r]);
-        px.peer_total[px.npeers] = reinterpret_cast<unsigned long long*>(pb + total_off);
-        px.peer_sync[px.npeers] = reinterpret_cast<PassSync*>(pb);
+        px.peer_slots[px.npeers] = reinterpret_cast<unsigned long long*>(pb + slots_off);
+        px.peer_rank[px.npeers] = r;
         ++px.npeers;
       }
     }
@@ -1026,7 +1031,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
   if (px.npeers > 0) {  // the window was set up but the one-launch pass is not taken after all: this rank's own buffers
     px = PartExchange{};
     px.mine = px.total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)c->part_parity * c->part_stride);
-    px.zero_mine = px.zero_total = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
+    px.zero_mine = reinterpret_cast<unsigned long long*>(c->d_part.as<unsigned char>() + (size_t)(c->part_parity ^ 1u) * c->part_stride);
     px.sync = c->d_sync.as<PassSync>();
     px.rank = c->rank;
   }

@@ -199,13 +199,10 @@ struct PassSync {
   unsigned rec_done;    // reconcile tiles finished (their REDs are performed at L2)
   unsigned prep_done;   // finalize tiles that have written their throttles' pre-records (nothing to wait for: early)
   unsigned match_done;  // pending-match tiles finished (affectedThrottles rows written)
-  unsigned pushed;      // multi-GPU: finalize tiles of this rank that have added their partial sums into every rank's totals
+  unsigned tot_done;    // multi-GPU: finalize tiles of this rank that have written the all-rank totals of their throttles
   unsigned exited;      // CTAs that are done with everything; the last one re-arms the counters
   unsigned error;       // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
   unsigned pad;
-  // multi-GPU, never re-armed (pass numbers only grow): flag[src] = last pass whose partial sums rank `src` has added into THIS
-  // rank's totals -- written over NVLink by src's last finalize tile, polled locally
-  unsigned flag[8];
 };
 constexpr int kPassSyncRearm = 6;  // leading counters the last CTA out (or the host, after a timed-out pass) zeroes
 // Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as one
@@ -287,29 +284,48 @@ __device__ __forceinline__ void cta_wait_at_least(const unsigned* counter, unsig
 // may start adding into the other buffer while readers of this one are still at work, and every pass leaves the OTHER
 // parity's buffers zeroed for its successor (they were last read one whole pass ago).
 // Single GPU / NCCL path: total == mine (NCCL all-reduces in place), no peers.
-// Peer path: the all-reduce is a PUSH inside the pass -- once this rank's reconcile tiles are done, its finalize tiles add
-// its partial sums into the `total` buffer of EVERY rank (red.add over NVLink, posted, no round trip) and the last of them
-// raises flag[rank] everywhere; a reader of `total` waits, locally, until all ranks' flags carry this pass's number.
+// Peer path: the all-reduce happens inside the pass, in the finalize tiles, without a single fence on the wire.  Once this
+// rank's reconcile tiles are done, the lane that owns (throttle, field) SENDS its 64-bit partial sum to every peer as two
+// 8-byte words {low half | pass number << 32} {high half | pass number << 32} into the slot that peer keeps for (this rank,
+// throttle, field) -- plain posted stores over NVLink, each word atomic, each carrying its own "valid" tag -- then polls, in
+// its OWN memory, the slots the peers write for the same (throttle, field), adds up, and stores the total locally.  The
+// decide tiles wait for a local counter of finished finalize tiles.  (The low-latency protocol of collective libraries:
+// data and flag travel in the same word, so neither side needs a system-scope fence or a round trip.)
 struct PartExchange {
   unsigned long long* mine;        // this rank's partial sums of this pass (reconcile tiles RED here)
   unsigned long long* total;       // sums over all ranks (what decide / status read)
   unsigned long long* zero_mine;   // other parity: left zeroed for the next pass
-  unsigned long long* zero_total;
-  unsigned long long* peer_total[7];
-  PassSync* peer_sync[7];
-  PassSync* sync;                  // this rank's counters and flags
+  unsigned long long* slots;       // [nranks][len][2] what the peers send THIS rank for this pass parity (slot of rank r at r * len * 2)
+  unsigned long long* peer_slots[7];  // the same array of peer i (mapped over NVLink)
+  int peer_rank[7];
+  PassSync* sync;                  // this rank's counters
   int npeers, rank;
-  unsigned epoch;                  // this pass's number
+  unsigned len;                    // (2R+1) * M values per rank
+  unsigned epoch;                  // this pass's number (never 0)
 };
 
-__device__ __forceinline__ void red_add_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// one 64-bit value as two self-validating words
+__device__ __forceinline__ void ll_send(unsigned long long* slot, unsigned long long v, unsigned epoch) {
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  st_relaxed_sys_u64(slot, (v & 0xffffffffull) | tag);
+  st_relaxed_sys_u64(slot + 1, (v >> 32) | tag);
+}
+__device__ __forceinline__ unsigned long long ll_recv(const unsigned long long* slot, unsigned epoch, unsigned* error_flag) {
+  unsigned long long w0 = 0, w1 = 0;
+  spin_until([&] {
+    w0 = ld_relaxed_sys_u64(slot);
+    w1 = ld_relaxed_sys_u64(slot + 1);
+    return (unsigned)(w0 >> 32) == epoch && (unsigned)(w1 >> 32) == epoch;
+  }, error_flag, 20);
+  return (w0 & 0xffffffffull) | (w1 << 32);
 }
 
 // How a dependent role waits for its producer: programmatic dependent launch between separate kernels ...
@@ -319,40 +335,24 @@ struct PdlSync {
   __device__ __forceinline__ void wait_matched() const {}   // same CTA: a barrier already ordered the rows
   __device__ __forceinline__ void wait_prepped() const { pdl_wait_primary(); }  // k_check's primary is k_finalize: complete, and everything before it
   __device__ __forceinline__ void signal_prepped() const {}
-  __device__ __forceinline__ void exchange_done(const PartExchange&) const {}
+  __device__ __forceinline__ void signal_totals() const {}
+  __device__ __forceinline__ unsigned* error_flag() const { return nullptr; }
 };
-// ... or counters inside the one fused kernel (plus the ranks' flags when the sums are exchanged over NVLink)
+// ... or counters inside the one fused kernel
 struct FlagSync {
   PassSync* s;
   unsigned n_rec, n_fin, n_match;
   __device__ __forceinline__ void wait_reconciled() const { cta_wait_at_least(&s->rec_done, n_rec, &s->error); }
   // the sums of every rank are in px.total
   __device__ __forceinline__ void wait_totals(const PartExchange& px) const {
-    if (px.npeers == 0) { wait_reconciled(); return; }
-    if (threadIdx.x == 0) {
-      for (int src = 0; src <= px.npeers; ++src) {
-        const unsigned* f = &s->flag[src];
-        spin_until([&] { return (int)(poll_gpu(f) - px.epoch) >= 0; }, &s->error, 40);  // written remotely, polled in local memory
-        acquire_sys(f);  // pass numbers only grow
-      }
-    }
-    __syncthreads();
+    if (px.npeers == 0) wait_reconciled();
+    else cta_wait_at_least(&s->tot_done, n_fin, &s->error);
   }
   __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match, &s->error); }
   __device__ __forceinline__ void wait_prepped() const { cta_wait_at_least(&s->prep_done, n_fin, &s->error); }
   __device__ __forceinline__ void signal_prepped() const { cta_signal(&s->prep_done); }
-  // this finalize tile has issued its adds into every rank's totals: once ALL of this rank's tiles have, the flags go up
-  __device__ __forceinline__ void exchange_done(const PartExchange& px) const {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();  // this CTA's remote adds are performed before the count below can be observed
-      if (atomicAdd(&s->pushed, 1u) == n_fin - 1) {
-        __threadfence_system();  // ... and, through the count, every other tile's
-        for (int i = 0; i < px.npeers; ++i) st_release_sys_u32(&px.peer_sync[i]->flag[px.rank], px.epoch);
-        st_release_sys_u32(&s->flag[px.rank], px.epoch);
-      }
-    }
-  }
+  __device__ __forceinline__ void signal_totals() const { cta_signal(&s->tot_done); }
+  __device__ __forceinline__ unsigned* error_flag() const { return &s->error; }
 };
 
 // ---- label -> table row ---------------------------------------------------------------------------
@@ -906,10 +906,8 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   if (is_res) {
     px.zero_mine[col] = 0ull;
     px.zero_mine[i_has] = 0ull;
-    if (px.npeers > 0) { px.zero_total[col] = 0ull; px.zero_total[i_has] = 0ull; }
   } else if (is_cnt) {
     px.zero_mine[i_val] = 0ull;
-    if (px.npeers > 0) px.zero_total[i_val] = 0ull;
   }
 
   // ---- CalculateThreshold(now): merged active overrides REPLACE spec.threshold; per resource name the first active
@@ -997,32 +995,31 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   // all-reduce happens right here, as a push: the lane adds its value into every rank's totals ----
   long long used_val = 0;
   bool used_has = false;
-  if (px.npeers > 0) {
-    if (is_res || is_cnt) {
-      const unsigned long long v = __ldcg(&px.mine[i_val]);
-      const unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
-      if (v) {
-        atomicAdd(&px.total[i_val], v);
-#pragma unroll
-        for (int i = 0; i < 7; ++i)
-          if (i < px.npeers) red_add_sys_u64(&px.peer_total[i][i_val], v);
-      }
-      if (h) {  // presence travels as a flag: any rank that saw the key stores the same 1
-        px.total[i_has] = 1ull;
-#pragma unroll
-        for (int i = 0; i < 7; ++i)
-          if (i < px.npeers) st_relaxed_sys_u64(&px.peer_total[i][i_has], 1ull);
-      }
-    }
-    sync.exchange_done(px);
-    sync.wait_totals(px);
-  }
   if (is_res || is_cnt) {
-    const unsigned long long v = __ldcg(&px.total[i_val]);
-    const unsigned long long h = is_res ? __ldcg(&px.total[i_has]) : 0ull;
+    unsigned long long v = __ldcg(&px.mine[i_val]);
+    unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
+    if (px.npeers > 0) {
+      // send first (to every peer), then receive: nobody waits for anybody before its own values are on the wire
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        if (i < px.npeers) {
+          unsigned long long* slot = px.peer_slots[i] + ((size_t)px.rank * px.len + i_val) * 2;
+          ll_send(slot, v, px.epoch);
+          if (is_res) ll_send(px.peer_slots[i] + ((size_t)px.rank * px.len + i_has) * 2, h, px.epoch);
+        }
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        if (i < px.npeers) {
+          v += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_val) * 2, px.epoch, sync.error_flag());
+          if (is_res) h += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_has) * 2, px.epoch, sync.error_flag());
+        }
+      px.total[i_val] = v;
+      if (is_res) px.total[i_has] = h;
+    }
     used_val = (long long)v;
     used_has = is_res ? h != 0ull : used_val > 0;  // Counts stays nil with zero counted pods (Q3)
   }
+  if (px.npeers > 0) sync.signal_totals();  // the decide tiles read px.total
   if (trace_row && threadIdx.x == 0 && used_val == 0x7fffffffffffffffll) trace_row[6] = 1;  // the loads have landed
   stamp(6);
   // status.throttled = calculatedThreshold.IsThrottled(used, onEqual=true) (throttle_controller.go:133)
@@ -1579,7 +1576,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       a.sync->rec_done = 0;
       a.sync->prep_done = 0;
       a.sync->match_done = 0;
-      a.sync->pushed = 0;
+      a.sync->tot_done = 0;
       a.sync->exited = 0;
     }
   }

@@ -33,7 +33,8 @@ for it in range(5):
     nm, nr, nf = int(roles[0]), int(roles[1]), int(roles[2])
     rec, fin, dec = rows[nm:nm + nr], rows[nm + nr:nm + nr + nf], rows[nm + nr + nf:]
     us = lambda a: (a.astype(np.float64) - float(t0)) / 1e3
-    print(f"[rank {rank}] pass {it}: launches {eng.timing().launches} span {us(rows[:,3]).max():.1f} us | reconcile end max {us(rec[:,3]).max():.1f} | finalize: waiting at {np.median(us(fin[:,4])):.1f}, "
-          f"all ranks ready {np.median(us(fin[:,5])):.1f} (max {us(fin[:,5]).max():.1f}), sums read {np.median(us(fin[:,6])):.1f}, done {us(fin[:,3]).max():.1f} | decide end max {us(dec[:,3]).max():.1f}", flush=True)
+    print(f"[rank {rank}] pass {it}: launches {eng.timing().launches} span {us(rows[:,3]).max():.1f} us | reconcile end max {us(rec[:,3]).max():.1f} | finalize: pre-records {np.median(us(fin[:,4])):.1f}, "
+          f"own reconcile seen {np.median(us(fin[:,5])):.1f} (max {us(fin[:,5]).max():.1f}), totals of all ranks read {np.median(us(fin[:,6])):.1f} (max {us(fin[:,6]).max():.1f}), done {us(fin[:,3]).max():.1f} | "
+          f"decide: words+pre staged {np.median(us(dec[:,5])):.1f}, sums seen {np.median(us(dec[:,6])):.1f} (max {us(dec[:,6]).max():.1f}), decided {np.median(us(dec[:,8])):.1f}, end max {us(dec[:,3]).max():.1f}", flush=True)
 eng.close()
 dist.destroy_process_group()

@@ -138,6 +138,31 @@ def make_snapshot(config: str, rank: int, world: int, rows_scale: int = 1):
     return snap
 
 
+def moved_bytes_estimate(snap, Wp):
+    """What the pass HAS to move in this implementation (an estimate, for the honest reading of the roofline): the resident pod
+    columns as stored (u32 row offsets instead of int64 labels, word info), the match / code words of each row's own namespace
+    list (the bitmaps are maintained word by word, zero words are never rewritten), per-throttle tables and sums."""
+    L, R, M = snap.L, snap.R, snap.m
+    n, p = snap.running.n, snap.pending.n
+    Lpad = (L + 7) // 8 * 8
+    row = 4 * Lpad + 8 * R + 16
+    words = 2  # words of a namespace's list, typical for namespaced Throttles
+    return (n + p) * row + (n + p) * words * 4 + p * (words * 8 + 1) + p * (8 * R + 12) + M * (16 * R + 48 + 8 * (2 * R + 1) * 2)
+
+
+def measured_traffic(config, rows_scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch from THIS round's `ncu --set full` capture, if the
+    committed summary (profiles/r2_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep) is for this workload."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        e = d.get(f"{config}x{rows_scale}")
+        if e:
+            return e["dram_bytes_read"] + e["dram_bytes_write"], e.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def algorithmic_bytes(snap, Wp):
     """bytes one pass must move, per kernel."""
     L, R, M = snap.L, snap.R, snap.m
@@ -360,7 +385,7 @@ def measure_config(bench, name, snap, steps, warmup, mode, peak, sharded=None, k
         "name": name, "workload": workload_label(name, snap, bench.world, sharded), "value": checks / (pass_ms * 1e-3), "unit": UNIT,
         "ms_per_step": pass_ms, "steps": steps, "launches_per_step": launches, "contexts_rotated": E,
         "roofline": {"bound": "hbm", "kernel": "k_pass", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes": ab["total"]},
+                     "algorithmic_bytes": ab["total"], "frac_moved": moved_bytes_estimate(snap, Wp) / (pass_ms * 1e-3) / 1e9 / peak},
     }
     if sharded:
         out["parallelism"] = sharded
@@ -634,7 +659,13 @@ def main():
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch needs ncu, which bench.py does not run: the
     # capture of the benched build is profiles/r2_ncu_pass_C2.txt (see profiles/README.md); null here rather than pasted.
     roofline = dict(head["roofline"])
-    roofline.update({"traffic": None, "traffic_source": "profiles/r2_ncu_pass_C2.txt (ncu --set full of this build; not measured inside bench.py)",
+    traffic, traffic_src = measured_traffic(args.config, args.rows_scale)
+    moved = moved_bytes_estimate(snap, Wp)
+    roofline.update({"traffic": traffic, "traffic_source": traffic_src or "none committed for this workload (ncu is not run inside bench.py)",
+                     "moved_bytes_estimate": moved, "frac_moved": moved / (pass_ms * 1e-3) / 1e9 / peak,
+                     "note": "achieved / frac use SURVEY.md 8(d)'s algorithmic bytes (dense bitmap written once per pass); the pass maintains its "
+                             "bitmaps word by word and stores int32 row offsets, so it moves fewer bytes than that -- frac_moved is the same time "
+                             "against the bytes it has to move (latency-bound at this size either way)",
                      "peak_source": peak_src, "kernel_ms": pass_ms, "timing": mode,
                      "other_timing": {"mode": other_mode, "ms_per_step": alt_ms, "frac": ab["total"] / (alt_ms * 1e-3) / 1e9 / peak},
                      "chained_kernel_ms": kernel_ms,

@@ -1688,6 +1688,66 @@ struct kth_plugin {
     return n;
   }
 
+  // ---- queue-ordered admission on the device (kt_admit_queue, csrc/kt_admit.cuh) ------------------------------
+  bool admit_queue_on_device_possible(const std::vector<PodObj>& queue) {
+    if (throttles.empty() || queue.empty()) return false;
+    if (!broken_valid) {
+      broken.clear();
+      for (size_t t = 0; t < throttles.size(); ++t)
+        if (throttles[t].live && !throttles[t].selector_error().empty()) broken.push_back(t);
+      broken_valid = true;
+    }
+    if (!broken.empty()) return false;  // some pod may run into a conversion error: framework.Error, no Reserve
+    for (auto& p : queue) {
+      const int id = ns_dict.find(p.ns);
+      if (id < 0 || !namespaces[(size_t)id].exists) return false;  // "namespace not found": Error as well
+      for (auto& kv : p.request)
+        if (kv.second.mant < 0) return false;  // the prefix-sum fixpoint needs the checks to be monotone in the reserved amounts
+    }
+    return true;
+  }
+  std::string admit_queue_on_device(const std::vector<PodObj>& queue) {
+    const size_t n = queue.size();
+    sync_all();
+    sync_status();
+    sync_reserved();
+    sync_pending(queue);
+    if (namespaces_dirty || throttles_dirty || status_dirty || reserved_dirty) { sync_all(); sync_status(); sync_reserved(); }
+    int32_t rounds = 0;
+    int64_t admitted_dev = 0;
+    check(kt_admit_queue(ctx, pend_capacity, (int64_t)n, 0, &rounds, &admitted_dev), "kt_admit_queue");
+    PendingResult r;
+    r.Wp = kt_match_words(ctx);
+    r.bitmap.assign(n * (size_t)r.Wp, 0);
+    r.codes.assign(n * 2 * (size_t)r.Wp, 0);
+    r.admit.assign(n, 1);
+    std::vector<int64_t> rows(n);
+    for (size_t i = 0; i < n; ++i) rows[i] = pend_capacity + (int64_t)i;
+    check(kt_get_check_rows(ctx, (int64_t)n, rows.data(), r.codes.data(), r.admit.data()), "kt_get_check_rows");
+    check(kt_get_match_rows(ctx, KT_PODS_PENDING, (int64_t)n, rows.data(), r.bitmap.data()), "kt_get_match_rows");
+    Writer out;
+    int admitted = 0;
+    std::vector<std::string> results(n);
+    for (size_t i = 0; i < n; ++i) {
+      Writer w;
+      prefilter_json(w, queue[i], r.row(i));
+      results[i] = w.out;
+      const bool success = w.out.compare(0, 17, "{\"code\":\"Success\"") == 0;
+      if (success != (r.admit[i] != 0)) fail("kt_admit_queue: the admit bit of " + queue[i].nn() + " contradicts its check codes");
+      if (!success) continue;
+      // Reserve (throttle_controller.go:271-292): ResourceAmountOfPod joins the reservation of every affected throttle -- what
+      // the device already counted for the pods behind this one
+      ++admitted;
+      for (int kind = 0; kind < 2; ++kind)
+        for (int t : affected(r.row(i), kind)) { cache[kind].add(throttles[(size_t)t].nn(), queue[i]); reservation_changed((size_t)t); }
+    }
+    if ((int64_t)admitted != admitted_dev) fail("kt_admit_queue: admitted count mismatch");
+    out.begin_obj().key("rounds").num(rounds).key("admitted").num(admitted).key("onDevice").raw("true").key("results").begin_arr();
+    for (size_t i = 0; i < n; ++i) out.begin_obj().key("pod").str(queue[i].nn()).key("round").num(0).key("preFilter").raw(results[i]).end_obj();
+    out.end_arr().end_obj();
+    return out.out;
+  }
+
   // ---- queue-ordered admission ----------------------------------------------------------------------------
   // The scheduler admits one pod per cycle: PreFilter, and on Success Reserve, so every admitted pod raises the reserved
   // amounts the NEXT pod is checked against (plugin.go:148-238).  For a sorted queue that sequence is reproduced exactly
@@ -1701,6 +1761,9 @@ struct kth_plugin {
     std::vector<PodObj> queue;
     for (auto& e : arr.arr) queue.push_back(pod_from(*e));
     const size_t n = queue.size();
+    if (admit_queue_on_device_possible(queue)) return admit_queue_on_device(queue);
+    // (below: the same semantics with host-orchestrated passes -- kept for queues the device fixpoint does not take: a pod that
+    // PreFilter answers with Error must not be reserved, and the fixpoint relies on non-negative requests)
     std::vector<std::string> results(n);
     std::vector<int> round_of(n, 0);
     std::vector<size_t> undecided(n);

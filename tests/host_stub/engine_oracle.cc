@@ -237,6 +237,54 @@ int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t* rows, uint32_t* codes
   }
   return KT_OK;
 }
+// Queue-ordered greedy admission, the slow and obvious way (the device runs a prefix-sum fixpoint, csrc/kt_admit.cuh): one
+// pod at a time in row order -- PreFilter against the observed status + the reservations so far, and on Success the pod's
+// ResourceAmountOfPod joins the reservation of every throttle it affects (plugin.go:148-238, reserved_resource_amounts.go:66-136).
+int kt_admit_queue(kt_ctx* c, int64_t first, int64_t count, uint32_t flags, int32_t* rounds, int64_t* admitted) {
+  if (!c || first < 0 || count < 0) return KT_ERR_INVALID;
+  if (!c->have_status) return fail(c, KT_ERR_STATE, "kt_admit_queue without kt_upload_status");
+  const Pods& pend = c->pods[KT_PODS_PENDING];
+  if (first + count > pend.n) return fail(c, KT_ERR_INVALID, "queue rows outside the pending table");
+  const size_t M = (size_t)c->m, R = (size_t)c->lim.n_resources, Wp = (size_t)c->words();
+  const uint32_t f = KT_EVAL_GIVEN_STATUS | KT_EVAL_SKIP_RECONCILE | (flags & KT_EVAL_ON_EQUAL);
+  const auto saved_r = c->reserved; const auto saved_p = c->reserved_present; const auto saved_c = c->reserved_cnt;
+  const bool saved_have = c->have_reserved;
+  if (!c->have_reserved) { c->reserved.assign(R * M, 0); c->reserved_present.assign(M, 0); c->reserved_cnt.assign(M, 0); }
+  c->have_reserved = true;
+  int rc = kt_evaluate(c, 0, f);
+  std::vector<uint32_t> codes = c->codes;
+  std::vector<uint8_t> admit = c->admit;
+  int64_t n_adm = 0;
+  bool dirty = false;
+  for (int64_t i = first; rc == KT_OK && i < first + count; ++i) {
+    if (dirty) { rc = kt_evaluate(c, 0, f); dirty = false; }
+    if (rc != KT_OK) break;
+    std::memcpy(&codes[(size_t)i * 2 * Wp], &c->codes[(size_t)i * 2 * Wp], 2 * Wp * 4);
+    admit[(size_t)i] = c->admit[(size_t)i];
+    if (!admit[(size_t)i]) continue;
+    ++n_adm;
+    const uint32_t present = pend.present[(size_t)i];
+    for (size_t w = 0; w < Wp; ++w)
+      for (uint32_t bits = c->pend_bitmap[(size_t)i * Wp + w]; bits; bits &= bits - 1) {
+        const size_t t = w * 32 + (size_t)__builtin_ctz(bits);
+        if (t >= M) continue;
+        for (size_t r = 0; r < R; ++r)
+          if ((present >> r) & 1) c->reserved[r * M + t] += pend.req[r * (size_t)pend.n + (size_t)i];
+        c->reserved_present[t] |= (present & (R >= 32 ? 0xffffffffu : ((1u << R) - 1u))) | KT_COUNT_BIT;
+        c->reserved_cnt[t] += 1;
+        dirty = true;
+      }
+  }
+  c->reserved = saved_r; c->reserved_present = saved_p; c->reserved_cnt = saved_c;
+  c->have_reserved = saved_have;
+  if (rc != KT_OK) return rc;
+  c->codes = codes;
+  c->admit = admit;
+  c->evaluated = true;
+  if (rounds) *rounds = 2;
+  if (admitted) *admitted = n_adm;
+  return KT_OK;
+}
 // the sparse list of the double: the non-zero code words of the dense rows, in row order
 int kt_set_sparse_check(kt_ctx* c, int64_t cap) {
   if (!c || cap < 0) return KT_ERR_INVALID;

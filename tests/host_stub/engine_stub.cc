@@ -67,6 +67,12 @@ int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t*, uint32_t* codes, uin
   return KT_OK;
 }
 int kt_set_sparse_check(kt_ctx*, int64_t) { return KT_OK; }
+int kt_admit_queue(kt_ctx*, int64_t, int64_t, uint32_t, int32_t* rounds, int64_t* admitted) {
+  if (!pass_ok()) return KT_ERR_CUDA;
+  if (rounds) *rounds = 1;
+  if (admitted) *admitted = 0;
+  return KT_OK;
+}
 int kt_get_check_sparse(kt_ctx* c, uint8_t* admit, uint32_t*, int64_t, int64_t* count) {
   if (!pass_ok()) return KT_ERR_CUDA;
   if (admit) std::memset(admit, 1, (size_t)c->n[KT_PODS_PENDING]);

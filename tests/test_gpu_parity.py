@@ -409,3 +409,61 @@ def test_step_api_equals_separate_calls(kt, oracle):
             np.testing.assert_array_equal(view(st.calc_present, np.uint32, (m,)), ref.calc_present)
     for eng in engines:
         eng.close()
+
+
+@pytest.mark.parametrize("kw", [dict(config="C2", m=200, n=4000, p=1000), dict(config="C3", m=120, n=3000, p=600, seed=9)])
+def test_device_queue_admission_equals_pod_by_pod(kt, oracle, kw):
+    """kt_admit_queue (per-throttle prefix sums over the admitted pods, iterated to the fixpoint on the device) gives
+    every pod of a 1000-pod queue the verdict and the check codes it gets when the queue is admitted ONE POD PER CYCLE --
+    PreFilter against observed status + reservations, Reserve on Success (plugin.go:148-238) -- emulated here with one oracle
+    evaluation per admitted pod."""
+    kw = dict(kw)
+    snap = synth.generate(kw.pop("config"), **kw)
+    fresh = oracle.columnar_evaluate(snap)
+    m, R, P = snap.m, snap.R, snap.pending.n
+    snap.status = dict(calculated=np.ones(m, np.uint8), calc_thr=fresh.calc_thr.copy(), calc_present=fresh.calc_present.copy(), calc_cnt=fresh.calc_cnt.copy(),
+                       used=fresh.used.copy(), used_present=fresh.used_present.copy(), used_cnt=fresh.used_cnt.copy(), throttled=fresh.throttled.copy())
+    # room for a few pods on most throttles, so that admissions and rejections interleave along the queue
+    rng = np.random.default_rng(3)
+    snap.thr = np.where(snap.thr > 0, fresh.used + (snap.thr * rng.uniform(0.0, 0.08, size=snap.thr.shape)).astype(np.int64) + 1, 0)
+    snap.thr_cnt = np.where(snap.thr_cnt > 0, fresh.used_cnt + rng.integers(0, 6, size=m), snap.thr_cnt)
+    snap.status["calc_thr"], snap.status["calc_cnt"] = snap.thr.copy(), snap.thr_cnt.copy()
+    snap.status["calc_present"] = snap.thr_present.copy()
+    snap.status["throttled"] = np.zeros(m, np.uint32)
+    snap.normalize()
+    flags = abi.EVAL_GIVEN_STATUS | abi.EVAL_SKIP_RECONCILE
+    eng = kt.Engine(snap.R, snap.L, snap.LN)
+    eng.upload_snapshot(snap)
+    rounds, admitted = eng.admit_queue(0, P)
+    got = eng.download()
+    eng.close()
+    # the reference sequence, one pod per cycle
+    W = got.words_per_row
+    base_reserved, base_present, base_cnt = snap.reserved.copy(), snap.reserved_present.copy(), snap.reserved_cnt.copy()
+    want_codes = np.zeros((P, 2 * W), np.uint32)
+    want_admit = np.zeros(P, np.uint8)
+    cur = oracle.columnar_evaluate(snap, flags, words_per_row=W)
+    bitmap = cur.pend_bitmap
+    rmask = np.uint32((1 << R) - 1)
+    n_adm = 0
+    for i in range(P):
+        want_codes[i], want_admit[i] = cur.codes[i], cur.admit[i]
+        if not cur.admit[i]:
+            continue
+        n_adm += 1
+        ts = np.nonzero(((bitmap[i][:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:m])[0]
+        if ts.size == 0:
+            continue
+        pres = snap.pending.present[i] & rmask
+        for r in range(R):
+            if (pres >> np.uint32(r)) & 1:
+                snap.reserved[r, ts] += snap.pending.req[r, i]
+        snap.reserved_present[ts] |= pres | abi.COUNT_BIT
+        snap.reserved_cnt[ts] += 1
+        snap.normalize()
+        cur = oracle.columnar_evaluate(snap, flags, words_per_row=W)
+    snap.reserved, snap.reserved_present, snap.reserved_cnt = base_reserved, base_present, base_cnt
+    np.testing.assert_array_equal(got.admit, want_admit)
+    np.testing.assert_array_equal(got.codes, want_codes)
+    assert admitted == n_adm and 0.05 * P < n_adm < 0.95 * P, (n_adm, P)  # not degenerate
+    assert 2 <= rounds <= 64, rounds

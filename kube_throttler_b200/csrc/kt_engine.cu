@@ -454,7 +454,7 @@ cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
   size_t smem = reconcile_smem_bytes(L, R, a.S, REG, kTileReconcile);
   const size_t smem_chk = check_smem_bytes(L, R, REG, kTileReconcile);
   if (smem_chk > smem) smem = smem_chk;
-  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
+  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin + a.n_prep, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }
 cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
@@ -1011,12 +1011,13 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
     a.n_rec = (unsigned)((run.n + kTileReconcile - 1) / kTileReconcile);
     a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
     a.n_chk = (unsigned)((pend.n + kTileReconcile - 1) / kTileReconcile);
+    a.n_prep = (a.n_fin + kPrepBatch - 1) / kPrepBatch;
     if (c->trace) {
-      const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;
+      const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin + a.n_prep;
       KT_CUDA(c, c->d_trace.reserve(rows * kTraceRow * 8));
       KT_CUDA(c, cudaMemsetAsync(c->d_trace.p, 0, rows * kTraceRow * 8, c->stream));
       a.trace = c->d_trace.as<unsigned long long>();
-      c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;
+      c->trace_roles[0] = a.n_prep + a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_fin; c->trace_roles[3] = a.n_chk;  // (prep tiles are counted with the match tiles)
     }
     KT_CUDA(c, dispatch_pass(c, a));
     run.bitmap_clean = pend.bitmap_clean = true;  // zero-filled (if need be) and written by this pass: maintained from here on

@@ -48,7 +48,7 @@ constexpr int kTileCheck = 64;       // pending pods per CTA
 constexpr int kMaxSlots = KT_SLOT_CAP;        // upper bound on the per-CTA accumulator slots (one per distinct 32-throttle word)
 constexpr uint32_t kFull = 0xffffffffu;
 #ifndef KT_STAGE_CHUNK
-#define KT_STAGE_CHUNK 2
+#define KT_STAGE_CHUNK 4
 #endif
 constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record values and sums a decide lane requests together
 constexpr int kPropose = 4;          // words a warp of a decide tile may propose to its CTA's staging table per round
@@ -876,10 +876,13 @@ struct __align__(16) PreHdr {
 constexpr uint32_t kPreLive = 1u, kPreE3 = 2u, kPreOnEqual = 4u, kPreGiven = 8u;
 __host__ __device__ inline size_t pre_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }
 
+constexpr unsigned kPrepBatch = 4;
+constexpr int kFinPrep = 1, kFinStatus = 2;  // the halves of a finalize tile: the fused pass runs them as separate tiles (prep first, so
+                                             // that nobody ever waits for pre-records), the chained k_finalize runs both
 template <class Sync>
 __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int R, int G, long long now, uint32_t eval_flags, const PartExchange& px,
                                               const ReconcileView& out, unsigned char* __restrict__ pre /* [M][pre_record_bytes(R)] */, int tile_index,
-                                              const Sync& sync, unsigned long long* trace_row = nullptr) {
+                                              const Sync& sync, unsigned long long* trace_row = nullptr, int halves = kFinPrep | kFinStatus) {
   // optional stage stamps (kt_enable_trace): [4] pre-records written; [5] this rank's reconcile tiles done; [6] sums of every
   // rank read; [7] status columns written
   auto stamp = [&](int k) {
@@ -902,12 +905,14 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
   const size_t i_val = is_res ? col : (size_t)2 * R * M + t;  // this lane's sum in a partial-sum buffer
   const size_t i_has = (size_t)(R + r) * M + t;               // resource lanes: its presence flag
 
-  // the other parity's buffers are left zeroed for the next pass -- before anything of this pass is signalled to anybody
-  if (is_res) {
-    px.zero_mine[col] = 0ull;
-    px.zero_mine[i_has] = 0ull;
-  } else if (is_cnt) {
-    px.zero_mine[i_val] = 0ull;
+  // the other parity's buffers are left zeroed for the next pass
+  if (halves & kFinStatus) {
+    if (is_res) {
+      px.zero_mine[col] = 0ull;
+      px.zero_mine[i_has] = 0ull;
+    } else if (is_cnt) {
+      px.zero_mine[i_val] = 0ull;
+    }
   }
 
   // ---- CalculateThreshold(now): merged active overrides REPLACE spec.threshold; per resource name the first active
@@ -966,8 +971,8 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     const uint32_t g = (__ballot_sync(kFull, pred) >> gbase) & gmask;
     return (g & rmask) | (((g >> R) & 1u) ? KT_COUNT_BIT : 0u);
   };
-  const uint32_t m_thr = group_mask(thr_has), m_base = group_mask(base_has), m_st = group_mask(g_st_thr);
-  {
+  if (halves & kFinPrep) {
+    const uint32_t m_thr = group_mask(thr_has), m_base = group_mask(base_has), m_st = group_mask(g_st_thr);
     unsigned char* rec = pre + (size_t)t * pre_record_bytes(R);
     long long* vals = reinterpret_cast<long long*>(rec + 16);  // thrv[R], base[R], thr_cnt, base_cnt
     if (is_res) {
@@ -985,9 +990,10 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
       vals[2 * R] = thr;
       vals[2 * R + 1] = base;
     }
+    sync.signal_prepped();
+    stamp(4);
+    if (!(halves & kFinStatus)) return;
   }
-  sync.signal_prepped();
-  stamp(4);
 
   sync.wait_reconciled();  // this rank's partial sums are complete and visible
   stamp(5);
@@ -1516,9 +1522,11 @@ struct PassArgs {
   long long now;
   uint32_t eval_flags;
   int L, R, S, G;
-  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match n_chk][reconcile n_rec][finalize n_fin][decide n_chk]; a tile only ever
-                                 // waits for SMALLER tickets (decide: match, finalize's prep half, reconcile -- with peers the finalize
-                                 // tiles' push) or for other GPUs, whose tiles are subject to the same order
+  unsigned n_prep;               // prep CTAs: each writes the pre-records of kPrepBatch finalize tiles' throttles
+  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [prep n_prep][match n_chk][reconcile n_rec][status n_fin][decide n_chk]; a tile only
+                                 // ever waits for SMALLER tickets (status: reconcile; decide: prep, match, reconcile -- with peers the status
+                                 // tiles' totals) or for other GPUs, whose tiles are subject to the same order.  The prep tiles come first
+                                 // and are gone within a few microseconds: nobody ever waits for a pre-record
   unsigned long long* trace;     // optional (kt_enable_trace): per CTA kTraceRow x u64 {ticket, sm, t_start, t_end, stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1546,9 +1554,14 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   __syncthreads();
   unsigned tile = s_ticket;
   const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
-  if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+  if (tile < a.n_prep) {  // pre-records: no dependencies, needed by every decide tile; few CTAs, so that match + reconcile tiles
+    for (unsigned j = 0; j < kPrepBatch; ++j) {  // still fit the first wave behind them
+      const unsigned ft = tile * kPrepBatch + j;
+      if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, nullptr, kFinPrep);
+    }
+  } else if ((tile -= a.n_prep) < a.n_chk) {  // no dependencies: early tickets, so that they are out of the way early
     // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
-    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
+    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;  // (tile: index within the role)
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
   } else if ((tile -= a.n_chk) < a.n_rec) {
@@ -1556,7 +1569,8 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
                                     a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_fin) {
-    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
+    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr,
+                  kFinStatus);
   } else {
     check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse,
                                       a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
@@ -1570,7 +1584,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       unsigned long long* row = a.trace + (size_t)s_ticket * kTraceRow;
       row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
     }
-    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
+    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin + a.n_prep;
     if (atomicAdd(&a.sync->exited, 1u) == total - 1) {
       a.sync->ticket = 0;
       a.sync->rec_done = 0;

@@ -368,6 +368,8 @@ struct ThrottleObj {
   bool st_thr_req_nil = true;
   ResAmount st_used;
   bool live = false;
+  bool host_dirty = true;  // applied since its last reconcile: the host-only parts of its status (messages, spec gauges) may differ even
+                           // when the device-side diff says its numbers do not
   bool metrics_pending = false;  // reconciled since its gauges were last written into the registry (see record_metrics)
   std::string nn() const { return ns + "/" + name; }
   std::string selector_error() const {  // the first podSelector that LabelSelectorAsSelector rejects
@@ -1136,13 +1138,31 @@ struct kth_plugin {
     Writer w;
     w.begin_obj();
     if (m == 0) { w.key("reconciled").num(0).key("changed").begin_arr().end_arr().key("requeueAfterNanos").begin_obj().end_obj().end_obj(); return w.out; }
+    // The informer copy of every status is on the device (sync_status: a no-op unless some status changed since the last
+    // upload), so the pass itself diffs what it computes against it (throttle_controller.go:157 DeepEqual): only the throttles it
+    // lists -- plus those applied since their last reconcile, whose host-only status parts may differ -- are looked at and
+    // downloaded below (the download and the host's work are proportional to what changed, not to M).
+    sync_status();
     check(kt_evaluate(ctx, clamp_ns(now.ns()), KT_EVAL_FRESH_STATUS | KT_EVAL_SKIP_CHECK), "kt_evaluate");
     const int R = lim.n_resources;
-    std::vector<int64_t> used((size_t)R * m), used_cnt(m), calc_thr((size_t)R * m), calc_cnt(m);
-    std::vector<uint32_t> used_present(m), throttled(m), calc_present(m);
-    std::vector<uint8_t> ovr_active(m);
+    std::vector<int32_t> todo_idx(m);
+    std::vector<int32_t> pos(m, -1);  // throttle column -> its row in the gathered status columns
+    size_t k = 0;
+    {
+      int64_t n_changed = 0;
+      check(kt_get_changed(ctx, todo_idx.data(), (int64_t)m, &n_changed, nullptr), "kt_get_changed");
+      std::vector<char> mark(m, 0);
+      for (int64_t i = 0; i < n_changed && i < (int64_t)m; ++i) mark[(size_t)todo_idx[(size_t)i]] = 1;
+      for (size_t t = 0; t < m; ++t)
+        if (throttles[t].host_dirty && throttles[t].live) mark[t] = 1;
+      for (size_t t = 0; t < m; ++t)
+        if (mark[t]) { pos[t] = (int32_t)k; todo_idx[k++] = (int32_t)t; }
+    }
+    std::vector<int64_t> used((size_t)R * std::max<size_t>(k, 1)), used_cnt(k), calc_thr((size_t)R * std::max<size_t>(k, 1)), calc_cnt(k);
+    std::vector<uint32_t> used_present(k), throttled(k), calc_present(k);
+    std::vector<uint8_t> ovr_active(k);
     kt_reconcile_out ro{used.data(), used_present.data(), used_cnt.data(), throttled.data(), calc_thr.data(), calc_present.data(), calc_cnt.data(), ovr_active.data()};
-    check(kt_get_reconcile(ctx, &ro), "kt_get_reconcile");
+    if (k) check(kt_get_reconcile_rows(ctx, (int64_t)k, todo_idx.data(), &ro), "kt_get_reconcile_rows");
     // pods that are reserved somewhere: their match rows decide what reconcile un-reserves (:135-155)
     std::vector<int64_t> rows;
     std::vector<std::string> row_pod;
@@ -1227,21 +1247,24 @@ struct kth_plugin {
       if (!o.live || o.throttler_name != name) continue;   // only responsible throttles are ever enqueued (:403-425)
       if (selector_fails[t]) continue;                      // affectedPods fails -> reconcile returns the error, status untouched
       ++reconciled;
+      const int32_t q = pos[t];  // >= 0: the device says its status changes (or the object was applied since its last reconcile)
+      if (q >= 0) {
+      o.host_dirty = false;
       ResAmount nu;  // used := ResourceAmount{}; used = used.Add(ResourceAmountOfPod(p)) ...
-      if (used_present[t] & KT_COUNT_BIT) {
+      if (used_present[q] & KT_COUNT_BIT) {
         nu.has_counts = true;
-        nu.pod = used_cnt[t];
+        nu.pod = used_cnt[q];
         nu.requests_nil = false;
         for (int r = 0; r < (int)cols.size(); ++r)
-          if ((used_present[t] >> r) & 1) nu.requests[r] = from_scale(r, used[(size_t)r * m + t]);
+          if ((used_present[q] >> r) & 1) nu.requests[r] = from_scale(r, used[(size_t)r * k + q]);
       }
       ResAmount nc;  // CalculateThreshold(now).Threshold
-      nc.has_counts = calc_present[t] & KT_COUNT_BIT;
-      nc.pod = nc.has_counts ? calc_cnt[t] : 0;
+      nc.has_counts = calc_present[q] & KT_COUNT_BIT;
+      nc.pod = nc.has_counts ? calc_cnt[q] : 0;
       nc.requests_nil = false;
       for (int r = 0; r < (int)cols.size(); ++r)
-        if ((calc_present[t] >> r) & 1) nc.requests[r] = from_scale(r, calc_thr[(size_t)r * m + t]);
-      if (!ovr_active[t]) nc = o.threshold;  // no active override: spec.threshold itself (keeps nil-ness and spelling)
+        if ((calc_present[q] >> r) & 1) nc.requests[r] = from_scale(r, calc_thr[(size_t)r * k + q]);
+      if (!ovr_active[q]) nc = o.threshold;  // no active override: spec.threshold itself (keeps nil-ness and spelling)
       const std::vector<std::string> msgs = override_messages(o);
       bool status_changed = false;
       if (!amount_equal(o.st_calc, nc) || o.st_messages != msgs) {  // Q6: otherwise the old calculatedAt is kept
@@ -1252,9 +1275,9 @@ struct kth_plugin {
         status_changed = true;
       }
       // newStatus.Throttled = CalculatedThreshold.Threshold.IsThrottled(Used, true): one entry per threshold resource
-      const bool thr_pod = throttled[t] & KT_COUNT_BIT;
+      const bool thr_pod = throttled[q] & KT_COUNT_BIT;
       std::map<int, bool> thr_req;
-      for (auto& kv : o.st_calc.requests) thr_req[kv.first] = (throttled[t] >> kv.first) & 1;
+      for (auto& kv : o.st_calc.requests) thr_req[kv.first] = (throttled[q] >> kv.first) & 1;
       const bool thr_nil = o.st_calc.requests.empty();
       if (thr_pod != o.st_thr_pod || thr_req != o.st_thr_req) status_changed = true;
       o.st_thr_pod = thr_pod;
@@ -1268,6 +1291,7 @@ struct kth_plugin {
         throttle_state_changed(t);  // PreFilter reads this status: cached verdicts of the pods it affects are void
         status_dirty = true;
       }
+      }  // (q >= 0)
       __int128 after = 0;
       if (next_override_happens_in(o, now, &after)) requeue.emplace_back(o.nn(), (long long)(after > INT64_MAX ? INT64_MAX : after));
       // unreserveAffectedPods: every affected pod the informer has observed leaves the reservation cache -- except, for a

@@ -876,7 +876,6 @@ struct __align__(16) PreHdr {
 constexpr uint32_t kPreLive = 1u, kPreE3 = 2u, kPreOnEqual = 4u, kPreGiven = 8u;
 __host__ __device__ inline size_t pre_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }
 
-constexpr unsigned kPrepBatch = 4;
 constexpr int kFinPrep = 1, kFinStatus = 2;  // the halves of a finalize tile: the fused pass runs them as separate tiles (prep first, so
                                              // that nobody ever waits for pre-records), the chained k_finalize runs both
 template <class Sync>
@@ -1522,11 +1521,9 @@ struct PassArgs {
   long long now;
   uint32_t eval_flags;
   int L, R, S, G;
-  unsigned n_prep;               // prep CTAs: each writes the pre-records of kPrepBatch finalize tiles' throttles
-  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [prep n_prep][match n_chk][reconcile n_rec][status n_fin][decide n_chk]; a tile only
-                                 // ever waits for SMALLER tickets (status: reconcile; decide: prep, match, reconcile -- with peers the status
-                                 // tiles' totals) or for other GPUs, whose tiles are subject to the same order.  The prep tiles come first
-                                 // and are gone within a few microseconds: nobody ever waits for a pre-record
+  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match (+ prep) n_chk][reconcile n_rec][status n_fin][decide n_chk]; a tile only
+                                 // ever waits for SMALLER tickets (status: reconcile; decide: match + prep, reconcile -- with peers the status
+                                 // tiles' totals) or for other GPUs, whose tiles are subject to the same order
   unsigned long long* trace;     // optional (kt_enable_trace): per CTA kTraceRow x u64 {ticket, sm, t_start, t_end, stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1554,12 +1551,12 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   __syncthreads();
   unsigned tile = s_ticket;
   const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
-  if (tile < a.n_prep) {  // pre-records: no dependencies, needed by every decide tile; few CTAs, so that match + reconcile tiles
-    for (unsigned j = 0; j < kPrepBatch; ++j) {  // still fit the first wave behind them
-      const unsigned ft = tile * kPrepBatch + j;
-      if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, nullptr, kFinPrep);
-    }
-  } else if ((tile -= a.n_prep) < a.n_chk) {  // no dependencies: early tickets, so that they are out of the way early
+  if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+    // The match tiles also write the pre-records (the prep half of the finalize tiles, spread over them): they hold the first
+    // tickets, so every pre-record exists a few microseconds into the pass and no decide tile ever waits for one -- without
+    // extra CTAs pushing reconcile tiles out of the first wave.
+    for (unsigned ft = tile; ft < a.n_fin; ft += a.n_chk)
+      finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, nullptr, kFinPrep);
     // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
     if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;  // (tile: index within the role)
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
@@ -1584,7 +1581,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       unsigned long long* row = a.trace + (size_t)s_ticket * kTraceRow;
       row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
     }
-    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin + a.n_prep;
+    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
     if (atomicAdd(&a.sync->exited, 1u) == total - 1) {
       a.sync->ticket = 0;
       a.sync->rec_done = 0;

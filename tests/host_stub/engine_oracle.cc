@@ -237,6 +237,52 @@ int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t* rows, uint32_t* codes
   }
   return KT_OK;
 }
+// Status diff of the last reconciling pass against the uploaded status, the obvious way (the device does it inside the pass).
+int kt_get_changed(kt_ctx* c, int32_t* idx, int64_t cap, int64_t* count, uint8_t* flags) {
+  if (!c || !count) return KT_ERR_INVALID;
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_changed before kt_evaluate");
+  if (!c->have_status) return fail(c, KT_ERR_STATE, "kt_get_changed without kt_upload_status");
+  const size_t M = (size_t)c->m, R = (size_t)c->lim.n_resources;
+  int64_t n = 0;
+  for (size_t t = 0; t < M; ++t) {
+    const bool live = (c->tflags[t] & KT_THR_RESPONSIBLE) && !(c->tflags[t] & KT_THR_SELECTOR_ERROR);
+    bool diff = false;
+    if (live) {
+      diff = !c->st_calculated[t] || c->o_used_present[t] != c->st_used_present[t] || c->o_throttled[t] != c->st_throttled[t] ||
+             c->o_calc_present[t] != c->st_calc_present[t];
+      if ((c->o_used_present[t] & KT_COUNT_BIT) && c->o_used_cnt[t] != c->st_used_cnt[t]) diff = true;
+      if ((c->o_calc_present[t] & KT_COUNT_BIT) && c->o_calc_cnt[t] != c->st_calc_cnt[t]) diff = true;
+      for (size_t r = 0; r < R; ++r) {
+        if (((c->o_used_present[t] >> r) & 1) && c->o_used[r * M + t] != c->st_used[r * M + t]) diff = true;
+        if (((c->o_calc_present[t] >> r) & 1) && c->o_calc_thr[r * M + t] != c->st_calc_thr[r * M + t]) diff = true;
+      }
+    }
+    if (flags) flags[t] = diff;
+    if (diff) { if (n < cap && idx) idx[n] = (int32_t)t; ++n; }
+  }
+  *count = n;
+  return KT_OK;
+}
+int kt_get_reconcile_rows(kt_ctx* c, int64_t k, const int32_t* idx, const kt_reconcile_out* o) {
+  if (!c || !o || k < 0 || (k > 0 && !idx)) return KT_ERR_INVALID;
+  if (!c->evaluated) return fail(c, KT_ERR_STATE, "kt_get_reconcile_rows before kt_evaluate");
+  const size_t M = (size_t)c->m, R = (size_t)c->lim.n_resources, K = (size_t)k;
+  for (size_t i = 0; i < K; ++i) {
+    const size_t t = (size_t)idx[i];
+    if (t >= M) return fail(c, KT_ERR_INVALID, "throttle out of range");
+    for (size_t r = 0; r < R; ++r) {
+      if (o->used) o->used[r * K + i] = c->o_used[r * M + t];
+      if (o->calc_thr) o->calc_thr[r * K + i] = c->o_calc_thr[r * M + t];
+    }
+    if (o->used_cnt) o->used_cnt[i] = c->o_used_cnt[t];
+    if (o->calc_cnt) o->calc_cnt[i] = c->o_calc_cnt[t];
+    if (o->used_present) o->used_present[i] = c->o_used_present[t];
+    if (o->throttled) o->throttled[i] = c->o_throttled[t];
+    if (o->calc_present) o->calc_present[i] = c->o_calc_present[t];
+    if (o->override_active) o->override_active[i] = c->o_ovr_active[t];
+  }
+  return KT_OK;
+}
 // Queue-ordered greedy admission, the slow and obvious way (the device runs a prefix-sum fixpoint, csrc/kt_admit.cuh): one
 // pod at a time in row order -- PreFilter against the observed status + the reservations so far, and on Success the pod's
 // ResourceAmountOfPod joins the reservation of every throttle it affects (plugin.go:148-238, reserved_resource_amounts.go:66-136).

@@ -67,6 +67,26 @@ int kt_get_check_rows(kt_ctx* c, int64_t k, const int64_t*, uint32_t* codes, uin
   return KT_OK;
 }
 int kt_set_sparse_check(kt_ctx*, int64_t) { return KT_OK; }
+int kt_get_changed(kt_ctx* c, int32_t* idx, int64_t cap, int64_t* count, uint8_t*) {
+  if (!pass_ok()) return KT_ERR_CUDA;
+  const int64_t m = c->m;  // timing mode: everything "changes"
+  for (int64_t t = 0; t < m && t < cap; ++t) idx[t] = (int32_t)t;
+  *count = m;
+  return KT_OK;
+}
+int kt_get_reconcile_rows(kt_ctx* c, int64_t k, const int32_t*, const kt_reconcile_out* o) {
+  if (!pass_ok()) return KT_ERR_CUDA;
+  const size_t K = (size_t)k, R = (size_t)c->R;
+  if (o->used) std::memset(o->used, 0, R * K * 8);
+  if (o->used_present) std::memset(o->used_present, 0, K * 4);
+  if (o->used_cnt) std::memset(o->used_cnt, 0, K * 8);
+  if (o->throttled) std::memset(o->throttled, 0, K * 4);
+  if (o->calc_thr) std::memset(o->calc_thr, 0, R * K * 8);
+  if (o->calc_present) std::memset(o->calc_present, 0, K * 4);
+  if (o->calc_cnt) std::memset(o->calc_cnt, 0, K * 8);
+  if (o->override_active) std::memset(o->override_active, 0, K);
+  return KT_OK;
+}
 int kt_admit_queue(kt_ctx*, int64_t, int64_t, uint32_t, int32_t* rounds, int64_t* admitted) {
   if (!pass_ok()) return KT_ERR_CUDA;
   if (rounds) *rounds = 1;

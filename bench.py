@@ -422,16 +422,33 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
     # The snapshot crosses the host link in the packed transfer format when it is representable (kt_upload_pods_packed:
     # 16-bit label-pair indices, request columns as 1- or 2-byte dictionary codes, presence in the meta word; expanded to the
     # int64 HBM columns by a device kernel): the link, not the device, bounds an end-to-end pass.
+    def pin_block(arrays, wc):
+        """The device-bound columns of one pod kind carved out of ONE pinned block (16-byte aligned pieces): the library sees that
+        they are contiguous and sends them across the link as one transfer."""
+        offs, at = [], 0
+        for a in arrays:
+            offs.append(at)
+            at += (a.nbytes + 15) & ~15
+        blk = kt.Pinned((max(at, 16),), np.uint8, upload_only=wc)
+        pinned.append(blk)
+        views = []
+        for a, o in zip(arrays, offs):
+            v = blk.array[o:o + a.nbytes].view(a.dtype).reshape(a.shape)
+            v[...] = a
+            views.append(v)
+        return views
+
     def packed_cols(wc):
         cols = []
         for pods in (r, p):
             try:
                 c = abi.packed_pods(pods, code_requests=True)
-                cols.append(abi.PackedPodCols(c.ns_bits, pin(c.pairs, wc), pin(c.labels16, wc), None, None, pin(c.meta, wc), pin(c.req_dict, wc),
-                                              pin(c.req_dict_off), pin(c.req_code_bytes), pin(c.req_codes, wc)))
+                labels16, pairs, meta, req_codes, req_dict = pin_block([c.labels16, c.pairs, c.meta, c.req_codes, c.req_dict], wc)
+                cols.append(abi.PackedPodCols(c.ns_bits, pairs, labels16, None, None, meta, req_dict, pin(c.req_dict_off), pin(c.req_code_bytes), req_codes))
             except ValueError:
                 c = abi.packed_pods(pods)
-                cols.append(abi.PackedPodCols(c.ns_bits, pin(c.pairs, wc), pin(c.labels16, wc), pin(c.req32, wc), pin(c.req_shift), pin(c.meta, wc)))
+                labels16, pairs, meta, req32 = pin_block([c.labels16, c.pairs, c.meta, c.req32], wc)
+                cols.append(abi.PackedPodCols(c.ns_bits, pairs, labels16, req32, pin(c.req_shift), meta))
         return tuple(cols)
 
     try:

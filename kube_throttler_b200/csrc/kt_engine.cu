@@ -1,51 +1,3 @@
-  // The columns a caller carved out of ONE pinned block (bench.py, a Go packer with one arena per snapshot) cross the link as
-  // one transfer: five copies of a few hundred KB each cost more in per-copy latency than their bytes.  Detected, not declared:
-  // the device-bound arrays span little more than their own size.
-  const void* h_ptr[5] = {pk->labels16, pk->pairs, pk->meta, coded ? (const void*)pk->req_codes : (const void*)pk->req32, coded ? (const void*)pk->req_dict : nullptr};
-  const size_t h_len[5] = {(size_t)L * n * 2, (size_t)pk->n_pairs * 8, (size_t)n * 4, coded ? code_bytes : (size_t)R * n * 4, coded ? dict_len * 8 : 0};
-  uintptr_t lo = UINTPTR_MAX, hi = 0;
-  size_t sum = 0;
-  for (int i = 0; i < 5; ++i)
-    if (h_len[i]) {
-      lo = std::min(lo, (uintptr_t)h_ptr[i]);
-      hi = std::max(hi, (uintptr_t)h_ptr[i] + h_len[i]);
-      sum += h_len[i];
-    }
-  const bool one_block = n > 0 && sum > 0 && (lo & 15) == 0 && hi - lo <= sum + 2048;
-  const uint16_t* d_labels16;
-  const int64_t* d_pairs;
-  const uint32_t* d_meta;
-  const void* d_req;
-  if (one_block) {
-    KT_CUDA(c, s.c_labels.reserve(hi - lo + 16));
-    KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
-    const unsigned char* base = s.c_labels.as<unsigned char>();
-    auto dev = [&](const void* h) { return h ? (const void*)(base + ((uintptr_t)h - lo)) : nullptr; };
-    d_labels16 = (const uint16_t*)dev(pk->labels16);
-    d_pairs = (const int64_t*)dev(pk->pairs);
-    d_meta = (const uint32_t*)dev(pk->meta);
-    d_req = dev(h_ptr[3]);
-    if (coded) {
-      rc.codes = (const unsigned char*)d_req;
-      rc.dict = (const int64_t*)dev(pk->req_dict);
-    }
-  } else {
-    // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
-    KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
-    if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
-    if ((err = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (err = upload(c, s.c_meta, pk->meta, (size_t)n))) return err;
-    if (coded) {
-      if ((err = upload(c, s.c_req, pk->req_codes, code_bytes)) || (err = upload(c, s.c_dict, pk->req_dict, dict_len))) return err;
-      rc.codes = s.c_req.as<unsigned char>();
-      rc.dict = s.c_dict.as<int64_t>();
-    } else if ((err = upload(c, s.c_req, pk->req32, (size_t)R * n))) {
-      return err;
-    }
-    d_labels16 = s.c_labels.as<uint16_t>();
-    d_pairs = s.c_pairs.as<int64_t>();
-    d_meta = s.c_meta.as<uint32_t>();
-    d_req = s.c_req.p;
-  }
 // kt_engine.cu -- implementation of the C ABI in include/kt_b200.h: context, HBM-resident snapshot,
 // kernel launches, result download, multi-GPU all-reduce.  There is NO CPU evaluation path in this
 // library: without a CUDA device every entry point that needs one fails with KT_ERR_CUDA.
@@ -53,7 +5,9 @@
 #include <dlfcn.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -769,16 +723,53 @@ static int upload_pods_packed_locked(kt_ctx* c, int kind, int64_t n, const kt_pa
   KT_CUDA(c, s.present.reserve((size_t)n * 4 + 16));
   KT_CUDA(c, s.flags.reserve((size_t)n * 4 + 16));
   KT_CUDA(c, s.ns.reserve((size_t)n * 4 + 16));
-  // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
-  KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
-  if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
-  if ((err = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (err = upload(c, s.c_meta, pk->meta, (size_t)n))) return err;
-  if (coded) {
-    if ((err = upload(c, s.c_req, pk->req_codes, code_bytes)) || (err = upload(c, s.c_dict, pk->req_dict, dict_len))) return err;
-    rc.codes = s.c_req.as<unsigned char>();
-    rc.dict = s.c_dict.as<int64_t>();
-  } else if ((err = upload(c, s.c_req, pk->req32, (size_t)R * n))) {
-    return err;
+  // The columns a caller carved out of ONE pinned block (bench.py, a Go packer with one arena per snapshot) cross the link as
+  // one transfer: five copies of a few hundred KB each cost more in per-copy latency than their bytes.  Detected, not declared:
+  // the device-bound arrays span little more than their own size.
+  const void* h_ptr[5] = {pk->labels16, pk->pairs, pk->meta, coded ? (const void*)pk->req_codes : (const void*)pk->req32, coded ? (const void*)pk->req_dict : nullptr};
+  const size_t h_len[5] = {(size_t)L * n * 2, (size_t)pk->n_pairs * 8, (size_t)n * 4, coded ? code_bytes : (size_t)R * n * 4, coded ? dict_len * 8 : 0};
+  uintptr_t lo = UINTPTR_MAX, hi = 0;
+  size_t sum = 0;
+  for (int i = 0; i < 5; ++i)
+    if (h_len[i]) {
+      lo = std::min(lo, (uintptr_t)h_ptr[i]);
+      hi = std::max(hi, (uintptr_t)h_ptr[i] + h_len[i]);
+      sum += h_len[i];
+    }
+  const bool one_block = n > 0 && sum > 0 && (lo & 15) == 0 && hi - lo <= sum + 2048;
+  const uint16_t* d_labels16;
+  const int64_t* d_pairs;
+  const uint32_t* d_meta;
+  const void* d_req;
+  if (one_block) {
+    KT_CUDA(c, s.c_labels.reserve(hi - lo + 16));
+    KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+    const unsigned char* base = s.c_labels.as<unsigned char>();
+    auto dev = [&](const void* h) { return h ? (const void*)(base + ((uintptr_t)h - lo)) : nullptr; };
+    d_labels16 = (const uint16_t*)dev(pk->labels16);
+    d_pairs = (const int64_t*)dev(pk->pairs);
+    d_meta = (const uint32_t*)dev(pk->meta);
+    d_req = dev(h_ptr[3]);
+    if (coded) {
+      rc.codes = (const unsigned char*)d_req;
+      rc.dict = (const int64_t*)dev(pk->req_dict);
+    }
+  } else {
+    // labels16 travels through the 32-bit staging buffer of the compact format (half of it is used)
+    KT_CUDA(c, s.c_labels.reserve((size_t)L * n * 2 + 16));
+    if (n > 0) KT_CUDA(c, cudaMemcpyAsync(s.c_labels.p, pk->labels16, (size_t)L * n * 2, cudaMemcpyHostToDevice, c->stream));
+    if ((err = upload(c, s.c_pairs, pk->pairs, (size_t)pk->n_pairs)) || (err = upload(c, s.c_meta, pk->meta, (size_t)n))) return err;
+    if (coded) {
+      if ((err = upload(c, s.c_req, pk->req_codes, code_bytes)) || (err = upload(c, s.c_dict, pk->req_dict, dict_len))) return err;
+      rc.codes = s.c_req.as<unsigned char>();
+      rc.dict = s.c_dict.as<int64_t>();
+    } else if ((err = upload(c, s.c_req, pk->req32, (size_t)R * n))) {
+      return err;
+    }
+    d_labels16 = s.c_labels.as<uint16_t>();
+    d_pairs = s.c_pairs.as<int64_t>();
+    d_meta = s.c_meta.as<uint32_t>();
+    d_req = s.c_req.p;
   }
   if (n > 0) {
     ReqShifts sh{};

@@ -179,6 +179,7 @@ struct kt_ctx {
   // multi-GPU
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  int sm_count = 0;
   // peer exchange window: [PassSync | this rank's sums, even / odd passes | all ranks' totals, even / odd passes], mapped by
   // every rank.  The fused pass does the all-reduce itself: finalize tiles ADD this rank's sums into every rank's totals
   // over NVLink and raise a per-rank flag (kt_kernels.cuh PartExchange).
@@ -191,6 +192,9 @@ struct kt_ctx {
   bool win_stale = false;     // the throttle set changed: the window's buffers are laid out for another M -> rebuilt (collectively) before the next pass
 };
 
+#ifndef KT_PASS_RESIDENT  // 1: a pass whose whole grid fits the device keeps its match CTAs on as decide tiles
+#define KT_PASS_RESIDENT 1
+#endif
 #ifndef KT_PASS_PDL  // 1: k_pass is launched with programmatic stream serialization (its launch overlaps the previous kernel's tail)
 #define KT_PASS_PDL 1
 #endif
@@ -451,12 +455,23 @@ cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, cons
                 c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>(), sparse_view(c));
 }
 template <int TPC, int B, int RT, bool REG>
-cudaError_t launch_pass(kt_ctx* c, const PassArgs& a) {
+cudaError_t launch_pass(kt_ctx* c, const PassArgs& a0) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
-  size_t smem = reconcile_smem_bytes(L, R, a.S, REG, kTileReconcile);
+  size_t smem = reconcile_smem_bytes(L, R, a0.S, REG, kTileReconcile);
   const size_t smem_chk = check_smem_bytes(L, R, REG, kTileReconcile);
   if (smem_chk > smem) smem = smem_chk;
-  return launch(c, k_pass<TPC, B, RT, REG>, 2 * a.n_chk + a.n_rec + a.n_fin, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
+  // Does the whole grid fit on the device at once?  Then the match CTAs stay on as the decide tiles (k_pass, "resident").
+  PassArgs a = a0;
+  a.n_status = (a.n_fin + kStatusBatch - 1) / kStatusBatch;
+  int per_sm = 0;
+  cudaError_t e = cudaFuncSetAttribute((const void*)k_pass<TPC, B, RT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<TPC, B, RT, REG>, kTileReconcile, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned capacity = (unsigned)per_sm * (unsigned)c->sm_count;
+  a.resident = (KT_PASS_RESIDENT != 0 && a.n_chk + a.n_rec + a.n_status <= capacity) ? 1u : 0u;
+  if (c->trace) c->trace_roles[2] = a.n_status, c->trace_roles[3] = a.resident ? 0 : a.n_chk;
+  return launch(c, k_pass<TPC, B, RT, REG>, (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }
 cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
@@ -519,6 +534,7 @@ int kt_create(kt_ctx** out, int device, const kt_limits* lim) {
     return KT_ERR_CUDA;
   }
   c->stream = c->own_stream;
+  if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) { delete c; return KT_ERR_CUDA; }
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { delete c; return KT_ERR_CUDA; }
   if (c->d_sync.reserve(sizeof(PassSync)) != cudaSuccess || cudaMemset(c->d_sync.p, 0, sizeof(PassSync)) != cudaSuccess) { kt_destroy(c); return KT_ERR_CUDA; }
@@ -1051,7 +1067,7 @@ static int evaluate_locked(kt_ctx* c, int64_t now, uint32_t flags) {
     a.n_fin = (unsigned)(((long long)M * G + kTileReconcile - 1) / kTileReconcile);
     a.n_chk = (unsigned)((pend.n + kTileReconcile - 1) / kTileReconcile);
     if (c->trace) {
-      const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;
+      const size_t rows = (size_t)2 * a.n_chk + a.n_rec + a.n_fin;  // (an upper bound of the grid: resident passes launch fewer CTAs)
       KT_CUDA(c, c->d_trace.reserve(rows * kTraceRow * 8));
       KT_CUDA(c, cudaMemsetAsync(c->d_trace.p, 0, rows * kTraceRow * 8, c->stream));
       a.trace = c->d_trace.as<unsigned long long>();

@@ -342,13 +342,16 @@ struct PdlSync {
 struct FlagSync {
   PassSync* s;
   unsigned n_rec, n_fin, n_match;
+  bool own_rows;  // resident pass: a decide tile reads the match rows its own CTA wrote (a CTA barrier orders them)
   __device__ __forceinline__ void wait_reconciled() const { cta_wait_at_least(&s->rec_done, n_rec, &s->error); }
   // the sums of every rank are in px.total
   __device__ __forceinline__ void wait_totals(const PartExchange& px) const {
     if (px.npeers == 0) wait_reconciled();
     else cta_wait_at_least(&s->tot_done, n_fin, &s->error);
   }
-  __device__ __forceinline__ void wait_matched() const { cta_wait_at_least(&s->match_done, n_match, &s->error); }
+  __device__ __forceinline__ void wait_matched() const {
+    if (!own_rows) cta_wait_at_least(&s->match_done, n_match, &s->error);
+  }
   __device__ __forceinline__ void wait_prepped() const { cta_wait_at_least(&s->prep_done, n_fin, &s->error); }
   __device__ __forceinline__ void signal_prepped() const { cta_signal(&s->prep_done); }
   __device__ __forceinline__ void signal_totals() const { cta_signal(&s->tot_done); }
@@ -876,6 +879,7 @@ struct __align__(16) PreHdr {
 constexpr uint32_t kPreLive = 1u, kPreE3 = 2u, kPreOnEqual = 4u, kPreGiven = 8u;
 __host__ __device__ inline size_t pre_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }
 
+constexpr unsigned kStatusBatch = 4;
 constexpr int kFinPrep = 1, kFinStatus = 2;  // the halves of a finalize tile: the fused pass runs them as separate tiles (prep first, so
                                              // that nobody ever waits for pre-records), the chained k_finalize runs both
 template <class Sync>
@@ -1521,9 +1525,12 @@ struct PassArgs {
   long long now;
   uint32_t eval_flags;
   int L, R, S, G;
-  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match (+ prep) n_chk][reconcile n_rec][status n_fin][decide n_chk]; a tile only
+  unsigned n_chk, n_rec, n_fin;  // tiles per role; tickets: [match (+ prep) n_chk][reconcile n_rec][status n_status][decide n_chk]; a tile only
                                  // ever waits for SMALLER tickets (status: reconcile; decide: match + prep, reconcile -- with peers the status
-                                 // tiles' totals) or for other GPUs, whose tiles are subject to the same order
+                                 // tiles' totals) or for other GPUs, whose tiles are subject to the same order -- unless the whole grid is
+                                 // resident (below)
+  unsigned n_status;             // CTAs that run the status halves: ceil(n_fin / kStatusBatch)
+  unsigned resident;             // 1: every CTA of the grid is on the device at once; the match CTAs stay on as the decide tiles
   unsigned long long* trace;     // optional (kt_enable_trace): per CTA kTraceRow x u64 {ticket, sm, t_start, t_end, stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1550,27 +1557,39 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
   }
   __syncthreads();
   unsigned tile = s_ticket;
-  const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk};
-  if (tile < a.n_chk) {  // no dependencies: first tickets, so that they are out of the way early
+  const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk, a.resident != 0};
+  unsigned long long* trow = a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr;
+  if (tile < a.n_chk) {  // no dependencies: first tickets
     // The match tiles also write the pre-records (the prep half of the finalize tiles, spread over them): they hold the first
     // tickets, so every pre-record exists a few microseconds into the pass and no decide tile ever waits for one -- without
     // extra CTAs pushing reconcile tiles out of the first wave.
     for (unsigned ft = tile; ft < a.n_fin; ft += a.n_chk)
       finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, nullptr, kFinPrep);
     // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
-    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;  // (tile: index within the role)
+    if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
     check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
+    if (a.resident) {
+      // RESIDENT pass (the host found that every CTA of the grid fits on the device at once): the CTA stays and becomes the decide
+      // tile of the same 128 pods -- already placed, its pre-wait work done long before the reconcile tiles finish, instead of a
+      // late CTA that is only launched when somebody else exits.  (It waits for LARGER tickets, which is only safe because all
+      // of them are resident; a grid that does not fit keeps the decide tiles behind the reconcile tiles.)
+      __syncthreads();
+      check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile, sync,
+                                        a.sparse, trow);
+    }
   } else if ((tile -= a.n_chk) < a.n_rec) {
-    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile,
-                                    a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
+    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow);
     cta_signal(&a.sync->rec_done);
-  } else if ((tile -= a.n_rec) < a.n_fin) {
-    finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)tile, sync, a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr,
-                  kFinStatus);
+  } else if ((tile -= a.n_rec) < a.n_status) {
+    // status halves (off the critical path): kStatusBatch finalize tiles per CTA, so that they do not cost the grid its residency
+    for (unsigned j = 0; j < kStatusBatch; ++j) {
+      const unsigned ft = tile * kStatusBatch + j;
+      if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, j == 0 ? trow : nullptr, kFinStatus);
+    }
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_fin, sync, a.sparse,
-                                      a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr);
+    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_status, sync,
+                                      a.sparse, trow);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -1581,7 +1600,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       unsigned long long* row = a.trace + (size_t)s_ticket * kTraceRow;
       row[0] = s_ticket; row[1] = smid; row[2] = t_start; row[3] = globaltimer_ns();
     }
-    const unsigned total = 2 * a.n_chk + a.n_rec + a.n_fin;
+    const unsigned total = (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status;
     if (atomicAdd(&a.sync->exited, 1u) == total - 1) {
       a.sync->ticket = 0;
       a.sync->rec_done = 0;

@@ -22,10 +22,10 @@ s = torch.cuda.Stream()
 eng.set_stream(s.cuda_stream)
 eng.enable_trace(True)
 STAGES = {
-    "match": [],
+    "match": ["(resident: decide) rows seen", "words + pre staged", "sums seen", "constants done", "decided"],
     "reconcile": ["rows landed", "2 words evaluated", "barrier", "words+sums", "sweep"],
     "finalize": ["pre-records", "reconcile seen", "sums read", "status written"],
-    "decide": ["match rows seen", "own words", "sums seen", "decided"],
+    "decide": ["match rows seen", "words + pre staged", "sums seen", "constants done", "decided"],
 }
 for it in range(4):
     with torch.cuda.stream(s):

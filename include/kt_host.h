@@ -101,6 +101,9 @@ const char* kth_unreserve_key(kth_plugin* p, const char* ns, const char* name);
  * kth_last_error).  kth_queue_row gives the row of a queued pod (-1: not queued); rows are stable while the pod stays queued. */
 int64_t kth_pre_filter_queue(kth_plugin* p, uint8_t* verdicts, int64_t cap);
 int64_t kth_queue_row(kth_plugin* p, const char* ns, const char* name);
+/* Row of a pod in the device's running-pod table (-1: unknown pod).  Diagnostic: rows are handed out from per-namespace arenas
+ * of 32 consecutive rows, so that the 32 rows a warp walks share a namespace under any churn. */
+int64_t kth_pod_row(kth_plugin* p, const char* ns, const char* name);
 const char* kth_last_error(void);
 /* {"queued":n,"rows":r,"passes":device passes over the queue so far,"hits":by-key calls answered from cached verdicts} */
 const char* kth_queue_stats(kth_plugin* p);

@@ -192,6 +192,9 @@ struct kt_ctx {
   bool win_stale = false;     // the throttle set changed: the window's buffers are laid out for another M -> rebuilt (collectively) before the next pass
 };
 
+#ifndef KT_WIDE_TILES  // 1: ClusterThrottle-heavy tables run the pass with 256-pod tiles
+#define KT_WIDE_TILES 1
+#endif
 #ifndef KT_PASS_RESIDENT  // 1: a pass whose whole grid fits the device keeps its match CTAs on as decide tiles
 #define KT_PASS_RESIDENT 1
 #endif
@@ -454,37 +457,46 @@ cudaError_t launch_check(kt_ctx* c, const PodView& pv, const TableView& tb, cons
                 (const unsigned char*)c->d_pre.as<unsigned char>(), px, c->pods[KT_PODS_PENDING].bitmap.as<uint32_t>(),
                 c->d_codes.as<uint32_t>(), c->d_admit.as<unsigned char>(), sparse_view(c));
 }
-template <int TPC, int B, int RT, bool REG>
+template <int TPC, int B, int RT, bool REG, int TILE>
 cudaError_t launch_pass(kt_ctx* c, const PassArgs& a0) {
   const int L = c->lim.label_slots, R = c->lim.n_resources;
-  size_t smem = reconcile_smem_bytes(L, R, a0.S, REG, kTileReconcile);
-  const size_t smem_chk = check_smem_bytes(L, R, REG, kTileReconcile);
+  size_t smem = reconcile_smem_bytes(L, R, a0.S, REG, TILE);
+  const size_t smem_chk = check_smem_bytes(L, R, REG, TILE);
   if (smem_chk > smem) smem = smem_chk;
-  // Does the whole grid fit on the device at once?  Then the match CTAs stay on as the decide tiles (k_pass, "resident").
   PassArgs a = a0;
+  a.n_rec = (unsigned)((a.run.n + TILE - 1) / TILE);
+  a.n_fin = (unsigned)(((long long)a.tb.M * a.G + TILE - 1) / TILE);
+  a.n_chk = (unsigned)((a.pend.n + TILE - 1) / TILE);
   a.n_status = (a.n_fin + kStatusBatch - 1) / kStatusBatch;
+  // Does the whole grid fit on the device at once?  Then the match CTAs stay on as the decide tiles (k_pass, "resident").
   int per_sm = 0;
-  cudaError_t e = cudaFuncSetAttribute((const void*)k_pass<TPC, B, RT, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute((const void*)k_pass<TPC, B, RT, REG, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<TPC, B, RT, REG>, kTileReconcile, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<TPC, B, RT, REG, TILE>, TILE, smem);
   if (e != cudaSuccess) return e;
   const unsigned capacity = (unsigned)per_sm * (unsigned)c->sm_count;
   a.resident = (KT_PASS_RESIDENT != 0 && a.n_chk + a.n_rec + a.n_status <= capacity) ? 1u : 0u;
-  if (c->trace) c->trace_roles[2] = a.n_status, c->trace_roles[3] = a.resident ? 0 : a.n_chk;
-  return launch(c, k_pass<TPC, B, RT, REG>, (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status, kTileReconcile, smem, /*pdl=*/KT_PASS_PDL != 0, a);
+  if (c->trace) { c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_status; c->trace_roles[3] = a.resident ? 0 : a.n_chk; }
+  return launch(c, k_pass<TPC, B, RT, REG, TILE>, (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status, TILE, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }
 cudaError_t dispatch_pass(kt_ctx* c, const PassArgs& a) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;
   const int R = c->lim.n_resources;
   const bool fast = c->lim.label_slots <= 8 && b2 && R <= 8;
+  // ClusterThrottle-heavy tables (a namespace's word list is long): 256 pods share a CTA's accumulator slots
+  const bool wide = KT_WIDE_TILES != 0 && a.S >= 8 && kTileReconcile == 128;
   if (fast) {
-    if (t1) return R <= 4 ? launch_pass<1, 2, 4, true>(c, a) : launch_pass<1, 2, 8, true>(c, a);
-    return R <= 4 ? launch_pass<2, 2, 4, true>(c, a) : launch_pass<2, 2, 8, true>(c, a);
+    if (wide) {
+      if (t1) return R <= 4 ? launch_pass<1, 2, 4, true, 256>(c, a) : launch_pass<1, 2, 8, true, 256>(c, a);
+      return R <= 4 ? launch_pass<2, 2, 4, true, 256>(c, a) : launch_pass<2, 2, 8, true, 256>(c, a);
+    }
+    if (t1) return R <= 4 ? launch_pass<1, 2, 4, true, kTileReconcile>(c, a) : launch_pass<1, 2, 8, true, kTileReconcile>(c, a);
+    return R <= 4 ? launch_pass<2, 2, 4, true, kTileReconcile>(c, a) : launch_pass<2, 2, 8, true, kTileReconcile>(c, a);
   }
-  if (t1 && b2) return launch_pass<1, 2, 0, false>(c, a);
-  if (t1) return launch_pass<1, 6, 0, false>(c, a);
-  if (b2) return launch_pass<2, 2, 0, false>(c, a);
-  return launch_pass<2, 6, 0, false>(c, a);
+  if (t1 && b2) return launch_pass<1, 2, 0, false, kTileReconcile>(c, a);
+  if (t1) return launch_pass<1, 6, 0, false, kTileReconcile>(c, a);
+  if (b2) return launch_pass<2, 2, 0, false, kTileReconcile>(c, a);
+  return launch_pass<2, 6, 0, false, kTileReconcile>(c, a);
 }
 cudaError_t dispatch_reconcile(kt_ctx* c, const PodView& pv, const TableView& tb, unsigned long long* part, unsigned blocks) {
   const bool t1 = c->ht.TPpad == 1, b2 = c->ht.B <= 2;

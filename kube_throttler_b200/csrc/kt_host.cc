@@ -2316,6 +2316,12 @@ const char* kth_reserve_key(kth_plugin* p, const char* ns, const char* name) {
 const char* kth_unreserve_key(kth_plugin* p, const char* ns, const char* name) {
   return guarded(p, [&]() { return p->reserve_key(ns ? ns : "", name ? name : "", false); });
 }
+int64_t kth_pod_row(kth_plugin* p, const char* ns, const char* name) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->pod_index.find(std::string(ns ? ns : "") + "/" + (name ? name : ""));
+  return it == p->pod_index.end() ? -1 : it->second;
+}
 int64_t kth_queue_row(kth_plugin* p, const char* ns, const char* name) {
   if (!p) return -1;
   std::lock_guard<std::mutex> lk(p->mu);

@@ -585,11 +585,10 @@ __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool
 //   S   per-CTA accumulator slots, one per distinct 32-throttle word the tile touches (host: from the
 //       largest per-namespace word list); words beyond S go straight to HBM
 // ------------------------------------------------------------------------------------------------
-template <int TPC, int B, int RT, bool REG>
+template <int TPC, int B, int RT, bool REG, int TILE = kTileReconcile>
 __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableView& tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
                                                unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */,
                                                unsigned char* smem_raw, int64_t tile_index, unsigned long long* trace_row = nullptr) {
-  constexpr int TILE = kTileReconcile;
   // optional stage stamps of warp 0 (kt_enable_trace): [4] the pod rows have landed, [5] first two words evaluated, [6] barrier
   // passed, [7] words + sums done, [8] sweep done
   auto stamp = [&](int k) {
@@ -1164,7 +1163,7 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 // into the CTA's staging slots.  After the wait one lane per (slot, throttle) fetches that throttle's sums -- one trip to
 // L2 for the whole CTA -- and finishes the record in place (what a finalize stage between reconcile and decide used to
 // hand over); then every lane decides its own pairs from shared memory.
-template <int TILE, class Sync>
+template <int TILE, int RT, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
                                                   const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
                                                   unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t tile_index, const Sync& sync,
@@ -1230,19 +1229,27 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       const long long* head = thrv + R;
       const uint32_t cand = nz & hq.x;
       uint32_t code;
-      // S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod)
-      bool s1 = hq.w & 1u;
-      for (uint32_t c = cand; c && !s1;) {
-        const int r = __ffs(c) - 1;
-        c &= c - 1;
-        s1 = s_req[r * TILE + tid] > thrv[r];
-      }
-      if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
-      else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
-      else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
-      else {
-        bool s4 = hq.w & 8u;                                         // S4 used+pod+reserved
-        const bool ge = hq.w & 16u;
+      bool s1 = hq.w & 1u, s4 = hq.w & 8u;  // the count lane's share of S1 / S4
+      const bool ge = hq.w & 16u;
+      if constexpr (RT > 0) {
+        // R is small and known: every resource compared, no data-dependent loop (S1 threshold.IsThrottled(podAmount, false)
+        // .IsThrottledFor(pod); S4 used + pod + reserved against the threshold, as pod against head = threshold - used - reserved)
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          if (r < R) {
+            const long long v = s_req[r * TILE + tid];
+            const bool on = (cand >> r) & 1;
+            s1 = s1 || (on && v > thrv[r]);
+            const long long hd = head[r];
+            s4 = s4 || (on && (ge ? v >= hd : v > hd));
+          }
+        }
+      } else {
+        for (uint32_t c = cand; c && !s1;) {
+          const int r = __ffs(c) - 1;
+          c &= c - 1;
+          s1 = s_req[r * TILE + tid] > thrv[r];
+        }
         for (uint32_t c = cand; c && !s4;) {
           const int r = __ffs(c) - 1;
           c &= c - 1;
@@ -1250,8 +1257,11 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
           const long long hd = head[r];
           s4 = ge ? v >= hd : v > hd;
         }
-        code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
       }
+      if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
+      else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
+      else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
+      else code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
       if (code) ok = 0;
       if (b < 16) c0 |= code << (2 * b);
       else c1 |= code << (2 * (b - 16));
@@ -1466,15 +1476,29 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       }
     }
     __syncthreads();
-    // 2. the slots are spread over the warps: pre-records now, the sums after the (first) wait
-    for (int slot = warp; slot < SLOTS; slot += WARPS) stage_pre(slot);
+    // 2. the slots in use are spread over the warps (by rank among the used ones: two words whose slots happen to be four apart
+    // must not land on the same warp): pre-records now, the sums after the (first) wait
+    int my_slot[2] = {-1, -1};
+    {
+      uint32_t used = __ballot_sync(kFull, lane < SLOTS && s_key[lane < SLOTS ? lane : 0] >= 0);
+      int rank = 0;
+      while (used) {
+        const int sidx = __ffs(used) - 1;
+        used &= used - 1;
+        if (rank % WARPS == warp && rank / WARPS < 2) my_slot[rank / WARPS] = sidx;
+        ++rank;
+      }
+    }
+    for (int j = 0; j < 2; ++j)
+      if (my_slot[j] >= 0) stage_pre(my_slot[j]);
     stamp(5);
     if (!sums_awaited) {
       sync.wait_totals(px);  // the sums of every running pod (of every rank) are in px.total
       sums_awaited = true;
       stamp(6);
     }
-    for (int slot = warp; slot < SLOTS; slot += WARPS) stage_post(slot);
+    for (int j = 0; j < 2; ++j)
+      if (my_slot[j] >= 0) stage_post(my_slot[j]);
     if (scattered && k == 0) { decide_scattered(); k = 1; }  // (k is otherwise unused by a scattered warp: marks "done")
     __syncthreads();
     stamp(7);
@@ -1499,7 +1523,7 @@ __global__ void __launch_bounds__(kTileCheck) k_check(PodView pods, TableView tb
   extern __shared__ __align__(16) unsigned char smem_raw[];
   check_match_tile<TPC, B, REG, kTileCheck>(pods, tb, L, bitmap, codes, smem_raw, blockIdx.x);
   __syncthreads();  // the tile's match rows are written (read back below) and the row staging is free again
-  check_decide_tile<kTileCheck>(pods, tb, R, decide_stage_words(R, kTileCheck), pre, px, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
+  check_decide_tile<kTileCheck, 0>(pods, tb, R, decide_stage_words(R, kTileCheck), pre, px, bitmap, codes, admit, smem_raw, blockIdx.x, PdlSync{}, sparse);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1539,8 +1563,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <int TPC, int B, int RT, bool REG>
-__global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconcile) k_pass(const __grid_constant__ PassArgs a) {
+// TILE: pods per CTA (= threads).  128 everywhere except ClusterThrottle-heavy tables, where every pod walks a dozen words and a
+// CTA's accumulator slots (one per word, 2 KB each at R = 8) are better shared by twice the pods (C3: 156 -> 119 us).
+template <int TPC, int B, int RT, bool REG, int TILE = kTileReconcile>
+__global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __grid_constant__ PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
   unsigned long long t_start = 0;
@@ -1567,7 +1593,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, nullptr, kFinPrep);
     // the first match tile also clears the sparse list's counter: every decide tile waits for ALL match tiles before it appends
     if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
-    check_match_tile<TPC, B, REG, kTileReconcile>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
+    check_match_tile<TPC, B, REG, TILE>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
     if (a.resident) {
       // RESIDENT pass (the host found that every CTA of the grid fits on the device at once): the CTA stays and becomes the decide
@@ -1575,11 +1601,11 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       // late CTA that is only launched when somebody else exits.  (It waits for LARGER tickets, which is only safe because all
       // of them are resident; a grid that does not fit keeps the decide tiles behind the reconcile tiles.)
       __syncthreads();
-      check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile, sync,
+      check_decide_tile<TILE, RT>(a.pend, a.tb, a.R, decide_stage_words(a.R, TILE), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile, sync,
                                         a.sparse, trow);
     }
   } else if ((tile -= a.n_chk) < a.n_rec) {
-    reconcile_tile<TPC, B, RT, REG>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow);
+    reconcile_tile<TPC, B, RT, REG, TILE>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_status) {
     // status halves (off the critical path): kStatusBatch finalize tiles per CTA, so that they do not cost the grid its residency
@@ -1588,7 +1614,7 @@ __global__ void __launch_bounds__(kTileReconcile, KT_PASS_THREADS / kTileReconci
       if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, j == 0 ? trow : nullptr, kFinStatus);
     }
   } else {
-    check_decide_tile<kTileReconcile>(a.pend, a.tb, a.R, decide_stage_words(a.R, kTileReconcile), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_status, sync,
+    check_decide_tile<TILE, RT>(a.pend, a.tb, a.R, decide_stage_words(a.R, TILE), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_status, sync,
                                       a.sparse, trow);
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)

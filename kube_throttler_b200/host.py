@@ -36,13 +36,15 @@ def _bind(L=None):
     L.kth_pre_filter_queue.restype = C.c_int64
     L.kth_queue_row.argtypes = [vp, cp, cp]
     L.kth_queue_row.restype = C.c_int64
+    L.kth_pod_row.argtypes = [vp, cp, cp]
+    L.kth_pod_row.restype = C.c_int64
     L.kth_last_error.restype = cp
     L._kth_bound = True
     return L
 
 
 HOST_EXPORTS = ["kth_new_plugin", "kth_new_plugin_error", "kth_free", "kth_apply", "kth_delete", "kth_reconcile_all", "kth_get_status", "kth_get_status_manifest",
-                "kth_pre_filter", "kth_pre_filter_key", "kth_reserve_key", "kth_unreserve_key", "kth_pre_filter_queue", "kth_queue_row", "kth_queue_stats", "kth_last_error", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
+                "kth_pre_filter", "kth_pre_filter_key", "kth_reserve_key", "kth_unreserve_key", "kth_pre_filter_queue", "kth_queue_row", "kth_pod_row", "kth_queue_stats", "kth_last_error", "kth_pre_filter_batch", "kth_admit_queue", "kth_reserve", "kth_unreserve", "kth_reserved", "kth_metrics", "kth_eval"]
 
 
 def _result(raw):
@@ -132,6 +134,9 @@ class Plugin:
 
     def queue_row(self, namespace, name) -> int:
         return int(self._L.kth_queue_row(self._h, namespace.encode(), name.encode()))
+
+    def pod_row(self, namespace, name) -> int:
+        return int(self._L.kth_pod_row(self._h, namespace.encode(), name.encode()))
 
     def queue_stats(self):
         return _result(self._L.kth_queue_stats(self._h))

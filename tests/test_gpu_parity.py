@@ -381,6 +381,22 @@ def test_step_api_equals_separate_calls(kt, oracle):
         engines.append(eng)
         got = None
     packed = [[abi.packed_pods(pods, code_requests=True) for pods in (s_.running, s_.pending)] for s_ in snaps]
+    # the second snapshot's columns are carved out of ONE host block per kind: the library detects it and sends one transfer
+    blocks = []
+    for k, c in enumerate(packed[1]):
+        arrays = [c.labels16, c.pairs, c.meta, c.req_codes, c.req_dict]
+        offs, at = [], 0
+        for a in arrays:
+            offs.append(at)
+            at += (a.nbytes + 15) & ~15
+        blk = kt.Pinned((at,), np.uint8)
+        blocks.append(blk)
+        views = []
+        for a, o in zip(arrays, offs):
+            v = blk.array[o:o + a.nbytes].view(a.dtype).reshape(a.shape)
+            v[...] = a
+            views.append(v)
+        packed[1][k] = abi.PackedPodCols(c.ns_bits, views[1], views[0], None, None, views[2], views[4], c.req_dict_off, c.req_code_bytes, views[3])
     for it in range(4):
         for eng, snap, pk in zip(engines, snaps, packed):  # both submitted before either is waited for
             if it == 3:

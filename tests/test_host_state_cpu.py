@@ -232,3 +232,34 @@ def test_deleted_pod_never_keeps_a_reservation(host_on_oracle):
     assert "default/q0" not in w.reserved("Throttle", "default/t")["pods"]
     assert w.prefilter(pod("default", "q1", "9500m", {"a": "1"}))["code"] == "Success"  # nothing reserved any more
     w.close()
+
+
+def test_rows_stay_namespace_clustered_under_churn(host_on_oracle):
+    """The device kernels walk a warp's 32 rows word by word, one or two rounds when they share a namespace: the host hands rows
+    out from per-namespace arenas of 32 consecutive rows, and a deleted pod's row goes back to its namespace, so after any mix of
+    arrivals and departures every 32-row chunk still holds pods of ONE namespace (the reference's pod informer is indexed by
+    namespace, plugin.go:81-84)."""
+    import random
+
+    rng = random.Random(4)
+    w = host_on_oracle(THROTTLER, SCHED)
+    nss = [f"ns{i}" for i in range(7)]
+    w.apply(*[namespace(n) for n in nss])
+    live = {}
+    for step in range(3000):
+        if live and rng.random() < 0.4:
+            key = rng.choice(sorted(live))
+            w.delete("Pod", key[1], key[0])
+            del live[key]
+        else:
+            key = (rng.choice(nss), f"p{step}")
+            w.apply(pod(key[0], key[1], "100m", {"a": "1"}, node="n", phase="Running"))
+            live[key] = True
+    chunk_ns = {}
+    for ns_, name in live:
+        row = w.pod_row(ns_, name)
+        assert row >= 0
+        assert chunk_ns.setdefault(row // 32, ns_) == ns_, (row, ns_, chunk_ns[row // 32])
+    rows = sorted(w.pod_row(*k) for k in live)
+    assert len(set(rows)) == len(rows) and rows[-1] < len(live) + 32 * len(nss) + 32 * 40  # slots are reused, the table stays compact
+    w.close()

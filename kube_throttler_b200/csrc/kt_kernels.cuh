@@ -51,6 +51,12 @@ constexpr uint32_t kFull = 0xffffffffu;
 #define KT_STAGE_CHUNK 4
 #endif
 constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record values and sums a decide lane requests together
+#ifndef KT_EVAL_PAIR  // 1: a lane's first two words are evaluated with their table gathers interleaved (eval_word2)
+#define KT_EVAL_PAIR 1
+#endif
+#ifndef KT_DECIDE_UNROLLED
+#define KT_DECIDE_UNROLLED 0
+#endif
 constexpr int kPropose = 4;          // words a warp of a decide tile may propose to its CTA's staging table per round
 constexpr int kTraceRow = 16;        // u64 per CTA of the optional in-kernel trace: {ticket, sm, t_start, t_end, 12 stage stamps}
 
@@ -551,6 +557,80 @@ __device__ __forceinline__ uint32_t eval_word(const TableView& tb, const PodRows
   return result;
 }
 
+// The first two words of a lane together: the table gathers of BOTH words for four labels at a time are in flight before any
+// of them is folded -- two words cost the latency of one (eval_word twice serialises them: the second word's loads only issue
+// after the first word's folds have consumed theirs).  Register-row family only (L <= 8).
+template <int TPC, int B>
+__device__ __forceinline__ void eval_word2(const TableView& tb, const PodRows<true>& rows, int ns, int w0, int w1, uint32_t& m0, uint32_t& m1) {
+  const uint32_t row_bytes = (uint32_t)tb.TPpad * 8u;
+  const int ws[2] = {w0, w1};
+  const unsigned char* wbase[2];
+  const uint32_t* nsm[2];
+  const uint32_t* need[2];
+#pragma unroll
+  for (int z = 0; z < 2; ++z) {
+    wbase[z] = reinterpret_cast<const unsigned char*>(tb.table) + (size_t)ws[z] * tb.rows * row_bytes;
+    nsm[z] = tb.nsmask + ((size_t)ns * tb.W + ws[z]) * tb.TPpad;
+    need[z] = tb.need + (size_t)ws[z] * tb.TPpad * B;
+  }
+  uint32_t result[2] = {0u, 0u};
+#pragma unroll 1
+  for (int s0 = 0; s0 < tb.TPpad; s0 += TPC) {
+    uint32_t sat[2][TPC], cnt[2][TPC][B];
+#pragma unroll
+    for (int z = 0; z < 2; ++z)
+#pragma unroll
+      for (int s = 0; s < TPC; ++s) {
+        sat[z][s] = __ldg(&nsm[z][s0 + s]);
+#pragma unroll
+        for (int b = 0; b < B; ++b) cnt[z][s][b] = 0;
+      }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[2][4][TPC * 2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned char* e = wbase[z] + rows.off[half * 4 + i] + s0 * 8;
+          if constexpr (TPC == 2) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(e));
+            v[z][i][0] = q.x; v[z][i][1] = q.y; v[z][i][2] = q.z; v[z][i][3] = q.w;
+          } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(e));
+            v[z][i][0] = q.x; v[z][i][1] = q.y;
+          }
+        }
+#pragma unroll
+      for (int z = 0; z < 2; ++z)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int s = 0; s < TPC; ++s) {
+            sat[z][s] &= v[z][i][2 * s];
+            uint32_t carry = v[z][i][2 * s + 1];  // ripple-add one bit into the bit-sliced counter
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+              const uint32_t t = cnt[z][s][b] & carry;
+              cnt[z][s][b] ^= carry;
+              carry = t;
+            }
+          }
+    }
+#pragma unroll
+    for (int z = 0; z < 2; ++z)
+#pragma unroll
+      for (int s = 0; s < TPC; ++s) {
+        uint32_t m = sat[z][s];
+#pragma unroll
+        for (int b = 0; b < B; ++b) m &= ~(cnt[z][s][b] ^ __ldg(&need[z][(s0 + s) * B + b]));
+        result[z] |= m;
+      }
+  }
+  m0 = result[0];
+  m1 = result[1];
+}
+
 // 32x32 bit-matrix transpose across the warp: in = lane l holds row l; out = lane b holds column b.
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   uint32_t m = 0x0000ffffu;
@@ -656,8 +736,13 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   // phase 1 -- the lane's first two words, back to back and independent of the other lanes (a match word only needs the
   // lane's own row): their 2 x Lpad table gathers are all in flight together
   uint32_t m0 = 0, m1 = 0;
-  if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
-  if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
+  if constexpr (REG && KT_EVAL_PAIR) {
+    if (wc.inl > 1) eval_word2<TPC, B>(tb, rows, ns, wc.w0, wc.w1, m0, m1);
+    else if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+  } else {
+    if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+    if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
+  }
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
 #pragma unroll
@@ -1145,8 +1230,13 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
   WordCursor wc;
   wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
   uint32_t m0 = 0, m1 = 0;  // the first two words: all their table gathers in flight together
-  if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
-  if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
+  if constexpr (REG && KT_EVAL_PAIR) {
+    if (wc.inl > 1) eval_word2<TPC, B>(tb, rows, ns, wc.w0, wc.w1, m0, m1);
+    else if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+  } else {
+    if (wc.inl > 0) m0 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w0);
+    if (wc.inl > 1) m1 = eval_word<TPC, B, REG>(tb, rows, Lpad, ns, wc.w1);
+  }
   if (pods.zero_fill) __syncthreads();  // zero-fill before the word stores (rows of a tile are zeroed by all its lanes)
   if (wc.inl > 0) bitmap[p * Wp + wc.w0] = m0;
   if (wc.inl > 1) bitmap[p * Wp + wc.w1] = m1;
@@ -1231,9 +1321,10 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       uint32_t code;
       bool s1 = hq.w & 1u, s4 = hq.w & 8u;  // the count lane's share of S1 / S4
       const bool ge = hq.w & 16u;
-      if constexpr (RT > 0) {
-        // R is small and known: every resource compared, no data-dependent loop (S1 threshold.IsThrottled(podAmount, false)
-        // .IsThrottledFor(pod); S4 used + pod + reserved against the threshold, as pod against head = threshold - used - reserved)
+      if constexpr (RT > 0 && KT_DECIDE_UNROLLED) {
+        // every resource compared, no data-dependent loop -- measured SLOWER than the loops below at C2 (pods ask for one or two
+        // of the throttles' resources; the loops stop at the first hit): kept behind KT_DECIDE_UNROLLED, off
+        // (S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod); S4 used + pod + reserved against the threshold)
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
           if (r < R) {

@@ -475,7 +475,9 @@ cudaError_t launch_pass(kt_ctx* c, const PassArgs& a0) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<TPC, B, RT, REG, TILE>, TILE, smem);
   if (e != cudaSuccess) return e;
   const unsigned capacity = (unsigned)per_sm * (unsigned)c->sm_count;
-  a.resident = (KT_PASS_RESIDENT != 0 && a.n_chk + a.n_rec + a.n_status <= capacity) ? 1u : 0u;
+  // (the status CTAs come last and are waited for by nobody on this GPU -- with peers only by decide tiles, after every
+  // reconcile tile has left -- so they do not count)
+  a.resident = (KT_PASS_RESIDENT != 0 && a.n_chk + a.n_rec <= capacity) ? 1u : 0u;
   if (c->trace) { c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_status; c->trace_roles[3] = a.resident ? 0 : a.n_chk; }
   return launch(c, k_pass<TPC, B, RT, REG, TILE>, (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status, TILE, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }

@@ -51,8 +51,8 @@ constexpr uint32_t kFull = 0xffffffffu;
 #define KT_STAGE_CHUNK 4
 #endif
 constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record values and sums a decide lane requests together
-#ifndef KT_EVAL_PAIR  // 1: a lane's first two words are evaluated with their table gathers interleaved (eval_word2)
-#define KT_EVAL_PAIR 1
+#ifndef KT_EVAL_PAIR  // 1: a lane's first two words are evaluated with their table gathers interleaved (eval_word2).  Measured
+#define KT_EVAL_PAIR 0  // slower at the 80-register cap of a resident pass (spills): C2 21.6 vs 20.9 us, C2 x10 100 vs 92 us -- off
 #endif
 #ifndef KT_DECIDE_UNROLLED
 #define KT_DECIDE_UNROLLED 0
@@ -963,7 +963,7 @@ struct __align__(16) PreHdr {
 constexpr uint32_t kPreLive = 1u, kPreE3 = 2u, kPreOnEqual = 4u, kPreGiven = 8u;
 __host__ __device__ inline size_t pre_record_bytes(int R) { return 16 + 16 * (size_t)R + 16; }
 
-constexpr unsigned kStatusBatch = 4;
+constexpr unsigned kStatusBatch = 1;  // finalize tiles (status halves) per status CTA
 constexpr int kFinPrep = 1, kFinStatus = 2;  // the halves of a finalize tile: the fused pass runs them as separate tiles (prep first, so
                                              // that nobody ever waits for pre-records), the chained k_finalize runs both
 template <class Sync>
@@ -1699,7 +1699,8 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
     reconcile_tile<TPC, B, RT, REG, TILE>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow);
     cta_signal(&a.sync->rec_done);
   } else if ((tile -= a.n_rec) < a.n_status) {
-    // status halves (off the critical path): kStatusBatch finalize tiles per CTA, so that they do not cost the grid its residency
+    // status halves (off the critical path; nobody on this GPU waits for them, so they need not be resident from the start: they
+    // take the slots the reconcile tiles leave, which is when their work begins anyway)
     for (unsigned j = 0; j < kStatusBatch; ++j) {
       const unsigned ft = tile * kStatusBatch + j;
       if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, j == 0 ? trow : nullptr, kFinStatus);

@@ -514,19 +514,24 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
         eng.step_submit(a_[0], a_[1], snap.now)
         consume(eng.step_wait())
 
-    # what the host link of this box can do at all (pinned, one 64 MiB copy each way): the floor of any e2e number
-    probe_h, probe_d = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    # what the host link of this box can do at all (one 64 MiB copy each way, from the same pinned allocator the step's buffers come
+    # from -- a buffer pinned on the far NUMA node measures that node's link, not this step's): the floor of any e2e number
+    probe_pin = kt.Pinned((64 << 20,), np.uint8)
+    probe_pin.array[:] = 1
+    probe_h, probe_d = torch.from_numpy(probe_pin.array), torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
     link = {}
     for name, (dst, s_) in (("h2d", (probe_d, probe_h)), ("d2h", (probe_h, probe_d))):
         best = 0.0
-        for _ in range(6):  # best of six single copies: the first ones pay for page pinning / clock ramp
+        for _ in range(8):  # best of eight single copies, timed on the device: the first ones pay for the clock ramp
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            e0.record()
             dst.copy_(s_, non_blocking=True)
+            e1.record()
             torch.cuda.synchronize()
-            best = max(best, (64 << 20) / (time.perf_counter() - t0) / 1e9)
+            best = max(best, (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9)
         link[name + "_gbs"] = best
-    del probe_h, probe_d
+    del probe_h, probe_d, probe_pin
 
     def time_steps(fn):
         for _ in range(3):

@@ -533,17 +533,18 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
         link[name + "_gbs"] = best
     del probe_h, probe_d, probe_pin
 
-    def time_steps(fn):
+    def time_steps(fn, steps=None):
+        steps = steps or args.e2e_steps
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
         bench.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        for _ in range(steps):
             fn()
         torch.cuda.synchronize()
         bench.barrier()
-        return checks_per_step * args.e2e_steps / bench.max_over_ranks(time.perf_counter() - t0)
+        return checks_per_step * steps / bench.max_over_ranks(time.perf_counter() - t0)
 
     wide_value = time_steps(step_wide)
     eng.set_async_uploads(True)  # the pinned columns live for the whole run: no need to wait for each copy before queueing the next
@@ -562,31 +563,55 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
     # Double-buffered steps: a second context (own stream, own snapshot buffers) is handed the NEXT step while this step's
     # pass runs and its results come back -- H2D, the pass and D2H of consecutive steps overlap; every step still copies its
     # inputs in and its results out and is waited for.  Single GPU only (a second context would need a second peer window set).
-    pipelined = None
+    pipelined, depth_values, best_depth, host_us = None, {}, 0, {}
     if world == 1 and packed:
+        # D contexts in a ring: step k+D-1 is submitted before step k is waited for.  One step's latency (two uploads, two unpack
+        # launches, the pass, three result copies, all in stream order, plus the host's submit and wake-up) is ~2.5x the time its
+        # bytes need on the link, so two contexts do not fill the link yet; three or four do.
+        ring = [eng]
         try:
-            eng2 = kt.Engine(snap.R, snap.L, snap.LN, device=bench.local_rank)
-            stream2 = torch.cuda.Stream()
-            eng2.set_stream(stream2.cuda_stream)
-            eng2.upload_snapshot(snap)
-            eng2.set_async_uploads(True)
-            eng2.set_sparse_check(sparse_cap)
-            pair, turn = (eng, eng2), [0]
             a_ = step_args(src[0])
-            pair[0].step_submit(a_[0], a_[1], snap.now)
+            for depth in (2, 4, 6, 8):
+                while len(ring) < depth:
+                    e2 = kt.Engine(snap.R, snap.L, snap.LN, device=bench.local_rank)
+                    st2 = torch.cuda.Stream()
+                    e2._bench_stream = st2  # keeps the stream alive as long as the engine
+                    e2.set_stream(st2.cuda_stream)
+                    e2.upload_snapshot(snap)
+                    e2.set_async_uploads(True)
+                    e2.set_sparse_check(sparse_cap)
+                    ring.append(e2)
+                turn = [0]
+                for k in range(depth - 1):
+                    ring[k].step_submit(a_[0], a_[1], snap.now)
 
-            def step_pipelined():
-                cur, nxt = pair[turn[0] & 1], pair[(turn[0] + 1) & 1]
-                nxt.step_submit(a_[0], a_[1], snap.now)  # step k+1 is queued on the other context's stream ...
-                consume(cur.step_wait())                  # ... while step k finishes
-                turn[0] += 1
+                host_ns = [0, 0, 0]  # inside kt_step_submit, inside kt_step_wait, steps
 
-            pipelined = time_steps(step_pipelined)
-            pair[turn[0] & 1].step_wait()
-            eng2.sync()
-            eng2.close()
+                def step_pipelined():
+                    t0_ = time.perf_counter_ns()
+                    ring[(turn[0] + depth - 1) % depth].step_submit(a_[0], a_[1], snap.now)  # step k+D-1 is queued on its own stream ...
+                    t1_ = time.perf_counter_ns()
+                    consume(ring[turn[0] % depth].step_wait())                              # ... while step k finishes
+                    host_ns[0] += t1_ - t0_
+                    host_ns[1] += time.perf_counter_ns() - t1_
+                    host_ns[2] += 1
+                    turn[0] += 1
+
+                v = time_steps(step_pipelined, 4 * args.e2e_steps)
+                for k in range(depth - 1):
+                    ring[(turn[0] + k) % depth].step_wait()
+                depth_values[str(depth)] = v
+                host_us[str(depth)] = {"submit": host_ns[0] / host_ns[2] / 1e3, "wait": host_ns[1] / host_ns[2] / 1e3}
+                if pipelined is None or v > pipelined:
+                    pipelined, best_depth = v, depth
         except Exception as e:  # noqa: BLE001 -- the serial number stands
             print(f"pipelined e2e unavailable: {e}", file=sys.stderr)
+        for e2 in ring[1:]:
+            try:
+                e2.sync()
+                e2.close()
+            except Exception:  # noqa: BLE001
+                pass
     if pipelined and pipelined > value:
         value = pipelined
     eng.set_sparse_check(0)
@@ -597,10 +622,11 @@ def measure_e2e(bench, eng, snap, Wp, args, checks_per_step):
     floor = checks_per_step / world / (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * world
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
             "path": (("kt_step_submit (kt_upload_pods_packed x2 + kt_evaluate + result copies) + kt_step_wait, pinned host buffers; " +
-                      ("two contexts alternating: step k+1 is submitted before step k is waited for" if pipelined and value == pipelined else "one context, serial"))
+                      (f"{best_depth} contexts in a ring: step k+{best_depth - 1} is submitted before step k is waited for" if pipelined and value == pipelined else "one context, serial"))
                      if packed else "kt_upload_pods x2 + kt_evaluate + kt_get_check_sparse + kt_get_reconcile (pinned host buffers)"),
             "serial": {"value": serial_value, "note": "one context: submit, wait, submit, ..."},
-            "double_buffered": {"value": pipelined, "note": "two contexts alternate: step k+1's upload overlaps step k's pass and download"},
+            "double_buffered": {"value": pipelined, "contexts": best_depth, "by_contexts": depth_values, "host_us_per_step": host_us,
+                                "note": "D contexts in a ring: the uploads of the next steps overlap this step's pass and download; every step still copies its inputs in and its results out and is waited for"},
             "separate_calls": {"value": separate_calls_value, "note": "kt_upload_pods_packed x2 + kt_evaluate + kt_get_check_sparse + kt_get_reconcile, one context"},
             "sparse_check_entries": n_sparse, "upload_memory": upload_memory, "pinned_upload_value": pinned_value, "host_affinity": bench.host_affinity,
             "wide_int64_upload": {"value": wide_value, "h2d_bytes_per_step": h2d_wide, "d2h_bytes_per_step": d2h_dense},

@@ -157,10 +157,11 @@ def measured_traffic(config, rows_scale):
         d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         e = d.get(f"{config}x{rows_scale}")
         if e:
-            return e["dram_bytes_read"] + e["dram_bytes_write"], e.get("source")
+            pipes = {k: e[k] for k in ("sm_throughput_pct", "issue_active_pct", "alu_pipe_pct", "lsu_pipe_pct", "dram_throughput_pct") if k in e and e[k] == e[k]}
+            return e["dram_bytes_read"] + e["dram_bytes_write"], e.get("source"), pipes
     except Exception:
         pass
-    return None, None
+    return None, None, None
 
 
 def algorithmic_bytes(snap, Wp):
@@ -704,13 +705,14 @@ def main():
     # The timed region launches ONE kernel per step (k_pass: match + reconcile + finalize + decide tiles), so that is the
     # dominant kernel and its average launch duration is region / K.  The three-kernel breakdown (kt_enable_timing switches
     # the library to its PDL-chained launch path) is reported beside it: `reconcile` is where the bytes are.
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch needs ncu, which bench.py does not run: the
-    # capture of the benched build is profiles/r2_ncu_pass_C2.txt (see profiles/README.md); null here rather than pasted.
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch needs ncu, which bench.py does not run: they are
+    # read from the committed capture of this workload (profiles/r2_traffic.json <- tools/ncu_traffic.py <- the .ncu-rep), with
+    # the pipe utilisations of the same capture (ALU pipe next to HBM %); null when there is no capture.
     roofline = dict(head["roofline"])
-    traffic, traffic_src = measured_traffic(args.config, args.rows_scale)
+    traffic, traffic_src, pipes = measured_traffic(args.config, args.rows_scale)
     moved = moved_bytes_estimate(snap, Wp)
     roofline.update({"traffic": traffic, "traffic_source": traffic_src or "none committed for this workload (ncu is not run inside bench.py)",
-                     "moved_bytes_estimate": moved, "frac_moved": moved / (pass_ms * 1e-3) / 1e9 / peak,
+                     "pipes_under_ncu": pipes, "moved_bytes_estimate": moved, "frac_moved": moved / (pass_ms * 1e-3) / 1e9 / peak,
                      "note": "achieved / frac use SURVEY.md 8(d)'s algorithmic bytes (dense bitmap written once per pass); the pass maintains its "
                              "bitmaps word by word and stores int32 row offsets, so it moves fewer bytes than that -- frac_moved is the same time "
                              "against the bytes it has to move (latency-bound at this size either way)",

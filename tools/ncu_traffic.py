@@ -28,6 +28,11 @@ for arg in sys.argv[1:]:
 
     out[key] = {"kernel": d.get("Kernel Name", "?")[:80], "grid": d.get("Grid Size"), "dram_bytes_read": to_bytes("dram__bytes_read.sum"),
                 "dram_bytes_write": to_bytes("dram__bytes_write.sum"), "gpu_time_us_under_ncu": to_us("gpu__time_duration.sum"),
+                "sm_throughput_pct": float(d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", "nan")),
+                "issue_active_pct": float(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan")),
+                "alu_pipe_pct": float(d.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "nan")),
+                "lsu_pipe_pct": float(d.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "nan")),
+                "dram_throughput_pct": float(d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "nan")),
                 "source": f"profiles/{os.path.basename(rep).replace('.ncu-rep', '.txt')} (ncu --set full --clock-control none, one launch)"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -45,9 +45,7 @@ for cfg, kw in cases:
     # row deltas: a few running rows rewritten in place (with their own values)
     k = min(17, snap.running.n)
     rows = np.sort(np.random.default_rng(1).choice(snap.running.n, size=k, replace=False)).astype(np.int64)
-    r = snap.running
-    eng.update_pod_rows(abi.PODS_RUNNING, rows, abi.PodCols(np.ascontiguousarray(r.labels[:, rows]), np.ascontiguousarray(r.req[:, rows]), r.present[rows].copy(),
-                                                             r.flags[rows].copy(), r.ns[rows].copy()))
+    eng.update_pod_rows(abi.PODS_RUNNING, rows, snap.running.rows(rows))
     eng.evaluate(snap.now)
     eng.sync()
     # observed status: device-side diff, changed rows, GIVEN_STATUS check, queue admission

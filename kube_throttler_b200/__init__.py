@@ -173,11 +173,11 @@ class Engine:
         self._ck(self._L.kt_enable_trace(self._h, int(on)))
 
     def trace(self):
-        """(rows[n][16] = ticket, sm, start_ns, end_ns, 12 stage stamps (4.. per role, see kt_kernels.cuh) ; roles[4] = tiles per role)
+        """(rows[n][32] = ticket, sm, start_ns, end_ns, 12 stage stamps (4.. per role, see kt_kernels.cuh), 16 cycle counts; roles[4] = tiles per role)
         of the last fused pass."""
         roles = np.zeros(4, np.uint32)
         n = self._L.kt_get_trace(self._h, None, 0, roles.ctypes.data)
-        rows = np.zeros((int(roles.sum()), 16), np.uint64)
+        rows = np.zeros((int(roles.sum()), 32), np.uint64)
         n = self._L.kt_get_trace(self._h, rows.ctypes.data, rows.shape[0], roles.ctypes.data)
         if n < 0:
             self._ck(int(n))

@@ -195,9 +195,6 @@ struct kt_ctx {
 #ifndef KT_WIDE_TILES  // 1: ClusterThrottle-heavy tables run the pass with 256-pod tiles
 #define KT_WIDE_TILES 1
 #endif
-#ifndef KT_PASS_RESIDENT  // 1: a pass whose whole grid fits the device keeps its match CTAs on as decide tiles
-#define KT_PASS_RESIDENT 1
-#endif
 #ifndef KT_PASS_PDL  // 1: k_pass is launched with programmatic stream serialization (its launch overlaps the previous kernel's tail)
 #define KT_PASS_PDL 1
 #endif
@@ -478,6 +475,13 @@ cudaError_t launch_pass(kt_ctx* c, const PassArgs& a0) {
   // (the status CTAs come last and are waited for by nobody on this GPU -- with peers only by decide tiles, after every
   // reconcile tile has left -- so they do not count)
   a.resident = (KT_PASS_RESIDENT != 0 && a.n_chk + a.n_rec <= capacity) ? 1u : 0u;
+  if (a.resident && KT_PASS_RESIDENT == 2) {
+    // shared second phase: the CTAs draw the decide sub-tiles and the status tiles from a ticket counter once their own tile
+    // is done; the grid is the match and reconcile tiles only
+    a.resident = 2u;
+    a.n_sub = (unsigned)((a.pend.n + TILE / 4 - 1) / (TILE / 4));
+    a.n_status = 0;
+  }
   if (c->trace) { c->trace_roles[0] = a.n_chk; c->trace_roles[1] = a.n_rec; c->trace_roles[2] = a.n_status; c->trace_roles[3] = a.resident ? 0 : a.n_chk; }
   return launch(c, k_pass<TPC, B, RT, REG, TILE>, (a.resident ? 1u : 2u) * a.n_chk + a.n_rec + a.n_status, TILE, smem, /*pdl=*/KT_PASS_PDL != 0, a);
 }
@@ -903,7 +907,7 @@ int kt_upload_throttles(kt_ctx* c, int32_t m, const kt_throttle_cols* cols, cons
   KT_CUDA(c, cudaMemsetAsync(c->d_part.p, 0, c->d_part.cap, c->stream));
   c->part_parity = 0;
   c->win_stale = c->win != nullptr;  // laid out for the previous M
-  KT_CUDA(c, c->d_pre.reserve((size_t)m * pre_record_bytes(R) + 16));
+  KT_CUDA(c, c->d_pre.reserve((size_t)((m + 31) & ~31) * pre_record_bytes(R) + 16));  // whole 32-throttle words: a decide slot is staged as one block
   KT_CUDA(c, c->d_changed.reserve(16 + (size_t)m * 5 + 16));
   KT_CUDA(c, cudaMemsetAsync(c->d_changed.p, 0, 16, c->stream));
   c->have_diff = false;

@@ -58,7 +58,7 @@ constexpr int kStageChunk = KT_STAGE_CHUNK;  // resources whose pre-record value
 #define KT_DECIDE_UNROLLED 0
 #endif
 constexpr int kPropose = 4;          // words a warp of a decide tile may propose to its CTA's staging table per round
-constexpr int kTraceRow = 16;        // u64 per CTA of the optional in-kernel trace: {ticket, sm, t_start, t_end, 12 stage stamps}
+constexpr int kTraceRow = 32;        // u64 per CTA of the optional in-kernel trace: {ticket, sm, t_start, t_end, 12 stage stamps (globaltimer ns), 16 cycle counts}
 
 // Word info of a pod row (k_translate_rows; valid for the tables it was computed with): the words whose namespace mask is
 // non-zero for the pod's namespace are the only ones the pod can match anything in.  Namespace-scoped Throttles give 1-3 of
@@ -207,10 +207,12 @@ struct PassSync {
   unsigned match_done;  // pending-match tiles finished (affectedThrottles rows written)
   unsigned tot_done;    // multi-GPU: finalize tiles of this rank that have written the all-rank totals of their throttles
   unsigned exited;      // CTAs that are done with everything; the last one re-arms the counters
+  unsigned dec_ticket;  // resident pass: next piece of the shared second phase (decide sub-tiles, status tiles)
+  unsigned spare;
   unsigned error;       // a wait gave up (kSpinTimeoutNs): a peer never arrived; the host reports it, the results are void
-  unsigned pad;
+  unsigned pad[3];
 };
-constexpr int kPassSyncRearm = 6;  // leading counters the last CTA out (or the host, after a timed-out pass) zeroes
+constexpr int kPassSyncRearm = 8;  // leading counters the last CTA out (or the host, after a timed-out pass) zeroes
 // Polling loads are RELAXED (performed at L2 / at the peer, no side effects on this SM); the acquire comes once, as one
 // acquire load of the same counter after the awaited value has been seen.  An acquire load per poll would invalidate the
 // SM's L1 on every iteration (CCTL.IVALL) and take the table rows of the tiles still working on that SM with it; an
@@ -652,10 +654,78 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return (unsigned long long)lo + ((unsigned long long)mi << 22) + ((unsigned long long)hi << 44);
 }
 
+// ---- bulk asynchronous copies (TMA engine, no tensor map: cp.async.bulk) completing on an mbarrier --------------------------
+// One elected lane arms the barrier with the byte count and issues the copies; the data lands in shared memory without passing
+// through anybody's registers and the consumers sleep on the barrier's phase instead of a scoreboard.  SASS: UBLKCP / SYNCS.
+#ifndef KT_BULK_ROWS  // 1: a reconcile tile's column slices (row offsets, requests, flags ...) are staged with bulk copies; 0: per-lane LDG.
+#define KT_BULK_ROWS 0  // Measured slower (profiles/README.md r2b: C2 +0.5 us, C2 x10 +4 us, C4 +0.7 us -- sixteen 0.5-1 KB copies per tile) -- off
+#endif
+#ifndef KT_SMEM_ADD32  // 1: 64-bit shared-memory accumulator adds as two native 32-bit atomics with a carry; 0: atomicAdd(u64) (a CAS loop)
+#define KT_SMEM_ADD32 1
+#endif
+#ifndef KT_PASS_RESIDENT  // 1: a pass whose whole grid fits the device keeps its match CTAs on as decide tiles; 2: ... and every CTA that
+#define KT_PASS_RESIDENT 2  // has finished its own tile shares the decide work (check_decide_quad)
+#endif
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy accesses to shared memory (earlier ST / LD of the same bytes) are ordered before the async-proxy copy that follows
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes),
+               "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {}  // try_wait suspends the thread for a hardware-chosen interval by itself
+}
+constexpr int kMaxWarps = 8;  // of a pass CTA (TILE <= 256)
+
+// 64-bit add into a shared-memory accumulator.  atomicAdd(unsigned long long*) on shared memory compiles to a compare-and-swap
+// loop (ATOMS.CAST.SPIN); two native 32-bit adds do the same mod 2^64: the low add returns the old low word, which tells
+// whether THIS add carried, and the carry travels with the high word.  (The halves are only read together after a barrier.)
+__device__ __forceinline__ void smem_add_u64(unsigned long long* acc, unsigned long long v) {
+  if constexpr (KT_SMEM_ADD32 != 0) {
+    unsigned* w = reinterpret_cast<unsigned*>(acc);
+    const unsigned lo = (unsigned)v;
+    unsigned hi = (unsigned)(v >> 32);
+    if (lo) {
+      const unsigned old = atomicAdd(w, lo);
+      hi += (old + lo) < old ? 1u : 0u;
+    }
+    if (hi) atomicAdd(w + 1, hi);
+  } else {
+    atomicAdd(acc, v);
+  }
+}
+
 // Shared-memory carve-up of k_reconcile (host and device must agree).  S = accumulator slots.
+constexpr int kStageCols = 12;  // u32 columns of a bulk-staged tile: 8 row offsets, winfo, flags, ns, present
+__host__ __device__ inline size_t reconcile_stage_offset(int L, int R, int S, bool reg_rows, int tile) {
+  const size_t b = (size_t)R * tile * 8 + (size_t)S * R * 32 * 8 + (reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4) + (size_t)tile * 4 + (size_t)S * 32 * 4 * 2 +
+                   (size_t)S * 4;
+  return (b + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool reg_rows, int tile) {
-  return (size_t)R * tile * 8 + (size_t)S * R * 32 * 8 + (reg_rows ? 0 : (size_t)((L + 7) & ~7) * tile * 4) + (size_t)tile * 4 + (size_t)S * 32 * 4 * 2 +
-         (size_t)S * 4;
+  return reconcile_stage_offset(L, R, S, reg_rows, tile) + (KT_BULK_ROWS != 0 && reg_rows ? (size_t)kStageCols * tile * 4 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,7 +738,8 @@ __host__ __device__ inline size_t reconcile_smem_bytes(int L, int R, int S, bool
 template <int TPC, int B, int RT, bool REG, int TILE = kTileReconcile>
 __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableView& tb, int L, int R, int S, uint32_t* __restrict__ bitmap,
                                                unsigned long long* __restrict__ part /* [2R+1][M]: used, present, cnt */,
-                                               unsigned char* smem_raw, int64_t tile_index, unsigned long long* trace_row = nullptr) {
+                                               unsigned char* smem_raw, int64_t tile_index, unsigned long long* trace_row = nullptr,
+                                               unsigned long long* row_bar = nullptr /* fresh transaction barrier (count 1, phase 0): stage the rows in bulk */) {
   // optional stage stamps of warp 0 (kt_enable_trace): [4] the pod rows have landed, [5] first two words evaluated, [6] barrier
   // passed, [7] words + sums done, [8] sweep done
   auto stamp = [&](int k) {
@@ -693,22 +764,43 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   const int64_t p = tile0 + tid;
   const bool valid = p < pods.n;
   const int64_t pc = valid ? p : pods.n - 1;  // clamped: every lane loads, invalid lanes are masked below
-  // ---- everything the lane needs of its pod row is requested at once: ONE trip to HBM, and nothing else is waited for
-  // before the table gathers of the first two words go out ----
-  const uint32_t winfo = __ldg(&pods.winfo[pc]);
-  const uint32_t flags = valid ? __ldg(&pods.flags[pc]) : 0u;
-  const int ns = __ldg(&pods.ns[pc]);
-  const uint32_t present = __ldg(&pods.present[pc]);
+  // ---- everything the tile needs of its pod rows is requested at once: ONE trip to HBM, and nothing else is waited for
+  // before the table gathers of the first two words go out.  A full tile of 16-byte aligned columns is fetched by the copy
+  // engine: thread 0 arms a transaction barrier and issues one bulk copy per column slice (8 row offsets, winfo, flags, ns,
+  // present: TILE * 4 bytes each; R request columns: TILE * 8 bytes each, straight into s_req) -- the slices land in shared
+  // memory without occupying anybody's registers or load queue; everybody else sleeps on the barrier.  Ragged tiles and
+  // unaligned tables (n not a multiple of 4) take the per-lane loads.
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_raw + reconcile_stage_offset(L, R, S, REG, TILE));  // [kStageCols][TILE]
+  const bool bulk = KT_BULK_ROWS != 0 && REG && RT > 0 && row_bar != nullptr && (pods.n & 3) == 0 && tile0 + TILE <= pods.n;  // CTA-uniform
+  if (bulk && tid == 0) {
+    mbar_expect_tx(row_bar, (unsigned)(kStageCols * TILE * 4 + R * TILE * 8));
+#pragma unroll
+    for (int kcol = 0; kcol < 8; ++kcol) bulk_copy_g2s(s_stage + kcol * TILE, pods.roff + (int64_t)kcol * pods.n + tile0, TILE * 4, row_bar);
+    bulk_copy_g2s(s_stage + 8 * TILE, pods.winfo + tile0, TILE * 4, row_bar);
+    bulk_copy_g2s(s_stage + 9 * TILE, pods.flags + tile0, TILE * 4, row_bar);
+    bulk_copy_g2s(s_stage + 10 * TILE, pods.ns + tile0, TILE * 4, row_bar);
+    bulk_copy_g2s(s_stage + 11 * TILE, pods.present + tile0, TILE * 4, row_bar);
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) bulk_copy_g2s(s_req + (size_t)r * TILE, pods.req + (int64_t)r * pods.n + tile0, TILE * 8, row_bar);
+  }
+  uint32_t winfo, flags, present;
+  int ns;
   PodRows<REG> rows;
   rows.init(s_rowid, tid, TILE);
-  load_rows<REG>(pods.roff, pods.n, pc, L, rows);
   long long rq[RT > 0 ? RT : 1];
-  if constexpr (RT > 0) {
-    const int64_t* rp = pods.req + pc;
+  if (!bulk) {
+    winfo = __ldg(&pods.winfo[pc]);
+    flags = valid ? __ldg(&pods.flags[pc]) : 0u;
+    ns = __ldg(&pods.ns[pc]);
+    present = __ldg(&pods.present[pc]);
+    load_rows<REG>(pods.roff, pods.n, pc, L, rows);
+    if constexpr (RT > 0) {
+      const int64_t* rp = pods.req + pc;
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      rq[r] = r < R ? __ldg(rp) : 0;
-      rp += pods.n;
+      for (int r = 0; r < RT; ++r) {
+        rq[r] = r < R ? __ldg(rp) : 0;
+        rp += pods.n;
+      }
     }
   }
   // The match bitmap is maintained, not rebuilt: a row can only ever be non-zero in the words of its namespace's list, so a
@@ -724,6 +816,21 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
     for (int i = tid; i < S * R * 32; i += TILE) s_used[i] = 0ull;
     for (int i = tid; i < S * 32; i += TILE) { s_cnt[i] = 0u; s_pres[i] = 0u; }
     if (tid < S) s_key[tid] = -1;
+  }
+  if constexpr (KT_BULK_ROWS != 0 && REG && RT > 0) {
+    if (bulk) {  // the slices have landed: the lane's own row out of shared memory
+      mbar_wait(row_bar, 0u);
+      winfo = s_stage[8 * TILE + tid];
+      flags = s_stage[9 * TILE + tid];
+      ns = (int)s_stage[10 * TILE + tid];
+      present = s_stage[11 * TILE + tid];
+#pragma unroll
+      for (int kcol = 0; kcol < 8; ++kcol) rows.off[kcol] = s_stage[kcol * TILE + tid];
+      // ResourceAmountOfPod(p) columns are in place; absent keys read as 0 (presence kept separately)
+#pragma unroll 1
+      for (int r = 0; r < R; ++r)
+        if (!((present >> r) & 1)) s_req[r * TILE + tid] = 0;
+    }
   }
   // shouldCountIn (throttle_controller.go:217-219): schedulerName == target && nodeName != ""
   const bool counted = (flags & (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED)) == (KT_POD_SCHEDULER_MATCH | KT_POD_SCHEDULED) &&
@@ -745,9 +852,11 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   }
   // ResourceAmountOfPod(p) columns -> shared memory (absent keys read as 0; presence kept separately)
   if constexpr (RT > 0) {
+    if (!bulk) {
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
-      if (r < R) s_req[r * TILE + tid] = ((present >> r) & 1) ? rq[r] : 0;
+      for (int r = 0; r < RT; ++r)
+        if (r < R) s_req[r * TILE + tid] = ((present >> r) & 1) ? rq[r] : 0;
+    }
   } else {
     const int64_t* rp = pods.req + pc;
     for (int r = 0; r < R; ++r) {
@@ -770,7 +879,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
   // Rows in ARRIVAL order (no two lanes of the warp in the same namespace): the word-by-word rounds below would run once per
   // lane for a handful of matches each.  Such a warp adds its pods' requests straight to the per-throttle sums in L2, one
   // RED per (matched throttle, resource) -- slower per match than the transposed sums, but no rounds.
-  if (warp_is_scattered(wc)) {
+  if (KT_SCATTER_WORDS < 32 && warp_is_scattered(wc)) {
 #pragma unroll 1
     for (int kk = 0; kk < wc.cnt; ++kk) {
       const int w = wc.at(tb, kk);
@@ -882,7 +991,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
         atomicOr(&s_pres[slot * 32 + lane], pres);
 #pragma unroll
         for (int r = 0; r < RT; ++r)
-          if (r < R && acc[r]) atomicAdd(&s_used[(slot * R + r) * 32 + lane], acc[r]);
+          if (r < R && acc[r]) smem_add_u64(&s_used[(slot * R + r) * 32 + lane], acc[r]);
       } else {  // more distinct words in this CTA than slots: straight to HBM
         atomicAdd(&part_cnt[t], (unsigned long long)cnt);
 #pragma unroll
@@ -906,7 +1015,7 @@ __device__ __forceinline__ void reconcile_tile(const PodView& pods, const TableV
         for (int r = 0; r < R; ++r) {
           const unsigned long long v = (unsigned long long)s_req[r * TILE + i];
           if (slot >= 0) {
-            if (v) atomicAdd(&s_used[(slot * R + r) * 32 + lane], v);
+            if (v) smem_add_u64(&s_used[(slot * R + r) * 32 + lane], v);
           } else {
             if (v) atomicAdd(&part_used[(size_t)r * tb.M + t], v);
             if ((pres >> r) & 1) part_pres[(size_t)r * tb.M + t] = 1ull;
@@ -1093,19 +1202,17 @@ __device__ __forceinline__ void finalize_tile(const ThrottleView& tv, int M, int
     unsigned long long h = is_res ? __ldcg(&px.mine[i_has]) : 0ull;
     if (px.npeers > 0) {
       // send first (to every peer), then receive: nobody waits for anybody before its own values are on the wire
-#pragma unroll
-      for (int i = 0; i < 7; ++i)
-        if (i < px.npeers) {
-          unsigned long long* slot = px.peer_slots[i] + ((size_t)px.rank * px.len + i_val) * 2;
-          ll_send(slot, v, px.epoch);
-          if (is_res) ll_send(px.peer_slots[i] + ((size_t)px.rank * px.len + i_has) * 2, h, px.epoch);
-        }
-#pragma unroll
-      for (int i = 0; i < 7; ++i)
-        if (i < px.npeers) {
-          v += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_val) * 2, px.epoch, sync.error_flag());
-          if (is_res) h += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_has) * 2, px.epoch, sync.error_flag());
-        }
+#pragma unroll 1
+      for (int i = 0; i < px.npeers; ++i) {
+        unsigned long long* slot = px.peer_slots[i] + ((size_t)px.rank * px.len + i_val) * 2;
+        ll_send(slot, v, px.epoch);
+        if (is_res) ll_send(px.peer_slots[i] + ((size_t)px.rank * px.len + i_has) * 2, h, px.epoch);
+      }
+#pragma unroll 1
+      for (int i = 0; i < px.npeers; ++i) {
+        v += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_val) * 2, px.epoch, sync.error_flag());
+        if (is_res) h += ll_recv(px.slots + ((size_t)px.peer_rank[i] * px.len + i_has) * 2, px.epoch, sync.error_flag());
+      }
       px.total[i_val] = v;
       if (is_res) px.total[i_has] = h;
     }
@@ -1253,6 +1360,238 @@ __device__ __forceinline__ void check_match_tile(const PodView& pods, const Tabl
 // into the CTA's staging slots.  After the wait one lane per (slot, throttle) fetches that throttle's sums -- one trip to
 // L2 for the whole CTA -- and finishes the record in place (what a finalize stage between reconcile and decide used to
 // hand over); then every lane decides its own pairs from shared memory.
+//
+// The building blocks, shared by the two decide tiles below (lane = pod: check_decide_tile; four lanes per pod, one per word:
+// check_decide_quad).
+
+// What a decide lane knows of its pod: the non-zero requests (IsThrottledFor only looks at those, Q5) and where they sit.
+struct DecidePod {
+  const long long* req;  // &s_req[column of this pod]; resource r at req[r * stride]
+  int stride;
+  uint32_t nz;
+  int64_t p;             // pending row
+};
+
+// one lane's verdicts on (some of) the throttles of one word, from the finished records of its slot: 2-bit codes, low / high half
+template <int RT>
+__device__ __forceinline__ uint2 decide_word_codes(uint32_t word, const unsigned char* recs, size_t rec, int R, const DecidePod& pod) {
+  uint32_t c0 = 0, c1 = 0;
+  const uint32_t nz = pod.nz;
+  while (word) {
+    const int b = __ffs(word) - 1;
+    word &= word - 1;
+    const unsigned char* cb = recs + (size_t)b * rec;
+    const uint4 hq = *reinterpret_cast<const uint4*>(cb);
+    const long long* thrv = reinterpret_cast<const long long*>(cb + 16);
+    const long long* head = thrv + R;
+    const uint32_t cand = nz & hq.x;
+    uint32_t code;
+    bool s1 = hq.w & 1u, s4 = hq.w & 8u;  // the count lane's share of S1 / S4
+    const bool ge = hq.w & 16u;
+    if constexpr (RT > 0 && KT_DECIDE_UNROLLED) {
+      // every resource compared, no data-dependent loop -- measured SLOWER than the loops below at C2 (pods ask for one or two
+      // of the throttles' resources; the loops stop at the first hit): kept behind KT_DECIDE_UNROLLED, off
+      // (S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod); S4 used + pod + reserved against the threshold)
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        if (r < R) {
+          const long long v = pod.req[r * pod.stride];
+          const bool on = (cand >> r) & 1;
+          s1 = s1 || (on && v > thrv[r]);
+          const long long hd = head[r];
+          s4 = s4 || (on && (ge ? v >= hd : v > hd));
+        }
+      }
+    } else {
+      for (uint32_t c = cand; c && !s1;) {
+        const int r = __ffs(c) - 1;
+        c &= c - 1;
+        s1 = pod.req[r * pod.stride] > thrv[r];
+      }
+      for (uint32_t c = cand; c && !s4;) {
+        const int r = __ffs(c) - 1;
+        c &= c - 1;
+        const long long v = pod.req[r * pod.stride];
+        const long long hd = head[r];
+        s4 = ge ? v >= hd : v > hd;
+      }
+    }
+    if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
+    else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
+    else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
+    else code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
+    if (b < 16) c0 |= code << (2 * b);
+    else c1 |= code << (2 * (b - 16));
+  }
+  return make_uint2(c0, c1);
+}
+// the code words of (pending row, word w) go out -- unconditionally: the code rows are maintained word by word, a pair that was
+// rejected by the previous pass and is not any more must read 0 again (codes can only be non-zero where match bits are, and
+// those do not move between passes)
+__device__ __forceinline__ void store_codes(uint2 c, int w, int Wp, int64_t p, uint32_t* __restrict__ codes, const SparseOut& sp, unsigned char& ok) {
+  if (c.x | c.y) ok = 0;
+  *reinterpret_cast<uint2*>(&codes[p * 2 * Wp + 2 * w]) = c;
+  if (sp.count) {
+    if (c.x) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c.x);
+    if (c.y) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c.y);
+  }
+}
+template <int RT>
+__device__ __forceinline__ void decide_word(uint32_t word, int w, const unsigned char* recs, size_t rec, int R, int Wp, const DecidePod& pod,
+                                            uint32_t* __restrict__ codes, const SparseOut& sp, unsigned char& ok) {
+  store_codes(decide_word_codes<RT>(word, recs, rec, R, pod), w, Wp, pod.p, codes, sp, ok);
+}
+
+// lane = throttle of word w: the raw pre-record into the staging slot (nothing here depends on the running pods)
+__device__ __forceinline__ void stage_pre_record(const unsigned char* __restrict__ pre, int w, uint32_t any, unsigned char* slot_recs, size_t rec, int R, int lane) {
+  if (w < 0 || !((any >> lane) & 1)) return;
+  const uint4* src = reinterpret_cast<const uint4*>(pre + (size_t)(w * 32 + lane) * rec);  // written earlier in this launch by another SM:
+  uint4* dst = reinterpret_cast<uint4*>(slot_recs + (size_t)lane * rec);                   // __ldcg, L2 is the point of coherence
+  for (int q = 0; q < R + 2; ++q) dst[q] = __ldcg(&src[q]);
+}
+// ... and, once the sums exist, the constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55)
+// in place.  alreadyUsed = status.used + reserved (absent values are 0, presence is the union); in GIVEN_STATUS mode
+// status.used and status.throttled are the observed ones and the sums are not looked at.
+__device__ __forceinline__ void stage_finish_record(const PartExchange& px, int w, uint32_t any, unsigned char* slot_recs, size_t rec, int R, int M, int lane) {
+  if (w < 0 || !((any >> lane) & 1)) return;
+  const int t = w * 32 + lane;
+  unsigned char* dst = slot_recs + (size_t)lane * rec;
+  long long* vals = reinterpret_cast<long long*>(dst + 16);  // thrv[R], base[R] -> head[R], thr_cnt, base_cnt
+  const PreHdr ph = *reinterpret_cast<const PreHdr*>(dst);
+  const bool live = ph.flags & kPreLive, e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
+  const long long c_used = given ? 0 : (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
+  CheckHdr h;
+  h.thr_has = h.m2 = h.m3 = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < R; r0 += kStageChunk) {
+    unsigned long long used[kStageChunk], uhas[kStageChunk];
+#pragma unroll
+    for (int q = 0; q < kStageChunk; ++q) {
+      const int r = r0 + q < R ? r0 + q : R - 1;  // clamped: the loads stay unconditional and in flight together
+      used[q] = given ? 0ull : __ldcg(&px.total[(size_t)r * M + t]);
+      uhas[q] = given ? 0ull : __ldcg(&px.total[(size_t)(R + r) * M + t]);
+    }
+#pragma unroll
+    for (int q = 0; q < kStageChunk; ++q) {
+      const int r = r0 + q;
+      if (r < R) {
+        const long long thr = vals[r];
+        long long au = vals[R + r];
+        const bool has = (ph.thr_has >> r) & 1;
+        bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
+        if (!given) {
+          const bool used_has = uhas[q] != 0ull;
+          au += (long long)used[q];
+          au_has = au_has || used_has;
+          m2 = has && used_has && (long long)used[q] >= thr;  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
+        }
+        const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+        vals[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
+        h.thr_has |= (has ? 1u : 0u) << r;
+        h.m2 |= (m2 ? 1u : 0u) << r;
+        h.m3 |= (s3 ? 1u : 0u) << r;
+      }
+    }
+  }
+  {  // the pod count: the pending pod itself counts 1
+    const long long thr = vals[2 * R];
+    long long au = vals[2 * R + 1];
+    const bool has = ph.thr_has & KT_COUNT_BIT;
+    bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
+    if (!given) {
+      const bool used_has = c_used > 0;  // Counts stays nil with zero counted pods (Q3)
+      au += c_used;
+      au_has = au_has || used_has;
+      m2 = has && used_has && c_used >= thr;
+    }
+    const bool s1 = has && 1 > thr;                                           // S1: pod count 1 > threshold (Q4)
+    const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
+    const bool s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);         // S4 (counts always present: the pod)
+    h.cntbits = (on_equal ? 16u : 0u) | (s1 ? 1u : 0u) | (m2 ? 2u : 0u) | (s3 ? 4u : 0u) | (s4 ? 8u : 0u);
+  }
+  if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
+  *reinterpret_cast<CheckHdr*>(dst) = h;
+}
+
+// One pair checked straight from L2 (pre-record + sums), no staging: for the pairs whose word found no staging slot (rows in
+// ARRIVAL order: a different namespace in every lane).  The same 4 steps.
+__device__ __forceinline__ uint32_t decide_pair_direct(const unsigned char* __restrict__ pre, const PartExchange& px, size_t rec, int R, int M, int t,
+                                                       const DecidePod& pod) {
+  const unsigned char* src = pre + (size_t)t * rec;
+  const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));
+  const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
+  PreHdr ph;
+  ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
+  if (!(ph.flags & kPreLive)) return KT_CHECK_NOT_THROTTLED;
+  const bool e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
+  bool s1, s2, s3, s4;
+  {  // the pod count: the pending pod itself counts 1
+    const long long thr = __ldcg(&pv[2 * R]);
+    long long au = __ldcg(&pv[2 * R + 1]);
+    const bool has = ph.thr_has & KT_COUNT_BIT;
+    bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
+    if (!given) {
+      const long long used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
+      const bool used_has = used > 0;
+      au += used;
+      au_has = au_has || used_has;
+      m2 = has && used_has && used >= thr;
+    }
+    s1 = has && 1 > thr;
+    s2 = m2;
+    s3 = has && au_has && (e3 ? au >= thr : au > thr);
+    s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);
+  }
+  for (uint32_t c = pod.nz; c;) {  // IsThrottledFor only looks at the pod's non-zero requests (Q5)
+    const int r = __ffs(c) - 1;
+    c &= c - 1;
+    const long long thr = __ldcg(&pv[r]);
+    long long au = __ldcg(&pv[R + r]);
+    const bool has = (ph.thr_has >> r) & 1;
+    bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
+    if (!given) {
+      const long long used = (long long)__ldcg(&px.total[(size_t)r * M + t]);
+      const bool used_has = __ldcg(&px.total[(size_t)(R + r) * M + t]) != 0ull;
+      au += used;
+      au_has = au_has || used_has;
+      m2 = has && used_has && used >= thr;
+    }
+    const long long v = pod.req[r * pod.stride];
+    s1 = s1 || (has && v > thr);
+    s2 = s2 || m2;
+    s3 = s3 || (has && au_has && (e3 ? au >= thr : au > thr));
+    s4 = s4 || (has && (on_equal ? v >= thr - au : v > thr - au));
+  }
+  return s1 ? KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD : ((s2 || s3) ? KT_CHECK_ACTIVE : (s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED));
+}
+// ... a whole word of such pairs
+__device__ __forceinline__ uint2 decide_word_direct_codes(uint32_t word, int w, const unsigned char* __restrict__ pre, const PartExchange& px, size_t rec, int R,
+                                                          int M, const DecidePod& pod) {
+  uint32_t c0 = 0, c1 = 0;
+  while (word) {
+    const int b = __ffs(word) - 1;
+    word &= word - 1;
+    const uint32_t code = decide_pair_direct(pre, px, rec, R, M, w * 32 + b, pod);
+    if (b < 16) c0 |= code << (2 * b);
+    else c1 |= code << (2 * (b - 16));
+  }
+  return make_uint2(c0, c1);
+}
+__device__ __forceinline__ void decide_word_direct(uint32_t word, int w, const unsigned char* __restrict__ pre, const PartExchange& px, size_t rec, int R, int M,
+                                                   int Wp, const DecidePod& pod, uint32_t* __restrict__ codes, const SparseOut& sp, unsigned char& ok) {
+  store_codes(decide_word_direct_codes(word, w, pre, px, rec, R, M, pod), w, Wp, pod.p, codes, sp, ok);
+}
+
+// the same out of line (everything by value: nothing of the caller has to live in local memory for it): the shared decide
+// tiles take this path only for words that found no staging slot, and keep their own code short
+__device__ __noinline__ uint2 decide_word_direct_far(uint32_t word, int w, const unsigned char* __restrict__ pre, unsigned long long* total, unsigned rec, int R, int M,
+                                                     const long long* req, int stride, uint32_t nz) {
+  PartExchange px{};
+  px.total = total;
+  const DecidePod pod{req, stride, nz, 0};
+  return decide_word_direct_codes(word, w, pre, px, rec, R, M, pod);
+}
+
 template <int TILE, int RT, class Sync>
 __device__ __forceinline__ void check_decide_tile(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
                                                   const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
@@ -1295,6 +1634,7 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       if (v != 0) nz |= 1u << r;
     }
   }
+  const DecidePod pod{s_req + tid, TILE, nz, p};
   if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
   WordCursor wc;
   wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
@@ -1307,209 +1647,17 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
   int k = 0;
   int cur = wc.at(tb, 0);
   bool sums_awaited = false;
-  // one lane's verdicts on the throttles of one word, from the finished records of its slot
-  auto decide_word = [&](uint32_t word, int w, const unsigned char* recs) {
-    uint32_t c0 = 0, c1 = 0;
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      const unsigned char* cb = recs + (size_t)b * rec;
-      const uint4 hq = *reinterpret_cast<const uint4*>(cb);
-      const long long* thrv = reinterpret_cast<const long long*>(cb + 16);
-      const long long* head = thrv + R;
-      const uint32_t cand = nz & hq.x;
-      uint32_t code;
-      bool s1 = hq.w & 1u, s4 = hq.w & 8u;  // the count lane's share of S1 / S4
-      const bool ge = hq.w & 16u;
-      if constexpr (RT > 0 && KT_DECIDE_UNROLLED) {
-        // every resource compared, no data-dependent loop -- measured SLOWER than the loops below at C2 (pods ask for one or two
-        // of the throttles' resources; the loops stop at the first hit): kept behind KT_DECIDE_UNROLLED, off
-        // (S1 threshold.IsThrottled(podAmount, false).IsThrottledFor(pod); S4 used + pod + reserved against the threshold)
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          if (r < R) {
-            const long long v = s_req[r * TILE + tid];
-            const bool on = (cand >> r) & 1;
-            s1 = s1 || (on && v > thrv[r]);
-            const long long hd = head[r];
-            s4 = s4 || (on && (ge ? v >= hd : v > hd));
-          }
-        }
-      } else {
-        for (uint32_t c = cand; c && !s1;) {
-          const int r = __ffs(c) - 1;
-          c &= c - 1;
-          s1 = s_req[r * TILE + tid] > thrv[r];
-        }
-        for (uint32_t c = cand; c && !s4;) {
-          const int r = __ffs(c) - 1;
-          c &= c - 1;
-          const long long v = s_req[r * TILE + tid];
-          const long long hd = head[r];
-          s4 = ge ? v >= hd : v > hd;
-        }
-      }
-      if (s1) code = KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD;
-      else if ((hq.w & 2u) || (nz & hq.y)) code = KT_CHECK_ACTIVE;   // S2 status.throttled.IsThrottledFor(pod)
-      else if ((hq.w & 4u) || (nz & hq.z)) code = KT_CHECK_ACTIVE;   // S3 used+reserved already over
-      else code = s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED;
-      if (code) ok = 0;
-      if (b < 16) c0 |= code << (2 * b);
-      else c1 |= code << (2 * (b - 16));
-    }
-    // unconditional: the code rows are maintained word by word -- a pair that was rejected by the previous pass and is not any
-    // more must read 0 again (codes can only be non-zero where match bits are, and those do not move between passes)
-    *reinterpret_cast<uint2*>(&codes[p * 2 * Wp + 2 * w]) = make_uint2(c0, c1);
-    if (sp.count) {
-      if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
-      if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
-    }
-  };
-  // lane = throttle of slot `slot`: the raw pre-record into the slot (nothing here depends on the running pods)
-  auto stage_pre = [&](int slot) {
-    const int w = s_key[slot];
-    if (w < 0 || !((s_any[slot] >> lane) & 1)) return;
-    const uint4* src = reinterpret_cast<const uint4*>(pre + (size_t)(w * 32 + lane) * rec);  // written earlier in this launch by another SM:
-    uint4* dst = reinterpret_cast<uint4*>(s_chk + ((size_t)slot * 32 + lane) * rec);         // __ldcg, L2 is the point of coherence
-    for (int q = 0; q < R + 2; ++q) dst[q] = __ldcg(&src[q]);
-  };
-  // ... and, once the sums exist, the constants of CheckThrottledFor (throttle_types.go:128-153 / clusterthrottle_types.go:30-55)
-  // in place.  alreadyUsed = status.used + reserved (absent values are 0, presence is the union); in GIVEN_STATUS mode
-  // status.used and status.throttled are the observed ones and the sums are not looked at.
-  auto stage_post = [&](int slot) {
-    const int w = s_key[slot];
-    if (w < 0 || !((s_any[slot] >> lane) & 1)) return;
-    const int t = w * 32 + lane;
-    unsigned char* dst = s_chk + ((size_t)slot * 32 + lane) * rec;
-    long long* vals = reinterpret_cast<long long*>(dst + 16);  // thrv[R], base[R] -> head[R], thr_cnt, base_cnt
-    const PreHdr ph = *reinterpret_cast<const PreHdr*>(dst);
-    const bool live = ph.flags & kPreLive, e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
-    const long long c_used = given ? 0 : (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
-    CheckHdr h;
-    h.thr_has = h.m2 = h.m3 = 0;
-#pragma unroll 1
-    for (int r0 = 0; r0 < R; r0 += kStageChunk) {
-      unsigned long long used[kStageChunk], uhas[kStageChunk];
-#pragma unroll
-      for (int q = 0; q < kStageChunk; ++q) {
-        const int r = r0 + q < R ? r0 + q : R - 1;  // clamped: the loads stay unconditional and in flight together
-        used[q] = given ? 0ull : __ldcg(&px.total[(size_t)r * M + t]);
-        uhas[q] = given ? 0ull : __ldcg(&px.total[(size_t)(R + r) * M + t]);
-      }
-#pragma unroll
-      for (int q = 0; q < kStageChunk; ++q) {
-        const int r = r0 + q;
-        if (r < R) {
-          const long long thr = vals[r];
-          long long au = vals[R + r];
-          const bool has = (ph.thr_has >> r) & 1;
-          bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
-          if (!given) {
-            const bool used_has = uhas[q] != 0ull;
-            au += (long long)used[q];
-            au_has = au_has || used_has;
-            m2 = has && used_has && (long long)used[q] >= thr;  // status.throttled of THIS pass: IsThrottled(used, onEqual = true)
-          }
-          const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
-          vals[R + r] = thr - au;  // head: S4 used + reserved + pod (>|>=) threshold  <=>  pod (>|>=) head
-          h.thr_has |= (has ? 1u : 0u) << r;
-          h.m2 |= (m2 ? 1u : 0u) << r;
-          h.m3 |= (s3 ? 1u : 0u) << r;
-        }
-      }
-    }
-    {  // the pod count: the pending pod itself counts 1
-      const long long thr = vals[2 * R];
-      long long au = vals[2 * R + 1];
-      const bool has = ph.thr_has & KT_COUNT_BIT;
-      bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
-      if (!given) {
-        const bool used_has = c_used > 0;  // Counts stays nil with zero counted pods (Q3)
-        au += c_used;
-        au_has = au_has || used_has;
-        m2 = has && used_has && c_used >= thr;
-      }
-      const bool s1 = has && 1 > thr;                                           // S1: pod count 1 > threshold (Q4)
-      const bool s3 = has && au_has && (e3 ? au >= thr : au > thr);
-      const bool s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);         // S4 (counts always present: the pod)
-      h.cntbits = (on_equal ? 16u : 0u) | (s1 ? 1u : 0u) | (m2 ? 2u : 0u) | (s3 ? 4u : 0u) | (s4 ? 8u : 0u);
-    }
-    if (!live) { h.thr_has = h.m2 = h.m3 = 0; h.cntbits &= 16u; }
-    *reinterpret_cast<CheckHdr*>(dst) = h;
-  };
 
   // Pending rows in ARRIVAL order (a different namespace in every lane): staging 32-throttle records word by word would take
   // one round per lane.  Such a warp checks its pairs one by one instead, every constant fetched from L2 -- the same 4 steps,
   // without the staging (done below, once the sums exist); it proposes no words to the CTA's rounds.
-  const bool scattered = warp_is_scattered(wc);
+  const bool scattered = KT_SCATTER_WORDS < 32 && warp_is_scattered(wc);
   if (scattered) cur = 0x7fffffff;
-  auto pair_direct = [&](int t) -> uint32_t {
-    const unsigned char* src = pre + (size_t)t * rec;
-    const uint4 phq = __ldcg(reinterpret_cast<const uint4*>(src));
-    const long long* pv = reinterpret_cast<const long long*>(src + 16);  // thrv[R], base[R], thr_cnt, base_cnt
-    PreHdr ph;
-    ph.thr_has = phq.x; ph.base_has = phq.y; ph.st_thr = phq.z; ph.flags = phq.w;
-    if (!(ph.flags & kPreLive)) return KT_CHECK_NOT_THROTTLED;
-    const bool e3 = ph.flags & kPreE3, on_equal = ph.flags & kPreOnEqual, given = ph.flags & kPreGiven;
-    bool s1, s2, s3, s4;
-    {  // the pod count: the pending pod itself counts 1
-      const long long thr = __ldcg(&pv[2 * R]);
-      long long au = __ldcg(&pv[2 * R + 1]);
-      const bool has = ph.thr_has & KT_COUNT_BIT;
-      bool au_has = ph.base_has & KT_COUNT_BIT, m2 = ph.st_thr & KT_COUNT_BIT;
-      if (!given) {
-        const long long used = (long long)__ldcg(&px.total[(size_t)2 * R * M + t]);
-        const bool used_has = used > 0;
-        au += used;
-        au_has = au_has || used_has;
-        m2 = has && used_has && used >= thr;
-      }
-      s1 = has && 1 > thr;
-      s2 = m2;
-      s3 = has && au_has && (e3 ? au >= thr : au > thr);
-      s4 = has && (on_equal ? au + 1 >= thr : au + 1 > thr);
-    }
-    for (uint32_t c = nz; c;) {  // IsThrottledFor only looks at the pod's non-zero requests (Q5)
-      const int r = __ffs(c) - 1;
-      c &= c - 1;
-      const long long thr = __ldcg(&pv[r]);
-      long long au = __ldcg(&pv[R + r]);
-      const bool has = (ph.thr_has >> r) & 1;
-      bool au_has = (ph.base_has >> r) & 1, m2 = (ph.st_thr >> r) & 1;
-      if (!given) {
-        const long long used = (long long)__ldcg(&px.total[(size_t)r * M + t]);
-        const bool used_has = __ldcg(&px.total[(size_t)(R + r) * M + t]) != 0ull;
-        au += used;
-        au_has = au_has || used_has;
-        m2 = has && used_has && used >= thr;
-      }
-      const long long v = s_req[r * TILE + tid];
-      s1 = s1 || (has && v > thr);
-      s2 = s2 || m2;
-      s3 = s3 || (has && au_has && (e3 ? au >= thr : au > thr));
-      s4 = s4 || (has && (on_equal ? v >= thr - au : v > thr - au));
-    }
-    return s1 ? KT_CHECK_POD_REQUESTS_EXCEEDS_THRESHOLD : ((s2 || s3) ? KT_CHECK_ACTIVE : (s4 ? KT_CHECK_INSUFFICIENT : KT_CHECK_NOT_THROTTLED));
-  };
   auto decide_scattered = [&]() {
 #pragma unroll 1
     for (int kk = 0; kk < wc.cnt; ++kk) {
       const int w = wc.at(tb, kk);
-      uint32_t word = __ldcg(&bitmap[p * Wp + w]);
-      uint32_t c0 = 0, c1 = 0;
-      while (word) {
-        const int b = __ffs(word) - 1;
-        word &= word - 1;
-        const uint32_t code = pair_direct(w * 32 + b);
-        if (code) ok = 0;
-        if (b < 16) c0 |= code << (2 * b);
-        else c1 |= code << (2 * (b - 16));
-      }
-      *reinterpret_cast<uint2*>(&codes[p * 2 * Wp + 2 * w]) = make_uint2(c0, c1);
-      if (sp.count) {
-        if (c0) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w), c0);
-        if (c1) sparse_append(sp, (uint32_t)p, (uint32_t)(2 * w + 1), c1);
-      }
+      decide_word_direct(__ldcg(&bitmap[p * Wp + w]), w, pre, px, rec, R, M, Wp, pod, codes, sp, ok);
     }
   };
 
@@ -1536,18 +1684,27 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       }
       int nq = 0;
       if (lane == 0) {
+        bool open = true;  // (unrolled with a flag instead of a counted loop: pw / pslot stay in registers)
+#pragma unroll
+        for (int q = 0; q < kPropose; ++q) {
+          if (open && pw[q] != 0x7fffffff) {
+            int sidx = (int)((unsigned)pw[q] % (unsigned)SLOTS), got = -1;
 #pragma unroll 1
-        for (; nq < kPropose && pw[nq] != 0x7fffffff; ++nq) {
-          int sidx = (int)((unsigned)pw[nq] % (unsigned)SLOTS), got = -1;
-#pragma unroll 1
-          for (int probes = 0; probes < SLOTS; ++probes) {
-            int key = *reinterpret_cast<volatile int*>(&s_key[sidx]);
-            if (key == -1) key = atomicCAS(&s_key[sidx], -1, pw[nq]);
-            if (key == -1 || key == pw[nq]) { got = sidx; break; }
-            sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
+            for (int probes = 0; probes < SLOTS; ++probes) {
+              int key = *reinterpret_cast<volatile int*>(&s_key[sidx]);
+              if (key == -1) key = atomicCAS(&s_key[sidx], -1, pw[q]);
+              if (key == -1 || key == pw[q]) { got = sidx; break; }
+              sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
+            }
+            if (got < 0) {
+              open = false;  // table full: the rest waits for the next round
+            } else {
+              pslot[q] = got;
+              nq = q + 1;
+            }
+          } else {
+            open = false;
           }
-          if (got < 0) break;  // table full: the rest waits for the next round
-          pslot[nq] = got;
         }
       }
       nq = __shfl_sync(kFull, nq, 0);
@@ -1576,27 +1733,30 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
       while (used) {
         const int sidx = __ffs(used) - 1;
         used &= used - 1;
-        if (rank % WARPS == warp && rank / WARPS < 2) my_slot[rank / WARPS] = sidx;
+        if (rank == warp) my_slot[0] = sidx;
+        if (rank == warp + WARPS) my_slot[1] = sidx;
         ++rank;
       }
     }
+#pragma unroll
     for (int j = 0; j < 2; ++j)
-      if (my_slot[j] >= 0) stage_pre(my_slot[j]);
+      if (my_slot[j] >= 0) stage_pre_record(pre, s_key[my_slot[j]], s_any[my_slot[j]], s_chk + (size_t)my_slot[j] * 32 * rec, rec, R, lane);
     stamp(5);
     if (!sums_awaited) {
       sync.wait_totals(px);  // the sums of every running pod (of every rank) are in px.total
       sums_awaited = true;
       stamp(6);
     }
+#pragma unroll
     for (int j = 0; j < 2; ++j)
-      if (my_slot[j] >= 0) stage_post(my_slot[j]);
+      if (my_slot[j] >= 0) stage_finish_record(px, s_key[my_slot[j]], s_any[my_slot[j]], s_chk + (size_t)my_slot[j] * 32 * rec, rec, R, M, lane);
     if (scattered && k == 0) { decide_scattered(); k = 1; }  // (k is otherwise unused by a scattered warp: marks "done")
     __syncthreads();
     stamp(7);
     // 3. every lane decides its own pairs
 #pragma unroll
     for (int q = 0; q < kPropose; ++q)
-      if (pword[q] && pslot[q] >= 0) decide_word(pword[q], pw[q], s_chk + (size_t)pslot[q] * 32 * rec);
+      if (pword[q] && pslot[q] >= 0) decide_word<RT>(pword[q], pw[q], s_chk + (size_t)pslot[q] * 32 * rec, rec, R, Wp, pod, codes, sp, ok);
     const int more = __syncthreads_or(cur != 0x7fffffff);  // pods with more words than fit one round (ClusterThrottle-heavy namespaces)
     if (!more) break;
     if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
@@ -1604,6 +1764,249 @@ __device__ __forceinline__ void check_decide_tile(const PodView& pods, const Tab
   }
   stamp(8);
   if (valid) admit[p] = ok;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The SHARED decide tiles of a resident pass.  When every match and reconcile CTA of the grid is on the device at once, the
+// decide work is not left to the P/TILE CTAs that matched the pending pods (one lane per pod walking its words and pairs one
+// after the other while every other SM has gone idle: 7 of the C2 pass's 19 us): every CTA that has finished its own tile --
+// match or reconcile -- draws sub-tiles of TILE/4 pending pods from a second ticket counter.  FOUR lanes per pod: lane q
+// fetches the pod's q-th word of the round and claims its staging slot (same-word lanes of a warp elect one claimant; a word
+// that finds no slot -- rows in arrival order -- is checked pair by pair straight from L2), and the pod's pairs are dealt out
+// to its four lanes bit by bit.  Everything before the wait for the sums -- requests, match words, slot claims, the
+// pre-records (one bulk copy of 32 records per slot) -- is done while the slowest reconcile tiles are still at work.
+//
+// KT_QUAD_DRYRUN: the code after the wait (constants, pair checks) runs once per CTA, late in the pass, on SMs that have been
+// executing other code: its instructions come from L2, miss by miss.  A tile that has to wait anyway walks that code once
+// (1) or over and over (2) on whatever the sums hold so far -- results thrown away, the raw pre-records fetched again -- so
+// that the real run finds its instructions in the SM's instruction caches.
+// ------------------------------------------------------------------------------------------------
+#ifndef KT_QUAD_FENCE  // 1: a shared decide tile looks at its three counters with relaxed loads and acquires once, with a fence; 0: three acquire loads
+#define KT_QUAD_FENCE 1
+#endif
+#ifndef KT_QUAD_DRYRUN  // measured (profiles/README.md r2b): the walk itself costs what it saves -- off
+#define KT_QUAD_DRYRUN 0
+#endif
+template <int TILE, int RT>
+__device__ __forceinline__ void check_decide_quad(const PodView& pods, const TableView& tb, int R, int KS, const unsigned char* __restrict__ pre,
+                                                  const PartExchange& px, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ codes,
+                                                  unsigned char* __restrict__ admit, unsigned char* smem_raw, int64_t sub, const FlagSync& sync,
+                                                  const SparseOut sp, unsigned long long* s_mbar /* [WARPS], initialised (count 1) */,
+                                                  unsigned& mbar_phase /* this warp's next parity */, unsigned long long* trace_row = nullptr) {
+  // optional stage stamps (kt_enable_trace) of the CTA's FIRST sub-tile: [9] match rows + pre-records visible, [10] slots
+  // claimed + pre-records requested, [11] sums of every rank visible, [12] constants finished, [13] decided
+  auto stamp = [&](int k) {
+    if (trace_row && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace_row[k] = t;
+    }
+  };
+  // ... and SM cycle counts of thread 0's way through its first round ([16 + k], %clock64): 0 entry, 1 requests in shared
+  // memory + counters seen, 2 match word loaded + slot claimed, 3 slots ranked + pre-records requested, 4 first dry run done,
+  // 5 sums visible, 6 pre-records landed, 7 constants finished, 8 CTA barrier, 9 own pairs decided, 10 round closed;
+  // [16 + 11] dry runs made
+  auto cyc = [&](int k) {
+    if (trace_row && threadIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+      trace_row[16 + k] = (unsigned long long)t;
+    }
+  };
+  cyc(0);
+  constexpr int WARPS = TILE / 32, PODS = TILE / 4;
+  const size_t rec = decide_record_bytes(R);
+  const int SLOTS = WARPS * KS;
+  long long* s_req = reinterpret_cast<long long*>(smem_raw);                          // [R][PODS] (carved as [R][TILE], like check_decide_tile)
+  unsigned char* s_chk = reinterpret_cast<unsigned char*>(s_req + (size_t)R * TILE);  // [SLOTS][32][rec]
+  int* s_key = reinterpret_cast<int*>(s_chk + (size_t)SLOTS * 32 * rec);              // [SLOTS] word index or -1
+  uint32_t* s_any = reinterpret_cast<uint32_t*>(s_key + SLOTS);                       // [SLOTS] throttles of the word some lane of the CTA matched
+  uint32_t* s_flag = s_any + SLOTS;                                                   // thread 0 -> CTA: the sums are complete
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = tid >> 2, q = tid & 3;  // pod of the sub-tile, lane of the pod
+  const int Wp = tb.Wp;
+  const int M = tb.M;
+  const int64_t p = sub * PODS + j;
+  const bool valid = p < pods.n;
+  const int64_t pc = valid ? p : pods.n - 1;
+  // thread 0: what has been signalled already?  Three relaxed loads in flight together with everybody's row loads -- a tile
+  // that starts late finds all of it there and pays ONE trip to L2 and one acquire fence instead of three waits in a row.
+  const unsigned* sums_counter = px.npeers == 0 ? &sync.s->rec_done : &sync.s->tot_done;
+  const unsigned sums_target = px.npeers == 0 ? sync.n_rec : sync.n_fin;
+  unsigned seen_match = 0, seen_prep = 0, seen_sums = 0;
+  if (tid == 0) {
+    if constexpr (KT_QUAD_FENCE != 0) {
+      seen_match = ld_relaxed_gpu(&sync.s->match_done);
+      seen_prep = ld_relaxed_gpu(&sync.s->prep_done);
+      seen_sums = ld_relaxed_gpu(sums_counter);
+    } else {  // three acquire loads: each one invalidates the SM's L1 under the reconcile tiles still working there
+      seen_match = ld_acquire_gpu(&sync.s->match_done);
+      seen_prep = ld_acquire_gpu(&sync.s->prep_done);
+      seen_sums = ld_acquire_gpu(sums_counter);
+    }
+  }
+  const int ns = valid ? __ldg(&pods.ns[pc]) : -1;
+  const uint32_t present = __ldg(&pods.present[pc]);
+  const uint32_t winfo = __ldg(&pods.winfo[pc]);
+  // ResourceAmountOfPod(pod): the pod's four lanes fetch every fourth resource each
+  uint32_t nz = 0;
+  for (int r = q; r < R; r += 4) {
+    long long v = __ldg(pods.req + (int64_t)r * pods.n + pc);
+    if (!((present >> r) & 1)) v = 0;
+    s_req[r * PODS + j] = v;
+    if (v != 0) nz |= 1u << r;
+  }
+  nz |= __shfl_xor_sync(kFull, nz, 1);
+  nz |= __shfl_xor_sync(kFull, nz, 2);
+  const DecidePod pod{s_req + j, PODS, nz, p};
+  if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
+  WordCursor wc;
+  wc.init(tb, winfo, ns, valid && (unsigned)ns < (unsigned)tb.NS);
+  if (tid == 0) {
+    // the match rows of EVERY pending tile (ours came from some other CTA) and the pre-records (early: they depend on nothing)
+    if (seen_match < sync.n_match) {
+      spin_until([&] { return poll_gpu(&sync.s->match_done) >= sync.n_match; }, &sync.s->error, 40);
+      acquire_gpu(&sync.s->match_done);
+    }
+    if (seen_prep < sync.n_fin) {
+      spin_until([&] { return poll_gpu(&sync.s->prep_done) >= sync.n_fin; }, &sync.s->error, 40);
+      acquire_gpu(&sync.s->prep_done);
+    }
+    *s_flag = seen_sums >= sums_target ? 1u : 0u;
+    if constexpr (KT_QUAD_FENCE != 0) fence_acquire_gpu();  // ONE acquire for every counter observed so far
+  }
+  __syncthreads();  // the slot table is initialised, the requests are in shared memory, the counters have been seen
+  bool sums_ready = *s_flag != 0u;
+  stamp(9);
+  cyc(1);
+
+  unsigned char ok = 1;
+  unsigned dry_runs = 0;
+#pragma unroll 1
+  for (int rd = 0;; ++rd) {
+    // 1. this lane's word of the round and its match word; lanes with matches need the word's 32 records staged
+    const int w = wc.at(tb, rd * 4 + q);  // 0x7fffffff: none left
+    const uint32_t mword = w != 0x7fffffff ? __ldcg(&bitmap[p * Wp + w]) : 0u;
+    int slot = -1;
+    {
+      const int key = mword ? w : 0x7fffffff;
+      const unsigned grp = __match_any_sync(kFull, key);  // the lanes of this warp that want the same word
+      const int leader = __ffs(grp) - 1;
+      const uint32_t gor = __reduce_or_sync(grp, mword);
+      if (mword && lane == leader) {  // open addressing from w mod SLOTS; full table: the group checks its pairs straight from L2
+        int sidx = (int)((unsigned)w % (unsigned)SLOTS);
+#pragma unroll 1
+        for (int probes = 0; probes < SLOTS; ++probes) {
+          int key2 = *reinterpret_cast<volatile int*>(&s_key[sidx]);
+          if (key2 == -1) key2 = atomicCAS(&s_key[sidx], -1, w);
+          if (key2 == -1 || key2 == w) { slot = sidx; break; }
+          sidx = sidx + 1 == SLOTS ? 0 : sidx + 1;
+        }
+        if (slot >= 0) atomicOr(&s_any[slot], gor);
+      }
+      slot = __shfl_sync(kFull, slot, leader);
+      if (!mword) slot = -1;
+    }
+    if (rd == 0) cyc(2);
+    proxy_fence_async();  // whatever this thread last wrote to the staging slots (generic proxy) is ordered before the bulk copies
+    __syncthreads();
+    // 2. the slots in use are spread over the warps (by rank among the used ones); one lane per warp asks the copy engine for
+    // its slots' pre-records: 32 consecutive records = one contiguous block of 32 * rec bytes per slot
+    int slot_a = -1, slot_b = -1;
+    {
+      uint32_t used = __ballot_sync(kFull, lane < SLOTS && s_key[lane < SLOTS ? lane : 0] >= 0);
+      int rank = 0;
+      while (used) {
+        const int sidx = __ffs(used) - 1;
+        used &= used - 1;
+        if (rank == warp) slot_a = sidx;
+        if (rank == warp + WARPS) slot_b = sidx;
+        ++rank;
+      }
+    }
+    const int n_mine = (slot_a >= 0) + (slot_b >= 0);
+    auto request_pre = [&]() {
+      if (n_mine && lane == 0) {
+        mbar_expect_tx(&s_mbar[warp], (unsigned)(n_mine * 32 * rec));
+        bulk_copy_g2s(s_chk + (size_t)slot_a * 32 * rec, pre + (size_t)s_key[slot_a] * 32 * rec, (unsigned)(32 * rec), &s_mbar[warp]);
+        if (slot_b >= 0) bulk_copy_g2s(s_chk + (size_t)slot_b * 32 * rec, pre + (size_t)s_key[slot_b] * 32 * rec, (unsigned)(32 * rec), &s_mbar[warp]);
+      }
+    };
+    request_pre();
+    if (rd == 0) { stamp(10); cyc(3); }
+    // 3. sums -> constants -> pairs.  The same instructions serve the dry runs (see above) and the real one.
+    int dry_left = KT_QUAD_DRYRUN == 1 ? 1 : (KT_QUAD_DRYRUN >= 2 ? 4096 : 0);
+    bool real;
+#pragma unroll 1
+    do {
+      if (!sums_ready) {
+        if (dry_left == 0) {
+          sync.wait_totals(px);  // the sums of every running pod (of every rank) are in px.total
+          sums_ready = true;
+        } else {  // look once; not there: one more walk through the code below
+          --dry_left;
+          if (tid == 0) {
+            const bool there = ld_acquire_gpu(sums_counter) >= sums_target;
+            *s_flag = there ? 1u : 0u;
+          }
+          __syncthreads();
+          sums_ready = *s_flag != 0u;
+        }
+      }
+      real = sums_ready;
+      if (real && rd == 0) { stamp(11); cyc(5); }
+      if (n_mine) {  // warp-uniform: the raw records have landed
+        mbar_wait(&s_mbar[warp], mbar_phase & 1u);
+        mbar_phase ^= 1u;
+      }
+      if (real && rd == 0) cyc(6);
+      if (slot_a >= 0) stage_finish_record(px, s_key[slot_a], s_any[slot_a], s_chk + (size_t)slot_a * 32 * rec, rec, R, M, lane);
+      if (slot_b >= 0) stage_finish_record(px, s_key[slot_b], s_any[slot_b], s_chk + (size_t)slot_b * 32 * rec, rec, R, M, lane);
+      if (real && rd == 0) cyc(7);
+      __syncthreads();
+      if (real && rd == 0) { stamp(12); cyc(8); }
+      // the pod's pairs, dealt out to its four lanes bit by bit; word i of the round belongs to lane i, which collects its codes
+      // (NOT unrolled: this code runs once per CTA, cold -- its instructions come from L2, and four copies are four times the misses)
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int src = (lane & ~3) | i;
+        const int wi = __shfl_sync(kFull, w, src);
+        const uint32_t mi = __shfl_sync(kFull, mword, src);
+        const int si = __shfl_sync(kFull, slot, src);
+        const uint32_t part = mi & (0x11111111u << q);
+        uint2 c = make_uint2(0u, 0u);
+        if (part) {
+          if (si >= 0) c = decide_word_codes<RT>(part, s_chk + (size_t)si * 32 * rec, rec, R, pod);
+          else c = decide_word_direct_far(part, wi, pre, px.total, (unsigned)rec, R, M, pod.req, pod.stride, pod.nz);
+        }
+        c.x |= __shfl_xor_sync(kFull, c.x, 1);
+        c.y |= __shfl_xor_sync(kFull, c.y, 1);
+        c.x |= __shfl_xor_sync(kFull, c.x, 2);
+        c.y |= __shfl_xor_sync(kFull, c.y, 2);
+        if (real && q == i && mi) store_codes(c, wi, Wp, p, codes, sp, ok);
+      }
+      if (real && rd == 0) cyc(9);
+      if (!real) {  // a dry run: the records it finished in place are void -- fetch the raw ones again
+        ++dry_runs;
+        proxy_fence_async();
+        __syncthreads();  // everybody is done with the slots
+        request_pre();
+        if (rd == 0 && dry_runs == 1) cyc(4);
+      }
+    } while (!real);
+    const int more = __syncthreads_or((rd + 1) * 4 < wc.cnt);  // pods with more than four words (ClusterThrottle-heavy namespaces)
+    if (rd == 0) cyc(10);
+    if (!more) break;
+    if (tid < SLOTS) { s_key[tid] = -1; s_any[tid] = 0u; }
+    __syncthreads();
+  }
+  stamp(13);
+  if (trace_row && tid == 0) trace_row[16 + 11] = dry_runs;
+  unsigned okw = ok;
+  okw &= __shfl_xor_sync(kFull, okw, 1);
+  okw &= __shfl_xor_sync(kFull, okw, 2);
+  if (valid && q == 0) admit[p] = (unsigned char)okw;
 }
 
 // k_check: both phases of one tile in one CTA (the PDL-chained path: phase 1 overlaps k_reconcile / k_finalize).
@@ -1645,7 +2048,10 @@ struct PassArgs {
                                  // tiles' totals) or for other GPUs, whose tiles are subject to the same order -- unless the whole grid is
                                  // resident (below)
   unsigned n_status;             // CTAs that run the status halves: ceil(n_fin / kStatusBatch)
-  unsigned resident;             // 1: every CTA of the grid is on the device at once; the match CTAs stay on as the decide tiles
+  unsigned resident;             // 1: every match and reconcile CTA of the grid is on the device at once; the match CTAs stay on as the decide
+                                 // tiles; 2: ... and every CTA that is through with its own tile shares the decide work (check_decide_quad)
+  unsigned n_sub;                // resident == 2: shared decide sub-tiles of TILE/4 pending pods (the grid has no status CTAs: n_status == 0,
+                                 // the n_fin status tiles are drawn from the same ticket counter as the sub-tiles)
   unsigned long long* trace;     // optional (kt_enable_trace): per CTA kTraceRow x u64 {ticket, sm, t_start, t_end, stage stamps} in globaltimer ns
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1659,7 +2065,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <int TPC, int B, int RT, bool REG, int TILE = kTileReconcile>
 __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __grid_constant__ PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned s_ticket;
+  __shared__ unsigned s_ticket, s_sub;
+  __shared__ __align__(8) unsigned long long s_mbar[kMaxWarps + 1];  // transaction barriers: one per warp (bulk copies of the shared decide tiles), [kMaxWarps] the reconcile tile's rows
   unsigned long long t_start = 0;
   // Launched with programmatic stream serialization: the NEXT launch in the stream (normally the next pass) may have its CTAs
   // placed while this one still runs -- they sit in the wait below until this grid has completed and flushed, so nothing of
@@ -1667,6 +2074,11 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
   // dependents at once: a grid whose CTAs are not all resident yet cannot be overtaken (the dependents only start when ALL
   // our CTAs have started), so the tiles we still owe always find an SM.
   pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kMaxWarps + 1; ++i) mbar_init(&s_mbar[i], 1u);
+    mbar_init_fence();
+  }
   pdl_wait_primary();
   if (threadIdx.x == 0) {
     s_ticket = atomicAdd(&a.sync->ticket, 1u);
@@ -1674,8 +2086,10 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
   }
   __syncthreads();
   unsigned tile = s_ticket;
-  const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk, a.resident != 0};
+  const FlagSync sync{a.sync, a.n_rec, a.n_fin, a.n_chk, a.resident == 1};
   unsigned long long* trow = a.trace ? a.trace + (size_t)s_ticket * kTraceRow : nullptr;
+  bool shares_decide = false;  // resident == 2: this CTA goes on to the shared second phase once its own tile is done
+  int own_status = -1;         // a status CTA's tile (passes that are not resident)
   if (tile < a.n_chk) {  // no dependencies: first tickets
     // The match tiles also write the pre-records (the prep half of the finalize tiles, spread over them): they hold the first
     // tickets, so every pre-record exists a few microseconds into the pass and no decide tile ever waits for one -- without
@@ -1686,7 +2100,7 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
     if (tile == 0 && threadIdx.x == 0 && a.sparse.count) *a.sparse.count = 0u;
     check_match_tile<TPC, B, REG, TILE>(a.pend, a.tb, a.L, a.pend_bitmap, a.codes, smem_raw, tile);
     cta_signal(&a.sync->match_done);
-    if (a.resident) {
+    if (KT_PASS_RESIDENT == 1 && a.resident == 1) {
       // RESIDENT pass (the host found that every CTA of the grid fits on the device at once): the CTA stays and becomes the decide
       // tile of the same 128 pods -- already placed, its pre-wait work done long before the reconcile tiles finish, instead of a
       // late CTA that is only launched when somebody else exits.  (It waits for LARGER tickets, which is only safe because all
@@ -1695,19 +2109,54 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
       check_decide_tile<TILE, RT>(a.pend, a.tb, a.R, decide_stage_words(a.R, TILE), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile, sync,
                                         a.sparse, trow);
     }
+    shares_decide = KT_PASS_RESIDENT == 2 && a.resident == 2;
   } else if ((tile -= a.n_chk) < a.n_rec) {
-    reconcile_tile<TPC, B, RT, REG, TILE>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow);
+    reconcile_tile<TPC, B, RT, REG, TILE>(a.run, a.tb, a.L, a.R, a.S, a.run_bitmap, a.px.mine, smem_raw, tile, trow, &s_mbar[kMaxWarps]);
     cta_signal(&a.sync->rec_done);
+    shares_decide = KT_PASS_RESIDENT == 2 && a.resident == 2;
   } else if ((tile -= a.n_rec) < a.n_status) {
-    // status halves (off the critical path; nobody on this GPU waits for them, so they need not be resident from the start: they
-    // take the slots the reconcile tiles leave, which is when their work begins anyway)
-    for (unsigned j = 0; j < kStatusBatch; ++j) {
-      const unsigned ft = tile * kStatusBatch + j;
-      if (ft < a.n_fin) finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)ft, sync, j == 0 ? trow : nullptr, kFinStatus);
-    }
+    // status tiles of a pass whose grid does not fit the device (off the critical path; nobody on this GPU waits for them, so
+    // they need not be resident from the start: they take the slots the reconcile tiles leave, which is when their work begins
+    // anyway).  Run below, by the one copy of the status code that the shared second phase uses as well.
+    own_status = (int)tile;
   } else {
     check_decide_tile<TILE, RT>(a.pend, a.tb, a.R, decide_stage_words(a.R, TILE), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, tile - a.n_status, sync,
                                       a.sparse, trow);
+  }
+  if ((KT_PASS_RESIDENT == 2 && shares_decide) || own_status >= 0) {
+    // RESIDENT pass, shared second phase: every match and reconcile CTA is on the device at once (the host checked), so a CTA
+    // that is through with its own tile may wait for ALL of them.  It draws work from a second ticket counter until none is
+    // left: the decide sub-tiles and the status tiles (the grid of such a pass has no status CTAs of its own).  With peers the
+    // status tiles come first -- they carry the exchange the decide tiles wait for; alone they come last, nobody waits for them.
+    unsigned mbar_phase = 0;
+    bool first = true;
+    const unsigned n_work = a.n_sub + a.n_fin;
+    while (true) {
+      bool is_status;
+      unsigned index;
+      if (own_status >= 0) {  // a status CTA: its one tile
+        is_status = true;
+        index = (unsigned)own_status;
+      } else {
+        __syncthreads();  // the CTA's shared memory is free again (previous role / previous piece of work)
+        if (threadIdx.x == 0) s_sub = atomicAdd(&a.sync->dec_ticket, 1u);
+        __syncthreads();
+        const unsigned work = s_sub;
+        if (work >= n_work) break;
+        const bool status_first = a.px.npeers > 0;
+        is_status = status_first ? work < a.n_fin : work >= a.n_sub;
+        index = status_first ? (is_status ? work : work - a.n_fin) : (is_status ? work - a.n_sub : work);
+      }
+      if (is_status) {
+        finalize_tile(a.tv, a.tb.M, a.R, a.G, a.now, a.eval_flags, a.px, a.out, a.pre, (int)index, sync, own_status >= 0 ? trow : nullptr, kFinStatus);
+        if (own_status >= 0) break;
+      } else {
+        if constexpr (KT_PASS_RESIDENT == 2)
+          check_decide_quad<TILE, RT>(a.pend, a.tb, a.R, decide_stage_words(a.R, TILE), a.pre, a.px, a.pend_bitmap, a.codes, a.admit, smem_raw, index, sync,
+                                      a.sparse, s_mbar, mbar_phase, first ? trow : nullptr);
+        first = false;
+      }
+    }
   }
   // the last CTA out re-arms the counters for the next launch (stream-ordered after this one)
   __syncthreads();
@@ -1725,6 +2174,8 @@ __global__ void __launch_bounds__(TILE, KT_PASS_THREADS / TILE) k_pass(const __g
       a.sync->prep_done = 0;
       a.sync->match_done = 0;
       a.sync->tot_done = 0;
+      a.sync->dec_ticket = 0;
+      a.sync->spare = 0;
       a.sync->exited = 0;
     }
   }

@@ -51,6 +51,30 @@ for it in range(4):
             x = x[r[:, 4 + k] > 0]
             if len(x):
                 print(f"            {label:18s} since pass start: med {np.median(x):5.1f}  p90 {np.percentile(x, 90):5.1f}  max {x.max():5.1f}")
+        if name in ("match", "reconcile") and (r[:, 9] > 0).any():  # shared decide tiles (resident pass): the CTA's first sub-tile
+            sel = r[:, 9] > 0
+            print(f"            -> {int(sel.sum())} of these CTAs went on to shared decide sub-tiles")
+            for k, label in enumerate(["rows + pre visible", "slots claimed", "sums seen", "constants done", "decided"]):
+                x = (r[sel, 9 + k] - t0) / 1e3
+                x = x[r[sel, 9 + k] > 0]
+                if len(x):
+                    print(f"            decide: {label:18s} since pass start: med {np.median(x):5.1f}  p90 {np.percentile(x, 90):5.1f}  max {x.max():5.1f}")
+            # SM cycle counts of thread 0's way through its first sub-tile (check_decide_quad): deltas between consecutive points
+            CYC = ["entry", "requests+counters", "word+claim", "ranked+pre asked", "(first dry run)", "sums visible", "pre landed", "constants", "barrier",
+                   "pairs decided", "round closed"]
+            c = r[sel][:, 16:27].astype(np.int64)
+            dry = r[sel][:, 27]
+            order = [0, 1, 2, 3, 5, 6, 7, 8, 9, 10]
+            parts = []
+            for a_, b_ in zip(order[:-1], order[1:]):
+                okm = (c[:, a_] > 0) & (c[:, b_] > 0)
+                if okm.any():
+                    d = c[okm, b_] - c[okm, a_]
+                    parts.append(f"{CYC[b_]} {int(np.median(d))}/{int(np.percentile(d, 90))}")
+            print("            decide cycles (median/p90 since the previous point): " + " | ".join(parts))
+            okm = (c[:, 4] > 0) & (c[:, 3] > 0)
+            if okm.any():
+                print(f"            dry runs: {int(np.median(dry))} median, {int(dry.max())} max; the first one took {int(np.median(c[okm, 4] - c[okm, 3]))} cycles (median)")
         if it == 3:
             worst = np.argsort(-en)[:4]
             for i in worst:

@@ -14,6 +14,8 @@ from kube_throttler_b200 import abi, synth
 
 cases = [("C3", dict(m=300, n=3000, p=500)), ("C3", dict(m=900, n=2500, p=400)), ("C2", dict(m=200, n=2000, p=300, L=12, q_max=6)),
          ("C2", dict(m=40, n=70, p=33, R=1))]
+if os.environ.get("KT_SANITIZE_SMALL"):  # a quick look at the fused resident pass only (shared second phase; 128- and 256-row tiles)
+    cases = [cases[0], cases[3]]
 if os.environ.get("KT_SANITIZE_BIG"):
     cases.append(("C2", dict(m=500, n=120_000, p=4000)))
 for cfg, kw in cases:

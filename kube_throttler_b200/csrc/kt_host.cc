@@ -17,6 +17,7 @@
 #include <set>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/kt_b200.h"
@@ -368,6 +369,7 @@ struct ThrottleObj {
   bool st_thr_req_nil = true;
   ResAmount st_used;
   bool live = false;
+  uint64_t seq = 0;        // creation order: device columns of deleted throttles are reused, lists keep the order the objects arrived in
   bool host_dirty = true;  // applied since its last reconcile: the host-only parts of its status (messages, spec gauges) may differ even
                            // when the device-side diff says its numbers do not
   bool metrics_pending = false;  // reconciled since its gauges were last written into the registry (see record_metrics)
@@ -474,6 +476,17 @@ struct kth_plugin {
 
   std::vector<ThrottleObj> throttles;  // column order == device order (both kinds interleaved, insertion order)
   std::unordered_map<std::string, int> thr_index;  // "T:ns/name" | "C:/name"
+  // Device columns of deleted throttles are handed out again (a scheduler that lives for months sees throttles come and go: M,
+  // the table compile and every pass would only ever grow otherwise).  Whatever lists throttles for the caller -- affected
+  // throttles of a pod (the order of the names inside a PreFilter reason), the broken-selector walk (WHICH error a pod gets),
+  // reconcile's changed list -- is in creation order, as the reference's lister-backed slices are, not in column order.
+  std::vector<int> free_thr;
+  uint64_t thr_seq = 0;
+  bool thr_reused = false;  // some column holds a younger throttle than a higher one: column order is not creation order any more
+  template <class V>
+  void creation_order(V& cols_list) const {  // sort a list of throttle columns by creation
+    if (thr_reused) std::stable_sort(cols_list.begin(), cols_list.end(), [&](size_t a, size_t b) { return throttles[a].seq < throttles[b].seq; });
+  }
   bool throttles_dirty = true, namespaces_dirty = true, status_dirty = true, reserved_dirty = true;
   std::vector<size_t> broken;  // columns of the throttles with a podSelector that does not convert (controller_error)
   bool broken_valid = false;
@@ -1242,7 +1255,10 @@ struct kth_plugin {
     int reconciled = 0;
     std::vector<std::string> changed;
     std::vector<std::pair<std::string, long long>> requeue;
-    for (size_t t = 0; t < m; ++t) {
+    std::vector<size_t> thr_order(m);
+    for (size_t t = 0; t < m; ++t) thr_order[t] = t;
+    creation_order(thr_order);
+    for (size_t t : thr_order) {
       ThrottleObj& o = throttles[t];
       if (!o.live || o.throttler_name != name) continue;   // only responsible throttles are ever enqueued (:403-425)
       if (selector_fails[t]) continue;                      // affectedPods fails -> reconcile returns the error, status untouched
@@ -1490,6 +1506,7 @@ struct kth_plugin {
         const size_t t = (size_t)w * 32 + (size_t)__builtin_ctz(bits);
         if (t < throttles.size() && throttles[t].kind == kind) out.push_back((int)t);
       }
+    creation_order(out);
     return out;
   }
   // affectedThrottles / affectedClusterThrottles error paths that never reach the device:
@@ -1504,6 +1521,7 @@ struct kth_plugin {
       broken.clear();
       for (size_t t = 0; t < throttles.size(); ++t)
         if (throttles[t].live && !throttles[t].selector_error().empty()) broken.push_back(t);
+      creation_order(broken);
       broken_valid = true;
     }
     for (size_t t : broken) {
@@ -1719,9 +1737,23 @@ struct kth_plugin {
       broken.clear();
       for (size_t t = 0; t < throttles.size(); ++t)
         if (throttles[t].live && !throttles[t].selector_error().empty()) broken.push_back(t);
+      creation_order(broken);
       broken_valid = true;
     }
     if (!broken.empty()) return false;  // some pod may run into a conversion error: framework.Error, no Reserve
+    // Reserve is idempotent per pod (podResourceAmountMap.add overwrites, reserved_resource_amounts.go:131-136): a queue pod that
+    // already holds a reservation -- reserved in an earlier cycle and neither bound-and-observed nor unreserved since -- or that
+    // stands in the queue twice adds NOTHING when it is admitted again, whereas the device's prefix sums would count its requests
+    // a second time for everybody behind it.  Such queues take the pod-by-pod passes of the host (found by the event-stream chaos
+    // test, seed 171: a bound pod's old pending manifest back in the queue).
+    {
+      std::unordered_set<std::string> holders;
+      for (int kind = 0; kind < 2; ++kind)
+        for (auto& thr : cache[kind].by_thr)
+          for (auto& pod : thr.second) holders.insert(pod.first);
+      for (auto& p : queue)
+        if (!holders.insert(p.nn()).second) return false;
+    }
     for (auto& p : queue) {
       const int id = ns_dict.find(p.ns);
       if (id < 0 || !namespaces[(size_t)id].exists) return false;  // "namespace not found": Error as well
@@ -1991,10 +2023,20 @@ struct kth_plugin {
     const std::string key = std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + o.nn();
     auto it = thr_index.find(key);
     if (it == thr_index.end()) {
-      thr_index[key] = (int)throttles.size();
-      throttles.push_back(std::move(o));
+      o.seq = ++thr_seq;
+      if (!free_thr.empty()) {  // the column of a deleted throttle (everything per column is re-uploaded: throttles_dirty below)
+        const int t = free_thr.back();
+        free_thr.pop_back();
+        thr_index[key] = t;
+        throttles[(size_t)t] = std::move(o);
+        thr_reused = true;
+      } else {
+        thr_index[key] = (int)throttles.size();
+        throttles.push_back(std::move(o));
+      }
     } else {  // spec update: the status subresource is kept unless the manifest carries one
       ThrottleObj& old = throttles[(size_t)it->second];
+      o.seq = old.seq;
       if (old.metrics_pending) record_metrics(old);  // the gauges keep the values of the last reconcile, not of this update
       if (!has_status) {
         o.st_calc = old.st_calc; o.st_calc_at_set = old.st_calc_at_set; o.st_calc_at = old.st_calc_at; o.st_messages = old.st_messages;
@@ -2009,8 +2051,9 @@ struct kth_plugin {
     const std::string nn = (kind == KT_KIND_THROTTLE ? ns : std::string()) + "/" + tname;
     auto it = thr_index.find(std::string(kind == KT_KIND_THROTTLE ? "T:" : "C:") + nn);
     if (it == thr_index.end()) return;
-    // the column is kept (device order is insertion order) but can never match or be reconciled again
+    // the column can never match or be reconciled again; the next new throttle takes it over
     ThrottleObj& o = throttles[(size_t)it->second];
+    free_thr.push_back(it->second);
     if (o.metrics_pending) { record_metrics(o); o.metrics_pending = false; }  // its series outlive it, as a GaugeVec's do
     o.live = false;
     o.terms.clear();
@@ -2343,7 +2386,9 @@ const char* kth_queue_stats(kth_plugin* p) {
   return guarded(p, [&]() -> std::string {
     Writer w;
     w.begin_obj().key("queued").num((long long)(p->pend_pod.size() - p->pend_free.size())).key("rows").num((long long)p->pend_pod.size());
-    w.key("passes").num((long long)p->queue.passes).key("hits").num((long long)p->queue.hits).end_obj();
+    w.key("passes").num((long long)p->queue.passes).key("hits").num((long long)p->queue.hits);
+    // device columns the throttles occupy (deleted throttles' columns are handed out again) and how many of them are live
+    w.key("throttleColumns").num((long long)p->throttles.size()).key("liveThrottles").num((long long)p->thr_index.size()).end_obj();
     return w.out;
   });
 }

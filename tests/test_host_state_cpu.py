@@ -263,3 +263,30 @@ def test_rows_stay_namespace_clustered_under_churn(host_on_oracle):
     rows = sorted(w.pod_row(*k) for k in live)
     assert len(set(rows)) == len(rows) and rows[-1] < len(live) + 32 * len(nss) + 32 * 40  # slots are reused, the table stays compact
     w.close()
+
+
+def test_deleted_throttles_give_their_device_columns_back(host_on_oracle):
+    """A scheduler that lives for months sees throttles come and go: the device column of a deleted throttle is handed to the
+    next new one (M, the table compile and every pass would only ever grow otherwise) -- and the lists the caller sees stay in
+    CREATION order, as the reference's lister-backed slices are, not in column order: the names inside a PreFilter reason."""
+    w = host_on_oracle(THROTTLER, SCHED)
+    w.apply(namespace("default"))
+    w.apply(*[throttle("default", f"t{i}", {"a": "1"}, cpu="100m") for i in range(5)])
+    w.reconcile_all()
+    assert w.queue_stats()["throttleColumns"] == 5
+    for round_ in range(20):  # churn: three go, three come, twenty times over
+        for i in (1, 2, 3):
+            w.delete("Throttle", f"t{i}" if round_ == 0 else f"n{round_ - 1}_{i}", "default")
+        w.apply(*[throttle("default", f"n{round_}_{i}", {"a": "1"}, cpu="100m") for i in (1, 2, 3)])
+        w.reconcile_all()
+    st = w.queue_stats()
+    assert st["throttleColumns"] == 5 and st["liveThrottles"] == 5, st
+    # t0 and t4 are the oldest, then the last round's three in the order they were applied -- whatever columns they sit in
+    r = w.prefilter(pod("default", "x", "500m", {"a": "1"}))
+    assert r["reasons"] == ["throttle[pod-requests-exceeds-threshold]=default/t0,default/t4,default/n19_1,default/n19_2,default/n19_3"], r
+    w.delete("Throttle", "t0", "default")
+    w.apply(throttle("default", "t0", {"a": "1"}, cpu="100m"))  # back under its old name, in its old column: now the youngest
+    r = w.prefilter(pod("default", "x", "500m", {"a": "1"}))
+    assert r["reasons"] == ["throttle[pod-requests-exceeds-threshold]=default/t4,default/n19_1,default/n19_2,default/n19_3,default/t0"], r
+    assert w.queue_stats()["throttleColumns"] == 5
+    w.close()

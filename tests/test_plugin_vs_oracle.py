@@ -309,6 +309,39 @@ def test_admit_queue_equals_one_pod_per_cycle(oracle, new_plugin, seed):
     dut.close()
 
 
+def test_admit_queue_with_pods_that_already_hold_a_reservation(oracle, new_plugin):
+    """Reserve is idempotent per pod (podResourceAmountMap.add overwrites, reserved_resource_amounts.go:131-136): a pod that was
+    reserved in an earlier cycle and comes through the queue again -- or stands in it twice -- adds nothing when it is admitted
+    again.  (Found by the event-stream chaos test, seed 171: the device's prefix sums counted such a pod a second time and
+    rejected the pod behind it.)"""
+    from test_scenarios import pod
+
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("ns0", {"team": "a"}))
+    both({"kind": "ClusterThrottle", "metadata": {"name": "ct"},
+          "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 3}, "resourceRequests": {"cpu": "1"}},
+                   "selector": {"selectorTerms": [{"podSelector": {}}]}}})
+    ref.reconcile_all(NOW), dut.reconcile_all(NOW)
+    q = [pod("ns0", f"q{i}", "200m", {}, scheduler=SCHED) for i in range(5)]
+    assert ref.prefilter(q[0])["code"] == dut.prefilter(q[0])["code"] == "Success"
+    assert ref.reserve(q[0])["code"] == dut.reserve(q[0])["code"] == "Success"
+    for queue in ([q[0], q[1], q[2], q[3]],          # q0 holds a reservation already: q1 and q2 still fit under pod <= 3
+                  [q[3], q[3], q[4]]):               # the same pod twice
+        want = []
+        for p in queue:
+            r = ref.prefilter(p)
+            if r["code"] == "Success":
+                assert ref.reserve(p)["code"] == "Success"
+            want.append(norm_prefilter(r))
+        got = dut.admit_queue(queue)
+        assert [norm_prefilter(x["preFilter"]) for x in got["results"]] == want, (got, want)
+        a, b = ref.reserved("ClusterThrottle", "/ct"), dut.reserved("ClusterThrottle", "/ct")
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (a, b)
+    assert sorted(dut.reserved("ClusterThrottle", "/ct")["pods"]) == ["ns0/q0", "ns0/q1", "ns0/q2"]
+    dut.close()
+
+
 def test_engine_limits_grow(oracle, new_plugin):
     """More label slots / resource columns / namespace labels than the engine was created with: the host layer re-creates
     the engine with larger limits and re-uploads its caches; decisions stay identical to the oracle's."""

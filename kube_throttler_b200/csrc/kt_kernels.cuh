@@ -16,8 +16,13 @@
 // shuffles so that one lane = one THROTTLE, which adds up its pods' requests from shared memory without
 // any atomics; warps meet in per-CTA shared-memory accumulators and only those reach HBM (RED.ADD.64).
 //
-// The three kernels are chained with programmatic dependent launch (griddepcontrol): k_check matches the
-// pending pods while k_reconcile is still summing, and only its 4-step compare waits for k_finalize.
+// A whole pass is ONE launch, k_pass: every CTA draws a ticket and becomes a pending-match tile (which also writes the
+// per-throttle pre-records), a reconcile tile, a status tile or a pending-decide tile; hand-offs are counters in L2.  When every
+// match and reconcile tile fits the device at once, the status tiles and the decide work (sub-tiles of TILE/4 pods, four lanes
+// per pod, pre-records staged with cp.async.bulk on mbarriers) are a ticket queue served by every CTA that has finished its own
+// tile (check_decide_quad).  Partial passes, per-kernel timing and the NCCL fallback run the same tile functions as the three
+// kernels above, chained with programmatic dependent launch (griddepcontrol): k_check matches the pending pods while k_reconcile
+// is still summing, and only its 4-step compare waits for k_finalize.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -50,15 +50,41 @@ struct Dict {
   size_t size() const { return names.size(); }
 };
 
-// label keys share one id space (pod and namespace labels, selector keys); values are numbered per key, so
-// the ids are dense in both dimensions and the device takes its direct key/value tables (kt_tables.cc)
+// The label dictionaries hold what SELECTORS mention and nothing else: label keys share one id space (podSelector and
+// namespaceSelector keys), values are numbered per key, so the ids are dense in both dimensions and the device takes its direct
+// key / value tables (kt_tables.cc).  Pods and namespaces are encoded THROUGH them: a label whose key no selector mentions cannot
+// influence any match and is dropped; a mentioned key with a value no requirement names becomes "some other value" (id 0 of every
+// key -- In / NotIn never name it, Exists / DoesNotExist only look at the key).  A scheduler that lives for months sees an unbounded
+// stream of label values (pod-template-hash, controller-uid, job-name): interning those grew the dictionaries, and the device's
+// value tables, with every pod ever seen.  When a new throttle brings new vocabulary, the rows that carry it are packed again.
+const char* const kOtherValue = "\x01other";  // not a legal label value: cannot collide with a real one
 struct LabelDict {
   Dict keys;
   std::vector<Dict> vals;
-  int64_t encode(const std::string& k, const std::string& v) {
+  uint32_t key_id(const std::string& k, bool* added = nullptr) {
+    const size_t n = keys.size();
     const uint32_t kid = keys.id(k);
     if (vals.size() <= kid) vals.resize(kid + 1);
-    return (int64_t)(((uint64_t)kid << 32) | vals[kid].id(v));
+    if (vals[kid].size() == 0) vals[kid].id(kOtherValue);
+    if (added) *added = keys.size() != n;
+    return kid;
+  }
+  uint32_t value_id(uint32_t kid, const std::string& v, bool* added = nullptr) {
+    const size_t n = vals[kid].size();
+    const uint32_t vid = vals[kid].id(v);
+    if (added) *added = vals[kid].size() != n;
+    return vid;
+  }
+  int64_t encode(const std::string& k, const std::string& v) const {  // KT_LABEL_EMPTY: no selector can see this label
+    const int kid = keys.find(k);
+    if (kid < 0) return KT_LABEL_EMPTY;
+    const int vid = vals[(size_t)kid].find(v);
+    return (int64_t)(((uint64_t)kid << 32) | (uint32_t)(vid < 0 ? 0 : vid));
+  }
+  size_t n_values() const {
+    size_t n = 0;
+    for (auto& d : vals) n += d.size();
+    return n;
   }
 };
 
@@ -716,7 +742,10 @@ struct kth_plugin {
     nsid[i] = 0;
     if (!p.live) return;  // tombstone: never counted, matches nothing
     int s = 0;
-    for (auto& kv : p.labels) lab[(size_t)(s++) * k + i] = labels.encode(kv.first, kv.second);
+    for (auto& kv : p.labels) {
+      const int64_t code = labels.encode(kv.first, kv.second);
+      if (code != KT_LABEL_EMPTY) lab[(size_t)(s++) * k + i] = code;
+    }
     for (auto& kv : p.request) {
       req[(size_t)kv.first * k + i] = at_scale(kv.first, kv.second);
       present[i] |= 1u << kv.first;
@@ -794,11 +823,14 @@ struct kth_plugin {
     std::vector<int64_t> lab((size_t)LN * std::max<size_t>(n, 1), KT_LABEL_EMPTY);
     for (size_t i = 0; i < n; ++i) {
       int s = 0;
-      for (auto& kv : namespaces[i].labels) lab[(size_t)(s++) * n + i] = labels.encode(kv.first, kv.second);
+      for (auto& kv : namespaces[i].labels) {
+        const int64_t code = labels.encode(kv.first, kv.second);
+        if (code != KT_LABEL_EMPTY) lab[(size_t)(s++) * n + i] = code;
+      }
       // A namespace the lister does not hold (never seen, or deleted) is not in the list affectedPods walks
       // (clusterthrottle_controller.go:227) -- no ClusterThrottle term may match it, not even one whose namespaceSelector is
       // empty.  Existing namespaces carry one internal label (a key no real label can have) that every term requires.
-      if (namespaces[i].exists) lab[(size_t)(s++) * n + i] = labels.encode(kNsExistsKey, "1");
+      if (namespaces[i].exists && labels.encode(kNsExistsKey, "1") != KT_LABEL_EMPTY) lab[(size_t)(s++) * n + i] = labels.encode(kNsExistsKey, "1");
     }
     check(kt_upload_namespaces(ctx, (int32_t)n, lab.data()), "kt_upload_namespaces");
     namespaces_dirty = false;
@@ -825,11 +857,10 @@ struct kth_plugin {
     std::vector<std::vector<Requirement>> ns_reqs_of_term;
     auto push_reqs = [&](const std::vector<Requirement>& reqs) {
       for (auto& r : reqs) {
-        const uint32_t kid = labels.keys.id(r.key);
-        if (labels.vals.size() <= kid) labels.vals.resize(kid + 1);
+        const uint32_t kid = labels.key_id(r.key);  // (all of it interned by sync_vocabulary already)
         req_key.push_back(kid);
         req_op.push_back(r.op);
-        for (auto& v : r.values) req_vals.push_back(labels.vals[kid].id(v));
+        for (auto& v : r.values) req_vals.push_back(labels.value_id(kid, v));
         req_val_off.push_back((int32_t)req_vals.size());
       }
     };
@@ -959,7 +990,52 @@ struct kth_plugin {
     else check(kt_set_reserved(ctx, nullptr, nullptr, nullptr), "kt_set_reserved");
     reserved_dirty = false;
   }
+  // What the selectors mention goes into the label dictionaries BEFORE any row is packed; rows that carry newly mentioned keys or
+  // values (they were packed as "invisible" / "some other value") are packed again.
+  void sync_vocabulary() {
+    if (!throttles_dirty) return;
+    std::unordered_set<std::string> new_keys;
+    std::unordered_map<std::string, std::unordered_set<std::string>> new_vals;
+    auto intern = [&](const std::vector<Requirement>& reqs) {
+      for (auto& r : reqs) {
+        bool added = false;
+        const uint32_t kid = labels.key_id(r.key, &added);
+        if (added) new_keys.insert(r.key);
+        for (auto& v : r.values) {
+          labels.value_id(kid, v, &added);
+          if (added) new_vals[r.key].insert(v);
+        }
+      }
+    };
+    bool cluster_terms = false;
+    for (auto& o : throttles)
+      for (auto& term : o.terms) {
+        intern(term.pod_sel.reqs);
+        if (o.kind == KT_KIND_CLUSTERTHROTTLE) { intern(term.ns_sel.reqs); cluster_terms = true; }
+      }
+    if (cluster_terms) {
+      bool added = false;
+      labels.key_id(kNsExistsKey, &added);
+      if (added) new_keys.insert(kNsExistsKey);
+    }
+    if (new_keys.empty() && new_vals.empty()) return;
+    auto carries_news = [&](const std::vector<std::pair<std::string, std::string>>& labs) {
+      for (auto& kv : labs) {
+        if (new_keys.count(kv.first)) return true;
+        auto it = new_vals.find(kv.first);
+        if (it != new_vals.end() && it->second.count(kv.second)) return true;
+      }
+      return false;
+    };
+    for (auto& p : pods) {
+      if (!p.live || !carries_news(p.labels)) continue;
+      if (p.row >= 0) dirty_rows.insert(p.row);
+      if (p.pend_row >= 0) pend_dirty.insert(p.pend_row);
+    }
+    namespaces_dirty = true;  // (a handful of rows: packed whole)
+  }
   void sync_all() {
+    sync_vocabulary();
     sync_pods();
     sync_namespaces();
     sync_throttles();
@@ -2388,7 +2464,9 @@ const char* kth_queue_stats(kth_plugin* p) {
     w.begin_obj().key("queued").num((long long)(p->pend_pod.size() - p->pend_free.size())).key("rows").num((long long)p->pend_pod.size());
     w.key("passes").num((long long)p->queue.passes).key("hits").num((long long)p->queue.hits);
     // device columns the throttles occupy (deleted throttles' columns are handed out again) and how many of them are live
-    w.key("throttleColumns").num((long long)p->throttles.size()).key("liveThrottles").num((long long)p->thr_index.size()).end_obj();
+    w.key("throttleColumns").num((long long)p->throttles.size()).key("liveThrottles").num((long long)p->thr_index.size());
+    // the label dictionaries: what the selectors mention (+ one "other value" entry per key), however many labels the pods carry
+    w.key("labelKeys").num((long long)p->labels.keys.size()).key("labelValues").num((long long)p->labels.n_values()).end_obj();
     return w.out;
   });
 }

@@ -290,3 +290,40 @@ def test_deleted_throttles_give_their_device_columns_back(host_on_oracle):
     assert r["reasons"] == ["throttle[pod-requests-exceeds-threshold]=default/t4,default/n19_1,default/n19_2,default/n19_3,default/t0"], r
     assert w.queue_stats()["throttleColumns"] == 5
     w.close()
+
+
+def test_label_dictionaries_hold_what_selectors_mention(oracle, host_on_oracle):
+    """Pods come and go with an unbounded stream of label values (pod-template-hash, controller-uid, job-name ...): the label
+    dictionaries -- and the device's value tables -- hold what the SELECTORS mention, not every value ever seen.  A label no selector
+    can see is dropped, a mentioned key with an unmentioned value is "some other value"; when a later throttle mentions a value
+    that pods already carry, exactly those rows are packed again and match."""
+    ref, dut = oracle.World(THROTTLER, SCHED), host_on_oracle(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("default"))
+    both(throttle("default", "t-app", {"app": "web"}, pod_cnt=100))
+    both({"kind": "Throttle", "metadata": {"namespace": "default", "name": "t-notin"},
+          "spec": {"throttlerName": THROTTLER, "threshold": {"resourceCounts": {"pod": 100}},
+                   "selector": {"selectorTerms": [{"podSelector": {"matchExpressions": [{"key": "tier", "operator": "NotIn", "values": ["db"]},
+                                                                                          {"key": "job", "operator": "Exists"}]}}]}}})
+    for i in range(400):  # every pod brings values nobody has seen before
+        both(pod("default", f"p{i}", "100m", {"app": "web" if i % 3 == 0 else f"app-{i}", "pod-template-hash": f"h{i}", "job": f"job-{i}", "tier": f"tier-{i % 7}"},
+                 node="n", phase="Running"))
+        if i % 2:
+            ref.delete("Pod", f"p{i - 1}", "default"), dut.delete("Pod", f"p{i - 1}", "default")
+    ref.reconcile_all(), dut.reconcile_all()
+    st = dut.queue_stats()
+    assert st["labelKeys"] == 3 and st["labelValues"] == 3 + 2, st  # app / tier / job; "web", "db" + one "other value" per key
+    for name in ("t-app", "t-notin"):
+        assert dut.status(name, "default")["used"] == ref.status(name, "default")["used"], name
+    assert dut.status("t-app", "default")["used"]["resourceCounts"]["pod"] > 0 and dut.status("t-notin", "default")["used"]["resourceCounts"]["pod"] == 200
+    # a throttle that mentions a value (and a key) pods already carry under "other" / "invisible"
+    both(throttle("default", "t-late", {"app": "app-7", "pod-template-hash": "h7"}, pod_cnt=100))
+    ref.reconcile_all(), dut.reconcile_all()
+    assert dut.status("t-late", "default")["used"] == ref.status("t-late", "default")["used"]
+    assert dut.status("t-late", "default")["used"]["resourceCounts"] == {"pod": 1}  # p7, found under its re-packed labels
+    probe = pod("default", "x", "100m", {"app": "app-7", "pod-template-hash": "h7", "tier": "db"})
+    a, b = ref.prefilter(probe), dut.prefilter(probe)
+    assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+    st = dut.queue_stats()
+    assert st["labelKeys"] == 4 and st["labelValues"] == 4 + 4, st
+    dut.close()

@@ -592,10 +592,20 @@ struct kth_plugin {
     if (!ok) fail("resource '" + cols[c].name + "': value " + kt::decimal_string(q) + " does not fit the int64 column at scale 1e" + std::to_string(cols[c].scale_exp));
     return v;
   }
+  // PreFilter of a manifest keeps no state: a resource name nobody has a column for -- no throttle's threshold, override or
+  // status mentions it, no pod of the informer requests it -- cannot influence the check (IsThrottledFor only looks at threshold
+  // resources) and is not given one; a stream of pending pods with ever new extended-resource names must not use up the
+  // KT_MAX_RESOURCES columns (or re-create the engine) for nothing.  Reserve and the informer events do intern: reservations
+  // and status.used carry every name.
+  bool check_only_names = false;
   std::map<int, Quantity> resource_list(const Node& n) {  // corev1.ResourceList
     std::map<int, Quantity> out;
     for (auto& kv : n.obj) {
-      const int c = column(kv.first);
+      const int c = check_only_names ? col_dict.find(kv.first) : column(kv.first);
+      if (c < 0) {
+        (void)kt::parse_quantity(kv.second->scalar());  // a malformed quantity is still an error
+        continue;
+      }
       const Quantity q = kt::parse_quantity(kv.second->scalar());
       note_quantity(c, q);
       out[c] = q;
@@ -2419,7 +2429,10 @@ const char* kth_get_status_manifest(kth_plugin* p, const char* ns, const char* n
 const char* kth_pre_filter(kth_plugin* p, const char* pod_json) {
   return guarded(p, [&]() {
     ktjson::NodePtr v = ktjson::parse(pod_json);
-    std::vector<PodObj> batch{p->pod_from(*v)};
+    p->check_only_names = true;
+    std::vector<PodObj> batch;
+    try { batch.push_back(p->pod_from(*v)); } catch (...) { p->check_only_names = false; throw; }
+    p->check_only_names = false;
     kth_plugin::PendingResult r = p->check_pending(batch, 0);  // PreFilter passes isThrottledOnEqual = false
     Writer w;
     p->prefilter_json(w, batch[0], r, 0);
@@ -2466,7 +2479,8 @@ const char* kth_queue_stats(kth_plugin* p) {
     // device columns the throttles occupy (deleted throttles' columns are handed out again) and how many of them are live
     w.key("throttleColumns").num((long long)p->throttles.size()).key("liveThrottles").num((long long)p->thr_index.size());
     // the label dictionaries: what the selectors mention (+ one "other value" entry per key), however many labels the pods carry
-    w.key("labelKeys").num((long long)p->labels.keys.size()).key("labelValues").num((long long)p->labels.n_values()).end_obj();
+    w.key("labelKeys").num((long long)p->labels.keys.size()).key("labelValues").num((long long)p->labels.n_values());
+    w.key("resourceColumns").num((long long)p->cols.size()).end_obj();
     return w.out;
   });
 }
@@ -2475,7 +2489,9 @@ const char* kth_pre_filter_batch(kth_plugin* p, const char* pods_json) {
     ktjson::NodePtr v = ktjson::parse(pods_json);
     if (!v->is(Node::Arr)) fail("expected a JSON array of pods");
     std::vector<PodObj> batch;
-    for (auto& e : v->arr) batch.push_back(p->pod_from(*e));
+    p->check_only_names = true;
+    try { for (auto& e : v->arr) batch.push_back(p->pod_from(*e)); } catch (...) { p->check_only_names = false; throw; }
+    p->check_only_names = false;
     kth_plugin::PendingResult r = p->check_pending(batch, 0);
     Writer w;
     w.begin_arr();

@@ -327,3 +327,33 @@ def test_label_dictionaries_hold_what_selectors_mention(oracle, host_on_oracle):
     st = dut.queue_stats()
     assert st["labelKeys"] == 4 and st["labelValues"] == 4 + 4, st
     dut.close()
+
+
+def test_prefilter_of_a_manifest_does_not_use_up_resource_columns(oracle, host_on_oracle):
+    """PreFilter keeps no state.  A pending pod that asks for a resource nobody has a column for -- no throttle mentions it, no
+    pod of the informer requests it -- cannot be influenced by it (IsThrottledFor only looks at threshold resources): the name gets
+    no column, and a stream of such pods neither hits the limit of distinct resource names nor re-creates the engine.  Reserve
+    does intern (the reservation carries every name)."""
+    ref, dut = oracle.World(THROTTLER, SCHED), host_on_oracle(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    both(namespace("default"))
+    both(throttle("default", "t", {"a": "1"}, cpu="300m", extra={"example.com/gpu": "2"}))
+    both(pod("default", "r0", "100m", {"a": "1"}, node="n", phase="Running", requests={"memory": "64Mi"}))
+    ref.reconcile_all(), dut.reconcile_all()
+    cols0 = dut.queue_stats()["resourceColumns"]
+    assert cols0 == 3  # cpu, example.com/gpu, memory
+    for i in range(60):  # far more distinct names than the 31 columns there are
+        p = pod("default", f"q{i}", "150m" if i % 2 else "250m", {"a": "1"}, requests={f"vendor-{i}.example.com/widget": str(i + 1), "example.com/gpu": str(i % 4)})
+        a, b = ref.prefilter(p), dut.prefilter(p)
+        assert (a["code"], a["reasons"]) == (b["code"], b["reasons"]), (i, a, b)
+    batch = [pod("default", f"b{i}", "100m", {"a": "1"}, requests={f"batch-{i}.example.com/x": "1"}) for i in range(40)]
+    assert [(r["code"], r["reasons"]) for r in dut.prefilter_batch(batch)] == [(r["code"], r["reasons"]) for r in (ref.prefilter(p) for p in batch)]
+    assert dut.queue_stats()["resourceColumns"] == cols0
+    with pytest.raises(RuntimeError):  # the quantity of an unknown name is still parsed
+        dut.prefilter(pod("default", "bad", "100m", {"a": "1"}, requests={"unknown.example.com/x": "1x"}))
+    p = pod("default", "keep", "100m", {"a": "1"}, requests={"kept.example.com/x": "3"})
+    assert ref.reserve(p)["code"] == dut.reserve(p)["code"] == "Success"
+    assert dut.queue_stats()["resourceColumns"] == cols0 + 1
+    a, b = ref.reserved("Throttle", "default/t"), dut.reserved("Throttle", "default/t")
+    assert sorted(a["pods"]) == sorted(b["pods"]) == ["default/keep"]
+    dut.close()

@@ -195,8 +195,10 @@ int kt_enable_timing(kt_ctx* ctx, int on);
 /* Tracing of the fused pass: with tracing on, every CTA of the next kt_evaluate records {ticket, SM id, start, end,
  * then up to 12 stage stamps whose meaning depends on the tile's role -- see the tile functions in csrc/kt_kernels.cuh}
  * (global timer, ns), then 16 SM-cycle counts of the shared decide tile's steps; kt_get_trace copies up to cap rows of 32
- * uint64 and returns the row count (or a negative kt_status).  Tickets are handed out in role order: pending-match tiles, reconcile tiles, finalize tiles,
- * pending-decide tiles (roles[] reports the four tile counts).  Diagnostic only; off by default. */
+ * uint64 and returns the row count (or a negative kt_status).  Tickets are handed out in role order: pending-match tiles,
+ * reconcile tiles, finalize tiles, pending-decide tiles (roles[] reports the four tile counts; a pass whose match and reconcile
+ * tiles fit the device at once has no finalize / decide CTAs of its own -- that work is drawn from a queue by the CTAs that have
+ * finished their tile, and the rows of those CTAs carry the stamps of their first decide sub-tile).  Diagnostic only; off by default. */
 int kt_enable_trace(kt_ctx* ctx, int on);
 int64_t kt_get_trace(kt_ctx* ctx, uint64_t* rows /*[cap][32]*/, int64_t cap, uint32_t roles[4]);
 /* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost). */

@@ -105,7 +105,9 @@ int64_t kth_queue_row(kth_plugin* p, const char* ns, const char* name);
  * of 32 consecutive rows, so that the 32 rows a warp walks share a namespace under any churn. */
 int64_t kth_pod_row(kth_plugin* p, const char* ns, const char* name);
 const char* kth_last_error(void);
-/* {"queued":n,"rows":r,"passes":device passes over the queue so far,"hits":by-key calls answered from cached verdicts} */
+/* {"queued":n,"rows":r,"passes":device passes over the queue so far,"hits":by-key calls answered from cached verdicts,
+ *  "throttleColumns":device columns the throttles occupy (deleted throttles' columns are reused),"liveThrottles":m,
+ *  "labelKeys":k,"labelValues":v (the label dictionaries: what the selectors mention),"resourceColumns":c} */
 const char* kth_queue_stats(kth_plugin* p);
 
 /* Queue-ordered admission: PreFilter and, on Success, Reserve for every pod of a SORTED scheduling queue, with exactly

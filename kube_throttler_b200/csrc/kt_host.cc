@@ -846,11 +846,99 @@ struct kth_plugin {
     namespaces_dirty = false;
   }
 
+  // ---- device columns in NAMESPACE order ----------------------------------------------------------------------------
+  // A pod only visits the 32-throttle words in which some throttle can apply to its namespace, and every word costs a round
+  // of table gathers and segmented sums: what a pass costs is the number of words per namespace.  Columns in the order the
+  // objects happened to arrive scatter a namespace's throttles over all the words (BASELINE C2 created in random order: 15.6
+  // words per pod instead of 1.7; C3: 31.7 instead of 10.7 -- tools/words_per_namespace.py).  So, whenever the throttle set
+  // changes, the columns are laid out again: Throttles by namespace, ClusterThrottles by the SET of namespaces their
+  // namespaceSelectors admit (largest sets first, equal sets adjacent), creation order inside a group; columns of deleted
+  // throttles disappear.  Nothing the caller sees depends on column order (creation_order above); everything per column on
+  // the device is uploaded again after a throttle change anyway.  (The pod rows get the same treatment: row arenas.)
+  static std::string ns_selector_signature(const ThrottleObj& o) {
+    std::string sig;
+    for (auto& t : o.terms) {
+      if (!t.ns_sel.error.empty()) { sig += "!|"; continue; }  // Q9: swallowed, the term matches no namespace
+      for (auto& r : t.ns_sel.reqs) {
+        sig += r.key;
+        sig += (char)('0' + r.op);
+        for (auto& v : r.values) { sig += v; sig += ','; }
+        sig += ';';
+      }
+      sig += '|';
+    }
+    return sig;
+  }
+  std::string namespace_set_of(const ThrottleObj& o) const {  // one character per namespace id: which namespaces some term admits
+    std::string set(namespaces.size(), '0');
+    for (size_t i = 0; i < namespaces.size(); ++i) {
+      if (!namespaces[i].exists) continue;
+      for (auto& t : o.terms)
+        if (t.ns_sel.error.empty() && ns_selector_matches(t.ns_sel, namespaces[i])) { set[i] = '1'; break; }
+    }
+    return set;
+  }
+  void reorder_columns() {
+    struct Key {
+      int kind;
+      long neg_size;
+      std::string set;
+      uint64_t seq;
+      size_t idx;
+    };
+    std::vector<Key> keys;
+    std::map<std::string, std::pair<long, std::string>> set_of;  // distinct ClusterThrottle signatures: evaluated once
+    bool dead = false;
+    for (size_t t = 0; t < throttles.size(); ++t) {
+      const ThrottleObj& o = throttles[t];
+      if (!o.live) { dead = true; continue; }
+      Key k{o.kind == KT_KIND_THROTTLE ? 0 : 1, 0, std::string(), o.seq, t};
+      if (o.kind == KT_KIND_THROTTLE) {
+        k.set = o.ns;
+      } else {
+        const std::string sig = ns_selector_signature(o);
+        auto it = set_of.find(sig);
+        if (it == set_of.end()) {
+          std::string set = namespace_set_of(o);
+          const long n = (long)std::count(set.begin(), set.end(), '1');
+          it = set_of.emplace(sig, std::make_pair(-n, std::move(set))).first;
+        }
+        k.neg_size = it->second.first;
+        k.set = it->second.second;
+      }
+      keys.push_back(std::move(k));
+    }
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+      if (a.kind != b.kind) return a.kind < b.kind;
+      if (a.neg_size != b.neg_size) return a.neg_size < b.neg_size;
+      if (a.set != b.set) return a.set < b.set;
+      return a.seq < b.seq;
+    });
+    bool same = !dead;
+    for (size_t i = 0; same && i < keys.size(); ++i) same = keys[i].idx == i;
+    if (same) return;
+    std::vector<ThrottleObj> laid_out;
+    laid_out.reserve(keys.size());
+    for (auto& k : keys) laid_out.push_back(std::move(throttles[k.idx]));
+    throttles = std::move(laid_out);
+    thr_index.clear();
+    free_thr.clear();
+    thr_reused = false;
+    for (size_t t = 0; t < throttles.size(); ++t) {
+      thr_index[std::string(throttles[t].kind == KT_KIND_THROTTLE ? "T:" : "C:") + throttles[t].nn()] = (int)t;
+      if (t && throttles[t].seq < throttles[t - 1].seq) thr_reused = true;  // column order is not creation order
+    }
+    broken_valid = false;
+    queue_void();
+    status_dirty = reserved_dirty = true;
+  }
+
   // Throttle specs -> kt_throttle_cols + kt_selector_table.  Terms after the first invalid podSelector are
   // unreachable in the reference (MatchesToPod returns the error first), so they are not compiled.
   void sync_throttles() {
     ensure_engine();
     if (!throttles_dirty) return;
+    reorder_columns();
     const int R = lim.n_resources;
     const size_t m = throttles.size();
     std::vector<uint8_t> kind(m), flags(m);
@@ -2480,7 +2568,28 @@ const char* kth_queue_stats(kth_plugin* p) {
     w.key("throttleColumns").num((long long)p->throttles.size()).key("liveThrottles").num((long long)p->thr_index.size());
     // the label dictionaries: what the selectors mention (+ one "other value" entry per key), however many labels the pods carry
     w.key("labelKeys").num((long long)p->labels.keys.size()).key("labelValues").num((long long)p->labels.n_values());
-    w.key("resourceColumns").num((long long)p->cols.size()).end_obj();
+    w.key("resourceColumns").num((long long)p->cols.size());
+    {  // 32-throttle words a namespace's pods visit (x100, mean over the existing namespaces): what the column order is about
+      long long total = 0, n_ns = 0;
+      for (size_t i = 0; i < p->namespaces.size(); ++i) {
+        if (!p->namespaces[i].exists) continue;
+        std::set<size_t> words;
+        for (size_t t = 0; t < p->throttles.size(); ++t) {
+          const ThrottleObj& o = p->throttles[t];
+          if (!o.live) continue;
+          bool applies = false;
+          if (o.kind == KT_KIND_THROTTLE) applies = o.ns == p->namespaces[i].name;
+          else
+            for (auto& term : o.terms)
+              if (term.ns_sel.error.empty() && kth_plugin::ns_selector_matches(term.ns_sel, p->namespaces[i])) { applies = true; break; }
+          if (applies) words.insert(t >> 5);
+        }
+        total += (long long)words.size();
+        ++n_ns;
+      }
+      w.key("wordsPerNamespaceX100").num(n_ns ? total * 100 / n_ns : 0);
+    }
+    w.end_obj();
     return w.out;
   });
 }

@@ -357,3 +357,36 @@ def test_prefilter_of_a_manifest_does_not_use_up_resource_columns(oracle, host_o
     a, b = ref.reserved("Throttle", "default/t"), dut.reserved("Throttle", "default/t")
     assert sorted(a["pods"]) == sorted(b["pods"]) == ["default/keep"]
     dut.close()
+
+
+def test_device_columns_are_laid_out_by_namespace(oracle, host_on_oracle):
+    """What a pass costs per pod is the number of 32-throttle words in which some throttle can apply to its namespace.  Throttles
+    arrive in whatever order their owners create them; the host lays the device columns out by namespace (ClusterThrottles by the
+    set of namespaces their namespaceSelectors admit), so a namespace's throttles share words -- and nothing the caller sees
+    depends on it: the names inside a reason stay in creation order."""
+    import random
+
+    rng = random.Random(3)
+    ref, dut = oracle.World(THROTTLER, SCHED), host_on_oracle(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i:02d}" for i in range(24)]
+    both(*[namespace(n, {"team": f"team{i % 3}"}) for i, n in enumerate(nss)])
+    objs = [throttle(n, f"t{j}", {"a": "1"}, cpu="100m") for n in nss for j in range(10)]
+    objs += [{"kind": "ClusterThrottle", "metadata": {"name": f"ct-{team}-{j}"},
+              "spec": {"throttlerName": THROTTLER, "threshold": {"resourceRequests": {"cpu": "100m"}},
+                       "selector": {"selectorTerms": [{"podSelector": {"matchLabels": {"a": "1"}}, "namespaceSelector": {"matchLabels": {"team": team}}}]}}}
+             for team in ("team0", "team1", "team2") for j in range(12)]
+    rng.shuffle(objs)  # 276 throttles = 9 words, created in random order: every namespace would see ~9 of them
+    both(*objs)
+    ref.reconcile_all(), dut.reconcile_all()
+    st = dut.queue_stats()
+    assert st["liveThrottles"] == st["throttleColumns"] == len(objs)
+    assert st["wordsPerNamespaceX100"] <= 400, st  # 10 Throttles of its own (1-2 words) + its team's 12 ClusterThrottles (1-2 words)
+    order = [o["metadata"].get("namespace", "") + "/" + o["metadata"]["name"] for o in objs]
+    for n in rng.sample(nss, 6):
+        probe = pod(n, "x", "500m", {"a": "1"})
+        a, b = ref.prefilter(probe), dut.prefilter(probe)
+        assert (a["code"], a["reasons"]) == (b["code"], b["reasons"])
+        names = b["reasons"][0].split("=")[1].split(",")  # clusterthrottle[...] comes first (plugin.go:182-213)
+        assert names == [x for x in order if x in names] and len(names) == 12, names
+    dut.close()

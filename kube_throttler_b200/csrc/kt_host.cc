@@ -828,6 +828,7 @@ struct kth_plugin {
   void sync_namespaces() {
     ensure_engine();
     if (!namespaces_dirty) return;
+    queue_void();  // (see sync_throttles)
     const int LN = lim.ns_label_slots;
     const size_t n = namespaces.size();
     std::vector<int64_t> lab((size_t)LN * std::max<size_t>(n, 1), KT_LABEL_EMPTY);
@@ -938,6 +939,10 @@ struct kth_plugin {
   void sync_throttles() {
     ensure_engine();
     if (!throttles_dirty) return;
+    // The cached verdicts of the resident queue were computed with the old tables: whoever brings the new ones to the device --
+    // a PreFilter pass or, before it, a reconcile -- voids them.  (Found by the resident-queue event stream of the second session
+    // of round 2: throttle edit, reconcile, PreFilter by key answered from the cache of the OLD throttle set.)
+    queue_void();
     reorder_columns();
     const int R = lim.n_resources;
     const size_t m = throttles.size();

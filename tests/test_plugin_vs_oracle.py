@@ -783,6 +783,102 @@ def test_event_stream_chaos(oracle, new_plugin, seed):
     run_event_stream(oracle, new_plugin, seed)
 
 
+def run_queue_stream(oracle, new_plugin, seed):
+    """The RESIDENT scheduling queue under churn: the pending pods are delivered by the informer (they live in the device's
+    pending table), PreFilter / Reserve / Unreserve address them by key, the whole queue is asked for in one call -- while
+    throttles of both kinds are created, edited (new selector vocabulary: rows packed as 'some other value' are packed again),
+    deleted and re-created (the device columns are laid out again), pods are relabelled, bound and deleted, namespaces relabelled.
+    Every by-key verdict must equal the oracle's PreFilter of the same pod, every verdict byte of the queue call its code."""
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    key = lambda p: (p["metadata"]["namespace"], p["metadata"]["name"])
+    nss = [f"ns{i}" for i in range(5)]
+    both(*[namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}) for n in nss])
+    throttles = [rand_throttle(rng, i, nss) for i in range(10)]
+    both(*throttles)
+    both(*[rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(50)])
+    queue = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(36)]
+    both(*queue)
+    names = {"Success": 1, "UnschedulableAndUnresolvable": 2, "Error": 3}
+    reserved, log = [], []
+    for step in range(50):
+        op = rng.random()
+        if op < 0.12:
+            now = rng.choice(TIMES); log.append(("reconcile", now))
+            try: ref.reconcile_all(now)
+            except RuntimeError: pass
+            dut.reconcile_all(now)
+        elif op < 0.40 and queue:
+            p = rng.choice(queue); log.append(("prefilter-key", key(p)))
+            a, b = ref.prefilter(p), dut.prefilter_key(*key(p))
+            assert norm_prefilter(a) == norm_prefilter(b), (seed, step, log[-5:], a, b)
+            if a["code"] == "Success" and rng.random() < 0.6:
+                assert ref.reserve(p)["code"] == dut.reserve_key(*key(p))["code"] == "Success"
+                if p not in reserved: reserved.append(p)
+        elif op < 0.47 and queue:
+            log.append(("prefilter-queue", len(queue)))
+            verdicts = dut.prefilter_queue()
+            for p in queue:
+                row = dut.queue_row(*key(p))
+                if row < 0:
+                    assert p["spec"]["schedulerName"] != SCHED, (seed, step, key(p))
+                    continue
+                assert verdicts[row] == names[ref.prefilter(p)["code"]], (seed, step, log[-5:], key(p))
+        elif op < 0.55 and reserved:
+            p = reserved.pop(rng.randrange(len(reserved))); log.append(("bind-or-unreserve", key(p)))
+            if rng.random() < 0.5:
+                queue.remove(p)
+                both(dict(p, spec=dict(p["spec"], nodeName="node-9"), status={"phase": "Running"}))
+                assert dut.queue_row(*key(p)) == -1
+            else:
+                ref.unreserve(p), dut.unreserve_key(*key(p))
+        elif op < 0.63 and queue:
+            p = rng.choice(queue); log.append(("relabel-queued", key(p)))
+            p["metadata"]["labels"] = rand_labels(rng)
+            both(p)
+        elif op < 0.78:
+            i = rng.randrange(len(throttles) + 3); log.append(("apply-throttle", i))  # an edit, or a new one
+            t = rand_throttle(rng, i, nss)
+            if i < len(throttles):
+                t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
+                if t["kind"] == "Throttle":
+                    for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+                throttles[i] = t
+            else:
+                t["metadata"]["name"] += f"-s{step}"
+                throttles.append(t)
+            both(t)
+        elif op < 0.84 and len(throttles) > 4:
+            t = throttles.pop(rng.randrange(len(throttles))); log.append(("delete-throttle", t["metadata"]["name"]))
+            md = t["metadata"]
+            ref.delete(t["kind"], md["name"], md.get("namespace", "")), dut.delete(t["kind"], md["name"], md.get("namespace", ""))
+        elif op < 0.89:
+            n = rng.choice(nss); log.append(("relabel-ns", n))
+            both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+        elif op < 0.94 and len(queue) > 10:
+            p = queue.pop(rng.randrange(len(queue))); log.append(("delete-queued", key(p)))
+            if p in reserved: reserved.remove(p)
+            ref.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"]), dut.delete("Pod", p["metadata"]["name"], p["metadata"]["namespace"])
+        else:
+            p = rand_pod(rng, rng.choice(nss), f"n{step}", False); queue.append(p); log.append(("new-queued", key(p)))
+            both(p)
+    for p in queue:
+        a, b = ref.prefilter(p), dut.prefilter_key(*key(p))
+        assert norm_prefilter(a) == norm_prefilter(b), (seed, "final", key(p), a, b)
+    for t in throttles:
+        k, nn = t["kind"], t["metadata"].get("namespace", "") + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (seed, "reserved", nn, a, b)
+    dut.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 2410, 2703, 2793])  # 2410 ...: a throttle edit, then a RECONCILE, then PreFilter by key -- the cached
+def test_resident_queue_event_stream(oracle, new_plugin, seed):      # verdicts of the old throttle set must not answer (they did)
+    """Random events against the resident scheduling queue, by key (tools/chaos_host.py runs more seeds on the CPU double)."""
+    run_queue_stream(oracle, new_plugin, seed)
+
+
 def test_pods_of_a_namespace_the_lister_does_not_hold(oracle, new_plugin):
     """ClusterThrottleController.affectedPods walks the namespaces the lister returns (clusterthrottle_controller.go:227): pods of
     a namespace that was never seen, or was deleted, are not counted by ANY ClusterThrottle -- not even one whose namespaceSelector

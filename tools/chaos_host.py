@@ -1,4 +1,4 @@
-"""More seeds of tests/test_plugin_vs_oracle.py::test_event_stream_chaos on the CPU: the product's host layer (kt_host.cc) over the
+"""More seeds of tests/test_plugin_vs_oracle.py::test_event_stream_chaos and ::test_resident_queue_event_stream on the CPU: the product's host layer (kt_host.cc) over the
 oracle-backed engine test double against the object-level oracle.      python tools/chaos_host.py [first=0] [last=200]"""
 import ctypes
 import functools
@@ -27,11 +27,12 @@ def main():
     ctor = functools.partial(host.Plugin, library=ctypes.CDLL(out))
     bad = 0
     for seed in range(first, last):
-        try:
-            T.run_event_stream(ko, ctor, seed)
-        except AssertionError as e:
-            bad += 1
-            print("seed", seed, "DIFFERS:", str(e)[:800])
+        for stream in (T.run_event_stream, T.run_queue_stream):
+            try:
+                stream(ko, ctor, seed)
+            except AssertionError as e:
+                bad += 1
+                print(stream.__name__, "seed", seed, "DIFFERS:", str(e)[:800])
     print(f"seeds {first}..{last - 1}: {bad} differences")
     return 1 if bad else 0
 

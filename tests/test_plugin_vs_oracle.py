@@ -659,13 +659,13 @@ def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
 
 # ---- random EVENT STREAMS: informer events, scheduling cycles and reconciles interleaved at random ---------------------------
 TIMES = ["2026-01-01T00:00:00Z", "2026-01-15T12:00:00Z", "2026-03-01T12:00:00Z", "2025-12-31T23:59:59Z"]
-def run_event_stream(oracle, new_plugin, seed):
+def run_event_stream(oracle, new_plugin, seed, n_thr=14, n_ns=4):
     rng = random.Random(seed)
     ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
     both = lambda *m: (ref.apply(*m), dut.apply(*m))
-    nss = [f"ns{i}" for i in range(4)]
+    nss = [f"ns{i}" for i in range(n_ns)]
     for n in nss: both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
-    throttles = [rand_throttle(rng, i, nss) for i in range(14)]
+    throttles = [rand_throttle(rng, i, nss) for i in range(n_thr)]  # (tools/chaos_host.py also runs 80 of them: several 32-throttle words)
     both(*throttles)
     pods = [rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(60)]
     both(*pods)
@@ -783,7 +783,7 @@ def test_event_stream_chaos(oracle, new_plugin, seed):
     run_event_stream(oracle, new_plugin, seed)
 
 
-def run_queue_stream(oracle, new_plugin, seed):
+def run_queue_stream(oracle, new_plugin, seed, n_thr=10):
     """The RESIDENT scheduling queue under churn: the pending pods are delivered by the informer (they live in the device's
     pending table), PreFilter / Reserve / Unreserve address them by key, the whole queue is asked for in one call -- while
     throttles of both kinds are created, edited (new selector vocabulary: rows packed as 'some other value' are packed again),
@@ -795,7 +795,7 @@ def run_queue_stream(oracle, new_plugin, seed):
     key = lambda p: (p["metadata"]["namespace"], p["metadata"]["name"])
     nss = [f"ns{i}" for i in range(5)]
     both(*[namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}) for n in nss])
-    throttles = [rand_throttle(rng, i, nss) for i in range(10)]
+    throttles = [rand_throttle(rng, i, nss) for i in range(n_thr)]
     both(*throttles)
     both(*[rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(50)])
     queue = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(36)]

@@ -27,12 +27,15 @@ def main():
     ctor = functools.partial(host.Plugin, library=ctypes.CDLL(out))
     bad = 0
     for seed in range(first, last):
-        for stream in (T.run_event_stream, T.run_queue_stream):
+        import functools as ft
+        for name, stream in (("events", T.run_event_stream), ("queue", T.run_queue_stream),
+                             ("events, 80 throttles x 9 namespaces", ft.partial(T.run_event_stream, n_thr=80, n_ns=9)),
+                             ("queue, 70 throttles", ft.partial(T.run_queue_stream, n_thr=70))):
             try:
                 stream(ko, ctor, seed)
             except AssertionError as e:
                 bad += 1
-                print(stream.__name__, "seed", seed, "DIFFERS:", str(e)[:800])
+                print(name, "seed", seed, "DIFFERS:", str(e)[:800])
     print(f"seeds {first}..{last - 1}: {bad} differences")
     return 1 if bad else 0
 

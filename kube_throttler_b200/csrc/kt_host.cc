@@ -507,6 +507,7 @@ struct kth_plugin {
   // throttles of a pod (the order of the names inside a PreFilter reason), the broken-selector walk (WHICH error a pod gets),
   // reconcile's changed list -- is in creation order, as the reference's lister-backed slices are, not in column order.
   std::vector<int> free_thr;
+  long long words_stat = -1;  // kth_queue_stats: words per namespace of the current layout (-1: not computed)
   uint64_t thr_seq = 0;
   bool thr_reused = false;  // some column holds a younger throttle than a higher one: column order is not creation order any more
   template <class V>
@@ -829,6 +830,7 @@ struct kth_plugin {
     ensure_engine();
     if (!namespaces_dirty) return;
     queue_void();  // (see sync_throttles)
+    words_stat = -1;
     const int LN = lim.ns_label_slots;
     const size_t n = namespaces.size();
     std::vector<int64_t> lab((size_t)LN * std::max<size_t>(n, 1), KT_LABEL_EMPTY);
@@ -943,6 +945,7 @@ struct kth_plugin {
     // a PreFilter pass or, before it, a reconcile -- voids them.  (Found by the resident-queue event stream of the second session
     // of round 2: throttle edit, reconcile, PreFilter by key answered from the cache of the OLD throttle set.)
     queue_void();
+    words_stat = -1;
     reorder_columns();
     const int R = lim.n_resources;
     const size_t m = throttles.size();
@@ -2574,7 +2577,7 @@ const char* kth_queue_stats(kth_plugin* p) {
     // the label dictionaries: what the selectors mention (+ one "other value" entry per key), however many labels the pods carry
     w.key("labelKeys").num((long long)p->labels.keys.size()).key("labelValues").num((long long)p->labels.n_values());
     w.key("resourceColumns").num((long long)p->cols.size());
-    {  // 32-throttle words a namespace's pods visit (x100, mean over the existing namespaces): what the column order is about
+    if (p->words_stat < 0 || p->throttles_dirty || p->namespaces_dirty) {  // (cached per table version: M x namespaces selector evaluations)
       long long total = 0, n_ns = 0;
       for (size_t i = 0; i < p->namespaces.size(); ++i) {
         if (!p->namespaces[i].exists) continue;
@@ -2592,8 +2595,11 @@ const char* kth_queue_stats(kth_plugin* p) {
         total += (long long)words.size();
         ++n_ns;
       }
-      w.key("wordsPerNamespaceX100").num(n_ns ? total * 100 / n_ns : 0);
+      p->words_stat = n_ns ? total * 100 / n_ns : 0;
     }
+    // 32-throttle words a namespace's pods visit (x100, mean over the existing namespaces): what the column order is about
+    w.key("wordsPerNamespaceX100").num(p->words_stat);
+    if (p->throttles_dirty || p->namespaces_dirty) p->words_stat = -1;  // not laid out yet: do not keep it
     w.end_obj();
     return w.out;
   });

@@ -39,7 +39,7 @@ def analyse(cfg):
         return wp.mean(), wp.max(), (wp*cnt).sum()/cnt.sum()
     rng=np.random.default_rng(0)
     orders={"synth order":np.arange(m), "random creation order":rng.permutation(m),
-            "sorted by (kind, namespace set)":np.array(sorted(range(m),key=lambda t:(int(snap.kind[t]), -int(applies[t].sum()), tuple(applies[t].tolist()), t)))}
+            "sorted by (kind, namespace set)":np.array(sorted(range(m),key=lambda t:(int(snap.kind[t]), tuple(applies[t].tolist()), t)))}
     print(cfg)
     for k,o in orders.items(): print("  %-36s words per namespace mean %.1f max %d | per running pod %.2f" % ((k,)+words(o)))
 for cfg in (sys.argv[1:] or ["C2", "C3"]):

@@ -90,7 +90,32 @@ def _gen_pods(rng, n: int, n_ns: int, R: int, L: int, running: bool, sort_by_nam
     return abi.PodCols(labels, req, present.astype(np.uint32), flags.astype(np.uint32), ns)
 
 
-def _gen_selectors(rng, m: int, kind: np.ndarray, q_max: int = 0):
+def _namespace_set(ns_reqs_of_terms, ns_labels) -> str:
+    """One character per namespace: does some term's namespaceSelector admit it?  (What kt_host.cc orders its ClusterThrottle
+    columns by: reorder_columns.)"""
+    LN, n_ns = ns_labels.shape
+    out = []
+    for ns in range(n_ns):
+        have = {int(v) >> 32: int(v) & 0xFFFFFFFF for v in ns_labels[:, ns] if int(v) != abi.LABEL_EMPTY}
+        ok_any = False
+        for reqs in ns_reqs_of_terms:
+            ok = True
+            for key, op, vals in reqs:
+                present = key in have
+                if op == abi.OP_IN: ok = present and have[key] in vals
+                elif op == abi.OP_NOTIN: ok = (not present) or have[key] not in vals
+                elif op == abi.OP_EXISTS: ok = present
+                else: ok = not present
+                if not ok:
+                    break
+            if ok:
+                ok_any = True
+                break
+        out.append("1" if ok_any else "0")
+    return "".join(out)
+
+
+def _gen_selectors(rng, m: int, kind: np.ndarray, q_max: int = 0, layout_ns_labels=None):
     """CSR selector table: T in {1,2} (80/20), Q in {1,2,3} (60/30/10); 85% equality, 5% each
     In(2-3 values) / NotIn / Exists / DoesNotExist.  ClusterThrottle terms get 0-2 namespace requirements.
     Requirement pool layout: all podSelector requirements (term order), then all namespaceSelector ones."""
@@ -129,6 +154,21 @@ def _gen_selectors(rng, m: int, kind: np.ndarray, q_max: int = 0):
             pod_reqs.append(pr)
             ns_reqs.append(nr)
         term_off.append(len(pod_reqs))
+    if layout_ns_labels is not None:
+        # the ClusterThrottles in the order the product's host layer lays its device columns out in: by the set of namespaces
+        # their namespaceSelectors admit (only WHICH selector goes to which ClusterThrottle index changes; everything else of a
+        # throttle is drawn independently of it)
+        blocks = [(pod_reqs[term_off[t]:term_off[t + 1]], ns_reqs[term_off[t]:term_off[t + 1]]) for t in range(m)]
+        ct = [t for t in range(m) if kind[t] == abi.KIND_CLUSTERTHROTTLE]
+        order = sorted(ct, key=lambda t: (_namespace_set(blocks[t][1], layout_ns_labels), t))
+        laid = list(blocks)
+        for dst, src in zip(ct, order):
+            laid[dst] = blocks[src]
+        term_off, pod_reqs, ns_reqs = [0], [], []
+        for pr, nr in laid:
+            pod_reqs.extend(pr)
+            ns_reqs.extend(nr)
+            term_off.append(len(pod_reqs))
     return build_selector_csr(term_off, pod_reqs, ns_reqs)
 
 
@@ -245,7 +285,7 @@ def true_used_numpy(snap: abi.Snapshot):
 
 def generate(config: str = "C2", *, seed=None, m=None, n=None, p=None, R=None, n_ns=None, cluster_frac=None,
              override_frac=None, L: int = 8, sort_by_namespace: bool = True, now: int = NOW_2026,
-             calibrate: bool = True, q_max: int = 0) -> abi.Snapshot:
+             calibrate: bool = True, q_max: int = 0, column_layout: bool = False) -> abi.Snapshot:
     """Build the snapshot of a BASELINE config (or a scaled variant via keyword overrides)."""
     base = dict(CONFIGS[config])
     for k, v in dict(seed=seed, m=m, n=n, p=p, R=R, n_ns=n_ns, cluster_frac=cluster_frac, override_frac=override_frac).items():
@@ -277,7 +317,8 @@ def generate(config: str = "C2", *, seed=None, m=None, n=None, p=None, R=None, n
     thr_flags = np.full(m, abi.THR_RESPONSIBLE, np.uint8)
     thr_flags[rng.random(m) < 0.01] = 0  # 1% belong to another throttler instance
 
-    sel = _gen_selectors(rng, m, kind, q_max)  # q_max > 3: terms needing > 3 keys present (6-bit counters)
+    # q_max > 3: terms needing > 3 keys present (6-bit counters); column_layout: ClusterThrottles ordered as kt_host.cc orders them
+    sel = _gen_selectors(rng, m, kind, q_max, layout_ns_labels=ns_labels if column_layout else None)
 
     snap = abi.Snapshot(
         R=R, L=L, LN=LN, running=running, pending=pending, ns_labels=ns_labels, kind=kind, thr_ns=thr_ns,

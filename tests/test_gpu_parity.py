@@ -64,6 +64,7 @@ def test_c1_example(kt, oracle):
     dict(config="C2", m=200, n=5000, p=700, L=12, q_max=6),               # terms with > 3 required keys: 6-bit counters
     dict(config="C3", m=120, n=2000, p=300, R=31, L=16),                  # the limits: every resource bit in use, two label chunks
     dict(config="C3", m=64, n=3000, p=400, L=3, R=2),                     # fewer label slots than a chunk
+    dict(config="C3", m=300, n=6000, p=800, column_layout=True),          # ClusterThrottles in the host layer's column order (by namespace set)
     dict(config="C2", m=150, n=300, p=6000),                              # far more pending than running rows: 50 CTAs serve ~200 decide sub-tiles / status tiles
     dict(config="C3", m=400, n=500, p=5000, sort_by_namespace=False),     # the same with ClusterThrottles and rows in arrival order: several rounds per sub-tile, pairs checked straight from L2
 ])

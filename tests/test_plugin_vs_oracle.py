@@ -659,7 +659,7 @@ def test_q8_finished_pods_keep_their_reservation(oracle, new_plugin):
 
 # ---- random EVENT STREAMS: informer events, scheduling cycles and reconciles interleaved at random ---------------------------
 TIMES = ["2026-01-01T00:00:00Z", "2026-01-15T12:00:00Z", "2026-03-01T12:00:00Z", "2025-12-31T23:59:59Z"]
-def run_event_stream(oracle, new_plugin, seed, n_thr=14, n_ns=4):
+def run_event_stream(oracle, new_plugin, seed, n_thr=14, n_ns=4, check_every_reconcile=False):
     rng = random.Random(seed)
     ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
     both = lambda *m: (ref.apply(*m), dut.apply(*m))
@@ -680,6 +680,15 @@ def run_event_stream(oracle, new_plugin, seed, n_thr=14, n_ns=4):
             try: ref.reconcile_all(now)
             except RuntimeError: pass
             dut.reconcile_all(now)
+            if check_every_reconcile:  # (tools/chaos_host.py: every status and reservation after EVERY reconcile, not only at the end)
+                for i, t in enumerate(throttles):
+                    ns = t["metadata"].get("namespace", "")
+                    if i not in gone:
+                        a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+                        assert norm_status(a) == norm_status(b), (seed, step, "status", t["metadata"], log[-5:], a, b)
+                    k, nn = t["kind"], ns + "/" + t["metadata"]["name"]
+                    a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+                    assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (seed, step, "reserved", nn, log[-5:], a, b)
         elif op < 0.23:
             batch = rng.sample(pending, 6); log.append(("prefilter-batch", [p["metadata"]["name"] for p in batch]))
             want = [ref.prefilter(p) for p in batch]

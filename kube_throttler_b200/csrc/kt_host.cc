@@ -1472,11 +1472,16 @@ struct kth_plugin {
       for (auto& kv : o.st_calc.requests) thr_req[kv.first] = (throttled[q] >> kv.first) & 1;
       const bool thr_nil = o.st_calc.requests.empty();
       if (thr_pod != o.st_thr_pod || thr_req != o.st_thr_req) status_changed = true;
-      o.st_thr_pod = thr_pod;
-      o.st_thr_req = thr_req;
-      o.st_thr_req_nil = thr_nil;
-      if (!amount_equal(o.st_used, nu) || o.st_used.requests_nil != nu.requests_nil) status_changed = true;
-      o.st_used = nu;
+      // apiequality.Semantic.DeepEqual (throttle_controller.go:157): an empty map IS a nil map -- a status that differs from the
+      // informer copy in nil-ness only is not written, and the copy keeps its own (found by a third random event stream, with
+      // statuses arriving through the informer: `used: {resourceRequests: {}}` on a throttle that matches no pod)
+      if (!amount_equal(o.st_used, nu)) status_changed = true;
+      if (status_changed) {  // UpdateStatus(newStatus): the whole of it replaces the copy
+        o.st_thr_pod = thr_pod;
+        o.st_thr_req = thr_req;
+        o.st_thr_req_nil = thr_nil;
+        o.st_used = nu;
+      }
       o.metrics_pending = true;  // both branches of the status comparison record (throttle_controller.go:159,187); see record_metrics
       if (status_changed) {
         changed.push_back(o.nn());

@@ -888,6 +888,78 @@ def test_resident_queue_event_stream(oracle, new_plugin, seed):      # verdicts 
     run_queue_stream(oracle, new_plugin, seed)
 
 
+def rand_status(rng):
+    """A status subresource as another writer (a restart, a second controller instance) may have left it."""
+    st = {}
+    if rng.random() < 0.8:
+        ct = {"threshold": rand_amount(rng, 2)}
+        if rng.random() < 0.7: ct["calculatedAt"] = rng.choice(TIMES)
+        if rng.random() < 0.2: ct["messages"] = ["m"]
+        st["calculatedThreshold"] = ct
+    thr = {}
+    if rng.random() < 0.6: thr["resourceCounts"] = {"pod": rng.random() < 0.3}
+    if rng.random() < 0.7: thr["resourceRequests"] = {k: rng.random() < 0.3 for k in rng.sample(["cpu", "memory", "nvidia.com/gpu"], rng.randrange(0, 3))}
+    if thr: st["throttled"] = thr
+    if rng.random() < 0.8: st["used"] = rand_amount(rng, 3)
+    return st
+
+
+def run_status_stream(oracle, new_plugin, seed):
+    """PreFilter reads the INFORMER COPY of .status (plugin.go:148-216 -> CheckThrottledFor with the status as it was last
+    delivered): statuses arrive through the informer -- at start-up, from another writer -- stale or plain wrong, with or without
+    calculatedAt (Q6: which threshold counts), with throttled flags and used amounts that have nothing to do with the pods;
+    reconciles replace them only where apiequality.Semantic.DeepEqual says they differ.  Every verdict in between and every status
+    after every reconcile must equal the oracle's."""
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    nss = [f"ns{i}" for i in range(4)]
+    both(*[namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}) for n in nss])
+    throttles = [rand_throttle(rng, i, nss) for i in range(12)]
+    both(*[dict(t, status=rand_status(rng)) if rng.random() < 0.7 else t for t in throttles])  # what the informer delivers at start-up
+    both(*[rand_pod(rng, rng.choice(nss), f"p{i}", True) for i in range(40)])
+    pending = [rand_pod(rng, rng.choice(nss), f"q{i}", False) for i in range(30)]
+    log = []
+    for step in range(40):
+        op = rng.random()
+        if op < 0.5:
+            p = rng.choice(pending); log.append(("prefilter", p["metadata"]["name"]))
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert norm_prefilter(a) == norm_prefilter(b), (seed, step, log[-5:], a, b)
+            if a["code"] == "Success" and rng.random() < 0.5:
+                assert ref.reserve(p)["code"] == dut.reserve(p)["code"]
+        elif op < 0.7:
+            i = rng.randrange(len(throttles)); log.append(("apply-status", i))  # another writer's status arrives through the informer
+            both(dict(throttles[i], status=rand_status(rng)))
+        elif op < 0.8:
+            i = rng.randrange(len(throttles)); log.append(("edit-spec", i))   # a spec update: the status is kept
+            t = rand_throttle(rng, i, nss); t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
+            if t["kind"] == "Throttle":
+                for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+            throttles[i] = t
+            both(t)
+        elif op < 0.9:
+            now = rng.choice(TIMES); log.append(("reconcile", now))
+            try: ref.reconcile_all(now)
+            except RuntimeError: pass
+            dut.reconcile_all(now)
+            for t in throttles:
+                ns = t["metadata"].get("namespace", "")
+                a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+                assert norm_status(a) == norm_status(b), (seed, step, "status", t["metadata"], log[-5:], a, b)
+        else:
+            batch = rng.sample(pending, 5); log.append(("batch", 5))
+            want = [ref.prefilter(p) for p in batch]
+            got = dut.prefilter_batch(batch)
+            assert [norm_prefilter(a) for a in want] == [norm_prefilter(b) for b in got], (seed, step, log[-5:])
+    dut.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 143])  # 143: `used: {resourceRequests: {}}` on a throttle that matches no pod -- nil and empty maps are EQUAL
+def test_status_event_stream(oracle, new_plugin, seed):
+    run_status_stream(oracle, new_plugin, seed)
+
+
 def test_pods_of_a_namespace_the_lister_does_not_hold(oracle, new_plugin):
     """ClusterThrottleController.affectedPods walks the namespaces the lister returns (clusterthrottle_controller.go:227): pods of
     a namespace that was never seen, or was deleted, are not counted by ANY ClusterThrottle -- not even one whose namespaceSelector

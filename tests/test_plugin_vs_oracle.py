@@ -960,6 +960,117 @@ def test_status_event_stream(oracle, new_plugin, seed):
     run_status_stream(oracle, new_plugin, seed)
 
 
+EXTRA_RES = [f"vendor{i}.example.com/dev" for i in range(18)]
+FINE = ["1n", "100n", "0.000001", "1u", "0.0015", "333m", "1.0000001"]
+def grow_pod(rng, ns, name, running, stage):
+    p = rand_pod(rng, ns, name, running)
+    # stage grows: more labels (-> 16 / 32 label slots), more resource names (-> 8 / 16 / 31 columns), finer quantities (column re-scale)
+    for i in range(rng.randrange(0, 1 + 4 * stage)):
+        p["metadata"]["labels"][f"extra-{rng.randrange(0, 6 * stage + 1)}"] = rng.choice(VALS)
+    reqs = p["spec"]["containers"][0]["resources"]["requests"]
+    for r in rng.sample(EXTRA_RES[: 3 + 4 * stage], rng.randrange(0, min(3 + stage, 3 + 4 * stage))):
+        reqs[r] = str(rng.randrange(0, 5))
+    if rng.random() < 0.15 * stage: reqs["cpu"] = rng.choice(FINE)
+    return p
+def grow_throttle(rng, i, nss, stage):
+    t = rand_throttle(rng, i, nss)
+    rr = t["spec"]["threshold"].setdefault("resourceRequests", {})
+    for r in rng.sample(EXTRA_RES[: 3 + 4 * stage], rng.randrange(0, 3)):
+        rr[r] = str(rng.randrange(0, 9))
+    if rng.random() < 0.1 * stage: rr["cpu"] = rng.choice(FINE + ["2", "0.5"])
+    if rng.random() < 0.3 and t["spec"]["selector"]["selectorTerms"]:
+        t["spec"]["selector"]["selectorTerms"][0]["podSelector"].setdefault("matchLabels", {})[f"extra-{rng.randrange(0, 6 * stage + 1)}"] = rng.choice(VALS)
+    return t
+def run_growth_stream(oracle, new_plugin, seed):
+    rng = random.Random(seed)
+    ref, dut = oracle.World(THROTTLER, SCHED), new_plugin(THROTTLER, SCHED)
+    both = lambda *m: (ref.apply(*m), dut.apply(*m))
+    key = lambda p: (p["metadata"]["namespace"], p["metadata"]["name"])
+    nss = [f"ns{i}" for i in range(4)]
+    both(*[namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}) for n in nss])
+    throttles = [grow_throttle(rng, i, nss, 0) for i in range(10)]
+    both(*throttles)
+    pods = [grow_pod(rng, rng.choice(nss), f"p{i}", True, 0) for i in range(30)]
+    both(*pods)
+    queue = [grow_pod(rng, rng.choice(nss), f"q{i}", False, 0) for i in range(16)]
+    both(*queue)
+    reserved, log = [], []
+    for step in range(48):
+        stage = step // 12  # the limits are crossed as the stream goes on
+        op = rng.random()
+        if op < 0.12:
+            now = rng.choice(TIMES); log.append(("reconcile", now))
+            try: ref.reconcile_all(now)
+            except RuntimeError: pass
+            dut.reconcile_all(now)
+            for t in throttles:
+                ns = t["metadata"].get("namespace", "")
+                a, b = ref.status(t["metadata"]["name"], ns), dut.status(t["metadata"]["name"], ns)
+                assert norm_status(a) == norm_status(b), (seed, step, "status", t["metadata"], log[-5:], a, b)
+        elif op < 0.35:
+            p = rng.choice(queue); log.append(("prefilter-key", key(p)))
+            a, b = ref.prefilter(p), dut.prefilter_key(*key(p))
+            assert norm_prefilter(a) == norm_prefilter(b), (seed, step, log[-5:], a, b)
+            if a["code"] == "Success" and rng.random() < 0.6:
+                assert ref.reserve(p)["code"] == dut.reserve_key(*key(p))["code"] == "Success"
+                if p not in reserved: reserved.append(p)
+        elif op < 0.5:
+            p = grow_pod(rng, rng.choice(nss), f"m{step}", False, stage); log.append(("prefilter-manifest", key(p)))
+            a, b = ref.prefilter(p), dut.prefilter(p)
+            assert norm_prefilter(a) == norm_prefilter(b), (seed, step, log[-5:], a, b)
+            if a["code"] == "Success" and rng.random() < 0.4:
+                assert ref.reserve(p)["code"] == dut.reserve(p)["code"]
+        elif op < 0.7:
+            p = grow_pod(rng, rng.choice(nss), f"n{step}", rng.random() < 0.6, stage); log.append(("new-pod", key(p)))
+            both(p)
+            if p["spec"]["nodeName"] == "" and p["status"]["phase"] == "Pending": queue.append(p)
+        elif op < 0.85:
+            i = rng.randrange(len(throttles) + 2); log.append(("apply-throttle", i))
+            t = grow_throttle(rng, i, nss, stage)
+            if i < len(throttles):
+                t["kind"] = throttles[i]["kind"]; t["metadata"] = throttles[i]["metadata"]
+                if t["kind"] == "Throttle":
+                    for term in t["spec"]["selector"]["selectorTerms"]: term.pop("namespaceSelector", None)
+                throttles[i] = t
+            else:
+                t["metadata"]["name"] += f"-s{step}"; throttles.append(t)
+            both(t)
+        elif op < 0.93 and reserved:
+            p = reserved.pop(rng.randrange(len(reserved))); log.append(("unreserve", key(p)))
+            ref.unreserve(p), dut.unreserve_key(*key(p))
+        else:
+            batch = rng.sample(queue, min(5, len(queue))); log.append(("admit-queue", len(batch)))
+            names = {p["metadata"]["name"] for p in reserved}
+            batch = [p for p in batch if p["metadata"]["name"] not in names]
+            want = []
+            for p in batch:
+                r = ref.prefilter(p)
+                if r["code"] == "Success": assert ref.reserve(p)["code"] == "Success"; reserved.append(p)
+                want.append((r["code"], r["reasons"]))
+            got = dut.admit_queue(batch)
+            assert [(x["preFilter"]["code"], x["preFilter"]["reasons"]) for x in got["results"]] == want, (seed, step, log[-5:])
+    for p in queue:
+        a, b = ref.prefilter(p), dut.prefilter_key(*key(p))
+        assert norm_prefilter(a) == norm_prefilter(b), (seed, "final", key(p), a, b)
+    for t in throttles:
+        k, nn = t["kind"], t["metadata"].get("namespace", "") + "/" + t["metadata"]["name"]
+        a, b = ref.reserved(k, nn), dut.reserved(k, nn)
+        assert sorted(a["pods"]) == sorted(b["pods"]) and norm_amount(a["amount"]) == norm_amount(b["amount"]), (seed, "reserved", nn, a, b)
+    st = dut.queue_stats()
+    dut.close()
+    return st
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_growth_event_stream(oracle, new_plugin, seed):
+    """A world that outgrows the engine's limits while it is in use: pods bring more and more labels (8 -> 16 -> 32 label slots)
+    and resource names (4 -> 8 -> 16 -> 31 columns) and finer quantities (a column is re-scaled) -- the host layer re-creates the
+    engine with larger limits and uploads its caches again, between PreFilter / Reserve by key and by manifest, reconciles, queue
+    admissions and throttle edits.  Nothing may be lost on the way: verdicts, statuses and reservations equal the oracle's."""
+    st = run_growth_stream(oracle, new_plugin, seed)
+    assert st["resourceColumns"] > 8, st
+
+
 def test_pods_of_a_namespace_the_lister_does_not_hold(oracle, new_plugin):
     """ClusterThrottleController.affectedPods walks the namespaces the lister returns (clusterthrottle_controller.go:227): pods of
     a namespace that was never seen, or was deleted, are not counted by ANY ClusterThrottle -- not even one whose namespaceSelector

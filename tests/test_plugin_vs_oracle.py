@@ -119,7 +119,8 @@ def norm_status(s):
 
 
 def norm_prefilter(r):
-    return {k: r.get(k) for k in ("code", "reasons", "event", "throttle", "clusterthrottle")}
+    # (an Error status carries its message and nothing else, plugin.go:154-156 / :166-168; the oracle's debug breakdown beside it is not compared)
+    return {k: r.get(k) for k in (("code", "reasons") if r.get("code") == "Error" else ("code", "reasons", "event", "throttle", "clusterthrottle"))}
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
@@ -792,7 +793,7 @@ def test_event_stream_chaos(oracle, new_plugin, seed):
     run_event_stream(oracle, new_plugin, seed)
 
 
-def run_queue_stream(oracle, new_plugin, seed, n_thr=10):
+def run_queue_stream(oracle, new_plugin, seed, n_thr=10, ns_deletes=False):
     """The RESIDENT scheduling queue under churn: the pending pods are delivered by the informer (they live in the device's
     pending table), PreFilter / Reserve / Unreserve address them by key, the whole queue is asked for in one call -- while
     throttles of both kinds are created, edited (new selector vocabulary: rows packed as 'some other value' are packed again),
@@ -863,8 +864,11 @@ def run_queue_stream(oracle, new_plugin, seed, n_thr=10):
             md = t["metadata"]
             ref.delete(t["kind"], md["name"], md.get("namespace", "")), dut.delete(t["kind"], md["name"], md.get("namespace", ""))
         elif op < 0.89:
-            n = rng.choice(nss); log.append(("relabel-ns", n))
-            both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
+            n = rng.choice(nss)
+            if ns_deletes and rng.random() < 0.4:  # (tools/chaos_host.py) the lister stops returning it; its pods and throttles stay: Error verdicts
+                log.append(("delete-ns", n)); ref.delete("Namespace", n), dut.delete("Namespace", n)
+            else:
+                log.append(("relabel-ns", n)); both(namespace(n, {"team": rng.choice(VALS), "env": rng.choice(VALS)}))
         elif op < 0.94 and len(queue) > 10:
             p = queue.pop(rng.randrange(len(queue))); log.append(("delete-queued", key(p)))
             if p in reserved: reserved.remove(p)

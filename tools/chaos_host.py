@@ -30,7 +30,7 @@ def main():
         import functools as ft
         for name, stream in (("events", ft.partial(T.run_event_stream, check_every_reconcile=True)), ("queue", T.run_queue_stream), ("statuses", T.run_status_stream), ("growth", T.run_growth_stream),
                              ("events, 80 throttles x 9 namespaces", ft.partial(T.run_event_stream, n_thr=80, n_ns=9, check_every_reconcile=True)),
-                             ("queue, 70 throttles", ft.partial(T.run_queue_stream, n_thr=70))):
+                             ("queue, 70 throttles, namespace deletes", ft.partial(T.run_queue_stream, n_thr=70, ns_deletes=True))):
             try:
                 stream(ko, ctor, seed)
             except AssertionError as e:
